@@ -1,0 +1,130 @@
+/* visocu.h -- the drop-in boundary: a thin extern "C" layer over the sm_100a CUDA kernels.
+ *
+ * It takes the place of the reference's device runtime (viso/opencl_wrapper.hh:19-166: Container / Buffer<T> /
+ * Kernel) and of the host loops that the reference runs on the CPU for this path.  POD arguments only, no
+ * C++/torch types, every function returns 0 on success or a negative VISOCU_E* code and never throws.
+ *
+ * One context = one GPU + one CUDA stream + a pool of device-resident "frames".  A frame holds everything the
+ * reference keeps per image in Matcher's ring buffer (matcher.h:232-241): the Sobel planes, the two feature
+ * record lists (sparse pass / dense pass) and their bin index.  Every entry point is batched: it takes arrays
+ * of frames / pairs and processes them with one launch per kernel, because a single 1241x376 frame is far too
+ * small to fill a B200 (hard part 3).
+ *
+ * Which reference interface each entry point replaces is cited next to it (paths relative to the reference).
+ */
+#ifndef VISOCU_H
+#define VISOCU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VISOCU_OK            0
+#define VISOCU_EINVAL       -1   /* bad argument (also: dims <= 0, bpl < width -- matcher.cpp:103-106) */
+#define VISOCU_ECUDA        -2   /* CUDA runtime error, text in visocu_last_error */
+#define VISOCU_ENODEVICE    -3   /* no sm_100 device: there is no CPU fallback */
+#define VISOCU_ECAPACITY    -4   /* an output list overflowed its buffer */
+#define VISOCU_ESTATE       -5   /* frame not computed yet / context not configured */
+
+typedef struct visocu_ctx visocu_ctx;
+
+/* Matcher::parameters, viso/matcher.h:42-69 -- same field order, same defaults (set by the C++ wrapper). */
+typedef struct {
+  int32_t nms_n, nms_tau, match_binsize, match_radius, match_disp_tolerance;
+  int32_t outlier_disp_tolerance, outlier_flow_tolerance, multi_stage, half_resolution, refinement;
+  double f, cu, cv, base;
+} visocu_params;
+
+/* Matcher::p_match, viso/matcher.h:86-100 (48 bytes). */
+typedef struct {
+  float u1p, v1p; int32_t i1p;
+  float u2p, v2p; int32_t i2p;
+  float u1c, v1c; int32_t i1c;
+  float u2c, v2c; int32_t i2c;
+} visocu_pmatch;
+
+/* Matcher::range, viso/matcher.h:152-157: search window per circle stage for one statistics bin. */
+typedef struct { float u_min[4], u_max[4], v_min[4], v_max[4]; } visocu_range;
+
+/* One matching job = the four ring-buffer entries of Matcher::matching (matcher.cpp:965); -1 = unused. */
+typedef struct { int32_t f1p, f2p, f1c, f2c; } visocu_quad;
+
+/* ---- runtime (replaces OpenCL::Container::init / getDevice, opencl_wrapper.cpp:66-128) ---- */
+int  visocu_create(int device, visocu_ctx** out);
+void visocu_destroy(visocu_ctx* ctx);
+const char* visocu_last_error(const visocu_ctx* ctx);          /* ctx may be NULL: last create() error */
+int  visocu_device_info(const visocu_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, char* name64);
+/* Allocates n_frames frame slots for width x height images.  `param.match_radius` is used as given (the C++
+ * Matcher halves it for half_resolution exactly like matcher.cpp:59-60 before calling).  Re-configurable. */
+int  visocu_configure(visocu_ctx* ctx, const visocu_params* param, int32_t width, int32_t height, int32_t n_frames);
+int  visocu_sync(visocu_ctx* ctx);
+/* CUDA-event timing on the context's stream (replaces Container::durationOfEvent, opencl_wrapper.cpp:157-164). */
+int  visocu_timer_start(visocu_ctx* ctx);
+int  visocu_timer_stop(visocu_ctx* ctx, float* ms);
+/* pinned host staging memory (optional, for callers that want truly asynchronous H2D) */
+int  visocu_host_alloc(visocu_ctx* ctx, size_t bytes, void** out);
+int  visocu_host_free(visocu_ctx* ctx, void* p);
+int  visocu_device_alloc(visocu_ctx* ctx, size_t bytes, void** out);
+int  visocu_device_free(visocu_ctx* ctx, void* p);
+int  visocu_memcpy_h2d(visocu_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+/* ---- feature front end: Matcher::pushBack -> computeFeatures (matcher.cpp:95-181, 649-732) ----
+ * imgs[k] is image k, `bpl_in` bytes per line, read only during the call.  If on_device != 0 the pointers are
+ * device pointers (inputs already resident in HBM).  For every frame: copy into the 16-byte-stride layout
+ * (matcher.cpp:158-175), [half image (630-647)], fused sobel5x5 / blob5x5 / checkerboard5x5 + both
+ * nonMaximumSuppression passes (filter.cpp:316-365, matcher.cpp:330-431, 684-694), computeDescriptors
+ * (433-477) and the bin index of createIndexVector (870-890).  n_sparse / n_dense (may be NULL) receive the
+ * record counts n?1 / n?2; the call synchronises only if they are requested. */
+int  visocu_push_frames(visocu_ctx* ctx, int32_t n, const int32_t* frames, const uint8_t* const* imgs,
+                        int32_t bpl_in, int32_t on_device, int32_t* n_sparse, int32_t* n_dense);
+int  visocu_frame_counts(visocu_ctx* ctx, int32_t n, const int32_t* frames, int32_t* n_sparse, int32_t* n_dense);
+/* the exported 12 x int32 records {u*s, v*s, 0, class, d1..d8} of matcher.cpp:707-731; pass 0 = sparse, 1 = dense */
+int  visocu_get_features(visocu_ctx* ctx, int32_t frame, int32_t pass, int32_t* out12, int32_t cap, int32_t* n_out);
+/* planes for parity checks / getGain: which = 0 du, 1 dv (matching resolution), 2 du_full, 3 dv_full,
+ * 4 padded input image, 5 half-resolution image.  dims3 = {w, h, bpl} of that plane. */
+int  visocu_get_plane(visocu_ctx* ctx, int32_t frame, int32_t which, uint8_t* out, size_t cap, int32_t* dims3);
+
+/* ---- filter:: functions (viso/filter.h:78-94), host buffers in and out, same argument order ---- */
+int  visocu_sobel5x5(visocu_ctx* ctx, const uint8_t* in, uint8_t* out_v, uint8_t* out_h, int32_t w, int32_t h);
+int  visocu_sobel3x3(visocu_ctx* ctx, const uint8_t* in, uint8_t* out_v, uint8_t* out_h, int32_t w, int32_t h);
+int  visocu_blob5x5(visocu_ctx* ctx, const uint8_t* in, int16_t* out, int32_t w, int32_t h);
+int  visocu_checkerboard5x5(visocu_ctx* ctx, const uint8_t* in, int16_t* out, int32_t w, int32_t h);
+/* Matcher::nonMaximumSuppression on caller-supplied response maps (matcher.cpp:330-431): out4 = (u,v,val,c) */
+int  visocu_nms(visocu_ctx* ctx, const int16_t* f1, const int16_t* f2, int32_t w, int32_t h, int32_t bpl,
+                int32_t nms_n, int32_t tau, int32_t* out4, int32_t cap, int32_t* n_out);
+
+/* ---- SAD circle matching: Matcher::matching + findMatch (+ pixel refinement) ----
+ * (matcher.cpp:965-1205, 892-963, 1456-1585).  method 0 = flow, 2 = quad.  pass 0 = sparse sets, 1 = dense.
+ * ranges[j] (host, u_bins*v_bins entries, matcher.cpp:734-868) is read only if use_prior.  refine != 0 applies
+ * relocateMinimum (refinement == 1 semantics) to the matches before they are returned.  out[j] receives at
+ * most cap[j] matches in the reference's order (ascending i1c for flow, ascending i1p for quad). */
+int  visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
+                  int32_t use_prior, const visocu_range* const* ranges, int32_t refine,
+                  visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out);
+/* pixel refinement alone on caller-supplied matches (Matcher::refinement with refinement == 1) */
+int  visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, visocu_pmatch* inout, int32_t n);
+/* work counters since the previous visocu_match_stats call: candidates that passed the window test (matcher.cpp:943) and
+ * bin entries scanned, summed over all jobs and hops -- the SAD roofline unit of SURVEY.md 8(d) */
+int  visocu_match_stats(visocu_ctx* ctx, uint64_t* sad_candidates, uint64_t* entries_scanned);
+
+/* ---- RANSAC: VisualOdometryMono::ransacEstimateF (viso_mono.cpp:41-72; virtual hook viso_mono.h:74) ----
+ * uv[j]: N[j] x 4 floats (u1p,v1p,u1c,v1c) already Hartley-normalised (viso_mono.cpp:217-263).
+ * samples[j]: iters x 8 indices drawn by the host with the reference's generator (viso.cpp:86-102).
+ * Per job: one warp per hypothesis does the 8-point fit (viso_mono.cpp:265-296), a batched pass scores all
+ * hypotheses (getInlier, 298-345, FP64 Sampson, |d| < thresh), the earliest hypothesis with the strictly
+ * largest count wins (56-57) and F is refitted on its inliers (61-69).  n_inliers < 10 => F9 = 0 (59-60).
+ * counts (iters, optional) and F_all (iters x 9, optional) expose per-hypothesis results for parity tests. */
+int  visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* const* uv, const int32_t* N,
+                     const int32_t* const* samples, int32_t iters, double thresh,
+                     double* F9, uint8_t* const* inlier_mask, int32_t* n_inliers, int32_t* best_iter,
+                     int32_t* const* counts, double* const* F_all);
+
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int  visocu_launch_count(const visocu_ctx* ctx, uint64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

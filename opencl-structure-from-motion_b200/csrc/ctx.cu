@@ -1,0 +1,339 @@
+// Context, frame pool and host<->device transport behind include/visocu.h.
+// Replaces the reference's OpenCL::Container / Buffer<T> runtime (viso/opencl_wrapper.hh:19-166,
+// viso/opencl_wrapper.cpp:66-164) with one CUDA stream per context and a pre-carved device pool.
+#include "visocu_internal.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+static thread_local std::string g_create_error;
+
+int visocu_set_error(visocu_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+extern "C" const char* visocu_last_error(const visocu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int visocu_create(int device, visocu_ctx** out) {
+  if (!out) return VISOCU_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return visocu_set_error(nullptr, VISOCU_ENODEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                            e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return visocu_set_error(nullptr, VISOCU_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return visocu_set_error(nullptr, VISOCU_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return visocu_set_error(nullptr, VISOCU_ENODEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+  visocu_ctx* ctx = new visocu_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount; ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
+  snprintf(ctx->name, sizeof ctx->name, "%s", prop.name);
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_stats, 2 * sizeof(uint64_t))) != cudaSuccess) {
+    visocu_set_error(nullptr, VISOCU_ECUDA, "context setup: %s", cudaGetErrorString(e));
+    delete ctx;
+    return VISOCU_ECUDA;
+  }
+  cudaMemset(ctx->d_stats, 0, 2 * sizeof(uint64_t));
+  *out = ctx;
+  return VISOCU_OK;
+}
+
+static void free_pool(visocu_ctx* ctx) {
+  if (ctx->pool) cudaFree(ctx->pool);
+  if (ctx->frames_d) cudaFree(ctx->frames_d);
+  ctx->pool = nullptr; ctx->frames_d = nullptr; ctx->configured = false;
+}
+
+extern "C" void visocu_destroy(visocu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_pool(ctx);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->d_stats) cudaFree(ctx->d_stats);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int visocu_device_info(const visocu_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, char* name64) {
+  if (!ctx) return VISOCU_EINVAL;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (name64) memcpy(name64, ctx->name, 64);
+  return VISOCU_OK;
+}
+
+int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return VISOCU_OK;
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  ctx->scratch = nullptr; ctx->scratch_bytes = 0;
+  size_t want = align_up(bytes + bytes / 4, 1 << 20);
+  CU_TRY(ctx, cudaMalloc(&ctx->scratch, want));
+  ctx->scratch_bytes = want;
+  return VISOCU_OK;
+}
+
+int visocu_ensure_pinned(visocu_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_bytes) return VISOCU_OK;
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr; ctx->pinned_bytes = 0;
+  size_t want = align_up(bytes + bytes / 4, 1 << 16);
+  CU_TRY(ctx, cudaMallocHost(&ctx->pinned, want));
+  ctx->pinned_bytes = want;
+  return VISOCU_OK;
+}
+
+// bytes per line rounded up to 16 (reference matcher.cpp:158-160)
+static int viso_bpl(int w) { return w + 15 - (w - 1) % 16; }
+
+extern "C" int visocu_configure(visocu_ctx* ctx, const visocu_params* p, int32_t width, int32_t height, int32_t n_frames) {
+  if (!ctx || !p) return VISOCU_EINVAL;
+  if (width <= 0 || height <= 0 || n_frames <= 0) return visocu_set_error(ctx, VISOCU_EINVAL, "bad dims %dx%d / %d frames", width, height, n_frames);
+  if (p->nms_n < 1 || p->nms_n > 14) return visocu_set_error(ctx, VISOCU_EINVAL, "nms_n=%d outside the supported range 1..14", p->nms_n);
+  if (p->match_binsize < 1) return visocu_set_error(ctx, VISOCU_EINVAL, "match_binsize must be positive");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  free_pool(ctx);
+  ctx->param = *p;
+  Geometry& g = ctx->g;
+  g.w = width; g.h = height; g.bpl = viso_bpl(width);
+  g.half = p->half_resolution ? 1 : 0;
+  g.scale = g.half ? 2 : 1;
+  if (g.half) { g.wm = width / 2; g.hm = height / 2; g.bplm = g.wm > 0 ? viso_bpl(g.wm) : 16; }   // matcher.cpp:630-634
+  else        { g.wm = width; g.hm = height; g.bplm = g.bpl; }
+  g.first_pass = p->multi_stage ? 0 : 1;
+  // sparse-pass neighbourhood (matcher.cpp:684-688)
+  int ns = p->nms_n * 3;
+  if (ns > 10) ns = p->nms_n > 10 ? p->nms_n : 10;
+  g.n[0] = ns; g.n[1] = p->nms_n;
+  g.tau = p->nms_tau;
+  for (int k = 0; k < 2; k++) {
+    g.ncx[k] = viso_cell_count(g.wm, g.n[k]);
+    g.ncy[k] = viso_cell_count(g.hm, g.n[k]);
+    g.cap[k] = 4 * g.ncx[k] * g.ncy[k] + 32;
+  }
+  g.binsize = p->match_binsize;
+  g.ub = (int)ceilf((float)width / (float)p->match_binsize);     // matcher.cpp:973-975 (full-resolution dims_c)
+  g.vb = (int)ceilf((float)height / (float)p->match_binsize);
+  g.nbins = 4 * g.ub * g.vb;
+  g.radius = p->match_radius; g.disp_tol = p->match_disp_tolerance;
+  if (g.ub > 4095 || g.vb > 4095 || width > 8191 * g.scale || height > 8191 * g.scale)
+    return visocu_set_error(ctx, VISOCU_EINVAL, "image or bin grid too large for the packed match keys");
+
+  // carve one pool
+  size_t plane_f = align_up((size_t)g.bpl * g.h + 64, 256), plane_m = align_up((size_t)g.bplm * g.hm + 64, 256);
+  size_t per = 0;
+  auto take = [&](size_t bytes) { size_t o = per; per += align_up(bytes, 256); return o; };
+  size_t o_img = take(plane_f), o_half = g.half ? take(plane_m) : 0, o_du = take(plane_m), o_dv = take(plane_m);
+  size_t o_duf = g.half ? take(plane_f) : 0, o_dvf = g.half ? take(plane_f) : 0;
+  size_t o_codes[2], o_blk[2], o_rec[2], o_bs[2], o_bc[2], o_be[2];
+  for (int k = 0; k < 2; k++) {
+    size_t cells = (size_t)g.ncx[k] * g.ncy[k];
+    o_codes[k] = take((cells + 1) * 4);
+    o_blk[k] = take((cells / 512 + 2) * 4);
+    o_rec[k] = take((size_t)g.cap[k] * 48);
+    o_bs[k] = take((size_t)(g.nbins + 1) * 4);
+    o_bc[k] = take((size_t)(g.nbins + 1) * 4);
+    o_be[k] = take((size_t)g.cap[k] * 8);
+  }
+  size_t o_cnt = take(64);
+  ctx->pool_bytes = per * (size_t)n_frames;
+  CU_TRY(ctx, cudaMalloc(&ctx->pool, ctx->pool_bytes));
+  CU_TRY(ctx, cudaMemsetAsync(ctx->pool, 0, ctx->pool_bytes, ctx->stream));
+  ctx->frames_h.assign(n_frames, FrameDev());
+  for (int f = 0; f < n_frames; f++) {
+    uint8_t* base = (uint8_t*)ctx->pool + per * (size_t)f;
+    FrameDev& F = ctx->frames_h[f];
+    F.img = base + o_img; F.half = g.half ? base + o_half : nullptr;
+    F.du = base + o_du; F.dv = base + o_dv;
+    F.du_full = g.half ? base + o_duf : nullptr; F.dv_full = g.half ? base + o_dvf : nullptr;
+    for (int k = 0; k < 2; k++) {
+      F.codes[k] = (uint32_t*)(base + o_codes[k]); F.blk[k] = (int32_t*)(base + o_blk[k]);
+      F.rec[k] = (int32_t*)(base + o_rec[k]); F.bin_start[k] = (int32_t*)(base + o_bs[k]);
+      F.bin_cursor[k] = (int32_t*)(base + o_bc[k]); F.bin_ent[k] = (int2*)(base + o_be[k]);
+    }
+    F.counts = (int32_t*)(base + o_cnt);
+  }
+  CU_TRY(ctx, cudaMalloc(&ctx->frames_d, sizeof(FrameDev) * (size_t)n_frames));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->frames_d, ctx->frames_h.data(), sizeof(FrameDev) * (size_t)n_frames, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->n_frames = n_frames;
+  ctx->h_counts.assign((size_t)n_frames * 2, 0);
+  ctx->frame_valid.assign(n_frames, 0);
+  ctx->configured = true;
+  return VISOCU_OK;
+}
+
+extern "C" int visocu_sync(visocu_ctx* ctx) {
+  if (!ctx) return VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return VISOCU_OK;
+}
+extern "C" int visocu_timer_start(visocu_ctx* ctx) {
+  if (!ctx) return VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return VISOCU_OK;
+}
+extern "C" int visocu_timer_stop(visocu_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CU_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+  CU_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return VISOCU_OK;
+}
+extern "C" int visocu_host_alloc(visocu_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaMallocHost(out, bytes));
+  return VISOCU_OK;
+}
+extern "C" int visocu_host_free(visocu_ctx* ctx, void* p) {
+  if (!ctx) return VISOCU_EINVAL;
+  CU_TRY(ctx, cudaFreeHost(p));
+  return VISOCU_OK;
+}
+extern "C" int visocu_device_alloc(visocu_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaMalloc(out, bytes));
+  return VISOCU_OK;
+}
+extern "C" int visocu_device_free(visocu_ctx* ctx, void* p) {
+  if (!ctx) return VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaFree(p));
+  return VISOCU_OK;
+}
+extern "C" int visocu_memcpy_h2d(visocu_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return VISOCU_OK;
+}
+extern "C" int visocu_launch_count(const visocu_ctx* ctx, uint64_t* n) {
+  if (!ctx || !n) return VISOCU_EINVAL;
+  *n = ctx->launches;
+  return VISOCU_OK;
+}
+
+static int check_frames(visocu_ctx* ctx, int32_t n, const int32_t* frames) {
+  if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
+  if (n <= 0 || !frames) return visocu_set_error(ctx, VISOCU_EINVAL, "empty frame list");
+  for (int i = 0; i < n; i++)
+    if (frames[i] < 0 || frames[i] >= ctx->n_frames) return visocu_set_error(ctx, VISOCU_EINVAL, "frame %d out of range", frames[i]);
+  return VISOCU_OK;
+}
+
+extern "C" int visocu_frame_counts(visocu_ctx* ctx, int32_t n, const int32_t* frames, int32_t* n_sparse, int32_t* n_dense) {
+  if (!ctx) return VISOCU_EINVAL;
+  int rc = check_frames(ctx, n, frames);
+  if (rc) return rc;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = visocu_ensure_pinned(ctx, (size_t)n * 16))) return rc;
+  int32_t* stage = (int32_t*)ctx->pinned;
+  for (int i = 0; i < n; i++)
+    CU_TRY(ctx, cudaMemcpyAsync(stage + 4 * i, ctx->frames_h[frames[i]].counts, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; i++) {
+    if (stage[4 * i + 2]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "feature list of frame %d overflowed", frames[i]);
+    ctx->h_counts[2 * (size_t)frames[i] + 0] = stage[4 * i + 0];
+    ctx->h_counts[2 * (size_t)frames[i] + 1] = stage[4 * i + 1];
+    if (n_sparse) n_sparse[i] = stage[4 * i + 0];
+    if (n_dense) n_dense[i] = stage[4 * i + 1];
+  }
+  return VISOCU_OK;
+}
+
+extern "C" int visocu_push_frames(visocu_ctx* ctx, int32_t n, const int32_t* frames, const uint8_t* const* imgs,
+                                  int32_t bpl_in, int32_t on_device, int32_t* n_sparse, int32_t* n_dense) {
+  if (!ctx) return VISOCU_EINVAL;
+  int rc = check_frames(ctx, n, frames);
+  if (rc) return rc;
+  if (!imgs) return visocu_set_error(ctx, VISOCU_EINVAL, "null image list");
+  const Geometry& g = ctx->g;
+  if (bpl_in < g.w) return visocu_set_error(ctx, VISOCU_EINVAL, "bytes per line %d < width %d", bpl_in, g.w);   // matcher.cpp:103
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int start = 0; start < n; start += VISO_MAX_BATCH) {
+    SlotList sl;
+    sl.n = n - start < VISO_MAX_BATCH ? n - start : VISO_MAX_BATCH;
+    for (int i = 0; i < sl.n; i++) {
+      int f = frames[start + i];
+      if (!imgs[start + i]) return visocu_set_error(ctx, VISOCU_EINVAL, "null image %d", start + i);
+      sl.s[i] = f;
+      // row-wise copy into the 16-byte stride (matcher.cpp:163-175); pad columns stay zero
+      CU_TRY(ctx, cudaMemcpy2DAsync(ctx->frames_h[f].img, g.bpl, imgs[start + i], bpl_in, g.w, g.h,
+                                    on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+      ctx->frame_valid[f] = 1;
+    }
+    if ((rc = visocu_launch_features(ctx, sl))) return rc;
+  }
+  // the host needs the record counts to size the matching launches: one small read-back per call
+  return visocu_frame_counts(ctx, n, frames, n_sparse, n_dense);
+}
+
+extern "C" int visocu_get_features(visocu_ctx* ctx, int32_t frame, int32_t pass, int32_t* out12, int32_t cap, int32_t* n_out) {
+  if (!ctx) return VISOCU_EINVAL;
+  int rc = check_frames(ctx, 1, &frame);
+  if (rc) return rc;
+  if (pass < 0 || pass > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "pass must be 0 or 1");
+  if (!ctx->frame_valid[frame]) return visocu_set_error(ctx, VISOCU_ESTATE, "frame %d holds no features", frame);
+  int32_t n = ctx->h_counts[2 * (size_t)frame + pass];
+  if (n_out) *n_out = n;
+  if (!out12) return VISOCU_OK;
+  if (cap < n) return visocu_set_error(ctx, VISOCU_ECAPACITY, "need room for %d records", n);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n > 0) CU_TRY(ctx, cudaMemcpyAsync(out12, ctx->frames_h[frame].rec[pass], (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return VISOCU_OK;
+}
+
+extern "C" int visocu_get_plane(visocu_ctx* ctx, int32_t frame, int32_t which, uint8_t* out, size_t cap, int32_t* dims3) {
+  if (!ctx) return VISOCU_EINVAL;
+  int rc = check_frames(ctx, 1, &frame);
+  if (rc) return rc;
+  const Geometry& g = ctx->g;
+  const FrameDev& F = ctx->frames_h[frame];
+  const uint8_t* src = nullptr;
+  int w = g.wm, h = g.hm, bpl = g.bplm;
+  switch (which) {
+    case 0: src = F.du; break;
+    case 1: src = F.dv; break;
+    case 2: src = F.du_full; w = g.w; h = g.h; bpl = g.bpl; break;
+    case 3: src = F.dv_full; w = g.w; h = g.h; bpl = g.bpl; break;
+    case 4: src = F.img; w = g.w; h = g.h; bpl = g.bpl; break;
+    case 5: src = F.half; break;
+    default: return visocu_set_error(ctx, VISOCU_EINVAL, "unknown plane %d", which);
+  }
+  if (!src) return visocu_set_error(ctx, VISOCU_ESTATE, "plane %d does not exist in this configuration", which);
+  if (dims3) { dims3[0] = w; dims3[1] = h; dims3[2] = bpl; }
+  if (!out) return VISOCU_OK;
+  size_t bytes = (size_t)bpl * h;
+  if (cap < bytes) return visocu_set_error(ctx, VISOCU_ECAPACITY, "plane needs %zu bytes", bytes);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return VISOCU_OK;
+}

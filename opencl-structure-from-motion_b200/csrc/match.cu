@@ -1,0 +1,409 @@
+// SAD circle matching and pixel refinement.
+//
+// What it reproduces (reference paths relative to /root/reference/viso):
+//   Matcher::findMatch ................. matcher.cpp:892-963   (32-byte SAD, simd.hh:426-432)
+//   Matcher::matching, method 0 and 2 .. matcher.cpp:965-1041, 1088-1153
+//   Matcher::relocateMinimum ........... matcher.cpp:1456-1496 (+ computeSmallDescriptor 479-506)
+//   Matcher::refinement (pixel mode) ... matcher.cpp:1498-1585
+//
+// Design: the reference walks candidate bins in a fixed order and keeps the first minimum.  Here a group of
+// 8 lanes scans the candidates of one query in parallel and reduces complete keys
+//   (SAD cost, candidate u_bin, candidate v_bin, candidate index)
+// whose minimum is exactly the candidate the reference's sequential loop would have kept, so the bin lists
+// need no internal order.  All hops of a circle run inside one kernel because each hop's query is the previous
+// hop's answer.  Accepted circles are compacted in ascending query order with a two-kernel scan; the flow
+// "pixel already matched" rule (matcher.cpp:1036-1039) only ever involves the up-to-three preceding records
+// because two features share a pixel only when they come from the same NMS cell.
+#include "visocu_internal.cuh"
+#include <cstring>
+
+namespace {
+
+constexpr int G = 8;                 // lanes per query
+constexpr int MATCH_THREADS = 256;   // 32 queries per block
+constexpr int CHUNK = 1024;          // queries per compaction block
+
+struct SetDev { const int32_t* rec; const int32_t* bin_start; const int2* bin_ent; int n; int pad; };
+struct MatchJob {
+  SetDev s[4];                       // 0 = 1p, 1 = 2p, 2 = 1c, 3 = 2c
+  const visocu_range* ranges;
+  int4* res;                         // per query: the other three indices of the circle + accepted flag
+  int32_t* blk;                      // accepted circles per CHUNK
+  visocu_pmatch* out;
+  int32_t* n_out;
+  const uint8_t* du[4];              // planes used by the refinement (full resolution)
+  const uint8_t* dv[4];
+  int nq, pad;
+};
+
+__device__ __forceinline__ int bin_index(const Geometry& g, int u, int v) {
+  const float bs = (float)g.binsize;
+  int ub = min((int)floorf((float)u / bs), g.ub - 1);
+  int vb = min((int)floorf((float)v / bs), g.vb - 1);
+  return vb * g.ub + ub;
+}
+
+// one hop: best candidate in set B for feature i1 of set A (all G lanes of the group call this together)
+__device__ __forceinline__ int find_match(const Geometry& g, const SetDev& A, int i1, const SetDev& B, int stat_bin, int stage,
+                                          bool flow, bool use_prior, const visocu_range* __restrict__ ranges, bool active, int sub,
+                                          unsigned& n_cand, unsigned& n_scan) {
+  unsigned long long best = ~0ull;
+  if (active) {
+    const int32_t* q = A.rec + (size_t)i1 * 12;
+    const int4 hdr = *(const int4*)q;
+    const uint4 qa = *(const uint4*)(q + 4), qb = *(const uint4*)(q + 8);
+    const int u1 = hdr.x, v1 = hdr.y, c = hdr.w;
+    float u_min, u_max, v_min, v_max;
+    if (use_prior) {
+      const visocu_range* r = ranges + stat_bin;
+      u_min = (float)u1 + r->u_min[stage]; u_max = (float)u1 + r->u_max[stage];
+      v_min = (float)v1 + r->v_min[stage]; v_max = (float)v1 + r->v_max[stage];
+    } else {
+      u_min = (float)(u1 - g.radius); u_max = (float)(u1 + g.radius);
+      v_min = (float)(v1 - g.radius); v_max = (float)(v1 + g.radius);
+    }
+    if (!flow) { v_min = (float)(v1 - g.disp_tol); v_max = (float)(v1 + g.disp_tol); }
+    const float bs = (float)g.binsize;
+    const int ubmin = min(max((int)floorf(u_min / bs), 0), g.ub - 1), ubmax = min(max((int)floorf(u_max / bs), 0), g.ub - 1);
+    const int vbmin = min(max((int)floorf(v_min / bs), 0), g.vb - 1), vbmax = min(max((int)floorf(v_max / bs), 0), g.vb - 1);
+    for (int vbin = vbmin; vbin <= vbmax; vbin++) {
+      const int row = (c * g.vb + vbin) * g.ub;
+      const int e0 = B.bin_start[row + ubmin], e1 = ubmax >= ubmin ? B.bin_start[row + ubmax + 1] : e0;
+      for (int e = e0 + sub; e < e1; e += G) {
+        const int2 ent = B.bin_ent[e];
+        const int u2 = ent.x & 0xFFFF, v2 = (int)((unsigned)ent.x >> 16);
+        n_scan++;
+        if ((float)u2 >= u_min && (float)u2 <= u_max && (float)v2 >= v_min && (float)v2 <= v_max) {
+          const int32_t* t = B.rec + (size_t)ent.y * 12;
+          const uint4 ta = *(const uint4*)(t + 4), tb = *(const uint4*)(t + 8);
+          unsigned sad = __vsadu4(qa.x, ta.x) + __vsadu4(qa.y, ta.y) + __vsadu4(qa.z, ta.z) + __vsadu4(qa.w, ta.w) +
+                         __vsadu4(qb.x, tb.x) + __vsadu4(qb.y, tb.y) + __vsadu4(qb.z, tb.z) + __vsadu4(qb.w, tb.w);
+          const int ub2 = min((int)floorf((float)u2 / bs), g.ub - 1);
+          unsigned long long key = ((unsigned long long)sad << 48) | ((unsigned long long)ub2 << 36) |
+                                   ((unsigned long long)vbin << 24) | (unsigned long long)ent.y;
+          best = key < best ? key : best;
+          n_cand++;
+        }
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int o = G / 2; o; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+    best = other < best ? other : best;
+  }
+  return best == ~0ull ? 0 : (int)(best & 0xFFFFFFull);    // min_ind defaults to 0 (matcher.cpp:898)
+}
+
+__global__ void __launch_bounds__(MATCH_THREADS) k_match(Geometry g, const MatchJob* jobs, int method, int use_prior, uint64_t* stats) {
+  const MatchJob& J = jobs[blockIdx.y];
+  const int sub = threadIdx.x % G;
+  const int i = blockIdx.x * (MATCH_THREADS / G) + threadIdx.x / G;
+  const bool active = i < J.nq;
+  unsigned n_cand = 0, n_scan = 0;
+  int4 res = make_int4(0, 0, 0, 0);
+  if (method == 0) {
+    int stat_bin = 0;
+    if (active) { const int2 uv = *(const int2*)(J.s[2].rec + (size_t)i * 12); stat_bin = bin_index(g, uv.x, uv.y); }
+    const int i1p = find_match(g, J.s[2], i, J.s[0], stat_bin, 0, true, use_prior, J.ranges, active, sub, n_cand, n_scan);
+    const int i1c2 = find_match(g, J.s[0], i1p, J.s[2], stat_bin, 1, true, use_prior, J.ranges, active, sub, n_cand, n_scan);
+    res = make_int4(i1p, 0, 0, i1c2 == i);
+  } else {
+    int stat_bin = 0;
+    if (active) { const int2 uv = *(const int2*)(J.s[0].rec + (size_t)i * 12); stat_bin = bin_index(g, uv.x, uv.y); }
+    const int i2p = find_match(g, J.s[0], i, J.s[1], stat_bin, 0, false, use_prior, J.ranges, active, sub, n_cand, n_scan);
+    const int i2c = find_match(g, J.s[1], i2p, J.s[3], stat_bin, 1, true, use_prior, J.ranges, active, sub, n_cand, n_scan);
+    const int i1c = find_match(g, J.s[3], i2c, J.s[2], stat_bin, 2, false, use_prior, J.ranges, active, sub, n_cand, n_scan);
+    const int i1p2 = find_match(g, J.s[2], i1c, J.s[0], stat_bin, 3, true, use_prior, J.ranges, active, sub, n_cand, n_scan);
+    int ok = 0;
+    if (active && i1p2 == i) {
+      const int u1p = J.s[0].rec[(size_t)i * 12], u2p = J.s[1].rec[(size_t)i2p * 12];
+      const int u1c = J.s[2].rec[(size_t)i1c * 12], u2c = J.s[3].rec[(size_t)i2c * 12];
+      ok = (u1p >= u2p && u1c >= u2c);
+    }
+    res = make_int4(i2p, i2c, i1c, ok);
+  }
+  if (active && sub == 0) J.res[i] = res;
+  // work counters: one atomic per warp
+  for (int o = 16; o; o >>= 1) { n_cand += __shfl_xor_sync(0xFFFFFFFFu, n_cand, o); n_scan += __shfl_xor_sync(0xFFFFFFFFu, n_scan, o); }
+  if ((threadIdx.x & 31) == 0 && (n_cand | n_scan)) {
+    atomicAdd((unsigned long long*)&stats[0], (unsigned long long)n_cand);
+    atomicAdd((unsigned long long*)&stats[1], (unsigned long long)n_scan);
+  }
+}
+
+// accepted-and-kept flag of query i (identical in the count and the emit kernel)
+__device__ __forceinline__ int keep_flag(const MatchJob& J, int method, int i) {
+  if (i >= J.nq) return 0;
+  if (!J.res[i].w) return 0;
+  if (method != 0) return 1;
+  const int2 uv = *(const int2*)(J.s[2].rec + (size_t)i * 12);
+  for (int j = i - 1; j >= 0 && j >= i - 3; j--) {
+    if (!J.res[j].w) continue;
+    const int2 o = *(const int2*)(J.s[2].rec + (size_t)j * 12);
+    if (o.x == uv.x && o.y == uv.y) return 0;      // an earlier accepted circle already owns this pixel
+  }
+  return 1;
+}
+
+__global__ void __launch_bounds__(CHUNK) k_match_count(const MatchJob* jobs, int method) {
+  const MatchJob& J = jobs[blockIdx.y];
+  if ((int)blockIdx.x * CHUNK >= J.nq && blockIdx.x > 0) return;
+  int f = keep_flag(J, method, blockIdx.x * CHUNK + threadIdx.x);
+  __shared__ int wsum[32];
+  for (int o = 16; o; o >>= 1) f += __shfl_xor_sync(0xFFFFFFFFu, f, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = f;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = wsum[threadIdx.x];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (threadIdx.x == 0) J.blk[blockIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(CHUNK) k_match_emit(const MatchJob* jobs, int method) {
+  const MatchJob& J = jobs[blockIdx.y];
+  const int nchunk = (J.nq + CHUNK - 1) / CHUNK;
+  if ((int)blockIdx.x >= nchunk) {
+    if (nchunk == 0 && blockIdx.x == 0 && threadIdx.x == 0) *J.n_out = 0;
+    return;
+  }
+  __shared__ int wsum[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int acc = 0;
+  for (int b = tid; b < (int)blockIdx.x; b += CHUNK) acc += J.blk[b];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+  if (lane == 0) wsum[wid] = acc;
+  __syncthreads();
+  if (tid < 32) {
+    int v = wsum[tid];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (tid == 0) s_base = v;
+  }
+  __syncthreads();
+  const int base = s_base;
+  __syncthreads();
+  const int i = blockIdx.x * CHUNK + tid;
+  const int f = keep_flag(J, method, i);
+  int incl = f;
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int v = wsum[tid], s = v;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, s, o); if (lane >= o) s += t; }
+    wsum[tid] = s - v;
+    if (tid == 31 && (int)blockIdx.x == nchunk - 1) *J.n_out = base + s;
+  }
+  __syncthreads();
+  if (!f) return;
+  const int pos = base + wsum[wid] + incl - 1;
+  const int4 r = J.res[i];
+  visocu_pmatch m;
+  if (method == 0) {
+    const int2 c = *(const int2*)(J.s[2].rec + (size_t)i * 12);
+    const int2 p = *(const int2*)(J.s[0].rec + (size_t)r.x * 12);
+    m.u1p = (float)p.x; m.v1p = (float)p.y; m.i1p = r.x;
+    m.u2p = -1.f; m.v2p = -1.f; m.i2p = -1;
+    m.u1c = (float)c.x; m.v1c = (float)c.y; m.i1c = i;
+    m.u2c = -1.f; m.v2c = -1.f; m.i2c = -1;
+  } else {
+    const int2 a = *(const int2*)(J.s[0].rec + (size_t)i * 12);
+    const int2 b = *(const int2*)(J.s[1].rec + (size_t)r.x * 12);
+    const int2 d = *(const int2*)(J.s[3].rec + (size_t)r.y * 12);
+    const int2 c = *(const int2*)(J.s[2].rec + (size_t)r.z * 12);
+    m.u1p = (float)a.x; m.v1p = (float)a.y; m.i1p = i;
+    m.u2p = (float)b.x; m.v2p = (float)b.y; m.i2p = r.x;
+    m.u1c = (float)c.x; m.v1c = (float)c.y; m.i1c = r.z;
+    m.u2c = (float)d.x; m.v2c = (float)d.y; m.i2c = r.y;
+  }
+  J.out[pos] = m;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pixel refinement.  16-byte descriptor of computeSmallDescriptor (matcher.cpp:479-506): (plane, dx, dy)
+__constant__ int8_t c_sd_plane[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1};
+__constant__ int8_t c_sd_dx[16] = {0, -2, 0, 2, -1, 0, 0, 1, -2, 0, 2, 0, 0, -1, 1, 0};
+__constant__ int8_t c_sd_dy[16] = {-2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2, -1, 0, 0, 1};
+
+// one warp relocates (u2,v2) in image 2 to the best of the 5x5 positions around it; lane = candidate
+__device__ __forceinline__ void relocate(const uint8_t* du1, const uint8_t* dv1, const uint8_t* du2, const uint8_t* dv2,
+                                         int bpl, int w, int h, float u1, float v1, float& u2, float& v2, int lane) {
+  if (u2 - 2 < VISO_MARGIN || u2 + 2 > w - 1 - VISO_MARGIN || v2 - 2 < VISO_MARGIN || v2 + 2 > h - 1 - VISO_MARGIN) return;
+  const int iu1 = (int)u1, iv1 = (int)v1;
+  int key = 0x7FFFFFFF;
+  if (lane < 25) {
+    const int cu = (int)u2 + lane % 5 - 2, cv = (int)v2 + lane / 5 - 2;
+    int sad = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int dx = c_sd_dx[k], dy = c_sd_dy[k];
+      const uint8_t* p1 = c_sd_plane[k] ? dv1 : du1;
+      const uint8_t* p2 = c_sd_plane[k] ? dv2 : du2;
+      int a = p1[(size_t)(iv1 + dy) * bpl + iu1 + dx], b = p2[(size_t)(cv + dy) * bpl + cu + dx];
+      sad += abs(a - b);
+    }
+    key = sad * 32 + lane;
+  }
+  key = __reduce_min_sync(0xFFFFFFFFu, key);
+  const int best = key & 31;
+  u2 += (float)(best % 5) - 2.0f;
+  v2 += (float)(best / 5) - 2.0f;
+}
+
+__global__ void __launch_bounds__(256) k_refine(Geometry g, const MatchJob* jobs, int method, visocu_pmatch* direct, int n_direct) {
+  const MatchJob& J = jobs[blockIdx.y];
+  const int n = direct ? n_direct : *J.n_out;
+  visocu_pmatch* list = direct ? direct : J.out;
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    visocu_pmatch m = list[i];
+    // reference descriptor always at (u1c,v1c) of the current left image (matcher.cpp:1544-1577)
+    relocate(J.du[2], J.dv[2], J.du[0], J.dv[0], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u1p, m.v1p, lane);
+    if (method == 2) {
+      relocate(J.du[2], J.dv[2], J.du[3], J.dv[3], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u2c, m.v2c, lane);
+      relocate(J.du[2], J.dv[2], J.du[1], J.dv[1], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u2p, m.v2p, lane);
+    }
+    if (lane == 0) list[i] = m;
+  }
+}
+
+int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJob& J) {
+  const int ids[4] = {q.f1p, q.f2p, q.f1c, q.f2c};
+  const bool need[4] = {true, method == 2, true, method == 2};
+  memset(&J, 0, sizeof J);
+  for (int k = 0; k < 4; k++) {
+    if (!need[k]) continue;
+    int f = ids[k];
+    if (f < 0 || f >= ctx->n_frames) return visocu_set_error(ctx, VISOCU_EINVAL, "match job references frame %d", f);
+    if (!ctx->frame_valid[f]) return visocu_set_error(ctx, VISOCU_ESTATE, "frame %d holds no features", f);
+    const FrameDev& F = ctx->frames_h[f];
+    J.s[k].rec = F.rec[pass]; J.s[k].bin_start = F.bin_start[pass]; J.s[k].bin_ent = F.bin_ent[pass];
+    J.s[k].n = ctx->h_counts[2 * (size_t)f + pass];
+    J.du[k] = ctx->g.half ? F.du_full : F.du;
+    J.dv[k] = ctx->g.half ? F.dv_full : F.dv;
+  }
+  return VISOCU_OK;
+}
+
+}  // namespace
+
+extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
+                            int32_t use_prior, const visocu_range* const* ranges, int32_t refine,
+                            visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out) {
+  if (!ctx) return VISOCU_EINVAL;
+  if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
+  if (n_jobs <= 0 || !jobs || !out || !cap || !n_out) return visocu_set_error(ctx, VISOCU_EINVAL, "bad match arguments");
+  if (method != 0 && method != 2) return visocu_set_error(ctx, VISOCU_EINVAL, "method %d not supported (0 = flow, 2 = quad)", method);
+  if (pass < ctx->g.first_pass || pass > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "pass %d not available", pass);
+  if (use_prior && !ranges) return visocu_set_error(ctx, VISOCU_EINVAL, "use_prior needs ranges");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const Geometry& g = ctx->g;
+  const int nstat = g.ub * g.vb;
+  for (int start = 0; start < n_jobs; start += VISO_MAX_BATCH) {
+    const int nb = n_jobs - start < VISO_MAX_BATCH ? n_jobs - start : VISO_MAX_BATCH;
+    std::vector<MatchJob> hj(nb);
+    size_t off = align_up(sizeof(MatchJob) * nb, 256);
+    int maxq = 0;
+    std::vector<size_t> o_res(nb), o_blk(nb), o_out(nb), o_cnt(nb), o_rng(nb);
+    for (int j = 0; j < nb; j++) {
+      int rc = fill_job(ctx, jobs[start + j], method, pass, hj[j]);
+      if (rc) return rc;
+      bool empty = false;
+      for (int k = 0; k < 4; k++) if ((k == 0 || k == 2 || method == 2) && hj[j].s[k].n == 0) empty = true;
+      const int nq = empty ? 0 : (method == 0 ? hj[j].s[2].n : hj[j].s[0].n);
+      hj[j].nq = nq;
+      if (nq > maxq) maxq = nq;
+      o_res[j] = off; off += align_up((size_t)(nq + 1) * 16, 256);
+      o_blk[j] = off; off += align_up((size_t)(nq / CHUNK + 2) * 4, 256);
+      o_out[j] = off; off += align_up((size_t)(nq + 1) * 48, 256);
+      o_cnt[j] = off; off += 256;
+      o_rng[j] = off; off += use_prior ? align_up((size_t)nstat * sizeof(visocu_range), 256) : 0;
+    }
+    int rc = visocu_ensure_scratch(ctx, off);
+    if (rc) return rc;
+    size_t stage_bytes = align_up(sizeof(MatchJob) * nb, 256) + (use_prior ? (size_t)nb * align_up((size_t)nstat * sizeof(visocu_range), 256) : 0) + (size_t)nb * 4;
+    if ((rc = visocu_ensure_pinned(ctx, stage_bytes))) return rc;
+    uint8_t* sb = (uint8_t*)ctx->scratch;
+    uint8_t* pin = (uint8_t*)ctx->pinned;
+    size_t pin_off = align_up(sizeof(MatchJob) * nb, 256);
+    for (int j = 0; j < nb; j++) {
+      hj[j].res = (int4*)(sb + o_res[j]); hj[j].blk = (int32_t*)(sb + o_blk[j]);
+      hj[j].out = (visocu_pmatch*)(sb + o_out[j]); hj[j].n_out = (int32_t*)(sb + o_cnt[j]);
+      if (use_prior) {
+        if (!ranges[start + j]) return visocu_set_error(ctx, VISOCU_EINVAL, "job %d has no ranges", start + j);
+        memcpy(pin + pin_off, ranges[start + j], (size_t)nstat * sizeof(visocu_range));
+        CU_TRY(ctx, cudaMemcpyAsync(sb + o_rng[j], pin + pin_off, (size_t)nstat * sizeof(visocu_range), cudaMemcpyHostToDevice, ctx->stream));
+        pin_off += align_up((size_t)nstat * sizeof(visocu_range), 256);
+        hj[j].ranges = (const visocu_range*)(sb + o_rng[j]);
+      }
+    }
+    memcpy(pin, hj.data(), sizeof(MatchJob) * nb);
+    CU_TRY(ctx, cudaMemcpyAsync(sb, pin, sizeof(MatchJob) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    const MatchJob* dj = (const MatchJob*)sb;
+    int32_t* pin_cnt = (int32_t*)(pin + pin_off);
+    if (maxq > 0) {
+      dim3 gm((maxq + MATCH_THREADS / G - 1) / (MATCH_THREADS / G), nb);
+      k_match<<<gm, MATCH_THREADS, 0, ctx->stream>>>(g, dj, method, use_prior, ctx->d_stats);
+      CU_LAUNCH_CHECK(ctx);
+    }
+    dim3 gc((maxq + CHUNK - 1) / CHUNK > 0 ? (maxq + CHUNK - 1) / CHUNK : 1, nb);
+    k_match_count<<<gc, CHUNK, 0, ctx->stream>>>(dj, method);
+    CU_LAUNCH_CHECK(ctx);
+    k_match_emit<<<gc, CHUNK, 0, ctx->stream>>>(dj, method);
+    CU_LAUNCH_CHECK(ctx);
+    if (refine && maxq > 0) {
+      int gx = (maxq + 7) / 8; if (gx > 4096) gx = 4096;
+      dim3 gr(gx, nb);
+      k_refine<<<gr, 256, 0, ctx->stream>>>(g, dj, method, nullptr, 0);
+      CU_LAUNCH_CHECK(ctx);
+    }
+    for (int j = 0; j < nb; j++) CU_TRY(ctx, cudaMemcpyAsync(pin_cnt + j, hj[j].n_out, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int j = 0; j < nb; j++) {
+      const int n = pin_cnt[j];
+      n_out[start + j] = n;
+      if (n > cap[start + j]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "job %d produced %d matches, room for %d", start + j, n, cap[start + j]);
+      if (n > 0) CU_TRY(ctx, cudaMemcpyAsync(out[start + j], hj[j].out, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return VISOCU_OK;
+}
+
+extern "C" int visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, visocu_pmatch* inout, int32_t n) {
+  if (!ctx || !job || (!inout && n > 0)) return VISOCU_EINVAL;
+  if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
+  if (method != 0 && method != 2) return visocu_set_error(ctx, VISOCU_EINVAL, "method %d not supported", method);
+  if (n <= 0) return VISOCU_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  MatchJob J;
+  int rc = fill_job(ctx, *job, method, 1, J);
+  if (rc) return rc;
+  size_t o_list = align_up(sizeof(MatchJob), 256);
+  if ((rc = visocu_ensure_scratch(ctx, o_list + (size_t)n * 48))) return rc;
+  uint8_t* sb = (uint8_t*)ctx->scratch;
+  visocu_pmatch* d_list = (visocu_pmatch*)(sb + o_list);
+  CU_TRY(ctx, cudaMemcpyAsync(sb, &J, sizeof J, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, cudaMemcpyAsync(d_list, inout, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
+  int gx = (n + 7) / 8; if (gx > 4096) gx = 4096;
+  k_refine<<<dim3(gx, 1), 256, 0, ctx->stream>>>(ctx->g, (const MatchJob*)sb, method, d_list, n);
+  CU_LAUNCH_CHECK(ctx);
+  CU_TRY(ctx, cudaMemcpyAsync(inout, d_list, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return VISOCU_OK;
+}
+
+extern "C" int visocu_match_stats(visocu_ctx* ctx, uint64_t* sad_candidates, uint64_t* entries_scanned) {
+  if (!ctx) return VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  uint64_t now[2];
+  CU_TRY(ctx, cudaMemcpyAsync(now, ctx->d_stats, sizeof now, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (sad_candidates) *sad_candidates = now[0] - ctx->h_stats[0];
+  if (entries_scanned) *entries_scanned = now[1] - ctx->h_stats[1];
+  ctx->h_stats[0] = now[0]; ctx->h_stats[1] = now[1];
+  return VISOCU_OK;
+}

@@ -1,0 +1,90 @@
+// Internal declarations shared by the CUDA translation units behind include/visocu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "visocu.h"
+
+#define VISO_MARGIN 6            // Matcher::margin, reference matcher.cpp:56
+#define VISO_MAX_BATCH 128       // frames / jobs per launch (larger batches are split by the host code)
+
+// Device pointers of one frame slot (everything Matcher keeps per image in its ring buffer, matcher.h:232-241).
+struct FrameDev {
+  uint8_t *img, *half, *du, *dv, *du_full, *dv_full;
+  uint32_t* codes[2];      // per NMS cell: 4 bytes (one per class) = (di<<4|dj) of the kept extremum or 0xFF
+  int32_t*  blk[2];        // per 512-cell chunk: number of records it emits (ordered compaction)
+  int32_t*  rec[2];        // 12 x int32 records, pass 0 = sparse, 1 = dense
+  int32_t*  bin_start[2];  // 4*ub*vb + 1 offsets into bin_ent
+  int32_t*  bin_cursor[2]; // scratch for the scatter
+  int2*     bin_ent[2];    // (u | v<<16, feature index), grouped by bin
+  int32_t*  counts;        // [0..1] record counts, [2] overflow flag
+};
+
+struct Geometry {
+  int w, h, bpl;           // full resolution, bpl = 16-byte stride (matcher.cpp:158-160)
+  int wm, hm, bplm;        // matching resolution (== full unless half_resolution, matcher.cpp:630-634)
+  int half, scale;
+  int first_pass;          // 0 if multi_stage (sparse + dense) else 1 (dense only)
+  int n[2], ncx[2], ncy[2], cap[2];
+  int tau;
+  int binsize, ub, vb, nbins;
+  int radius, disp_tol;
+};
+
+struct SlotList { int n; int s[VISO_MAX_BATCH]; };
+
+struct visocu_ctx {
+  int device = 0;
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  char name[64] = {0};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  bool configured = false;
+  visocu_params param{};
+  Geometry g{};
+  int n_frames = 0;
+  void* pool = nullptr;
+  size_t pool_bytes = 0;
+  std::vector<FrameDev> frames_h;
+  FrameDev* frames_d = nullptr;
+  std::vector<int32_t> h_counts;     // 2 per frame, host mirror (valid after a push that synchronised)
+  std::vector<uint8_t> frame_valid;
+  // scratch for matching / ransac, grown on demand
+  void* scratch = nullptr; size_t scratch_bytes = 0;
+  void* pinned = nullptr;  size_t pinned_bytes = 0;
+  uint64_t launches = 0;
+  size_t filter_smem_attr = 0;       // dynamic shared memory opted in for the fused kernel on this device
+  uint64_t* d_stats = nullptr;       // [0] SAD candidates, [1] entries scanned
+  uint64_t h_stats[2] = {0, 0};
+};
+
+int visocu_set_error(visocu_ctx* ctx, int code, const char* fmt, ...);
+int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes);
+int visocu_ensure_pinned(visocu_ctx* ctx, size_t bytes);
+
+#define CU_TRY(ctx, expr)                                                                        \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return visocu_set_error((ctx), VISOCU_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, \
+                              cudaGetErrorString(e__));                                          \
+  } while (0)
+
+#define CU_LAUNCH_CHECK(ctx)                  \
+  do {                                        \
+    (ctx)->launches++;                        \
+    CU_TRY((ctx), cudaGetLastError());        \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// cells of Matcher::nonMaximumSuppression along one axis: origins n+margin+k(n+1) < len-n-margin (matcher.cpp:344-345)
+__host__ __device__ static inline int viso_cell_count(int len, int n) {
+  int s = len - 2 * n - 2 * VISO_MARGIN;
+  return s > 0 ? (s + n) / (n + 1) : 0;
+}
+
+// launchers implemented in the kernel translation units
+int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl);

@@ -1,0 +1,209 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI of include/visocu.h, against the unmodified
+reference CPU path (oracle/_ref, prebuilt; the checker only) on identical synthetic inputs.
+Integer stages are compared bit-exactly, list order included (SURVEY.md 8d checkpoints P1-P6, P8)."""
+import numpy as np
+import pytest
+
+import synth
+import pyref
+import visocu_py as V
+
+pytestmark = pytest.mark.gpu
+
+
+def params_pair(**kw):
+    """(reference params, C-ABI params): the Matcher constructor halves match_radius at half resolution
+    (matcher.cpp:59-60); the C-ABI takes the effective value."""
+    rp = pyref.MatcherParams(**kw)
+    vp = V.Params(**kw)
+    if vp.half_resolution:
+        vp.match_radius = vp.match_radius // 2
+    return rp, vp
+
+
+def valid(plane, w):
+    return plane[2:-2, 2:w - 2]
+
+
+CASES = [
+    dict(width=1241, height=376, half_resolution=1),
+    dict(width=1241, height=376, half_resolution=0),
+    dict(width=1241, height=376, half_resolution=0, nms_n=4),      # flow demo setting: sparse n = 10
+    dict(width=337, height=211, half_resolution=0, nms_n=2),       # quad demo setting, ragged size
+    dict(width=640, height=480, half_resolution=1, nms_n=5, nms_tau=30),
+    dict(width=130, height=70, half_resolution=0, multi_stage=0),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: '-'.join('%s%s' % (k[:4], v) for k, v in c.items()))
+def test_features_match_reference(ctx, ref, case):
+    case = dict(case)
+    w, h = case.pop('width'), case.pop('height')
+    rp, vp = params_pair(**case)
+    a, b = synth.blob_pair(w, h, seed=7)
+    rm = ref.matcher(rp)
+    rm.push(a); rm.push(b)
+    ctx.configure(vp, w, h, 2)
+    ns, nd = ctx.push_frames([0, 1], [a, b])
+    rc = rm.counts()
+    assert (ns.tolist(), nd.tolist()) == ([rc['1p1'], rc['1c1']], [rc['1p2'], rc['1c2']])
+    for frame, tag in ((0, '1p'), (1, '1c')):
+        if vp.multi_stage:
+            assert np.array_equal(ctx.features(frame, 0), rm.maxima(tag + '1')), 'sparse records differ'
+        assert np.array_equal(ctx.features(frame, 1), rm.maxima(tag + '2')), 'dense records differ'
+        du, dv, (rw, rh, rbpl) = rm.sobel(tag)
+        gdu, (gw, gh, gbpl) = ctx.plane(frame, 0)
+        gdv, _ = ctx.plane(frame, 1)
+        assert (gw, gh, gbpl) == (rw, rh, rbpl)
+        assert np.array_equal(valid(gdu, gw), valid(du, rw)) and np.array_equal(valid(gdv, gw), valid(dv, rw))
+        if vp.half_resolution:
+            duf, dvf, (fw, fh, fb) = rm.sobel(tag, full=True)
+            g2, (w2, h2, b2) = ctx.plane(frame, 2)
+            g3, _ = ctx.plane(frame, 3)
+            assert (w2, h2, b2) == (fw, fh, fb)
+            assert np.array_equal(valid(g2, w2), valid(duf, fw)) and np.array_equal(valid(g3, w2), valid(dvf, fw))
+
+
+def test_half_image(ctx, ref):
+    rp, vp = params_pair(half_resolution=1)
+    a, _ = synth.blob_pair(1241, 376, seed=3)
+    rm = ref.matcher(rp)
+    half, (wh, hh, bh) = rm.half_image(pyref.padded(a), 1241)
+    ctx.configure(vp, 1241, 376, 1)
+    ctx.push_frames([0], [a])
+    g, (gw, gh, gb) = ctx.plane(0, 5)
+    assert (gw, gh, gb) == (wh, hh, bh)
+    assert np.array_equal(g[:, :gw], half[:, :wh])
+
+
+def test_standalone_filters(ctx, ref):
+    img = synth.blob_pair(320, 200, seed=5)[0]
+    du, dv = ctx.sobel5x5(img); rdu, rdv = ref.sobel5x5(img)
+    assert np.array_equal(du[2:-2, 2:-2], rdu[2:-2, 2:-2]) and np.array_equal(dv[2:-2, 2:-2], rdv[2:-2, 2:-2])
+    du, dv = ctx.sobel3x3(img); rdu, rdv = ref.sobel3x3(img)
+    assert np.array_equal(du[1:-1, 1:-1], rdu[1:-1, 1:-1]) and np.array_equal(dv[1:-1, 1:-1], rdv[1:-1, 1:-1])
+    f1 = ctx.blob5x5(img); r1 = ref.blob5x5(img)
+    assert np.array_equal(f1[3:-2, 3:-2], r1[3:-2, 3:-2])
+    f2 = ctx.checkerboard5x5(img); r2 = ref.checkerboard5x5(img)
+    assert np.array_equal(f2[2:-2, 2:-66], r2[2:-2, 2:-66])       # the reference's row pass stops short (filter.cpp:268)
+    # NMS on the reference's own response maps
+    rm = ref.matcher(pyref.MatcherParams())
+    for n in (3, 9):
+        got = ctx.nms(r1, r2, 320, n, 50)
+        want = rm.nms(r1, r2, 320, n)
+        assert np.array_equal(got, want)
+
+
+def _flow_setup(ctx, ref, w, h, half, seed=11, **kw):
+    rp, vp = params_pair(half_resolution=half, **kw)
+    a, b = synth.blob_pair(w, h, seed=seed)
+    rm = ref.matcher(rp)
+    rm.push(a); rm.push(b)
+    ctx.configure(vp, w, h, 2)
+    ctx.push_frames([0, 1], [a, b])
+    return rm
+
+
+@pytest.mark.parametrize('half', [1, 0])
+@pytest.mark.parametrize('size', [(1241, 376), (400, 300)])
+def test_flow_matching_two_pass(ctx, ref, size, half):
+    w, h = size
+    rm = _flow_setup(ctx, ref, w, h, half)
+    quad = (0, -1, 1, -1)
+    # pass 1: sparse sets, full search window (P4)
+    want1 = rm.matching(0, 0, False)
+    got1 = ctx.match([quad], 0, 0)[0]
+    assert len(want1) > 50
+    assert got1.tobytes() == want1.tobytes()
+    # priors from the reference's own host stages (P5), then pass 2 with priors and pixel refinement (P6)
+    ranges = rm.prior(rm.remove_outliers(want1, 0), 0)
+    want2 = rm.matching(1, 0, True)
+    got2 = ctx.match([quad], 0, 1, ranges=[ranges])[0]
+    assert len(want2) > 200
+    assert got2.tobytes() == want2.tobytes()
+    want3 = rm.refinement(want2, 0)
+    got3 = ctx.match([quad], 0, 1, ranges=[ranges], refine=True)[0]
+    assert got3.tobytes() == want3.tobytes()
+    assert ctx.refine(quad, 0, want2).tobytes() == want3.tobytes()
+    cand, scanned = ctx.match_stats()
+    assert cand > 0 and scanned >= cand
+
+
+@pytest.mark.parametrize('half', [1, 0])
+def test_quad_matching_two_pass(ctx, ref, half):
+    w, h = 1241, 376
+    rp, vp = params_pair(half_resolution=half, nms_n=2)
+    lp, rpv, lc, rc = synth.blob_quad(w, h, seed=21)
+    rm = ref.matcher(rp)
+    rm.push(lp, rpv); rm.push(lc, rc)
+    ctx.configure(vp, w, h, 4)
+    ctx.push_frames([0, 1, 2, 3], [lp, rpv, lc, rc])
+    for frame, tag in ((0, '1p2'), (1, '2p2'), (2, '1c2'), (3, '2c2')):
+        assert np.array_equal(ctx.features(frame, 1), rm.maxima(tag))
+    quad = (0, 1, 2, 3)
+    want1 = rm.matching(0, 2, False)
+    got1 = ctx.match([quad], 2, 0)[0]
+    assert len(want1) > 50 and got1.tobytes() == want1.tobytes()
+    ranges = rm.prior(rm.remove_outliers(want1, 2), 2)
+    want2 = rm.matching(1, 2, True)
+    got2 = ctx.match([quad], 2, 1, ranges=[ranges])[0]
+    assert len(want2) > 200 and got2.tobytes() == want2.tobytes()
+    want3 = rm.refinement(want2, 2)
+    got3 = ctx.match([quad], 2, 1, ranges=[ranges], refine=True)[0]
+    assert got3.tobytes() == want3.tobytes()
+
+
+def test_batched_jobs_equal_single_jobs(ctx, ref):
+    """Batch dimension: 6 frames / 3 independent pairs in one launch give the same lists as one at a time."""
+    w, h = 500, 260
+    rp, vp = params_pair()
+    ctx.configure(vp, w, h, 6)
+    pairs = [synth.blob_pair(w, h, seed=s) for s in (31, 32, 33)]
+    ctx.push_frames(list(range(6)), [im for p in pairs for im in p])
+    quads = [(0, -1, 1, -1), (2, -1, 3, -1), (4, -1, 5, -1)]
+    batched = ctx.match(quads, 0, 0)
+    for k, (a, b) in enumerate(pairs):
+        rm = ref.matcher(rp)
+        rm.push(a); rm.push(b)
+        want = rm.matching(0, 0, False)
+        assert batched[k].tobytes() == want.tobytes()
+        assert np.array_equal(ctx.features(2 * k + 1, 1), rm.maxima('1c2'))
+
+
+def _normalized_F(F):
+    F = F / np.linalg.norm(F)
+    k = np.argmax(np.abs(F))
+    return F * np.sign(F.flat[k])
+
+
+def test_ransac_against_reference(ctx, ref_nofma):
+    """P8: identical sample table -> per-hypothesis inlier counts, winner, inlier set and F.
+    Tolerances: F (unit Frobenius norm, fixed sign) to 1e-8 absolute; per-hypothesis counts may differ only for
+    hypotheses whose 8-point system is numerically rank deficient (different null-space basis) or whose matches
+    sit within rounding of the threshold: at most 1% of hypotheses, each by a bounded amount checked below."""
+    seq = synth.corridor_sequence(2, seed=1234)
+    mp = pyref.MonoParams(match=pyref.MatcherParams(), f=synth.KITTI_F, cu=synth.KITTI_CU, cv=synth.KITTI_CV,
+                          height=1.6, pitch=-0.08)
+    vo = ref_nofma.mono(mp)
+    vo.process(seq[0]); vo.process(seq[1])
+    pm = vo.matches()
+    assert len(pm) > 100
+    ok, pmn, Tp, Tc = vo.normalize(pm)
+    assert ok
+    rng = np.random.default_rng(5)
+    iters = 2000
+    samples = np.stack([rng.choice(len(pmn), 8, replace=False) for _ in range(iters)]).astype(np.int32)
+    want = vo.ransac_with_samples(pmn, samples)
+    uv = np.stack([pmn['u1p'], pmn['v1p'], pmn['u1c'], pmn['v1c']], axis=1)
+    got = ctx.ransac([uv], [samples], 1e-5, want_all=True)[0]
+    diff = got['counts'] != want['counts']
+    assert diff.mean() <= 0.01, 'hypothesis counts differ for %d of %d' % (diff.sum(), iters)
+    assert got['best_iter'] == want['best_iter']
+    assert got['n_inliers'] == want['n_inliers']
+    assert np.array_equal(got['inliers'], want['inliers'])
+    assert np.abs(_normalized_F(got['F']) - _normalized_F(want['F'])).max() < 1e-8
+    # the non-degenerate hypotheses agree to rounding as well
+    same = ~diff
+    Fg = np.stack([_normalized_F(f) for f in got['F_all'][same]])
+    Fw = np.stack([_normalized_F(f) for f in want['F_all'][same]])
+    assert np.median(np.abs(Fg - Fw).max(axis=(1, 2))) < 1e-10
