@@ -20,6 +20,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the libraries are built with -fvisibility=hidden */
+#endif
 
 #define VISOCU_OK            0
 #define VISOCU_EINVAL       -1   /* bad argument (also: dims <= 0, bpl < width -- matcher.cpp:103-106) */
@@ -124,6 +127,9 @@ int  visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* const* uv, co
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int  visocu_launch_count(const visocu_ctx* ctx, uint64_t* n);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

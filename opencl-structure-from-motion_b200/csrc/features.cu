@@ -155,7 +155,10 @@ __global__ void __launch_bounds__(FILTER_THREADS) k_filter_nms(Geometry g, const
       const int gx = fx0 + cx;
       const uint8_t* col = simg + (gx - 2 - ix0);          // p[0] of hrow for image-tile row r is col[r*IS]
       const bool core_x = gx >= x0 && gx < x0 + TW && gx < g.bplm;
-      const bool valid_x = gx >= 2 && gx <= g.wm - 3;
+      // columns w-2 .. bpl-3 are computed too, from the zero pad: the reference filters its whole 16-byte-stride
+      // buffer and a descriptor of a maximum at u = w-7 samples column w-2 (its pad bytes are uninitialised heap
+      // memory there, zero in the common case of a fresh allocation)
+      const bool valid_x = gx >= 2 && gx <= g.bplm - 3;
       int hd[5], ha[5], h1[5], h3[5], hc[5], pc[5];
 #pragma unroll
       for (int k = 0; k < 4; k++) {

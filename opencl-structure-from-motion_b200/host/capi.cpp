@@ -1,0 +1,234 @@
+// extern "C" access to the C++ host layer for the Python tests and bench.py (ctypes), plus the sharded
+// sequence runner (independent sequences, one host worker set and one CUDA stream per Matcher,
+// no collective).  Plain pointers and sizes only.
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <sstream>
+#include <thread>
+#include <vector>
+
+#include "delaunay.h"
+#include "device.h"
+#include "filter.h"
+#include "matcher.h"
+#include "viso_mono.h"
+#include "visocu.h"
+
+#define VISOB_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+struct MonoParamsC {          // flat mirror of VisualOdometryMono::parameters (same as oracle/pyref.py MonoParams)
+  Matcher::parameters match;
+  int32_t bucket_max_features; double bucket_width, bucket_height;
+  double f, cu, cv;
+  double height, pitch; int32_t ransac_iters; double inlier_threshold, motion_threshold;
+};
+VisualOdometryMono::parameters to_cpp(const MonoParamsC* p) {
+  VisualOdometryMono::parameters q;
+  q.match = p->match;
+  q.bucket.max_features = p->bucket_max_features; q.bucket.bucket_width = p->bucket_width; q.bucket.bucket_height = p->bucket_height;
+  q.calib.f = p->f; q.calib.cu = p->cu; q.calib.cv = p->cv;
+  q.height = p->height; q.pitch = p->pitch; q.ransac_iters = p->ransac_iters;
+  q.inlier_threshold = p->inlier_threshold; q.motion_threshold = p->motion_threshold;
+  return q;
+}
+int copy_matches(const std::vector<Matcher::p_match>& v, void* out, int cap) {
+  const int n = (int)v.size();
+  if (out && n > 0) memcpy(out, v.data(), sizeof(Matcher::p_match) * (size_t)std::min(n, cap));
+  return n;
+}
+struct MonoAccess : public VisualOdometryMono {
+  explicit MonoAccess(VisualOdometryMono::parameters p) : VisualOdometryMono(p) {}
+};
+}  // namespace
+
+VISOB_API void visob_set_device(int device) { visob::set_device(device); }
+
+// ---- Matcher
+VISOB_API void* visob_matcher_create(const Matcher::parameters* p) { return new Matcher(*p); }
+VISOB_API void visob_matcher_destroy(void* m) { delete (Matcher*)m; }
+VISOB_API void visob_matcher_push(void* m, uint8_t* I1, uint8_t* I2, const int32_t* dims, int replace) {
+  uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+  ((Matcher*)m)->pushBack(I1, I2, d, replace != 0);
+}
+VISOB_API void visob_matcher_push_device(void* m, const uint8_t* I1, const uint8_t* I2, const int32_t* dims, int replace) {
+  uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+  ((Matcher*)m)->pushBackDevice(I1, I2, d, replace != 0);
+}
+VISOB_API void visob_matcher_match_features(void* m, int method) { ((Matcher*)m)->matchFeatures(method, 0); }
+VISOB_API void visob_matcher_bucket(void* m, int max_features, float bw, float bh) { ((Matcher*)m)->bucketFeatures(max_features, bw, bh); }
+VISOB_API int visob_matcher_get_matches(void* m, int stage, void* out, int cap) { return copy_matches(((Matcher*)m)->matches(stage), out, cap); }
+VISOB_API void visob_matcher_counts(void* m, int32_t* out8) { for (int k = 0; k < 8; k++) out8[k] = ((Matcher*)m)->featureCount(k); }
+VISOB_API float visob_matcher_gain(void* m, const int32_t* inl, int n) { return ((Matcher*)m)->getGain(std::vector<int32_t>(inl, inl + n)); }
+VISOB_API void* visob_matcher_context(void* m) { return ((Matcher*)m)->context(); }
+VISOB_API int visob_matcher_remove_outliers(void* m, void* inout, int n, int method) {
+  std::vector<Matcher::p_match> pm((Matcher::p_match*)inout, (Matcher::p_match*)inout + n);
+  ((Matcher*)m)->removeOutliers(pm, method);
+  return copy_matches(pm, inout, n);
+}
+VISOB_API int visob_matcher_prior(void* m, const void* matches, int n, int method, float* ranges_out, int cap_bins) {
+  std::vector<Matcher::p_match> pm((const Matcher::p_match*)matches, (const Matcher::p_match*)matches + n);
+  ((Matcher*)m)->computePriorStatistics(pm, method);
+  const std::vector<Matcher::range>& r = ((Matcher*)m)->priorRanges();
+  if (ranges_out) memcpy(ranges_out, r.data(), sizeof(Matcher::range) * (size_t)std::min((int)r.size(), cap_bins));
+  return (int)r.size();
+}
+
+// ---- filter::
+VISOB_API int visob_filter(int which, const uint8_t* in, uint8_t* out_a, uint8_t* out_b, int16_t* out16, int w, int h) {
+  try {
+    if (which == 0) filter::sobel5x5(in, out_a, out_b, w, h);
+    else if (which == 1) filter::sobel3x3(in, out_a, out_b, w, h);
+    else if (which == 2) filter::blob5x5(in, out16, w, h);
+    else filter::checkerboard5x5(in, out16, w, h);
+  } catch (const std::exception&) { return -1; }
+  return 0;
+}
+
+// ---- mono odometry
+VISOB_API void* visob_mono_create(const MonoParamsC* p) { return new MonoAccess(to_cpp(p)); }
+VISOB_API void visob_mono_destroy(void* v) { delete (MonoAccess*)v; }
+VISOB_API int visob_mono_process(void* v, uint8_t* I, const int32_t* dims, int replace) {
+  uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+  return ((MonoAccess*)v)->process(I, d, replace != 0) ? 1 : 0;
+}
+VISOB_API int visob_mono_process_device(void* v, const uint8_t* I, const int32_t* dims, int replace) {
+  uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+  return ((MonoAccess*)v)->processDevice(I, d, replace != 0) ? 1 : 0;
+}
+VISOB_API int visob_mono_process_matches(void* v, const void* matches, int n) {
+  std::vector<Matcher::p_match> pm((const Matcher::p_match*)matches, (const Matcher::p_match*)matches + n);
+  return ((VisualOdometry*)(MonoAccess*)v)->process(pm) ? 1 : 0;
+}
+VISOB_API void visob_mono_get_motion(void* v, double* out16) {
+  Matrix T = ((MonoAccess*)v)->getMotion();
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out16[4 * i + j] = T.val[i][j];
+}
+VISOB_API int visob_mono_get_matches(void* v, void* out, int cap) { return copy_matches(((MonoAccess*)v)->usedMatches(), out, cap); }
+VISOB_API int visob_mono_get_inliers(void* v, int32_t* out, int cap) {
+  std::vector<int32_t> in = ((MonoAccess*)v)->getInlierIndices();
+  if (out) memcpy(out, in.data(), sizeof(int32_t) * (size_t)std::min((int)in.size(), cap));
+  return (int)in.size();
+}
+VISOB_API int visob_mono_get_F(void* v, double* F9) {
+  const Matrix& F = ((MonoAccess*)v)->lastF();
+  if (!F.val) return 0;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F9[3 * i + j] = F.val[i][j];
+  return 1;
+}
+VISOB_API int visob_mono_get_samples(void* v, int32_t* out, int cap) {
+  const std::vector<int>& s = ((MonoAccess*)v)->lastSamples();
+  if (out) for (int i = 0; i < std::min((int)s.size(), cap); i++) out[i] = s[i];
+  return (int)s.size();
+}
+VISOB_API void* visob_mono_matcher(void* v) { return ((MonoAccess*)v)->getMatcher(); }
+
+// ---- host utilities exposed for tests
+VISOB_API int visob_delaunay(const int32_t* x, const int32_t* y, int n, int32_t* tri_out, int cap_tri) {
+  std::vector<int32_t> tri;
+  visob::delaunay_triangles(x, y, n, tri);
+  const int nt = (int)tri.size() / 3;
+  if (tri_out) memcpy(tri_out, tri.data(), sizeof(int32_t) * 3 * (size_t)std::min(nt, cap_tri));
+  return nt;
+}
+VISOB_API void visob_svd(const double* A, int m, int n, double* U, double* W, double* V) {
+  Matrix M(m, n, A), Um, Wm, Vm;
+  M.svd(Um, Wm, Vm);
+  for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) U[i * m + j] = Um.val[i][j];
+  for (int i = 0; i < std::min(m, n); i++) W[i] = Wm.val[i][0];
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = Vm.val[i][j];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sharded sequence runner.  S independent sequences live on one GPU; `step` feeds one new frame (or stereo pair)
+// to every sequence and matches it against that sequence's previous frame.  Sequences are dealt round-robin to
+// `threads` host workers; every Matcher has its own CUDA stream, so kernels of different sequences overlap on the
+// GPU while other workers run the host stages (outlier removal, priors, bucketing).
+namespace {
+struct Runner {
+  int device, S, threads, mode, method;      // mode 0 = Matcher only, 1 = VisualOdometryMono::process
+  int bucket_max; float bucket_w, bucket_h;
+  std::vector<Matcher*> matchers;
+  std::vector<MonoAccess*> monos;
+  std::vector<int32_t> last_matches;         // per sequence: matches of the last step (mode 1: 1 = process ok, else 0 in last_ok)
+  std::vector<int32_t> last_ok;
+};
+}  // namespace
+
+VISOB_API void* visob_runner_create(int device, int n_sequences, int threads, int mode, int method, const MonoParamsC* p) {
+  Runner* r = new Runner();
+  r->device = device; r->S = n_sequences; r->threads = std::max(1, std::min(threads, n_sequences)); r->mode = mode; r->method = method;
+  r->bucket_max = p->bucket_max_features; r->bucket_w = (float)p->bucket_width; r->bucket_h = (float)p->bucket_height;
+  visob::set_device(device);
+  for (int s = 0; s < n_sequences; s++) {
+    if (mode == 1) r->monos.push_back(new MonoAccess(to_cpp(p)));
+    else r->matchers.push_back(new Matcher(p->match));
+  }
+  r->last_matches.assign(n_sequences, 0);
+  r->last_ok.assign(n_sequences, 0);
+  return r;
+}
+VISOB_API void visob_runner_destroy(void* h) {
+  Runner* r = (Runner*)h;
+  for (Matcher* m : r->matchers) delete m;
+  for (MonoAccess* m : r->monos) delete m;
+  delete r;
+}
+// imgs / imgs2: S pointers (imgs2 may be null for mono / flow).  on_device: pointers are device memory.
+// bucket: apply bucketFeatures after matching (mode 0).  Returns wall seconds spent in the step.
+VISOB_API double visob_runner_step(void* h, const uint8_t* const* imgs, const uint8_t* const* imgs2, const int32_t* dims,
+                                   int on_device, int bucket, int32_t* n_matches_out, int32_t* ok_out) {
+  Runner* r = (Runner*)h;
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&](int tid) {
+    visob::set_device(r->device);
+    uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+    for (int s = tid; s < r->S; s += r->threads) {
+      if (r->mode == 1) {
+        MonoAccess* vo = r->monos[s];
+        bool ok = on_device ? vo->processDevice(imgs[s], d, false) : vo->process(const_cast<uint8_t*>(imgs[s]), d, false);
+        r->last_ok[s] = ok ? 1 : 0;
+        r->last_matches[s] = vo->getNumberOfMatches();
+      } else {
+        Matcher* m = r->matchers[s];
+        const uint8_t* i2 = imgs2 ? imgs2[s] : 0;
+        if (on_device) m->pushBackDevice(imgs[s], i2, d, false);
+        else m->pushBack(const_cast<uint8_t*>(imgs[s]), const_cast<uint8_t*>(i2), d, false);
+        m->matchFeatures(r->method, 0);
+        if (bucket) m->bucketFeatures(r->bucket_max, r->bucket_w, r->bucket_h);
+        r->last_matches[s] = (int32_t)m->matches(2).size();
+        r->last_ok[s] = 1;
+      }
+    }
+  };
+  if (r->threads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < r->threads; t++) pool.emplace_back(work, t);
+    for (std::thread& t : pool) t.join();
+  }
+  if (n_matches_out) memcpy(n_matches_out, r->last_matches.data(), sizeof(int32_t) * r->S);
+  if (ok_out) memcpy(ok_out, r->last_ok.data(), sizeof(int32_t) * r->S);
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+VISOB_API int visob_runner_get_matches(void* h, int seq, void* out, int cap) {
+  Runner* r = (Runner*)h;
+  if (seq < 0 || seq >= r->S) return -1;
+  if (r->mode == 1) return copy_matches(r->monos[seq]->usedMatches(), out, cap);
+  return copy_matches(r->matchers[seq]->matches(2), out, cap);
+}
+VISOB_API void visob_runner_get_motion(void* h, int seq, double* out16) {
+  Runner* r = (Runner*)h;
+  if (r->mode != 1 || seq < 0 || seq >= r->S) return;
+  Matrix T = r->monos[seq]->getMotion();
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out16[4 * i + j] = T.val[i][j];
+}
+VISOB_API uint64_t visob_runner_launches(void* h) {
+  Runner* r = (Runner*)h;
+  uint64_t total = 0, n = 0;
+  for (Matcher* m : r->matchers) if (m->context() && visocu_launch_count(m->context(), &n) == 0) total += n;
+  for (MonoAccess* v : r->monos) if (v->getMatcher()->context() && visocu_launch_count(v->getMatcher()->context(), &n) == 0) total += n;
+  return total;
+}

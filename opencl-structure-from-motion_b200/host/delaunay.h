@@ -1,0 +1,12 @@
+// Exact Delaunay triangulation of integer points (see delaunay.cpp).
+#ifndef VISOB_DELAUNAY_H
+#define VISOB_DELAUNAY_H
+#include <stdint.h>
+#include <vector>
+
+namespace visob {
+// tri receives 3 indices (into x/y) per triangle, counter-clockwise.  Coordinates must satisfy |x|,|y| < 2^15.
+// Of several points with identical coordinates only the one with the lowest index is triangulated.
+void delaunay_triangles(const int32_t* x, const int32_t* y, int n, std::vector<int32_t>& tri);
+}
+#endif

@@ -1,0 +1,305 @@
+// Host side of the feature front end.  See matcher.h for the split between GPU and host work.
+// Reference behaviour restated here (paths relative to /root/reference/viso):
+//   constructor ........................ matcher.cpp:38-62     pushBack ............ matcher.cpp:95-181
+//   matchFeatures ...................... matcher.cpp:183-241   bucketFeatures ...... matcher.cpp:243-284
+//   getGain ............................ matcher.cpp:286-324   computePriorStatistics matcher.cpp:734-868
+//   removeOutliers ..................... matcher.cpp:1207-1377
+#include "matcher.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "delaunay.h"
+#include "device.h"
+#include "visocu.h"
+
+using std::vector;
+
+namespace visob {
+static thread_local int t_device = 0;
+void set_device(int device) { t_device = device; }
+int current_device() { return t_device; }
+}  // namespace visob
+
+static_assert(sizeof(Matcher::p_match) == sizeof(visocu_pmatch), "p_match layout");
+static_assert(sizeof(Matcher::range) == sizeof(visocu_range), "range layout");
+static_assert(sizeof(Matcher::parameters) == sizeof(visocu_params), "parameters layout");
+
+Matcher::Matcher(parameters param) : param(param), ctx(0), cfg_w(0), cfg_h(0), have_I1p(false), have_I1c(false) {
+  margin = 5 + 1;
+  if (param.half_resolution) this->param.match_radius /= 2;     // matcher.cpp:59-60
+  device = visob::current_device();
+  for (int k = 0; k < 4; k++) slot[k] = -1;
+  for (int k = 0; k < 8; k++) n_feat[k] = 0;
+  for (int k = 0; k < 3; k++) dims_p[k] = dims_c[k] = 0;
+}
+
+Matcher::~Matcher() {
+  if (ctx) visocu_destroy(ctx);
+}
+
+bool Matcher::ensureContext(int32_t w, int32_t h) {
+  if (!ctx) {
+    if (visocu_create(device, &ctx) != VISOCU_OK) {
+      std::cerr << "ERROR: " << visocu_last_error(0) << std::endl;
+      ctx = 0;
+      return false;
+    }
+  }
+  if (w != cfg_w || h != cfg_h) {
+    visocu_params vp;
+    memcpy(&vp, &param, sizeof vp);
+    if (visocu_configure(ctx, &vp, w, h, 4) != VISOCU_OK) {
+      std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+      return false;
+    }
+    cfg_w = w; cfg_h = h;
+    for (int k = 0; k < 4; k++) slot[k] = -1;        // features of another image size cannot be matched
+    for (int k = 0; k < 8; k++) n_feat[k] = 0;
+    have_I1p = have_I1c = false;
+  }
+  return true;
+}
+
+void Matcher::pushBack(uint8_t* I1, uint8_t* I2, uint32_t* dims, const bool replace) { push(I1, I2, dims, replace, false); }
+void Matcher::pushBackDevice(const uint8_t* d_I1, const uint8_t* d_I2, uint32_t* dims, const bool replace) { push(d_I1, d_I2, dims, replace, true); }
+
+void Matcher::push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool replace, bool on_device) {
+  const int32_t width = dims[0], height = dims[1], bpl = dims[2];
+  if (width <= 0 || height <= 0 || bpl < width || I1 == 0) {
+    std::cerr << "ERROR: Image dimension mismatch!" << std::endl;
+    return;
+  }
+  if (!ensureContext(width, height)) return;
+  if (!replace) {
+    // current -> previous: the device frames swap roles, nothing is copied
+    std::swap(slot[0], slot[2]);
+    std::swap(slot[1], slot[3]);
+    for (int k = 0; k < 2; k++) { n_feat[0 + k] = n_feat[2 + k]; n_feat[4 + k] = n_feat[6 + k]; }
+    I1p.swap(I1c);
+    have_I1p = have_I1c;
+    for (int k = 0; k < 3; k++) dims_p[k] = dims_c[k];
+  }
+  dims_c[0] = width; dims_c[1] = height; dims_c[2] = width + 15 - (width - 1) % 16;
+  // pick device frames for the new current images: reuse the ones just vacated (or never used)
+  bool used[4] = {false, false, false, false};
+  if (slot[0] >= 0) used[slot[0]] = true;
+  if (slot[1] >= 0) used[slot[1]] = true;
+  int32_t fresh[2], nf = 0;
+  for (int k = 0; k < 4 && nf < 2; k++) if (!used[k]) fresh[nf++] = k;
+  slot[2] = fresh[0];
+  slot[3] = I2 ? fresh[1] : -1;
+  int32_t frames[2] = {slot[2], slot[3]};
+  const uint8_t* imgs[2] = {I1, I2};
+  int32_t ns[2] = {0, 0}, nd[2] = {0, 0};
+  const int nimg = I2 ? 2 : 1;
+  if (visocu_push_frames(ctx, nimg, frames, imgs, bpl, on_device ? 1 : 0, ns, nd) != VISOCU_OK) {
+    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+    slot[2] = slot[3] = -1;
+    n_feat[2] = n_feat[3] = n_feat[6] = n_feat[7] = 0;
+    return;
+  }
+  n_feat[2] = ns[0]; n_feat[6] = nd[0];
+  n_feat[3] = I2 ? ns[1] : 0; n_feat[7] = I2 ? nd[1] : 0;
+  // host copy of the left image for getGain
+  if (!on_device) {
+    I1c.resize((size_t)dims_c[2] * height);
+    for (int32_t v = 0; v < height; v++) memcpy(&I1c[(size_t)v * dims_c[2]], I1 + (size_t)v * bpl, width);
+    have_I1c = true;
+  } else {
+    have_I1c = false;
+  }
+}
+
+bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_prior, bool refine) {
+  visocu_quad q = {slot[0], slot[1], slot[2], slot[3]};
+  const int32_t base = pass == 0 ? 0 : 4;
+  const int32_t nq = method == 0 ? n_feat[base + 2] : n_feat[base + 0];
+  out.resize((size_t)nq + 1);
+  visocu_pmatch* optr = reinterpret_cast<visocu_pmatch*>(out.data());
+  const visocu_range* rptr = reinterpret_cast<const visocu_range*>(ranges.data());
+  int32_t cap = nq + 1, n = 0;
+  int rc = visocu_match(ctx, 1, &q, method, pass, use_prior ? 1 : 0, use_prior ? &rptr : 0, refine ? 1 : 0, &optr, &cap, &n);
+  if (rc != VISOCU_OK) {
+    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+    out.clear();
+    return false;
+  }
+  out.resize(n);
+  return true;
+}
+
+void Matcher::matchFeatures(int32_t method, Matrix* Tr_delta) {
+  // sanity checks of matcher.cpp:190-212: silently keep the old matches if a needed set is empty
+  const int32_t* n1 = n_feat;       // sparse: 1p 2p 1c 2c
+  const int32_t* n2 = n_feat + 4;   // dense
+  if (method == 0) {
+    if (n2[0] == 0 || n2[2] == 0) return;
+    if (param.multi_stage && (n1[0] == 0 || n1[2] == 0)) return;
+  } else if (method == 1) {
+    std::cerr << "ERROR: Matcher method 1 (stereo) is not available in this implementation" << std::endl;
+    return;
+  } else {
+    if (n2[0] == 0 || n2[1] == 0 || n2[2] == 0 || n2[3] == 0) return;
+    if (param.multi_stage && (n1[0] == 0 || n1[1] == 0 || n1[2] == 0 || n1[3] == 0)) return;
+  }
+  if (param.refinement > 1) {
+    std::cerr << "ERROR: sub-pixel refinement (refinement=2) is not available in this implementation; using pixel refinement" << std::endl;
+  }
+  (void)Tr_delta;   // the motion-predicted search of matcher.cpp:1114-1134 is not implemented: plain search is used
+  p_matched_1.clear();
+  p_matched_2.clear();
+  const bool refine = param.refinement > 0;
+  if (param.multi_stage) {
+    if (!matching(0, p_matched_1, method, false, false)) return;
+    removeOutliers(p_matched_1, method);
+    computePriorStatistics(p_matched_1, method);
+    if (!matching(1, p_matched_2, method, true, refine)) return;
+    removeOutliers(p_matched_2, method);
+  } else {
+    if (!matching(1, p_matched_2, method, false, refine)) return;
+    removeOutliers(p_matched_2, method);
+  }
+}
+
+void Matcher::bucketFeatures(int32_t max_features, float bucket_width, float bucket_height) {
+  float u_max = 0, v_max = 0;
+  for (const p_match& m : p_matched_2) {
+    if (m.u1c > u_max) u_max = m.u1c;
+    if (m.v1c > v_max) v_max = m.v1c;
+  }
+  const int32_t cols = (int32_t)floor(u_max / bucket_width) + 1, rows = (int32_t)floor(v_max / bucket_height) + 1;
+  vector<vector<p_match> > buckets((size_t)cols * rows);
+  for (const p_match& m : p_matched_2) {
+    const int32_t u = (int32_t)floor(m.u1c / bucket_width), v = (int32_t)floor(m.v1c / bucket_height);
+    buckets[(size_t)v * cols + u].push_back(m);
+  }
+  p_matched_2.clear();
+  for (vector<p_match>& b : buckets) {
+    // same library call as the reference (matcher.cpp:270): the kept subset depends on the process-wide rand()
+    // stream, which VisualOdometry seeds with srand(0)
+    std::random_shuffle(b.begin(), b.end());
+    int32_t k = 0;
+    for (const p_match& m : b) {
+      p_matched_2.push_back(m);
+      if (++k >= max_features) break;
+    }
+  }
+}
+
+static float window_mean(const vector<uint8_t>& I, int32_t bpl, int32_t u_min, int32_t u_max, int32_t v_min, int32_t v_max) {
+  float mean = 0;
+  for (int32_t v = v_min; v <= v_max; v++)
+    for (int32_t u = u_min; u <= u_max; u++) mean += (float)I[(size_t)v * bpl + u];
+  return mean / (float)((u_max - u_min + 1) * (v_max - v_min + 1));
+}
+
+float Matcher::getGain(vector<int32_t> inliers) {
+  if (!have_I1p || !have_I1c || p_matched_2.empty() || inliers.empty()) return 1;
+  const int32_t ws = 3;
+  float gain = 0;
+  int32_t num = 0;
+  auto clampi = [](int32_t x, int32_t hi) { return std::min(std::max(x, 0), hi); };
+  for (int32_t idx : inliers) {
+    if (idx >= (int32_t)p_matched_2.size()) continue;
+    const p_match& m = p_matched_2[idx];
+    // note: the reference clamps to dims_p[0] / dims_p[1] (one past the last pixel) for both images
+    const float mp = window_mean(I1p, dims_p[2], clampi((int32_t)m.u1p - ws, dims_p[0]), clampi((int32_t)m.u1p + ws, dims_p[0]),
+                                 clampi((int32_t)m.v1p - ws, dims_p[1] - 1), clampi((int32_t)m.v1p + ws, dims_p[1] - 1));
+    const float mc = window_mean(I1c, dims_c[2], clampi((int32_t)m.u1c - ws, dims_p[0]), clampi((int32_t)m.u1c + ws, dims_p[0]),
+                                 clampi((int32_t)m.v1c - ws, dims_p[1] - 1), clampi((int32_t)m.v1c + ws, dims_p[1] - 1));
+    if (mp > 10) { gain += mc / mp; num++; }
+  }
+  return num > 0 ? gain / (float)num : 1;
+}
+
+void Matcher::computePriorStatistics(vector<p_match>& p_matched, int32_t method) {
+  const float bs = (float)param.match_binsize;
+  const int32_t ub = (int32_t)ceil((float)dims_c[0] / bs), vb = (int32_t)ceil((float)dims_c[1] / bs);
+  const int32_t nbin = ub * vb, stages = method == 2 ? 4 : 2, nd = stages * 2;
+  // running min / max of the displacements seen in the 3x3 bin neighbourhood of every match
+  vector<float> lo((size_t)nbin * 8, 1000000.f), hi((size_t)nbin * 8, -1000000.f);
+  vector<uint8_t> seen(nbin, 0);
+  for (const p_match& m : p_matched) {
+    float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float ru, rv;
+    if (method == 0) {
+      d[0] = m.u1p - m.u1c; d[1] = m.v1p - m.v1c; d[2] = m.u1c - m.u1p; d[3] = m.v1c - m.v1p;
+      ru = m.u1c; rv = m.v1c;
+    } else if (method == 1) {
+      d[0] = m.u2c - m.u1c; d[2] = m.u1c - m.u2c;
+      ru = m.u1c; rv = m.v1c;
+    } else {
+      d[0] = m.u2p - m.u1p; d[2] = m.u2c - m.u2p; d[3] = m.v2c - m.v2p; d[4] = m.u1c - m.u2c;
+      d[6] = m.u1p - m.u1c; d[7] = m.v1p - m.v1c;
+      ru = m.u1p; rv = m.v1p;
+    }
+    const int32_t cu = (int32_t)floor(ru / bs), cv = (int32_t)floor(rv / bs);
+    const int32_t u0 = std::min(std::max(cu - 1, 0), ub - 1), u1 = std::min(std::max(cu + 1, 0), ub - 1);
+    const int32_t v0 = std::min(std::max(cv - 1, 0), vb - 1), v1 = std::min(std::max(cv + 1, 0), vb - 1);
+    for (int32_t v = v0; v <= v1; v++)
+      for (int32_t u = u0; u <= u1; u++) {
+        const size_t b = (size_t)v * ub + u;
+        seen[b] = 1;
+        for (int32_t i = 0; i < nd; i++) {
+          if (d[i] < lo[b * 8 + i]) lo[b * 8 + i] = d[i];
+          if (d[i] > hi[b * 8 + i]) hi[b * 8 + i] = d[i];
+        }
+      }
+  }
+  ranges.assign(nbin, range());
+  for (int32_t b = 0; b < nbin; b++) {
+    float dmin[8], dmax[8];
+    for (int32_t i = 0; i < 8; i++) {
+      dmin[i] = seen[b] ? lo[(size_t)b * 8 + i] : (float)(-param.match_radius);
+      dmax[i] = seen[b] ? hi[(size_t)b * 8 + i] : (float)(+param.match_radius);
+    }
+    range r;
+    memset(&r, 0, sizeof r);
+    for (int32_t i = 0; i < stages; i++) {
+      for (int32_t a = 0; a < 2; a++) {                // widen to at least 20 pixels (matcher.cpp:845-854)
+        const float span = dmax[i * 2 + a] - dmin[i * 2 + a];
+        if (span < 20) {
+          const float grow = ceil((20 - span) / 2);
+          dmin[i * 2 + a] -= grow;
+          dmax[i * 2 + a] += grow;
+        }
+      }
+      r.u_min[i] = dmin[i * 2 + 0]; r.u_max[i] = dmax[i * 2 + 0];
+      r.v_min[i] = dmin[i * 2 + 1]; r.v_max[i] = dmax[i * 2 + 1];
+    }
+    ranges[b] = r;
+  }
+}
+
+void Matcher::removeOutliers(vector<p_match>& p_matched, int32_t method) {
+  const int32_t n = (int32_t)p_matched.size();
+  if (n <= 3) return;
+  vector<int32_t> x(n), y(n), tri;
+  for (int32_t i = 0; i < n; i++) { x[i] = (int32_t)p_matched[i].u1c; y[i] = (int32_t)p_matched[i].v1c; }
+  visob::delaunay_triangles(x.data(), y.data(), n, tri);
+  vector<int32_t> support(n, 0);
+  const float flow_tol = (float)param.outlier_flow_tolerance, disp_tol = (float)param.outlier_disp_tolerance;
+  auto edge_ok = [&](const p_match& a, const p_match& b) -> bool {
+    if (method == 0) {
+      return fabs((a.u1c - a.u1p) - (b.u1c - b.u1p)) + fabs((a.v1c - a.v1p) - (b.v1c - b.v1p)) < flow_tol;
+    } else if (method == 1) {
+      return fabs((a.u1c - a.u2c) - (b.u1c - b.u2c)) < disp_tol;
+    }
+    return fabs((a.u1p - a.u2p) - (b.u1p - b.u2p)) < disp_tol &&
+           fabs((a.u1c - a.u1p) - (b.u1c - b.u1p)) + fabs((a.v1c - a.v1p) - (b.v1c - b.v1p)) < flow_tol;
+  };
+  for (size_t t = 0; t + 2 < tri.size(); t += 3) {
+    const int32_t p1 = tri[t], p2 = tri[t + 1], p3 = tri[t + 2];
+    if (edge_ok(p_matched[p1], p_matched[p2])) { support[p1]++; support[p2]++; }
+    if (edge_ok(p_matched[p2], p_matched[p3])) { support[p2]++; support[p3]++; }
+    if (edge_ok(p_matched[p1], p_matched[p3])) { support[p1]++; support[p3]++; }
+  }
+  int32_t k = 0;
+  for (int32_t i = 0; i < n; i++)
+    if (support[i] >= 4) p_matched[k++] = p_matched[i];
+  p_matched.resize(k);
+}

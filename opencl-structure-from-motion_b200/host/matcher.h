@@ -1,0 +1,102 @@
+// Matcher with the reference's public interface (viso/matcher.h:37-136): same parameters struct and defaults,
+// same p_match layout, same pushBack / matchFeatures / bucketFeatures / getMatches / getGain signatures and
+// error behaviour, so it is a drop-in for libviso2's feature front end.  What runs where:
+//   GPU (through include/visocu.h): image copy into the 16-byte stride, half-resolution image, 5x5 filters,
+//       both non-maximum-suppression passes, descriptors, bin index, SAD circle matching (flow and quad),
+//       pixel refinement.
+//   host (this class): ring-buffer bookkeeping, computePriorStatistics, removeOutliers (own exact Delaunay
+//       triangulation + support vote), bucketFeatures, getGain.
+// Not supported yet: method 1 (stereo only), refinement == 2 (sub-pixel), Tr_delta-guided search.
+#ifndef VISOB_MATCHER_H
+#define VISOB_MATCHER_H
+#include <stdint.h>
+#include <vector>
+
+#include "matrix.h"
+
+struct visocu_ctx;
+
+class Matcher {
+public:
+  struct parameters {
+    int32_t nms_n;                   // non-max-suppression: min. distance between maxima (in pixels)
+    int32_t nms_tau;                 // non-max-suppression: interest point peakiness threshold
+    int32_t match_binsize;           // matching bin width/height (affects efficiency only)
+    int32_t match_radius;            // matching radius (du/dv in pixels)
+    int32_t match_disp_tolerance;    // dv tolerance for stereo matches (in pixels)
+    int32_t outlier_disp_tolerance;  // outlier removal: disparity tolerance (in pixels)
+    int32_t outlier_flow_tolerance;  // outlier removal: flow tolerance (in pixels)
+    int32_t multi_stage;             // 0=disabled,1=multistage matching (denser and faster)
+    int32_t half_resolution;         // 0=disabled,1=match at half resolution, refine at full resolution
+    int32_t refinement;              // refinement (0=none,1=pixel,2=subpixel)
+    double f, cu, cv, base;          // calibration (only for match prediction)
+    parameters() {
+      nms_n = 3; nms_tau = 50; match_binsize = 50; match_radius = 200; match_disp_tolerance = 2;
+      outlier_disp_tolerance = 5; outlier_flow_tolerance = 5; multi_stage = 1; half_resolution = 1; refinement = 1;
+      f = 1; cu = 0; cv = 0; base = 1;
+    }
+  };
+
+  Matcher(parameters param);
+  ~Matcher();
+
+  void setIntrinsics(double f, double cu, double cv, double base) {
+    param.f = f; param.cu = cu; param.cv = cv; param.base = base;
+  }
+
+  struct p_match {
+    float u1p, v1p; int32_t i1p;
+    float u2p, v2p; int32_t i2p;
+    float u1c, v1c; int32_t i1c;
+    float u2c, v2c; int32_t i2c;
+    p_match() {}
+    p_match(float u1p, float v1p, int32_t i1p, float u2p, float v2p, int32_t i2p,
+            float u1c, float v1c, int32_t i1c, float u2c, float v2c, int32_t i2c)
+        : u1p(u1p), v1p(v1p), i1p(i1p), u2p(u2p), v2p(v2p), i2p(i2p),
+          u1c(u1c), v1c(v1c), i1c(i1c), u2c(u2c), v2c(v2c), i2c(i2c) {}
+  };
+
+  // dims = {width, height, bytes per line}; the images are only read during the call
+  void pushBack(uint8_t* I1, uint8_t* I2, uint32_t* dims, const bool replace);
+  void pushBack(uint8_t* I1, uint32_t* dims, const bool replace) { pushBack(I1, 0, dims, replace); }
+  // method: 0 = flow, 2 = quad matching (1 = stereo is not available in this implementation)
+  void matchFeatures(int32_t method, Matrix* Tr_delta = 0);
+  void bucketFeatures(int32_t max_features, float bucket_width, float bucket_height);
+  std::vector<Matcher::p_match> getMatches() { return p_matched_2; }
+  float getGain(std::vector<int32_t> inliers);
+
+  // ---- extensions (not in the reference) ----
+  // same as pushBack, but the images already live in device memory of this matcher's GPU
+  void pushBackDevice(const uint8_t* d_I1, const uint8_t* d_I2, uint32_t* dims, const bool replace);
+  visocu_ctx* context() { return ctx; }
+  // stage access for parity tests: 1 = pass-1 list after removeOutliers, 2 = getMatches()
+  const std::vector<p_match>& matches(int stage) const { return stage == 1 ? p_matched_1 : p_matched_2; }
+  int32_t featureCount(int which) const { return which >= 0 && which < 8 ? n_feat[which] : 0; }   // 1p1 2p1 1c1 2c1 1p2 2p2 1c2 2c2
+  // host stages, usable on their own (used by the batch runner and the tests)
+  struct range { float u_min[4], u_max[4], v_min[4], v_max[4]; };
+  void computePriorStatistics(std::vector<p_match>& p_matched, int32_t method);
+  void removeOutliers(std::vector<p_match>& p_matched, int32_t method);
+  const std::vector<range>& priorRanges() const { return ranges; }
+
+private:
+  void push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool replace, bool on_device);
+  bool ensureContext(int32_t w, int32_t h);
+  bool matching(int pass, std::vector<p_match>& out, int32_t method, bool use_prior, bool refine);
+
+  parameters param;
+  int32_t margin;
+  visocu_ctx* ctx;
+  int device;
+  int32_t cfg_w, cfg_h;
+  // ring buffer: frame slots of the context.  slot[0] = previous left, [1] = previous right, [2] = current left,
+  // [3] = current right (-1 = empty)
+  int32_t slot[4];
+  int32_t n_feat[8];
+  int32_t dims_p[3], dims_c[3];
+  std::vector<uint8_t> I1p, I1c;         // host copies kept for getGain (matcher.cpp:286-324)
+  bool have_I1p, have_I1c;
+  std::vector<p_match> p_matched_1, p_matched_2;
+  std::vector<range> ranges;
+};
+
+#endif

@@ -1,0 +1,228 @@
+// Host side of monocular odometry.  Reference behaviour restated (paths relative to /root/reference/viso):
+//   process ............... viso_mono.cpp:33-39     estimateMotion ........ viso_mono.cpp:100-190
+//   ransacEstimateF ....... viso_mono.cpp:41-72     normalizeFeaturePoints  viso_mono.cpp:217-263
+//   findBestPlane ......... viso_mono.cpp:74-98     smallerThanMedian ..... viso_mono.cpp:192-215
+//   EtoRt ................. viso_mono.cpp:347-392   triangulateChieral .... viso_mono.cpp:394-431
+#include "viso_mono.h"
+
+#include <algorithm>
+#include <cmath>
+#include <iostream>
+#include <numeric>
+
+#include "visocu.h"
+
+using std::vector;
+
+VisualOdometryMono::VisualOdometryMono(parameters param) : VisualOdometry(param), param(param) {}
+VisualOdometryMono::~VisualOdometryMono() {}
+
+bool VisualOdometryMono::process(uint8_t* I, uint32_t* dims, bool replace) {
+  matcher->pushBack(I, dims, replace);
+  matcher->matchFeatures(0);
+  matcher->bucketFeatures(param.bucket.max_features, param.bucket.bucket_width, param.bucket.bucket_height);
+  p_matched = matcher->getMatches();
+  return updateMotion();
+}
+
+bool VisualOdometryMono::processDevice(const uint8_t* d_I, uint32_t* dims, bool replace) {
+  matcher->pushBackDevice(d_I, 0, dims, replace);
+  matcher->matchFeatures(0);
+  matcher->bucketFeatures(param.bucket.max_features, param.bucket.bucket_width, param.bucket.bucket_height);
+  p_matched = matcher->getMatches();
+  return updateMotion();
+}
+
+// GPU RANSAC.  The host only draws the sample table with the reference's generator, in the reference's order
+// (one getRandomSample per iteration), so a run is comparable with the reference hypothesis by hypothesis.
+Matrix VisualOdometryMono::ransacEstimateF(const vector<Matcher::p_match>& p_matched) {
+  inliers.clear();
+  const int32_t N = (int32_t)p_matched.size(), iters = param.ransac_iters;
+  samples_last.resize((size_t)iters * 8);
+  for (int32_t k = 0; k < iters; k++) {
+    vector<int> s = getRandomSample(N, 8);
+    std::copy(s.begin(), s.end(), samples_last.begin() + (size_t)k * 8);
+  }
+  vector<float> uv((size_t)N * 4);
+  for (int32_t i = 0; i < N; i++) {
+    uv[4 * i + 0] = p_matched[i].u1p; uv[4 * i + 1] = p_matched[i].v1p;
+    uv[4 * i + 2] = p_matched[i].u1c; uv[4 * i + 3] = p_matched[i].v1c;
+  }
+  vector<uint8_t> mask(N);
+  double F9[9];
+  int32_t n_inl = 0, best = -1;
+  const float* uvp = uv.data();
+  const int32_t* sp = samples_last.data();
+  uint8_t* mp = mask.data();
+  visocu_ctx* ctx = matcher->context();
+  if (!ctx || visocu_ransac_F(ctx, 1, &uvp, &N, &sp, iters, param.inlier_threshold, F9, &mp, &n_inl, &best, 0, 0) != VISOCU_OK) {
+    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+    return Matrix();
+  }
+  for (int32_t i = 0; i < N; i++)
+    if (mask[i]) inliers.push_back(i);
+  if (inliers.size() < 10) return Matrix();
+  return Matrix(3, 3, F9);
+}
+
+double VisualOdometryMono::findBestPlane(const Matrix& x_plane, double threshold, double weight) {
+  // signed distance of every point to the plane normal direction, then the mode of a Gaussian kernel density
+  const double ny = cos(-param.pitch), nz = sin(-param.pitch);
+  const int32_t n = x_plane.n;
+  vector<double> d(n);
+  for (int32_t i = 0; i < n; i++) d[i] = ny * x_plane.val[0][i] + nz * x_plane.val[1][i];
+  double best_sum = 0;
+  int32_t best_idx = 0;
+  for (int32_t i = 0; i < n; i++) {
+    if (d[i] <= threshold) continue;
+    double sum = 0;
+    for (int32_t j = 0; j < n; j++) {
+      const double dist = d[j] - d[i];
+      sum += exp(-dist * dist * weight);
+    }
+    if (sum > best_sum) { best_sum = sum; best_idx = i; }
+  }
+  return d[best_idx];
+}
+
+vector<double> VisualOdometryMono::estimateMotion(vector<Matcher::p_match> p_matched) {
+  const int32_t N = (int32_t)p_matched.size();
+  if (N < 10) return vector<double>();
+  double K_data[9] = {param.calib.f, 0, param.calib.cu, 0, param.calib.f, param.calib.cv, 0, 0, 1};
+  Matrix K(3, 3, K_data);
+  Matrix Tp, Tc;
+  vector<Matcher::p_match> normalized = p_matched;
+  if (!normalizeFeaturePoints(normalized, Tp, Tc)) return vector<double>();
+
+  Matrix F = ransacEstimateF(normalized);
+  if (F.val == 0) return vector<double>();
+  F_last = F;
+
+  // denormalise, essential matrix, rank 2 again
+  F = ~Tc * F * Tp;
+  Matrix E = ~K * F * K;
+  Matrix U, W, V;
+  E.svd(U, W, V);
+  W.val[2][0] = 0;
+  E = U * Matrix::diag(W) * ~V;
+
+  Matrix X, R, t;
+  EtoRt(E, K, p_matched, X, R, t);
+  if (X.val == 0) return vector<double>();
+
+  X = X / X.getMat(3, 0, 3, -1);
+  vector<int32_t> pos_idx;
+  for (int32_t i = 0; i < X.n; i++)
+    if (X.val[2][i] > 0) pos_idx.push_back(i);
+  Matrix X_plane = X.extractCols(pos_idx);
+  if (X_plane.n < 10) return vector<double>();
+
+  double median;
+  smallerThanMedian(X_plane, median);
+  if (median > param.motion_threshold) return vector<double>();
+
+  Matrix x_plane(2, X_plane.n);
+  x_plane.setMat(X_plane.getMat(1, 0, 2, -1), 0, 0);
+  const double sigma = median / 50.0;
+  const double weight = 1.0 / (2.0 * sigma * sigma);
+  const double threshold = median / param.motion_threshold;
+  const double best_d = findBestPlane(x_plane, threshold, weight);
+  t = t * param.height / best_d;
+
+  const double ry = asin(R.val[0][2]);
+  const double rx = asin(-R.val[1][2] / cos(ry));
+  const double rz = asin(-R.val[0][1] / cos(ry));
+  vector<double> tr(6);
+  tr[0] = rx; tr[1] = ry; tr[2] = rz;
+  tr[3] = t.val[0][0]; tr[4] = t.val[1][0]; tr[5] = t.val[2][0];
+  return tr;
+}
+
+Matrix VisualOdometryMono::smallerThanMedian(Matrix& X, double& median) {
+  vector<double> dist(X.n);
+  vector<int32_t> idx(X.n);
+  for (int32_t i = 0; i < X.n; i++) dist[i] = fabs(X.val[0][i]) + fabs(X.val[1][i]) + fabs(X.val[2][i]);
+  std::iota(idx.begin(), idx.end(), 0);
+  std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return dist[a] < dist[b]; });
+  const int32_t half = (int32_t)idx.size() / 2;
+  median = dist[idx[half]];
+  Matrix X_small(4, half + 1);
+  for (int32_t j = 0; j <= half; j++)
+    for (int32_t i = 0; i < 4; i++) X_small.val[i][j] = X.val[i][idx[j]];
+  return X_small;
+}
+
+// Hartley normalisation.  The sums are accumulated in double but every intermediate coordinate is written back
+// into the float fields of p_match, exactly like the reference (viso_mono.cpp:217-263): the rounding matters for
+// the RANSAC inputs.
+bool VisualOdometryMono::normalizeFeaturePoints(vector<Matcher::p_match>& p_matched, Matrix& Tp, Matrix& Tc) {
+  const double n = (double)p_matched.size();
+  double cpu = 0, cpv = 0, ccu = 0, ccv = 0;
+  for (const Matcher::p_match& m : p_matched) { cpu += m.u1p; cpv += m.v1p; ccu += m.u1c; ccv += m.v1c; }
+  cpu /= n; cpv /= n; ccu /= n; ccv /= n;
+  for (Matcher::p_match& m : p_matched) { m.u1p -= cpu; m.v1p -= cpv; m.u1c -= ccu; m.v1c -= ccv; }
+  double sp = 0, sc = 0;
+  for (const Matcher::p_match& m : p_matched) {
+    sp += std::sqrt(m.u1p * m.u1p + m.v1p * m.v1p);      // float sqrt of a float sum, as in the reference
+    sc += std::sqrt(m.u1c * m.u1c + m.v1c * m.v1c);
+  }
+  if (fabs(sp) < 1e-10 || fabs(sc) < 1e-10) return false;
+  sp = sqrt(2.0) * n / sp;
+  sc = sqrt(2.0) * n / sc;
+  for (Matcher::p_match& m : p_matched) { m.u1p *= sp; m.v1p *= sp; m.u1c *= sc; m.v1c *= sc; }
+  double Tp_data[9] = {sp, 0, -sp * cpu, 0, sp, -sp * cpv, 0, 0, 1};
+  double Tc_data[9] = {sc, 0, -sc * ccu, 0, sc, -sc * ccv, 0, 0, 1};
+  Tp = Matrix(3, 3, Tp_data);
+  Tc = Matrix(3, 3, Tc_data);
+  return true;
+}
+
+void VisualOdometryMono::EtoRt(Matrix& E, Matrix& K, vector<Matcher::p_match>& p_matched, Matrix& X, Matrix& R, Matrix& t) {
+  double W_data[9] = {0, -1, 0, +1, 0, 0, 0, 0, 1};
+  double Z_data[9] = {0, +1, 0, -1, 0, 0, 0, 0, 0};
+  Matrix W(3, 3, W_data), Z(3, 3, Z_data);
+  Matrix U, S, V;
+  E.svd(U, S, V);
+  Matrix T = U * Z * ~U;
+  Matrix Ra = U * W * (~V);
+  Matrix Rb = U * (~W) * (~V);
+  t = Matrix(3, 1);
+  t.val[0][0] = T.val[2][1]; t.val[1][0] = T.val[0][2]; t.val[2][0] = T.val[1][0];
+  if (Ra.det() < 0) Ra = -Ra;
+  if (Rb.det() < 0) Rb = -Rb;
+  // four (R, t) candidates, keep the one with most points in front of both cameras (first wins on ties)
+  Matrix Rs[4] = {Ra, Ra, Rb, Rb};
+  Matrix ts[4] = {t, -t, t, -t};
+  Matrix X_curr;
+  int32_t max_inliers = 0;
+  for (int32_t i = 0; i < 4; i++) {
+    const int32_t num = triangulateChieral(p_matched, K, Rs[i], ts[i], X_curr);
+    if (num > max_inliers) { max_inliers = num; X = X_curr; R = Rs[i]; t = ts[i]; }
+  }
+}
+
+int32_t VisualOdometryMono::triangulateChieral(vector<Matcher::p_match>& p_matched, Matrix& K, Matrix& R, Matrix& t, Matrix& X) {
+  X = Matrix(4, (int32_t)p_matched.size());
+  Matrix P1(3, 4), P2(3, 4);
+  P1.setMat(K, 0, 0);
+  P2.setMat(R, 0, 0);
+  P2.setMat(t, 0, 3);
+  P2 = K * P2;
+  Matrix J(4, 4), U, S, V;
+  for (int32_t i = 0; i < (int32_t)p_matched.size(); i++) {
+    const Matcher::p_match& m = p_matched[i];
+    for (int32_t j = 0; j < 4; j++) {
+      J.val[0][j] = P1.val[2][j] * m.u1p - P1.val[0][j];
+      J.val[1][j] = P1.val[2][j] * m.v1p - P1.val[1][j];
+      J.val[2][j] = P2.val[2][j] * m.u1c - P2.val[0][j];
+      J.val[3][j] = P2.val[2][j] * m.v1c - P2.val[1][j];
+    }
+    J.svd(U, S, V);
+    for (int32_t r = 0; r < 4; r++) X.val[r][i] = V.val[r][3];
+  }
+  Matrix AX1 = P1 * X, BX1 = P2 * X;
+  int32_t num = 0;
+  for (int32_t i = 0; i < X.n; i++)
+    if (AX1.val[2][i] * X.val[3][i] > 0 && BX1.val[2][i] * X.val[3][i] > 0) num++;
+  return num;
+}

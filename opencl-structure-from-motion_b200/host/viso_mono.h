@@ -1,0 +1,46 @@
+// Monocular visual odometry with the reference's interface (viso/viso_mono.h:27-88).  The RANSAC step
+// (ransacEstimateF, the reference's accelerator hook viso_mono.h:74 / viso_mono_cl.cpp:153-194) runs on the GPU
+// through visocu_ransac_F; the remaining pose recovery stays on the host for now.
+#ifndef VISOB_VISO_MONO_H
+#define VISOB_VISO_MONO_H
+#include "viso.h"
+
+class VisualOdometryMono : public VisualOdometry {
+public:
+  struct parameters : public VisualOdometry::parameters {
+    double height;            // camera height above ground (meters)
+    double pitch;             // camera pitch (rad, negative=pointing down)
+    int32_t ransac_iters;     // number of RANSAC iterations
+    double inlier_threshold;  // fundamental matrix inlier threshold
+    double motion_threshold;  // directly return false on small motions
+    parameters() {
+      height = 1.0; pitch = 0.0; ransac_iters = 2000; inlier_threshold = 0.00001; motion_threshold = 100.0;
+    }
+  };
+
+  VisualOdometryMono(parameters param);
+  ~VisualOdometryMono();
+
+  // returns false if the motion is too small or an error occurred; valid after two calls
+  bool process(uint8_t* I, uint32_t* dims, bool replace = false);
+
+  // extensions for tests / the batch runner
+  bool processDevice(const uint8_t* d_I, uint32_t* dims, bool replace = false);
+  const Matrix& lastF() const { return F_last; }
+  const std::vector<int>& lastSamples() const { return samples_last; }
+
+private:
+  virtual Matrix ransacEstimateF(const std::vector<Matcher::p_match>& p_matched);
+  virtual double findBestPlane(const Matrix& x_plane, double threshold, double weight);
+  std::vector<double> estimateMotion(std::vector<Matcher::p_match> p_matched);
+  Matrix smallerThanMedian(Matrix& X, double& median);
+  bool normalizeFeaturePoints(std::vector<Matcher::p_match>& p_matched, Matrix& Tp, Matrix& Tc);
+  void EtoRt(Matrix& E, Matrix& K, std::vector<Matcher::p_match>& p_matched, Matrix& X, Matrix& R, Matrix& t);
+  int32_t triangulateChieral(std::vector<Matcher::p_match>& p_matched, Matrix& K, Matrix& R, Matrix& t, Matrix& X);
+
+protected:
+  const parameters param;
+  Matrix F_last;
+  std::vector<int> samples_last;
+};
+#endif

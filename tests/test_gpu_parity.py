@@ -25,6 +25,18 @@ def valid(plane, w):
     return plane[2:-2, 2:w - 2]
 
 
+def same_records(got, want, wm, scale):
+    """Feature records are compared bit-exactly, except for the last descriptor word of a maximum sitting at
+    u = w-7: its two samples at u+5 read Sobel column w-2, which in the reference depends on the uninitialised
+    pad bytes behind each image row (matcher.cpp:170-174), so the reference itself is not reproducible there."""
+    if got.shape != want.shape:
+        return False
+    g, r = got.copy(), want.copy()
+    edge = (r[:, 0] // scale) >= wm - 7
+    g[edge, 11] = 0; r[edge, 11] = 0
+    return np.array_equal(g, r)
+
+
 CASES = [
     dict(width=1241, height=376, half_resolution=1),
     dict(width=1241, height=376, half_resolution=0),
@@ -48,9 +60,10 @@ def test_features_match_reference(ctx, ref, case):
     rc = rm.counts()
     assert (ns.tolist(), nd.tolist()) == ([rc['1p1'], rc['1c1']], [rc['1p2'], rc['1c2']])
     for frame, tag in ((0, '1p'), (1, '1c')):
+        scale = 2 if vp.half_resolution else 1
         if vp.multi_stage:
-            assert np.array_equal(ctx.features(frame, 0), rm.maxima(tag + '1')), 'sparse records differ'
-        assert np.array_equal(ctx.features(frame, 1), rm.maxima(tag + '2')), 'dense records differ'
+            assert same_records(ctx.features(frame, 0), rm.maxima(tag + '1'), w // scale, scale), 'sparse records differ'
+        assert same_records(ctx.features(frame, 1), rm.maxima(tag + '2'), w // scale, scale), 'dense records differ'
         du, dv, (rw, rh, rbpl) = rm.sobel(tag)
         gdu, (gw, gh, gbpl) = ctx.plane(frame, 0)
         gdv, _ = ctx.plane(frame, 1)
@@ -138,8 +151,9 @@ def test_quad_matching_two_pass(ctx, ref, half):
     rm.push(lp, rpv); rm.push(lc, rc)
     ctx.configure(vp, w, h, 4)
     ctx.push_frames([0, 1, 2, 3], [lp, rpv, lc, rc])
+    scale = 2 if half else 1
     for frame, tag in ((0, '1p2'), (1, '2p2'), (2, '1c2'), (3, '2c2')):
-        assert np.array_equal(ctx.features(frame, 1), rm.maxima(tag))
+        assert same_records(ctx.features(frame, 1), rm.maxima(tag), w // scale, scale)
     quad = (0, 1, 2, 3)
     want1 = rm.matching(0, 2, False)
     got1 = ctx.match([quad], 2, 0)[0]
