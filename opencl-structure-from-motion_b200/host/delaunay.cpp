@@ -74,6 +74,36 @@ struct Mesh {
   }
 };
 
+// x(n+1) = (1366 x(n) + 150889) mod 714025, scaled to [0, choices)
+struct PivotSource {
+  unsigned long long seed = 1;
+  int next(unsigned choices) {
+    seed = (seed * 1366ull + 150889ull) % 714025ull;
+    return (int)(seed / (714025ull / choices + 1));
+  }
+};
+
+bool before_xy(const Mesh& m, int a, int px, int py) { return m.px[a] < px || (m.px[a] == px && m.py[a] < py); }
+bool after_xy(const Mesh& m, int a, int px, int py) { return m.px[a] > px || (m.px[a] == px && m.py[a] > py); }
+
+void pivot_quicksort(const Mesh& m, int* a, int n, PivotSource& rnd) {
+  if (n < 2) return;
+  if (n == 2) {
+    if (after_xy(m, a[0], m.px[a[1]], m.py[a[1]])) std::swap(a[0], a[1]);
+    return;
+  }
+  const int pv = a[rnd.next((unsigned)n)];
+  const int px = m.px[pv], py = m.py[pv];
+  int left = -1, right = n;
+  while (left < right) {
+    do { left++; } while (left <= right && before_xy(m, a[left], px, py));
+    do { right--; } while (left <= right && after_xy(m, a[right], px, py));
+    if (left < right) std::swap(a[left], a[right]);
+  }
+  if (left > 1) pivot_quicksort(m, a, left, rnd);
+  if (right < n - 2) pivot_quicksort(m, a + right + 1, n - right - 1, rnd);
+}
+
 struct Handles { int ldo, rdo; };   // ccw hull edge out of the leftmost vertex, cw hull edge out of the rightmost
 
 bool less_axis(const Mesh& m, int a, int b, int axis) {
@@ -185,14 +215,14 @@ void delaunay_triangles(const int32_t* x, const int32_t* y, int n, std::vector<i
   Mesh m;
   m.px = x; m.py = y;
   m.org.reserve(8 * (size_t)n); m.onext.reserve(8 * (size_t)n); m.oprev.reserve(8 * (size_t)n); m.dead.reserve(8 * (size_t)n);
-  // sort by (x, y); of several input points on the same pixel only one takes part (Triangle ignores duplicates)
+  // sort by (x, y); of several input points on the same pixel only one takes part (Triangle ignores duplicates).
+  // Which of the duplicates survives depends on the order an unstable sort leaves them in, and removeOutliers
+  // keeps exactly the survivor, so the sort is the same randomised quicksort (Hoare partition, pivots from the
+  // generator seeded with 1) that the reference's triangulation uses.
   std::vector<int> v(n);
   for (int i = 0; i < n; i++) v[i] = i;
-  std::sort(v.begin(), v.end(), [&](int a, int b) {
-    if (x[a] != x[b]) return x[a] < x[b];
-    if (y[a] != y[b]) return y[a] < y[b];
-    return a < b;
-  });
+  PivotSource pivots;
+  pivot_quicksort(m, v.data(), n, pivots);
   int k = 0;
   for (int i = 1; i < n; i++)
     if (x[v[i]] != x[v[k]] || y[v[i]] != y[v[k]]) v[++k] = v[i];

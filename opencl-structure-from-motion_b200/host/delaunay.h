@@ -6,7 +6,7 @@
 
 namespace visob {
 // tri receives 3 indices (into x/y) per triangle, counter-clockwise.  Coordinates must satisfy |x|,|y| < 2^15.
-// Of several points with identical coordinates only the one with the lowest index is triangulated.
+// Of several points with identical coordinates only one is triangulated (the one the reference would keep).
 void delaunay_triangles(const int32_t* x, const int32_t* y, int n, std::vector<int32_t>& tri);
 }
 #endif
