@@ -124,6 +124,13 @@ int  visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* const* uv, co
                      double* F9, uint8_t* const* inlier_mask, int32_t* n_inliers, int32_t* best_iter,
                      int32_t* const* counts, double* const* F_all);
 
+/* host<->device bytes copied by this context since creation (bench.py's h2d / d2h bytes per step) */
+int  visocu_transfer_bytes(const visocu_ctx* ctx, uint64_t* h2d, uint64_t* d2h);
+/* event timing of the fused filter+NMS launches on the context's stream (replaces the per-call
+ * Container::durationOfEvent prints of viso_mono_cl.cpp:245-248).  While enabled every fused launch is
+ * followed by an event synchronise; read = accumulated milliseconds, launches and frames since enable. */
+int  visocu_profile(visocu_ctx* ctx, int32_t enable);
+int  visocu_profile_read(const visocu_ctx* ctx, double* filter_ms, uint64_t* launches, uint64_t* frames);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int  visocu_launch_count(const visocu_ctx* ctx, uint64_t* n);
 

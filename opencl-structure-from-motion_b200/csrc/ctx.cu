@@ -65,6 +65,8 @@ extern "C" void visocu_destroy(visocu_ctx* ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
+  if (ctx->pev0) cudaEventDestroy(ctx->pev0);
+  if (ctx->pev1) cudaEventDestroy(ctx->pev1);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -174,7 +176,7 @@ extern "C" int visocu_configure(visocu_ctx* ctx, const visocu_params* p, int32_t
     F.counts = (int32_t*)(base + o_cnt);
   }
   CU_TRY(ctx, cudaMalloc(&ctx->frames_d, sizeof(FrameDev) * (size_t)n_frames));
-  CU_TRY(ctx, cudaMemcpyAsync(ctx->frames_d, ctx->frames_h.data(), sizeof(FrameDev) * (size_t)n_frames, cudaMemcpyHostToDevice, ctx->stream));
+  CU_COPY(ctx, ctx->frames_d, ctx->frames_h.data(), sizeof(FrameDev) * (size_t)n_frames, cudaMemcpyHostToDevice);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->n_frames = n_frames;
   ctx->h_counts.assign((size_t)n_frames * 2, 0);
@@ -229,8 +231,29 @@ extern "C" int visocu_device_free(visocu_ctx* ctx, void* p) {
 extern "C" int visocu_memcpy_h2d(visocu_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (!ctx) return VISOCU_EINVAL;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  CU_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU_COPY(ctx, dst, src, bytes, cudaMemcpyHostToDevice);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return VISOCU_OK;
+}
+extern "C" int visocu_transfer_bytes(const visocu_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {
+  if (!ctx) return VISOCU_EINVAL;
+  if (h2d) *h2d = ctx->h2d_bytes;
+  if (d2h) *d2h = ctx->d2h_bytes;
+  return VISOCU_OK;
+}
+extern "C" int visocu_profile(visocu_ctx* ctx, int32_t enable) {
+  if (!ctx) return VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (enable && !ctx->pev0) { CU_TRY(ctx, cudaEventCreate(&ctx->pev0)); CU_TRY(ctx, cudaEventCreate(&ctx->pev1)); }
+  ctx->profile = enable ? 1 : 0;
+  ctx->filter_ms = 0; ctx->filter_launches = 0; ctx->filter_frames = 0;
+  return VISOCU_OK;
+}
+extern "C" int visocu_profile_read(const visocu_ctx* ctx, double* filter_ms, uint64_t* launches, uint64_t* frames) {
+  if (!ctx) return VISOCU_EINVAL;
+  if (filter_ms) *filter_ms = ctx->filter_ms;
+  if (launches) *launches = ctx->filter_launches;
+  if (frames) *frames = ctx->filter_frames;
   return VISOCU_OK;
 }
 extern "C" int visocu_launch_count(const visocu_ctx* ctx, uint64_t* n) {
@@ -255,7 +278,7 @@ extern "C" int visocu_frame_counts(visocu_ctx* ctx, int32_t n, const int32_t* fr
   if ((rc = visocu_ensure_pinned(ctx, (size_t)n * 16))) return rc;
   int32_t* stage = (int32_t*)ctx->pinned;
   for (int i = 0; i < n; i++)
-    CU_TRY(ctx, cudaMemcpyAsync(stage + 4 * i, ctx->frames_h[frames[i]].counts, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_COPY(ctx, stage + 4 * i, ctx->frames_h[frames[i]].counts, 16, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < n; i++) {
     if (stage[4 * i + 2]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "feature list of frame %d overflowed", frames[i]);
@@ -286,6 +309,7 @@ extern "C" int visocu_push_frames(visocu_ctx* ctx, int32_t n, const int32_t* fra
       // row-wise copy into the 16-byte stride (matcher.cpp:163-175); pad columns stay zero
       CU_TRY(ctx, cudaMemcpy2DAsync(ctx->frames_h[f].img, g.bpl, imgs[start + i], bpl_in, g.w, g.h,
                                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+      if (!on_device) ctx->h2d_bytes += (uint64_t)g.w * g.h;
       ctx->frame_valid[f] = 1;
     }
     if ((rc = visocu_launch_features(ctx, sl))) return rc;
@@ -305,7 +329,7 @@ extern "C" int visocu_get_features(visocu_ctx* ctx, int32_t frame, int32_t pass,
   if (!out12) return VISOCU_OK;
   if (cap < n) return visocu_set_error(ctx, VISOCU_ECAPACITY, "need room for %d records", n);
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if (n > 0) CU_TRY(ctx, cudaMemcpyAsync(out12, ctx->frames_h[frame].rec[pass], (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n > 0) CU_COPY(ctx, out12, ctx->frames_h[frame].rec[pass], (size_t)n * 48, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return VISOCU_OK;
 }
@@ -333,7 +357,7 @@ extern "C" int visocu_get_plane(visocu_ctx* ctx, int32_t frame, int32_t which, u
   size_t bytes = (size_t)bpl * h;
   if (cap < bytes) return visocu_set_error(ctx, VISOCU_ECAPACITY, "plane needs %zu bytes", bytes);
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  CU_TRY(ctx, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_COPY(ctx, out, src, bytes, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return VISOCU_OK;
 }

@@ -446,8 +446,17 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
       ctx->filter_smem_attr = smem;
     }
     dim3 grid((g.bplm + TW - 1) / TW, (g.hm + TH - 1) / TH, sl.n);
+    if (ctx->profile) CU_TRY(ctx, cudaEventRecord(ctx->pev0, st));
     k_filter_nms<<<grid, FILTER_THREADS, smem, st>>>(g, ctx->frames_d, sl, nmax);
     CU_LAUNCH_CHECK(ctx);
+    if (ctx->profile) {
+      // profiling mode only: this synchronises the stream after every fused launch
+      float ms = 0;
+      CU_TRY(ctx, cudaEventRecord(ctx->pev1, st));
+      CU_TRY(ctx, cudaEventSynchronize(ctx->pev1));
+      CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->pev0, ctx->pev1));
+      ctx->filter_ms += ms; ctx->filter_launches++; ctx->filter_frames += sl.n;
+    }
   }
   int maxchunk = 1;
   for (int p = g.first_pass; p < 2; p++) {

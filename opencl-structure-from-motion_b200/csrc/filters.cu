@@ -114,15 +114,15 @@ int run_filter(visocu_ctx* ctx, const uint8_t* in, uint8_t* oa, uint8_t* ob, int
   uint8_t* d_a = d_in + na;
   uint8_t* d_b = d_a + na;
   int16_t* d_16 = (int16_t*)(d_b + na);
-  CU_TRY(ctx, cudaMemcpyAsync(d_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
+  CU_COPY(ctx, d_in, in, n, cudaMemcpyHostToDevice);
   dim3 b(32, 8), g((w + 31) / 32, (h + 7) / 8);
   k_filter_plain<<<g, b, 0, ctx->stream>>>(d_in, d_a, d_b, d_16, w, h, mode);
   CU_LAUNCH_CHECK(ctx);
   if (mode <= 1) {
-    CU_TRY(ctx, cudaMemcpyAsync(oa, d_a, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(ob, d_b, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_COPY(ctx, oa, d_a, n, cudaMemcpyDeviceToHost);
+    CU_COPY(ctx, ob, d_b, n, cudaMemcpyDeviceToHost);
   } else {
-    CU_TRY(ctx, cudaMemcpyAsync(o16, d_16, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_COPY(ctx, o16, d_16, n * 2, cudaMemcpyDeviceToHost);
   }
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return VISOCU_OK;
@@ -162,12 +162,12 @@ extern "C" int visocu_nms(visocu_ctx* ctx, const int16_t* f1, const int16_t* f2,
   int16_t* d1 = (int16_t*)ctx->scratch;
   int16_t* d2 = (int16_t*)((uint8_t*)ctx->scratch + plane);
   uint32_t* dc = (uint32_t*)((uint8_t*)ctx->scratch + 2 * plane);
-  CU_TRY(ctx, cudaMemcpyAsync(d1, f1, (size_t)bpl * h * 2, cudaMemcpyHostToDevice, ctx->stream));
-  CU_TRY(ctx, cudaMemcpyAsync(d2, f2, (size_t)bpl * h * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CU_COPY(ctx, d1, f1, (size_t)bpl * h * 2, cudaMemcpyHostToDevice);
+  CU_COPY(ctx, d2, f2, (size_t)bpl * h * 2, cudaMemcpyHostToDevice);
   k_nms_plain<<<(unsigned)((cells + 127) / 128), 128, 0, ctx->stream>>>(d1, d2, w, h, bpl, nms_n, tau, ncx, ncy, dc);
   CU_LAUNCH_CHECK(ctx);
   std::vector<uint32_t> codes(cells);
-  CU_TRY(ctx, cudaMemcpyAsync(codes.data(), dc, cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_COPY(ctx, codes.data(), dc, cells * 4, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   // expand the per-cell code words into the reference's (u, v, val, class) list, cell-column-major
   int n = 0;

@@ -335,13 +335,13 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
       if (use_prior) {
         if (!ranges[start + j]) return visocu_set_error(ctx, VISOCU_EINVAL, "job %d has no ranges", start + j);
         memcpy(pin + pin_off, ranges[start + j], (size_t)nstat * sizeof(visocu_range));
-        CU_TRY(ctx, cudaMemcpyAsync(sb + o_rng[j], pin + pin_off, (size_t)nstat * sizeof(visocu_range), cudaMemcpyHostToDevice, ctx->stream));
+        CU_COPY(ctx, sb + o_rng[j], pin + pin_off, (size_t)nstat * sizeof(visocu_range), cudaMemcpyHostToDevice);
         pin_off += align_up((size_t)nstat * sizeof(visocu_range), 256);
         hj[j].ranges = (const visocu_range*)(sb + o_rng[j]);
       }
     }
     memcpy(pin, hj.data(), sizeof(MatchJob) * nb);
-    CU_TRY(ctx, cudaMemcpyAsync(sb, pin, sizeof(MatchJob) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    CU_COPY(ctx, sb, pin, sizeof(MatchJob) * nb, cudaMemcpyHostToDevice);
     const MatchJob* dj = (const MatchJob*)sb;
     int32_t* pin_cnt = (int32_t*)(pin + pin_off);
     if (maxq > 0) {
@@ -360,13 +360,13 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
       k_refine<<<gr, 256, 0, ctx->stream>>>(g, dj, method, nullptr, 0);
       CU_LAUNCH_CHECK(ctx);
     }
-    for (int j = 0; j < nb; j++) CU_TRY(ctx, cudaMemcpyAsync(pin_cnt + j, hj[j].n_out, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int j = 0; j < nb; j++) CU_COPY(ctx, pin_cnt + j, hj[j].n_out, 4, cudaMemcpyDeviceToHost);
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (int j = 0; j < nb; j++) {
       const int n = pin_cnt[j];
       n_out[start + j] = n;
       if (n > cap[start + j]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "job %d produced %d matches, room for %d", start + j, n, cap[start + j]);
-      if (n > 0) CU_TRY(ctx, cudaMemcpyAsync(out[start + j], hj[j].out, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+      if (n > 0) CU_COPY(ctx, out[start + j], hj[j].out, (size_t)n * 48, cudaMemcpyDeviceToHost);
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   }
@@ -386,12 +386,12 @@ extern "C" int visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t me
   if ((rc = visocu_ensure_scratch(ctx, o_list + (size_t)n * 48))) return rc;
   uint8_t* sb = (uint8_t*)ctx->scratch;
   visocu_pmatch* d_list = (visocu_pmatch*)(sb + o_list);
-  CU_TRY(ctx, cudaMemcpyAsync(sb, &J, sizeof J, cudaMemcpyHostToDevice, ctx->stream));
-  CU_TRY(ctx, cudaMemcpyAsync(d_list, inout, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
+  CU_COPY(ctx, sb, &J, sizeof J, cudaMemcpyHostToDevice);
+  CU_COPY(ctx, d_list, inout, (size_t)n * 48, cudaMemcpyHostToDevice);
   int gx = (n + 7) / 8; if (gx > 4096) gx = 4096;
   k_refine<<<dim3(gx, 1), 256, 0, ctx->stream>>>(ctx->g, (const MatchJob*)sb, method, d_list, n);
   CU_LAUNCH_CHECK(ctx);
-  CU_TRY(ctx, cudaMemcpyAsync(inout, d_list, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_COPY(ctx, inout, d_list, (size_t)n * 48, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return VISOCU_OK;
 }
@@ -400,7 +400,7 @@ extern "C" int visocu_match_stats(visocu_ctx* ctx, uint64_t* sad_candidates, uin
   if (!ctx) return VISOCU_EINVAL;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   uint64_t now[2];
-  CU_TRY(ctx, cudaMemcpyAsync(now, ctx->d_stats, sizeof now, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_COPY(ctx, now, ctx->d_stats, sizeof now, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (sad_candidates) *sad_candidates = now[0] - ctx->h_stats[0];
   if (entries_scanned) *entries_scanned = now[1] - ctx->h_stats[1];

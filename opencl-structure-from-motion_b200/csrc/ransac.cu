@@ -398,15 +398,15 @@ extern "C" int visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* con
       hj[j].mask = sb + o_mask[j]; hj[j].inl = (int32_t*)(sb + o_inl[j]); hj[j].A = (double*)(sb + o_A[j]);
       hj[j].F9 = (double*)(sb + o_out[j]); hj[j].n_inl = (int32_t*)(sb + o_n[j]);
       memcpy(pin + po, uv[start + j], (size_t)n * 16);
-      CU_TRY(ctx, cudaMemcpyAsync(sb + o_uv[j], pin + po, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+      CU_COPY(ctx, sb + o_uv[j], pin + po, (size_t)n * 16, cudaMemcpyHostToDevice);
       po += align_up((size_t)n * 16, 256);
       memcpy(pin + po, samples[start + j], (size_t)iters * 32);
-      CU_TRY(ctx, cudaMemcpyAsync(sb + o_smp[j], pin + po, (size_t)iters * 32, cudaMemcpyHostToDevice, ctx->stream));
+      CU_COPY(ctx, sb + o_smp[j], pin + po, (size_t)iters * 32, cudaMemcpyHostToDevice);
       po += align_up((size_t)iters * 32, 256);
       CU_TRY(ctx, cudaMemsetAsync(sb + o_cnt[j], 0, (size_t)iters * 4, ctx->stream));
     }
     memcpy(pin, hj.data(), sizeof(RansacJob) * nb);
-    CU_TRY(ctx, cudaMemcpyAsync(sb, pin, sizeof(RansacJob) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    CU_COPY(ctx, sb, pin, sizeof(RansacJob) * nb, cudaMemcpyHostToDevice);
     const RansacJob* dj = (const RansacJob*)sb;
     k_hypotheses<<<dim3((iters + 3) / 4, nb), 128, 0, ctx->stream>>>(dj, iters);
     CU_LAUNCH_CHECK(ctx);
@@ -419,14 +419,14 @@ extern "C" int visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* con
     double* pinF = (double*)(pin + po);
     int32_t* pinN = (int32_t*)(pin + po + align_up((size_t)nb * 72, 256));
     for (int j = 0; j < nb; j++) {
-      CU_TRY(ctx, cudaMemcpyAsync(pinF + 9 * j, hj[j].F9, 72, cudaMemcpyDeviceToHost, ctx->stream));
-      CU_TRY(ctx, cudaMemcpyAsync(pinN + 2 * j, hj[j].n_inl, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CU_COPY(ctx, pinF + 9 * j, hj[j].F9, 72, cudaMemcpyDeviceToHost);
+      CU_COPY(ctx, pinN + 2 * j, hj[j].n_inl, 8, cudaMemcpyDeviceToHost);
       if (inlier_mask && inlier_mask[start + j])
-        CU_TRY(ctx, cudaMemcpyAsync(inlier_mask[start + j], hj[j].mask, (size_t)hj[j].N, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_COPY(ctx, inlier_mask[start + j], hj[j].mask, (size_t)hj[j].N, cudaMemcpyDeviceToHost);
       if (counts && counts[start + j])
-        CU_TRY(ctx, cudaMemcpyAsync(counts[start + j], hj[j].counts, (size_t)iters * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_COPY(ctx, counts[start + j], hj[j].counts, (size_t)iters * 4, cudaMemcpyDeviceToHost);
       if (F_all && F_all[start + j])
-        CU_TRY(ctx, cudaMemcpyAsync(F_all[start + j], hj[j].F_all, (size_t)iters * 72, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_COPY(ctx, F_all[start + j], hj[j].F_all, (size_t)iters * 72, cudaMemcpyDeviceToHost);
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (int j = 0; j < nb; j++) {

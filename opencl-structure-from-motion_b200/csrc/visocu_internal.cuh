@@ -56,6 +56,10 @@ struct visocu_ctx {
   void* pinned = nullptr;  size_t pinned_bytes = 0;
   uint64_t launches = 0;
   size_t filter_smem_attr = 0;       // dynamic shared memory opted in for the fused kernel on this device
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;   // host<->device traffic issued by this context
+  int profile = 0;                   // time the fused filter+NMS launches with events (visocu_profile)
+  cudaEvent_t pev0 = nullptr, pev1 = nullptr;
+  double filter_ms = 0; uint64_t filter_launches = 0, filter_frames = 0;
   uint64_t* d_stats = nullptr;       // [0] SAD candidates, [1] entries scanned
   uint64_t h_stats[2] = {0, 0};
 };
@@ -70,6 +74,14 @@ int visocu_ensure_pinned(visocu_ctx* ctx, size_t bytes);
     if (e__ != cudaSuccess)                                                                      \
       return visocu_set_error((ctx), VISOCU_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, \
                               cudaGetErrorString(e__));                                          \
+  } while (0)
+
+// async copy on the context's stream with byte accounting (bench.py reports h2d / d2h bytes per step)
+#define CU_COPY(ctx, dst, src, bytes, kind)                                                   \
+  do {                                                                                        \
+    if ((kind) == cudaMemcpyHostToDevice) (ctx)->h2d_bytes += (uint64_t)(bytes);               \
+    else if ((kind) == cudaMemcpyDeviceToHost) (ctx)->d2h_bytes += (uint64_t)(bytes);          \
+    CU_TRY((ctx), cudaMemcpyAsync((dst), (src), (bytes), (kind), (ctx)->stream));             \
   } while (0)
 
 #define CU_LAUNCH_CHECK(ctx)                  \

@@ -225,6 +225,13 @@ VISOB_API void visob_runner_get_motion(void* h, int seq, double* out16) {
   Matrix T = r->monos[seq]->getMotion();
   for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out16[4 * i + j] = T.val[i][j];
 }
+VISOB_API void visob_runner_transfer_bytes(void* h, uint64_t* h2d, uint64_t* d2h) {
+  Runner* r = (Runner*)h;
+  uint64_t a = 0, b = 0, x = 0, y = 0;
+  for (Matcher* m : r->matchers) if (m->context() && visocu_transfer_bytes(m->context(), &x, &y) == 0) { a += x; b += y; }
+  for (MonoAccess* v : r->monos) if (v->getMatcher()->context() && visocu_transfer_bytes(v->getMatcher()->context(), &x, &y) == 0) { a += x; b += y; }
+  *h2d = a; *d2h = b;
+}
 VISOB_API uint64_t visob_runner_launches(void* h) {
   Runner* r = (Runner*)h;
   uint64_t total = 0, n = 0;

@@ -227,3 +227,8 @@ class Runner:
 
     def launches(self):
         return int(lib().visob_runner_launches(self.h))
+
+    def transfer_bytes(self):
+        a = C.c_uint64(); b = C.c_uint64()
+        lib().visob_runner_transfer_bytes(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value

@@ -102,6 +102,19 @@ class Context:
         self._ck(lib().visocu_launch_count(self.h, C.byref(n)), 'launch_count')
         return n.value
 
+    def transfer_bytes(self):
+        a = C.c_uint64(); b = C.c_uint64()
+        self._ck(lib().visocu_transfer_bytes(self.h, C.byref(a), C.byref(b)), 'transfer_bytes')
+        return a.value, b.value
+
+    def profile(self, enable=True):
+        self._ck(lib().visocu_profile(self.h, int(enable)), 'profile')
+
+    def profile_read(self):
+        ms = C.c_double(); n = C.c_uint64(); f = C.c_uint64()
+        self._ck(lib().visocu_profile_read(self.h, C.byref(ms), C.byref(n), C.byref(f)), 'profile_read')
+        return ms.value, n.value, f.value
+
     def device_alloc(self, nbytes):
         p = C.c_void_p()
         self._ck(lib().visocu_device_alloc(self.h, C.c_size_t(nbytes), C.byref(p)), 'device_alloc')

@@ -11,11 +11,24 @@ import host_py as H
 pytestmark = pytest.mark.gpu
 
 
+def pad_safe_width(w, nms_n, half):
+    """True if no maximum can sit at u = w-7, where the reference's descriptor depends on uninitialised pad bytes
+    (SURVEY.md 8c caveat 3): (w - 2n - 13) mod (n+1) != 0 for the sparse and the dense neighbourhood size."""
+    wm = w // 2 if half else w
+    ns = nms_n * 3
+    if ns > 10:
+        ns = max(nms_n, 10)
+    return all((wm - 2 * n - 13) % (n + 1) != 0 for n in (ns, nms_n))
+
+
 @pytest.mark.parametrize('kw', [dict(), dict(half_resolution=0), dict(multi_stage=0), dict(nms_n=4, half_resolution=0),
                                 dict(refinement=0)],
                          ids=['defaults', 'fullres', 'singlestage', 'nms4', 'norefine'])
 def test_matcher_flow_final_list(ref, kw):
-    a, b = synth.blob_pair(1241, 376, seed=41)
+    p = V.Params(**kw)
+    width = 1241 if pad_safe_width(1241, p.nms_n, p.half_resolution) else 1242
+    assert pad_safe_width(width, p.nms_n, p.half_resolution)
+    a, b = synth.blob_pair(width, 376, seed=41)
     rm = ref.matcher(pyref.MatcherParams(**kw)); hm = H.Matcher(V.Params(**kw))
     for m in (rm, hm):
         m.push(a); m.push(b); m.match_features(0)
@@ -49,7 +62,8 @@ def test_matcher_sequence_ring_buffer_and_replace(ref):
 
 
 def test_matcher_quad_final_list_and_bucketing(ref):
-    lp, rpv, lc, rc = synth.blob_quad(1241, 376, seed=45)
+    assert pad_safe_width(1242, 2, 0)
+    lp, rpv, lc, rc = synth.blob_quad(1242, 376, seed=45)
     kw = dict(nms_n=2, half_resolution=0)
     rm = ref.matcher(pyref.MatcherParams(**kw)); hm = H.Matcher(V.Params(**kw))
     for m in (rm, hm):
@@ -89,25 +103,32 @@ def _mono_params(lib, bucket_max):
     return pyref.MonoParams(match=pyref.MatcherParams(), **kw), H.MonoParams(match=V.Params(), **kw)
 
 
-def test_mono_odometry_sequence(ref_nofma):
+def test_mono_odometry_sequence(ref):
     """VisualOdometryMono::process over a short corridor drive.  Both sides draw the RANSAC samples from a fresh
     std::default_random_engine(71) and bucket with rand() after srand(0), so the sample tables coincide as long as
     the match lists do.  Tolerances: rotation entries 1e-6 absolute, translation 1e-6 relative."""
     seq = synth.corridor_sequence(4, seed=1234)
-    rp, hp = _mono_params(ref_nofma, 2)
-    rv = ref_nofma.mono(rp); hv = H.Mono(hp)
+    rp, hp = _mono_params(ref, 2)
+    # rand() is process-wide state: run the two implementations one after the other, each from its own srand(0)
+    rv = ref.mono(rp)
+    want = []
     for k in range(len(seq)):
-        ok_r = rv.process(seq[k]); ok_h = hv.process(seq[k])
+        ok = rv.process(seq[k])
+        want.append((ok, rv.matches(), rv.inliers(), rv.motion()))
+    del rv
+    hv = H.Mono(hp)
+    for k in range(len(seq)):
+        ok_h = hv.process(seq[k])
+        ok_r, a, inl, Tr = want[k]
         assert ok_r == ok_h
         if k == 0:
             continue
-        a, b = rv.matches(), hv.matches()
-        assert sorted(a.tolist()) == sorted(b.tolist())          # same bucketed set
-        if a.tobytes() != b.tobytes():
-            pytest.skip('rand() streams diverged (bucket order); set-level parity only')
         assert ok_r
-        assert np.array_equal(rv.inliers(), hv.inliers())
-        Tr, Th = rv.motion(), hv.motion()
+        b = hv.matches()
+        assert len(a) > 100
+        assert a.tobytes() == b.tobytes()                       # same bucketed list, same order
+        assert np.array_equal(inl, hv.inliers())
+        Th = hv.motion()
         assert np.abs(Tr[:3, :3] - Th[:3, :3]).max() < 1e-6
         assert np.abs(Tr[:3, 3] - Th[:3, 3]).max() < 1e-6 * max(1.0, np.abs(Tr[:3, 3]).max())
         assert abs(Th[2, 3]) > 0.3                               # the drive moves 0.8 m forward per frame
