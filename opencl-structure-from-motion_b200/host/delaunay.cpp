@@ -16,49 +16,54 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 
 namespace visob {
 namespace {
 
+struct HalfEdge { int32_t onext, oprev, org, dead; };
+
 struct Mesh {
   const int32_t* px;
   const int32_t* py;
-  std::vector<int32_t> onext, oprev, org;   // per directed edge; sym(e) = e ^ 1
-  std::vector<uint8_t> dead;
+  std::vector<HalfEdge> he;                 // per directed edge; sym(e) = e ^ 1
+  void set_points(const int32_t* x, const int32_t* y) { px = x; py = y; }
 
   int make_edge(int a, int b) {
-    int e = (int)org.size();
-    org.push_back(a); org.push_back(b);
-    onext.push_back(e); onext.push_back(e + 1);
-    oprev.push_back(e); oprev.push_back(e + 1);
-    dead.push_back(0); dead.push_back(0);
+    const int e = (int)he.size();
+    he.push_back(HalfEdge{e, e, a, 0});
+    he.push_back(HalfEdge{e + 1, e + 1, b, 0});
     return e;
   }
   static int sym(int e) { return e ^ 1; }
-  int dest(int e) const { return org[e ^ 1]; }
-  int lnext(int e) const { return oprev[e ^ 1]; }
-  int rprev(int e) const { return onext[e ^ 1]; }
+  int org(int e) const { return he[e].org; }
+  int dest(int e) const { return he[e ^ 1].org; }
+  int onext(int e) const { return he[e].onext; }
+  int oprev(int e) const { return he[e].oprev; }
+  int lnext(int e) const { return he[e ^ 1].oprev; }
+  int rprev(int e) const { return he[e ^ 1].onext; }
   // put the isolated half-edge e right after x in the counter-clockwise ring around x's origin
   void insert_after(int x, int e) {
-    int n = onext[x];
-    onext[e] = n; oprev[e] = x;
-    oprev[n] = e; onext[x] = e;
+    const int n = he[x].onext;
+    he[e].onext = n; he[e].oprev = x;
+    he[n].oprev = e; he[x].onext = e;
   }
   void unlink(int e) {
-    int n = onext[e], p = oprev[e];
-    onext[p] = n; oprev[n] = p;
-    onext[e] = oprev[e] = e;
+    const int n = he[e].onext, p = he[e].oprev;
+    he[p].onext = n; he[n].oprev = p;
+    he[e].onext = he[e].oprev = e;
   }
   // new edge from dest(a) to org(b) so that a, the new edge and b share their left face
   int connect(int a, int b) {
-    int e = make_edge(dest(a), org[b]);
+    int e = make_edge(dest(a), org(b));
     insert_after(lnext(a), e);
     insert_after(b, sym(e));
     return e;
   }
   void remove(int e) {
     unlink(e); unlink(sym(e));
-    dead[e] = dead[e ^ 1] = 1;
+    he[e].dead = he[e ^ 1].dead = 1;
   }
   // > 0 iff a, b, c make a left turn
   int64_t ccw(int a, int b, int c) const {
@@ -106,54 +111,57 @@ void pivot_quicksort(const Mesh& m, int* a, int n, PivotSource& rnd) {
 
 struct Handles { int ldo, rdo; };   // ccw hull edge out of the leftmost vertex, cw hull edge out of the rightmost
 
-bool less_axis(const Mesh& m, int a, int b, int axis) {
-  if (axis == 0) return m.px[a] != m.px[b] ? m.px[a] < m.px[b] : m.py[a] < m.py[b];
-  return m.py[a] != m.py[b] ? m.py[a] < m.py[b] : m.px[a] < m.px[b];
-}
-
 // The partition tree: halves by the node's axis, children by the other axis, leaves (<= 3 vertices) sorted by x.
-void partition(const Mesh& m, int* v, int n, int axis) {
-  if (n <= 3) axis = 0;
+// Vertices are numbered by their rank in (x, y) order.  Every node keeps its vertex set twice, once in x order (xl)
+// and once in (y, x) order (yl); a split takes the first half of the list of its axis and distributes the other list
+// stably with one linear pass, so no comparison sort is needed below the root.  On return xl holds the final order.
+void partition(int* xl, int* yl, int n, int axis, uint8_t* side, int* tmp) {
+  if (n <= 3) return;                       // xl is already the x-sorted leaf
   const int divider = n >> 1;
-  if (n <= 3) {
-    std::sort(v, v + n, [&](int a, int b) { return less_axis(m, a, b, 0); });
-    return;
+  int* from = axis == 0 ? xl : yl;          // list that defines the halves
+  int* other = axis == 0 ? yl : xl;
+  for (int i = 0; i < divider; i++) side[from[i]] = 0;
+  for (int i = divider; i < n; i++) side[from[i]] = 1;
+  int a = 0, b = 0;
+  for (int i = 0; i < n; i++) {
+    const int id = other[i];
+    if (side[id]) tmp[b++] = id; else other[a++] = id;
   }
-  std::nth_element(v, v + divider, v + n, [&](int a, int b) { return less_axis(m, a, b, axis); });
-  partition(m, v, divider, 1 - axis);
-  partition(m, v + divider, n - divider, 1 - axis);
+  for (int i = 0; i < b; i++) other[divider + i] = tmp[i];
+  partition(xl, yl, divider, 1 - axis, side, tmp);
+  partition(xl + divider, yl + divider, n - divider, 1 - axis, side, tmp);
 }
 
 Handles merge(Mesh& m, Handles L, Handles R, int axis) {
   int ldo = L.ldo, ldi = L.rdo, rdi = R.ldo, rdo = R.rdo;
   if (axis == 1) {
     // the two sets are separated by a horizontal line: seat the handles on the y-extremes
-    while (m.py[m.dest(ldo)] < m.py[m.org[ldo]]) ldo = m.rprev(ldo);
-    while (m.py[m.dest(m.onext[ldi])] > m.py[m.org[ldi]]) ldi = Mesh::sym(m.onext[ldi]);
-    while (m.py[m.dest(rdi)] < m.py[m.org[rdi]]) rdi = m.rprev(rdi);
-    while (m.py[m.dest(m.onext[rdo])] > m.py[m.org[rdo]]) rdo = Mesh::sym(m.onext[rdo]);
+    while (m.py[m.dest(ldo)] < m.py[m.org(ldo)]) ldo = m.rprev(ldo);
+    while (m.py[m.dest(m.onext(ldi))] > m.py[m.org(ldi)]) ldi = Mesh::sym(m.onext(ldi));
+    while (m.py[m.dest(rdi)] < m.py[m.org(rdi)]) rdi = m.rprev(rdi);
+    while (m.py[m.dest(m.onext(rdo))] > m.py[m.org(rdo)]) rdo = Mesh::sym(m.onext(rdo));
   }
   // lower common tangent
   bool changed;
   do {
     changed = false;
-    if (m.ccw(m.org[ldi], m.dest(ldi), m.org[rdi]) > 0) { ldi = m.lnext(ldi); changed = true; }
-    if (m.ccw(m.dest(rdi), m.org[rdi], m.org[ldi]) > 0) { rdi = m.rprev(rdi); changed = true; }
+    if (m.ccw(m.org(ldi), m.dest(ldi), m.org(rdi)) > 0) { ldi = m.lnext(ldi); changed = true; }
+    if (m.ccw(m.dest(rdi), m.org(rdi), m.org(ldi)) > 0) { rdi = m.rprev(rdi); changed = true; }
   } while (changed);
   int basel = m.connect(Mesh::sym(rdi), ldi);       // from org(rdi) = lower right to org(ldi) = lower left
-  if (m.org[ldi] == m.org[ldo]) ldo = Mesh::sym(basel);
-  if (m.org[rdi] == m.org[rdo]) rdo = basel;
+  if (m.org(ldi) == m.org(ldo)) ldo = Mesh::sym(basel);
+  if (m.org(rdi) == m.org(rdo)) rdo = basel;
   // knit the seam upwards
   for (;;) {
-    const int lowerright = m.org[basel], lowerleft = m.dest(basel);
-    int lcand = m.onext[Mesh::sym(basel)], rcand = m.oprev[basel];
+    const int lowerright = m.org(basel), lowerleft = m.dest(basel);
+    int lcand = m.onext(Mesh::sym(basel)), rcand = m.oprev(basel);
     int upperleft = m.dest(lcand), upperright = m.dest(rcand);
     const bool leftfinished = m.ccw(upperleft, lowerleft, lowerright) <= 0;
     const bool rightfinished = m.ccw(upperright, lowerleft, lowerright) <= 0;
     if (leftfinished && rightfinished) break;
     if (!leftfinished) {
       for (;;) {
-        const int nx = m.onext[lcand];
+        const int nx = m.onext(lcand);
         if (nx == Mesh::sym(basel)) break;
         const int apex = m.dest(nx);
         if (m.ccw(lowerleft, upperleft, apex) <= 0) break;                 // no real triangle beyond lcand
@@ -164,7 +172,7 @@ Handles merge(Mesh& m, Handles L, Handles R, int axis) {
     }
     if (!rightfinished) {
       for (;;) {
-        const int nx = m.oprev[rcand];
+        const int nx = m.oprev(rcand);
         if (nx == basel) break;
         const int apex = m.dest(nx);
         if (m.ccw(lowerright, apex, upperright) <= 0) break;
@@ -180,8 +188,8 @@ Handles merge(Mesh& m, Handles L, Handles R, int axis) {
   }
   if (axis == 1) {
     // back to the x-extremes expected by the parent (vertical cut) and by the leaves
-    while (m.px[m.dest(m.oprev[ldo])] < m.px[m.org[ldo]]) ldo = Mesh::sym(m.oprev[ldo]);
-    while (m.px[m.dest(rdo)] > m.px[m.org[rdo]]) rdo = m.lnext(rdo);
+    while (m.px[m.dest(m.oprev(ldo))] < m.px[m.org(ldo)]) ldo = Mesh::sym(m.oprev(ldo));
+    while (m.px[m.dest(rdo)] > m.px[m.org(rdo)]) rdo = m.lnext(rdo);
   }
   return Handles{ldo, rdo};
 }
@@ -209,40 +217,122 @@ Handles build(Mesh& m, const int* v, int n, int axis) {
 
 }  // namespace
 
+namespace {
+
+struct Scratch {
+  std::vector<int32_t> sx, sy, orig, cnt;
+  std::vector<int> v, yl, tmp, a, b;
+  std::vector<uint8_t> side;
+  Mesh m;
+};
+
+// stable counting sort of ids by key[id] (keys in [lo, lo + range))
+void counting_pass(const std::vector<int>& in, std::vector<int>& out, const int32_t* key, int lo, int range, std::vector<int32_t>& cnt) {
+  cnt.assign((size_t)range + 1, 0);
+  for (int id : in) cnt[key[id] - lo + 1]++;
+  for (int k = 0; k < range; k++) cnt[k + 1] += cnt[k];
+  out.resize(in.size());
+  for (int id : in) out[cnt[key[id] - lo]++] = id;
+}
+
+// Builds the triangulation in S.m; S.orig maps mesh vertex numbers to input indices.  Returns the final hull handles
+// ({-1,-1} if fewer than two distinct points).
+Handles triangulate(Scratch& S, const int32_t* x, const int32_t* y, int n) {
+  Handles none{-1, -1};
+  if (n < 2) return none;
+  int xlo = x[0], xhi = x[0], ylo = y[0], yhi = y[0];
+  for (int i = 1; i < n; i++) {
+    xlo = std::min(xlo, x[i]); xhi = std::max(xhi, x[i]);
+    ylo = std::min(ylo, y[i]); yhi = std::max(yhi, y[i]);
+  }
+  // sort by (x, y, input index): two stable counting passes (pixel coordinates span a few thousand values)
+  S.a.resize(n);
+  for (int i = 0; i < n; i++) S.a[i] = i;
+  counting_pass(S.a, S.b, y, ylo, yhi - ylo + 1, S.cnt);
+  counting_pass(S.b, S.a, x, xlo, xhi - xlo + 1, S.cnt);
+  bool duplicates = false;
+  for (int i = 1; i < n && !duplicates; i++) duplicates = x[S.a[i]] == x[S.a[i - 1]] && y[S.a[i]] == y[S.a[i - 1]];
+  S.orig.clear();
+  if (!duplicates) {
+    S.orig.assign(S.a.begin(), S.a.end());
+  } else {
+    // Of several input points on the same pixel only one takes part (Triangle ignores duplicates).  Which one
+    // survives depends on the order an unstable sort leaves them in, and removeOutliers keeps exactly the survivor,
+    // so in this (rare, quad matching only) case the sort is redone with the same randomised quicksort (Hoare
+    // partition, pivots from the generator seeded with 1) the reference's triangulation uses, and the first of
+    // each run of equal points is kept.
+    for (int i = 0; i < n; i++) S.a[i] = i;
+    Mesh tmpm;
+    tmpm.set_points(x, y);
+    PivotSource pivots;
+    pivot_quicksort(tmpm, S.a.data(), n, pivots);
+    S.orig.push_back(S.a[0]);
+    for (int i = 1; i < n; i++)
+      if (x[S.a[i]] != x[S.orig.back()] || y[S.a[i]] != y[S.orig.back()]) S.orig.push_back(S.a[i]);
+  }
+  const int nu = (int)S.orig.size();
+  if (nu < 2) return none;
+  // vertices renumbered by (x, y) rank, coordinates stored in that order
+  S.sx.resize(nu); S.sy.resize(nu);
+  for (int i = 0; i < nu; i++) { S.sx[i] = x[S.orig[i]]; S.sy[i] = y[S.orig[i]]; }
+  S.v.resize(nu);
+  for (int i = 0; i < nu; i++) S.v[i] = i;
+  counting_pass(S.v, S.yl, S.sy.data(), ylo, yhi - ylo + 1, S.cnt);     // ids in (y, x) order
+  S.side.resize(nu); S.tmp.resize(nu);
+  S.m.set_points(S.sx.data(), S.sy.data());
+  S.m.he.clear();
+  S.m.he.reserve(12 * (size_t)nu);
+  // root: vertical cut of the x-sorted list, children by alternating axes
+  partition(S.v.data(), S.yl.data(), nu, 0, S.side.data(), S.tmp.data());
+  return build(S.m, S.v.data(), nu, 0);
+}
+
+Scratch& scratch() {
+  static thread_local Scratch S;     // reused from call to call (one ~5 k point triangulation per frame pair and worker)
+  return S;
+}
+
+}  // namespace
+
 void delaunay_triangles(const int32_t* x, const int32_t* y, int n, std::vector<int32_t>& tri) {
   tri.clear();
   if (n < 3) return;
-  Mesh m;
-  m.px = x; m.py = y;
-  m.org.reserve(8 * (size_t)n); m.onext.reserve(8 * (size_t)n); m.oprev.reserve(8 * (size_t)n); m.dead.reserve(8 * (size_t)n);
-  // sort by (x, y); of several input points on the same pixel only one takes part (Triangle ignores duplicates).
-  // Which of the duplicates survives depends on the order an unstable sort leaves them in, and removeOutliers
-  // keeps exactly the survivor, so the sort is the same randomised quicksort (Hoare partition, pivots from the
-  // generator seeded with 1) that the reference's triangulation uses.
-  std::vector<int> v(n);
-  for (int i = 0; i < n; i++) v[i] = i;
-  PivotSource pivots;
-  pivot_quicksort(m, v.data(), n, pivots);
-  int k = 0;
-  for (int i = 1; i < n; i++)
-    if (x[v[i]] != x[v[k]] || y[v[i]] != y[v[k]]) v[++k] = v[i];
-  const int nu = k + 1;
-  if (nu < 3) return;
-  // root: vertical cut of the x-sorted list, children by alternating axes
-  const int divider = nu >> 1;
-  if (nu - divider >= 2) {
-    if (divider >= 2) partition(m, v.data(), divider, 1);
-    partition(m, v.data() + divider, nu - divider, 1);
-  }
-  build(m, v.data(), nu, 0);
+  Scratch& S = scratch();
+  if (triangulate(S, x, y, n).ldo < 0) return;
+  const Mesh& m = S.m;
   // every bounded face is a counter-clockwise triangle; report each once, from its lowest-numbered half-edge
-  const int ne = (int)m.org.size();
+  const int ne = (int)m.he.size();
+  tri.reserve(6 * S.orig.size());
   for (int e = 0; e < ne; e++) {
-    if (m.dead[e]) continue;
-    const int e2 = m.lnext(e), e3 = m.lnext(e2);
-    if (m.lnext(e3) != e || e2 < e || e3 < e) continue;
-    const int a = m.org[e], b = m.org[e2], c = m.org[e3];
-    if (m.ccw(a, b, c) > 0) { tri.push_back(a); tri.push_back(b); tri.push_back(c); }
+    if (m.he[e].dead) continue;
+    const int e2 = m.lnext(e);
+    if (e2 < e) continue;
+    const int e3 = m.lnext(e2);
+    if (e3 < e || m.lnext(e3) != e) continue;
+    const int a = m.org(e), b = m.org(e2), c = m.org(e3);
+    if (m.ccw(a, b, c) > 0) { tri.push_back(S.orig[a]); tri.push_back(S.orig[b]); tri.push_back(S.orig[c]); }
+  }
+}
+
+void delaunay_edges(const int32_t* x, const int32_t* y, int n, std::vector<int32_t>& edges) {
+  edges.clear();
+  if (n < 3) return;
+  Scratch& S = scratch();
+  Handles h = triangulate(S, x, y, n);
+  if (h.ldo < 0) return;
+  Mesh& m = S.m;
+  // mark the half-edges whose left face is the unbounded face: one walk around it, starting at the clockwise
+  // hull edge out of the rightmost vertex.  Every other face of a Delaunay triangulation is a triangle.
+  int e = h.rdo;
+  do { m.he[e].dead |= 2; e = m.lnext(e); } while (e != h.rdo);
+  const int ne = (int)m.he.size();
+  edges.reserve(9 * S.orig.size());
+  for (int k = 0; k < ne; k += 2) {
+    const int d0 = m.he[k].dead, d1 = m.he[k + 1].dead;
+    if ((d0 | d1) & 1) continue;
+    const int t = (d0 & 2 ? 0 : 1) + (d1 & 2 ? 0 : 1);
+    if (t == 0) continue;
+    edges.push_back(S.orig[m.he[k].org]); edges.push_back(S.orig[m.he[k + 1].org]); edges.push_back(t);
   }
 }
 

@@ -8,5 +8,8 @@ namespace visob {
 // tri receives 3 indices (into x/y) per triangle, counter-clockwise.  Coordinates must satisfy |x|,|y| < 2^15.
 // Of several points with identical coordinates only one is triangulated (the one the reference would keep).
 void delaunay_triangles(const int32_t* x, const int32_t* y, int n, std::vector<int32_t>& tri);
+// The same triangulation as an edge list: (a, b, t) per undirected edge, t = number of triangles (1 or 2) it bounds.
+// This is all the support vote of removeOutliers needs and skips the face enumeration.
+void delaunay_edges(const int32_t* x, const int32_t* y, int n, std::vector<int32_t>& edges);
 }
 #endif

@@ -278,10 +278,11 @@ void Matcher::computePriorStatistics(vector<p_match>& p_matched, int32_t method)
 void Matcher::removeOutliers(vector<p_match>& p_matched, int32_t method) {
   const int32_t n = (int32_t)p_matched.size();
   if (n <= 3) return;
-  vector<int32_t> x(n), y(n), tri;
+  static thread_local vector<int32_t> x, y, edges, support;
+  x.resize(n); y.resize(n);
   for (int32_t i = 0; i < n; i++) { x[i] = (int32_t)p_matched[i].u1c; y[i] = (int32_t)p_matched[i].v1c; }
-  visob::delaunay_triangles(x.data(), y.data(), n, tri);
-  vector<int32_t> support(n, 0);
+  visob::delaunay_edges(x.data(), y.data(), n, edges);
+  support.assign(n, 0);
   const float flow_tol = (float)param.outlier_flow_tolerance, disp_tol = (float)param.outlier_disp_tolerance;
   auto edge_ok = [&](const p_match& a, const p_match& b) -> bool {
     if (method == 0) {
@@ -292,11 +293,10 @@ void Matcher::removeOutliers(vector<p_match>& p_matched, int32_t method) {
     return fabs((a.u1p - a.u2p) - (b.u1p - b.u2p)) < disp_tol &&
            fabs((a.u1c - a.u1p) - (b.u1c - b.u1p)) + fabs((a.v1c - a.v1p) - (b.v1c - b.v1p)) < flow_tol;
   };
-  for (size_t t = 0; t + 2 < tri.size(); t += 3) {
-    const int32_t p1 = tri[t], p2 = tri[t + 1], p3 = tri[t + 2];
-    if (edge_ok(p_matched[p1], p_matched[p2])) { support[p1]++; support[p2]++; }
-    if (edge_ok(p_matched[p2], p_matched[p3])) { support[p2]++; support[p3]++; }
-    if (edge_ok(p_matched[p1], p_matched[p3])) { support[p1]++; support[p3]++; }
+  // the reference votes per triangle edge (matcher.cpp:1259-1362): an edge shared by two triangles counts twice
+  for (size_t e = 0; e + 2 < edges.size(); e += 3) {
+    const int32_t a = edges[e], b = edges[e + 1], t = edges[e + 2];
+    if (edge_ok(p_matched[a], p_matched[b])) { support[a] += t; support[b] += t; }
   }
   int32_t k = 0;
   for (int32_t i = 0; i < n; i++)
