@@ -287,6 +287,7 @@ def main():
     ap.add_argument('--sequences', type=int, default=64, help='independent sequences per GPU (config 5 uses 64)')
     ap.add_argument('--threads', type=int, default=0, help='host worker threads per rank (default: cores / ranks)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dry-run', action='store_true', help='no GPU work: fake per-rank timings over gloo (tests of the N>1 plumbing)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -309,21 +310,30 @@ def main():
                           'e2e': {'value': round(val, 2), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
         return
 
+    tdev = 'cpu' if args.dry_run else 'cuda'
     if world > 1:
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    res_dev, res_e2e, roof, threads, info = run_ours(args, rank, world, local_rank)
+        if args.dry_run:
+            dist.init_process_group('gloo')
+        else:
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    if args.dry_run:
+        ms = 10.0 * (rank + 1) * args.steps
+        fake = dict(ms=ms, wall=ms * 1e-3, launches=0, h2d=0, d2h=0, matches_per_pair=0.0, ok_frac=0.0, clocks=None)
+        res_dev, res_e2e, roof, threads, info = fake, dict(fake), None, 1, {'name': 'none (dry run)'}
+    else:
+        res_dev, res_e2e, roof, threads, info = run_ours(args, rank, world, local_rank)
     ms_dev, ms_e2e = res_dev['ms'], res_e2e['ms']
     launches = res_dev['launches']
     if world > 1:
         import torch
         import torch.distributed as dist
-        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device='cuda')
+        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=tdev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e = float(t[0]), float(t[1])
-        l = torch.tensor([launches], dtype=torch.int64, device='cuda')
+        l = torch.tensor([launches], dtype=torch.int64, device=tdev)
         dist.all_reduce(l, op=dist.ReduceOp.SUM)
         launches = int(l[0])
         dist.barrier()
@@ -334,7 +344,7 @@ def main():
     pairs = S * world * K
     line = {'metric': METRIC, 'value': round(pairs / (ms_dev * 1e-3), 2), 'unit': UNIT, 'n_gpus': world, 'steps': K,
             'warmup': args.warmup, 'ms_per_step': round(ms_dev / K, 4), 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': 'u8', 'data': 'dry-run' if args.dry_run else 'synthetic',
             'config': {'workload': workload_name, 'sequences_per_gpu': S, 'frame_pairs_per_step': S * world,
                        'host_threads_per_gpu': threads, 'inputs': 'frames resident in HBM (pushBackDevice); every step uses new frames, '
                        '%d sequences x 0.47 MB per step, L2 not flushed between steps (working set of a step = %d MB of planes and records)' % (S, int(S * 3.3)),
@@ -344,7 +354,7 @@ def main():
             'e2e': {'value': round(pairs / (ms_e2e * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(res_e2e['h2d'] * world),
                     'd2h_bytes_per_step': int(res_e2e['d2h'] * world), 'api': 'Matcher::pushBack(host image) + matchFeatures + getMatches'},
             'gpu_launches': launches, 'roofline': roof}
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline and not args.dry_run:
         try:
             val, secs, cores, sample = reference_run(args.workload, 5, 1)
             line['cpu_baseline'] = {'value': round(val, 2), 'unit': UNIT, 'cores': cores, 'kind': 'reference', 'sample': sample}
