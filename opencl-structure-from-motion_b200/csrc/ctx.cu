@@ -179,6 +179,10 @@ extern "C" int visocu_configure(visocu_ctx* ctx, const visocu_params* p, int32_t
   CU_COPY(ctx, ctx->frames_d, ctx->frames_h.data(), sizeof(FrameDev) * (size_t)n_frames, cudaMemcpyHostToDevice);
   CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->n_frames = n_frames;
+  {
+    int rc = visocu_make_tensor_map(ctx, per);
+    if (rc) return rc;
+  }
   ctx->h_counts.assign((size_t)n_frames * 2, 0);
   ctx->frame_valid.assign(n_frames, 0);
   ctx->configured = true;

@@ -12,6 +12,7 @@
 // reduced to "window minimum == cell minimum", and the output order (cell-column-major, then class) is
 // rebuilt with a deterministic scan instead of push_back.
 #include "visocu_internal.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -108,146 +109,254 @@ __global__ void __launch_bounds__(256) k_sobel_full(Geometry g, const FrameDev* 
 
 // ----------------------------------------------------------------------------------------------------------
 // Fused kernel.  One CTA = one TW x TH tile of one image.
-//   phase 1  stage the image tile plus halo in shared memory (word loads, zero outside the image)
-//   phase 2  column walkers: 5-row register windows of the five horizontal sums -> du, dv (global, core only),
-//            blob f1 and checkerboard f2 (shared memory only)
-//   phase 3  one thread per owned NMS cell and pass: cell extrema (first in column-major order wins), then for
-//            the extrema that pass the tau test a window scan for a strictly better value
+//   phase 1  one elected thread issues a TMA tile load (cp.async.bulk.tensor.3d, zero fill outside the image) of the
+//            image tile plus halo into shared memory; everybody waits on the mbarrier.
+//   phase 2  register-window filters.  A thread owns one 32-bit word (4 pixels) of a row segment and walks down the
+//            rows.  All arithmetic is done on two 16-bit lanes per register ((b0,b2) and (b1,b3) of the word): every
+//            intermediate is kept non-negative by a bias (765 on the horizontal (1,2,0,-2,-1) sum, 510 on the
+//            (1,1,0,-1,-1) sum, ...), so plain 32-bit integer adds and subtracts never carry between the lanes.
+//            du and dv leave as one coalesced 32-bit store per word and row; the blob response f1 (+6375) and the
+//            checkerboard response f2 (+2040) go to shared memory only.
+//   phase 3  NMS on the biased responses.  Dense cells: one thread per cell; sparse cells: four lanes per cell, each
+//            scanning every fourth column, combined with warp shuffles.  Extrema are reduced as keys
+//            (value << 8 | position) so that "first in column-major order" falls out of a min / max.  The four
+//            candidates of a cell that pass the tau test get a window scan for a strictly better value.
 // A cell is owned by the tile that contains its origin; the halo is nmax to the left/top and 2*nmax to the
 // right/bottom because a cell spans [i,i+n] and its extremum's neighbourhood [i-n,i+2n] (matcher.cpp:356,383).
-__global__ void __launch_bounds__(FILTER_THREADS) k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const FrameDev F = frames[sl.s[blockIdx.z]];
-  const uint8_t* __restrict__ I = g.half ? F.half : F.img;
+constexpr int BIAS_F1 = 6375;    // 25 * 255: f1 + BIAS_F1 >= 0
+constexpr int BIAS_F2 = 2040;    //  8 * 255
+#define K2(v) ((uint32_t)(v) | ((uint32_t)(v) << 16))   /* the same constant in both 16-bit lanes */
+
+struct TileShape { int nmax, FW, FH, NWo, NW, IS, IH, FS; size_t img_bytes, smem; };
+__host__ __device__ inline TileShape tile_shape(int nmax) {
+  TileShape t;
+  t.nmax = nmax;
+  t.FW = TW + 3 * nmax; t.FH = TH + 3 * nmax;
+  // response columns start at fxs = fx0 rounded down to a multiple of 4 (fx0 = x0 - nmax, x0 multiple of TW)
+  const int lead = ((-nmax) % 4 + 4) % 4;                 // fx0 - fxs
+  t.NWo = (lead + t.FW + 3) / 4;                           // response words per row
+  t.NW = (t.NWo + 2 + 3) & ~3;                             // image words per row (one extra word on each side), 16 B multiple
+  t.IS = t.NW * 4; t.IH = t.FH + 4;
+  t.FS = t.NWo * 4;
+  t.img_bytes = ((size_t)t.IH * t.IS + 127) & ~(size_t)127;
+  t.smem = t.img_bytes + 2 * (size_t)t.FH * t.FS * sizeof(int16_t) + 128;
+  return t;
+}
+
+struct Win {   // 5-row windows of the horizontal sums of one word: [row slot][lane pair A=(b0,b2), B=(b1,b3)]
+  uint32_t hd[5][2], ha[5][2], h1[5][2], h3[5][2], hc[5][2], pc[5][2];
+};
+
+// horizontal sums of the 4 pixels of word C (neighbours L, R) into window slot S
+template <int S>
+__device__ __forceinline__ void hrow4(Win& w, uint32_t L, uint32_t C, uint32_t R, bool core) {
+  const uint32_t s2a = __funnelshift_r(L, C, 16);          // bytes l2 l3 b0 b1
+  const uint32_t s2b = __funnelshift_r(C, R, 16);          // bytes b2 b3 r0 r1
+  uint32_t t[6];
+  t[0] = s2a & 0x00FF00FFu;                                // (l2, b0)
+  t[1] = __byte_perm(s2a, 0, 0x4341);                      // (l3, b1)
+  t[2] = C & 0x00FF00FFu;                                  // (b0, b2)
+  t[3] = __byte_perm(C, 0, 0x4341);                        // (b1, b3)
+  t[4] = s2b & 0x00FF00FFu;                                // (b2, r0)
+  t[5] = __byte_perm(s2b, 0, 0x4341);                      // (b3, r1)
+#pragma unroll
+  for (int k = 0; k < 2; k++) {                            // k = 0: pixels (b0,b2), k = 1: pixels (b1,b3)
+    const uint32_t t0 = t[k], t1 = t[k + 1], t2 = t[k + 2], t3 = t[k + 3], t4 = t[k + 4];
+    if (core) {
+      w.hd[S][k] = (t0 + 2 * t1 + K2(765)) - (t4 + 2 * t3);          // (1,2,0,-2,-1) + 765
+      w.ha[S][k] = (t0 + t4) + 4 * (t1 + t3) + 6 * t2;               // (1,4,6,4,1)
+    }
+    w.h1[S][k] = t0 + t1 + t2 + t3 + t4;
+    w.h3[S][k] = t1 + t2 + t3;
+    w.hc[S][k] = (t0 + t1 + K2(510)) - (t3 + t4);                    // (1,1,0,-1,-1) + 510
+    w.pc[S][k] = t2;
+  }
+}
+
+__device__ __forceinline__ bool mbar_wait_or_trap(uint32_t bar, uint32_t phase) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    if (done) return true;
+    if (clock64() - t0 > 2000000000LL) __trap();           // about one second: never hang the GPU on a TMA mistake
+  }
+}
+
+__global__ void __launch_bounds__(FILTER_THREADS, 2)
+k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  const int slot = sl.s[blockIdx.z];
+  const FrameDev F = frames[slot];
   const int tid = threadIdx.x;
+  const TileShape ts = tile_shape(nmax);
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const int fx0 = x0 - nmax, fy0 = y0 - nmax;              // origin of the response region
-  const int FW = TW + 3 * nmax, FH = TH + 3 * nmax;
-  const int FS = (FW + 1) & ~1;                            // int16 row stride of the response planes
-  const int ix0 = (fx0 - 2) & ~3;                          // image tile origin, rounded down to a word
-  const int iy0 = fy0 - 2;
-  const int IH = FH + 4;
-  const int IS = ((fx0 + FW + 2 - ix0) + 15) & ~15;        // byte row stride of the image tile
+  const int fx0 = x0 - nmax, fy0 = y0 - nmax;              // origin of the response region that NMS reads
+  const int fxs = fx0 & ~3;                                // response columns in shared memory start here
+  const int rx0 = fxs - 4, iy0 = fy0 - 2;                  // image tile origin
+  const int FH = ts.FH, FS = ts.FS, IS = ts.IS, IH = ts.IH, NWo = ts.NWo;
   uint8_t* simg = smem;
-  int16_t* sf1 = (int16_t*)(smem + (((size_t)IH * IS + 15) & ~(size_t)15));
+  int16_t* sf1 = (int16_t*)(smem + ts.img_bytes);
   int16_t* sf2 = sf1 + (size_t)FH * FS;
 
   // ---- phase 1
-  {
+  if (use_tma) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(simg);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)(IH * IS);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          :: "r"(dst), "l"(&tmap), "r"(rx0), "r"(iy0), "r"(slot), "r"(bar) : "memory");
+    }
+    mbar_wait_or_trap(bar, 0);
+  } else {
+    const uint8_t* __restrict__ I = g.half ? F.half : F.img;
     const int words = IS >> 2;
     for (int idx = tid; idx < IH * words; idx += FILTER_THREADS) {
-      int ly = idx / words, lw = idx - ly * words;
-      int gx = ix0 + 4 * lw, gy = iy0 + ly;
+      const int ly = idx / words, lw = idx - ly * words;
+      const int gx = rx0 + 4 * lw, gy = iy0 + ly;
       uint32_t v = 0;
       if (gy >= 0 && gy < g.hm && gx >= 0 && gx < g.bplm) v = __ldg((const uint32_t*)(I + (size_t)gy * g.bplm + gx));
       *(uint32_t*)(simg + ly * IS + 4 * lw) = v;
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   // ---- phase 2
   {
     const int nseg = (FH + SEG - 1) / SEG;
-    for (int item = tid; item < FW * nseg; item += FILTER_THREADS) {
-      const int seg = item / FW, cx = item - seg * FW;
+    for (int item = tid; item < NWo * nseg; item += FILTER_THREADS) {
+      const int seg = item / NWo, j = item - seg * NWo;
       const int ly0 = seg * SEG;
       const int nrow = min(SEG, FH - ly0);
-      const int gx = fx0 + cx;
-      const uint8_t* col = simg + (gx - 2 - ix0);          // p[0] of hrow for image-tile row r is col[r*IS]
-      const bool core_x = gx >= x0 && gx < x0 + TW && gx < g.bplm;
-      // columns w-2 .. bpl-3 are computed too, from the zero pad: the reference filters its whole 16-byte-stride
-      // buffer and a descriptor of a maximum at u = w-7 samples column w-2 (its pad bytes are uninitialised heap
-      // memory there, zero in the common case of a fresh allocation)
-      const bool valid_x = gx >= 2 && gx <= g.bplm - 3;
-      int hd[5], ha[5], h1[5], h3[5], hc[5], pc[5];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        HRow r = hrow(col + (ly0 + k) * IS);
-        hd[k] = r.hd; ha[k] = r.ha; h1[k] = r.h1; h3[k] = r.h3; hc[k] = r.hc; pc[k] = r.pc;
-      }
+      const int gx = fxs + 4 * j;                                          // first pixel of this word
+      const uint32_t* col = (const uint32_t*)simg + j;                     // words j, j+1, j+2 of an image-tile row
+      const int IW = IS >> 2;
+      const bool core = gx >= x0 && gx < x0 + TW && gx < g.bplm;           // du/dv are written for core words only
+      Win w;
+#define VISO_HROW(S, r) { const uint32_t* q = col + (r) * IW; hrow4<S>(w, q[0], q[1], q[2], core); }
+      VISO_HROW(0, ly0) VISO_HROW(1, ly0 + 1) VISO_HROW(2, ly0 + 2) VISO_HROW(3, ly0 + 3)
       for (int r5 = 0; r5 < nrow; r5 += 5) {
-#pragma unroll
-        for (int ph = 0; ph < 5; ph++) {
-          const int lr = r5 + ph;
-          if (lr < nrow) {
-            const int s0 = ph % 5, s1 = (ph + 1) % 5, s2 = (ph + 2) % 5, s3 = (ph + 3) % 5, s4 = (ph + 4) % 5;
-            {
-              HRow r = hrow(col + (ly0 + lr + 4) * IS);
-              hd[s4] = r.hd; ha[s4] = r.ha; h1[s4] = r.h1; h3[s4] = r.h3; hc[s4] = r.hc; pc[s4] = r.pc;
-            }
-            const int ly = ly0 + lr, gy = fy0 + ly;
-            int f1 = -(h1[s0] + h1[s1] + h1[s2] + h1[s3] + h1[s4]) + 2 * (h3[s1] + h3[s2] + h3[s3]) + 7 * pc[s2];
-            int f2 = (hc[s0] + hc[s1]) - (hc[s3] + hc[s4]);
-            sf1[ly * FS + cx] = (int16_t)f1;
-            sf2[ly * FS + cx] = (int16_t)f2;
-            if (core_x && gy >= y0 && gy < y0 + TH && gy < g.hm) {
-              int du = 128, dv = 128;
-              if (valid_x && gy >= 2 && gy <= g.hm - 3) {
-                du = (((hd[s0] + hd[s4]) + 4 * (hd[s1] + hd[s3]) + 6 * hd[s2]) >> 7) + 128;   // |sum| <= 12240: no saturation
-                dv = (((ha[s0] - ha[s4]) + 2 * (ha[s1] - ha[s3])) >> 7) + 128;
-              }
-              F.du[(size_t)gy * g.bplm + gx] = (uint8_t)du;
-              F.dv[(size_t)gy * g.bplm + gx] = (uint8_t)dv;
-            }
-          }
+#define VISO_STEP(PH)                                                                                                  \
+        if (r5 + PH < nrow) {                                                                                          \
+          constexpr int s0 = PH % 5, s1 = (PH + 1) % 5, s2 = (PH + 2) % 5, s3 = (PH + 3) % 5, s4 = (PH + 4) % 5;       \
+          const int ly = ly0 + r5 + PH, gy = fy0 + ly;                                                                 \
+          VISO_HROW(s4, ly + 4)                                                                                        \
+          uint32_t f1[2], f2[2], du[2], dv[2];                                                                         \
+          _Pragma("unroll") for (int k = 0; k < 2; k++) {                                                              \
+            const uint32_t b3 = w.h3[s1][k] + w.h3[s2][k] + w.h3[s3][k];                                               \
+            const uint32_t b5 = w.h1[s0][k] + w.h1[s1][k] + w.h1[s2][k] + w.h1[s3][k] + w.h1[s4][k];                   \
+            f1[k] = (7 * w.pc[s2][k] + 2 * b3 + K2(BIAS_F1)) - b5;                                                     \
+            f2[k] = (w.hc[s0][k] + w.hc[s1][k] + K2(BIAS_F2)) - (w.hc[s3][k] + w.hc[s4][k]);                           \
+            if (core) {                                                                                                \
+              const uint32_t a = (w.hd[s0][k] + w.hd[s4][k]) + 4 * (w.hd[s1][k] + w.hd[s3][k]) + 6 * w.hd[s2][k] + K2(4144); \
+              du[k] = (a >> 7) & 0x01FF01FFu;                                                                          \
+              const uint32_t b = (w.ha[s0][k] + 2 * w.ha[s1][k] + K2(12240 + 4144)) - (w.ha[s4][k] + 2 * w.ha[s3][k]); \
+              dv[k] = (b >> 7) & 0x01FF01FFu;                                                                          \
+            }                                                                                                          \
+          }                                                                                                            \
+          *(uint2*)(sf1 + ly * FS + 4 * j) = make_uint2(__byte_perm(f1[0], f1[1], 0x5410), __byte_perm(f1[0], f1[1], 0x7632)); \
+          *(uint2*)(sf2 + ly * FS + 4 * j) = make_uint2(__byte_perm(f2[0], f2[1], 0x5410), __byte_perm(f2[0], f2[1], 0x7632)); \
+          if (core && gy >= y0 && gy < y0 + TH && gy < g.hm) {                                                         \
+            uint32_t wu = du[0] | (du[1] << 8), wv = dv[0] | (dv[1] << 8);                                             \
+            if (gy < 2 || gy > g.hm - 3) { wu = 0x80808080u; wv = 0x80808080u; }                                       \
+            if (gx == 0) { wu = (wu & 0xFFFF0000u) | 0x8080u; wv = (wv & 0xFFFF0000u) | 0x8080u; }                     \
+            if (gx == g.bplm - 4) { wu = (wu & 0x0000FFFFu) | 0x80800000u; wv = (wv & 0x0000FFFFu) | 0x80800000u; }    \
+            *(uint32_t*)(F.du + (size_t)gy * g.bplm + gx) = wu;                                                        \
+            *(uint32_t*)(F.dv + (size_t)gy * g.bplm + gx) = wv;                                                        \
+          }                                                                                                            \
         }
+        VISO_STEP(0) VISO_STEP(1) VISO_STEP(2) VISO_STEP(3) VISO_STEP(4)
+#undef VISO_STEP
       }
+#undef VISO_HROW
     }
   }
   __syncthreads();
 
   // ---- phase 3
   {
-    int klo[2], nk[2], llo[2], nl[2], total = 0, first[2];
-    for (int p = 0; p < 2; p++) {
-      nk[p] = nl[p] = klo[p] = llo[p] = 0; first[p] = total;
-      if (p < g.first_pass) continue;
+    const int cshift = fx0 - fxs;                                          // response column of pixel fx0
+    const int xhi = g.wm - 1 - VISO_MARGIN - fxs, yhi = g.hm - 1 - VISO_MARGIN - fy0;   // window clamps, smem coordinates
+    (void)cshift;
+    for (int p = g.first_pass; p < 2; p++) {
       const int n = g.n[p], step = n + 1, org = n + VISO_MARGIN;
-      int a = x0 - org; klo[p] = a > 0 ? (a + step - 1) / step : 0;
-      int b = x0 + TW - org; int khi = b > 0 ? min((b + step - 1) / step, g.ncx[p]) : 0;
-      a = y0 - org; llo[p] = a > 0 ? (a + step - 1) / step : 0;
-      b = y0 + TH - org; int lhi = b > 0 ? min((b + step - 1) / step, g.ncy[p]) : 0;
-      nk[p] = max(khi - klo[p], 0); nl[p] = max(lhi - llo[p], 0);
-      total += nk[p] * nl[p];
-    }
-    const int xhi = g.wm - 1 - VISO_MARGIN - fx0, yhi = g.hm - 1 - VISO_MARGIN - fy0;   // window clamps, region-local
-    for (int item = tid; item < total; item += FILTER_THREADS) {
-      const int p = (item >= first[1] && nk[1] * nl[1] > 0) ? 1 : 0;
-      const int loc = item - first[p];
-      const int kk = loc % nk[p], ll = loc / nk[p];
-      const int k = klo[p] + kk, l = llo[p] + ll;
-      const int n = g.n[p];
-      const int lx = n + VISO_MARGIN + k * (n + 1) - fx0, ly = n + VISO_MARGIN + l * (n + 1) - fy0;
-      const int16_t* q1 = sf1 + ly * FS + lx;
-      const int16_t* q2 = sf2 + ly * FS + lx;
-      int f1min = q1[0], f1max = f1min, f2min = q2[0], f2max = f2min;
-      int p1min = 0, p1max = 0, p2min = 0, p2max = 0;      // (di<<4 | dj)
-      for (int di = 0; di <= n; di++) {
-        for (int dj = 0; dj <= n; dj++) {
-          int v = q1[dj * FS + di], pos = (di << 4) | dj;
-          if (v < f1min) { f1min = v; p1min = pos; } else if (v > f1max) { f1max = v; p1max = pos; }
-          v = q2[dj * FS + di];
-          if (v < f2min) { f2min = v; p2min = pos; } else if (v > f2max) { f2max = v; p2max = pos; }
-        }
-      }
-      // keep an extremum iff nothing in its clamped (2n+1)^2 window is strictly better; positions inside the
-      // cell can never be strictly better than the cell extremum, so the reference's cell exclusion is implied
-      auto keep = [&](const int16_t* sf, int pos, int val, bool is_min) -> bool {
-        const int ex = lx + (pos >> 4), ey = ly + (pos & 15);
-        const int xe = min(ex + n, xhi), ye = min(ey + n, yhi);
-        for (int i2 = ex - n; i2 <= xe; i2++)
-          for (int j2 = ey - n; j2 <= ye; j2++) {
-            int v = sf[j2 * FS + i2];
-            if (is_min ? (v < val) : (v > val)) return false;
+      int a = x0 - org; const int klo = a > 0 ? (a + step - 1) / step : 0;
+      int b = x0 + TW - org; const int khi = b > 0 ? min((b + step - 1) / step, g.ncx[p]) : 0;
+      a = y0 - org; const int llo = a > 0 ? (a + step - 1) / step : 0;
+      b = y0 + TH - org; const int lhi = b > 0 ? min((b + step - 1) / step, g.ncy[p]) : 0;
+      const int nk = max(khi - klo, 0), nl = max(lhi - llo, 0);
+      const int ncell = nk * nl;
+      const int G = p == 0 ? 4 : 1;                                        // lanes per cell
+      const int nitem = ((ncell * G + 31) & ~31);                          // whole warps take part in the shuffles
+      for (int item = tid; item < nitem; item += FILTER_THREADS) {
+        const int cell = item / G, t = item - cell * G;
+        const bool live = cell < ncell;
+        const int kk = live ? cell % nk : 0, ll = live ? cell / nk : 0;
+        const int k = klo + kk, l = llo + ll;
+        const int lx = org + k * step - fxs, ly = org + l * step - fy0;
+        int k1min = 0x7FFFFFFF, k1max = -1, k2min = 0x7FFFFFFF, k2max = -1;
+        if (live) {
+          for (int di = t; di <= n; di += G) {
+            const int16_t* q1 = sf1 + ly * FS + lx + di;
+            const int16_t* q2 = sf2 + ly * FS + lx + di;
+            for (int dj = 0; dj <= n; dj++) {
+              const int pos = (di << 4) | dj;
+              const int v1 = q1[dj * FS], v2 = q2[dj * FS];
+              k1min = min(k1min, (v1 << 8) | pos); k1max = max(k1max, (v1 << 8) | (255 - pos));
+              k2min = min(k2min, (v2 << 8) | pos); k2max = max(k2max, (v2 << 8) | (255 - pos));
+            }
           }
-        return true;
-      };
-      uint32_t code = 0xFFFFFFFFu;
-      if (f1min <= -g.tau && keep(sf1, p1min, f1min, true))  code = (code & 0xFFFFFF00u) | (uint32_t)p1min;
-      if (f1max >= g.tau  && keep(sf1, p1max, f1max, false)) code = (code & 0xFFFF00FFu) | ((uint32_t)p1max << 8);
-      if (f2min <= -g.tau && keep(sf2, p2min, f2min, true))  code = (code & 0xFF00FFFFu) | ((uint32_t)p2min << 16);
-      if (f2max >= g.tau  && keep(sf2, p2max, f2max, false)) code = (code & 0x00FFFFFFu) | ((uint32_t)p2max << 24);
-      F.codes[p][(size_t)k * g.ncy[p] + l] = code;
+        }
+        if (G == 4) {
+#pragma unroll
+          for (int o = 1; o < 4; o <<= 1) {
+            k1min = min(k1min, __shfl_xor_sync(0xFFFFFFFFu, k1min, o)); k1max = max(k1max, __shfl_xor_sync(0xFFFFFFFFu, k1max, o));
+            k2min = min(k2min, __shfl_xor_sync(0xFFFFFFFFu, k2min, o)); k2max = max(k2max, __shfl_xor_sync(0xFFFFFFFFu, k2max, o));
+          }
+        }
+        // candidate c: 0 = f1 min, 1 = f1 max, 2 = f2 min, 3 = f2 max.  Keep it iff it passes the tau test and nothing
+        // in its clamped (2n+1)^2 window is strictly better; positions inside the cell can never be strictly better
+        // than the cell extremum, so the reference's cell exclusion is implied.
+        auto candidate = [&](int c) -> uint32_t {
+          const int key = c == 0 ? k1min : (c == 1 ? k1max : (c == 2 ? k2min : k2max));
+          const bool is_min = (c & 1) == 0;
+          const int val = key >> 8, pos = is_min ? (key & 255) : 255 - (key & 255);
+          const int bias = c < 2 ? BIAS_F1 : BIAS_F2;
+          if (is_min ? (val > bias - g.tau) : (val < bias + g.tau)) return 0xFFu;
+          const int16_t* sf = c < 2 ? sf1 : sf2;
+          const int ex = lx + (pos >> 4), ey = ly + (pos & 15);
+          const int xe = min(ex + n, xhi), ye = min(ey + n, yhi);
+          for (int j2 = ey - n; j2 <= ye; j2++) {
+            const int16_t* row = sf + j2 * FS;
+            for (int i2 = ex - n; i2 <= xe; i2++) {
+              const int v = row[i2];
+              if (is_min ? (v < val) : (v > val)) return 0xFFu;
+            }
+          }
+          return (uint32_t)pos;
+        };
+        uint32_t code;
+        if (G == 4) {
+          code = (live ? candidate(t) : 0xFFu) << (8 * t);
+          code |= __shfl_xor_sync(0xFFFFFFFFu, code, 1);
+          code |= __shfl_xor_sync(0xFFFFFFFFu, code, 2);
+        } else {
+          code = 0xFFFFFFFFu;
+          if (live) code = candidate(0) | (candidate(1) << 8) | (candidate(2) << 16) | (candidate(3) << 24);
+        }
+        if (live && t == 0) F.codes[p][(size_t)k * g.ncy[p] + l] = code;
+      }
     }
   }
 }
@@ -438,16 +547,14 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
   }
   const int nmax = g.first_pass == 0 ? (g.n[0] > g.n[1] ? g.n[0] : g.n[1]) : g.n[1];
   {
-    const int FW = TW + 3 * nmax, FH = TH + 3 * nmax, FS = (FW + 1) & ~1;
-    const int IS = (FW + 4 + 3 + 15) & ~15, IH = FH + 4;
-    size_t smem = (((size_t)IH * IS + 15) & ~(size_t)15) + 2 * (size_t)FH * FS * sizeof(int16_t);
-    if (smem > ctx->filter_smem_attr) {
-      CU_TRY(ctx, cudaFuncSetAttribute(k_filter_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      ctx->filter_smem_attr = smem;
+    const TileShape ts = tile_shape(nmax);
+    if (ts.smem > ctx->filter_smem_attr) {
+      CU_TRY(ctx, cudaFuncSetAttribute(k_filter_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts.smem));
+      ctx->filter_smem_attr = ts.smem;
     }
     dim3 grid((g.bplm + TW - 1) / TW, (g.hm + TH - 1) / TH, sl.n);
     if (ctx->profile) CU_TRY(ctx, cudaEventRecord(ctx->pev0, st));
-    k_filter_nms<<<grid, FILTER_THREADS, smem, st>>>(g, ctx->frames_d, sl, nmax);
+    k_filter_nms<<<grid, FILTER_THREADS, ts.smem, st>>>(g, ctx->frames_d, sl, nmax, ctx->tmap_img, ctx->use_tma);
     CU_LAUNCH_CHECK(ctx);
     if (ctx->profile) {
       // profiling mode only: this synchronises the stream after every fused launch
@@ -471,5 +578,37 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
   dim3 gb(1, 2, sl.n);
   k_build_bins<<<gb, 1024, 0, st>>>(g, ctx->frames_d, sl);
   CU_LAUNCH_CHECK(ctx);
+  return VISOCU_OK;
+}
+
+// TMA descriptor of the matching-resolution image plane of every frame slot: a 3-D tensor (bytes per line, rows,
+// frame slots) with the tile box of tile_shape(nmax); out-of-bounds elements are filled with zeros, which is what
+// the filters expect outside the image.
+int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes) {
+  const Geometry& g = ctx->g;
+  const int nmax = g.first_pass == 0 ? (g.n[0] > g.n[1] ? g.n[0] : g.n[1]) : g.n[1];
+  const TileShape ts = tile_shape(nmax);
+  ctx->use_tma = 0;
+  const char* env = getenv("VISOCU_TMA");
+  if (env && env[0] == '0') return VISOCU_OK;             // debugging switch: stage the tile with plain loads
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CU_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return visocu_set_error(ctx, VISOCU_ECUDA, "cuTensorMapEncodeTiled is not available");
+  const FrameDev& F0 = ctx->frames_h[0];
+  void* base = g.half ? (void*)F0.half : (void*)F0.img;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.bplm, (cuuint64_t)g.hm, (cuuint64_t)ctx->n_frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.bplm, (cuuint64_t)frame_stride_bytes};
+  const cuuint32_t box[3] = {(cuuint32_t)ts.IS, (cuuint32_t)ts.IH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (ts.IS > 256 || ts.IH > 256) return visocu_set_error(ctx, VISOCU_EINVAL, "tile box %dx%d exceeds the TMA limit", ts.IS, ts.IH);
+  CUresult r = ((EncodeFn)fn)(&ctx->tmap_img, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return visocu_set_error(ctx, VISOCU_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  ctx->use_tma = 1;
   return VISOCU_OK;
 }

@@ -1,5 +1,6 @@
 // Internal declarations shared by the CUDA translation units behind include/visocu.h.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -55,6 +56,8 @@ struct visocu_ctx {
   void* scratch = nullptr; size_t scratch_bytes = 0;
   void* pinned = nullptr;  size_t pinned_bytes = 0;
   uint64_t launches = 0;
+  CUtensorMap tmap_img;              // TMA descriptor of the matching-resolution image planes of the pool
+  int use_tma = 0;
   size_t filter_smem_attr = 0;       // dynamic shared memory opted in for the fused kernel on this device
   uint64_t h2d_bytes = 0, d2h_bytes = 0;   // host<->device traffic issued by this context
   int profile = 0;                   // time the fused filter+NMS launches with events (visocu_profile)
@@ -100,3 +103,4 @@ __host__ __device__ static inline int viso_cell_count(int len, int n) {
 
 // launchers implemented in the kernel translation units
 int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl);
+int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes);
