@@ -127,7 +127,7 @@ constexpr int BIAS_F1 = 6375;    // 25 * 255: f1 + BIAS_F1 >= 0
 constexpr int BIAS_F2 = 2040;    //  8 * 255
 #define K2(v) ((uint32_t)(v) | ((uint32_t)(v) << 16))   /* the same constant in both 16-bit lanes */
 
-struct TileShape { int nmax, FW, FH, NWo, NW, IS, IH, FS; size_t img_bytes, smem; };
+struct TileShape { int nmax, FW, FH, NWo, NW, IS, IH, FS, iw0; size_t img_bytes, smem; };
 __host__ __device__ inline TileShape tile_shape(int nmax) {
   TileShape t;
   t.nmax = nmax;
@@ -135,11 +135,14 @@ __host__ __device__ inline TileShape tile_shape(int nmax) {
   // response columns start at fxs = fx0 rounded down to a multiple of 4 (fx0 = x0 - nmax, x0 multiple of TW)
   const int lead = ((-nmax) % 4 + 4) % 4;                 // fx0 - fxs
   t.NWo = (lead + t.FW + 3) / 4;                           // response words per row
-  t.NW = (t.NWo + 2 + 3) & ~3;                             // image words per row (one extra word on each side), 16 B multiple
+  // the image tile starts one word left of the response columns, moved further left to a 16-byte boundary because
+  // the TMA needs a 16-byte aligned global address for the first element of the box
+  t.iw0 = ((((-(nmax + lead + 4)) % 16) + 16) % 16) / 4;   // words between the tile origin and response word -1
+  t.NW = (t.iw0 + t.NWo + 2 + 3) & ~3;                     // image words per row, 16 B multiple
   t.IS = t.NW * 4; t.IH = t.FH + 4;
   t.FS = t.NWo * 4;
   t.img_bytes = ((size_t)t.IH * t.IS + 127) & ~(size_t)127;
-  t.smem = t.img_bytes + 2 * (size_t)t.FH * t.FS * sizeof(int16_t) + 128;
+  t.smem = t.img_bytes + 2 * (size_t)t.FH * t.FS * sizeof(int16_t) + 16;   // + the mbarrier
   return t;
 }
 
@@ -186,9 +189,7 @@ __device__ __forceinline__ bool mbar_wait_or_trap(uint32_t bar, uint32_t phase) 
 
 __global__ void __launch_bounds__(FILTER_THREADS, 2)
 k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __grid_constant__ CUtensorMap tmap, int use_tma) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar;
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  extern __shared__ __align__(128) uint8_t smem[];
   const int slot = sl.s[blockIdx.z];
   const FrameDev F = frames[slot];
   const int tid = threadIdx.x;
@@ -196,15 +197,16 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const int fx0 = x0 - nmax, fy0 = y0 - nmax;              // origin of the response region that NMS reads
   const int fxs = fx0 & ~3;                                // response columns in shared memory start here
-  const int rx0 = fxs - 4, iy0 = fy0 - 2;                  // image tile origin
+  const int rx0 = fxs - 4 - 4 * ts.iw0, iy0 = fy0 - 2;      // image tile origin (16-byte aligned in x)
   const int FH = ts.FH, FS = ts.FS, IS = ts.IS, IH = ts.IH, NWo = ts.NWo;
   uint8_t* simg = smem;
   int16_t* sf1 = (int16_t*)(smem + ts.img_bytes);
   int16_t* sf2 = sf1 + (size_t)FH * FS;
+  uint64_t* s_bar = (uint64_t*)(sf2 + (size_t)FH * FS);
 
   // ---- phase 1
   if (use_tma) {
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(simg);
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
@@ -240,7 +242,7 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
       const int ly0 = seg * SEG;
       const int nrow = min(SEG, FH - ly0);
       const int gx = fxs + 4 * j;                                          // first pixel of this word
-      const uint32_t* col = (const uint32_t*)simg + j;                     // words j, j+1, j+2 of an image-tile row
+      const uint32_t* col = (const uint32_t*)simg + ts.iw0 + j;            // words L, C, R of an image-tile row
       const int IW = IS >> 2;
       const bool core = gx >= x0 && gx < x0 + TW && gx < g.bplm;           // du/dv are written for core words only
       Win w;
@@ -336,13 +338,24 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
           if (is_min ? (val > bias - g.tau) : (val < bias + g.tau)) return 0xFFu;
           const int16_t* sf = c < 2 ? sf1 : sf2;
           const int ex = lx + (pos >> 4), ey = ly + (pos & 15);
-          const int xe = min(ex + n, xhi), ye = min(ey + n, yhi);
+          const int xs = ex - n, xe = min(ex + n, xhi), ye = min(ey + n, yhi);
+          // row-wise packed scan: two responses per 32-bit word, VIMNMX.U16x2 reduction, one exit test per row.
+          // Maxima are handled as minima of the complemented values; lanes outside [xs, xe] are forced to 0xFFFF.
+          const uint32_t flip = is_min ? 0u : 0xFFFFFFFFu;
+          const uint32_t target = is_min ? (uint32_t)val : (uint32_t)(0xFFFF - val);
+          const int w0 = xs >> 1, w1 = xe >> 1;
+          const uint32_t m0 = (xs & 1) ? 0x0000FFFFu : 0u, m1 = (xe & 1) ? 0u : 0xFFFF0000u;
           for (int j2 = ey - n; j2 <= ye; j2++) {
-            const int16_t* row = sf + j2 * FS;
-            for (int i2 = ex - n; i2 <= xe; i2++) {
-              const int v = row[i2];
-              if (is_min ? (v < val) : (v > val)) return 0xFFu;
+            const uint32_t* row = (const uint32_t*)(sf + j2 * FS);
+            uint32_t acc = (row[w0] ^ flip) | m0;
+            if (w1 > w0) {
+#pragma unroll 4
+              for (int wq = w0 + 1; wq < w1; wq++) acc = __vminu2(acc, row[wq] ^ flip);
+              acc = __vminu2(acc, (row[w1] ^ flip) | m1);
+            } else {
+              acc |= m1;
             }
+            if (min(acc & 0xFFFFu, acc >> 16) < target) return 0xFFu;
           }
           return (uint32_t)pos;
         };
