@@ -188,7 +188,7 @@ __device__ __forceinline__ bool mbar_wait_or_trap(uint32_t bar, uint32_t phase) 
 }
 
 __global__ void __launch_bounds__(FILTER_THREADS, 2)
-k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __grid_constant__ CUtensorMap tmap, int use_tma, int max_cells) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int slot = sl.s[blockIdx.z];
   const FrameDev F = frames[slot];
@@ -288,25 +288,41 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
 
   // ---- phase 3
   {
-    const int cshift = fx0 - fxs;                                          // response column of pixel fx0
+    uint32_t* s_code = (uint32_t*)(s_bar + 2);                             // one code word per owned cell (both passes)
+    uint32_t* s_queue = s_code + max_cells;                                // candidates that passed the tau test
+    int* s_qn = (int*)(s_bar + 1);
     const int xhi = g.wm - 1 - VISO_MARGIN - fxs, yhi = g.hm - 1 - VISO_MARGIN - fy0;   // window clamps, smem coordinates
-    (void)cshift;
-    for (int p = g.first_pass; p < 2; p++) {
-      const int n = g.n[p], step = n + 1, org = n + VISO_MARGIN;
-      int a = x0 - org; const int klo = a > 0 ? (a + step - 1) / step : 0;
+    int klo[2], nk[2], llo[2], nl[2], cbase[2];
+    int ncell_total = 0;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      klo[p] = llo[p] = nk[p] = nl[p] = 0; cbase[p] = ncell_total;
+      if (p < g.first_pass) continue;
+      const int step = g.n[p] + 1, org = g.n[p] + VISO_MARGIN;
+      int a = x0 - org; klo[p] = a > 0 ? (a + step - 1) / step : 0;
       int b = x0 + TW - org; const int khi = b > 0 ? min((b + step - 1) / step, g.ncx[p]) : 0;
-      a = y0 - org; const int llo = a > 0 ? (a + step - 1) / step : 0;
+      a = y0 - org; llo[p] = a > 0 ? (a + step - 1) / step : 0;
       b = y0 + TH - org; const int lhi = b > 0 ? min((b + step - 1) / step, g.ncy[p]) : 0;
-      const int nk = max(khi - klo, 0), nl = max(lhi - llo, 0);
-      const int ncell = nk * nl;
+      nk[p] = max(khi - klo[p], 0); nl[p] = max(lhi - llo[p], 0);
+      ncell_total += nk[p] * nl[p];
+    }
+    if (tid == 0) *s_qn = 0;
+    __syncthreads();
+
+    // 3a: cell extrema.  Dense cells: one thread per cell; sparse cells: four lanes per cell, each scanning every
+    // fourth column, combined with warp shuffles.  Candidates that pass the tau test are queued.
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      if (p < g.first_pass) continue;
+      const int n = g.n[p], step = n + 1, org = n + VISO_MARGIN;
+      const int ncell = nk[p] * nl[p];
       const int G = p == 0 ? 4 : 1;                                        // lanes per cell
       const int nitem = ((ncell * G + 31) & ~31);                          // whole warps take part in the shuffles
       for (int item = tid; item < nitem; item += FILTER_THREADS) {
         const int cell = item / G, t = item - cell * G;
         const bool live = cell < ncell;
-        const int kk = live ? cell % nk : 0, ll = live ? cell / nk : 0;
-        const int k = klo + kk, l = llo + ll;
-        const int lx = org + k * step - fxs, ly = org + l * step - fy0;
+        const int kk = live ? cell % nk[p] : 0, ll = live ? cell / nk[p] : 0;
+        const int lx = org + (klo[p] + kk) * step - fxs, ly = org + (llo[p] + ll) * step - fy0;
         int k1min = 0x7FFFFFFF, k1max = -1, k2min = 0x7FFFFFFF, k2max = -1;
         if (live) {
           for (int di = t; di <= n; di += G) {
@@ -327,49 +343,68 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
             k2min = min(k2min, __shfl_xor_sync(0xFFFFFFFFu, k2min, o)); k2max = max(k2max, __shfl_xor_sync(0xFFFFFFFFu, k2max, o));
           }
         }
-        // candidate c: 0 = f1 min, 1 = f1 max, 2 = f2 min, 3 = f2 max.  Keep it iff it passes the tau test and nothing
-        // in its clamped (2n+1)^2 window is strictly better; positions inside the cell can never be strictly better
-        // than the cell extremum, so the reference's cell exclusion is implied.
-        auto candidate = [&](int c) -> uint32_t {
-          const int key = c == 0 ? k1min : (c == 1 ? k1max : (c == 2 ? k2min : k2max));
-          const bool is_min = (c & 1) == 0;
-          const int val = key >> 8, pos = is_min ? (key & 255) : 255 - (key & 255);
-          const int bias = c < 2 ? BIAS_F1 : BIAS_F2;
-          if (is_min ? (val > bias - g.tau) : (val < bias + g.tau)) return 0xFFu;
-          const int16_t* sf = c < 2 ? sf1 : sf2;
-          const int ex = lx + (pos >> 4), ey = ly + (pos & 15);
-          const int xs = ex - n, xe = min(ex + n, xhi), ye = min(ey + n, yhi);
-          // row-wise packed scan: two responses per 32-bit word, VIMNMX.U16x2 reduction, one exit test per row.
-          // Maxima are handled as minima of the complemented values; lanes outside [xs, xe] are forced to 0xFFFF.
-          const uint32_t flip = is_min ? 0u : 0xFFFFFFFFu;
-          const uint32_t target = is_min ? (uint32_t)val : (uint32_t)(0xFFFF - val);
-          const int w0 = xs >> 1, w1 = xe >> 1;
-          const uint32_t m0 = (xs & 1) ? 0x0000FFFFu : 0u, m1 = (xe & 1) ? 0u : 0xFFFF0000u;
-          for (int j2 = ey - n; j2 <= ye; j2++) {
-            const uint32_t* row = (const uint32_t*)(sf + j2 * FS);
-            uint32_t acc = (row[w0] ^ flip) | m0;
-            if (w1 > w0) {
-#pragma unroll 4
-              for (int wq = w0 + 1; wq < w1; wq++) acc = __vminu2(acc, row[wq] ^ flip);
-              acc = __vminu2(acc, (row[w1] ^ flip) | m1);
-            } else {
-              acc |= m1;
-            }
-            if (min(acc & 0xFFFFu, acc >> 16) < target) return 0xFFu;
+        if (live) {
+          if (t == 0) s_code[cbase[p] + cell] = 0xFFFFFFFFu;
+          // class c: 0 = f1 min, 1 = f1 max, 2 = f2 min, 3 = f2 max
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            if (G == 4 && c != t) continue;
+            const int key = c == 0 ? k1min : (c == 1 ? k1max : (c == 2 ? k2min : k2max));
+            const bool is_min = (c & 1) == 0;
+            const int val = key >> 8, pos = is_min ? (key & 255) : 255 - (key & 255);
+            const int bias = c < 2 ? BIAS_F1 : BIAS_F2;
+            if (is_min ? (val <= bias - g.tau) : (val >= bias + g.tau))
+              s_queue[atomicAdd(s_qn, 1)] = (uint32_t)(cbase[p] + cell) | ((uint32_t)c << 16) | ((uint32_t)pos << 18) | ((uint32_t)p << 26);
           }
-          return (uint32_t)pos;
-        };
-        uint32_t code;
-        if (G == 4) {
-          code = (live ? candidate(t) : 0xFFu) << (8 * t);
-          code |= __shfl_xor_sync(0xFFFFFFFFu, code, 1);
-          code |= __shfl_xor_sync(0xFFFFFFFFu, code, 2);
-        } else {
-          code = 0xFFFFFFFFu;
-          if (live) code = candidate(0) | (candidate(1) << 8) | (candidate(2) << 16) | (candidate(3) << 24);
         }
-        if (live && t == 0) F.codes[p][(size_t)k * g.ncy[p] + l] = code;
       }
+    }
+    __syncthreads();
+
+    // 3b: one thread per queued candidate.  Keep it iff nothing in its clamped (2n+1)^2 window is strictly better;
+    // positions inside the cell can never be strictly better than the cell extremum, so the reference's cell
+    // exclusion is implied.  Row-wise packed scan: two responses per 32-bit word, VIMNMX.U16x2 reduction, one exit
+    // test per row; maxima are handled as minima of the complemented values; lanes outside the window read as 0xFFFF.
+    const int nq = *s_qn;
+    for (int q = tid; q < nq; q += FILTER_THREADS) {
+      const uint32_t ent = s_queue[q];
+      const int p = ent >> 26, c = (ent >> 16) & 3, pos = (ent >> 18) & 255, gcell = ent & 0xFFFF;
+      const int cell = gcell - cbase[p];
+      const int n = g.n[p], step = n + 1, org = n + VISO_MARGIN;
+      const int kk = cell % nk[p], ll = cell / nk[p];
+      const int lx = org + (klo[p] + kk) * step - fxs, ly = org + (llo[p] + ll) * step - fy0;
+      const int16_t* sf = c < 2 ? sf1 : sf2;
+      const bool is_min = (c & 1) == 0;
+      const int ex = lx + (pos >> 4), ey = ly + (pos & 15);
+      const int val = sf[ey * FS + ex];
+      const int xs = ex - n, xe = min(ex + n, xhi), ye = min(ey + n, yhi);
+      const uint32_t flip = is_min ? 0u : 0xFFFFFFFFu;
+      const uint32_t target = is_min ? (uint32_t)val : (uint32_t)(0xFFFF - val);
+      const int w0 = xs >> 1, w1 = xe >> 1;
+      const uint32_t m0 = (xs & 1) ? 0x0000FFFFu : 0u, m1 = (xe & 1) ? 0u : 0xFFFF0000u;
+      bool keep = true;
+      for (int j2 = ey - n; j2 <= ye; j2++) {
+        const uint32_t* row = (const uint32_t*)(sf + j2 * FS);
+        uint32_t acc = (row[w0] ^ flip) | m0;
+        if (w1 > w0) {
+#pragma unroll 4
+          for (int wq = w0 + 1; wq < w1; wq++) acc = __vminu2(acc, row[wq] ^ flip);
+          acc = __vminu2(acc, (row[w1] ^ flip) | m1);
+        } else {
+          acc |= m1;
+        }
+        if (min(acc & 0xFFFFu, acc >> 16) < target) { keep = false; break; }
+      }
+      if (keep) ((uint8_t*)s_code)[4 * gcell + c] = (uint8_t)pos;
+    }
+    __syncthreads();
+
+    // 3c: code words to global memory, cell-column-major
+    for (int idx = tid; idx < ncell_total; idx += FILTER_THREADS) {
+      const int p = (idx >= cbase[1] && nk[1] * nl[1] > 0) ? 1 : 0;
+      const int cell = idx - cbase[p];
+      const int kk = cell % nk[p], ll = cell / nk[p];
+      F.codes[p][(size_t)(klo[p] + kk) * g.ncy[p] + (llo[p] + ll)] = s_code[idx];
     }
   }
 }
@@ -561,13 +596,17 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
   const int nmax = g.first_pass == 0 ? (g.n[0] > g.n[1] ? g.n[0] : g.n[1]) : g.n[1];
   {
     const TileShape ts = tile_shape(nmax);
-    if (ts.smem > ctx->filter_smem_attr) {
-      CU_TRY(ctx, cudaFuncSetAttribute(k_filter_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts.smem));
-      ctx->filter_smem_attr = ts.smem;
+    // owned NMS cells of one tile (both passes): code words + a queue of up to four candidates per cell
+    int max_cells = 0;
+    for (int p = g.first_pass; p < 2; p++) max_cells += ((TW + g.n[p]) / (g.n[p] + 1) + 1) * ((TH + g.n[p]) / (g.n[p] + 1) + 1);
+    const size_t smem_bytes = ts.smem + (size_t)max_cells * 20;
+    if (smem_bytes > ctx->filter_smem_attr) {
+      CU_TRY(ctx, cudaFuncSetAttribute(k_filter_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      ctx->filter_smem_attr = smem_bytes;
     }
     dim3 grid((g.bplm + TW - 1) / TW, (g.hm + TH - 1) / TH, sl.n);
     if (ctx->profile) CU_TRY(ctx, cudaEventRecord(ctx->pev0, st));
-    k_filter_nms<<<grid, FILTER_THREADS, ts.smem, st>>>(g, ctx->frames_d, sl, nmax, ctx->tmap_img, ctx->use_tma);
+    k_filter_nms<<<grid, FILTER_THREADS, smem_bytes, st>>>(g, ctx->frames_d, sl, nmax, ctx->tmap_img, ctx->use_tma, max_cells);
     CU_LAUNCH_CHECK(ctx);
     if (ctx->profile) {
       // profiling mode only: this synchronises the stream after every fused launch
