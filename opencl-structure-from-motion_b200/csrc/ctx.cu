@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 
 static thread_local std::string g_create_error;
 
@@ -47,6 +48,7 @@ extern "C" int visocu_create(int device, visocu_ctx** out) {
     return VISOCU_ECUDA;
   }
   cudaMemset(ctx->d_stats, 0, 2 * sizeof(uint64_t));
+  if (const char* e = getenv("VISOCU_DBG")) ctx->dbg_flags = atoi(e);
   *out = ctx;
   return VISOCU_OK;
 }

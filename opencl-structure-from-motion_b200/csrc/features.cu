@@ -188,7 +188,7 @@ __device__ __forceinline__ bool mbar_wait_or_trap(uint32_t bar, uint32_t phase) 
 }
 
 __global__ void __launch_bounds__(FILTER_THREADS, 2)
-k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __grid_constant__ CUtensorMap tmap, int use_tma, int max_cells) {
+k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __grid_constant__ CUtensorMap tmap, int use_tma, int max_cells, int dbg) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int slot = sl.s[blockIdx.z];
   const FrameDev F = frames[slot];
@@ -308,6 +308,7 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
     }
     if (tid == 0) *s_qn = 0;
     __syncthreads();
+    if (dbg & 2) return;
 
     // 3a: cell extrema.  Dense cells: one thread per cell; sparse cells: four lanes per cell, each scanning every
     // fourth column, combined with warp shuffles.  Candidates that pass the tau test are queued.
@@ -330,9 +331,9 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
             const int16_t* q2 = sf2 + ly * FS + lx + di;
             for (int dj = 0; dj <= n; dj++) {
               const int pos = (di << 4) | dj;
-              const int v1 = q1[dj * FS], v2 = q2[dj * FS];
-              k1min = min(k1min, (v1 << 8) | pos); k1max = max(k1max, (v1 << 8) | (255 - pos));
-              k2min = min(k2min, (v2 << 8) | pos); k2max = max(k2max, (v2 << 8) | (255 - pos));
+              const int a1 = q1[dj * FS] * 256 + pos, a2 = q2[dj * FS] * 256 + pos;      // (value << 8) | position
+              k1min = min(k1min, a1); k1max = max(k1max, a1 ^ 255);                    // ^255: position -> 255 - position
+              k2min = min(k2min, a2); k2max = max(k2max, a2 ^ 255);
             }
           }
         }
@@ -365,7 +366,7 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
     // positions inside the cell can never be strictly better than the cell extremum, so the reference's cell
     // exclusion is implied.  Row-wise packed scan: two responses per 32-bit word, VIMNMX.U16x2 reduction, one exit
     // test per row; maxima are handled as minima of the complemented values; lanes outside the window read as 0xFFFF.
-    const int nq = *s_qn;
+    const int nq = (dbg & 1) ? 0 : *s_qn;     // dbg: timing experiments only (profiles/), results are wrong when set
     for (int q = tid; q < nq; q += FILTER_THREADS) {
       const uint32_t ent = s_queue[q];
       const int p = ent >> 26, c = (ent >> 16) & 3, pos = (ent >> 18) & 255, gcell = ent & 0xFFFF;
@@ -383,7 +384,11 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
       const int w0 = xs >> 1, w1 = xe >> 1;
       const uint32_t m0 = (xs & 1) ? 0x0000FFFFu : 0u, m1 = (xe & 1) ? 0u : 0xFFFF0000u;
       bool keep = true;
-      for (int j2 = ey - n; j2 <= ye; j2++) {
+      // rows are visited centre-out (ey, ey-1, ey+1, ...): responses are smooth, so a candidate that is not a window
+      // extremum is usually beaten by a close neighbour and leaves after one or two rows
+      for (int d = 0; d <= 2 * n && keep; d++) {
+        const int j2 = ey + ((d & 1) ? -((d + 1) >> 1) : (d >> 1));
+        if (j2 > ye) continue;
         const uint32_t* row = (const uint32_t*)(sf + j2 * FS);
         uint32_t acc = (row[w0] ^ flip) | m0;
         if (w1 > w0) {
@@ -393,7 +398,7 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
         } else {
           acc |= m1;
         }
-        if (min(acc & 0xFFFFu, acc >> 16) < target) { keep = false; break; }
+        if (min(acc & 0xFFFFu, acc >> 16) < target) keep = false;
       }
       if (keep) ((uint8_t*)s_code)[4 * gcell + c] = (uint8_t)pos;
     }
@@ -606,7 +611,7 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
     }
     dim3 grid((g.bplm + TW - 1) / TW, (g.hm + TH - 1) / TH, sl.n);
     if (ctx->profile) CU_TRY(ctx, cudaEventRecord(ctx->pev0, st));
-    k_filter_nms<<<grid, FILTER_THREADS, smem_bytes, st>>>(g, ctx->frames_d, sl, nmax, ctx->tmap_img, ctx->use_tma, max_cells);
+    k_filter_nms<<<grid, FILTER_THREADS, smem_bytes, st>>>(g, ctx->frames_d, sl, nmax, ctx->tmap_img, ctx->use_tma, max_cells, ctx->dbg_flags);
     CU_LAUNCH_CHECK(ctx);
     if (ctx->profile) {
       // profiling mode only: this synchronises the stream after every fused launch
