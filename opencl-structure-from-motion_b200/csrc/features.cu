@@ -384,11 +384,7 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
       const int w0 = xs >> 1, w1 = xe >> 1;
       const uint32_t m0 = (xs & 1) ? 0x0000FFFFu : 0u, m1 = (xe & 1) ? 0u : 0xFFFF0000u;
       bool keep = true;
-      // rows are visited centre-out (ey, ey-1, ey+1, ...): responses are smooth, so a candidate that is not a window
-      // extremum is usually beaten by a close neighbour and leaves after one or two rows
-      for (int d = 0; d <= 2 * n && keep; d++) {
-        const int j2 = ey + ((d & 1) ? -((d + 1) >> 1) : (d >> 1));
-        if (j2 > ye) continue;
+      for (int j2 = ey - n; j2 <= ye && keep; j2++) {
         const uint32_t* row = (const uint32_t*)(sf + j2 * FS);
         uint32_t acc = (row[w0] ^ flip) | m0;
         if (w1 > w0) {

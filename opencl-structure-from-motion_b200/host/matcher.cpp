@@ -7,6 +7,8 @@
 #include "matcher.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +21,17 @@
 using std::vector;
 
 namespace visob {
+// optional per-stage wall-clock accounting of the host layer (bench.py --host-timing); seconds, summed over threads
+std::atomic<long long> g_stage_ns[8];
+std::atomic<long long> g_stage_calls[8];
+struct StageTimer {
+  int id; std::chrono::steady_clock::time_point t0;
+  explicit StageTimer(int id) : id(id), t0(std::chrono::steady_clock::now()) {}
+  ~StageTimer() {
+    g_stage_ns[id] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    g_stage_calls[id]++;
+  }
+};
 static thread_local int t_device = 0;
 void set_device(int device) { t_device = device; }
 int current_device() { return t_device; }
@@ -73,6 +86,7 @@ void Matcher::push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool re
     std::cerr << "ERROR: Image dimension mismatch!" << std::endl;
     return;
   }
+  visob::StageTimer timer(0);
   if (!ensureContext(width, height)) return;
   if (!replace) {
     // current -> previous: the device frames swap roles, nothing is copied
@@ -115,6 +129,7 @@ void Matcher::push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool re
 }
 
 bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_prior, bool refine) {
+  visob::StageTimer timer(1 + pass);
   visocu_quad q = {slot[0], slot[1], slot[2], slot[3]};
   const int32_t base = pass == 0 ? 0 : 4;
   const int32_t nq = method == 0 ? n_feat[base + 2] : n_feat[base + 0];
@@ -217,6 +232,7 @@ float Matcher::getGain(vector<int32_t> inliers) {
 }
 
 void Matcher::computePriorStatistics(vector<p_match>& p_matched, int32_t method) {
+  visob::StageTimer timer(3);
   const float bs = (float)param.match_binsize;
   const int32_t ub = (int32_t)ceil((float)dims_c[0] / bs), vb = (int32_t)ceil((float)dims_c[1] / bs);
   const int32_t nbin = ub * vb, stages = method == 2 ? 4 : 2, nd = stages * 2;
@@ -278,6 +294,7 @@ void Matcher::computePriorStatistics(vector<p_match>& p_matched, int32_t method)
 void Matcher::removeOutliers(vector<p_match>& p_matched, int32_t method) {
   const int32_t n = (int32_t)p_matched.size();
   if (n <= 3) return;
+  visob::StageTimer timer(n < 2000 ? 4 : 5);
   static thread_local vector<int32_t> x, y, edges, support;
   x.resize(n); y.resize(n);
   for (int32_t i = 0; i < n; i++) { x[i] = (int32_t)p_matched[i].u1c; y[i] = (int32_t)p_matched[i].v1c; }

@@ -50,6 +50,14 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def stage_times(reset=True):
+    """Host-layer wall-clock per stage, summed over worker threads: dict name -> (seconds, calls)."""
+    sec = np.zeros(8); calls = np.zeros(8, np.int64)
+    lib().visob_stage_times(_p(sec), _p(calls), int(reset))
+    names = ['pushBack', 'matching_pass1', 'matching_pass2', 'priors', 'removeOutliers_small', 'removeOutliers_large']
+    return {n: (float(sec[k]), int(calls[k])) for k, n in enumerate(names)}
+
+
 def set_device(d):
     lib().visob_set_device(int(d))
 
