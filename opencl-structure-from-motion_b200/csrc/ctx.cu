@@ -20,6 +20,12 @@ int visocu_set_error(visocu_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
+cudaError_t visocu_stream_wait(visocu_ctx* ctx) {
+  if (!ctx->ev_sync) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_sync);
+}
+
 extern "C" const char* visocu_last_error(const visocu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int visocu_create(int device, visocu_ctx** out) {
@@ -49,6 +55,9 @@ extern "C" int visocu_create(int device, visocu_ctx** out) {
   }
   cudaMemset(ctx->d_stats, 0, 2 * sizeof(uint64_t));
   if (const char* e = getenv("VISOCU_DBG")) ctx->dbg_flags = atoi(e);
+  // VISOCU_BLOCKING_SYNC=1: waiting host threads sleep (for runs with more worker threads than cores)
+  if (const char* e = getenv("VISOCU_BLOCKING_SYNC"))
+    if (e[0] == '1') cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming);
   *out = ctx;
   return VISOCU_OK;
 }
@@ -69,6 +78,7 @@ extern "C" void visocu_destroy(visocu_ctx* ctx) {
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->pev0) cudaEventDestroy(ctx->pev0);
   if (ctx->pev1) cudaEventDestroy(ctx->pev1);
+  if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -86,7 +96,7 @@ extern "C" int visocu_device_info(const visocu_ctx* ctx, int32_t* sm_count, int3
 
 int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->scratch_bytes) return VISOCU_OK;
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   if (ctx->scratch) cudaFree(ctx->scratch);
   ctx->scratch = nullptr; ctx->scratch_bytes = 0;
   size_t want = align_up(bytes + bytes / 4, 1 << 20);
@@ -97,7 +107,7 @@ int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes) {
 
 int visocu_ensure_pinned(visocu_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->pinned_bytes) return VISOCU_OK;
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   ctx->pinned = nullptr; ctx->pinned_bytes = 0;
   size_t want = align_up(bytes + bytes / 4, 1 << 16);
@@ -115,7 +125,7 @@ extern "C" int visocu_configure(visocu_ctx* ctx, const visocu_params* p, int32_t
   if (p->nms_n < 1 || p->nms_n > 14) return visocu_set_error(ctx, VISOCU_EINVAL, "nms_n=%d outside the supported range 1..14", p->nms_n);
   if (p->match_binsize < 1) return visocu_set_error(ctx, VISOCU_EINVAL, "match_binsize must be positive");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   free_pool(ctx);
   ctx->param = *p;
   Geometry& g = ctx->g;
@@ -179,7 +189,7 @@ extern "C" int visocu_configure(visocu_ctx* ctx, const visocu_params* p, int32_t
   }
   CU_TRY(ctx, cudaMalloc(&ctx->frames_d, sizeof(FrameDev) * (size_t)n_frames));
   CU_COPY(ctx, ctx->frames_d, ctx->frames_h.data(), sizeof(FrameDev) * (size_t)n_frames, cudaMemcpyHostToDevice);
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   ctx->n_frames = n_frames;
   {
     int rc = visocu_make_tensor_map(ctx, per);
@@ -194,7 +204,7 @@ extern "C" int visocu_configure(visocu_ctx* ctx, const visocu_params* p, int32_t
 extern "C" int visocu_sync(visocu_ctx* ctx) {
   if (!ctx) return VISOCU_EINVAL;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   return VISOCU_OK;
 }
 extern "C" int visocu_timer_start(visocu_ctx* ctx) {
@@ -238,7 +248,7 @@ extern "C" int visocu_memcpy_h2d(visocu_ctx* ctx, void* dst, const void* src, si
   if (!ctx) return VISOCU_EINVAL;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   CU_COPY(ctx, dst, src, bytes, cudaMemcpyHostToDevice);
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   return VISOCU_OK;
 }
 extern "C" int visocu_transfer_bytes(const visocu_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {
@@ -285,7 +295,7 @@ extern "C" int visocu_frame_counts(visocu_ctx* ctx, int32_t n, const int32_t* fr
   int32_t* stage = (int32_t*)ctx->pinned;
   for (int i = 0; i < n; i++)
     CU_COPY(ctx, stage + 4 * i, ctx->frames_h[frames[i]].counts, 16, cudaMemcpyDeviceToHost);
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   for (int i = 0; i < n; i++) {
     if (stage[4 * i + 2]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "feature list of frame %d overflowed", frames[i]);
     ctx->h_counts[2 * (size_t)frames[i] + 0] = stage[4 * i + 0];
@@ -336,7 +346,7 @@ extern "C" int visocu_get_features(visocu_ctx* ctx, int32_t frame, int32_t pass,
   if (cap < n) return visocu_set_error(ctx, VISOCU_ECAPACITY, "need room for %d records", n);
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if (n > 0) CU_COPY(ctx, out12, ctx->frames_h[frame].rec[pass], (size_t)n * 48, cudaMemcpyDeviceToHost);
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   return VISOCU_OK;
 }
 
@@ -364,6 +374,6 @@ extern "C" int visocu_get_plane(visocu_ctx* ctx, int32_t frame, int32_t which, u
   if (cap < bytes) return visocu_set_error(ctx, VISOCU_ECAPACITY, "plane needs %zu bytes", bytes);
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   CU_COPY(ctx, out, src, bytes, cudaMemcpyDeviceToHost);
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   return VISOCU_OK;
 }

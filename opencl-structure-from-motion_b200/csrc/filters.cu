@@ -124,7 +124,7 @@ int run_filter(visocu_ctx* ctx, const uint8_t* in, uint8_t* oa, uint8_t* ob, int
   } else {
     CU_COPY(ctx, o16, d_16, n * 2, cudaMemcpyDeviceToHost);
   }
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   return VISOCU_OK;
 }
 
@@ -168,7 +168,7 @@ extern "C" int visocu_nms(visocu_ctx* ctx, const int16_t* f1, const int16_t* f2,
   CU_LAUNCH_CHECK(ctx);
   std::vector<uint32_t> codes(cells);
   CU_COPY(ctx, codes.data(), dc, cells * 4, cudaMemcpyDeviceToHost);
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   // expand the per-cell code words into the reference's (u, v, val, class) list, cell-column-major
   int n = 0;
   for (size_t c = 0; c < cells; c++) {

@@ -361,14 +361,14 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
       CU_LAUNCH_CHECK(ctx);
     }
     for (int j = 0; j < nb; j++) CU_COPY(ctx, pin_cnt + j, hj[j].n_out, 4, cudaMemcpyDeviceToHost);
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, visocu_stream_wait(ctx));
     for (int j = 0; j < nb; j++) {
       const int n = pin_cnt[j];
       n_out[start + j] = n;
       if (n > cap[start + j]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "job %d produced %d matches, room for %d", start + j, n, cap[start + j]);
       if (n > 0) CU_COPY(ctx, out[start + j], hj[j].out, (size_t)n * 48, cudaMemcpyDeviceToHost);
     }
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, visocu_stream_wait(ctx));
   }
   return VISOCU_OK;
 }
@@ -392,7 +392,7 @@ extern "C" int visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t me
   k_refine<<<dim3(gx, 1), 256, 0, ctx->stream>>>(ctx->g, (const MatchJob*)sb, method, d_list, n);
   CU_LAUNCH_CHECK(ctx);
   CU_COPY(ctx, inout, d_list, (size_t)n * 48, cudaMemcpyDeviceToHost);
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   return VISOCU_OK;
 }
 
@@ -401,7 +401,7 @@ extern "C" int visocu_match_stats(visocu_ctx* ctx, uint64_t* sad_candidates, uin
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   uint64_t now[2];
   CU_COPY(ctx, now, ctx->d_stats, sizeof now, cudaMemcpyDeviceToHost);
-  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
   if (sad_candidates) *sad_candidates = now[0] - ctx->h_stats[0];
   if (entries_scanned) *entries_scanned = now[1] - ctx->h_stats[1];
   ctx->h_stats[0] = now[0]; ctx->h_stats[1] = now[1];

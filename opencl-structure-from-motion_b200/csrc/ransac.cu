@@ -428,7 +428,7 @@ extern "C" int visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* con
       if (F_all && F_all[start + j])
         CU_COPY(ctx, F_all[start + j], hj[j].F_all, (size_t)iters * 72, cudaMemcpyDeviceToHost);
     }
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, visocu_stream_wait(ctx));
     for (int j = 0; j < nb; j++) {
       memcpy(F9 + 9 * (size_t)(start + j), pinF + 9 * j, 72);
       n_inliers[start + j] = pinN[2 * j];

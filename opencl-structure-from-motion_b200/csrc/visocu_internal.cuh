@@ -41,6 +41,7 @@ struct visocu_ctx {
   char name[64] = {0};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_sync = nullptr;     // blocking-sync event: host threads sleep instead of spinning while the GPU works
   std::string err;
   bool configured = false;
   visocu_params param{};
@@ -69,6 +70,7 @@ struct visocu_ctx {
 };
 
 int visocu_set_error(visocu_ctx* ctx, int code, const char* fmt, ...);
+cudaError_t visocu_stream_wait(visocu_ctx* ctx);     // waits for the context's stream (yielding the CPU if ev_sync exists)
 int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes);
 int visocu_ensure_pinned(visocu_ctx* ctx, size_t bytes);
 

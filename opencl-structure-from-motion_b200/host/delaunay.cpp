@@ -284,6 +284,11 @@ Handles triangulate(Scratch& S, const int32_t* x, const int32_t* y, int n) {
   S.m.he.reserve(12 * (size_t)nu);
   // root: vertical cut of the x-sorted list, children by alternating axes
   partition(S.v.data(), S.yl.data(), nu, 0, S.side.data(), S.tmp.data());
+  // renumber once more, in partition order: every subtree of the divide-and-conquer then works on a contiguous range
+  // of vertices (and of the edges it creates), which keeps the merge loops in cache
+  S.cnt.resize(nu); S.yl.resize(nu);
+  for (int i = 0; i < nu; i++) { S.cnt[i] = S.sx[S.v[i]]; S.yl[i] = S.sy[S.v[i]]; S.tmp[i] = S.orig[S.v[i]]; }
+  for (int i = 0; i < nu; i++) { S.sx[i] = S.cnt[i]; S.sy[i] = S.yl[i]; S.orig[i] = S.tmp[i]; S.v[i] = i; }
   return build(S.m, S.v.data(), nu, 0);
 }
 
