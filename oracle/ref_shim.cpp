@@ -26,6 +26,8 @@
 #include <iterator>
 #include <limits>
 #include <chrono>
+#include <mutex>
+#include <streambuf>
 #include <mm_malloc.h>
 
 #define private public
@@ -80,11 +82,26 @@ VisualOdometryMono::parameters to_ref(const RefMonoParams* p) {
 }
 
 // StartTimer prints "Estimate F time" / "Best plane time" on every estimateMotion call
-// (timer.hh:9-34, viso_mono.cpp:117-173); keep the test/bench stdout clean.
+// (timer.hh:9-34, viso_mono.cpp:117-173); keep the test/bench stdout clean.  Several threads may
+// run reference objects at once (bench.py times one sequence per host core), so the silencer is
+// reference counted and the sink is a stateless discard buffer.
+struct DiscardBuf : public std::streambuf {
+  int overflow(int c) override { return c; }
+  std::streamsize xsputn(const char*, std::streamsize n) override { return n; }
+};
 struct CoutSilencer {
-  std::streambuf* old; std::ostringstream sink;
-  CoutSilencer() : old(std::cout.rdbuf()) { std::cout.rdbuf(sink.rdbuf()); }
-  ~CoutSilencer() { std::cout.rdbuf(old); }
+  static std::mutex& mtx() { static std::mutex m; return m; }
+  static int& users() { static int n = 0; return n; }
+  static std::streambuf*& saved() { static std::streambuf* p = nullptr; return p; }
+  static DiscardBuf& sink() { static DiscardBuf b; return b; }
+  CoutSilencer() {
+    std::lock_guard<std::mutex> lock(mtx());
+    if (users()++ == 0) saved() = std::cout.rdbuf(&sink());
+  }
+  ~CoutSilencer() {
+    std::lock_guard<std::mutex> lock(mtx());
+    if (--users() == 0) std::cout.rdbuf(saved());
+  }
 };
 
 int copy_matches(const std::vector<Matcher::p_match>& v, void* out, int cap) {
@@ -384,7 +401,6 @@ REF_API double ref_time_mono_sequence(const RefMonoParams* p, uint8_t* imgs, siz
     if (per_pair_s) per_pair_s[k - 1] = s;
     if (ok_out) ok_out[k - 1] = ok ? 1 : 0;
     if (motions16) { Matrix T = vo.getMotion(); for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) motions16[16 * (k - 1) + 4 * i + j] = T.val[i][j]; }
-    quiet.sink.str("");
   }
   return total;
 }
