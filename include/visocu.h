@@ -99,15 +99,17 @@ int  visocu_nms(visocu_ctx* ctx, const int16_t* f1, const int16_t* f2, int32_t w
                 int32_t nms_n, int32_t tau, int32_t* out4, int32_t cap, int32_t* n_out);
 
 /* ---- SAD circle matching: Matcher::matching + findMatch (+ pixel refinement) ----
- * (matcher.cpp:965-1205, 892-963, 1456-1585).  method 0 = flow, 2 = quad.  pass 0 = sparse sets, 1 = dense.
- * ranges[j] (host, u_bins*v_bins entries, matcher.cpp:734-868) is read only if use_prior.  refine != 0 applies
- * relocateMinimum (refinement == 1 semantics) to the matches before they are returned.  out[j] receives at
- * most cap[j] matches in the reference's order (ascending i1c for flow, ascending i1p for quad). */
+ * (matcher.cpp:965-1205, 892-963, 1379-1585).  method 0 = flow, 1 = stereo, 2 = quad.  pass 0 = sparse sets,
+ * 1 = dense.  ranges[j] (host, u_bins*v_bins entries, matcher.cpp:734-868) is read only if use_prior.  refine = 1
+ * applies relocateMinimum (pixel), refine = 2 parabolicFitting (sub-pixel; drops the matches the reference drops)
+ * before the matches are returned.  out[j] receives at most cap[j] matches in the reference's order (ascending
+ * i1c for flow and stereo, ascending i1p for quad). */
 int  visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
                   int32_t use_prior, const visocu_range* const* ranges, int32_t refine,
                   visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out);
-/* pixel refinement alone on caller-supplied matches (Matcher::refinement with refinement == 1) */
-int  visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, visocu_pmatch* inout, int32_t n);
+/* Matcher::refinement alone on caller-supplied matches: mode 1 = pixel, 2 = sub-pixel (n_out <= n survive) */
+int  visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, int32_t mode, visocu_pmatch* inout, int32_t n,
+                   int32_t* n_out);
 /* work counters since the previous visocu_match_stats call: candidates that passed the window test (matcher.cpp:943) and
  * bin entries scanned, summed over all jobs and hops -- the SAD roofline unit of SURVEY.md 8(d) */
 int  visocu_match_stats(visocu_ctx* ctx, uint64_t* sad_candidates, uint64_t* entries_scanned);

@@ -15,6 +15,7 @@
 // "pixel already matched" rule (matcher.cpp:1036-1039) only ever involves the up-to-three preceding records
 // because two features share a pixel only when they come from the same NMS cell.
 #include "visocu_internal.cuh"
+#include <cmath>
 #include <cstring>
 
 namespace {
@@ -30,6 +31,7 @@ struct MatchJob {
   int4* res;                         // per query: the other three indices of the circle + accepted flag
   int32_t* blk;                      // accepted circles per CHUNK
   visocu_pmatch* out;
+  uint8_t* keep;                     // sub-pixel refinement: 0 = match dropped
   int32_t* n_out;
   const uint8_t* du[4];              // planes used by the refinement (full resolution)
   const uint8_t* dv[4];
@@ -109,6 +111,15 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(Geometry g, const Match
     const int i1p = find_match(g, J.s[2], i, J.s[0], stat_bin, 0, true, use_prior, J.ranges, active, sub, n_cand, n_scan);
     const int i1c2 = find_match(g, J.s[0], i1p, J.s[2], stat_bin, 1, true, use_prior, J.ranges, active, sub, n_cand, n_scan);
     res = make_int4(i1p, 0, 0, i1c2 == i);
+  } else if (method == 1) {
+    // stereo (matcher.cpp:1045-1084): current left -> current right -> back, positive disparity
+    int stat_bin = 0;
+    if (active) { const int2 uv = *(const int2*)(J.s[2].rec + (size_t)i * 12); stat_bin = bin_index(g, uv.x, uv.y); }
+    const int i2c = find_match(g, J.s[2], i, J.s[3], stat_bin, 0, false, use_prior, J.ranges, active, sub, n_cand, n_scan);
+    const int i1c2 = find_match(g, J.s[3], i2c, J.s[2], stat_bin, 1, false, use_prior, J.ranges, active, sub, n_cand, n_scan);
+    int ok = 0;
+    if (active && i1c2 == i) ok = J.s[2].rec[(size_t)i * 12] >= J.s[3].rec[(size_t)i2c * 12];
+    res = make_int4(i2c, 0, 0, ok);
   } else {
     int stat_bin = 0;
     if (active) { const int2 uv = *(const int2*)(J.s[0].rec + (size_t)i * 12); stat_bin = bin_index(g, uv.x, uv.y); }
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(Geometry g, const Match
 __device__ __forceinline__ int keep_flag(const MatchJob& J, int method, int i) {
   if (i >= J.nq) return 0;
   if (!J.res[i].w) return 0;
-  if (method != 0) return 1;
+  if (method == 2) return 1;                       // flow and stereo keep one match per current-left pixel
   const int2 uv = *(const int2*)(J.s[2].rec + (size_t)i * 12);
   for (int j = i - 1; j >= 0 && j >= i - 3; j--) {
     if (!J.res[j].w) continue;
@@ -209,6 +220,13 @@ __global__ void __launch_bounds__(CHUNK) k_match_emit(const MatchJob* jobs, int 
     m.u2p = -1.f; m.v2p = -1.f; m.i2p = -1;
     m.u1c = (float)c.x; m.v1c = (float)c.y; m.i1c = i;
     m.u2c = -1.f; m.v2c = -1.f; m.i2c = -1;
+  } else if (method == 1) {
+    const int2 c = *(const int2*)(J.s[2].rec + (size_t)i * 12);
+    const int2 d = *(const int2*)(J.s[3].rec + (size_t)r.x * 12);
+    m.u1p = -1.f; m.v1p = -1.f; m.i1p = -1;
+    m.u2p = -1.f; m.v2p = -1.f; m.i2p = -1;
+    m.u1c = (float)c.x; m.v1c = (float)c.y; m.i1c = i;
+    m.u2c = (float)d.x; m.v2c = (float)d.y; m.i2c = r.x;
   } else {
     const int2 a = *(const int2*)(J.s[0].rec + (size_t)i * 12);
     const int2 b = *(const int2*)(J.s[1].rec + (size_t)r.x * 12);
@@ -253,26 +271,135 @@ __device__ __forceinline__ void relocate(const uint8_t* du1, const uint8_t* dv1,
   v2 += (float)(best / 5) - 2.0f;
 }
 
-__global__ void __launch_bounds__(256) k_refine(Geometry g, const MatchJob* jobs, int method, visocu_pmatch* direct, int n_direct) {
+// (AtA)^-1 At of the 9 x 6 design matrix [j^2, i^2, i*j, j, i, 1], i, j = -1..1 (matcher.cpp:1509-1521): the
+// least-squares paraboloid through the 3x3 costs around the integer minimum is b = c_pinv * costs.
+__constant__ double c_pinv[54];
+
+// sub-pixel variant (parabolicFitting, matcher.cpp:1379-1454): 7x7 integer costs, first minimum, reject minima on the
+// border of the search area, paraboloid fit, reject offsets of a pixel or more.  Returns false if the match is dropped.
+__device__ __forceinline__ bool parabolic(const uint8_t* du1, const uint8_t* dv1, const uint8_t* du2, const uint8_t* dv2,
+                                          int bpl, int w, int h, float u1, float v1, float& u2, float& v2, int lane) {
+  if (u2 - 3 < VISO_MARGIN || u2 + 3 > w - 1 - VISO_MARGIN || v2 - 3 < VISO_MARGIN || v2 + 3 > h - 1 - VISO_MARGIN) return false;
+  const int iu1 = (int)u1, iv1 = (int)v1, iu2 = (int)u2, iv2 = (int)v2;
+  int cost[2];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int idx = lane + 32 * r;
+    int sad = 0x7FFFFF;
+    if (idx < 49) {
+      const int cu = iu2 + idx % 7 - 3, cv = iv2 + idx / 7 - 3;
+      sad = 0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const int dx = c_sd_dx[k], dy = c_sd_dy[k];
+        const uint8_t* p1 = c_sd_plane[k] ? dv1 : du1;
+        const uint8_t* p2 = c_sd_plane[k] ? dv2 : du2;
+        sad += abs((int)p1[(size_t)(iv1 + dy) * bpl + iu1 + dx] - (int)p2[(size_t)(cv + dy) * bpl + cu + dx]);
+      }
+    }
+    cost[r] = sad;
+  }
+  int key = min(cost[0] * 64 + lane, cost[1] * 64 + lane + 32);
+  key = __reduce_min_sync(0xFFFFFFFFu, key);
+  const int best = key & 63, bu = best % 7, bv = best / 7;
+  if (bu == 0 || bu == 6 || bv == 0 || bv == 6) return false;
+  double b[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < 9; q++) {
+    const int idx = (bv + q / 3 - 1) * 7 + (bu + q % 3 - 1);
+    const double c = (double)__shfl_sync(0xFFFFFFFFu, idx < 32 ? cost[0] : cost[1], idx & 31);
+#pragma unroll
+    for (int r = 0; r < 6; r++) b[r] = fma(c_pinv[r * 9 + q], c, b[r]);
+  }
+  const float divisor = (float)(b[2] * b[2] - 4.0 * b[0] * b[1]);
+  if (fabsf(divisor) < 1e-8 || fabs(b[2]) < 1e-8) return false;
+  const float ddv = (float)((2.0 * b[0] * b[4] - b[2] * b[3]) / (double)divisor);
+  const float ddu = (float)(-(b[4] + 2.0 * b[1] * (double)ddv) / b[2]);
+  if (fabsf(ddu) >= 1.0f || fabsf(ddv) >= 1.0f) return false;
+  u2 = (float)((double)u2 + ((double)(float)bu - 3.0 + (double)ddu));
+  v2 = (float)((double)v2 + ((double)(float)bv - 3.0 + (double)ddv));
+  return true;
+}
+
+// mode 1 = relocateMinimum (pixel), 2 = parabolicFitting (sub-pixel, may drop the match: keep[i] = 0)
+__global__ void __launch_bounds__(256) k_refine(Geometry g, const MatchJob* jobs, int method, int mode, visocu_pmatch* direct,
+                                                int n_direct, uint8_t* keep_direct) {
   const MatchJob& J = jobs[blockIdx.y];
   const int n = direct ? n_direct : *J.n_out;
   visocu_pmatch* list = direct ? direct : J.out;
+  uint8_t* keep = direct ? keep_direct : J.keep;
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
     visocu_pmatch m = list[i];
-    // reference descriptor always at (u1c,v1c) of the current left image (matcher.cpp:1544-1577)
-    relocate(J.du[2], J.dv[2], J.du[0], J.dv[0], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u1p, m.v1p, lane);
-    if (method == 2) {
-      relocate(J.du[2], J.dv[2], J.du[3], J.dv[3], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u2c, m.v2c, lane);
-      relocate(J.du[2], J.dv[2], J.du[1], J.dv[1], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u2p, m.v2p, lane);
+    bool ok = true;
+    // the reference descriptor is always taken at (u1c,v1c) of the current left image (matcher.cpp:1544-1577);
+    // hops: previous left (flow, quad), current right (stereo, quad), previous right (quad)
+    if (method == 0 || method == 2) {
+      if (mode == 2) ok = parabolic(J.du[2], J.dv[2], J.du[0], J.dv[0], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u1p, m.v1p, lane);
+      else relocate(J.du[2], J.dv[2], J.du[0], J.dv[0], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u1p, m.v1p, lane);
     }
-    if (lane == 0) list[i] = m;
+    if (ok && (method == 1 || method == 2)) {
+      if (mode == 2) ok = parabolic(J.du[2], J.dv[2], J.du[3], J.dv[3], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u2c, m.v2c, lane);
+      else relocate(J.du[2], J.dv[2], J.du[3], J.dv[3], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u2c, m.v2c, lane);
+    }
+    if (ok && method == 2) {
+      if (mode == 2) ok = parabolic(J.du[2], J.dv[2], J.du[1], J.dv[1], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u2p, m.v2p, lane);
+      else relocate(J.du[2], J.dv[2], J.du[1], J.dv[1], g.bpl, g.w, g.h, m.u1c, m.v1c, m.u2p, m.v2p, lane);
+    }
+    if (lane == 0) {
+      list[i] = m;
+      if (keep) keep[i] = ok ? 1 : 0;
+    }
   }
+}
+
+// host: pseudo-inverse of the paraboloid design matrix by Gauss-Jordan elimination with partial pivoting
+void make_pinv(double* out54) {
+  double A[9][6], M[6][12];
+  for (int q = 0; q < 9; q++) {
+    const double i = q / 3 - 1, j = q % 3 - 1;
+    const double row[6] = {j * j, i * i, i * j, j, i, 1};
+    for (int c = 0; c < 6; c++) A[q][c] = row[c];
+  }
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) {
+      double s = 0;
+      for (int q = 0; q < 9; q++) s += A[q][r] * A[q][c];
+      M[r][c] = s; M[r][6 + c] = r == c;
+    }
+  for (int c = 0; c < 6; c++) {
+    int piv = c;
+    for (int r = c + 1; r < 6; r++) if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
+    for (int k = 0; k < 12; k++) { double t = M[c][k]; M[c][k] = M[piv][k]; M[piv][k] = t; }
+    const double d = M[c][c];
+    for (int k = 0; k < 12; k++) M[c][k] /= d;
+    for (int r = 0; r < 6; r++) {
+      if (r == c) continue;
+      const double f = M[r][c];
+      for (int k = 0; k < 12; k++) M[r][k] -= f * M[c][k];
+    }
+  }
+  for (int r = 0; r < 6; r++)
+    for (int q = 0; q < 9; q++) {
+      double s = 0;
+      for (int c = 0; c < 6; c++) s += M[r][6 + c] * A[q][c];
+      out54[r * 9 + q] = s;
+    }
+}
+
+int upload_pinv(visocu_ctx* ctx) {
+  if (ctx->pinv_ready) return VISOCU_OK;
+  double p[54];
+  make_pinv(p);
+  CU_TRY(ctx, cudaMemcpyToSymbolAsync(c_pinv, p, sizeof p, 0, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(ctx, visocu_stream_wait(ctx));
+  ctx->pinv_ready = 1;
+  return VISOCU_OK;
 }
 
 int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJob& J) {
   const int ids[4] = {q.f1p, q.f2p, q.f1c, q.f2c};
-  const bool need[4] = {true, method == 2, true, method == 2};
+  const bool need[4] = {method != 1, method == 2, true, method != 0};
   memset(&J, 0, sizeof J);
   for (int k = 0; k < 4; k++) {
     if (!need[k]) continue;
@@ -296,7 +423,9 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
   if (!ctx) return VISOCU_EINVAL;
   if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
   if (n_jobs <= 0 || !jobs || !out || !cap || !n_out) return visocu_set_error(ctx, VISOCU_EINVAL, "bad match arguments");
-  if (method != 0 && method != 2) return visocu_set_error(ctx, VISOCU_EINVAL, "method %d not supported (0 = flow, 2 = quad)", method);
+  if (method < 0 || method > 2) return visocu_set_error(ctx, VISOCU_EINVAL, "method %d not supported (0 = flow, 1 = stereo, 2 = quad)", method);
+  if (refine < 0 || refine > 2) return visocu_set_error(ctx, VISOCU_EINVAL, "refine must be 0, 1 or 2");
+  if (refine == 2) { int rc0 = upload_pinv(ctx); if (rc0) return rc0; }
   if (pass < ctx->g.first_pass || pass > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "pass %d not available", pass);
   if (use_prior && !ranges) return visocu_set_error(ctx, VISOCU_EINVAL, "use_prior needs ranges");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -307,19 +436,21 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
     std::vector<MatchJob> hj(nb);
     size_t off = align_up(sizeof(MatchJob) * nb, 256);
     int maxq = 0;
-    std::vector<size_t> o_res(nb), o_blk(nb), o_out(nb), o_cnt(nb), o_rng(nb);
+    std::vector<size_t> o_res(nb), o_blk(nb), o_out(nb), o_cnt(nb), o_rng(nb), o_keep(nb);
     for (int j = 0; j < nb; j++) {
       int rc = fill_job(ctx, jobs[start + j], method, pass, hj[j]);
       if (rc) return rc;
       bool empty = false;
-      for (int k = 0; k < 4; k++) if ((k == 0 || k == 2 || method == 2) && hj[j].s[k].n == 0) empty = true;
-      const int nq = empty ? 0 : (method == 0 ? hj[j].s[2].n : hj[j].s[0].n);
+      const bool need[4] = {method != 1, method == 2, true, method != 0};
+      for (int k = 0; k < 4; k++) if (need[k] && hj[j].s[k].n == 0) empty = true;
+      const int nq = empty ? 0 : (method == 2 ? hj[j].s[0].n : hj[j].s[2].n);
       hj[j].nq = nq;
       if (nq > maxq) maxq = nq;
       o_res[j] = off; off += align_up((size_t)(nq + 1) * 16, 256);
       o_blk[j] = off; off += align_up((size_t)(nq / CHUNK + 2) * 4, 256);
       o_out[j] = off; off += align_up((size_t)(nq + 1) * 48, 256);
       o_cnt[j] = off; off += 256;
+      o_keep[j] = off; off += align_up((size_t)nq + 1, 256);
       o_rng[j] = off; off += use_prior ? align_up((size_t)nstat * sizeof(visocu_range), 256) : 0;
     }
     int rc = visocu_ensure_scratch(ctx, off);
@@ -332,6 +463,7 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
     for (int j = 0; j < nb; j++) {
       hj[j].res = (int4*)(sb + o_res[j]); hj[j].blk = (int32_t*)(sb + o_blk[j]);
       hj[j].out = (visocu_pmatch*)(sb + o_out[j]); hj[j].n_out = (int32_t*)(sb + o_cnt[j]);
+      hj[j].keep = sb + o_keep[j];
       if (use_prior) {
         if (!ranges[start + j]) return visocu_set_error(ctx, VISOCU_EINVAL, "job %d has no ranges", start + j);
         memcpy(pin + pin_off, ranges[start + j], (size_t)nstat * sizeof(visocu_range));
@@ -357,7 +489,7 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
     if (refine && maxq > 0) {
       int gx = (maxq + 7) / 8; if (gx > 4096) gx = 4096;
       dim3 gr(gx, nb);
-      k_refine<<<gr, 256, 0, ctx->stream>>>(g, dj, method, nullptr, 0);
+      k_refine<<<gr, 256, 0, ctx->stream>>>(g, dj, method, refine, nullptr, 0, nullptr);
       CU_LAUNCH_CHECK(ctx);
     }
     for (int j = 0; j < nb; j++) CU_COPY(ctx, pin_cnt + j, hj[j].n_out, 4, cudaMemcpyDeviceToHost);
@@ -368,31 +500,55 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
       if (n > cap[start + j]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "job %d produced %d matches, room for %d", start + j, n, cap[start + j]);
       if (n > 0) CU_COPY(ctx, out[start + j], hj[j].out, (size_t)n * 48, cudaMemcpyDeviceToHost);
     }
+    std::vector<std::vector<uint8_t> > keep(refine == 2 ? nb : 0);
+    for (int j = 0; j < (int)keep.size(); j++) {
+      keep[j].resize((size_t)n_out[start + j] + 1);
+      if (n_out[start + j] > 0) CU_COPY(ctx, keep[j].data(), hj[j].keep, (size_t)n_out[start + j], cudaMemcpyDeviceToHost);
+    }
     CU_TRY(ctx, visocu_stream_wait(ctx));
+    // sub-pixel refinement drops matches (matcher.cpp:1546-1577 `continue`): order-preserving compaction
+    for (int j = 0; j < (int)keep.size(); j++) {
+      visocu_pmatch* list = out[start + j];
+      int kept = 0;
+      for (int i = 0; i < n_out[start + j]; i++)
+        if (keep[j][i]) list[kept++] = list[i];
+      n_out[start + j] = kept;
+    }
   }
   return VISOCU_OK;
 }
 
-extern "C" int visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, visocu_pmatch* inout, int32_t n) {
-  if (!ctx || !job || (!inout && n > 0)) return VISOCU_EINVAL;
+extern "C" int visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, int32_t mode, visocu_pmatch* inout, int32_t n,
+                             int32_t* n_out) {
+  if (!ctx || !job || (!inout && n > 0) || !n_out) return VISOCU_EINVAL;
   if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
-  if (method != 0 && method != 2) return visocu_set_error(ctx, VISOCU_EINVAL, "method %d not supported", method);
+  if (method < 0 || method > 2 || mode < 1 || mode > 2) return visocu_set_error(ctx, VISOCU_EINVAL, "bad method / mode");
+  *n_out = n;
   if (n <= 0) return VISOCU_OK;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (mode == 2) { int rc0 = upload_pinv(ctx); if (rc0) return rc0; }
   MatchJob J;
   int rc = fill_job(ctx, *job, method, 1, J);
   if (rc) return rc;
-  size_t o_list = align_up(sizeof(MatchJob), 256);
-  if ((rc = visocu_ensure_scratch(ctx, o_list + (size_t)n * 48))) return rc;
+  size_t o_list = align_up(sizeof(MatchJob), 256), o_keep = o_list + align_up((size_t)n * 48, 256);
+  if ((rc = visocu_ensure_scratch(ctx, o_keep + (size_t)n + 256))) return rc;
   uint8_t* sb = (uint8_t*)ctx->scratch;
   visocu_pmatch* d_list = (visocu_pmatch*)(sb + o_list);
   CU_COPY(ctx, sb, &J, sizeof J, cudaMemcpyHostToDevice);
   CU_COPY(ctx, d_list, inout, (size_t)n * 48, cudaMemcpyHostToDevice);
   int gx = (n + 7) / 8; if (gx > 4096) gx = 4096;
-  k_refine<<<dim3(gx, 1), 256, 0, ctx->stream>>>(ctx->g, (const MatchJob*)sb, method, d_list, n);
+  k_refine<<<dim3(gx, 1), 256, 0, ctx->stream>>>(ctx->g, (const MatchJob*)sb, method, mode, d_list, n, sb + o_keep);
   CU_LAUNCH_CHECK(ctx);
+  std::vector<uint8_t> keep(n);
   CU_COPY(ctx, inout, d_list, (size_t)n * 48, cudaMemcpyDeviceToHost);
+  CU_COPY(ctx, keep.data(), sb + o_keep, (size_t)n, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, visocu_stream_wait(ctx));
+  if (mode == 2) {
+    int kept = 0;
+    for (int i = 0; i < n; i++)
+      if (keep[i]) inout[kept++] = inout[i];
+    *n_out = kept;
+  }
   return VISOCU_OK;
 }
 

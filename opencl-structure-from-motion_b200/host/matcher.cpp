@@ -128,16 +128,16 @@ void Matcher::push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool re
   }
 }
 
-bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_prior, bool refine) {
+bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_prior, int refine) {
   visob::StageTimer timer(1 + pass);
   visocu_quad q = {slot[0], slot[1], slot[2], slot[3]};
   const int32_t base = pass == 0 ? 0 : 4;
-  const int32_t nq = method == 0 ? n_feat[base + 2] : n_feat[base + 0];
+  const int32_t nq = method == 2 ? n_feat[base + 0] : n_feat[base + 2];
   out.resize((size_t)nq + 1);
   visocu_pmatch* optr = reinterpret_cast<visocu_pmatch*>(out.data());
   const visocu_range* rptr = reinterpret_cast<const visocu_range*>(ranges.data());
   int32_t cap = nq + 1, n = 0;
-  int rc = visocu_match(ctx, 1, &q, method, pass, use_prior ? 1 : 0, use_prior ? &rptr : 0, refine ? 1 : 0, &optr, &cap, &n);
+  int rc = visocu_match(ctx, 1, &q, method, pass, use_prior ? 1 : 0, use_prior ? &rptr : 0, refine, &optr, &cap, &n);
   if (rc != VISOCU_OK) {
     std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
     out.clear();
@@ -155,21 +155,18 @@ void Matcher::matchFeatures(int32_t method, Matrix* Tr_delta) {
     if (n2[0] == 0 || n2[2] == 0) return;
     if (param.multi_stage && (n1[0] == 0 || n1[2] == 0)) return;
   } else if (method == 1) {
-    std::cerr << "ERROR: Matcher method 1 (stereo) is not available in this implementation" << std::endl;
-    return;
+    if (n2[2] == 0 || n2[3] == 0) return;
+    if (param.multi_stage && (n1[2] == 0 || n1[3] == 0)) return;
   } else {
     if (n2[0] == 0 || n2[1] == 0 || n2[2] == 0 || n2[3] == 0) return;
     if (param.multi_stage && (n1[0] == 0 || n1[1] == 0 || n1[2] == 0 || n1[3] == 0)) return;
   }
-  if (param.refinement > 1) {
-    std::cerr << "ERROR: sub-pixel refinement (refinement=2) is not available in this implementation; using pixel refinement" << std::endl;
-  }
   (void)Tr_delta;   // the motion-predicted search of matcher.cpp:1114-1134 is not implemented: plain search is used
   p_matched_1.clear();
   p_matched_2.clear();
-  const bool refine = param.refinement > 0;
+  const int refine = param.refinement <= 0 ? 0 : (param.refinement == 1 ? 1 : 2);
   if (param.multi_stage) {
-    if (!matching(0, p_matched_1, method, false, false)) return;
+    if (!matching(0, p_matched_1, method, false, 0)) return;
     removeOutliers(p_matched_1, method);
     computePriorStatistics(p_matched_1, method);
     if (!matching(1, p_matched_2, method, true, refine)) return;

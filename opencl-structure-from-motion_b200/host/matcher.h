@@ -3,10 +3,10 @@
 // error behaviour, so it is a drop-in for libviso2's feature front end.  What runs where:
 //   GPU (through include/visocu.h): image copy into the 16-byte stride, half-resolution image, 5x5 filters,
 //       both non-maximum-suppression passes, descriptors, bin index, SAD circle matching (flow and quad),
-//       pixel refinement.
+//       pixel and sub-pixel refinement.
 //   host (this class): ring-buffer bookkeeping, computePriorStatistics, removeOutliers (own exact Delaunay
 //       triangulation + support vote), bucketFeatures, getGain.
-// Not supported yet: method 1 (stereo only), refinement == 2 (sub-pixel), Tr_delta-guided search.
+// Not supported yet: the Tr_delta-guided search window of quad matching (plain search is used).
 #ifndef VISOB_MATCHER_H
 #define VISOB_MATCHER_H
 #include <stdint.h>
@@ -59,7 +59,7 @@ public:
   // dims = {width, height, bytes per line}; the images are only read during the call
   void pushBack(uint8_t* I1, uint8_t* I2, uint32_t* dims, const bool replace);
   void pushBack(uint8_t* I1, uint32_t* dims, const bool replace) { pushBack(I1, 0, dims, replace); }
-  // method: 0 = flow, 2 = quad matching (1 = stereo is not available in this implementation)
+  // method: 0 = flow, 1 = stereo, 2 = quad matching
   void matchFeatures(int32_t method, Matrix* Tr_delta = 0);
   void bucketFeatures(int32_t max_features, float bucket_width, float bucket_height);
   std::vector<Matcher::p_match> getMatches() { return p_matched_2; }
@@ -81,7 +81,7 @@ public:
 private:
   void push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool replace, bool on_device);
   bool ensureContext(int32_t w, int32_t h);
-  bool matching(int pass, std::vector<p_match>& out, int32_t method, bool use_prior, bool refine);
+  bool matching(int pass, std::vector<p_match>& out, int32_t method, bool use_prior, int refine);
 
   parameters param;
   int32_t margin;

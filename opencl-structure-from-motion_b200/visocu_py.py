@@ -218,11 +218,12 @@ class Context:
                                     optr, _p(caps), _p(nout)), 'match')
         return [outs[k][:nout[k]].copy() for k in range(nj)]
 
-    def refine(self, quad, method, matches):
+    def refine(self, quad, method, matches, mode=1):
         q = np.zeros(1, QUAD); q[0] = tuple(quad)
         m = np.array(matches, dtype=P_MATCH, copy=True)
-        self._ck(lib().visocu_refine(self.h, _p(q), method, _p(m), len(m)), 'refine')
-        return m
+        n = C.c_int32(len(m))
+        self._ck(lib().visocu_refine(self.h, _p(q), method, mode, _p(m), len(m), C.byref(n)), 'refine')
+        return m[:n.value].copy()
 
     def match_stats(self):
         a = C.c_uint64(); b = C.c_uint64()

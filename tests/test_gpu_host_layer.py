@@ -132,3 +132,52 @@ def test_mono_odometry_sequence(ref):
         assert np.abs(Tr[:3, :3] - Th[:3, :3]).max() < 1e-6
         assert np.abs(Tr[:3, 3] - Th[:3, 3]).max() < 1e-6 * max(1.0, np.abs(Tr[:3, 3]).max())
         assert abs(Th[2, 3]) > 0.3                               # the drive moves 0.8 m forward per frame
+
+
+def test_matcher_stereo_method1(ref):
+    """Matcher method 1 (stereo, matcher.cpp:1045-1084): one stereo pair, left-right-left circle, positive disparity."""
+    assert pad_safe_width(1242, 3, 0)
+    lp, rpv, lc, rc = synth.blob_quad(1242, 376, seed=47)
+    for kw in (dict(half_resolution=0), dict()):
+        width_ok = pad_safe_width(1242, 3, kw.get('half_resolution', 1))
+        assert width_ok
+        rm = ref.matcher(pyref.MatcherParams(**kw)); hm = H.Matcher(V.Params(**kw))
+        for m in (rm, hm):
+            m.push(lc, rc); m.match_features(1)
+        want = rm.matches(2)
+        assert len(want) > 1000
+        assert np.all(want['u1c'] >= want['u2c']) and np.all(want['i1p'] == -1)
+        assert hm.matches(1).tobytes() == rm.matches(1).tobytes()
+        assert hm.matches(2).tobytes() == want.tobytes()
+
+
+def test_matcher_subpixel_refinement(ref):
+    """refinement = 2 (parabolicFitting, matcher.cpp:1379-1454) with the flow demo's parameters
+    (matlab/demo_matching_flow.m:12-21).  Integer stages identical; the sub-pixel coordinates come from a
+    double-precision least-squares solve done differently here (constant pseudo-inverse instead of a Gauss-Jordan solve
+    per match): tolerance 1e-4 pixel."""
+    kw = dict(nms_n=4, refinement=2, half_resolution=0)
+    assert pad_safe_width(1242, 4, 0)
+    a, b = synth.blob_pair(1242, 376, seed=49)
+    rm = ref.matcher(pyref.MatcherParams(**kw)); hm = H.Matcher(V.Params(**kw))
+    for m in (rm, hm):
+        m.push(a); m.push(b); m.match_features(0)
+    want, got = rm.matches(2), hm.matches(2)
+    assert len(want) > 1000 and len(got) == len(want)
+    for f in ('i1p', 'i1c', 'u1c', 'v1c'):
+        assert np.array_equal(got[f], want[f])
+    assert np.abs(got['u1p'] - want['u1p']).max() < 1e-4 and np.abs(got['v1p'] - want['v1p']).max() < 1e-4
+    frac = np.abs(want['u1p'] - np.round(want['u1p']))
+    assert (frac > 1e-3).mean() > 0.5                                   # it really is sub-pixel
+    # quad matching with sub-pixel refinement: three relocations per match
+    lp, rpv, lc, rc = synth.blob_quad(1242, 376, seed=51)
+    kw = dict(nms_n=2, refinement=2, half_resolution=0)
+    rm = ref.matcher(pyref.MatcherParams(**kw)); hm = H.Matcher(V.Params(**kw))
+    for m in (rm, hm):
+        m.push(lp, rpv); m.push(lc, rc); m.match_features(2)
+    want, got = rm.matches(2), hm.matches(2)
+    assert len(want) > 500 and len(got) == len(want)
+    for f in ('i1p', 'i2p', 'i1c', 'i2c', 'u1c', 'v1c'):
+        assert np.array_equal(got[f], want[f])
+    for f in ('u1p', 'v1p', 'u2p', 'v2p', 'u2c', 'v2c'):
+        assert np.abs(got[f] - want[f]).max() < 1e-4
