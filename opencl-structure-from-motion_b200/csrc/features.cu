@@ -13,6 +13,7 @@
 // rebuilt with a deterministic scan instead of push_back.
 #include "visocu_internal.cuh"
 #include <cstdlib>
+#include <mutex>
 
 namespace {
 
@@ -601,10 +602,18 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
     int max_cells = 0;
     for (int p = g.first_pass; p < 2; p++) max_cells += ((TW + g.n[p]) / (g.n[p] + 1) + 1) * ((TH + g.n[p]) / (g.n[p] + 1) + 1);
     const size_t smem_bytes = ts.smem + (size_t)max_cells * 20;
-    if (smem_bytes > ctx->filter_smem_attr) {
-      CU_TRY(ctx, cudaFuncSetAttribute(k_filter_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      ctx->filter_smem_attr = smem_bytes;
+    // opt in to large dynamic shared memory once per device (the attribute belongs to the function on a device, not
+    // to a context: several contexts with different tile shapes share it)
+    {
+      static std::mutex mtx;
+      static bool done[64] = {false};
+      std::lock_guard<std::mutex> lock(mtx);
+      if (!done[ctx->device & 63]) {
+        CU_TRY(ctx, cudaFuncSetAttribute(k_filter_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        done[ctx->device & 63] = true;
+      }
     }
+    if (smem_bytes > 227 * 1024) return visocu_set_error(ctx, VISOCU_EINVAL, "tile needs %zu bytes of shared memory", smem_bytes);
     dim3 grid((g.bplm + TW - 1) / TW, (g.hm + TH - 1) / TH, sl.n);
     if (ctx->profile) CU_TRY(ctx, cudaEventRecord(ctx->pev0, st));
     k_filter_nms<<<grid, FILTER_THREADS, smem_bytes, st>>>(g, ctx->frames_d, sl, nmax, ctx->tmap_img, ctx->use_tma, max_cells, ctx->dbg_flags);

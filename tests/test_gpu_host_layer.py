@@ -136,11 +136,9 @@ def test_mono_odometry_sequence(ref):
 
 def test_matcher_stereo_method1(ref):
     """Matcher method 1 (stereo, matcher.cpp:1045-1084): one stereo pair, left-right-left circle, positive disparity."""
-    assert pad_safe_width(1242, 3, 0)
-    lp, rpv, lc, rc = synth.blob_quad(1242, 376, seed=47)
+    lp, rpv, lc, rc = synth.blob_quad(1244, 376, seed=47)
     for kw in (dict(half_resolution=0), dict()):
-        width_ok = pad_safe_width(1242, 3, kw.get('half_resolution', 1))
-        assert width_ok
+        assert pad_safe_width(1244, 3, kw.get('half_resolution', 1))
         rm = ref.matcher(pyref.MatcherParams(**kw)); hm = H.Matcher(V.Params(**kw))
         for m in (rm, hm):
             m.push(lc, rc); m.match_features(1)
