@@ -126,6 +126,18 @@ int  visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* const* uv, co
                      double* F9, uint8_t* const* inlier_mask, int32_t* n_inliers, int32_t* best_iter,
                      int32_t* const* counts, double* const* F_all);
 
+/* ---- pose recovery helpers after RANSAC ----
+ * visocu_triangulate: VisualOdometryMono::triangulateChieral (viso_mono.cpp:394-431) for up to four (R|t) candidates
+ * at once.  uv: N x 4 floats (u1p,v1p,u1c,v1c) in pixels; P1: 3x4 projection of the previous camera, P2: n_sol 3x4
+ * projections of the current camera (row-major).  X receives n_sol blocks of 4 x N homogeneous points (row-major, not
+ * normalised: the null vector of each 4x4 system, sign arbitrary); n_front[s] = points in front of both cameras.
+ * visocu_best_plane: VisualOdometryMono::findBestPlane (viso_mono.cpp:74-98; the reference's OpenCL hook
+ * viso_mono_cl.cpp:255-280): index of the candidate d_i > threshold with the largest sum_j exp(-(d_j-d_i)^2 weight),
+ * first maximum wins, 0 if there is no candidate. */
+int  visocu_triangulate(visocu_ctx* ctx, const float* uv, int32_t N, const double* P1, const double* P2, int32_t n_sol,
+                        double* X, int32_t* n_front);
+int  visocu_best_plane(visocu_ctx* ctx, const double* d, int32_t n, double threshold, double weight, int32_t* best_idx);
+
 /* host<->device bytes copied by this context since creation (bench.py's h2d / d2h bytes per step) */
 int  visocu_transfer_bytes(const visocu_ctx* ctx, uint64_t* h2d, uint64_t* d2h);
 /* event timing of the fused filter+NMS launches on the context's stream (replaces the per-call

@@ -1,0 +1,148 @@
+// Pose-recovery helpers of monocular odometry that follow the RANSAC step.
+//
+// What it reproduces (reference paths relative to /root/reference/viso):
+//   VisualOdometryMono::triangulateChieral ... viso_mono.cpp:394-431  (N independent 4x4 null-vector problems per (R|t))
+//   VisualOdometryMono::findBestPlane ........ viso_mono.cpp:74-98    (O(n^2) Gaussian vote; the reference's OpenCL
+//                                              offload is plane_calc_sums, kernels/plane_and_inliers.cl:142-162, float32)
+// Here both run in FP64.  The triangulation does all four (R|t) candidates of EtoRt (viso_mono.cpp:347-392) in one
+// launch, one thread per (candidate, match): a 4x4 one-sided Jacobi in registers replaces Matrix::svd.
+#include "visocu_internal.cuh"
+#include <cstring>
+
+namespace {
+
+struct TriJob {
+  const float4* uv;      // N x (u1p, v1p, u1c, v1c) in pixels
+  double* X;             // n_sol x 4 x N
+  int32_t* n_front;      // n_sol
+  int N, n_sol;
+  double P1[12];
+  double P2[4][12];
+};
+
+__global__ void __launch_bounds__(128) k_triangulate(TriJob job) {
+  const int i = blockIdx.x * 128 + threadIdx.x, sol = blockIdx.y;
+  int front = 0;
+  if (i < job.N) {
+    const float4 m = job.uv[i];
+    const double* P1 = job.P1;
+    const double* P2 = job.P2[sol];
+    // J rows (viso_mono.cpp:411-416); g[c][r] = column c of J
+    double g[4][4], v[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      g[c][0] = P1[8 + c] * (double)m.x - P1[c];
+      g[c][1] = P1[8 + c] * (double)m.y - P1[4 + c];
+      g[c][2] = P2[8 + c] * (double)m.z - P2[c];
+      g[c][3] = P2[8 + c] * (double)m.w - P2[4 + c];
+#pragma unroll
+      for (int r = 0; r < 4; r++) v[c][r] = r == c ? 1.0 : 0.0;
+    }
+    for (int sweep = 0; sweep < 40; sweep++) {
+      bool rotated = false;
+#pragma unroll
+      for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int q = p + 1; q < 4; q++) {
+          double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) { alpha = fma(g[p][k], g[p][k], alpha); beta = fma(g[q][k], g[q][k], beta); gamma = fma(g[p][k], g[q][k], gamma); }
+          if (fabs(gamma) > 1e-15 * sqrt(alpha * beta)) {
+            const double zeta = (beta - alpha) / (2.0 * gamma);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const double a = g[p][k], b = g[q][k];
+              g[p][k] = c * a - s * b; g[q][k] = s * a + c * b;
+              const double va = v[p][k], vb = v[q][k];
+              v[p][k] = c * va - s * vb; v[q][k] = s * va + c * vb;
+            }
+            rotated = true;
+          }
+        }
+      if (!rotated) break;
+    }
+    double nrm[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) { nrm[c] = 0; for (int k = 0; k < 4; k++) nrm[c] = fma(g[c][k], g[c][k], nrm[c]); }
+    int js = 0;
+#pragma unroll
+    for (int c = 1; c < 4; c++) if (nrm[c] < nrm[js]) js = c;
+    double X[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) X[r] = js == 0 ? v[0][r] : (js == 1 ? v[1][r] : (js == 2 ? v[2][r] : v[3][r]));
+    double* out = job.X + (size_t)sol * 4 * job.N;
+#pragma unroll
+    for (int r = 0; r < 4; r++) out[(size_t)r * job.N + i] = X[r];
+    // points in front of both cameras (viso_mono.cpp:421-427)
+    const double a = P1[8] * X[0] + P1[9] * X[1] + P1[10] * X[2] + P1[11] * X[3];
+    const double b = P2[8] * X[0] + P2[9] * X[1] + P2[10] * X[2] + P2[11] * X[3];
+    front = (a * X[3] > 0 && b * X[3] > 0) ? 1 : 0;
+  }
+  const unsigned bal = __ballot_sync(0xFFFFFFFFu, front);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&job.n_front[sol], __popc(bal));
+}
+
+// one thread per candidate i: sum_j exp(-(d_j - d_i)^2 w) in the reference's summation order; candidates need d_i > threshold
+__global__ void __launch_bounds__(256) k_plane_sums(const double* d, int n, double threshold, double weight, double* sums) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const double di = d[i];
+  double sum = -1.0;                      // marks "not a candidate"
+  if (di > threshold) {
+    sum = 0;
+    for (int j = 0; j < n; j++) {
+      const double dist = d[j] - di;
+      sum += exp(-dist * dist * weight);
+    }
+  }
+  sums[i] = sum;
+}
+
+}  // namespace
+
+extern "C" int visocu_triangulate(visocu_ctx* ctx, const float* uv, int32_t N, const double* P1, const double* P2, int32_t n_sol,
+                                  double* X, int32_t* n_front) {
+  if (!ctx || !uv || !P1 || !P2 || !X || !n_front || N <= 0 || n_sol < 1 || n_sol > 4) return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad triangulate arguments") : VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t o_uv = 0, o_X = align_up((size_t)N * 16, 256), o_cnt = o_X + align_up((size_t)n_sol * 4 * N * 8, 256);
+  int rc = visocu_ensure_scratch(ctx, o_cnt + 256);
+  if (rc) return rc;
+  uint8_t* sb = (uint8_t*)ctx->scratch;
+  TriJob job;
+  job.uv = (const float4*)(sb + o_uv); job.X = (double*)(sb + o_X); job.n_front = (int32_t*)(sb + o_cnt);
+  job.N = N; job.n_sol = n_sol;
+  memcpy(job.P1, P1, sizeof job.P1);
+  memcpy(job.P2, P2, sizeof(double) * 12 * n_sol);
+  CU_COPY(ctx, sb + o_uv, uv, (size_t)N * 16, cudaMemcpyHostToDevice);
+  CU_TRY(ctx, cudaMemsetAsync(sb + o_cnt, 0, 16, ctx->stream));
+  k_triangulate<<<dim3((N + 127) / 128, n_sol), 128, 0, ctx->stream>>>(job);
+  CU_LAUNCH_CHECK(ctx);
+  CU_COPY(ctx, X, sb + o_X, (size_t)n_sol * 4 * N * 8, cudaMemcpyDeviceToHost);
+  CU_COPY(ctx, n_front, sb + o_cnt, (size_t)n_sol * 4, cudaMemcpyDeviceToHost);
+  CU_TRY(ctx, visocu_stream_wait(ctx));
+  return VISOCU_OK;
+}
+
+extern "C" int visocu_best_plane(visocu_ctx* ctx, const double* d, int32_t n, double threshold, double weight, int32_t* best_idx) {
+  if (!ctx || !d || !best_idx || n <= 0) return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad best_plane arguments") : VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t o_s = align_up((size_t)n * 8, 256);
+  int rc = visocu_ensure_scratch(ctx, 2 * o_s);
+  if (rc) return rc;
+  uint8_t* sb = (uint8_t*)ctx->scratch;
+  CU_COPY(ctx, sb, d, (size_t)n * 8, cudaMemcpyHostToDevice);
+  k_plane_sums<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const double*)sb, n, threshold, weight, (double*)(sb + o_s));
+  CU_LAUNCH_CHECK(ctx);
+  std::vector<double> sums(n);
+  CU_COPY(ctx, sums.data(), sb + o_s, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  CU_TRY(ctx, visocu_stream_wait(ctx));
+  // arg-max with the reference's rule: strictly larger wins, so the first maximum is kept; index 0 if no candidate
+  double best_sum = 0;
+  int32_t best = 0;
+  for (int32_t i = 0; i < n; i++)
+    if (sums[i] > best_sum) { best_sum = sums[i]; best = i; }
+  *best_idx = best;
+  return VISOCU_OK;
+}

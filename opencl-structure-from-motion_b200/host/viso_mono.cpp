@@ -65,22 +65,18 @@ Matrix VisualOdometryMono::ransacEstimateF(const vector<Matcher::p_match>& p_mat
   return Matrix(3, 3, F9);
 }
 
+// GPU Gaussian vote (the reference's second accelerator hook, viso_mono.h:75 / viso_mono_cl.cpp:255-280)
 double VisualOdometryMono::findBestPlane(const Matrix& x_plane, double threshold, double weight) {
-  // signed distance of every point to the plane normal direction, then the mode of a Gaussian kernel density
+  // signed distance of every point along the plane normal, then the mode of a Gaussian kernel density
   const double ny = cos(-param.pitch), nz = sin(-param.pitch);
   const int32_t n = x_plane.n;
   vector<double> d(n);
   for (int32_t i = 0; i < n; i++) d[i] = ny * x_plane.val[0][i] + nz * x_plane.val[1][i];
-  double best_sum = 0;
   int32_t best_idx = 0;
-  for (int32_t i = 0; i < n; i++) {
-    if (d[i] <= threshold) continue;
-    double sum = 0;
-    for (int32_t j = 0; j < n; j++) {
-      const double dist = d[j] - d[i];
-      sum += exp(-dist * dist * weight);
-    }
-    if (sum > best_sum) { best_sum = sum; best_idx = i; }
+  visocu_ctx* ctx = matcher->context();
+  if (!ctx || visocu_best_plane(ctx, d.data(), n, threshold, weight, &best_idx) != VISOCU_OK) {
+    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+    return d[0];
   }
   return d[best_idx];
 }
@@ -190,14 +186,42 @@ void VisualOdometryMono::EtoRt(Matrix& E, Matrix& K, vector<Matcher::p_match>& p
   t.val[0][0] = T.val[2][1]; t.val[1][0] = T.val[0][2]; t.val[2][0] = T.val[1][0];
   if (Ra.det() < 0) Ra = -Ra;
   if (Rb.det() < 0) Rb = -Rb;
-  // four (R, t) candidates, keep the one with most points in front of both cameras (first wins on ties)
+  // four (R, t) candidates, keep the one with most points in front of both cameras (first wins on ties).  All four
+  // triangulations (4 N independent 4x4 null-vector problems) run in one GPU launch.
   Matrix Rs[4] = {Ra, Ra, Rb, Rb};
   Matrix ts[4] = {t, -t, t, -t};
-  Matrix X_curr;
+  const int32_t N = (int32_t)p_matched.size();
+  Matrix P1(3, 4);
+  P1.setMat(K, 0, 0);
+  double P1d[12], P2d[48];
+  P1.getData(P1d);
+  for (int32_t i = 0; i < 4; i++) {
+    Matrix P2(3, 4);
+    P2.setMat(Rs[i], 0, 0);
+    P2.setMat(ts[i], 0, 3);
+    P2 = K * P2;
+    P2.getData(P2d + 12 * i);
+  }
+  vector<float> uv((size_t)N * 4);
+  for (int32_t i = 0; i < N; i++) {
+    uv[4 * i + 0] = p_matched[i].u1p; uv[4 * i + 1] = p_matched[i].v1p;
+    uv[4 * i + 2] = p_matched[i].u1c; uv[4 * i + 3] = p_matched[i].v1c;
+  }
+  vector<double> Xall((size_t)16 * N);
+  int32_t n_front[4] = {0, 0, 0, 0};
+  visocu_ctx* ctx = matcher->context();
+  if (!ctx || visocu_triangulate(ctx, uv.data(), N, P1d, P2d, 4, Xall.data(), n_front) != VISOCU_OK) {
+    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+    return;
+  }
   int32_t max_inliers = 0;
   for (int32_t i = 0; i < 4; i++) {
-    const int32_t num = triangulateChieral(p_matched, K, Rs[i], ts[i], X_curr);
-    if (num > max_inliers) { max_inliers = num; X = X_curr; R = Rs[i]; t = ts[i]; }
+    if (n_front[i] > max_inliers) {
+      max_inliers = n_front[i];
+      X = Matrix(4, N, Xall.data() + (size_t)4 * N * i);
+      R = Rs[i];
+      t = ts[i];
+    }
   }
 }
 
