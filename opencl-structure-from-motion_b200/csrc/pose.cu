@@ -38,6 +38,12 @@ __global__ void __launch_bounds__(128) k_triangulate(TriJob job) {
 #pragma unroll
       for (int r = 0; r < 4; r++) v[c][r] = r == c ? 1.0 : 0.0;
     }
+    double total = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) total = fma(g[c][k], g[c][k], total);
+    const double tiny = 1e-28 * total;      // columns this small are numerically null (J has rank 3): leave them alone
     for (int sweep = 0; sweep < 40; sweep++) {
       bool rotated = false;
 #pragma unroll
@@ -47,7 +53,7 @@ __global__ void __launch_bounds__(128) k_triangulate(TriJob job) {
           double alpha = 0, beta = 0, gamma = 0;
 #pragma unroll
           for (int k = 0; k < 4; k++) { alpha = fma(g[p][k], g[p][k], alpha); beta = fma(g[q][k], g[q][k], beta); gamma = fma(g[p][k], g[q][k], gamma); }
-          if (fabs(gamma) > 1e-15 * sqrt(alpha * beta)) {
+          if (alpha > tiny && beta > tiny && fabs(gamma) > 1e-15 * sqrt(alpha * beta)) {
             const double zeta = (beta - alpha) / (2.0 * gamma);
             const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
             const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
@@ -84,20 +90,24 @@ __global__ void __launch_bounds__(128) k_triangulate(TriJob job) {
   if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&job.n_front[sol], __popc(bal));
 }
 
-// one thread per candidate i: sum_j exp(-(d_j - d_i)^2 w) in the reference's summation order; candidates need d_i > threshold
+// one warp per candidate i: sum_j exp(-(d_j - d_i)^2 w) with a fixed lane-strided + butterfly summation order
+// (deterministic; differs from the reference's sequential order only in rounding).  Candidates need d_i > threshold.
 __global__ void __launch_bounds__(256) k_plane_sums(const double* d, int n, double threshold, double weight, double* sums) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= n) return;
   const double di = d[i];
-  double sum = -1.0;                      // marks "not a candidate"
-  if (di > threshold) {
-    sum = 0;
-    for (int j = 0; j < n; j++) {
-      const double dist = d[j] - di;
-      sum += exp(-dist * dist * weight);
-    }
+  if (!(di > threshold)) {
+    if (lane == 0) sums[i] = -1.0;          // marks "not a candidate"
+    return;
   }
-  sums[i] = sum;
+  double sum = 0;
+  for (int j = lane; j < n; j += 32) {
+    const double dist = d[j] - di;
+    sum += exp(-dist * dist * weight);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+  if (lane == 0) sums[i] = sum;
 }
 
 }  // namespace
@@ -133,7 +143,7 @@ extern "C" int visocu_best_plane(visocu_ctx* ctx, const double* d, int32_t n, do
   if (rc) return rc;
   uint8_t* sb = (uint8_t*)ctx->scratch;
   CU_COPY(ctx, sb, d, (size_t)n * 8, cudaMemcpyHostToDevice);
-  k_plane_sums<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const double*)sb, n, threshold, weight, (double*)(sb + o_s));
+  k_plane_sums<<<(n + 7) / 8, 256, 0, ctx->stream>>>((const double*)sb, n, threshold, weight, (double*)(sb + o_s));
   CU_LAUNCH_CHECK(ctx);
   std::vector<double> sums(n);
   CU_COPY(ctx, sums.data(), sb + o_s, (size_t)n * 8, cudaMemcpyDeviceToHost);

@@ -59,6 +59,15 @@ __device__ __forceinline__ void warp_jacobi_null(double (&g)[R], int lane, doubl
 #pragma unroll
   for (int k = 0; k < 9; k++) v[k] = (k == lane) ? 1.0 : 0.0;
   const bool col = lane < 9;
+  // A column whose norm has fallen 14 orders of magnitude below the matrix norm is numerically null (the 8 x 9
+  // constraint matrix always has one): its entries are rounding noise that no rotation can orthogonalise any further,
+  // so it is left alone instead of being rotated until the sweep limit.
+  double total = 0;
+#pragma unroll
+  for (int k = 0; k < R; k++) total = fma(g[k], g[k], total);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+  const double tiny = 1e-28 * total;
   for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; sweep++) {
     bool rotated = false;
     for (int r = 0; r < 9; r++) {
@@ -77,7 +86,7 @@ __device__ __forceinline__ void warp_jacobi_null(double (&g)[R], int lane, doubl
           const double a = first ? g[k] : og[k], b = first ? og[k] : g[k];
           alpha = fma(a, a, alpha); beta = fma(b, b, beta); gamma = fma(a, b, gamma);
         }
-        if (fabs(gamma) > JACOBI_TOL * sqrt(alpha * beta)) {
+        if (alpha > tiny && beta > tiny && fabs(gamma) > JACOBI_TOL * sqrt(alpha * beta)) {
           const double zeta = (beta - alpha) / (2.0 * gamma);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;

@@ -46,7 +46,7 @@ struct MonoAccess : public VisualOdometryMono {
 VISOB_API void visob_set_device(int device) { visob::set_device(device); }
 
 namespace visob { extern std::atomic<long long> g_stage_ns[8]; extern std::atomic<long long> g_stage_calls[8]; }
-// stage ids: 0 pushBack, 1 matching pass 1, 2 matching pass 2 (+refinement), 3 priors, 4 removeOutliers (< 2000 matches), 5 removeOutliers (larger)
+// stage ids: 0 pushBack, 1 matching pass 1, 2 matching pass 2 (+refinement), 3 priors, 4 removeOutliers (< 2000 matches), 5 removeOutliers (larger), 6 ransacEstimateF, 7 estimateMotion (total, includes 6)
 VISOB_API void visob_stage_times(double* seconds8, int64_t* calls8, int reset) {
   for (int k = 0; k < 8; k++) {
     seconds8[k] = visob::g_stage_ns[k].load() * 1e-9; calls8[k] = visob::g_stage_calls[k].load();

@@ -48,7 +48,12 @@ Matcher::Matcher(parameters param) : param(param), ctx(0), cfg_w(0), cfg_h(0), h
   for (int k = 0; k < 4; k++) slot[k] = -1;
   for (int k = 0; k < 8; k++) n_feat[k] = 0;
   for (int k = 0; k < 3; k++) dims_p[k] = dims_c[k] = 0;
+  memset(&rnd_data, 0, sizeof rnd_data);
+  memset(rnd_state, 0, sizeof rnd_state);
+  initstate_r(1, rnd_state, sizeof rnd_state, &rnd_data);     // the state rand() starts from
 }
+
+void Matcher::seedShuffle(unsigned seed) { srandom_r(seed, &rnd_data); }
 
 Matcher::~Matcher() {
   if (ctx) visocu_destroy(ctx);
@@ -191,9 +196,14 @@ void Matcher::bucketFeatures(int32_t max_features, float bucket_width, float buc
   }
   p_matched_2.clear();
   for (vector<p_match>& b : buckets) {
-    // same library call as the reference (matcher.cpp:270): the kept subset depends on the process-wide rand()
-    // stream, which VisualOdometry seeds with srand(0)
-    std::random_shuffle(b.begin(), b.end());
+    // std::random_shuffle of the reference (matcher.cpp:270) restated: libstdc++ swaps element i with element
+    // rand() % (i + 1); rand() is glibc's additive-feedback generator, reproduced here by random_r on this object's state
+    for (size_t i = 1; i < b.size(); i++) {
+      int32_t r = 0;
+      random_r(&rnd_data, &r);
+      const size_t j = (size_t)r % (i + 1);
+      if (i != j) std::swap(b[i], b[j]);
+    }
     int32_t k = 0;
     for (const p_match& m : b) {
       p_matched_2.push_back(m);

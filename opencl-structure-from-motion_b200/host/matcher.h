@@ -10,6 +10,7 @@
 #ifndef VISOB_MATCHER_H
 #define VISOB_MATCHER_H
 #include <stdint.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "matrix.h"
@@ -69,6 +70,10 @@ public:
   // same as pushBack, but the images already live in device memory of this matcher's GPU
   void pushBackDevice(const uint8_t* d_I1, const uint8_t* d_I2, uint32_t* dims, const bool replace);
   visocu_ctx* context() { return ctx; }
+  // bucketFeatures shuffles with the same generator as the reference's std::random_shuffle (glibc rand()), but the
+  // state is owned by this object: no process-wide lock, and sharded runs are reproducible.  Default state = rand()
+  // without srand; VisualOdometry reseeds with 0 exactly where the reference calls srand(0) (viso.cpp:35).
+  void seedShuffle(unsigned seed);
   // stage access for parity tests: 1 = pass-1 list after removeOutliers, 2 = getMatches()
   const std::vector<p_match>& matches(int stage) const { return stage == 1 ? p_matched_1 : p_matched_2; }
   int32_t featureCount(int which) const { return which >= 0 && which < 8 ? n_feat[which] : 0; }   // 1p1 2p1 1c1 2c1 1p2 2p2 1c2 2c2
@@ -97,6 +102,8 @@ private:
   bool have_I1p, have_I1c;
   std::vector<p_match> p_matched_1, p_matched_2;
   std::vector<range> ranges;
+  struct random_data rnd_data;
+  char rnd_state[128];
 };
 
 #endif

@@ -307,6 +307,9 @@ void Matrix::svd(Matrix& U2, Matrix& W, Matrix& V) {
     for (int32_t j = 0; j < N; j++) g[(size_t)j * M + i] = val[i][j];
   for (int32_t j = 0; j < N; j++) v[(size_t)j * N + j] = 1.0;
   const FLOAT tol = 1e-15;
+  FLOAT total = 0;
+  for (size_t k = 0; k < g.size(); k++) total += g[k] * g[k];
+  const FLOAT tiny = 1e-28 * total;       // numerically null columns are left alone (rounding noise cannot be rotated away)
   bool converged = false;
   for (int sweep = 0; sweep < 60 && !converged; sweep++) {
     converged = true;
@@ -316,7 +319,7 @@ void Matrix::svd(Matrix& U2, Matrix& W, Matrix& V) {
         FLOAT* gq = &g[(size_t)q * M];
         FLOAT alpha = 0, beta = 0, gamma = 0;
         for (int32_t i = 0; i < M; i++) { alpha += gp[i] * gp[i]; beta += gq[i] * gq[i]; gamma += gp[i] * gq[i]; }
-        if (fabs(gamma) <= tol * sqrt(alpha * beta)) continue;
+        if (alpha <= tiny || beta <= tiny || fabs(gamma) <= tol * sqrt(alpha * beta)) continue;
         converged = false;
         const FLOAT zeta = (beta - alpha) / (2.0 * gamma);
         const FLOAT t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));

@@ -9,7 +9,8 @@ VisualOdometry::VisualOdometry(parameters param) : sample_generator(71), param(p
   matcher = new Matcher(param.match);
   Tr_delta = Matrix::eye(4);
   Tr_valid = false;
-  srand(0);      // bucketFeatures' random_shuffle draws from rand() (viso.cpp:35)
+  srand(0);                  // as the reference does (viso.cpp:35)
+  matcher->seedShuffle(0);   // ... and the matcher's own copy of that generator, which bucketFeatures draws from
 }
 
 VisualOdometry::~VisualOdometry() { delete matcher; }

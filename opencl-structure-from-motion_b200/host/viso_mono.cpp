@@ -12,6 +12,23 @@
 
 #include "visocu.h"
 
+#include <atomic>
+#include <chrono>
+namespace visob {
+extern std::atomic<long long> g_stage_ns[8];
+extern std::atomic<long long> g_stage_calls[8];
+}
+namespace {
+struct MonoTimer {
+  int id; std::chrono::steady_clock::time_point t0;
+  explicit MonoTimer(int id) : id(id), t0(std::chrono::steady_clock::now()) {}
+  ~MonoTimer() {
+    visob::g_stage_ns[id] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    visob::g_stage_calls[id]++;
+  }
+};
+}
+
 using std::vector;
 
 VisualOdometryMono::VisualOdometryMono(parameters param) : VisualOdometry(param), param(param) {}
@@ -36,6 +53,7 @@ bool VisualOdometryMono::processDevice(const uint8_t* d_I, uint32_t* dims, bool 
 // GPU RANSAC.  The host only draws the sample table with the reference's generator, in the reference's order
 // (one getRandomSample per iteration), so a run is comparable with the reference hypothesis by hypothesis.
 Matrix VisualOdometryMono::ransacEstimateF(const vector<Matcher::p_match>& p_matched) {
+  MonoTimer timer(6);
   inliers.clear();
   const int32_t N = (int32_t)p_matched.size(), iters = param.ransac_iters;
   samples_last.resize((size_t)iters * 8);
@@ -82,6 +100,7 @@ double VisualOdometryMono::findBestPlane(const Matrix& x_plane, double threshold
 }
 
 vector<double> VisualOdometryMono::estimateMotion(vector<Matcher::p_match> p_matched) {
+  MonoTimer timer(7);
   const int32_t N = (int32_t)p_matched.size();
   if (N < 10) return vector<double>();
   double K_data[9] = {param.calib.f, 0, param.calib.cu, 0, param.calib.f, param.calib.cv, 0, 0, 1};

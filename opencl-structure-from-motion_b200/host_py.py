@@ -54,7 +54,8 @@ def stage_times(reset=True):
     """Host-layer wall-clock per stage, summed over worker threads: dict name -> (seconds, calls)."""
     sec = np.zeros(8); calls = np.zeros(8, np.int64)
     lib().visob_stage_times(_p(sec), _p(calls), int(reset))
-    names = ['pushBack', 'matching_pass1', 'matching_pass2', 'priors', 'removeOutliers_small', 'removeOutliers_large']
+    names = ['pushBack', 'matching_pass1', 'matching_pass2', 'priors', 'removeOutliers_small', 'removeOutliers_large',
+             'ransacEstimateF', 'estimateMotion_total']
     return {n: (float(sec[k]), int(calls[k])) for k, n in enumerate(names)}
 
 

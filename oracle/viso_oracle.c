@@ -437,6 +437,9 @@ void vo_refine_pixel(vo_match* pm, int n, int method, const int32_t dims_p[3], c
 void vo_svd(double* a, int m, int n, double* w, double* v) {
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) v[i * n + j] = i == j;
+  double total = 0;
+  for (int k = 0; k < m * n; k++) total += a[k] * a[k];
+  const double tiny = 1e-28 * total; /* numerically null columns (the 8x9 system always has one) are left alone */
   for (int sweep = 0; sweep < 60; sweep++) {
     int rotated = 0;
     for (int p = 0; p < n - 1; p++)
@@ -445,7 +448,7 @@ void vo_svd(double* a, int m, int n, double* w, double* v) {
         for (int i = 0; i < m; i++) {
           alpha += a[i * n + p] * a[i * n + p]; beta += a[i * n + q] * a[i * n + q]; gamma += a[i * n + p] * a[i * n + q];
         }
-        if (fabs(gamma) <= 1e-15 * sqrt(alpha * beta)) continue;
+        if (alpha <= tiny || beta <= tiny || fabs(gamma) <= 1e-15 * sqrt(alpha * beta)) continue;
         rotated = 1;
         const double zeta = (beta - alpha) / (2.0 * gamma);
         const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
