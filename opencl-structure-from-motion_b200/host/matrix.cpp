@@ -330,7 +330,7 @@ void Matrix::svd(Matrix& U2, Matrix& W, Matrix& V) {
         for (int32_t i = 0; i < N; i++) { const FLOAT a = vp[i], b = vq[i]; vp[i] = c * a - s * b; vq[i] = s * a + c * b; }
       }
   }
-  if (!converged) cerr << "ERROR in SVD: No convergence in 60 Jacobi sweeps" << endl;
+  if (!converged) cerr << "ERROR in SVD: No convergence in 60 Jacobi sweeps" << endl;   // cf. matrix.cpp:713-714
   std::vector<FLOAT> w(N);
   for (int32_t j = 0; j < N; j++) {
     FLOAT s = 0;
@@ -343,12 +343,37 @@ void Matrix::svd(Matrix& U2, Matrix& W, Matrix& V) {
   Matrix Un(M, N);
   V = Matrix(N, N);
   std::vector<FLOAT> ws(N);
+  // left singular vectors: g_j / sigma_j; for a (numerically) zero singular value that quotient is noise, so the column
+  // is completed to an orthonormal set instead (the pose recovery multiplies with the full U of a rank-2 matrix)
+  const FLOAT wmax = N > 0 ? w[order[0]] : 0;
+  for (int32_t k = 0; k < N && k < M; k++) {
+    const int32_t j = order[k];
+    if (w[j] > 1e-13 * wmax && w[j] > 0) {
+      for (int32_t i = 0; i < M; i++) Un.val[i][k] = g[(size_t)j * M + i] / w[j];
+      continue;
+    }
+    FLOAT best = -1;
+    std::vector<FLOAT> cand(M), pick(M, 0.0);
+    for (int32_t e = 0; e < M; e++) {
+      for (int32_t i = 0; i < M; i++) cand[i] = i == e ? 1.0 : 0.0;
+      for (int pass = 0; pass < 2; pass++)
+        for (int32_t c = 0; c < k; c++) {
+          FLOAT dot = 0;
+          for (int32_t i = 0; i < M; i++) dot += Un.val[i][c] * cand[i];
+          for (int32_t i = 0; i < M; i++) cand[i] -= dot * Un.val[i][c];
+        }
+      FLOAT nrm = 0;
+      for (int32_t i = 0; i < M; i++) nrm += cand[i] * cand[i];
+      if (nrm > best) { best = nrm; pick = cand; }
+    }
+    const FLOAT inv = best > 0 ? 1.0 / sqrt(best) : 0.0;
+    for (int32_t i = 0; i < M; i++) Un.val[i][k] = pick[i] * inv;
+  }
   for (int32_t k = 0; k < N; k++) {
     const int32_t j = order[k];
     ws[k] = w[j];
     int32_t neg = 0;
     for (int32_t i = 0; i < M; i++) {
-      Un.val[i][k] = w[j] > 0 ? g[(size_t)j * M + i] / w[j] : 0.0;
       if (Un.val[i][k] < 0) neg++;
     }
     for (int32_t i = 0; i < N; i++) {
