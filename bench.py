@@ -265,7 +265,10 @@ def run_ours(args, rank, world, local_rank):
         peaks, which = measured_peaks()
         achieved = alg * nfr / (fms * 1e-3) / 1e9 if fms > 0 else 0.0
         roof = {'bound': 'hbm', 'kernel': 'k_filter_nms', 'achieved': round(achieved, 2), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': round(achieved / peaks['hbm_gbs'], 5), 'traffic': None, 'peak_source': which + ' (MEASURED_PEAKS.json hbm_gbs)',
+                'frac': round(achieved / peaks['hbm_gbs'], 5),
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this workload, from the committed
+                # `ncu --set full` capture profiles/r1_v2_filter_nms_raw.csv (60.72 MB + 110.33 MB)
+                'traffic': 171055104, 'traffic_source': 'profiles/r1_v2_filter_nms_summary.md', 'peak_source': which + ' (MEASURED_PEAKS.json hbm_gbs)',
                 'launch_ms': round(fms / max(nl, 1), 5), 'frames_per_launch': nb,
                 'algorithmic_bytes_per_launch': int(alg * nb),
                 'workload': '128 frames of 1241x376 per launch, half_resolution=0 (180 MB of algorithmic traffic per launch, larger than L2)',
@@ -282,7 +285,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='flow', choices=['flow', 'quad', 'mono'])

@@ -123,14 +123,18 @@ void Matcher::push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool re
   }
   n_feat[2] = ns[0]; n_feat[6] = nd[0];
   n_feat[3] = I2 ? ns[1] : 0; n_feat[7] = I2 ? nd[1] : 0;
-  // host copy of the left image for getGain
-  if (!on_device) {
-    I1c.resize((size_t)dims_c[2] * height);
-    for (int32_t v = 0; v < height; v++) memcpy(&I1c[(size_t)v * dims_c[2]], I1 + (size_t)v * bpl, width);
-    have_I1c = true;
-  } else {
-    have_I1c = false;
-  }
+  // getGain needs the two left images on the host (matcher.cpp:286-324); they are fetched from the device on demand
+  have_I1c = false;
+}
+
+// padded copy of a left image (previous or current) from the device frame it lives in
+bool Matcher::fetchImage(int which, vector<uint8_t>& out) {
+  const int32_t f = slot[which];
+  if (f < 0 || !ctx) return false;
+  int32_t d3[3];
+  if (visocu_get_plane(ctx, f, 4, 0, 0, d3) != VISOCU_OK) return false;
+  out.resize((size_t)d3[2] * d3[1]);
+  return visocu_get_plane(ctx, f, 4, out.data(), out.size(), d3) == VISOCU_OK;
 }
 
 bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_prior, int refine) {
@@ -220,7 +224,10 @@ static float window_mean(const vector<uint8_t>& I, int32_t bpl, int32_t u_min, i
 }
 
 float Matcher::getGain(vector<int32_t> inliers) {
-  if (!have_I1p || !have_I1c || p_matched_2.empty() || inliers.empty()) return 1;
+  if (slot[0] < 0 || slot[2] < 0 || p_matched_2.empty() || inliers.empty()) return 1;
+  if (!have_I1p) have_I1p = fetchImage(0, I1p);
+  if (!have_I1c) have_I1c = fetchImage(2, I1c);
+  if (!have_I1p || !have_I1c) return 1;
   const int32_t ws = 3;
   float gain = 0;
   int32_t num = 0;

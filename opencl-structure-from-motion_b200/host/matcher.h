@@ -86,6 +86,7 @@ public:
 private:
   void push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool replace, bool on_device);
   bool ensureContext(int32_t w, int32_t h);
+  bool fetchImage(int which, std::vector<uint8_t>& out);
   bool matching(int pass, std::vector<p_match>& out, int32_t method, bool use_prior, int refine);
 
   parameters param;
@@ -98,7 +99,7 @@ private:
   int32_t slot[4];
   int32_t n_feat[8];
   int32_t dims_p[3], dims_c[3];
-  std::vector<uint8_t> I1p, I1c;         // host copies kept for getGain (matcher.cpp:286-324)
+  std::vector<uint8_t> I1p, I1c;         // host copies for getGain (matcher.cpp:286-324), fetched from the device lazily
   bool have_I1p, have_I1c;
   std::vector<p_match> p_matched_1, p_matched_2;
   std::vector<range> ranges;
