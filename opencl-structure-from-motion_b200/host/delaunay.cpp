@@ -24,16 +24,28 @@ namespace {
 
 struct HalfEdge { int32_t onext, oprev, org, dead; };
 
+struct Pt { int32_t x, y; };
+
 struct Mesh {
-  const int32_t* px;
-  const int32_t* py;
-  std::vector<HalfEdge> he;                 // per directed edge; sym(e) = e ^ 1
-  void set_points(const int32_t* x, const int32_t* y) { px = x; py = y; }
+  const Pt* pt;
+  HalfEdge* he;                             // per directed edge; sym(e) = e ^ 1 (storage owned by the caller)
+  int nhe, cap;
+  std::vector<HalfEdge> store;
+  void set_points(const Pt* p) { pt = p; }
+  void reset(size_t want) {
+    if (store.size() < want) store.resize(want);
+    he = store.data(); cap = (int)store.size(); nhe = 0;
+  }
 
   int make_edge(int a, int b) {
-    const int e = (int)he.size();
-    he.push_back(HalfEdge{e, e, a, 0});
-    he.push_back(HalfEdge{e + 1, e + 1, b, 0});
+    if (nhe + 2 > cap) {                    // cannot happen with the 12 n reservation (3 n live + deleted edges); grow anyway
+      store.resize(store.size() * 2 + 64);
+      he = store.data(); cap = (int)store.size();
+    }
+    const int e = nhe;
+    he[e] = HalfEdge{e, e, a, 0};
+    he[e + 1] = HalfEdge{e + 1, e + 1, b, 0};
+    nhe += 2;
     return e;
   }
   static int sym(int e) { return e ^ 1; }
@@ -67,13 +79,15 @@ struct Mesh {
   }
   // > 0 iff a, b, c make a left turn
   int64_t ccw(int a, int b, int c) const {
-    return (int64_t)(px[a] - px[c]) * (py[b] - py[c]) - (int64_t)(py[a] - py[c]) * (px[b] - px[c]);
+    const Pt A = pt[a], B = pt[b], C = pt[c];
+    return (int64_t)(A.x - C.x) * (B.y - C.y) - (int64_t)(A.y - C.y) * (B.x - C.x);
   }
   // > 0 iff d lies strictly inside the circle through a, b, c (a, b, c counter-clockwise)
   int64_t incircle(int a, int b, int c, int d) const {
-    const int64_t adx = px[a] - px[d], ady = py[a] - py[d];
-    const int64_t bdx = px[b] - px[d], bdy = py[b] - py[d];
-    const int64_t cdx = px[c] - px[d], cdy = py[c] - py[d];
+    const Pt A = pt[a], B = pt[b], C = pt[c], D = pt[d];
+    const int64_t adx = A.x - D.x, ady = A.y - D.y;
+    const int64_t bdx = B.x - D.x, bdy = B.y - D.y;
+    const int64_t cdx = C.x - D.x, cdy = C.y - D.y;
     const int64_t al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
     return al * (bdx * cdy - cdx * bdy) + bl * (cdx * ady - adx * cdy) + cl * (adx * bdy - bdx * ady);
   }
@@ -88,17 +102,17 @@ struct PivotSource {
   }
 };
 
-bool before_xy(const Mesh& m, int a, int px, int py) { return m.px[a] < px || (m.px[a] == px && m.py[a] < py); }
-bool after_xy(const Mesh& m, int a, int px, int py) { return m.px[a] > px || (m.px[a] == px && m.py[a] > py); }
+bool before_xy(const Mesh& m, int a, int px, int py) { return m.pt[a].x < px || (m.pt[a].x == px && m.pt[a].y < py); }
+bool after_xy(const Mesh& m, int a, int px, int py) { return m.pt[a].x > px || (m.pt[a].x == px && m.pt[a].y > py); }
 
 void pivot_quicksort(const Mesh& m, int* a, int n, PivotSource& rnd) {
   if (n < 2) return;
   if (n == 2) {
-    if (after_xy(m, a[0], m.px[a[1]], m.py[a[1]])) std::swap(a[0], a[1]);
+    if (after_xy(m, a[0], m.pt[a[1]].x, m.pt[a[1]].y)) std::swap(a[0], a[1]);
     return;
   }
   const int pv = a[rnd.next((unsigned)n)];
-  const int px = m.px[pv], py = m.py[pv];
+  const int px = m.pt[pv].x, py = m.pt[pv].y;
   int left = -1, right = n;
   while (left < right) {
     do { left++; } while (left <= right && before_xy(m, a[left], px, py));
@@ -123,9 +137,11 @@ void partition(int* xl, int* yl, int n, int axis, uint8_t* side, int* tmp) {
   for (int i = 0; i < divider; i++) side[from[i]] = 0;
   for (int i = divider; i < n; i++) side[from[i]] = 1;
   int a = 0, b = 0;
-  for (int i = 0; i < n; i++) {
+  for (int i = 0; i < n; i++) {            // branch-free stable distribution (the side bits are unpredictable)
     const int id = other[i];
-    if (side[id]) tmp[b++] = id; else other[a++] = id;
+    const int s = side[id];
+    tmp[b] = id; other[a] = id;
+    b += s; a += 1 - s;
   }
   for (int i = 0; i < b; i++) other[divider + i] = tmp[i];
   partition(xl, yl, divider, 1 - axis, side, tmp);
@@ -136,10 +152,10 @@ Handles merge(Mesh& m, Handles L, Handles R, int axis) {
   int ldo = L.ldo, ldi = L.rdo, rdi = R.ldo, rdo = R.rdo;
   if (axis == 1) {
     // the two sets are separated by a horizontal line: seat the handles on the y-extremes
-    while (m.py[m.dest(ldo)] < m.py[m.org(ldo)]) ldo = m.rprev(ldo);
-    while (m.py[m.dest(m.onext(ldi))] > m.py[m.org(ldi)]) ldi = Mesh::sym(m.onext(ldi));
-    while (m.py[m.dest(rdi)] < m.py[m.org(rdi)]) rdi = m.rprev(rdi);
-    while (m.py[m.dest(m.onext(rdo))] > m.py[m.org(rdo)]) rdo = Mesh::sym(m.onext(rdo));
+    while (m.pt[m.dest(ldo)].y < m.pt[m.org(ldo)].y) ldo = m.rprev(ldo);
+    while (m.pt[m.dest(m.onext(ldi))].y > m.pt[m.org(ldi)].y) ldi = Mesh::sym(m.onext(ldi));
+    while (m.pt[m.dest(rdi)].y < m.pt[m.org(rdi)].y) rdi = m.rprev(rdi);
+    while (m.pt[m.dest(m.onext(rdo))].y > m.pt[m.org(rdo)].y) rdo = Mesh::sym(m.onext(rdo));
   }
   // lower common tangent
   bool changed;
@@ -188,8 +204,8 @@ Handles merge(Mesh& m, Handles L, Handles R, int axis) {
   }
   if (axis == 1) {
     // back to the x-extremes expected by the parent (vertical cut) and by the leaves
-    while (m.px[m.dest(m.oprev(ldo))] < m.px[m.org(ldo)]) ldo = Mesh::sym(m.oprev(ldo));
-    while (m.px[m.dest(rdo)] > m.px[m.org(rdo)]) rdo = m.lnext(rdo);
+    while (m.pt[m.dest(m.oprev(ldo))].x < m.pt[m.org(ldo)].x) ldo = Mesh::sym(m.oprev(ldo));
+    while (m.pt[m.dest(rdo)].x > m.pt[m.org(rdo)].x) rdo = m.lnext(rdo);
   }
   return Handles{ldo, rdo};
 }
@@ -221,6 +237,7 @@ namespace {
 
 struct Scratch {
   std::vector<int32_t> sx, sy, orig, cnt;
+  std::vector<Pt> pts, pts_in;
   std::vector<int> v, yl, tmp, a, b;
   std::vector<uint8_t> side;
   Mesh m;
@@ -263,7 +280,9 @@ Handles triangulate(Scratch& S, const int32_t* x, const int32_t* y, int n) {
     // each run of equal points is kept.
     for (int i = 0; i < n; i++) S.a[i] = i;
     Mesh tmpm;
-    tmpm.set_points(x, y);
+    S.pts_in.resize(n);
+    for (int i = 0; i < n; i++) S.pts_in[i] = Pt{x[i], y[i]};
+    tmpm.set_points(S.pts_in.data());
     PivotSource pivots;
     pivot_quicksort(tmpm, S.a.data(), n, pivots);
     S.orig.push_back(S.a[0]);
@@ -279,16 +298,15 @@ Handles triangulate(Scratch& S, const int32_t* x, const int32_t* y, int n) {
   for (int i = 0; i < nu; i++) S.v[i] = i;
   counting_pass(S.v, S.yl, S.sy.data(), ylo, yhi - ylo + 1, S.cnt);     // ids in (y, x) order
   S.side.resize(nu); S.tmp.resize(nu);
-  S.m.set_points(S.sx.data(), S.sy.data());
-  S.m.he.clear();
-  S.m.he.reserve(12 * (size_t)nu);
+  S.m.reset(12 * (size_t)nu + 64);
   // root: vertical cut of the x-sorted list, children by alternating axes
   partition(S.v.data(), S.yl.data(), nu, 0, S.side.data(), S.tmp.data());
   // renumber once more, in partition order: every subtree of the divide-and-conquer then works on a contiguous range
   // of vertices (and of the edges it creates), which keeps the merge loops in cache
-  S.cnt.resize(nu); S.yl.resize(nu);
-  for (int i = 0; i < nu; i++) { S.cnt[i] = S.sx[S.v[i]]; S.yl[i] = S.sy[S.v[i]]; S.tmp[i] = S.orig[S.v[i]]; }
-  for (int i = 0; i < nu; i++) { S.sx[i] = S.cnt[i]; S.sy[i] = S.yl[i]; S.orig[i] = S.tmp[i]; S.v[i] = i; }
+  S.pts.resize(nu);
+  for (int i = 0; i < nu; i++) { S.pts[i] = Pt{S.sx[S.v[i]], S.sy[S.v[i]]}; S.tmp[i] = S.orig[S.v[i]]; }
+  for (int i = 0; i < nu; i++) { S.orig[i] = S.tmp[i]; S.v[i] = i; }
+  S.m.set_points(S.pts.data());
   return build(S.m, S.v.data(), nu, 0);
 }
 
@@ -306,7 +324,7 @@ void delaunay_triangles(const int32_t* x, const int32_t* y, int n, std::vector<i
   if (triangulate(S, x, y, n).ldo < 0) return;
   const Mesh& m = S.m;
   // every bounded face is a counter-clockwise triangle; report each once, from its lowest-numbered half-edge
-  const int ne = (int)m.he.size();
+  const int ne = m.nhe;
   tri.reserve(6 * S.orig.size());
   for (int e = 0; e < ne; e++) {
     if (m.he[e].dead) continue;
@@ -330,7 +348,7 @@ void delaunay_edges(const int32_t* x, const int32_t* y, int n, std::vector<int32
   // hull edge out of the rightmost vertex.  Every other face of a Delaunay triangulation is a triangle.
   int e = h.rdo;
   do { m.he[e].dead |= 2; e = m.lnext(e); } while (e != h.rdo);
-  const int ne = (int)m.he.size();
+  const int ne = m.nhe;
   edges.reserve(9 * S.orig.size());
   for (int k = 0; k < ne; k += 2) {
     const int d0 = m.he[k].dead, d1 = m.he[k + 1].dead;
