@@ -60,7 +60,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(',')])
+
+    def mark(self):
+        """start (first call) / end (second call) of the timed region"""
+        self.marks = getattr(self, 'marks', []) + [time.time()]
 
     def stop(self):
         if not self.proc:
@@ -70,10 +74,16 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        marks = getattr(self, 'marks', [])
+        rows = self.rows
+        if len(marks) == 2:          # samples taken during the timed region (the 200 ms sampling grid is padded by one tick)
+            inside = [r for r in rows if marks[0] - 0.25 <= r[0] <= marks[1] + 0.25]
+            rows = inside or rows[-1:]
+        rows = [r[1:] for r in rows]
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
                 'samples': len(sm)}
 
@@ -202,6 +212,7 @@ def run_ours(args, rank, world, local_rank):
 
     def timed(on_device):
         runner = Hh.Runner(local_rank, S, threads, mode, method, mp)
+        sampler = ClockSampler(local_rank) if (rank == 0 and on_device) else None     # sampling starts before the warm-up
         base = dev if on_device else pinned
         stereo = workload == 'quad'
         k = 0
@@ -213,18 +224,22 @@ def run_ours(args, rank, world, local_rank):
         l0 = runner.launches(); b0 = runner.transfer_bytes()
         Hh.stage_times(reset=True)
         tctx.sync(); barrier()
-        sampler = ClockSampler(local_rank) if (rank == 0 and on_device) else None
+        if sampler:
+            sampler.mark()
         tctx.timer_start()
         t0 = time.perf_counter()
-        total_matches = 0; oks = 0
-        for _ in range(K):
-            secs, nm, ok = runner.step(frame_ptrs(base, k), dims, frame_ptrs(base, k, True) if stereo else None,
-                                       on_device=on_device, bucket=stereo)
-            total_matches += int(nm.sum()); oks += int(ok.sum())
-            k += 1
+        # the K timed steps run back to back inside the host library: every worker walks its own sequences through
+        # the K frames, no barrier between steps (the sequences are independent)
+        steps1 = [frame_ptrs(base, k + j) for j in range(K)]
+        steps2 = [frame_ptrs(base, k + j, True) for j in range(K)] if stereo else None
+        secs, nm, ok = runner.run(steps1, dims, steps2, on_device=on_device, bucket=stereo)
+        total_matches = int(nm.sum()); oks = int(ok.sum())
+        k += K
         tctx.sync()
         ms = tctx.timer_stop()
         wall = time.perf_counter() - t0
+        if sampler:
+            sampler.mark()
         clocks = sampler.stop() if sampler else None
         barrier()
         l1 = runner.launches(); b1 = runner.transfer_bytes()

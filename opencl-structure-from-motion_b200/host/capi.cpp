@@ -222,6 +222,47 @@ VISOB_API double visob_runner_step(void* h, const uint8_t* const* imgs, const ui
   if (ok_out) memcpy(ok_out, r->last_ok.data(), sizeof(int32_t) * r->S);
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
+// K steps without a barrier between them: worker t walks its sequences (t, t + threads, ...) through all K frames.
+// imgs / imgs2: K x S pointers, step-major.  n_matches_out / ok_out (K x S, optional) receive per-pair results.
+VISOB_API double visob_runner_run(void* h, int n_steps, const uint8_t* const* imgs, const uint8_t* const* imgs2, const int32_t* dims,
+                                  int on_device, int bucket, int32_t* n_matches_out, int32_t* ok_out) {
+  Runner* r = (Runner*)h;
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&](int tid) {
+    visob::set_device(r->device);
+    uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+    for (int k = 0; k < n_steps; k++) {
+      for (int s = tid; s < r->S; s += r->threads) {
+        const uint8_t* i1 = imgs[(size_t)k * r->S + s];
+        const uint8_t* i2 = imgs2 ? imgs2[(size_t)k * r->S + s] : 0;
+        int32_t nm = 0, ok = 1;
+        if (r->mode == 1) {
+          MonoAccess* vo = r->monos[s];
+          ok = (on_device ? vo->processDevice(i1, d, false) : vo->process(const_cast<uint8_t*>(i1), d, false)) ? 1 : 0;
+          nm = vo->getNumberOfMatches();
+        } else {
+          Matcher* m = r->matchers[s];
+          if (on_device) m->pushBackDevice(i1, i2, d, false);
+          else m->pushBack(const_cast<uint8_t*>(i1), const_cast<uint8_t*>(i2), d, false);
+          m->matchFeatures(r->method, 0);
+          if (bucket) m->bucketFeatures(r->bucket_max, r->bucket_w, r->bucket_h);
+          nm = (int32_t)m->matches(2).size();
+        }
+        r->last_matches[s] = nm; r->last_ok[s] = ok;
+        if (n_matches_out) n_matches_out[(size_t)k * r->S + s] = nm;
+        if (ok_out) ok_out[(size_t)k * r->S + s] = ok;
+      }
+    }
+  };
+  if (r->threads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < r->threads; t++) pool.emplace_back(work, t);
+    for (std::thread& t : pool) t.join();
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 VISOB_API int visob_runner_get_matches(void* h, int seq, void* out, int cap) {
   Runner* r = (Runner*)h;
   if (seq < 0 || seq >= r->S) return -1;

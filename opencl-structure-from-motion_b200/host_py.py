@@ -41,6 +41,7 @@ def lib():
             getattr(L, name).restype = C.c_void_p
         L.visob_matcher_gain.restype = C.c_float
         L.visob_runner_step.restype = C.c_double
+        L.visob_runner_run.restype = C.c_double
         L.visob_runner_launches.restype = C.c_uint64
         _lib = L
     return _lib
@@ -220,6 +221,16 @@ class Runner:
         nm = np.zeros(S, np.int32); ok = np.zeros(S, np.int32)
         d = np.ascontiguousarray(dims, np.int32)
         secs = lib().visob_runner_step(self.h, a, b, _p(d), int(on_device), int(bucket), _p(nm), _p(ok))
+        return secs, nm, ok
+
+    def run(self, ptr_steps, dims, ptr_steps2=None, on_device=False, bucket=False):
+        """K steps with no barrier in between; ptr_steps: K lists of S pointers."""
+        K, S = len(ptr_steps), self.S
+        a = (C.c_void_p * (K * S))(*[p for row in ptr_steps for p in row])
+        b = (C.c_void_p * (K * S))(*[p for row in ptr_steps2 for p in row]) if ptr_steps2 is not None else None
+        nm = np.zeros((K, S), np.int32); ok = np.zeros((K, S), np.int32)
+        d = np.ascontiguousarray(dims, np.int32)
+        secs = lib().visob_runner_run(self.h, K, a, b, _p(d), int(on_device), int(bucket), _p(nm), _p(ok))
         return secs, nm, ok
 
     def matches(self, seq):
