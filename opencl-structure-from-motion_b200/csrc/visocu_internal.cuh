@@ -56,6 +56,7 @@ struct visocu_ctx {
   // scratch for matching / ransac, grown on demand
   void* scratch = nullptr; size_t scratch_bytes = 0;
   void* pinned = nullptr;  size_t pinned_bytes = 0;
+  uint8_t* img_stage = nullptr; size_t img_stage_bytes = 0;   // contiguous landing area for host images
   uint64_t launches = 0;
   CUtensorMap tmap_img;              // TMA descriptor of the matching-resolution image planes of the pool
   int use_tma = 0;
