@@ -230,6 +230,20 @@ class Context:
         self._ck(lib().visocu_match_stats(self.h, C.byref(a), C.byref(b)), 'match_stats')
         return a.value, b.value
 
+    # ---- pose helpers
+    def triangulate(self, uv, P1, P2s):
+        uv = np.ascontiguousarray(uv, np.float32); N = len(uv)
+        P1 = np.ascontiguousarray(P1, np.float64); P2s = np.ascontiguousarray(P2s, np.float64)
+        ns = len(P2s)
+        X = np.zeros((ns, 4, N)); nf = np.zeros(ns, np.int32)
+        self._ck(lib().visocu_triangulate(self.h, _p(uv), N, _p(P1), _p(P2s), ns, _p(X), _p(nf)), 'triangulate')
+        return X, nf
+
+    def best_plane(self, d, threshold, weight):
+        d = np.ascontiguousarray(d, np.float64); idx = C.c_int32()
+        self._ck(lib().visocu_best_plane(self.h, _p(d), len(d), C.c_double(threshold), C.c_double(weight), C.byref(idx)), 'best_plane')
+        return idx.value
+
     # ---- ransac
     def ransac(self, uv_list, samples_list, thresh=1e-5, want_all=False):
         nj = len(uv_list)
