@@ -150,19 +150,58 @@ VISOB_API void visob_svd(const double* A, int m, int n, double* U, double* W, do
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Sharded sequence runner.  S independent sequences live on one GPU; `step` feeds one new frame (or stereo pair)
-// to every sequence and matches it against that sequence's previous frame.  Sequences are dealt round-robin to
-// `threads` host workers; every Matcher has its own CUDA stream, so kernels of different sequences overlap on the
-// GPU while other workers run the host stages (outlier removal, priors, bucketing).
+// Sharded sequence runner.  S independent sequences live on one GPU; sequences are dealt round-robin to `threads` host
+// workers.  Matcher mode: every worker drives its sequences through ONE MatcherBatch (one context, one stream, every GPU
+// stage a single batched launch for all of the worker's sequences) and runs their host stages (outlier removal, priors,
+// bucketing) in between; the workers' streams overlap on the GPU.  Mono-odometry mode: one VisualOdometryMono per
+// sequence (each with its own stream).
 namespace {
 struct Runner {
   int device, S, threads, mode, method;      // mode 0 = Matcher only, 1 = VisualOdometryMono::process
   int bucket_max; float bucket_w, bucket_h;
-  std::vector<Matcher*> matchers;
-  std::vector<MonoAccess*> monos;
-  std::vector<int32_t> last_matches;         // per sequence: matches of the last step (mode 1: 1 = process ok, else 0 in last_ok)
-  std::vector<int32_t> last_ok;
+  std::vector<MatcherBatch*> batches;        // one per worker (mode 0)
+  std::vector<MonoAccess*> monos;            // one per sequence (mode 1)
+  std::vector<int32_t> last_matches, last_ok;
+  Matcher& matcher_of(int seq) { return batches[seq % threads]->sequence(seq / threads); }
 };
+
+// one frame for every sequence of worker `tid`
+void runner_advance(Runner* r, int tid, const uint8_t* const* imgs, const uint8_t* const* imgs2, const int32_t* dims, int on_device,
+                    int bucket, int32_t* n_matches_out, int32_t* ok_out) {
+  uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+  if (r->mode == 1) {
+    for (int s = tid; s < r->S; s += r->threads) {
+      MonoAccess* vo = r->monos[s];
+      const bool ok = on_device ? vo->processDevice(imgs[s], d, false) : vo->process(const_cast<uint8_t*>(imgs[s]), d, false);
+      r->last_ok[s] = ok ? 1 : 0;
+      r->last_matches[s] = vo->getNumberOfMatches();
+    }
+  } else {
+    MatcherBatch* b = r->batches[tid];
+    std::vector<const uint8_t*> i1, i2;
+    for (int s = tid; s < r->S; s += r->threads) { i1.push_back(imgs[s]); if (imgs2) i2.push_back(imgs2[s]); }
+    b->pushBack(i1.data(), imgs2 ? i2.data() : 0, d, false, on_device != 0);
+    b->matchFeatures(r->method);
+    int k = 0;
+    for (int s = tid; s < r->S; s += r->threads, k++) {
+      Matcher& m = b->sequence(k);
+      if (bucket) m.bucketFeatures(r->bucket_max, r->bucket_w, r->bucket_h);
+      r->last_matches[s] = (int32_t)m.matches(2).size();
+      r->last_ok[s] = 1;
+    }
+  }
+  for (int s = tid; s < r->S; s += r->threads) {
+    if (n_matches_out) n_matches_out[s] = r->last_matches[s];
+    if (ok_out) ok_out[s] = r->last_ok[s];
+  }
+}
+
+template <class F> void run_workers(int threads, F work) {
+  if (threads == 1) { work(0); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++) pool.emplace_back(work, t);
+  for (std::thread& t : pool) t.join();
+}
 }  // namespace
 
 VISOB_API void* visob_runner_create(int device, int n_sequences, int threads, int mode, int method, const MonoParamsC* p) {
@@ -170,9 +209,14 @@ VISOB_API void* visob_runner_create(int device, int n_sequences, int threads, in
   r->device = device; r->S = n_sequences; r->threads = std::max(1, std::min(threads, n_sequences)); r->mode = mode; r->method = method;
   r->bucket_max = p->bucket_max_features; r->bucket_w = (float)p->bucket_width; r->bucket_h = (float)p->bucket_height;
   visob::set_device(device);
-  for (int s = 0; s < n_sequences; s++) {
-    if (mode == 1) r->monos.push_back(new MonoAccess(to_cpp(p)));
-    else r->matchers.push_back(new Matcher(p->match));
+  if (mode == 1) {
+    for (int s = 0; s < n_sequences; s++) r->monos.push_back(new MonoAccess(to_cpp(p)));
+  } else {
+    for (int t = 0; t < r->threads; t++) {
+      int n = 0;
+      for (int s = t; s < n_sequences; s += r->threads) n++;
+      r->batches.push_back(new MatcherBatch(p->match, n));
+    }
   }
   r->last_matches.assign(n_sequences, 0);
   r->last_ok.assign(n_sequences, 0);
@@ -180,7 +224,7 @@ VISOB_API void* visob_runner_create(int device, int n_sequences, int threads, in
 }
 VISOB_API void visob_runner_destroy(void* h) {
   Runner* r = (Runner*)h;
-  for (Matcher* m : r->matchers) delete m;
+  for (MatcherBatch* b : r->batches) delete b;
   for (MonoAccess* m : r->monos) delete m;
   delete r;
 }
@@ -190,36 +234,10 @@ VISOB_API double visob_runner_step(void* h, const uint8_t* const* imgs, const ui
                                    int on_device, int bucket, int32_t* n_matches_out, int32_t* ok_out) {
   Runner* r = (Runner*)h;
   auto t0 = std::chrono::steady_clock::now();
-  auto work = [&](int tid) {
+  run_workers(r->threads, [&](int tid) {
     visob::set_device(r->device);
-    uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
-    for (int s = tid; s < r->S; s += r->threads) {
-      if (r->mode == 1) {
-        MonoAccess* vo = r->monos[s];
-        bool ok = on_device ? vo->processDevice(imgs[s], d, false) : vo->process(const_cast<uint8_t*>(imgs[s]), d, false);
-        r->last_ok[s] = ok ? 1 : 0;
-        r->last_matches[s] = vo->getNumberOfMatches();
-      } else {
-        Matcher* m = r->matchers[s];
-        const uint8_t* i2 = imgs2 ? imgs2[s] : 0;
-        if (on_device) m->pushBackDevice(imgs[s], i2, d, false);
-        else m->pushBack(const_cast<uint8_t*>(imgs[s]), const_cast<uint8_t*>(i2), d, false);
-        m->matchFeatures(r->method, 0);
-        if (bucket) m->bucketFeatures(r->bucket_max, r->bucket_w, r->bucket_h);
-        r->last_matches[s] = (int32_t)m->matches(2).size();
-        r->last_ok[s] = 1;
-      }
-    }
-  };
-  if (r->threads == 1) {
-    work(0);
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < r->threads; t++) pool.emplace_back(work, t);
-    for (std::thread& t : pool) t.join();
-  }
-  if (n_matches_out) memcpy(n_matches_out, r->last_matches.data(), sizeof(int32_t) * r->S);
-  if (ok_out) memcpy(ok_out, r->last_ok.data(), sizeof(int32_t) * r->S);
+    runner_advance(r, tid, imgs, imgs2, dims, on_device, bucket, n_matches_out, ok_out);
+  });
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 // K steps without a barrier between them: worker t walks its sequences (t, t + threads, ...) through all K frames.
@@ -228,46 +246,19 @@ VISOB_API double visob_runner_run(void* h, int n_steps, const uint8_t* const* im
                                   int on_device, int bucket, int32_t* n_matches_out, int32_t* ok_out) {
   Runner* r = (Runner*)h;
   auto t0 = std::chrono::steady_clock::now();
-  auto work = [&](int tid) {
+  run_workers(r->threads, [&](int tid) {
     visob::set_device(r->device);
-    uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
-    for (int k = 0; k < n_steps; k++) {
-      for (int s = tid; s < r->S; s += r->threads) {
-        const uint8_t* i1 = imgs[(size_t)k * r->S + s];
-        const uint8_t* i2 = imgs2 ? imgs2[(size_t)k * r->S + s] : 0;
-        int32_t nm = 0, ok = 1;
-        if (r->mode == 1) {
-          MonoAccess* vo = r->monos[s];
-          ok = (on_device ? vo->processDevice(i1, d, false) : vo->process(const_cast<uint8_t*>(i1), d, false)) ? 1 : 0;
-          nm = vo->getNumberOfMatches();
-        } else {
-          Matcher* m = r->matchers[s];
-          if (on_device) m->pushBackDevice(i1, i2, d, false);
-          else m->pushBack(const_cast<uint8_t*>(i1), const_cast<uint8_t*>(i2), d, false);
-          m->matchFeatures(r->method, 0);
-          if (bucket) m->bucketFeatures(r->bucket_max, r->bucket_w, r->bucket_h);
-          nm = (int32_t)m->matches(2).size();
-        }
-        r->last_matches[s] = nm; r->last_ok[s] = ok;
-        if (n_matches_out) n_matches_out[(size_t)k * r->S + s] = nm;
-        if (ok_out) ok_out[(size_t)k * r->S + s] = ok;
-      }
-    }
-  };
-  if (r->threads == 1) {
-    work(0);
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < r->threads; t++) pool.emplace_back(work, t);
-    for (std::thread& t : pool) t.join();
-  }
+    for (int k = 0; k < n_steps; k++)
+      runner_advance(r, tid, imgs + (size_t)k * r->S, imgs2 ? imgs2 + (size_t)k * r->S : 0, dims, on_device, bucket,
+                     n_matches_out ? n_matches_out + (size_t)k * r->S : 0, ok_out ? ok_out + (size_t)k * r->S : 0);
+  });
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 VISOB_API int visob_runner_get_matches(void* h, int seq, void* out, int cap) {
   Runner* r = (Runner*)h;
   if (seq < 0 || seq >= r->S) return -1;
   if (r->mode == 1) return copy_matches(r->monos[seq]->usedMatches(), out, cap);
-  return copy_matches(r->matchers[seq]->matches(2), out, cap);
+  return copy_matches(r->matcher_of(seq).matches(2), out, cap);
 }
 VISOB_API void visob_runner_get_motion(void* h, int seq, double* out16) {
   Runner* r = (Runner*)h;
@@ -278,14 +269,14 @@ VISOB_API void visob_runner_get_motion(void* h, int seq, double* out16) {
 VISOB_API void visob_runner_transfer_bytes(void* h, uint64_t* h2d, uint64_t* d2h) {
   Runner* r = (Runner*)h;
   uint64_t a = 0, b = 0, x = 0, y = 0;
-  for (Matcher* m : r->matchers) if (m->context() && visocu_transfer_bytes(m->context(), &x, &y) == 0) { a += x; b += y; }
+  for (MatcherBatch* m : r->batches) if (m->context() && visocu_transfer_bytes(m->context(), &x, &y) == 0) { a += x; b += y; }
   for (MonoAccess* v : r->monos) if (v->getMatcher()->context() && visocu_transfer_bytes(v->getMatcher()->context(), &x, &y) == 0) { a += x; b += y; }
   *h2d = a; *d2h = b;
 }
 VISOB_API uint64_t visob_runner_launches(void* h) {
   Runner* r = (Runner*)h;
   uint64_t total = 0, n = 0;
-  for (Matcher* m : r->matchers) if (m->context() && visocu_launch_count(m->context(), &n) == 0) total += n;
+  for (MatcherBatch* m : r->batches) if (m->context() && visocu_launch_count(m->context(), &n) == 0) total += n;
   for (MonoAccess* v : r->monos) if (v->getMatcher()->context() && visocu_launch_count(v->getMatcher()->context(), &n) == 0) total += n;
   return total;
 }

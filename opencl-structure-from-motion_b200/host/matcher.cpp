@@ -41,7 +41,7 @@ static_assert(sizeof(Matcher::p_match) == sizeof(visocu_pmatch), "p_match layout
 static_assert(sizeof(Matcher::range) == sizeof(visocu_range), "range layout");
 static_assert(sizeof(Matcher::parameters) == sizeof(visocu_params), "parameters layout");
 
-Matcher::Matcher(parameters param) : param(param), ctx(0), cfg_w(0), cfg_h(0), have_I1p(false), have_I1c(false) {
+Matcher::Matcher(parameters param) : param(param), ctx(0), owns_ctx(true), slot_base(0), cfg_w(0), cfg_h(0), have_I1p(false), have_I1c(false) {
   margin = 5 + 1;
   if (param.half_resolution) this->param.match_radius /= 2;     // matcher.cpp:59-60
   device = visob::current_device();
@@ -56,10 +56,22 @@ Matcher::Matcher(parameters param) : param(param), ctx(0), cfg_w(0), cfg_h(0), h
 void Matcher::seedShuffle(unsigned seed) { srandom_r(seed, &rnd_data); }
 
 Matcher::~Matcher() {
-  if (ctx) visocu_destroy(ctx);
+  if (ctx && owns_ctx) visocu_destroy(ctx);
+}
+
+void Matcher::useSharedContext(visocu_ctx* shared, int32_t first_frame, int32_t w, int32_t h) {
+  if (ctx && owns_ctx) visocu_destroy(ctx);
+  ctx = shared; owns_ctx = false; slot_base = first_frame; cfg_w = w; cfg_h = h;
+  for (int k = 0; k < 4; k++) slot[k] = -1;
+  for (int k = 0; k < 8; k++) n_feat[k] = 0;
 }
 
 bool Matcher::ensureContext(int32_t w, int32_t h) {
+  if (!owns_ctx) {
+    if (w == cfg_w && h == cfg_h) return true;
+    std::cerr << "ERROR: Image dimension mismatch!" << std::endl;      // a shared context is configured once for one image size
+    return false;
+  }
   if (!ctx) {
     if (visocu_create(device, &ctx) != VISOCU_OK) {
       std::cerr << "ERROR: " << visocu_last_error(0) << std::endl;
@@ -86,13 +98,25 @@ void Matcher::pushBack(uint8_t* I1, uint8_t* I2, uint32_t* dims, const bool repl
 void Matcher::pushBackDevice(const uint8_t* d_I1, const uint8_t* d_I2, uint32_t* dims, const bool replace) { push(d_I1, d_I2, dims, replace, true); }
 
 void Matcher::push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool replace, bool on_device) {
+  visob::StageTimer timer(0);
+  int32_t frames[2];
+  if (!pushPrepare(I1, I2, dims, replace, frames)) return;
+  const uint8_t* imgs[2] = {I1, I2};
+  int32_t ns[2] = {0, 0}, nd[2] = {0, 0};
+  const int nimg = I2 ? 2 : 1;
+  const bool ok = visocu_push_frames(ctx, nimg, frames, imgs, (int32_t)dims[2], on_device ? 1 : 0, ns, nd) == VISOCU_OK;
+  if (!ok) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+  pushFinish(ok, I2 != 0, ns, nd);
+}
+
+// ring-buffer bookkeeping of pushBack (matcher.cpp:108-160); frames[] receives the device frames of the new images
+bool Matcher::pushPrepare(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool replace, int32_t* frames) {
   const int32_t width = dims[0], height = dims[1], bpl = dims[2];
   if (width <= 0 || height <= 0 || bpl < width || I1 == 0) {
     std::cerr << "ERROR: Image dimension mismatch!" << std::endl;
-    return;
+    return false;
   }
-  visob::StageTimer timer(0);
-  if (!ensureContext(width, height)) return;
+  if (!ensureContext(width, height)) return false;
   if (!replace) {
     // current -> previous: the device frames swap roles, nothing is copied
     std::swap(slot[0], slot[2]);
@@ -105,24 +129,24 @@ void Matcher::push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool re
   dims_c[0] = width; dims_c[1] = height; dims_c[2] = width + 15 - (width - 1) % 16;
   // pick device frames for the new current images: reuse the ones just vacated (or never used)
   bool used[4] = {false, false, false, false};
-  if (slot[0] >= 0) used[slot[0]] = true;
-  if (slot[1] >= 0) used[slot[1]] = true;
+  if (slot[0] >= 0) used[slot[0] - slot_base] = true;
+  if (slot[1] >= 0) used[slot[1] - slot_base] = true;
   int32_t fresh[2], nf = 0;
-  for (int k = 0; k < 4 && nf < 2; k++) if (!used[k]) fresh[nf++] = k;
+  for (int k = 0; k < 4 && nf < 2; k++) if (!used[k]) fresh[nf++] = slot_base + k;
   slot[2] = fresh[0];
   slot[3] = I2 ? fresh[1] : -1;
-  int32_t frames[2] = {slot[2], slot[3]};
-  const uint8_t* imgs[2] = {I1, I2};
-  int32_t ns[2] = {0, 0}, nd[2] = {0, 0};
-  const int nimg = I2 ? 2 : 1;
-  if (visocu_push_frames(ctx, nimg, frames, imgs, bpl, on_device ? 1 : 0, ns, nd) != VISOCU_OK) {
-    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+  frames[0] = slot[2]; frames[1] = slot[3];
+  return true;
+}
+
+void Matcher::pushFinish(bool ok, bool stereo, const int32_t* ns, const int32_t* nd) {
+  if (!ok) {
     slot[2] = slot[3] = -1;
     n_feat[2] = n_feat[3] = n_feat[6] = n_feat[7] = 0;
     return;
   }
   n_feat[2] = ns[0]; n_feat[6] = nd[0];
-  n_feat[3] = I2 ? ns[1] : 0; n_feat[7] = I2 ? nd[1] : 0;
+  n_feat[3] = stereo ? ns[1] : 0; n_feat[7] = stereo ? nd[1] : 0;
   // getGain needs the two left images on the host (matcher.cpp:286-324); they are fetched from the device on demand
   have_I1c = false;
 }
@@ -140,8 +164,7 @@ bool Matcher::fetchImage(int which, vector<uint8_t>& out) {
 bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_prior, int refine) {
   visob::StageTimer timer(1 + pass);
   visocu_quad q = {slot[0], slot[1], slot[2], slot[3]};
-  const int32_t base = pass == 0 ? 0 : 4;
-  const int32_t nq = method == 2 ? n_feat[base + 0] : n_feat[base + 2];
+  const int32_t nq = queryCount(pass, method);
   out.resize((size_t)nq + 1);
   visocu_pmatch* optr = reinterpret_cast<visocu_pmatch*>(out.data());
   const visocu_range* rptr = reinterpret_cast<const visocu_range*>(ranges.data());
@@ -157,34 +180,51 @@ bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_
 }
 
 void Matcher::matchFeatures(int32_t method, Matrix* Tr_delta) {
-  // sanity checks of matcher.cpp:190-212: silently keep the old matches if a needed set is empty
+  (void)Tr_delta;   // the motion-predicted search of matcher.cpp:1114-1134 is not implemented: plain search is used
+  if (!matchBegin(method)) return;
+  const int refine = refineMode();
+  if (param.multi_stage) {
+    if (!matching(0, p_matched_1, method, false, 0)) return;
+    matchAfterPass1(method);
+    if (!matching(1, p_matched_2, method, true, refine)) return;
+  } else {
+    if (!matching(1, p_matched_2, method, false, refine)) return;
+  }
+  matchAfterPass2(method);
+}
+
+// sanity checks of matcher.cpp:190-212: silently keep the old matches if a needed set is empty
+bool Matcher::matchBegin(int32_t method) {
   const int32_t* n1 = n_feat;       // sparse: 1p 2p 1c 2c
   const int32_t* n2 = n_feat + 4;   // dense
   if (method == 0) {
-    if (n2[0] == 0 || n2[2] == 0) return;
-    if (param.multi_stage && (n1[0] == 0 || n1[2] == 0)) return;
+    if (n2[0] == 0 || n2[2] == 0) return false;
+    if (param.multi_stage && (n1[0] == 0 || n1[2] == 0)) return false;
   } else if (method == 1) {
-    if (n2[2] == 0 || n2[3] == 0) return;
-    if (param.multi_stage && (n1[2] == 0 || n1[3] == 0)) return;
+    if (n2[2] == 0 || n2[3] == 0) return false;
+    if (param.multi_stage && (n1[2] == 0 || n1[3] == 0)) return false;
   } else {
-    if (n2[0] == 0 || n2[1] == 0 || n2[2] == 0 || n2[3] == 0) return;
-    if (param.multi_stage && (n1[0] == 0 || n1[1] == 0 || n1[2] == 0 || n1[3] == 0)) return;
+    if (n2[0] == 0 || n2[1] == 0 || n2[2] == 0 || n2[3] == 0) return false;
+    if (param.multi_stage && (n1[0] == 0 || n1[1] == 0 || n1[2] == 0 || n1[3] == 0)) return false;
   }
-  (void)Tr_delta;   // the motion-predicted search of matcher.cpp:1114-1134 is not implemented: plain search is used
   p_matched_1.clear();
   p_matched_2.clear();
-  const int refine = param.refinement <= 0 ? 0 : (param.refinement == 1 ? 1 : 2);
-  if (param.multi_stage) {
-    if (!matching(0, p_matched_1, method, false, 0)) return;
-    removeOutliers(p_matched_1, method);
-    computePriorStatistics(p_matched_1, method);
-    if (!matching(1, p_matched_2, method, true, refine)) return;
-    removeOutliers(p_matched_2, method);
-  } else {
-    if (!matching(1, p_matched_2, method, false, refine)) return;
-    removeOutliers(p_matched_2, method);
-  }
+  return true;
 }
+
+int Matcher::refineMode() const { return param.refinement <= 0 ? 0 : (param.refinement == 1 ? 1 : 2); }
+
+int32_t Matcher::queryCount(int pass, int32_t method) const {
+  const int32_t base = pass == 0 ? 0 : 4;
+  return method == 2 ? n_feat[base + 0] : n_feat[base + 2];
+}
+
+// host stages between the two matching passes (matcher.cpp:223-226) and after the second (matcher.cpp:232)
+void Matcher::matchAfterPass1(int32_t method) {
+  removeOutliers(p_matched_1, method);
+  computePriorStatistics(p_matched_1, method);
+}
+void Matcher::matchAfterPass2(int32_t method) { removeOutliers(p_matched_2, method); }
 
 void Matcher::bucketFeatures(int32_t max_features, float bucket_width, float bucket_height) {
   float u_max = 0, v_max = 0;
@@ -333,4 +373,112 @@ void Matcher::removeOutliers(vector<p_match>& p_matched, int32_t method) {
   for (int32_t i = 0; i < n; i++)
     if (support[i] >= 4) p_matched[k++] = p_matched[i];
   p_matched.resize(k);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MatcherBatch: S independent sequences on ONE context.  Every GPU stage is issued once for all sequences (the C-ABI is
+// batched: one launch per kernel covers all S frames / pairs), the host stages run per sequence in between.  The result
+// of every sequence is identical to what a stand-alone Matcher produces.
+MatcherBatch::MatcherBatch(Matcher::parameters param, int32_t n_sequences) : ctx(0), width(0), height(0) {
+  for (int32_t s = 0; s < n_sequences; s++) seq.push_back(new Matcher(param));
+  device = visob::current_device();
+}
+
+MatcherBatch::~MatcherBatch() {
+  for (Matcher* m : seq) delete m;
+  if (ctx) visocu_destroy(ctx);
+}
+
+bool MatcherBatch::ensure(int32_t w, int32_t h) {
+  if (ctx && w == width && h == height) return true;
+  if (!ctx && visocu_create(device, &ctx) != VISOCU_OK) {
+    std::cerr << "ERROR: " << visocu_last_error(0) << std::endl;
+    ctx = 0;
+    return false;
+  }
+  visocu_params vp;
+  memcpy(&vp, &seq[0]->param, sizeof vp);
+  if (visocu_configure(ctx, &vp, w, h, 4 * (int32_t)seq.size()) != VISOCU_OK) {
+    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+    return false;
+  }
+  width = w; height = h;
+  for (size_t s = 0; s < seq.size(); s++) seq[s]->useSharedContext(ctx, 4 * (int32_t)s, w, h);
+  return true;
+}
+
+void MatcherBatch::pushBack(const uint8_t* const* I1, const uint8_t* const* I2, uint32_t* dims, bool replace, bool on_device) {
+  visob::StageTimer timer(0);
+  if ((int32_t)dims[0] <= 0 || (int32_t)dims[1] <= 0 || dims[2] < dims[0]) {
+    std::cerr << "ERROR: Image dimension mismatch!" << std::endl;
+    return;
+  }
+  if (!ensure((int32_t)dims[0], (int32_t)dims[1])) return;
+  const size_t S = seq.size();
+  vector<int32_t> frames, owner;
+  vector<const uint8_t*> imgs;
+  for (size_t s = 0; s < S; s++) {
+    int32_t f[2];
+    const uint8_t* i2 = I2 ? I2[s] : 0;
+    if (!seq[s]->pushPrepare(I1[s], i2, dims, replace, f)) continue;
+    frames.push_back(f[0]); imgs.push_back(I1[s]); owner.push_back((int32_t)s);
+    if (i2) { frames.push_back(f[1]); imgs.push_back(i2); owner.push_back((int32_t)s); }
+  }
+  if (frames.empty()) return;
+  vector<int32_t> ns(frames.size()), nd(frames.size());
+  const bool ok = visocu_push_frames(ctx, (int32_t)frames.size(), frames.data(), imgs.data(), (int32_t)dims[2], on_device ? 1 : 0,
+                                     ns.data(), nd.data()) == VISOCU_OK;
+  if (!ok) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+  for (size_t k = 0; k < frames.size();) {
+    const int32_t s = owner[k];
+    const bool stereo = k + 1 < frames.size() && owner[k + 1] == s;
+    seq[s]->pushFinish(ok, stereo, &ns[k], &nd[k]);
+    k += stereo ? 2 : 1;
+  }
+}
+
+bool MatcherBatch::matchPass(const vector<int32_t>& active, int pass, int32_t method, bool use_prior, int refine) {
+  visob::StageTimer timer(1 + pass);
+  const size_t n = active.size();
+  vector<visocu_quad> quads(n);
+  vector<visocu_pmatch*> outs(n);
+  vector<const visocu_range*> rptr(n);
+  vector<int32_t> cap(n), cnt(n);
+  for (size_t k = 0; k < n; k++) {
+    Matcher* m = seq[active[k]];
+    vector<Matcher::p_match>& out = pass == 0 ? m->p_matched_1 : m->p_matched_2;
+    const int32_t nq = m->queryCount(pass, method);
+    out.resize((size_t)nq + 1);
+    quads[k] = visocu_quad{m->slot[0], m->slot[1], m->slot[2], m->slot[3]};
+    outs[k] = reinterpret_cast<visocu_pmatch*>(out.data());
+    rptr[k] = reinterpret_cast<const visocu_range*>(m->ranges.data());
+    cap[k] = nq + 1;
+  }
+  const int rc = visocu_match(ctx, (int32_t)n, quads.data(), method, pass, use_prior ? 1 : 0, use_prior ? rptr.data() : 0, refine,
+                              outs.data(), cap.data(), cnt.data());
+  if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+  for (size_t k = 0; k < n; k++) {
+    Matcher* m = seq[active[k]];
+    (pass == 0 ? m->p_matched_1 : m->p_matched_2).resize(rc == VISOCU_OK ? cnt[k] : 0);
+  }
+  return rc == VISOCU_OK;
+}
+
+void MatcherBatch::matchFeatures(int32_t method) {
+  if (!ctx) return;
+  vector<int32_t> active;
+  for (size_t s = 0; s < seq.size(); s++)
+    if (seq[s]->matchBegin(method)) active.push_back((int32_t)s);
+  if (active.empty()) return;
+  const Matcher::parameters& p = seq[0]->param;
+  const int refine = seq[0]->refineMode();
+  if (p.multi_stage) {
+    if (!matchPass(active, 0, method, false, 0)) return;
+    for (int32_t s : active) seq[s]->matchAfterPass1(method);
+    if (!matchPass(active, 1, method, true, refine)) return;
+  } else {
+    if (!matchPass(active, 1, method, false, refine)) return;
+  }
+  for (int32_t s : active) seq[s]->matchAfterPass2(method);
 }

@@ -84,7 +84,17 @@ public:
   const std::vector<range>& priorRanges() const { return ranges; }
 
 private:
+  friend class MatcherBatch;
   void push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool replace, bool on_device);
+  // stage functions shared by the stand-alone path and MatcherBatch
+  void useSharedContext(visocu_ctx* shared, int32_t first_frame, int32_t w, int32_t h);
+  bool pushPrepare(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool replace, int32_t* frames);
+  void pushFinish(bool ok, bool stereo, const int32_t* ns, const int32_t* nd);
+  bool matchBegin(int32_t method);
+  void matchAfterPass1(int32_t method);
+  void matchAfterPass2(int32_t method);
+  int refineMode() const;
+  int32_t queryCount(int pass, int32_t method) const;
   bool ensureContext(int32_t w, int32_t h);
   bool fetchImage(int which, std::vector<uint8_t>& out);
   bool matching(int pass, std::vector<p_match>& out, int32_t method, bool use_prior, int refine);
@@ -92,6 +102,8 @@ private:
   parameters param;
   int32_t margin;
   visocu_ctx* ctx;
+  bool owns_ctx;
+  int32_t slot_base;                     // first device frame of this matcher inside its context
   int device;
   int32_t cfg_w, cfg_h;
   // ring buffer: frame slots of the context.  slot[0] = previous left, [1] = previous right, [2] = current left,
@@ -105,6 +117,29 @@ private:
   std::vector<range> ranges;
   struct random_data rnd_data;
   char rnd_state[128];
+};
+
+// Extension (not in the reference): S independent sequences that share one context, so that every GPU stage is ONE
+// batched launch for all of them.  sequence(i) is an ordinary Matcher (bucketFeatures, getMatches, getGain ...); do
+// not call its pushBack / matchFeatures directly.
+class MatcherBatch {
+public:
+  MatcherBatch(Matcher::parameters param, int32_t n_sequences);
+  ~MatcherBatch();
+  // one image (and optionally one right image) per sequence; dims as for Matcher::pushBack
+  void pushBack(const uint8_t* const* I1, const uint8_t* const* I2, uint32_t* dims, bool replace, bool on_device = false);
+  void matchFeatures(int32_t method);
+  int32_t size() const { return (int32_t)seq.size(); }
+  Matcher& sequence(int32_t i) { return *seq[i]; }
+  visocu_ctx* context() { return ctx; }
+
+private:
+  bool ensure(int32_t w, int32_t h);
+  bool matchPass(const std::vector<int32_t>& active, int pass, int32_t method, bool use_prior, int refine);
+  std::vector<Matcher*> seq;
+  visocu_ctx* ctx;
+  int device;
+  int32_t width, height;
 };
 
 #endif

@@ -179,3 +179,30 @@ def test_matcher_subpixel_refinement(ref):
         assert np.array_equal(got[f], want[f])
     for f in ('u1p', 'v1p', 'u2p', 'v2p', 'u2c', 'v2c'):
         assert np.abs(got[f] - want[f]).max() < 1e-4
+
+
+def test_sequence_runner_equals_single_matchers(ref):
+    """Sharded runner (MatcherBatch per worker: one batched launch per GPU stage for all of a worker's sequences) gives,
+    for every sequence and frame, exactly the list a stand-alone Matcher / the reference gives."""
+    import ctypes as C
+    S, T = 5, 3
+    seqs = [synth.blob_sequence(T, 500, 260, seed=60 + s) for s in range(S)]
+    mp = H.MonoParams(match=V.Params())
+    for threads in (1, 2):
+        runner = H.Runner(0, S, threads, 0, 0, mp)
+        dims = np.array([500, 260, 500], np.int32)
+        for k in range(T):
+            imgs = [np.ascontiguousarray(seqs[s][k]) for s in range(S)]
+            secs, nm, ok = runner.step([i.ctypes.data for i in imgs], dims)
+            if k == 0:
+                assert nm.tolist() == [0] * S
+        got = [runner.matches(s) for s in range(S)]
+        runner.close()
+        for s in range(S):
+            rm = ref.matcher(pyref.MatcherParams())
+            for k in range(T):
+                rm.push(seqs[s][k])
+                if k:
+                    rm.match_features(0)
+            want = rm.matches(2)
+            assert len(want) > 300 and got[s].tobytes() == want.tobytes(), (threads, s)
