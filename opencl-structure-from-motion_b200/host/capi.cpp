@@ -169,21 +169,18 @@ struct Runner {
 void runner_advance(Runner* r, int tid, const uint8_t* const* imgs, const uint8_t* const* imgs2, const int32_t* dims, int on_device,
                     int bucket, int32_t* n_matches_out, int32_t* ok_out) {
   uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
-  if (r->mode == 1) {
-    for (int s = tid; s < r->S; s += r->threads) {
+  MatcherBatch* b = r->batches[tid];
+  std::vector<const uint8_t*> i1, i2;
+  for (int s = tid; s < r->S; s += r->threads) { i1.push_back(imgs[s]); if (imgs2) i2.push_back(imgs2[s]); }
+  b->pushBack(i1.data(), imgs2 ? i2.data() : 0, d, false, on_device != 0);
+  b->matchFeatures(r->method);
+  int k = 0;
+  for (int s = tid; s < r->S; s += r->threads, k++) {
+    if (r->mode == 1) {
       MonoAccess* vo = r->monos[s];
-      const bool ok = on_device ? vo->processDevice(imgs[s], d, false) : vo->process(const_cast<uint8_t*>(imgs[s]), d, false);
-      r->last_ok[s] = ok ? 1 : 0;
+      r->last_ok[s] = vo->processMatched() ? 1 : 0;
       r->last_matches[s] = vo->getNumberOfMatches();
-    }
-  } else {
-    MatcherBatch* b = r->batches[tid];
-    std::vector<const uint8_t*> i1, i2;
-    for (int s = tid; s < r->S; s += r->threads) { i1.push_back(imgs[s]); if (imgs2) i2.push_back(imgs2[s]); }
-    b->pushBack(i1.data(), imgs2 ? i2.data() : 0, d, false, on_device != 0);
-    b->matchFeatures(r->method);
-    int k = 0;
-    for (int s = tid; s < r->S; s += r->threads, k++) {
+    } else {
       Matcher& m = b->sequence(k);
       if (bucket) m.bucketFeatures(r->bucket_max, r->bucket_w, r->bucket_h);
       r->last_matches[s] = (int32_t)m.matches(2).size();
@@ -209,13 +206,17 @@ VISOB_API void* visob_runner_create(int device, int n_sequences, int threads, in
   r->device = device; r->S = n_sequences; r->threads = std::max(1, std::min(threads, n_sequences)); r->mode = mode; r->method = method;
   r->bucket_max = p->bucket_max_features; r->bucket_w = (float)p->bucket_width; r->bucket_h = (float)p->bucket_height;
   visob::set_device(device);
+  for (int t = 0; t < r->threads; t++) {
+    int n = 0;
+    for (int s = t; s < n_sequences; s += r->threads) n++;
+    r->batches.push_back(new MatcherBatch(p->match, n));
+  }
   if (mode == 1) {
-    for (int s = 0; s < n_sequences; s++) r->monos.push_back(new MonoAccess(to_cpp(p)));
-  } else {
-    for (int t = 0; t < r->threads; t++) {
-      int n = 0;
-      for (int s = t; s < n_sequences; s += r->threads) n++;
-      r->batches.push_back(new MatcherBatch(p->match, n));
+    // one odometry object per sequence, running on its sequence of the worker's batch
+    for (int s = 0; s < n_sequences; s++) {
+      MonoAccess* vo = new MonoAccess(to_cpp(p));
+      vo->adoptMatcher(&r->batches[s % r->threads]->sequence(s / r->threads));
+      r->monos.push_back(vo);
     }
   }
   r->last_matches.assign(n_sequences, 0);
@@ -224,8 +225,8 @@ VISOB_API void* visob_runner_create(int device, int n_sequences, int threads, in
 }
 VISOB_API void visob_runner_destroy(void* h) {
   Runner* r = (Runner*)h;
-  for (MatcherBatch* b : r->batches) delete b;
   for (MonoAccess* m : r->monos) delete m;
+  for (MatcherBatch* b : r->batches) delete b;
   delete r;
 }
 // imgs / imgs2: S pointers (imgs2 may be null for mono / flow).  on_device: pointers are device memory.
@@ -270,13 +271,11 @@ VISOB_API void visob_runner_transfer_bytes(void* h, uint64_t* h2d, uint64_t* d2h
   Runner* r = (Runner*)h;
   uint64_t a = 0, b = 0, x = 0, y = 0;
   for (MatcherBatch* m : r->batches) if (m->context() && visocu_transfer_bytes(m->context(), &x, &y) == 0) { a += x; b += y; }
-  for (MonoAccess* v : r->monos) if (v->getMatcher()->context() && visocu_transfer_bytes(v->getMatcher()->context(), &x, &y) == 0) { a += x; b += y; }
   *h2d = a; *d2h = b;
 }
 VISOB_API uint64_t visob_runner_launches(void* h) {
   Runner* r = (Runner*)h;
   uint64_t total = 0, n = 0;
   for (MatcherBatch* m : r->batches) if (m->context() && visocu_launch_count(m->context(), &n) == 0) total += n;
-  for (MonoAccess* v : r->monos) if (v->getMatcher()->context() && visocu_launch_count(v->getMatcher()->context(), &n) == 0) total += n;
   return total;
 }

@@ -7,13 +7,21 @@
 VisualOdometry::VisualOdometry(parameters param) : sample_generator(71), param(param) {
   J = 0; p_observe = 0; p_predict = 0;
   matcher = new Matcher(param.match);
+  owns_matcher = true;
   Tr_delta = Matrix::eye(4);
   Tr_valid = false;
   srand(0);                  // as the reference does (viso.cpp:35)
   matcher->seedShuffle(0);   // ... and the matcher's own copy of that generator, which bucketFeatures draws from
 }
 
-VisualOdometry::~VisualOdometry() { delete matcher; }
+VisualOdometry::~VisualOdometry() { if (owns_matcher) delete matcher; }
+
+void VisualOdometry::adoptMatcher(Matcher* external) {
+  if (owns_matcher) delete matcher;
+  matcher = external;
+  owns_matcher = false;
+  matcher->seedShuffle(0);     // same state the own matcher had (viso.cpp:35)
+}
 
 bool VisualOdometry::updateMotion() {
   std::vector<double> tr = estimateMotion(p_matched);

@@ -48,6 +48,8 @@ public:
   // extension: the matches fed to the last motion estimate (after bucketing)
   const std::vector<Matcher::p_match>& usedMatches() const { return p_matched; }
   Matcher* getMatcher() { return matcher; }
+  // extension: run on a matcher owned by somebody else (a MatcherBatch sequence); the own one is released
+  void adoptMatcher(Matcher* external);
 
 protected:
   bool updateMotion();
@@ -61,6 +63,7 @@ protected:
   Matrix Tr_delta;
   bool Tr_valid;
   Matcher* matcher;
+  bool owns_matcher;
   std::vector<int32_t> inliers;
   double* J;
   double* p_observe;

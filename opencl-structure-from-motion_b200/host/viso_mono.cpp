@@ -50,6 +50,12 @@ bool VisualOdometryMono::processDevice(const uint8_t* d_I, uint32_t* dims, bool 
   return updateMotion();
 }
 
+bool VisualOdometryMono::processMatched() {
+  matcher->bucketFeatures(param.bucket.max_features, param.bucket.bucket_width, param.bucket.bucket_height);
+  p_matched = matcher->getMatches();
+  return updateMotion();
+}
+
 // GPU RANSAC.  The host only draws the sample table with the reference's generator, in the reference's order
 // (one getRandomSample per iteration), so a run is comparable with the reference hypothesis by hypothesis.
 Matrix VisualOdometryMono::ransacEstimateF(const vector<Matcher::p_match>& p_matched) {

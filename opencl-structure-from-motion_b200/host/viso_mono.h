@@ -26,6 +26,8 @@ public:
 
   // extensions for tests / the batch runner
   bool processDevice(const uint8_t* d_I, uint32_t* dims, bool replace = false);
+  // the second half of process() for callers that pushed and matched through a MatcherBatch: bucketing + motion
+  bool processMatched();
   const Matrix& lastF() const { return F_last; }
   const std::vector<int>& lastSamples() const { return samples_last; }
 

@@ -206,3 +206,27 @@ def test_sequence_runner_equals_single_matchers(ref):
                     rm.match_features(0)
             want = rm.matches(2)
             assert len(want) > 300 and got[s].tobytes() == want.tobytes(), (threads, s)
+
+
+def test_mono_runner_equals_single_objects():
+    """Mono odometry through the sharded runner (shared MatcherBatch + per-sequence odometry objects) equals stand-alone
+    VisualOdometryMono objects: same matches, same inliers, same pose."""
+    S, T = 3, 3
+    seqs = [synth.corridor_sequence(T, seed=1234 + s) for s in range(S)]
+    _, hp = _mono_params(None, 2)
+    runner = H.Runner(0, S, 2, 1, 0, hp)
+    dims = np.array([1241, 376, 1241], np.int32)
+    poses = []
+    for k in range(T):
+        imgs = [np.ascontiguousarray(seqs[s][k]) for s in range(S)]
+        secs, nm, ok = runner.step([i.ctypes.data for i in imgs], dims)
+        assert k == 0 or ok.tolist() == [1] * S
+    got_m = [runner.matches(s) for s in range(S)]
+    got_T = [runner.motion(s) for s in range(S)]
+    runner.close()
+    for s in range(S):
+        hv = H.Mono(hp)
+        for k in range(T):
+            hv.process(seqs[s][k])
+        assert hv.matches().tobytes() == got_m[s].tobytes()
+        assert np.abs(hv.motion() - got_T[s]).max() < 1e-9
