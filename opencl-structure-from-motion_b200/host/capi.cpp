@@ -159,6 +159,7 @@ namespace {
 struct Runner {
   int device, S, threads, mode, method;      // mode 0 = Matcher only, 1 = VisualOdometryMono::process
   int bucket_max; float bucket_w, bucket_h;
+  MonoParamsC params;
   std::vector<MatcherBatch*> batches;        // one per worker (mode 0)
   std::vector<MonoAccess*> monos;            // one per sequence (mode 1)
   std::vector<int32_t> last_matches, last_ok;
@@ -174,13 +175,34 @@ void runner_advance(Runner* r, int tid, const uint8_t* const* imgs, const uint8_
   for (int s = tid; s < r->S; s += r->threads) { i1.push_back(imgs[s]); if (imgs2) i2.push_back(imgs2[s]); }
   b->pushBack(i1.data(), imgs2 ? i2.data() : 0, d, false, on_device != 0);
   b->matchFeatures(r->method);
-  int k = 0;
-  for (int s = tid; s < r->S; s += r->threads, k++) {
-    if (r->mode == 1) {
-      MonoAccess* vo = r->monos[s];
-      r->last_ok[s] = vo->processMatched() ? 1 : 0;
-      r->last_matches[s] = vo->getNumberOfMatches();
-    } else {
+  if (r->mode == 1) {
+    // bucketing + normalisation + sample tables per sequence, then ONE RANSAC call for all of this worker's sequences
+    std::vector<int> ids;
+    std::vector<const float*> uv;
+    std::vector<int32_t> N;
+    std::vector<const int32_t*> smp;
+    for (int s = tid; s < r->S; s += r->threads) {
+      const float* u = 0; int32_t n = 0; const int32_t* sp = 0;
+      r->last_ok[s] = 0;
+      if (r->monos[s]->batchPrepare(&u, &n, &sp)) { ids.push_back(s); uv.push_back(u); N.push_back(n); smp.push_back(sp); }
+      r->last_matches[s] = r->monos[s]->getNumberOfMatches();
+    }
+    if (!ids.empty()) {
+      const int nj = (int)ids.size();
+      std::vector<double> F(9 * (size_t)nj);
+      std::vector<int32_t> ninl(nj), best(nj);
+      std::vector<std::vector<uint8_t> > masks(nj);
+      std::vector<uint8_t*> mptr(nj);
+      for (int j = 0; j < nj; j++) { masks[j].resize(N[j]); mptr[j] = masks[j].data(); }
+      visocu_ctx* ctx = b->context();
+      const VisualOdometryMono::parameters mp = to_cpp(&r->params);
+      if (visocu_ransac_F(ctx, nj, uv.data(), N.data(), smp.data(), mp.ransac_iters, mp.inlier_threshold, F.data(), mptr.data(),
+                          ninl.data(), best.data(), 0, 0) == VISOCU_OK)
+        for (int j = 0; j < nj; j++) r->last_ok[ids[j]] = r->monos[ids[j]]->batchFinish(&F[9 * (size_t)j], mptr[j]) ? 1 : 0;
+    }
+  } else {
+    int k = 0;
+    for (int s = tid; s < r->S; s += r->threads, k++) {
       Matcher& m = b->sequence(k);
       if (bucket) m.bucketFeatures(r->bucket_max, r->bucket_w, r->bucket_h);
       r->last_matches[s] = (int32_t)m.matches(2).size();
@@ -204,6 +226,7 @@ template <class F> void run_workers(int threads, F work) {
 VISOB_API void* visob_runner_create(int device, int n_sequences, int threads, int mode, int method, const MonoParamsC* p) {
   Runner* r = new Runner();
   r->device = device; r->S = n_sequences; r->threads = std::max(1, std::min(threads, n_sequences)); r->mode = mode; r->method = method;
+  r->params = *p;
   r->bucket_max = p->bucket_max_features; r->bucket_w = (float)p->bucket_width; r->bucket_h = (float)p->bucket_height;
   visob::set_device(device);
   for (int t = 0; t < r->threads; t++) {

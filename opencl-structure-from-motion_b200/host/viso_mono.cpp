@@ -58,24 +58,33 @@ bool VisualOdometryMono::processMatched() {
 
 // GPU RANSAC.  The host only draws the sample table with the reference's generator, in the reference's order
 // (one getRandomSample per iteration), so a run is comparable with the reference hypothesis by hypothesis.
-Matrix VisualOdometryMono::ransacEstimateF(const vector<Matcher::p_match>& p_matched) {
-  MonoTimer timer(6);
-  inliers.clear();
-  const int32_t N = (int32_t)p_matched.size(), iters = param.ransac_iters;
+void VisualOdometryMono::drawSamples(int32_t N) {
+  const int32_t iters = param.ransac_iters;
   samples_last.resize((size_t)iters * 8);
   for (int32_t k = 0; k < iters; k++) {
     vector<int> s = getRandomSample(N, 8);
     std::copy(s.begin(), s.end(), samples_last.begin() + (size_t)k * 8);
   }
-  vector<float> uv((size_t)N * 4);
-  for (int32_t i = 0; i < N; i++) {
-    uv[4 * i + 0] = p_matched[i].u1p; uv[4 * i + 1] = p_matched[i].v1p;
-    uv[4 * i + 2] = p_matched[i].u1c; uv[4 * i + 3] = p_matched[i].v1c;
+}
+
+void VisualOdometryMono::packNormalized(const vector<Matcher::p_match>& pm) {
+  uv_last.resize(pm.size() * 4);
+  for (size_t i = 0; i < pm.size(); i++) {
+    uv_last[4 * i + 0] = pm[i].u1p; uv_last[4 * i + 1] = pm[i].v1p;
+    uv_last[4 * i + 2] = pm[i].u1c; uv_last[4 * i + 3] = pm[i].v1c;
   }
+}
+
+Matrix VisualOdometryMono::ransacEstimateF(const vector<Matcher::p_match>& p_matched) {
+  MonoTimer timer(6);
+  inliers.clear();
+  const int32_t N = (int32_t)p_matched.size(), iters = param.ransac_iters;
+  drawSamples(N);
+  packNormalized(p_matched);
   vector<uint8_t> mask(N);
   double F9[9];
   int32_t n_inl = 0, best = -1;
-  const float* uvp = uv.data();
+  const float* uvp = uv_last.data();
   const int32_t* sp = samples_last.data();
   uint8_t* mp = mask.data();
   visocu_ctx* ctx = matcher->context();
@@ -87,6 +96,36 @@ Matrix VisualOdometryMono::ransacEstimateF(const vector<Matcher::p_match>& p_mat
     if (mask[i]) inliers.push_back(i);
   if (inliers.size() < 10) return Matrix();
   return Matrix(3, 3, F9);
+}
+
+// ---- batched variant used by the sequence runner: the RANSAC of several sequences is ONE visocu_ransac_F call
+bool VisualOdometryMono::batchPrepare(const float** uv, int32_t* N, const int32_t** samples) {
+  matcher->bucketFeatures(param.bucket.max_features, param.bucket.bucket_width, param.bucket.bucket_height);
+  p_matched = matcher->getMatches();
+  batch_ready = false;
+  if ((int32_t)p_matched.size() < 10) return false;
+  normalized_last = p_matched;
+  if (!normalizeFeaturePoints(normalized_last, Tp_last, Tc_last)) return false;
+  drawSamples((int32_t)normalized_last.size());
+  packNormalized(normalized_last);
+  *uv = uv_last.data(); *N = (int32_t)normalized_last.size(); *samples = samples_last.data();
+  batch_ready = true;
+  return true;
+}
+
+bool VisualOdometryMono::batchFinish(const double* F9, const uint8_t* mask) {
+  if (!batch_ready) return false;
+  inliers.clear();
+  for (size_t i = 0; i < normalized_last.size(); i++)
+    if (mask[i]) inliers.push_back((int32_t)i);
+  if (inliers.size() < 10) return false;
+  Matrix F(3, 3, F9);
+  F_last = F;
+  vector<double> tr = poseFromF(F, p_matched, Tp_last, Tc_last);
+  if (tr.size() != 6) return false;
+  Tr_delta = transformationVectorToMatrix(tr);
+  Tr_valid = true;
+  return true;
 }
 
 // GPU Gaussian vote (the reference's second accelerator hook, viso_mono.h:75 / viso_mono_cl.cpp:255-280)
@@ -109,8 +148,6 @@ vector<double> VisualOdometryMono::estimateMotion(vector<Matcher::p_match> p_mat
   MonoTimer timer(7);
   const int32_t N = (int32_t)p_matched.size();
   if (N < 10) return vector<double>();
-  double K_data[9] = {param.calib.f, 0, param.calib.cu, 0, param.calib.f, param.calib.cv, 0, 0, 1};
-  Matrix K(3, 3, K_data);
   Matrix Tp, Tc;
   vector<Matcher::p_match> normalized = p_matched;
   if (!normalizeFeaturePoints(normalized, Tp, Tc)) return vector<double>();
@@ -118,6 +155,13 @@ vector<double> VisualOdometryMono::estimateMotion(vector<Matcher::p_match> p_mat
   Matrix F = ransacEstimateF(normalized);
   if (F.val == 0) return vector<double>();
   F_last = F;
+  return poseFromF(F, p_matched, Tp, Tc);
+}
+
+// everything of estimateMotion after the RANSAC step (viso_mono.cpp:125-189)
+vector<double> VisualOdometryMono::poseFromF(Matrix F, vector<Matcher::p_match>& p_matched, Matrix& Tp, Matrix& Tc) {
+  double K_data[9] = {param.calib.f, 0, param.calib.cu, 0, param.calib.f, param.calib.cv, 0, 0, 1};
+  Matrix K(3, 3, K_data);
 
   // denormalise, essential matrix, rank 2 again
   F = ~Tc * F * Tp;

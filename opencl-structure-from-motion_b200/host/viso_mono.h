@@ -28,6 +28,10 @@ public:
   bool processDevice(const uint8_t* d_I, uint32_t* dims, bool replace = false);
   // the second half of process() for callers that pushed and matched through a MatcherBatch: bucketing + motion
   bool processMatched();
+  // batched RANSAC (sequence runner): batchPrepare buckets, normalises and draws the samples of this sequence;
+  // the caller runs visocu_ransac_F for several sequences at once and hands F and the inlier mask to batchFinish
+  bool batchPrepare(const float** uv, int32_t* N, const int32_t** samples);
+  bool batchFinish(const double* F9, const uint8_t* mask);
   const Matrix& lastF() const { return F_last; }
   const std::vector<int>& lastSamples() const { return samples_last; }
 
@@ -35,6 +39,9 @@ private:
   virtual Matrix ransacEstimateF(const std::vector<Matcher::p_match>& p_matched);
   virtual double findBestPlane(const Matrix& x_plane, double threshold, double weight);
   std::vector<double> estimateMotion(std::vector<Matcher::p_match> p_matched);
+  std::vector<double> poseFromF(Matrix F, std::vector<Matcher::p_match>& p_matched, Matrix& Tp, Matrix& Tc);
+  void drawSamples(int32_t N);
+  void packNormalized(const std::vector<Matcher::p_match>& pm);
   Matrix smallerThanMedian(Matrix& X, double& median);
   bool normalizeFeaturePoints(std::vector<Matcher::p_match>& p_matched, Matrix& Tp, Matrix& Tc);
   void EtoRt(Matrix& E, Matrix& K, std::vector<Matcher::p_match>& p_matched, Matrix& X, Matrix& R, Matrix& t);
@@ -44,5 +51,9 @@ protected:
   const parameters param;
   Matrix F_last;
   std::vector<int> samples_last;
+  std::vector<float> uv_last;
+  std::vector<Matcher::p_match> normalized_last;
+  Matrix Tp_last, Tc_last;
+  bool batch_ready = false;
 };
 #endif
