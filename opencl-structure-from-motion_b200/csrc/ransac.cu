@@ -8,7 +8,7 @@
 // counters, 3 launches per 16 hypotheses) which this replaces with FP64 kernels over all hypotheses at once.
 //
 // Design (not the reference's Numerical-Recipes svdcmp, matrix.cpp:586-814):
-//   k_hypotheses  one warp per hypothesis.  Lane c < 9 owns column c of the 8x9 constraint matrix and of V;
+//   k_hypotheses  three hypotheses per warp.  Lane 9h + c owns column c of the 8x9 constraint matrix of hypothesis h and of V;
 //                 a one-sided (Hestenes) Jacobi SVD orthogonalises the columns with a 9-round round-robin
 //                 pairing (partner of column i in round r is (r - i) mod 9), partner columns travel by
 //                 warp shuffle.  The column that ends with the smallest norm marks the null vector; the
@@ -51,35 +51,39 @@ __device__ __forceinline__ void constraint_row(const float4 m, double* a) {
   a[6] = (double)u1p; a[7] = (double)v1p; a[8] = 1.0;
 }
 
-// One-sided Jacobi on the columns of an R x 9 matrix held one column per lane (lanes >= 9 idle but shuffling).
-// On return nullv[0..8] on every lane = the right singular vector of the smallest singular value.
+// One-sided Jacobi on the columns of R x 9 matrices held one column per lane, THREE matrices per warp: lane = 9 h + c
+// owns column c of matrix h (lanes 27..31 idle but shuffling).  On return nullv[0..8] on every lane of group h = the right
+// singular vector of the smallest singular value of matrix h.
 template <int R>
 __device__ __forceinline__ void warp_jacobi_null(double (&g)[R], int lane, double (&nullv)[9]) {
+  const int c = lane % 9, h = lane / 9;
+  const bool col = lane < 27;
+  const int base = col ? 9 * h : 0;
   double v[9];
 #pragma unroll
-  for (int k = 0; k < 9; k++) v[k] = (k == lane) ? 1.0 : 0.0;
-  const bool col = lane < 9;
+  for (int k = 0; k < 9; k++) v[k] = (col && k == c) ? 1.0 : 0.0;
   // A column whose norm has fallen 14 orders of magnitude below the matrix norm is numerically null (the 8 x 9
   // constraint matrix always has one): its entries are rounding noise that no rotation can orthogonalise any further,
   // so it is left alone instead of being rotated until the sweep limit.
+  double own = 0;
+#pragma unroll
+  for (int k = 0; k < R; k++) own = fma(g[k], g[k], own);
   double total = 0;
 #pragma unroll
-  for (int k = 0; k < R; k++) total = fma(g[k], g[k], total);
-#pragma unroll
-  for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+  for (int k = 0; k < 9; k++) total += __shfl_sync(0xFFFFFFFFu, own, base + k);
   const double tiny = 1e-28 * total;
   for (int sweep = 0; sweep < JACOBI_MAX_SWEEPS; sweep++) {
     bool rotated = false;
     for (int r = 0; r < 9; r++) {
-      int j = r - lane; if (j < 0) j += 9;
-      const int src = col ? j : lane;
+      int j = r - c; if (j < 0) j += 9;
+      const int src = col ? base + j : lane;
       double og[R], ov[9];
 #pragma unroll
       for (int k = 0; k < R; k++) og[k] = __shfl_sync(0xFFFFFFFFu, g[k], src);
 #pragma unroll
       for (int k = 0; k < 9; k++) ov[k] = __shfl_sync(0xFFFFFFFFu, v[k], src);
-      if (col && j != lane) {
-        const bool first = lane < j;       // this lane holds the lower-numbered column of the pair
+      if (col && j != c) {
+        const bool first = c < j;          // this lane holds the lower-numbered column of the pair
         double alpha = 0, beta = 0, gamma = 0;
 #pragma unroll
         for (int k = 0; k < R; k++) {
@@ -89,13 +93,13 @@ __device__ __forceinline__ void warp_jacobi_null(double (&g)[R], int lane, doubl
         if (alpha > tiny && beta > tiny && fabs(gamma) > JACOBI_TOL * sqrt(alpha * beta)) {
           const double zeta = (beta - alpha) / (2.0 * gamma);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
           // a' = c a - s b ; b' = s a + c b
-          const double mo = first ? -s : s;
+          const double mo = first ? -sn : sn;
 #pragma unroll
-          for (int k = 0; k < R; k++) g[k] = c * g[k] + mo * og[k];
+          for (int k = 0; k < R; k++) g[k] = cs * g[k] + mo * og[k];
 #pragma unroll
-          for (int k = 0; k < 9; k++) v[k] = c * v[k] + mo * ov[k];
+          for (int k = 0; k < 9; k++) v[k] = cs * v[k] + mo * ov[k];
           rotated = true;
         }
       }
@@ -105,17 +109,15 @@ __device__ __forceinline__ void warp_jacobi_null(double (&g)[R], int lane, doubl
   double nrm = 0;
 #pragma unroll
   for (int k = 0; k < R; k++) nrm = fma(g[k], g[k], nrm);
-  if (!col) nrm = 1e300;
-  int best = lane;
-  double bn = nrm;
+  int best = 0;
+  double bn = __shfl_sync(0xFFFFFFFFu, nrm, base);
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    const double on = __shfl_xor_sync(0xFFFFFFFFu, bn, o);
-    const int ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
-    if (on < bn || (on == bn && ob < best)) { bn = on; best = ob; }
+  for (int k = 1; k < 9; k++) {
+    const double on = __shfl_sync(0xFFFFFFFFu, nrm, base + k);
+    if (on < bn) { bn = on; best = k; }
   }
 #pragma unroll
-  for (int k = 0; k < 9; k++) nullv[k] = __shfl_sync(0xFFFFFFFFu, v[k], best);
+  for (int k = 0; k < 9; k++) nullv[k] = __shfl_sync(0xFFFFFFFFu, v[k], base + best);
 }
 
 // rank-2 projection of a 3x3 matrix (row-major): F <- F - sigma3 u3 v3^T  (viso_mono.cpp:291-295)
@@ -165,29 +167,32 @@ __device__ __forceinline__ void rank2(double (&F)[9]) {
 
 __global__ void __launch_bounds__(128) k_hypotheses(const RansacJob* jobs, int iters) {
   const RansacJob& J = jobs[blockIdx.y];
-  const int hyp = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (hyp >= iters) return;
-  // lane c < 9 builds column c of the 8 x 9 constraint matrix
+  const int lane = threadIdx.x & 31, c = lane % 9, h = lane / 9;
+  const int hyp = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 3 + h;       // three hypotheses per warp
+  const bool live = lane < 27 && hyp < iters;
+  if ((blockIdx.x * 4 + (threadIdx.x >> 5)) * 3 >= iters) return;      // whole warp beyond the table
+  // lane 9 h + c builds column c of the 8 x 9 constraint matrix of hypothesis h
   double g[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) {
-    const int idx = J.samples[hyp * 8 + r];
-    double row[9];
-    constraint_row(J.uv[idx], row);
     double x = 0;
+    if (live) {
+      const int idx = J.samples[hyp * 8 + r];
+      double row[9];
+      constraint_row(J.uv[idx], row);
 #pragma unroll
-    for (int c = 0; c < 9; c++) x = (c == lane) ? row[c] : x;
+      for (int k = 0; k < 9; k++) x = (k == c) ? row[k] : x;
+    }
     g[r] = x;
   }
   double f[9];
   warp_jacobi_null<8>(g, lane, f);
   rank2(f);
-  if (lane < 9) {
+  if (live) {
     double x = 0;
 #pragma unroll
-    for (int c = 0; c < 9; c++) x = (c == lane) ? f[c] : x;
-    J.F_all[(size_t)hyp * 9 + lane] = x;
+    for (int k = 0; k < 9; k++) x = (k == c) ? f[k] : x;
+    J.F_all[(size_t)hyp * 9 + c] = x;
   }
 }
 
@@ -417,7 +422,7 @@ extern "C" int visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* con
     memcpy(pin, hj.data(), sizeof(RansacJob) * nb);
     CU_COPY(ctx, sb, pin, sizeof(RansacJob) * nb, cudaMemcpyHostToDevice);
     const RansacJob* dj = (const RansacJob*)sb;
-    k_hypotheses<<<dim3((iters + 3) / 4, nb), 128, 0, ctx->stream>>>(dj, iters);
+    k_hypotheses<<<dim3((iters + 11) / 12, nb), 128, 0, ctx->stream>>>(dj, iters);
     CU_LAUNCH_CHECK(ctx);
     int ty = (iters + HYP_PER_TILE - 1) / HYP_PER_TILE;
     k_score<<<dim3((maxN + SCORE_THREADS - 1) / SCORE_THREADS, ty, nb), SCORE_THREADS, 0, ctx->stream>>>(dj, iters, thresh);
