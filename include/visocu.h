@@ -62,6 +62,8 @@ int  visocu_device_info(const visocu_ctx* ctx, int32_t* sm_count, int32_t* cc_ma
 /* Allocates n_frames frame slots for width x height images.  `param.match_radius` is used as given (the C++
  * Matcher halves it for half_resolution exactly like matcher.cpp:59-60 before calling).  Re-configurable. */
 int  visocu_configure(visocu_ctx* ctx, const visocu_params* param, int32_t width, int32_t height, int32_t n_frames);
+/* Matcher::setIntrinsics (matcher.h:78-83): calibration used by the motion-predicted quad search */
+int  visocu_set_intrinsics(visocu_ctx* ctx, double f, double cu, double cv, double base);
 int  visocu_sync(visocu_ctx* ctx);
 /* CUDA-event timing on the context's stream (replaces Container::durationOfEvent, opencl_wrapper.cpp:157-164). */
 int  visocu_timer_start(visocu_ctx* ctx);
@@ -103,9 +105,11 @@ int  visocu_nms(visocu_ctx* ctx, const int16_t* f1, const int16_t* f2, int32_t w
  * 1 = dense.  ranges[j] (host, u_bins*v_bins entries, matcher.cpp:734-868) is read only if use_prior.  refine = 1
  * applies relocateMinimum (pixel), refine = 2 parabolicFitting (sub-pixel; drops the matches the reference drops)
  * before the matches are returned.  out[j] receives at most cap[j] matches in the reference's order (ascending
- * i1c for flow and stereo, ascending i1p for quad). */
+ * i1c for flow and stereo, ascending i1p for quad).  tr_delta (optional, quad only): per job the first three rows
+ * (12 doubles) of the previous motion estimate; enables the motion-predicted search of matcher.cpp:1112-1138 with the
+ * calibration f, cu, cv, base of the configured parameters (VisualOdometryStereo::process, viso_stereo.cpp:35). */
 int  visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
-                  int32_t use_prior, const visocu_range* const* ranges, int32_t refine,
+                  int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
                   visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out);
 /* Matcher::refinement alone on caller-supplied matches: mode 1 = pixel, 2 = sub-pixel (n_out <= n survive) */
 int  visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, int32_t mode, visocu_pmatch* inout, int32_t n,

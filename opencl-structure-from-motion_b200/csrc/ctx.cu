@@ -202,6 +202,11 @@ extern "C" int visocu_configure(visocu_ctx* ctx, const visocu_params* p, int32_t
   return VISOCU_OK;
 }
 
+extern "C" int visocu_set_intrinsics(visocu_ctx* ctx, double f, double cu, double cv, double base) {
+  if (!ctx) return VISOCU_EINVAL;
+  ctx->param.f = f; ctx->param.cu = cu; ctx->param.cv = cv; ctx->param.base = base;
+  return VISOCU_OK;
+}
 extern "C" int visocu_sync(visocu_ctx* ctx) {
   if (!ctx) return VISOCU_EINVAL;
   CU_TRY(ctx, cudaSetDevice(ctx->device));

@@ -33,6 +33,9 @@ struct MatchJob {
   visocu_pmatch* out;
   uint8_t* keep;                     // sub-pixel refinement: 0 = match dropped
   int32_t* n_out;
+  double tr[12];                     // rows 0..2 of Tr_delta (previous -> current), used if has_tr
+  double f, cu, cv, base;            // calibration for the prediction (Matcher::parameters)
+  int has_tr, pad2;
   const uint8_t* du[4];              // planes used by the refinement (full resolution)
   const uint8_t* dv[4];
   int nq, pad;
@@ -98,6 +101,68 @@ __device__ __forceinline__ int find_match(const Geometry& g, const SetDev& A, in
   return best == ~0ull ? 0 : (int)(best & 0xFFFFFFull);    // min_ind defaults to 0 (matcher.cpp:898)
 }
 
+// the same hop with a predicted position (up, vp): cost = SAD + 4 * distance to the prediction, in double precision
+// (matcher.cpp:948-953).  The arithmetic uses explicit IEEE operations (no FMA contraction), so it equals the reference
+// built with -ffp-contract=off bit for bit.  Keys: (cost as ordered double bits, then u_bin, v_bin, index).
+__device__ __forceinline__ int find_match_predicted(const Geometry& g, const SetDev& A, int i1, const SetDev& B, int stat_bin, int stage,
+                                                    bool flow, bool use_prior, const visocu_range* __restrict__ ranges, bool active,
+                                                    int sub, double up, double vp, unsigned& n_cand, unsigned& n_scan) {
+  unsigned long long best_cost = ~0ull, best_ord = ~0ull;
+  if (active) {
+    const int32_t* q = A.rec + (size_t)i1 * 12;
+    const int4 hdr = *(const int4*)q;
+    const uint4 qa = *(const uint4*)(q + 4), qb = *(const uint4*)(q + 8);
+    const int u1 = hdr.x, v1 = hdr.y, c = hdr.w;
+    float u_min, u_max, v_min, v_max;
+    if (use_prior) {
+      const visocu_range* r = ranges + stat_bin;
+      u_min = (float)u1 + r->u_min[stage]; u_max = (float)u1 + r->u_max[stage];
+      v_min = (float)v1 + r->v_min[stage]; v_max = (float)v1 + r->v_max[stage];
+    } else {
+      u_min = (float)(u1 - g.radius); u_max = (float)(u1 + g.radius);
+      v_min = (float)(v1 - g.radius); v_max = (float)(v1 + g.radius);
+    }
+    if (!flow) { v_min = (float)(v1 - g.disp_tol); v_max = (float)(v1 + g.disp_tol); }
+    const float bs = (float)g.binsize;
+    const int ubmin = min(max((int)floorf(u_min / bs), 0), g.ub - 1), ubmax = min(max((int)floorf(u_max / bs), 0), g.ub - 1);
+    const int vbmin = min(max((int)floorf(v_min / bs), 0), g.vb - 1), vbmax = min(max((int)floorf(v_max / bs), 0), g.vb - 1);
+    const bool predicted = up >= 0 && vp >= 0;
+    for (int vbin = vbmin; vbin <= vbmax; vbin++) {
+      const int row = (c * g.vb + vbin) * g.ub;
+      const int e0 = B.bin_start[row + ubmin], e1 = ubmax >= ubmin ? B.bin_start[row + ubmax + 1] : e0;
+      for (int e = e0 + sub; e < e1; e += G) {
+        const int2 ent = B.bin_ent[e];
+        const int u2 = ent.x & 0xFFFF, v2 = (int)((unsigned)ent.x >> 16);
+        n_scan++;
+        if ((float)u2 >= u_min && (float)u2 <= u_max && (float)v2 >= v_min && (float)v2 <= v_max) {
+          const int32_t* t = B.rec + (size_t)ent.y * 12;
+          const uint4 ta = *(const uint4*)(t + 4), tb = *(const uint4*)(t + 8);
+          unsigned sad = __vsadu4(qa.x, ta.x) + __vsadu4(qa.y, ta.y) + __vsadu4(qa.z, ta.z) + __vsadu4(qa.w, ta.w) +
+                         __vsadu4(qb.x, tb.x) + __vsadu4(qb.y, tb.y) + __vsadu4(qb.z, tb.z) + __vsadu4(qb.w, tb.w);
+          double cost = (double)sad;
+          if (predicted) {
+            const double du = __dsub_rn((double)u2, up), dv = __dsub_rn((double)v2, vp);
+            const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv)));
+            cost = __dadd_rn(cost, __dmul_rn(4.0, dist));
+          }
+          const int ub2 = min((int)floorf((float)u2 / bs), g.ub - 1);
+          const unsigned long long cb = (unsigned long long)__double_as_longlong(cost);      // cost >= 0: bit order = value order
+          const unsigned long long ord = ((unsigned long long)ub2 << 36) | ((unsigned long long)vbin << 24) | (unsigned long long)ent.y;
+          if (cb < best_cost || (cb == best_cost && ord < best_ord)) { best_cost = cb; best_ord = ord; }
+          n_cand++;
+        }
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int o = G / 2; o; o >>= 1) {
+    const unsigned long long oc = __shfl_xor_sync(0xFFFFFFFFu, best_cost, o), oo = __shfl_xor_sync(0xFFFFFFFFu, best_ord, o);
+    if (oc < best_cost || (oc == best_cost && oo < best_ord)) { best_cost = oc; best_ord = oo; }
+  }
+  return best_cost == ~0ull ? 0 : (int)(best_ord & 0xFFFFFFull);
+}
+
 __global__ void __launch_bounds__(MATCH_THREADS) k_match(Geometry g, const MatchJob* jobs, int method, int use_prior, uint64_t* stats) {
   const MatchJob& J = jobs[blockIdx.y];
   const int sub = threadIdx.x % G;
@@ -124,9 +189,34 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(Geometry g, const Match
     int stat_bin = 0;
     if (active) { const int2 uv = *(const int2*)(J.s[0].rec + (size_t)i * 12); stat_bin = bin_index(g, uv.x, uv.y); }
     const int i2p = find_match(g, J.s[0], i, J.s[1], stat_bin, 0, false, use_prior, J.ranges, active, sub, n_cand, n_scan);
-    const int i2c = find_match(g, J.s[1], i2p, J.s[3], stat_bin, 1, true, use_prior, J.ranges, active, sub, n_cand, n_scan);
-    const int i1c = find_match(g, J.s[3], i2c, J.s[2], stat_bin, 2, false, use_prior, J.ranges, active, sub, n_cand, n_scan);
-    const int i1p2 = find_match(g, J.s[2], i1c, J.s[0], stat_bin, 3, true, use_prior, J.ranges, active, sub, n_cand, n_scan);
+    int i2c, i1c, i1p2;
+    if (J.has_tr) {
+      // motion-predicted search (matcher.cpp:1112-1138): the previous stereo match is triangulated, moved by Tr_delta and
+      // projected into the current right image; candidates are penalised by their distance to that prediction.
+      double up = -1, vp = -1, u1pd = -1, v1pd = -1;
+      if (active) {
+        const int2 a = *(const int2*)(J.s[0].rec + (size_t)i * 12);
+        const int u2p = J.s[1].rec[(size_t)i2p * 12];
+        u1pd = (double)a.x; v1pd = (double)a.y;
+        const double d = fmax(__dsub_rn(u1pd, (double)u2p), 1.0);
+        const double x1p = __ddiv_rn(__dmul_rn(__dsub_rn(u1pd, J.cu), J.base), d);
+        const double y1p = __ddiv_rn(__dmul_rn(__dsub_rn(v1pd, J.cv), J.base), d);
+        const double z1p = __ddiv_rn(__dmul_rn(J.f, J.base), d);
+        const double* t = J.tr;
+        const double x2c = __dsub_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(t[0], x1p), __dmul_rn(t[1], y1p)), __dmul_rn(t[2], z1p)), t[3]), J.base);
+        const double y2c = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(t[4], x1p), __dmul_rn(t[5], y1p)), __dmul_rn(t[6], z1p)), t[7]);
+        const double z2c = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(t[8], x1p), __dmul_rn(t[9], y1p)), __dmul_rn(t[10], z1p)), t[11]);
+        up = __dadd_rn(__ddiv_rn(__dmul_rn(J.f, x2c), z2c), J.cu);
+        vp = __dadd_rn(__ddiv_rn(__dmul_rn(J.f, y2c), z2c), J.cv);
+      }
+      i2c = find_match_predicted(g, J.s[1], i2p, J.s[3], stat_bin, 1, true, use_prior, J.ranges, active, sub, up, vp, n_cand, n_scan);
+      i1c = find_match(g, J.s[3], i2c, J.s[2], stat_bin, 2, false, use_prior, J.ranges, active, sub, n_cand, n_scan);
+      i1p2 = find_match_predicted(g, J.s[2], i1c, J.s[0], stat_bin, 3, true, use_prior, J.ranges, active, sub, u1pd, v1pd, n_cand, n_scan);
+    } else {
+      i2c = find_match(g, J.s[1], i2p, J.s[3], stat_bin, 1, true, use_prior, J.ranges, active, sub, n_cand, n_scan);
+      i1c = find_match(g, J.s[3], i2c, J.s[2], stat_bin, 2, false, use_prior, J.ranges, active, sub, n_cand, n_scan);
+      i1p2 = find_match(g, J.s[2], i1c, J.s[0], stat_bin, 3, true, use_prior, J.ranges, active, sub, n_cand, n_scan);
+    }
     int ok = 0;
     if (active && i1p2 == i) {
       const int u1p = J.s[0].rec[(size_t)i * 12], u2p = J.s[1].rec[(size_t)i2p * 12];
@@ -418,7 +508,7 @@ int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJ
 }  // namespace
 
 extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
-                            int32_t use_prior, const visocu_range* const* ranges, int32_t refine,
+                            int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
                             visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out) {
   if (!ctx) return VISOCU_EINVAL;
   if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
@@ -464,6 +554,9 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
       hj[j].res = (int4*)(sb + o_res[j]); hj[j].blk = (int32_t*)(sb + o_blk[j]);
       hj[j].out = (visocu_pmatch*)(sb + o_out[j]); hj[j].n_out = (int32_t*)(sb + o_cnt[j]);
       hj[j].keep = sb + o_keep[j];
+      hj[j].f = ctx->param.f; hj[j].cu = ctx->param.cu; hj[j].cv = ctx->param.cv; hj[j].base = ctx->param.base;
+      hj[j].has_tr = (method == 2 && tr_delta && tr_delta[start + j]) ? 1 : 0;
+      if (hj[j].has_tr) memcpy(hj[j].tr, tr_delta[start + j], sizeof hj[j].tr);
       if (use_prior) {
         if (!ranges[start + j]) return visocu_set_error(ctx, VISOCU_EINVAL, "job %d has no ranges", start + j);
         memcpy(pin + pin_off, ranges[start + j], (size_t)nstat * sizeof(visocu_range));

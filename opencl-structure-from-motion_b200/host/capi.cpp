@@ -13,6 +13,7 @@
 #include "filter.h"
 #include "matcher.h"
 #include "viso_mono.h"
+#include "viso_stereo.h"
 #include "visocu.h"
 
 #define VISOB_API extern "C" __attribute__((visibility("default")))
@@ -132,6 +133,47 @@ VISOB_API int visob_mono_get_samples(void* v, int32_t* out, int cap) {
   return (int)s.size();
 }
 VISOB_API void* visob_mono_matcher(void* v) { return ((MonoAccess*)v)->getMatcher(); }
+
+// ---- stereo odometry
+namespace {
+struct StereoParamsC {        // flat mirror of VisualOdometryStereo::parameters (same as oracle/pyref.py StereoParams)
+  Matcher::parameters match;
+  int32_t bucket_max_features; double bucket_width, bucket_height;
+  double f, cu, cv;
+  double base; int32_t ransac_iters; double inlier_threshold; int32_t reweighting;
+};
+struct StereoAccess : public VisualOdometryStereo {
+  explicit StereoAccess(VisualOdometryStereo::parameters p) : VisualOdometryStereo(p) {}
+};
+}  // namespace
+VISOB_API void* visob_stereo_create(const StereoParamsC* p) {
+  VisualOdometryStereo::parameters q;
+  q.match = p->match;
+  q.bucket.max_features = p->bucket_max_features; q.bucket.bucket_width = p->bucket_width; q.bucket.bucket_height = p->bucket_height;
+  q.calib.f = p->f; q.calib.cu = p->cu; q.calib.cv = p->cv;
+  q.base = p->base; q.ransac_iters = p->ransac_iters; q.inlier_threshold = p->inlier_threshold; q.reweighting = p->reweighting != 0;
+  return new StereoAccess(q);
+}
+VISOB_API void visob_stereo_destroy(void* v) { delete (StereoAccess*)v; }
+VISOB_API int visob_stereo_process(void* v, uint8_t* I1, uint8_t* I2, const int32_t* dims, int replace) {
+  uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+  return ((StereoAccess*)v)->process(I1, I2, d, replace != 0) ? 1 : 0;
+}
+VISOB_API void visob_stereo_get_motion(void* v, double* out16) {
+  Matrix T = ((StereoAccess*)v)->getMotion();
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out16[4 * i + j] = T.val[i][j];
+}
+VISOB_API int visob_stereo_get_matches(void* v, void* out, int cap) { return copy_matches(((StereoAccess*)v)->usedMatches(), out, cap); }
+VISOB_API int visob_stereo_get_inliers(void* v, int32_t* out, int cap) {
+  std::vector<int32_t> in = ((StereoAccess*)v)->getInlierIndices();
+  if (out) memcpy(out, in.data(), sizeof(int32_t) * (size_t)std::min((int)in.size(), cap));
+  return (int)in.size();
+}
+VISOB_API void visob_matcher_match_features_tr(void* m, int method, const double* tr16) {
+  Matrix T(4, 4, tr16);
+  ((Matcher*)m)->matchFeatures(method, &T);
+}
+VISOB_API void visob_matcher_set_intrinsics(void* m, double f, double cu, double cv, double base) { ((Matcher*)m)->setIntrinsics(f, cu, cv, base); }
 
 // ---- host utilities exposed for tests
 VISOB_API int visob_delaunay(const int32_t* x, const int32_t* y, int n, int32_t* tri_out, int cap_tri) {

@@ -41,7 +41,7 @@ static_assert(sizeof(Matcher::p_match) == sizeof(visocu_pmatch), "p_match layout
 static_assert(sizeof(Matcher::range) == sizeof(visocu_range), "range layout");
 static_assert(sizeof(Matcher::parameters) == sizeof(visocu_params), "parameters layout");
 
-Matcher::Matcher(parameters param) : param(param), ctx(0), owns_ctx(true), slot_base(0), cfg_w(0), cfg_h(0), have_I1p(false), have_I1c(false) {
+Matcher::Matcher(parameters param) : param(param), ctx(0), owns_ctx(true), slot_base(0), cfg_w(0), cfg_h(0), have_I1p(false), have_I1c(false), has_tr(false) {
   margin = 5 + 1;
   if (param.half_resolution) this->param.match_radius /= 2;     // matcher.cpp:59-60
   device = visob::current_device();
@@ -169,7 +169,9 @@ bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_
   visocu_pmatch* optr = reinterpret_cast<visocu_pmatch*>(out.data());
   const visocu_range* rptr = reinterpret_cast<const visocu_range*>(ranges.data());
   int32_t cap = nq + 1, n = 0;
-  int rc = visocu_match(ctx, 1, &q, method, pass, use_prior ? 1 : 0, use_prior ? &rptr : 0, refine, &optr, &cap, &n);
+  const double* tptr = tr_rows;
+  int rc = visocu_match(ctx, 1, &q, method, pass, use_prior ? 1 : 0, use_prior ? &rptr : 0, (has_tr && method == 2) ? &tptr : 0, refine,
+                        &optr, &cap, &n);
   if (rc != VISOCU_OK) {
     std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
     out.clear();
@@ -180,8 +182,17 @@ bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_
 }
 
 void Matcher::matchFeatures(int32_t method, Matrix* Tr_delta) {
-  (void)Tr_delta;   // the motion-predicted search of matcher.cpp:1114-1134 is not implemented: plain search is used
   if (!matchBegin(method)) return;
+  // motion-predicted search (quad matching only, matcher.cpp:1112-1138): rows 0..2 of Tr_delta go to the kernel
+  has_tr = false;
+  if (Tr_delta && method == 2 && Tr_delta->m >= 3 && Tr_delta->n >= 4) {
+    has_tr = true;
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 4; c++) tr_rows[4 * r + c] = Tr_delta->val[r][c];
+    visocu_params vp;
+    memcpy(&vp, &param, sizeof vp);
+    visocu_set_intrinsics(ctx, vp.f, vp.cu, vp.cv, vp.base);      // setIntrinsics may have been called after the first push
+  }
   const int refine = refineMode();
   if (param.multi_stage) {
     if (!matching(0, p_matched_1, method, false, 0)) return;
@@ -455,7 +466,7 @@ bool MatcherBatch::matchPass(const vector<int32_t>& active, int pass, int32_t me
     rptr[k] = reinterpret_cast<const visocu_range*>(m->ranges.data());
     cap[k] = nq + 1;
   }
-  const int rc = visocu_match(ctx, (int32_t)n, quads.data(), method, pass, use_prior ? 1 : 0, use_prior ? rptr.data() : 0, refine,
+  const int rc = visocu_match(ctx, (int32_t)n, quads.data(), method, pass, use_prior ? 1 : 0, use_prior ? rptr.data() : 0, 0, refine,
                               outs.data(), cap.data(), cnt.data());
   if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
   for (size_t k = 0; k < n; k++) {

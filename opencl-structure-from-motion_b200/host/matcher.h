@@ -6,7 +6,7 @@
 //       pixel and sub-pixel refinement.
 //   host (this class): ring-buffer bookkeeping, computePriorStatistics, removeOutliers (own exact Delaunay
 //       triangulation + support vote), bucketFeatures, getGain.
-// Not supported yet: the Tr_delta-guided search window of quad matching (plain search is used).
+// The Tr_delta-guided search of quad matching (matcher.cpp:1112-1138) runs on the GPU as well.
 #ifndef VISOB_MATCHER_H
 #define VISOB_MATCHER_H
 #include <stdint.h>
@@ -115,6 +115,8 @@ private:
   bool have_I1p, have_I1c;
   std::vector<p_match> p_matched_1, p_matched_2;
   std::vector<range> ranges;
+  bool has_tr;
+  double tr_rows[12];
   struct random_data rnd_data;
   char rnd_state[128];
 };

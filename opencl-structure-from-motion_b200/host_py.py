@@ -27,6 +27,22 @@ class MonoParams(C.Structure):
             setattr(self, k, v)
 
 
+class StereoParams(C.Structure):
+    """VisualOdometryStereo::parameters flattened (reference viso.h:33-62, viso_stereo.h:32-46)."""
+    _fields_ = [('match', Params), ('bucket_max_features', C.c_int32), ('bucket_width', C.c_double),
+                ('bucket_height', C.c_double), ('f', C.c_double), ('cu', C.c_double), ('cv', C.c_double),
+                ('base', C.c_double), ('ransac_iters', C.c_int32), ('inlier_threshold', C.c_double), ('reweighting', C.c_int32)]
+
+    def __init__(self, match=None, **kw):
+        super().__init__()
+        self.match = match if match is not None else Params()
+        d = dict(bucket_max_features=2, bucket_width=50.0, bucket_height=50.0, f=1.0, cu=0.0, cv=0.0,
+                 base=1.0, ransac_iters=200, inlier_threshold=2.0, reweighting=1)
+        d.update(kw)
+        for k, v in d.items():
+            setattr(self, k, v)
+
+
 _lib = None
 
 
@@ -36,7 +52,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise VisocuError(LIB_PATH + ' is missing: run __graft_entry__.build()')
         L = C.CDLL(LIB_PATH)
-        for name in ('visob_matcher_create', 'visob_mono_create', 'visob_mono_matcher', 'visob_runner_create',
+        for name in ('visob_matcher_create', 'visob_mono_create', 'visob_mono_matcher', 'visob_runner_create', 'visob_stereo_create',
                      'visob_matcher_context'):
             getattr(L, name).restype = C.c_void_p
         L.visob_matcher_gain.restype = C.c_float
@@ -88,8 +104,14 @@ class Matcher:
             I2 = np.ascontiguousarray(I2, np.uint8)
         lib().visob_matcher_push(self.h, _p(I1), _p(I2), _p(_dims(I1)), int(replace))
 
-    def match_features(self, method):
-        lib().visob_matcher_match_features(self.h, method)
+    def match_features(self, method, tr_delta=None):
+        if tr_delta is None:
+            lib().visob_matcher_match_features(self.h, method)
+        else:
+            lib().visob_matcher_match_features_tr(self.h, method, _p(np.ascontiguousarray(tr_delta, np.float64)))
+
+    def set_intrinsics(self, f, cu, cv, base):
+        lib().visob_matcher_set_intrinsics(self.h, C.c_double(f), C.c_double(cu), C.c_double(cv), C.c_double(base))
 
     def bucket(self, max_features, bw, bh):
         lib().visob_matcher_bucket(self.h, max_features, C.c_float(bw), C.c_float(bh))
@@ -181,6 +203,40 @@ class Mono:
         if n:
             lib().visob_mono_get_samples(self.h, _p(out), n)
         return out.reshape(-1, 8)
+
+
+class Stereo:
+    def __init__(self, params):
+        self.params = params
+        self.h = C.c_void_p(lib().visob_stereo_create(C.byref(params)))
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            lib().visob_stereo_destroy(self.h)
+            self.h = None
+
+    def process(self, I1, I2, replace=False):
+        I1 = np.ascontiguousarray(I1, np.uint8); I2 = np.ascontiguousarray(I2, np.uint8)
+        return bool(lib().visob_stereo_process(self.h, _p(I1), _p(I2), _p(_dims(I1)), int(replace)))
+
+    def motion(self):
+        out = np.zeros((4, 4))
+        lib().visob_stereo_get_motion(self.h, _p(out))
+        return out
+
+    def matches(self):
+        n = lib().visob_stereo_get_matches(self.h, None, 0)
+        out = np.zeros(n, P_MATCH)
+        if n:
+            lib().visob_stereo_get_matches(self.h, _p(out), n)
+        return out
+
+    def inliers(self):
+        n = lib().visob_stereo_get_inliers(self.h, None, 0)
+        out = np.zeros(n, np.int32)
+        if n:
+            lib().visob_stereo_get_inliers(self.h, _p(out), n)
+        return out
 
 
 def delaunay(x, y):

@@ -199,7 +199,7 @@ class Context:
         return out[:cnt.value].copy()
 
     # ---- matching
-    def match(self, quads, method, pass_, ranges=None, refine=False):
+    def match(self, quads, method, pass_, ranges=None, refine=False, tr_delta=None):
         """quads: list of (f1p, f2p, f1c, f2c).  ranges: list of (ub*vb) RANGE arrays or None.  Returns list of P_MATCH arrays."""
         nj = len(quads)
         q = np.zeros(nj, QUAD)
@@ -214,7 +214,11 @@ class Context:
         if ranges is not None:
             ranges = [np.ascontiguousarray(r) for r in ranges]
             rptr = (C.c_void_p * nj)(*[r.ctypes.data for r in ranges])
-        self._ck(lib().visocu_match(self.h, nj, _p(q), method, pass_, int(ranges is not None), rptr, int(refine),
+        tptr = None
+        if tr_delta is not None:
+            trs = [np.ascontiguousarray(np.asarray(t, np.float64)[:3, :4]) for t in tr_delta]
+            tptr = (C.c_void_p * nj)(*[t.ctypes.data for t in trs])
+        self._ck(lib().visocu_match(self.h, nj, _p(q), method, pass_, int(ranges is not None), rptr, tptr, int(refine),
                                     optr, _p(caps), _p(nout)), 'match')
         return [outs[k][:nout[k]].copy() for k in range(nj)]
 

