@@ -14,6 +14,8 @@
 #include "matcher.h"
 #include "viso_mono.h"
 #include "viso_stereo.h"
+#include "reconstruction.h"
+#include "sfm.h"
 #include "visocu.h"
 
 #define VISOB_API extern "C" __attribute__((visibility("default")))
@@ -174,6 +176,37 @@ VISOB_API void visob_matcher_match_features_tr(void* m, int method, const double
   ((Matcher*)m)->matchFeatures(method, &T);
 }
 VISOB_API void visob_matcher_set_intrinsics(void* m, double f, double cu, double cv, double base) { ((Matcher*)m)->setIntrinsics(f, cu, cv, base); }
+
+// ---- reconstruction and the facade
+VISOB_API void* visob_recon_create() { return new Reconstruction(); }
+VISOB_API void visob_recon_destroy(void* r) { delete (Reconstruction*)r; }
+VISOB_API void visob_recon_set_calibration(void* r, double f, double cu, double cv) { ((Reconstruction*)r)->setCalibration(f, cu, cv); }
+VISOB_API void visob_recon_update(void* r, const void* matches, int n, const double* tr16, int point_type, int min_track_length,
+                                  double max_dist, double min_angle) {
+  const Matcher::p_match* m = (const Matcher::p_match*)matches;
+  ((Reconstruction*)r)->update(std::vector<Matcher::p_match>(m, m + n), Matrix(4, 4, tr16), point_type, min_track_length, max_dist, min_angle);
+}
+VISOB_API int visob_recon_get_points(void* r, float* out3, int cap) {
+  const std::vector<Point3d>& pts = ((Reconstruction*)r)->getPoints();
+  for (int i = 0; i < (int)pts.size() && i < cap; i++) { out3[3 * i] = pts[i].x; out3[3 * i + 1] = pts[i].y; out3[3 * i + 2] = pts[i].z; }
+  return (int)pts.size();
+}
+VISOB_API void* visob_sfm_create(const MonoParamsC* p, const int32_t* dims) {
+  StructureFromMotion* s = new StructureFromMotion(to_cpp(p), std::array<uint32_t, 3>{{(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]}}, true);
+  s->setVerbose(false);
+  return s;
+}
+VISOB_API void visob_sfm_destroy(void* s) { delete (StructureFromMotion*)s; }
+VISOB_API void visob_sfm_update(void* s, uint8_t* img) { ((StructureFromMotion*)s)->update(img); }
+VISOB_API int visob_sfm_get_points(void* s, float* out3, int cap) {
+  const std::vector<Point3d>& pts = ((StructureFromMotion*)s)->getPoints();
+  for (int i = 0; i < (int)pts.size() && i < cap; i++) { out3[3 * i] = pts[i].x; out3[3 * i + 1] = pts[i].y; out3[3 * i + 2] = pts[i].z; }
+  return (int)pts.size();
+}
+VISOB_API void visob_sfm_get_pose(void* s, double* out16) {
+  const Matrix& T = ((StructureFromMotion*)s)->getPose();
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out16[4 * i + j] = T.val[i][j];
+}
 
 // ---- host utilities exposed for tests
 VISOB_API int visob_delaunay(const int32_t* x, const int32_t* y, int n, int32_t* tri_out, int cap_tri) {

@@ -52,7 +52,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise VisocuError(LIB_PATH + ' is missing: run __graft_entry__.build()')
         L = C.CDLL(LIB_PATH)
-        for name in ('visob_matcher_create', 'visob_mono_create', 'visob_mono_matcher', 'visob_runner_create', 'visob_stereo_create',
+        for name in ('visob_matcher_create', 'visob_mono_create', 'visob_mono_matcher', 'visob_runner_create', 'visob_stereo_create', 'visob_recon_create', 'visob_sfm_create',
                      'visob_matcher_context'):
             getattr(L, name).restype = C.c_void_p
         L.visob_matcher_gain.restype = C.c_float
@@ -236,6 +236,35 @@ class Stereo:
         out = np.zeros(n, np.int32)
         if n:
             lib().visob_stereo_get_inliers(self.h, _p(out), n)
+        return out
+
+
+class Sfm:
+    """StructureFromMotion facade (host/sfm.h)."""
+
+    def __init__(self, params, width, height):
+        self.dims = np.array([width, height, width], np.int32)
+        self.h = C.c_void_p(lib().visob_sfm_create(C.byref(params), _p(self.dims)))
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            lib().visob_sfm_destroy(self.h)
+            self.h = None
+
+    def update(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        lib().visob_sfm_update(self.h, _p(img))
+
+    def points(self):
+        n = lib().visob_sfm_get_points(self.h, None, 0)
+        out = np.zeros((n, 3), np.float32)
+        if n:
+            lib().visob_sfm_get_points(self.h, _p(out), n)
+        return out
+
+    def pose(self):
+        out = np.zeros((4, 4))
+        lib().visob_sfm_get_pose(self.h, _p(out))
         return out
 
 

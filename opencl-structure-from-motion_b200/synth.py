@@ -158,3 +158,44 @@ def corridor_sequence(n_frames, width=1241, height=376, seed=1234, start=0, **kw
 
 def corridor_stereo_frame(k, width=1241, height=376, seed=1234, baseline=0.54):
     return corridor_frame(k, width, height, seed), corridor_frame(k, width, height, seed, baseline_x=baseline)
+
+
+def track_sequence(n_frames=12, n_points=600, seed=11, width=1241, height=376, f=KITTI_F, cu=KITTI_CU, cv=KITTI_CV,
+                   step=0.8, drop=0.15, noise=0.2):
+    """Synthetic feature tracks for the Reconstruction tests: random 3-D points ahead of a camera that drives forward
+    with a slight yaw; every frame pair yields flow matches (48-byte p_match records, only the 1p / 1c fields used)
+    whose feature indices chain from frame to frame like the matcher's i1p / i1c, plus the motion previous -> current
+    camera frame.  Points drop out at random so that tracks end and get reconstructed.  Returns a list of
+    (matches, Tr) per frame pair."""
+    rng = np.random.RandomState(seed)
+    P = np.stack([rng.uniform(-8, 8, n_points), rng.uniform(-2.5, 1.6, n_points), rng.uniform(4, 60, n_points)], 1)
+    dt = np.dtype([('u1p', 'f4'), ('v1p', 'f4'), ('i1p', 'i4'), ('u2p', 'f4'), ('v2p', 'f4'), ('i2p', 'i4'),
+                   ('u1c', 'f4'), ('v1c', 'f4'), ('i1c', 'i4'), ('u2c', 'f4'), ('v2c', 'f4'), ('i2c', 'i4')])
+    poses = []                      # world -> camera k
+    for k in range(n_frames):
+        yaw = 0.01 * np.sin(0.3 * k)
+        R = np.array([[np.cos(yaw), 0, -np.sin(yaw)], [0, 1, 0], [np.sin(yaw), 0, np.cos(yaw)]])
+        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = -R @ np.array([0.05 * k, 0.0, step * k])
+        poses.append(T)
+    obs = []
+    for k in range(n_frames):
+        X = P @ poses[k][:3, :3].T + poses[k][:3, 3]
+        u = f * X[:, 0] / X[:, 2] + cu + rng.normal(0, noise, n_points)
+        v = f * X[:, 1] / X[:, 2] + cv + rng.normal(0, noise, n_points)
+        vis = (X[:, 2] > 1.5) & (u > 6) & (u < width - 7) & (v > 6) & (v < height - 7) & (rng.rand(n_points) > drop)
+        index = rng.permutation(n_points).astype(np.int32)          # feature index of every point in this frame
+        obs.append((u.astype(np.float32), v.astype(np.float32), vis, index))
+    out = []
+    for k in range(1, n_frames):
+        up, vp, visp, ip = obs[k - 1]
+        uc, vc, visc, ic = obs[k]
+        both = np.nonzero(visp & visc)[0]
+        both = both[np.argsort(ic[both])]
+        m = np.zeros(len(both), dt)
+        for name in ('u2p', 'v2p', 'u2c', 'v2c'):
+            m[name] = -1
+        m['i2p'] = -1; m['i2c'] = -1
+        m['u1p'] = up[both]; m['v1p'] = vp[both]; m['i1p'] = ip[both]
+        m['u1c'] = uc[both]; m['v1c'] = vc[both]; m['i1c'] = ic[both]
+        out.append((m, poses[k] @ np.linalg.inv(poses[k - 1])))
+    return out

@@ -93,6 +93,7 @@ class RefLib:
         L.ref_matcher_create.restype = C.c_void_p
         L.ref_mono_create.restype = C.c_void_p
         L.ref_stereo_create.restype = C.c_void_p
+        L.ref_recon_create.restype = C.c_void_p
         L.ref_mono_matcher.restype = C.c_void_p
         L.ref_matcher_gain.restype = C.c_float
         L.ref_time_matcher_sequence.restype = C.c_double
@@ -148,6 +149,9 @@ class RefLib:
 
     def mono(self, params):
         return RefMono(self, params)
+
+    def reconstruction(self):
+        return Recon(self.lib, 'ref_recon')
 
     def stereo(self, params):
         return RefStereo(self, params)
@@ -274,6 +278,39 @@ class RefMatcher:
     def gain(self, inliers):
         a = np.ascontiguousarray(inliers, np.int32)
         return float(self.lib.ref_matcher_gain(self.h, _p(a), len(a)))
+
+
+class Recon:
+    """Reconstruction driven through a C shim; `prefix` selects the library's entry points (the reference shim and the
+    B200 host library export the same five functions under different prefixes)."""
+
+    def __init__(self, lib, prefix):
+        self.lib, self.prefix = lib, prefix
+        self.h = C.c_void_p(self._f('create')())
+
+    def _f(self, name):
+        return getattr(self.lib, '%s_%s' % (self.prefix, name))
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            self._f('destroy')(self.h)
+            self.h = None
+
+    def set_calibration(self, f, cu, cv):
+        self._f('set_calibration')(self.h, C.c_double(f), C.c_double(cu), C.c_double(cv))
+
+    def update(self, matches, tr, point_type=1, min_track_length=2, max_dist=30.0, min_angle=2.0):
+        matches = np.ascontiguousarray(matches, P_MATCH)
+        tr = np.ascontiguousarray(tr, np.float64)
+        self._f('update')(self.h, _p(matches), len(matches), _p(tr), int(point_type), int(min_track_length),
+                          C.c_double(max_dist), C.c_double(min_angle))
+
+    def points(self):
+        n = self._f('get_points')(self.h, None, 0)
+        out = np.zeros((n, 3), np.float32)
+        if n:
+            self._f('get_points')(self.h, _p(out), n)
+        return out
 
 
 class RefStereo:

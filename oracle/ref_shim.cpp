@@ -33,6 +33,7 @@
 #define private public
 #define protected public
 #include "matcher.h"
+#include "reconstruction.h"
 #include "filter.h"
 #include "viso_mono.h"
 #include "viso_stereo.h"
@@ -378,6 +379,21 @@ VisualOdometryStereo::parameters to_ref(const RefStereoParams* p) {
   return q;
 }
 }  // namespace
+// ---- Reconstruction (reconstruction.h:40-67), driven with explicit match lists and motions
+REF_API void* ref_recon_create() { return new Reconstruction(); }
+REF_API void ref_recon_destroy(void* r) { delete (Reconstruction*)r; }
+REF_API void ref_recon_set_calibration(void* r, double f, double cu, double cv) { ((Reconstruction*)r)->setCalibration(f, cu, cv); }
+REF_API void ref_recon_update(void* r, const void* matches, int n, const double* tr16, int point_type, int min_track_length,
+                              double max_dist, double min_angle) {
+  const Matcher::p_match* m = (const Matcher::p_match*)matches;
+  ((Reconstruction*)r)->update(std::vector<Matcher::p_match>(m, m + n), Matrix(4, 4, tr16), point_type, min_track_length, max_dist, min_angle);
+}
+REF_API int ref_recon_get_points(void* r, float* out3, int cap) {
+  const std::vector<Point3d>& pts = ((Reconstruction*)r)->getPoints();
+  for (int i = 0; i < (int)pts.size() && i < cap; i++) { out3[3 * i] = pts[i].x; out3[3 * i + 1] = pts[i].y; out3[3 * i + 2] = pts[i].z; }
+  return (int)pts.size();
+}
+
 REF_API void* ref_stereo_create(const RefStereoParams* p) { return new VisualOdometryStereo(to_ref(p)); }
 REF_API void ref_stereo_destroy(void* v) { delete (VisualOdometryStereo*)v; }
 REF_API int ref_stereo_process(void* v, uint8_t* I1, uint8_t* I2, const int32_t* dims, int replace) {

@@ -115,3 +115,26 @@ def test_bench_rank_aggregation_gloo():
     assert abs(r['ms_per_step'] - 20.0) < 1e-6
     assert abs(r['value'] - 2 * r['config']['sequences_per_gpu'] / 0.020) < 1e-3
     assert r['gpu_launches'] == 0 and r['data'] == 'dry-run'
+
+
+@pytest.mark.parametrize('point_type,min_len,min_angle', [(0, 2, 3.0), (1, 2, 2.0), (2, 3, 1.0)])
+def test_reconstruction_matches_reference(ref, point_type, min_len, min_angle):
+    """Reconstruction::update (reconstruction.cpp:50-146) on synthetic feature tracks: same tracks end in the same
+    frames, so the point lists have the same length and order; coordinates agree to float rounding (the 4x4 null vector
+    comes from a different SVD algorithm, then both sides run the same Gauss-Newton to convergence at 1e-5)."""
+    import synth
+    seq = synth.track_sequence(n_frames=14, n_points=700, seed=21)
+    rr = ref.reconstruction()
+    hr = pyref.Recon(H.lib(), 'visob_recon')
+    for r in (rr, hr):
+        r.set_calibration(synth.KITTI_F, synth.KITTI_CU, synth.KITTI_CV)
+    total = 0
+    for m, tr in seq:
+        for r in (rr, hr):
+            r.update(m, tr, point_type, min_len, 30.0, min_angle)
+        a, b = rr.points(), hr.points()
+        assert len(a) == len(b)
+        if len(a):
+            assert np.abs(a - b).max() <= 1e-5 * max(1.0, np.abs(a).max())
+        total = len(a)
+    assert total > 50
