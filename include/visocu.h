@@ -107,10 +107,18 @@ int  visocu_nms(visocu_ctx* ctx, const int16_t* f1, const int16_t* f2, int32_t w
  * before the matches are returned.  out[j] receives at most cap[j] matches in the reference's order (ascending
  * i1c for flow and stereo, ascending i1p for quad).  tr_delta (optional, quad only): per job the first three rows
  * (12 doubles) of the previous motion estimate; enables the motion-predicted search of matcher.cpp:1112-1138 with the
- * calibration f, cu, cv, base of the configured parameters (VisualOdometryStereo::process, viso_stereo.cpp:35). */
+ * calibration f, cu, cv, base of the configured parameters (VisualOdometryStereo::process, viso_stereo.cpp:35).
+ * outliers (optional, n_jobs entries): if non-null, Matcher::removeOutliers (matcher.cpp:1207-1377) runs on the device
+ * right after the matching / refinement and only the survivors are copied back; outliers[j] is set to 1.  A list the
+ * device path cannot take (too long for shared memory, or two matches on the same pixel) comes back complete with
+ * outliers[j] = 0, and the caller has to run the vote itself. */
 int  visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
                   int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
-                  visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out);
+                  visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers);
+/* Matcher::removeOutliers alone on caller-supplied match lists (host memory, compacted in place).  status[j] = 0: done,
+ * 1: list unchanged, not handled by the device path (see visocu_match). */
+int  visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t method, visocu_pmatch* const* inout, const int32_t* n,
+                            int32_t* n_out, int32_t* status);
 /* Matcher::refinement alone on caller-supplied matches: mode 1 = pixel, 2 = sub-pixel (n_out <= n survive) */
 int  visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, int32_t mode, visocu_pmatch* inout, int32_t n,
                    int32_t* n_out);

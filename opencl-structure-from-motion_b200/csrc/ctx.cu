@@ -72,9 +72,14 @@ extern "C" void visocu_destroy(visocu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (getenv("VISOCU_RO_STATS") && ctx->ro_jobs)
+    fprintf(stderr, "[outliers] %llu lists on the device (%llu declined), mean us: sort %.1f partition %.1f build %.1f vote %.1f\n",
+            (unsigned long long)ctx->ro_jobs, (unsigned long long)ctx->ro_declined, 1e-3 * ctx->ro_ns[0] / ctx->ro_jobs,
+            1e-3 * ctx->ro_ns[1] / ctx->ro_jobs, 1e-3 * ctx->ro_ns[2] / ctx->ro_jobs, 1e-3 * ctx->ro_ns[3] / ctx->ro_jobs);
   free_pool(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->img_stage) cudaFree(ctx->img_stage);
+  if (ctx->counts_stage) cudaFree(ctx->counts_stage);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->pev0) cudaEventDestroy(ctx->pev0);
@@ -93,6 +98,11 @@ extern "C" int visocu_device_info(const visocu_ctx* ctx, int32_t* sm_count, int3
   if (cc_minor) *cc_minor = ctx->cc_minor;
   if (name64) memcpy(name64, ctx->name, 64);
   return VISOCU_OK;
+}
+
+bool visocu_uniform_carveout() {
+  static const bool on = [] { const char* e = getenv("VISOCU_CARVEOUT"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes) {
@@ -353,10 +363,23 @@ extern "C" int visocu_push_frames(visocu_ctx* ctx, int32_t n, const int32_t* fra
       }
       ctx->frame_valid[f] = 1;
     }
+    if (!ctx->counts_stage) CU_TRY(ctx, cudaMalloc(&ctx->counts_stage, VISO_MAX_BATCH * 16));
     if ((rc = visocu_launch_features(ctx, sl))) return rc;
+    // the host needs the record counts to size the matching launches: one small read-back per launch
+    if ((rc = visocu_ensure_pinned(ctx, (size_t)sl.n * 16))) return rc;
+    int32_t* stage = (int32_t*)ctx->pinned;
+    CU_COPY(ctx, stage, ctx->counts_stage, (size_t)sl.n * 16, cudaMemcpyDeviceToHost);
+    CU_TRY(ctx, visocu_stream_wait(ctx));
+    for (int i = 0; i < sl.n; i++) {
+      const int f = sl.s[i];
+      if (stage[4 * i + 2]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "feature list of frame %d overflowed", f);
+      ctx->h_counts[2 * (size_t)f + 0] = stage[4 * i + 0];
+      ctx->h_counts[2 * (size_t)f + 1] = stage[4 * i + 1];
+      if (n_sparse) n_sparse[start + i] = stage[4 * i + 0];
+      if (n_dense) n_dense[start + i] = stage[4 * i + 1];
+    }
   }
-  // the host needs the record counts to size the matching launches: one small read-back per call
-  return visocu_frame_counts(ctx, n, frames, n_sparse, n_dense);
+  return VISOCU_OK;
 }
 
 extern "C" int visocu_get_features(visocu_ctx* ctx, int32_t frame, int32_t pass, int32_t* out12, int32_t cap, int32_t* n_out) {

@@ -582,6 +582,15 @@ __global__ void __launch_bounds__(1024) k_build_bins(Geometry g, const FrameDev*
   }
 }
 
+// record counts (and the overflow flag) of the frames of one launch, gathered for a single read-back
+__global__ void k_gather_counts(const FrameDev* frames, SlotList sl, int32_t* out) {
+  const int i = threadIdx.x;
+  if (i < sl.n) {
+    const int32_t* c = frames[sl.s[i]].counts;
+    out[4 * i] = c[0]; out[4 * i + 1] = c[1]; out[4 * i + 2] = c[2]; out[4 * i + 3] = 0;
+  }
+}
+
 }  // namespace
 
 int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
@@ -610,6 +619,15 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
       std::lock_guard<std::mutex> lock(mtx);
       if (!done[ctx->device & 63]) {
         CU_TRY(ctx, cudaFuncSetAttribute(k_filter_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (visocu_uniform_carveout()) {
+          // one shared-memory / L1 split for every kernel of the pipeline: an SM never has to drain to switch
+          CU_TRY(ctx, cudaFuncSetAttribute(k_half_image, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          CU_TRY(ctx, cudaFuncSetAttribute(k_sobel_full, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          CU_TRY(ctx, cudaFuncSetAttribute(k_filter_nms, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          CU_TRY(ctx, cudaFuncSetAttribute(k_cell_count, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          CU_TRY(ctx, cudaFuncSetAttribute(k_emit_records, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          CU_TRY(ctx, cudaFuncSetAttribute(k_build_bins, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
         done[ctx->device & 63] = true;
       }
     }
@@ -640,6 +658,10 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
   dim3 gb(1, 2, sl.n);
   k_build_bins<<<gb, 1024, 0, st>>>(g, ctx->frames_d, sl);
   CU_LAUNCH_CHECK(ctx);
+  if (ctx->counts_stage) {
+    k_gather_counts<<<1, VISO_MAX_BATCH, 0, st>>>(ctx->frames_d, sl, ctx->counts_stage);
+    CU_LAUNCH_CHECK(ctx);
+  }
   return VISOCU_OK;
 }
 

@@ -15,6 +15,8 @@
 // "pixel already matched" rule (matcher.cpp:1036-1039) only ever involves the up-to-three preceding records
 // because two features share a pixel only when they come from the same NMS cell.
 #include "visocu_internal.cuh"
+#include "outliers.cuh"
+#include <mutex>
 #include <cmath>
 #include <cstring>
 
@@ -509,7 +511,7 @@ int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJ
 
 extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
                             int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
-                            visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out) {
+                            visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers) {
   if (!ctx) return VISOCU_EINVAL;
   if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
   if (n_jobs <= 0 || !jobs || !out || !cap || !n_out) return visocu_set_error(ctx, VISOCU_EINVAL, "bad match arguments");
@@ -519,14 +521,25 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
   if (pass < ctx->g.first_pass || pass > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "pass %d not available", pass);
   if (use_prior && !ranges) return visocu_set_error(ctx, VISOCU_EINVAL, "use_prior needs ranges");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (visocu_uniform_carveout()) {
+    static std::mutex mtx;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lock(mtx);
+    if (!done[ctx->device & 63]) {
+      CU_TRY(ctx, cudaFuncSetAttribute(k_match, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CU_TRY(ctx, cudaFuncSetAttribute(k_match_count, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CU_TRY(ctx, cudaFuncSetAttribute(k_match_emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CU_TRY(ctx, cudaFuncSetAttribute(k_refine, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      done[ctx->device & 63] = true;
+    }
+  }
   const Geometry& g = ctx->g;
   const int nstat = g.ub * g.vb;
   for (int start = 0; start < n_jobs; start += VISO_MAX_BATCH) {
     const int nb = n_jobs - start < VISO_MAX_BATCH ? n_jobs - start : VISO_MAX_BATCH;
     std::vector<MatchJob> hj(nb);
-    size_t off = align_up(sizeof(MatchJob) * nb, 256);
+    std::vector<RoJob> rj(outliers ? nb : 0);
     int maxq = 0;
-    std::vector<size_t> o_res(nb), o_blk(nb), o_out(nb), o_cnt(nb), o_rng(nb), o_keep(nb);
     for (int j = 0; j < nb; j++) {
       int rc = fill_job(ctx, jobs[start + j], method, pass, hj[j]);
       if (rc) return rc;
@@ -536,39 +549,61 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
       const int nq = empty ? 0 : (method == 2 ? hj[j].s[0].n : hj[j].s[2].n);
       hj[j].nq = nq;
       if (nq > maxq) maxq = nq;
+      if (use_prior && !ranges[start + j]) return visocu_set_error(ctx, VISOCU_EINVAL, "job %d has no ranges", start + j);
+    }
+    // Device scratch.  A header block (job descriptors of both kernels and the prior ranges of every job) goes up in ONE
+    // copy; the per-job result words come back in ONE copy; the match lists have a uniform stride so that ONE 2-D copy
+    // into pinned memory fetches them all.  (Every API call costs microseconds under the driver's lock, and with many
+    // worker threads sharing a GPU that lock is what bounds the throughput.)
+    const size_t rb = use_prior ? align_up((size_t)nstat * sizeof(visocu_range), 256) : 0;
+    const size_t h_mj = 0, h_rj = align_up(sizeof(MatchJob) * nb, 256);
+    const size_t h_rng = h_rj + (outliers ? align_up(sizeof(RoJob) * nb, 256) : 0);
+    const size_t hdr_bytes = h_rng + rb * nb;
+    const size_t o_words = hdr_bytes, words_bytes = (size_t)nb * 64;                  // 16 int32 per job
+    const size_t ostride = align_up((size_t)(maxq + 1) * 48, 256);
+    const size_t o_list = align_up(o_words + words_bytes, 256);                      // lists of the matching kernels
+    const size_t o_list2 = o_list + ostride * nb;                                    // survivors of the outlier removal
+    size_t off = o_list2 + (outliers ? ostride * nb : 0);
+    std::vector<size_t> o_res(nb), o_blk(nb), o_keep(nb), o_idx(nb), o_vert(nb);
+    for (int j = 0; j < nb; j++) {
+      const int nq = hj[j].nq;
       o_res[j] = off; off += align_up((size_t)(nq + 1) * 16, 256);
       o_blk[j] = off; off += align_up((size_t)(nq / CHUNK + 2) * 4, 256);
-      o_out[j] = off; off += align_up((size_t)(nq + 1) * 48, 256);
-      o_cnt[j] = off; off += 256;
       o_keep[j] = off; off += align_up((size_t)nq + 1, 256);
-      o_rng[j] = off; off += use_prior ? align_up((size_t)nstat * sizeof(visocu_range), 256) : 0;
+      if (outliers) {
+        o_idx[j] = off; off += align_up((size_t)(nq + 1) * 4, 256);
+        o_vert[j] = off; off += align_up((size_t)(nq + 1) * 4, 256);
+      }
     }
     int rc = visocu_ensure_scratch(ctx, off);
     if (rc) return rc;
-    size_t stage_bytes = align_up(sizeof(MatchJob) * nb, 256) + (use_prior ? (size_t)nb * align_up((size_t)nstat * sizeof(visocu_range), 256) : 0) + (size_t)nb * 4;
-    if ((rc = visocu_ensure_pinned(ctx, stage_bytes))) return rc;
+    const bool stage_lists = ostride * nb <= ((size_t)64 << 20);                     // else copy list by list to the caller
+    const size_t p_words = align_up(hdr_bytes, 256), p_lists = p_words + align_up(words_bytes, 256);
+    if ((rc = visocu_ensure_pinned(ctx, p_lists + (stage_lists ? ostride * nb : 0)))) return rc;
     uint8_t* sb = (uint8_t*)ctx->scratch;
     uint8_t* pin = (uint8_t*)ctx->pinned;
-    size_t pin_off = align_up(sizeof(MatchJob) * nb, 256);
     for (int j = 0; j < nb; j++) {
+      int32_t* words = (int32_t*)(sb + o_words) + 16 * j;
       hj[j].res = (int4*)(sb + o_res[j]); hj[j].blk = (int32_t*)(sb + o_blk[j]);
-      hj[j].out = (visocu_pmatch*)(sb + o_out[j]); hj[j].n_out = (int32_t*)(sb + o_cnt[j]);
+      hj[j].out = (visocu_pmatch*)(sb + o_list + ostride * j); hj[j].n_out = words + 8;
       hj[j].keep = sb + o_keep[j];
       hj[j].f = ctx->param.f; hj[j].cu = ctx->param.cu; hj[j].cv = ctx->param.cv; hj[j].base = ctx->param.base;
       hj[j].has_tr = (method == 2 && tr_delta && tr_delta[start + j]) ? 1 : 0;
       if (hj[j].has_tr) memcpy(hj[j].tr, tr_delta[start + j], sizeof hj[j].tr);
       if (use_prior) {
-        if (!ranges[start + j]) return visocu_set_error(ctx, VISOCU_EINVAL, "job %d has no ranges", start + j);
-        memcpy(pin + pin_off, ranges[start + j], (size_t)nstat * sizeof(visocu_range));
-        CU_COPY(ctx, sb + o_rng[j], pin + pin_off, (size_t)nstat * sizeof(visocu_range), cudaMemcpyHostToDevice);
-        pin_off += align_up((size_t)nstat * sizeof(visocu_range), 256);
-        hj[j].ranges = (const visocu_range*)(sb + o_rng[j]);
+        memcpy(pin + h_rng + rb * j, ranges[start + j], (size_t)nstat * sizeof(visocu_range));
+        hj[j].ranges = (const visocu_range*)(sb + h_rng + rb * j);
+      }
+      if (outliers) {
+        rj[j].in = hj[j].out; rj[j].keep_in = (refine == 2 && maxq > 0) ? hj[j].keep : nullptr; rj[j].n_in = hj[j].n_out;
+        rj[j].out = (visocu_pmatch*)(sb + o_list2 + ostride * j);
+        rj[j].result = words; rj[j].idx = (int32_t*)(sb + o_idx[j]); rj[j].vert = (int32_t*)(sb + o_vert[j]);
       }
     }
-    memcpy(pin, hj.data(), sizeof(MatchJob) * nb);
-    CU_COPY(ctx, sb, pin, sizeof(MatchJob) * nb, cudaMemcpyHostToDevice);
-    const MatchJob* dj = (const MatchJob*)sb;
-    int32_t* pin_cnt = (int32_t*)(pin + pin_off);
+    memcpy(pin + h_mj, hj.data(), sizeof(MatchJob) * nb);
+    if (outliers) memcpy(pin + h_rj, rj.data(), sizeof(RoJob) * nb);
+    CU_COPY(ctx, sb, pin, hdr_bytes, cudaMemcpyHostToDevice);
+    const MatchJob* dj = (const MatchJob*)(sb + h_mj);
     if (maxq > 0) {
       dim3 gm((maxq + MATCH_THREADS / G - 1) / (MATCH_THREADS / G), nb);
       k_match<<<gm, MATCH_THREADS, 0, ctx->stream>>>(g, dj, method, use_prior, ctx->d_stats);
@@ -585,20 +620,44 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
       k_refine<<<gr, 256, 0, ctx->stream>>>(g, dj, method, refine, nullptr, 0, nullptr);
       CU_LAUNCH_CHECK(ctx);
     }
-    for (int j = 0; j < nb; j++) CU_COPY(ctx, pin_cnt + j, hj[j].n_out, 4, cudaMemcpyDeviceToHost);
+    // Matcher::removeOutliers on the device: one CTA per list, reads the list (and the sub-pixel keep flags) where the
+    // kernels above left them and writes the survivors to the second list area
+    if (outliers && (rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, maxq))) return rc;
+    int32_t* pw = (int32_t*)(pin + p_words);
+    CU_COPY(ctx, pw, sb + o_words, words_bytes, cudaMemcpyDeviceToHost);
     CU_TRY(ctx, visocu_stream_wait(ctx));
+    int maxn = 0;
     for (int j = 0; j < nb; j++) {
-      const int n = pin_cnt[j];
+      const int n = outliers ? pw[16 * j] : pw[16 * j + 8];
       n_out[start + j] = n;
+      if (n > maxn) maxn = n;
       if (n > cap[start + j]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "job %d produced %d matches, room for %d", start + j, n, cap[start + j]);
-      if (n > 0) CU_COPY(ctx, out[start + j], hj[j].out, (size_t)n * 48, cudaMemcpyDeviceToHost);
+      if (outliers) {
+        const int status = pw[16 * j + 1];
+        outliers[start + j] = status == 0 ? 1 : 0;
+        if (status == 0 && n > 3) { for (int k = 0; k < 4; k++) ctx->ro_ns[k] += (uint64_t)pw[16 * j + 4 + k]; ctx->ro_jobs++; }
+        else if (status != 0) ctx->ro_declined++;
+      }
     }
-    std::vector<std::vector<uint8_t> > keep(refine == 2 ? nb : 0);
+    const uint8_t* lists = sb + (outliers ? o_list2 : o_list);
+    if (maxn > 0 && stage_lists) {
+      const size_t wbytes = (size_t)maxn * 48;
+      ctx->d2h_bytes += (uint64_t)wbytes * nb;
+      CU_TRY(ctx, cudaMemcpy2DAsync(pin + p_lists, wbytes, lists, ostride, wbytes, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (maxn > 0) {
+      for (int j = 0; j < nb; j++)
+        if (n_out[start + j] > 0) CU_COPY(ctx, out[start + j], lists + ostride * j, (size_t)n_out[start + j] * 48, cudaMemcpyDeviceToHost);
+    }
+    const bool host_keep = refine == 2 && !outliers;       // the device outlier pass applies the keep flags itself
+    std::vector<std::vector<uint8_t> > keep(host_keep ? nb : 0);
     for (int j = 0; j < (int)keep.size(); j++) {
       keep[j].resize((size_t)n_out[start + j] + 1);
       if (n_out[start + j] > 0) CU_COPY(ctx, keep[j].data(), hj[j].keep, (size_t)n_out[start + j], cudaMemcpyDeviceToHost);
     }
-    CU_TRY(ctx, visocu_stream_wait(ctx));
+    if (maxn > 0) CU_TRY(ctx, visocu_stream_wait(ctx));
+    if (maxn > 0 && stage_lists)
+      for (int j = 0; j < nb; j++)
+        if (n_out[start + j] > 0) memcpy(out[start + j], pin + p_lists + (size_t)maxn * 48 * j, (size_t)n_out[start + j] * 48);
     // sub-pixel refinement drops matches (matcher.cpp:1546-1577 `continue`): order-preserving compaction
     for (int j = 0; j < (int)keep.size(); j++) {
       visocu_pmatch* list = out[start + j];

@@ -56,6 +56,7 @@ struct visocu_ctx {
   // scratch for matching / ransac, grown on demand
   void* scratch = nullptr; size_t scratch_bytes = 0;
   void* pinned = nullptr;  size_t pinned_bytes = 0;
+  int32_t* counts_stage = nullptr;   // device: 4 int32 per frame of the last feature launch (one read-back per push)
   uint8_t* img_stage = nullptr; size_t img_stage_bytes = 0;   // contiguous landing area for host images
   uint64_t launches = 0;
   CUtensorMap tmap_img;              // TMA descriptor of the matching-resolution image planes of the pool
@@ -69,11 +70,13 @@ struct visocu_ctx {
   double filter_ms = 0; uint64_t filter_launches = 0, filter_frames = 0;
   uint64_t* d_stats = nullptr;       // [0] SAD candidates, [1] entries scanned
   uint64_t h_stats[2] = {0, 0};
+  uint64_t ro_ns[4] = {0, 0, 0, 0}, ro_jobs = 0, ro_declined = 0;   // device outlier removal: phase times (VISOCU_RO_STATS)
 };
 
 int visocu_set_error(visocu_ctx* ctx, int code, const char* fmt, ...);
 cudaError_t visocu_stream_wait(visocu_ctx* ctx);     // waits for the context's stream (yielding the CPU if ev_sync exists)
 int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes);
+bool visocu_uniform_carveout();                      // VISOCU_CARVEOUT=0 leaves the per-kernel default split
 int visocu_ensure_pinned(visocu_ctx* ctx, size_t bytes);
 
 #define CU_TRY(ctx, expr)                                                                        \

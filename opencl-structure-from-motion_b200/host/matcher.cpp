@@ -32,6 +32,12 @@ struct StageTimer {
     g_stage_calls[id]++;
   }
 };
+// Matcher::removeOutliers runs on the device behind the matching kernels unless VISOB_HOST_OUTLIERS=1 (the host
+// implementation in delaunay.cpp stays the path for lists the device declines: too long, or duplicate positions)
+bool device_outliers() {
+  static const bool on = [] { const char* e = getenv("VISOB_HOST_OUTLIERS"); return !(e && e[0] == '1'); }();
+  return on;
+}
 static thread_local int t_device = 0;
 void set_device(int device) { t_device = device; }
 int current_device() { return t_device; }
@@ -42,6 +48,7 @@ static_assert(sizeof(Matcher::range) == sizeof(visocu_range), "range layout");
 static_assert(sizeof(Matcher::parameters) == sizeof(visocu_params), "parameters layout");
 
 Matcher::Matcher(parameters param) : param(param), ctx(0), owns_ctx(true), slot_base(0), cfg_w(0), cfg_h(0), have_I1p(false), have_I1c(false), has_tr(false) {
+  ro_done[0] = ro_done[1] = false;
   margin = 5 + 1;
   if (param.half_resolution) this->param.match_radius /= 2;     // matcher.cpp:59-60
   device = visob::current_device();
@@ -170,8 +177,10 @@ bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_
   const visocu_range* rptr = reinterpret_cast<const visocu_range*>(ranges.data());
   int32_t cap = nq + 1, n = 0;
   const double* tptr = tr_rows;
+  int32_t done = 0;
   int rc = visocu_match(ctx, 1, &q, method, pass, use_prior ? 1 : 0, use_prior ? &rptr : 0, (has_tr && method == 2) ? &tptr : 0, refine,
-                        &optr, &cap, &n);
+                        &optr, &cap, &n, visob::device_outliers() ? &done : 0);
+  ro_done[pass] = done != 0;
   if (rc != VISOCU_OK) {
     std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
     out.clear();
@@ -232,10 +241,12 @@ int32_t Matcher::queryCount(int pass, int32_t method) const {
 
 // host stages between the two matching passes (matcher.cpp:223-226) and after the second (matcher.cpp:232)
 void Matcher::matchAfterPass1(int32_t method) {
-  removeOutliers(p_matched_1, method);
+  if (!ro_done[0]) removeOutliers(p_matched_1, method);
   computePriorStatistics(p_matched_1, method);
 }
-void Matcher::matchAfterPass2(int32_t method) { removeOutliers(p_matched_2, method); }
+void Matcher::matchAfterPass2(int32_t method) {
+  if (!ro_done[1]) removeOutliers(p_matched_2, method);
+}
 
 void Matcher::bucketFeatures(int32_t max_features, float bucket_width, float bucket_height) {
   float u_max = 0, v_max = 0;
@@ -366,14 +377,15 @@ void Matcher::removeOutliers(vector<p_match>& p_matched, int32_t method) {
   visob::delaunay_edges(x.data(), y.data(), n, edges);
   support.assign(n, 0);
   const float flow_tol = (float)param.outlier_flow_tolerance, disp_tol = (float)param.outlier_disp_tolerance;
+  // float arithmetic throughout, as in the reference (matcher.cpp:1273-1349: float flows, fabs on floats)
   auto edge_ok = [&](const p_match& a, const p_match& b) -> bool {
     if (method == 0) {
-      return fabs((a.u1c - a.u1p) - (b.u1c - b.u1p)) + fabs((a.v1c - a.v1p) - (b.v1c - b.v1p)) < flow_tol;
+      return fabsf((a.u1c - a.u1p) - (b.u1c - b.u1p)) + fabsf((a.v1c - a.v1p) - (b.v1c - b.v1p)) < flow_tol;
     } else if (method == 1) {
-      return fabs((a.u1c - a.u2c) - (b.u1c - b.u2c)) < disp_tol;
+      return fabsf((a.u1c - a.u2c) - (b.u1c - b.u2c)) < disp_tol;
     }
-    return fabs((a.u1p - a.u2p) - (b.u1p - b.u2p)) < disp_tol &&
-           fabs((a.u1c - a.u1p) - (b.u1c - b.u1p)) + fabs((a.v1c - a.v1p) - (b.v1c - b.v1p)) < flow_tol;
+    return fabsf((a.u1p - a.u2p) - (b.u1p - b.u2p)) < disp_tol &&
+           fabsf((a.u1c - a.u1p) - (b.u1c - b.u1p)) + fabsf((a.v1c - a.v1p) - (b.v1c - b.v1p)) < flow_tol;
   };
   // the reference votes per triangle edge (matcher.cpp:1259-1362): an edge shared by two triangles counts twice
   for (size_t e = 0; e + 2 < edges.size(); e += 3) {
@@ -455,7 +467,7 @@ bool MatcherBatch::matchPass(const vector<int32_t>& active, int pass, int32_t me
   vector<visocu_quad> quads(n);
   vector<visocu_pmatch*> outs(n);
   vector<const visocu_range*> rptr(n);
-  vector<int32_t> cap(n), cnt(n);
+  vector<int32_t> cap(n), cnt(n), done(n, 0);
   for (size_t k = 0; k < n; k++) {
     Matcher* m = seq[active[k]];
     vector<Matcher::p_match>& out = pass == 0 ? m->p_matched_1 : m->p_matched_2;
@@ -467,10 +479,11 @@ bool MatcherBatch::matchPass(const vector<int32_t>& active, int pass, int32_t me
     cap[k] = nq + 1;
   }
   const int rc = visocu_match(ctx, (int32_t)n, quads.data(), method, pass, use_prior ? 1 : 0, use_prior ? rptr.data() : 0, 0, refine,
-                              outs.data(), cap.data(), cnt.data());
+                              outs.data(), cap.data(), cnt.data(), visob::device_outliers() ? done.data() : 0);
   if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
   for (size_t k = 0; k < n; k++) {
     Matcher* m = seq[active[k]];
+    m->ro_done[pass] = rc == VISOCU_OK && done[k] != 0;
     (pass == 0 ? m->p_matched_1 : m->p_matched_2).resize(rc == VISOCU_OK ? cnt[k] : 0);
   }
   return rc == VISOCU_OK;

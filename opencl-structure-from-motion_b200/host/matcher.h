@@ -116,6 +116,7 @@ private:
   std::vector<p_match> p_matched_1, p_matched_2;
   std::vector<range> ranges;
   bool has_tr;
+  bool ro_done[2];                  // removeOutliers of the pass already ran on the device
   double tr_rows[12];
   struct random_data rnd_data;
   char rnd_state[128];

@@ -199,7 +199,7 @@ class Context:
         return out[:cnt.value].copy()
 
     # ---- matching
-    def match(self, quads, method, pass_, ranges=None, refine=False, tr_delta=None):
+    def match(self, quads, method, pass_, ranges=None, refine=False, tr_delta=None, outliers=False):
         """quads: list of (f1p, f2p, f1c, f2c).  ranges: list of (ub*vb) RANGE arrays or None.  Returns list of P_MATCH arrays."""
         nj = len(quads)
         q = np.zeros(nj, QUAD)
@@ -218,9 +218,21 @@ class Context:
         if tr_delta is not None:
             trs = [np.ascontiguousarray(np.asarray(t, np.float64)[:3, :4]) for t in tr_delta]
             tptr = (C.c_void_p * nj)(*[t.ctypes.data for t in trs])
+        done = np.zeros(nj, np.int32) if outliers else None
         self._ck(lib().visocu_match(self.h, nj, _p(q), method, pass_, int(ranges is not None), rptr, tptr, int(refine),
-                                    optr, _p(caps), _p(nout)), 'match')
-        return [outs[k][:nout[k]].copy() for k in range(nj)]
+                                    optr, _p(caps), _p(nout), _p(done)), 'match')
+        res = [outs[k][:nout[k]].copy() for k in range(nj)]
+        return (res, done) if outliers else res
+
+    def remove_outliers(self, lists, method):
+        """Matcher::removeOutliers on the device for a batch of match lists.  Returns (survivor lists, status array);
+        status 1 = not handled by the device path, list returned unchanged."""
+        nj = len(lists)
+        bufs = [np.array(l, dtype=P_MATCH, copy=True) for l in lists]
+        ptr = (C.c_void_p * nj)(*[b.ctypes.data for b in bufs])
+        n = np.array([len(b) for b in bufs], np.int32); nout = np.zeros(nj, np.int32); status = np.zeros(nj, np.int32)
+        self._ck(lib().visocu_remove_outliers(self.h, nj, method, ptr, _p(n), _p(nout), _p(status)), 'remove_outliers')
+        return [bufs[k][:nout[k]].copy() for k in range(nj)], status
 
     def refine(self, quad, method, matches, mode=1):
         q = np.zeros(1, QUAD); q[0] = tuple(quad)
