@@ -16,6 +16,7 @@ import argparse
 import ctypes as C
 import json
 import os
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')   # one CUDA stream per host worker: see csrc/ctx.cu, visocu_create
 import subprocess
 import sys
 import threading

@@ -4,6 +4,7 @@
 #include "visocu_internal.cuh"
 #include <cstdarg>
 #include <cstdio>
+#include <sched.h>
 #include <cstring>
 #include <cmath>
 #include <cstdlib>
@@ -20,10 +21,49 @@ int visocu_set_error(visocu_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
+// Host-side wait for the context's stream.  Several host threads share the GPU (one context each), and there may be more
+// of them than cores.  The default wait costs no driver call while it waits: a stream memory operation
+// (cuStreamWriteValue32) stores a sequence number into pinned host memory when the stream reaches it, and the thread
+// polls that word, yielding the core between polls - the driver's lock stays free for the threads that are launching
+// work, and a waiting thread does not keep a runnable one off its core.  VISOCU_WAIT=sync falls back to
+// cudaStreamSynchronize (spinning inside the driver), VISOCU_BLOCKING_SYNC=1 to a blocking event.
+namespace {
+typedef CUresult (*WriteValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+WriteValueFn write_value_fn() {
+  static WriteValueFn fn = [] {
+    const char* e = getenv("VISOCU_WAIT");
+    if (e && e[0] == 's') return (WriteValueFn) nullptr;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return (WriteValueFn) nullptr;
+    return (WriteValueFn)p;
+  }();
+  return fn;
+}
+}  // namespace
+
 cudaError_t visocu_stream_wait(visocu_ctx* ctx) {
-  if (!ctx->ev_sync) return cudaStreamSynchronize(ctx->stream);
-  cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
-  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_sync);
+  if (ctx->ev_sync) {
+    cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_sync);
+  }
+  WriteValueFn wv = write_value_fn();
+  if (wv && ctx->wait_flag) {
+    const uint32_t seq = ++ctx->wait_seq;
+    if (wv((CUstream)ctx->stream, (CUdeviceptr)(uintptr_t)ctx->wait_flag_dev, seq, 0) == CUDA_SUCCESS) {
+      volatile uint32_t* flag = ctx->wait_flag;
+      unsigned spins = 0;
+      while (*flag != seq) {
+        if ((++spins & 0x3FFF) == 0) {                 // now and then: did the stream die?
+          cudaError_t e = cudaStreamQuery(ctx->stream);
+          if (e != cudaSuccess && e != cudaErrorNotReady) return e;
+        }
+        sched_yield();
+      }
+      return cudaSuccess;
+    }
+  }
+  return cudaStreamSynchronize(ctx->stream);
 }
 
 extern "C" const char* visocu_last_error(const visocu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -31,6 +71,11 @@ extern "C" const char* visocu_last_error(const visocu_ctx* ctx) { return ctx ? c
 extern "C" int visocu_create(int device, visocu_ctx** out) {
   if (!out) return VISOCU_EINVAL;
   *out = nullptr;
+  // One context = one stream, and a process drives many of them (one per host worker).  With the default of 8 hardware
+  // work queues, streams share queues and a 1 ms outlier-removal kernel at the head of one stream stalls the kernels of
+  // its queue neighbours; 32 queues removed that (flow bench: 13.9 k -> 23.2 k pairs/s).  Only effective if set before
+  // the process initialises CUDA, hence also at the top of bench.py; an explicit user setting wins.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0)
@@ -54,6 +99,17 @@ extern "C" int visocu_create(int device, visocu_ctx** out) {
     return VISOCU_ECUDA;
   }
   cudaMemset(ctx->d_stats, 0, 2 * sizeof(uint64_t));
+  {
+    // completion word of visocu_stream_wait: pinned, mapped, written by the stream itself
+    void* flag = nullptr;
+    if (cudaHostAlloc(&flag, 64, cudaHostAllocMapped) == cudaSuccess) {
+      memset(flag, 0, 64);
+      void* dev = nullptr;
+      if (cudaHostGetDevicePointer(&dev, flag, 0) == cudaSuccess) { ctx->wait_flag = (volatile uint32_t*)flag; ctx->wait_flag_dev = dev; }
+      else cudaFreeHost(flag);
+    }
+    cudaGetLastError();
+  }
   if (const char* e = getenv("VISOCU_DBG")) ctx->dbg_flags = atoi(e);
   // VISOCU_BLOCKING_SYNC=1: waiting host threads sleep (for runs with more worker threads than cores)
   if (const char* e = getenv("VISOCU_BLOCKING_SYNC"))
@@ -72,14 +128,20 @@ extern "C" void visocu_destroy(visocu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  if (getenv("VISOCU_RO_STATS") && ctx->ro_jobs)
-    fprintf(stderr, "[outliers] %llu lists on the device (%llu declined), mean us: sort %.1f partition %.1f build %.1f vote %.1f\n",
-            (unsigned long long)ctx->ro_jobs, (unsigned long long)ctx->ro_declined, 1e-3 * ctx->ro_ns[0] / ctx->ro_jobs,
-            1e-3 * ctx->ro_ns[1] / ctx->ro_jobs, 1e-3 * ctx->ro_ns[2] / ctx->ro_jobs, 1e-3 * ctx->ro_ns[3] / ctx->ro_jobs);
+  if (getenv("VISOCU_RO_STATS") && (ctx->ro_jobs || ctx->ro_declined)) {
+    const double nj = ctx->ro_jobs ? (double)ctx->ro_jobs : 1.0;
+    fprintf(stderr, "[outliers] %llu lists on the device, mean us: sort %.1f partition %.1f build %.1f vote %.1f; declined %llu "
+            "(too long %llu, duplicates %llu, guard %llu; mean length %.0f)\n",
+            (unsigned long long)ctx->ro_jobs, 1e-3 * ctx->ro_ns[0] / nj, 1e-3 * ctx->ro_ns[1] / nj, 1e-3 * ctx->ro_ns[2] / nj,
+            1e-3 * ctx->ro_ns[3] / nj, (unsigned long long)ctx->ro_declined, (unsigned long long)ctx->ro_reason[1],
+            (unsigned long long)ctx->ro_reason[2], (unsigned long long)ctx->ro_reason[3],
+            ctx->ro_declined ? (double)ctx->ro_declined_n / (double)ctx->ro_declined : 0.0);
+  }
   free_pool(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->img_stage) cudaFree(ctx->img_stage);
   if (ctx->counts_stage) cudaFree(ctx->counts_stage);
+  if (ctx->wait_flag) cudaFreeHost((void*)ctx->wait_flag);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->pev0) cudaEventDestroy(ctx->pev0);

@@ -564,7 +564,10 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
     const size_t o_list = align_up(o_words + words_bytes, 256);                      // lists of the matching kernels
     const size_t o_list2 = o_list + ostride * nb;                                    // survivors of the outlier removal
     size_t off = o_list2 + (outliers ? ostride * nb : 0);
-    std::vector<size_t> o_res(nb), o_blk(nb), o_keep(nb), o_idx(nb), o_vert(nb);
+    std::vector<size_t> o_res(nb), o_blk(nb), o_keep(nb), o_idx(nb), o_vert(nb), o_hnd(nb), o_rep(nb);
+    const bool dedupe = outliers && method != 0;       // flow matching keeps one match per pixel (matcher.cpp:1036-1039)
+    const size_t kstride = (size_t)maxq + 1;             // words per job in the position buffer
+    size_t o_keys = 0;
     for (int j = 0; j < nb; j++) {
       const int nq = hj[j].nq;
       o_res[j] = off; off += align_up((size_t)(nq + 1) * 16, 256);
@@ -573,13 +576,17 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
       if (outliers) {
         o_idx[j] = off; off += align_up((size_t)(nq + 1) * 4, 256);
         o_vert[j] = off; off += align_up((size_t)(nq + 1) * 4, 256);
+        o_hnd[j] = off; off += align_up((size_t)(nq / 2 + 2) * 8, 256);
+        o_rep[j] = off; off += align_up((size_t)nq + 1, 256);
       }
     }
+    if (dedupe) { o_keys = off; off += align_up(kstride * 4 * nb, 256); }
     int rc = visocu_ensure_scratch(ctx, off);
     if (rc) return rc;
     const bool stage_lists = ostride * nb <= ((size_t)64 << 20);                     // else copy list by list to the caller
     const size_t p_words = align_up(hdr_bytes, 256), p_lists = p_words + align_up(words_bytes, 256);
-    if ((rc = visocu_ensure_pinned(ctx, p_lists + (stage_lists ? ostride * nb : 0)))) return rc;
+    const size_t p_keys = p_lists + (stage_lists ? ostride * nb : 0);
+    if ((rc = visocu_ensure_pinned(ctx, p_keys + (dedupe ? kstride * 5 * nb : 0)))) return rc;
     uint8_t* sb = (uint8_t*)ctx->scratch;
     uint8_t* pin = (uint8_t*)ctx->pinned;
     for (int j = 0; j < nb; j++) {
@@ -598,6 +605,7 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
         rj[j].in = hj[j].out; rj[j].keep_in = (refine == 2 && maxq > 0) ? hj[j].keep : nullptr; rj[j].n_in = hj[j].n_out;
         rj[j].out = (visocu_pmatch*)(sb + o_list2 + ostride * j);
         rj[j].result = words; rj[j].idx = (int32_t*)(sb + o_idx[j]); rj[j].vert = (int32_t*)(sb + o_vert[j]);
+        rj[j].hnd = (uint16_t*)(sb + o_hnd[j]); rj[j].rep = nullptr;
       }
     }
     memcpy(pin + h_mj, hj.data(), sizeof(MatchJob) * nb);
@@ -622,6 +630,28 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
     }
     // Matcher::removeOutliers on the device: one CTA per list, reads the list (and the sub-pixel keep flags) where the
     // kernels above left them and writes the survivors to the second list area
+    if (dedupe && maxq > 0) {
+      // Quad and stereo matching can put several matches on one pixel.  Which of them Triangle triangulates is decided
+      // by replaying its quicksort on the host (ro_resolve_duplicates): positions down, flags up, one round trip.
+      if ((rc = visocu_launch_outlier_keys(ctx, (const RoJob*)(sb + h_rj), nb, (uint32_t*)(sb + o_keys), (int)kstride))) return rc;
+      uint32_t* pk = (uint32_t*)(pin + p_keys);
+      uint8_t* prep = pin + p_keys + kstride * 4 * nb;
+      int32_t* pw0 = (int32_t*)(pin + p_words);
+      CU_COPY(ctx, pw0, sb + o_words, words_bytes, cudaMemcpyDeviceToHost);
+      CU_COPY(ctx, pk, sb + o_keys, kstride * 4 * nb, cudaMemcpyDeviceToHost);
+      CU_TRY(ctx, visocu_stream_wait(ctx));
+      bool any = false;
+      for (int j = 0; j < nb; j++) {
+        const int n = pw0[16 * j + 8];
+        if (n > 3 && n <= (int)kstride && ro_resolve_duplicates(pk + kstride * j, n, prep + kstride * j)) { rj[j].rep = sb + o_rep[j]; any = true; }
+      }
+      if (any) {
+        for (int j = 0; j < nb; j++)
+          if (rj[j].rep) CU_COPY(ctx, sb + o_rep[j], prep + kstride * j, (size_t)pw0[16 * j + 8], cudaMemcpyHostToDevice);
+        memcpy(pin + h_rj, rj.data(), sizeof(RoJob) * nb);
+        CU_COPY(ctx, sb + h_rj, pin + h_rj, sizeof(RoJob) * nb, cudaMemcpyHostToDevice);
+      }
+    }
     if (outliers && (rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, maxq))) return rc;
     int32_t* pw = (int32_t*)(pin + p_words);
     CU_COPY(ctx, pw, sb + o_words, words_bytes, cudaMemcpyDeviceToHost);
@@ -636,7 +666,7 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
         const int status = pw[16 * j + 1];
         outliers[start + j] = status == 0 ? 1 : 0;
         if (status == 0 && n > 3) { for (int k = 0; k < 4; k++) ctx->ro_ns[k] += (uint64_t)pw[16 * j + 4 + k]; ctx->ro_jobs++; }
-        else if (status != 0) ctx->ro_declined++;
+        else if (status != 0) { ctx->ro_declined++; ctx->ro_reason[status & 3]++; ctx->ro_declined_n += (uint64_t)pw[16 * j + 3]; }
       }
     }
     const uint8_t* lists = sb + (outliers ? o_list2 : o_list);

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -28,6 +29,11 @@ constexpr int RO_THREADS = 1024;        // with 64 registers each: the CTA owns 
                                         // warps compete with the single-threaded top merges for issue slots
 constexpr int NIL = 0xFFFF;
 constexpr uint16_t DEAD = 0xFFFF;
+
+__host__ __device__ inline int ro_edge_capacity(int n) { return (int)(3.04f * (float)n) + 64; }
+__host__ __device__ inline size_t ro_smem_bytes(int n) {
+  return (((size_t)12 * ro_edge_capacity(n) + 15) & ~(size_t)15) + (size_t)4 * n + 16;
+}
 
 struct Mesh {
   uint16_t *nx, *pv, *og;      // per half-edge: next / previous around the origin (counter-clockwise), origin vertex
@@ -43,26 +49,25 @@ struct Mesh {
   __device__ __forceinline__ int rprev(int e) const { return nx[e ^ 1]; }
   __device__ __forceinline__ int px(int v) const { return (int)(pt[v] & 0xFFFFu); }
   __device__ __forceinline__ int py(int v) const { return (int)(pt[v] >> 16); }
-  __device__ __forceinline__ bool tick() {           // false once the guard is used up or another thread failed
-    if (--guard < 0) *fail = 1;
-    return *fail == 0;
-  }
-  // > 0 iff a, b, c make a left turn
-  __device__ __forceinline__ long long ccw(int a, int b, int c) const {
+  __device__ __forceinline__ bool tick() { return --guard >= 0; }    // false once this thread's loop budget is used up
+  // Predicates in 32-bit arithmetic with 64-bit products only where needed: exact for coordinates below 8192 (checked
+  // when the keys are built; larger images go to the host).  > 0 iff a, b, c make a left turn
+  __device__ __forceinline__ int ccw(int a, int b, int c) const {
     const uint32_t A = pt[a], B = pt[b], C = pt[c];
-    const long long ax = (int)(A & 0xFFFF) - (int)(C & 0xFFFF), ay = (int)(A >> 16) - (int)(C >> 16);
-    const long long bx = (int)(B & 0xFFFF) - (int)(C & 0xFFFF), by = (int)(B >> 16) - (int)(C >> 16);
-    return ax * by - ay * bx;
+    const int cx = (int)(C & 0xFFFF), cy = (int)(C >> 16);
+    const int ax = (int)(A & 0xFFFF) - cx, ay = (int)(A >> 16) - cy;
+    const int bx = (int)(B & 0xFFFF) - cx, by = (int)(B >> 16) - cy;
+    return ax * by - ay * bx;                                        // |.| < 2^27
   }
   // > 0 iff d lies strictly inside the circle through a, b, c (counter-clockwise)
   __device__ __forceinline__ long long incircle(int a, int b, int c, int d) const {
     const uint32_t A = pt[a], B = pt[b], C = pt[c], D = pt[d];
     const int dx = (int)(D & 0xFFFF), dy = (int)(D >> 16);
-    const long long adx = (int)(A & 0xFFFF) - dx, ady = (int)(A >> 16) - dy;
-    const long long bdx = (int)(B & 0xFFFF) - dx, bdy = (int)(B >> 16) - dy;
-    const long long cdx = (int)(C & 0xFFFF) - dx, cdy = (int)(C >> 16) - dy;
-    const long long al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
-    return al * (bdx * cdy - cdx * bdy) + bl * (cdx * ady - adx * cdy) + cl * (adx * bdy - bdx * ady);
+    const int adx = (int)(A & 0xFFFF) - dx, ady = (int)(A >> 16) - dy;
+    const int bdx = (int)(B & 0xFFFF) - dx, bdy = (int)(B >> 16) - dy;
+    const int cdx = (int)(C & 0xFFFF) - dx, cdy = (int)(C >> 16) - dy;
+    const int al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;     // < 2^27
+    return (long long)al * (bdx * cdy - cdx * bdy) + (long long)bl * (cdx * ady - adx * cdy) + (long long)cl * (adx * bdy - bdx * ady);
   }
 };
 
@@ -177,7 +182,7 @@ __device__ Handles leaf(Mesh& m, FreeList& fl, int v, int n) {
   const int a = make_edge(m, fl, v, v + 1);
   const int b = make_edge(m, fl, v + 1, v + 2);
   insert_after(m, b, a ^ 1);
-  const long long area = m.ccw(v, v + 1, v + 2);
+  const int area = m.ccw(v, v + 1, v + 2);
   if (area == 0) return Handles{a, b ^ 1};
   const int c = connect(m, fl, b, a);
   if (area > 0) return Handles{a, b ^ 1};
@@ -248,14 +253,16 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   if (tid == 0) { s_bump = 0; s_fail = 0; s_flag = 0; }
   __syncthreads();
 
-  // capacity of this launch's shared memory: 12 E bytes of half-edges (E = 3.3 n + 64 edges), 4 n of points, 4 n of
-  // per-subtree handles and free lists (indexed by first vertex / 2; later the vote counters)
-  const int ecap = (int)(3.3f * (float)n) + 64;
-  const size_t need = (((size_t)12 * ecap + 15) & ~(size_t)15) + (size_t)4 * n + (size_t)8 * (n / 2 + 2) + 16;
+  // capacity of this launch's shared memory: 12 E bytes of half-edges and 4 n of points.  A triangulation of n points
+  // has fewer than 3 n edges and the free lists recycle every deleted one, so E = 3.04 n + 64 is enough in practice
+  // (measured peak 2.98 n); running out trips the guard and hands the list to the host.
+  const int ecap = ro_edge_capacity(n);
+  const size_t need = ro_smem_bytes(n);
+  const int nl = n;                                  // list length; n becomes the number of mesh vertices (distinct positions)
   if (n <= 3 || n > 0x7FF0 || need > (size_t)smem_bytes) {
     // nothing to vote on (matcher.cpp:1210-1211), or too large for the device path: hand the list over unchanged
     copy_records(J.out, J.in, src, n);
-    if (tid == 0) { J.result[0] = n; J.result[1] = n <= 3 ? 0 : 1; J.result[2] = 0; }
+    if (tid == 0) { J.result[0] = n; J.result[1] = n <= 3 ? 0 : 1; J.result[2] = 0; J.result[3] = n; }
     return;
   }
 
@@ -264,7 +271,8 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   uint16_t* he_pv = he_nx + 2 * ecap;
   uint16_t* he_og = he_pv + 2 * ecap;
   uint32_t* pts = (uint32_t*)(smem + (((size_t)12 * ecap + 15) & ~(size_t)15));
-  uint16_t* h_l = (uint16_t*)(pts + n);
+  // hull handles and free lists of the subtrees (indexed by first vertex / 2) are touched twice per merge: global scratch
+  uint16_t* h_l = J.hnd;
   uint16_t* h_r = h_l + (n / 2 + 2);
   uint16_t* f_h = h_r + (n / 2 + 2);
   uint16_t* f_t = f_h + (n / 2 + 2);
@@ -299,28 +307,46 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   };
 
   // ---- 1. order by (x, y); positions are the truncated coordinates in the current left image (matcher.cpp:1230-1233)
+  // (records the duplicate resolution excluded get the padding key: they are no vertices, collect no votes and drop out)
+  if (tid == 0) s_more = 0;
   for (int i = tid; i < npad; i += RO_THREADS) {
     unsigned long long key = ~0ull;
-    if (i < n) {
+    if (i < nl && (!J.rep || J.rep[src[i]])) {
       const visocu_pmatch& r = J.in[src[i]];
       const int x = (int)r.u1c, y = (int)r.v1c;
-      if (x < 0 || y < 0 || x > 0xFFFF || y > 0xFFFF) s_flag = 1;
+      if (x < 0 || y < 0 || x > 8191 || y > 8191) s_fail = 1;        // range of the 32-bit predicates
       key = ((unsigned long long)(unsigned)x << 40) | ((unsigned long long)(unsigned)y << 16) | (unsigned)i;
     }
     keys[i] = key;
   }
   __syncthreads();
   bitonic();
-  for (int i = tid; i < n; i += RO_THREADS) {
+  for (int i = tid; i < npad; i += RO_THREADS)
+    if (keys[i] != ~0ull && (i + 1 == npad || keys[i + 1] == ~0ull)) s_more = i + 1;     // number of vertices
+  __syncthreads();
+  for (int i = tid; i < s_more; i += RO_THREADS) {
     const unsigned long long key = keys[i];
-    if (i > 0 && (keys[i - 1] >> 16) == (key >> 16)) s_flag = 1;           // two matches on one pixel: Triangle's
-    ax[i] = (uint16_t)(key >> 40); ay[i] = (uint16_t)(key >> 16);          // choice depends on its quicksort -> host
+    if (i > 0 && (keys[i - 1] >> 16) == (key >> 16)) s_flag = 1;           // two vertices on one pixel
+    ax[i] = (uint16_t)(key >> 40); ay[i] = (uint16_t)(key >> 16);
     ain[i] = (uint16_t)key;
   }
   __syncthreads();
+  if (s_fail) {
+    copy_records(J.out, J.in, src, nl);
+    if (tid == 0) { J.result[0] = nl; J.result[1] = 1; J.result[2] = 0; J.result[3] = nl; }
+    return;
+  }
   if (s_flag) {
-    copy_records(J.out, J.in, src, n);
-    if (tid == 0) { J.result[0] = n; J.result[1] = 1; J.result[2] = 0; }
+    // Two vertices on one pixel: the caller did not resolve the duplicates (ro_resolve_duplicates) - Triangle's choice
+    // among them depends on its randomised quicksort, which is replayed on the host, not here.
+    copy_records(J.out, J.in, src, nl);
+    if (tid == 0) { J.result[0] = nl; J.result[1] = 2; J.result[2] = 0; J.result[3] = nl; }
+    return;
+  }
+  n = s_more;                                        // number of vertices (records that take part)
+  if (n <= 3) {
+    copy_records(J.out, J.in, src, nl);
+    if (tid == 0) { J.result[0] = nl; J.result[1] = 3; J.result[2] = 0; J.result[3] = nl; }
     return;
   }
   for (int i = tid; i < npad; i += RO_THREADS)
@@ -400,9 +426,12 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   Mesh m;
   m.nx = he_nx; m.pv = he_pv; m.og = he_og; m.pt = pts; m.bump = &s_bump; m.ecap = ecap; m.fail = &s_fail;
   m.guard = 64 * ecap;
+  unsigned long long t_level = now();
   for (int d = maxdepth; d >= 0; d--) {
     {
-      for (int j = tid; j < (1 << d); j += RO_THREADS) {
+      // Threads of a warp that run different merges take turns (the merges diverge completely), so the subtrees of a
+      // level are dealt to the warps first: 32 or fewer subtrees run on 32 different warps, one lane each.
+      for (int j = (tid & 31) * (RO_THREADS / 32) + (tid >> 5); j < (1 << d); j += RO_THREADS) {
         int lo = 0, sz = n;
         bool exists = true;
         for (int t = d - 1; t >= 0; t--) {
@@ -425,16 +454,19 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
           }
           h = merge(m, fl, Handles{h_l[sl], h_r[sl]}, Handles{h_l[sr], h_r[sr]}, d & 1);
         }
+        if (m.guard < 0) s_fail = 1;
         h_l[lo >> 1] = (uint16_t)h.ldo; h_r[lo >> 1] = (uint16_t)h.rdo;
         f_h[lo >> 1] = (uint16_t)fl.head; f_t[lo >> 1] = (uint16_t)fl.tail;
       }
     }
     __syncthreads();
+    if (tid == 0 && d < 7) { const unsigned long long t = now(); J.result[9 + d] = (int32_t)(t - t_level); t_level = t; }
+    else if (tid == 0) t_level = now();
     if (s_fail) break;
   }
   if (s_fail) {
-    copy_records(J.out, J.in, src, n);
-    if (tid == 0) { J.result[0] = n; J.result[1] = 1; J.result[2] = s_bump; }
+    copy_records(J.out, J.in, src, nl);
+    if (tid == 0) { J.result[0] = nl; J.result[1] = 3; J.result[2] = s_bump; J.result[3] = nl; }
     return;
   }
 
@@ -448,13 +480,13 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   }
   __syncthreads();
   if (s_fail) {
-    copy_records(J.out, J.in, src, n);
-    if (tid == 0) { J.result[0] = n; J.result[1] = 1; J.result[2] = s_bump; }
+    copy_records(J.out, J.in, src, nl);
+    if (tid == 0) { J.result[0] = nl; J.result[1] = 3; J.result[2] = s_bump; J.result[3] = nl; }
     return;
   }
-  // one vote counter per list position, where the handles were: 4 arrays of (n / 2 + 2) 16-bit entries >= n words
-  unsigned int* support = (unsigned int*)h_l;
-  for (int i = tid; i < n; i += RO_THREADS) support[i] = 0;
+  // one vote counter per list position; the ring pointers of the mesh are no longer needed, the counters take their place
+  unsigned int* support = (unsigned int*)he_nx;
+  for (int i = tid; i < nl; i += RO_THREADS) support[i] = 0;
   __syncthreads();
   const int nedge = min(s_bump, ecap);
   for (int k = tid; k < nedge; k += RO_THREADS) {
@@ -471,8 +503,8 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   }
   __syncthreads();
   {
-    const int per = (n + RO_THREADS - 1) / RO_THREADS;
-    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
+    const int per = (nl + RO_THREADS - 1) / RO_THREADS;
+    const int i0 = min(tid * per, nl), i1 = min(i0 + per, nl);
     int cnt = 0;
     for (int i = i0; i < i1; i++) cnt += support[i] >= 4u ? 1 : 0;
     int total;
@@ -484,7 +516,7 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
     __syncthreads();
     copy_records(J.out, J.in, kept, total);
     if (tid == 0) {
-      J.result[0] = total; J.result[1] = 0; J.result[2] = s_bump;
+      J.result[0] = total; J.result[1] = 0; J.result[2] = s_bump; J.result[3] = nl;
       // phase times in nanoseconds (sort, partition, build, vote + compaction): read by profiles/profile_outliers.py
       const unsigned long long t_end = now();
       J.result[4] = (int32_t)(t_sorted - t_start); J.result[5] = (int32_t)(t_part - t_sorted);
@@ -493,12 +525,26 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   }
 }
 
+// positions of all records of a list for the host-side duplicate resolution
+__global__ void k_outlier_keys(const RoJob* __restrict__ jobs, uint32_t* keys, int stride) {
+  const RoJob J = jobs[blockIdx.y];
+  const int n = *J.n_in;
+  uint32_t* out = keys + (size_t)blockIdx.y * stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t k = 0xFFFFFFFFu;
+    if (!J.keep_in || J.keep_in[i]) {
+      const int x = (int)J.in[i].u1c, y = (int)J.in[i].v1c;
+      if (x >= 0 && y >= 0 && x <= 0xFFFF && y <= 0xFFFF) k = ((uint32_t)x << 16) | (uint32_t)y;
+    }
+    out[i] = k;
+  }
+}
+
 }  // namespace
 
 int visocu_launch_remove_outliers(visocu_ctx* ctx, const RoJob* jobs_dev, int n_jobs, int method, int max_records) {
   // shared memory for the largest list of the launch, at most the 227 KB a CTA can have
-  const int ecap = (int)(3.3f * (float)max_records) + 64;
-  size_t smem = (((size_t)12 * ecap + 15) & ~(size_t)15) + (size_t)4 * max_records + (size_t)8 * (max_records / 2 + 2) + 16;
+  size_t smem = ro_smem_bytes(max_records);
   const size_t smem_max = 227 * 1024 - 256;          // the kernel also has a few static shared variables
   if (smem > smem_max) smem = smem_max;
   if (smem < 16 * 1024) smem = 16 * 1024;
@@ -527,7 +573,8 @@ extern "C" int visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t m
   if (method < 0 || method > 2) return visocu_set_error(ctx, VISOCU_EINVAL, "method %d not supported", method);
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   std::vector<RoJob> hj(n_jobs);
-  std::vector<size_t> o_in(n_jobs), o_out(n_jobs), o_idx(n_jobs), o_vert(n_jobs), o_res(n_jobs);
+  std::vector<size_t> o_in(n_jobs), o_out(n_jobs), o_idx(n_jobs), o_vert(n_jobs), o_res(n_jobs), o_hnd(n_jobs), o_rep(n_jobs);
+  std::vector<std::vector<uint8_t> > reps(n_jobs);
   size_t off = align_up(sizeof(RoJob) * n_jobs, 256);
   int maxn = 0;
   for (int j = 0; j < n_jobs; j++) {
@@ -538,34 +585,113 @@ extern "C" int visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t m
     o_out[j] = off; off += align_up(cnt * 48, 256);
     o_idx[j] = off; off += align_up(cnt * 4, 256);
     o_vert[j] = off; off += align_up(cnt * 4, 256);
+    o_hnd[j] = off; off += align_up((cnt / 2 + 2) * 8, 256);
+    o_rep[j] = off; off += align_up(cnt, 256);
     o_res[j] = off; off += 256;
   }
   int rc = visocu_ensure_scratch(ctx, off);
   if (rc) return rc;
-  if ((rc = visocu_ensure_pinned(ctx, align_up(sizeof(RoJob) * n_jobs, 256) + (size_t)n_jobs * 32))) return rc;
+  if ((rc = visocu_ensure_pinned(ctx, align_up(sizeof(RoJob) * n_jobs, 256) + (size_t)n_jobs * 64))) return rc;
   uint8_t* sb = (uint8_t*)ctx->scratch;
   uint8_t* pin = (uint8_t*)ctx->pinned;
   for (int j = 0; j < n_jobs; j++) {
     RoJob& J = hj[j];
     J.in = (const visocu_pmatch*)(sb + o_in[j]); J.keep_in = nullptr; J.out = (visocu_pmatch*)(sb + o_out[j]);
-    J.result = (int32_t*)(sb + o_res[j]); J.n_in = J.result + 8;
-    J.idx = (int32_t*)(sb + o_idx[j]); J.vert = (int32_t*)(sb + o_vert[j]);
+    J.result = (int32_t*)(sb + o_res[j]); J.n_in = J.result + 8;   // [9..15]: times of the top merge levels
+    J.idx = (int32_t*)(sb + o_idx[j]); J.vert = (int32_t*)(sb + o_vert[j]); J.hnd = (uint16_t*)(sb + o_hnd[j]);
     if (n[j] > 0) CU_COPY(ctx, sb + o_in[j], inout[j], (size_t)n[j] * 48, cudaMemcpyHostToDevice);
+    J.rep = nullptr;
+    if (n[j] > 3) {
+      std::vector<uint32_t> keys((size_t)n[j]);
+      for (int i = 0; i < n[j]; i++) {
+        const int x = (int)inout[j][i].u1c, y = (int)inout[j][i].v1c;
+        keys[i] = (x >= 0 && y >= 0 && x <= 0xFFFF && y <= 0xFFFF) ? ((uint32_t)x << 16) | (uint32_t)y : 0xFFFFFFFFu;
+      }
+      reps[j].resize((size_t)n[j]);
+      if (ro_resolve_duplicates(keys.data(), n[j], reps[j].data())) {
+        CU_COPY(ctx, sb + o_rep[j], reps[j].data(), (size_t)n[j], cudaMemcpyHostToDevice);
+        J.rep = sb + o_rep[j];
+      }
+    }
     CU_COPY(ctx, (void*)J.n_in, &n[j], 4, cudaMemcpyHostToDevice);
   }
   memcpy(pin, hj.data(), sizeof(RoJob) * n_jobs);
   CU_COPY(ctx, sb, pin, sizeof(RoJob) * n_jobs, cudaMemcpyHostToDevice);
   if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)sb, n_jobs, method, maxn))) return rc;
   int32_t* pin_res = (int32_t*)(pin + align_up(sizeof(RoJob) * n_jobs, 256));
-  for (int j = 0; j < n_jobs; j++) CU_COPY(ctx, pin_res + 8 * j, hj[j].result, 32, cudaMemcpyDeviceToHost);
+  for (int j = 0; j < n_jobs; j++) CU_COPY(ctx, pin_res + 16 * j, hj[j].result, 64, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, visocu_stream_wait(ctx));
   for (int j = 0; j < n_jobs; j++) {
-    n_out[j] = pin_res[8 * j]; status[j] = pin_res[8 * j + 1];
+    n_out[j] = pin_res[16 * j]; status[j] = pin_res[16 * j + 1];
     if (getenv("VISOCU_RO_STATS") && j == 0)
       fprintf(stderr, "[outliers] n=%d kept=%d status=%d edges=%d (%.2f n) ns: sort %d partition %d build %d vote %d\n", n[j], pin_res[0], pin_res[1],
-              pin_res[2], n[j] ? (double)pin_res[2] / n[j] : 0.0, pin_res[4], pin_res[5], pin_res[6], pin_res[7]);
+              pin_res[2], n[j] ? (double)pin_res[2] / n[j] : 0.0, pin_res[4], pin_res[5], pin_res[6], pin_res[7]),
+      fprintf(stderr, "[outliers] merge levels 0..6 (ns): %d %d %d %d %d %d %d\n", pin_res[9], pin_res[10], pin_res[11], pin_res[12], pin_res[13], pin_res[14], pin_res[15]);
     if (status[j] == 0 && n_out[j] > 0) CU_COPY(ctx, inout[j], hj[j].out, (size_t)n_out[j] * 48, cudaMemcpyDeviceToHost);
   }
   CU_TRY(ctx, visocu_stream_wait(ctx));
   return VISOCU_OK;
+}
+
+int visocu_launch_outlier_keys(visocu_ctx* ctx, const RoJob* jobs_dev, int n_jobs, uint32_t* keys_dev, int stride) {
+  int gx = (stride + 255) / 256; if (gx > 64) gx = 64;
+  k_outlier_keys<<<dim3(gx, n_jobs), 256, 0, ctx->stream>>>(jobs_dev, keys_dev, stride);
+  CU_LAUNCH_CHECK(ctx);
+  return VISOCU_OK;
+}
+
+// Triangle's vertexsort (a randomised quicksort: Hoare partition, pivot index from x' = (1366 x + 150889) mod 714025
+// starting at 1, scaled to the subarray length) replayed on the positions in list order; the first of every run of equal
+// positions is the point Triangle triangulates, the others it ignores (they collect no votes and are removed).
+bool ro_resolve_duplicates(const uint32_t* keys, int n_records, uint8_t* rep) {
+  static thread_local std::vector<uint32_t> kk, seen_words;
+  static thread_local std::vector<int32_t> a, rec;
+  kk.clear(); rec.clear();
+  for (int i = 0; i < n_records; i++)
+    if (keys[i] != 0xFFFFFFFFu) { kk.push_back(keys[i]); rec.push_back(i); }
+  const int n = (int)kk.size();
+  // any position taken twice?  (open-addressing hash set, a few n entries: stays in the cache)
+  size_t cap = 64;
+  while (cap < (size_t)4 * n) cap <<= 1;
+  seen_words.assign(cap, 0xFFFFFFFFu);
+  bool dup = false;
+  for (int i = 0; i < n && !dup; i++) {
+    const uint32_t k = kk[i];
+    size_t h = ((size_t)k * 2654435761u) & (cap - 1);
+    while (seen_words[h] != 0xFFFFFFFFu) {
+      if (seen_words[h] == k) { dup = true; break; }
+      h = (h + 1) & (cap - 1);
+    }
+    seen_words[h] = k;
+  }
+  if (!dup) return false;
+  a.resize(n);
+  for (int i = 0; i < n; i++) a[i] = i;
+  unsigned seed = 1;
+  std::vector<std::pair<int, int> > stack;
+  stack.push_back(std::make_pair(0, n));
+  while (!stack.empty()) {
+    const int lo = stack.back().first, len = stack.back().second;
+    stack.pop_back();
+    if (len < 2) continue;
+    int32_t* v = a.data() + lo;
+    if (len == 2) {
+      if (kk[v[0]] > kk[v[1]]) std::swap(v[0], v[1]);
+      continue;
+    }
+    seed = (seed * 1366u + 150889u) % 714025u;
+    const uint32_t pkey = kk[v[seed / (714025u / (unsigned)len + 1u)]];
+    int left = -1, right = len;
+    while (left < right) {
+      do { left++; } while (left <= right && kk[v[left]] < pkey);
+      do { right--; } while (left <= right && kk[v[right]] > pkey);
+      if (left < right) std::swap(v[left], v[right]);
+    }
+    if (right < len - 2) stack.push_back(std::make_pair(lo + right + 1, len - right - 1));    // taken second
+    if (left > 1) stack.push_back(std::make_pair(lo, left));                                   // taken first
+  }
+  for (int i = 0; i < n_records; i++) rep[i] = 0;
+  for (int i = 0; i < n; i++)
+    if (i == 0 || kk[a[i]] != kk[a[i - 1]]) rep[rec[a[i]]] = 1;
+  return true;
 }

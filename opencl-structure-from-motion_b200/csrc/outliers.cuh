@@ -7,11 +7,21 @@ struct RoJob {
   const uint8_t* keep_in;      // flags of the sub-pixel refinement (0 = dropped), or null
   const int32_t* n_in;         // number of records in `in` (device counter written by the emit kernel)
   visocu_pmatch* out;          // survivors, order preserved
-  int32_t* result;             // [0] records in out, [1] status: 0 = outliers removed, 1 = list unchanged, host must vote
+  int32_t* result;             // [0] records in out, [1] status: 0 = outliers removed, else list unchanged and the host must
+                               //     vote (1 = too long for shared memory, 2 = duplicate positions, 3 = internal guard)
                                // [2] edges allocated (diagnostics)
   int32_t* idx;                // scratch, n_in entries: list position -> record index
   int32_t* vert;               // scratch, n_in entries: mesh vertex -> list position
+  const uint8_t* rep;          // optional, per record: 0 = duplicate position that Triangle ignores (ro_resolve_duplicates)
+  uint16_t* hnd;               // scratch, 4 * (n_in / 2 + 2) entries: hull handles and free lists of the subtrees
 };
 
+// Positions of all records of a list as x << 16 | y (0xFFFFFFFF for records dropped by the sub-pixel refinement), for the
+// host-side duplicate resolution below.  keys_dev: n_jobs rows of `stride` words.
+int visocu_launch_outlier_keys(visocu_ctx* ctx, const RoJob* jobs_dev, int n_jobs, uint32_t* keys_dev, int stride);
+// Several matches on one pixel (quad and stereo matching): Triangle triangulates one point per position, the one its
+// randomised quicksort leaves first among the equal ones.  Replays that sort on the host (microseconds) and marks the
+// records that take part: rep[i] = 1.  Returns false, leaving rep untouched, if all positions are distinct.
+bool ro_resolve_duplicates(const uint32_t* keys, int n_records, uint8_t* rep);
 // launches one CTA per job on the context's stream; jobs is a device array
 int visocu_launch_remove_outliers(visocu_ctx* ctx, const RoJob* jobs_dev, int n_jobs, int method, int max_records);

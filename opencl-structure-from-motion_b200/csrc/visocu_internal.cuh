@@ -41,6 +41,7 @@ struct visocu_ctx {
   char name[64] = {0};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  volatile uint32_t* wait_flag = nullptr; void* wait_flag_dev = nullptr; uint32_t wait_seq = 0;   // see visocu_stream_wait
   cudaEvent_t ev_sync = nullptr;     // blocking-sync event: host threads sleep instead of spinning while the GPU works
   std::string err;
   bool configured = false;
@@ -70,7 +71,7 @@ struct visocu_ctx {
   double filter_ms = 0; uint64_t filter_launches = 0, filter_frames = 0;
   uint64_t* d_stats = nullptr;       // [0] SAD candidates, [1] entries scanned
   uint64_t h_stats[2] = {0, 0};
-  uint64_t ro_ns[4] = {0, 0, 0, 0}, ro_jobs = 0, ro_declined = 0;   // device outlier removal: phase times (VISOCU_RO_STATS)
+  uint64_t ro_ns[4] = {0, 0, 0, 0}, ro_jobs = 0, ro_declined = 0, ro_reason[4] = {0, 0, 0, 0}, ro_declined_n = 0;   // device outlier removal: phase times (VISOCU_RO_STATS)
 };
 
 int visocu_set_error(visocu_ctx* ctx, int code, const char* fmt, ...);

@@ -83,11 +83,20 @@ def padded(img):
 class RefLib:
     """The reference itself.  variant: '' (g++ default FMA contraction) or 'nofma' (-ffp-contract=off)."""
 
-    def __init__(self, variant=''):
+    def __init__(self, variant='', fresh=False):
         name = 'libvisoref%s.so' % ('_' + variant if variant else '')
         path = os.path.join(HERE, '_ref', name)
         if not os.path.exists(path):
             raise FileNotFoundError(path + ' (run `make -C oracle ref` where /root/reference exists)')
+        if fresh:
+            # The reference keeps process-wide state (the function-static sample generator of viso.cpp:88): a test
+            # that needs it in its initial state loads a private copy of the library, which has its own statics.
+            import shutil
+            import tempfile
+            self._tmp = tempfile.NamedTemporaryFile(suffix='.so', delete=False)
+            self._tmp.close()
+            shutil.copyfile(path, self._tmp.name)
+            path = self._tmp.name
         self.lib = L = C.CDLL(path)
         L.ref_build_info.restype = C.c_char_p
         L.ref_matcher_create.restype = C.c_void_p

@@ -103,10 +103,11 @@ def _mono_params(lib, bucket_max):
     return pyref.MonoParams(match=pyref.MatcherParams(), **kw), H.MonoParams(match=V.Params(), **kw)
 
 
-def test_mono_odometry_sequence(ref):
+def test_mono_odometry_sequence():
     """VisualOdometryMono::process over a short corridor drive.  Both sides draw the RANSAC samples from a fresh
     std::default_random_engine(71) and bucket with rand() after srand(0), so the sample tables coincide as long as
     the match lists do.  Tolerances: rotation entries 1e-6 absolute, translation 1e-6 relative."""
+    ref = pyref.RefLib(fresh=True)                    # own copy: the sample generator is process-wide state (viso.cpp:88)
     seq = synth.corridor_sequence(4, seed=1234)
     rp, hp = _mono_params(ref, 2)
     # rand() is process-wide state: run the two implementations one after the other, each from its own srand(0)
@@ -249,10 +250,11 @@ def test_quad_matching_with_motion_prediction(ref_nofma):
     assert got.tobytes() == want.tobytes()
 
 
-def test_stereo_odometry_sequence(ref_nofma):
+def test_stereo_odometry_sequence():
     """VisualOdometryStereo::process over a short stereo corridor drive: quad matching with motion prediction from the
     second pair on, 3-point RANSAC + Gauss-Newton on the host.  Same sample stream (fresh engine(71) on both sides),
     same matches -> same inliers; pose within 1e-6 (rotation entries absolute, translation relative)."""
+    ref_nofma = pyref.RefLib('nofma', fresh=True)     # own copy: the sample generator is process-wide state (viso.cpp:88)
     frames = [synth.corridor_stereo_frame(k, seed=1234) for k in range(4)]
     kw = dict(f=synth.KITTI_F, cu=synth.KITTI_CU, cv=synth.KITTI_CV, base=0.54)
     rp = pyref.StereoParams(match=pyref.MatcherParams(), **kw); hp = H.StereoParams(match=V.Params(), **kw)
@@ -278,10 +280,12 @@ def test_stereo_odometry_sequence(ref_nofma):
         assert abs(abs(Th[2, 3]) - 0.8) < 0.05                      # 0.8 m forward per frame, metric thanks to the baseline
 
 
-def test_structure_from_motion_facade(ref):
+def test_structure_from_motion_facade():
     """StructureFromMotion::update (sfm.hh:46-77): odometry, pose accumulation, replace-on-failure and track-based
     reconstruction.  The reference facade itself needs the OpenCL headers, so its few lines are restated here on top of
-    the reference's own VisualOdometryMono and Reconstruction objects."""
+    the reference's own VisualOdometryMono and Reconstruction objects (a private copy of the library: the sample
+    generator of the shared one has been advanced by the odometry test)."""
+    ref = pyref.RefLib(fresh=True)
     seq = synth.corridor_sequence(7, seed=1234)
     rp, hp = _mono_params(ref, 2)
     rv = ref.mono(rp); rr = ref.reconstruction()
