@@ -244,10 +244,11 @@ def run_ours(args, rank, world, local_rank):
         clocks = sampler.stop() if sampler else None
         barrier()
         l1 = runner.launches(); b1 = runner.transfer_bytes()
+        ro = runner.outlier_stats()
         stages = {k: round(1e3 * v[0] / max(v[1], 1), 4) for k, v in Hh.stage_times().items()}
         runner.close()
         return dict(ms=ms, wall=wall, launches=l1 - l0, h2d=(b1[0] - b0[0]) / K, d2h=(b1[1] - b0[1]) / K,
-                    matches_per_pair=total_matches / float(S * K), ok_frac=oks / float(S * K), clocks=clocks, stages=stages)
+                    matches_per_pair=total_matches / float(S * K), ok_frac=oks / float(S * K), clocks=clocks, stages=stages, outliers=ro)
 
     res_dev = timed(True)
     res_e2e = timed(False)
@@ -371,7 +372,9 @@ def main():
                        '%d sequences x 0.47 MB per step, L2 not flushed between steps (working set of a step = %d MB of planes and records)' % (S, int(S * 3.3)),
                        'device': info['name'], 'matches_per_pair': round(res_dev['matches_per_pair'], 1),
                        'process_ok_fraction': res_dev['ok_frac'],
-                       'host_ms_per_call': res_dev.get('stages')},
+                       'host_ms_per_call': res_dev.get('stages'),
+                       'outlier_removal': dict(where='device (csrc/outliers.cu; lists it declines go to the host implementation)',
+                                               **res_dev.get('outliers', {}))},
             'clocks': res_dev['clocks'],
             'e2e': {'value': round(pairs / (ms_e2e * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(res_e2e['h2d'] * world),
                     'd2h_bytes_per_step': int(res_e2e['d2h'] * world), 'api': 'Matcher::pushBack(host image) + matchFeatures + getMatches'},

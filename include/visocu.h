@@ -159,6 +159,9 @@ int  visocu_profile(visocu_ctx* ctx, int32_t enable);
 int  visocu_profile_read(const visocu_ctx* ctx, double* filter_ms, uint64_t* launches, uint64_t* frames);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int  visocu_launch_count(const visocu_ctx* ctx, uint64_t* n);
+/* device outlier removal so far: out8 = lists handled, lists declined (too long, duplicates, guard: [2..4]), and the
+ * summed kernel time of the handled lists in nanoseconds ([5] sort + partition, [6] build, [7] vote + compaction) */
+int  visocu_outlier_stats(const visocu_ctx* ctx, uint64_t* out8);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

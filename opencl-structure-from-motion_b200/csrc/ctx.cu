@@ -350,6 +350,14 @@ extern "C" int visocu_profile_read(const visocu_ctx* ctx, double* filter_ms, uin
   if (frames) *frames = ctx->filter_frames;
   return VISOCU_OK;
 }
+extern "C" int visocu_outlier_stats(const visocu_ctx* ctx, uint64_t* out8) {
+  if (!ctx || !out8) return VISOCU_EINVAL;
+  out8[0] = ctx->ro_jobs; out8[1] = ctx->ro_declined;
+  out8[2] = ctx->ro_reason[1]; out8[3] = ctx->ro_reason[2]; out8[4] = ctx->ro_reason[3];
+  out8[5] = ctx->ro_ns[0] + ctx->ro_ns[1]; out8[6] = ctx->ro_ns[2]; out8[7] = ctx->ro_ns[3];
+  return VISOCU_OK;
+}
+
 extern "C" int visocu_launch_count(const visocu_ctx* ctx, uint64_t* n) {
   if (!ctx || !n) return VISOCU_EINVAL;
   *n = ctx->launches;

@@ -371,6 +371,14 @@ VISOB_API void visob_runner_transfer_bytes(void* h, uint64_t* h2d, uint64_t* d2h
   for (MatcherBatch* m : r->batches) if (m->context() && visocu_transfer_bytes(m->context(), &x, &y) == 0) { a += x; b += y; }
   *h2d = a; *d2h = b;
 }
+VISOB_API void visob_runner_outlier_stats(void* h, uint64_t* out8) {
+  Runner* r = (Runner*)h;
+  uint64_t one[8];
+  for (int k = 0; k < 8; k++) out8[k] = 0;
+  for (MatcherBatch* m : r->batches)
+    if (m->context() && visocu_outlier_stats(m->context(), one) == 0)
+      for (int k = 0; k < 8; k++) out8[k] += one[k];
+}
 VISOB_API uint64_t visob_runner_launches(void* h) {
   Runner* r = (Runner*)h;
   uint64_t total = 0, n = 0;

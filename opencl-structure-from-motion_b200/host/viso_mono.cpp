@@ -100,6 +100,7 @@ Matrix VisualOdometryMono::ransacEstimateF(const vector<Matcher::p_match>& p_mat
 
 // ---- batched variant used by the sequence runner: the RANSAC of several sequences is ONE visocu_ransac_F call
 bool VisualOdometryMono::batchPrepare(const float** uv, int32_t* N, const int32_t** samples) {
+  MonoTimer timer(6);
   matcher->bucketFeatures(param.bucket.max_features, param.bucket.bucket_width, param.bucket.bucket_height);
   p_matched = matcher->getMatches();
   batch_ready = false;
@@ -114,6 +115,7 @@ bool VisualOdometryMono::batchPrepare(const float** uv, int32_t* N, const int32_
 }
 
 bool VisualOdometryMono::batchFinish(const double* F9, const uint8_t* mask) {
+  MonoTimer timer(7);
   if (!batch_ready) return false;
   inliers.clear();
   for (size_t i = 0; i < normalized_last.size(); i++)

@@ -333,6 +333,15 @@ class Runner:
     def launches(self):
         return int(lib().visob_runner_launches(self.h))
 
+    def outlier_stats(self):
+        """Device outlier removal: lists handled / declined and mean kernel phase times (microseconds)."""
+        out = np.zeros(8, np.uint64)
+        lib().visob_runner_outlier_stats(self.h, _p(out))
+        n = max(int(out[0]), 1)
+        return dict(lists=int(out[0]), declined=int(out[1]), declined_too_long=int(out[2]), declined_duplicates=int(out[3]),
+                    declined_guard=int(out[4]), sort_partition_us=round(float(out[5]) / n / 1e3, 1),
+                    build_us=round(float(out[6]) / n / 1e3, 1), vote_us=round(float(out[7]) / n / 1e3, 1))
+
     def transfer_bytes(self):
         a = C.c_uint64(); b = C.c_uint64()
         lib().visob_runner_transfer_bytes(self.h, C.byref(a), C.byref(b))
