@@ -119,19 +119,24 @@ extern "C" int visocu_triangulate(visocu_ctx* ctx, const float* uv, int32_t N, c
   const size_t o_uv = 0, o_X = align_up((size_t)N * 16, 256), o_cnt = o_X + align_up((size_t)n_sol * 4 * N * 8, 256);
   int rc = visocu_ensure_scratch(ctx, o_cnt + 256);
   if (rc) return rc;
+  if ((rc = visocu_ensure_pinned(ctx, o_cnt + 256))) return rc;       // same layout in pinned memory: no pageable copies
   uint8_t* sb = (uint8_t*)ctx->scratch;
+  uint8_t* pin = (uint8_t*)ctx->pinned;
   TriJob job;
   job.uv = (const float4*)(sb + o_uv); job.X = (double*)(sb + o_X); job.n_front = (int32_t*)(sb + o_cnt);
   job.N = N; job.n_sol = n_sol;
   memcpy(job.P1, P1, sizeof job.P1);
   memcpy(job.P2, P2, sizeof(double) * 12 * n_sol);
-  CU_COPY(ctx, sb + o_uv, uv, (size_t)N * 16, cudaMemcpyHostToDevice);
+  memcpy(pin + o_uv, uv, (size_t)N * 16);
+  CU_COPY(ctx, sb + o_uv, pin + o_uv, (size_t)N * 16, cudaMemcpyHostToDevice);
   CU_TRY(ctx, cudaMemsetAsync(sb + o_cnt, 0, 16, ctx->stream));
   k_triangulate<<<dim3((N + 127) / 128, n_sol), 128, 0, ctx->stream>>>(job);
   CU_LAUNCH_CHECK(ctx);
-  CU_COPY(ctx, X, sb + o_X, (size_t)n_sol * 4 * N * 8, cudaMemcpyDeviceToHost);
-  CU_COPY(ctx, n_front, sb + o_cnt, (size_t)n_sol * 4, cudaMemcpyDeviceToHost);
+  // X and the counters are adjacent in both layouts: one read-back
+  CU_COPY(ctx, pin + o_X, sb + o_X, o_cnt - o_X + 16, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, visocu_stream_wait(ctx));
+  memcpy(X, pin + o_X, (size_t)n_sol * 4 * N * 8);
+  memcpy(n_front, pin + o_cnt, (size_t)n_sol * 4);
   return VISOCU_OK;
 }
 
@@ -141,12 +146,15 @@ extern "C" int visocu_best_plane(visocu_ctx* ctx, const double* d, int32_t n, do
   const size_t o_s = align_up((size_t)n * 8, 256);
   int rc = visocu_ensure_scratch(ctx, 2 * o_s);
   if (rc) return rc;
+  if ((rc = visocu_ensure_pinned(ctx, 2 * o_s))) return rc;
   uint8_t* sb = (uint8_t*)ctx->scratch;
-  CU_COPY(ctx, sb, d, (size_t)n * 8, cudaMemcpyHostToDevice);
+  uint8_t* pin = (uint8_t*)ctx->pinned;
+  memcpy(pin, d, (size_t)n * 8);
+  CU_COPY(ctx, sb, pin, (size_t)n * 8, cudaMemcpyHostToDevice);
   k_plane_sums<<<(n + 7) / 8, 256, 0, ctx->stream>>>((const double*)sb, n, threshold, weight, (double*)(sb + o_s));
   CU_LAUNCH_CHECK(ctx);
-  std::vector<double> sums(n);
-  CU_COPY(ctx, sums.data(), sb + o_s, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  const double* sums = (const double*)(pin + o_s);
+  CU_COPY(ctx, pin + o_s, sb + o_s, (size_t)n * 8, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, visocu_stream_wait(ctx));
   // arg-max with the reference's rule: strictly larger wins, so the first maximum is kept; index 0 if no candidate
   double best_sum = 0;

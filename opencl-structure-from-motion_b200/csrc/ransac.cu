@@ -376,8 +376,11 @@ extern "C" int visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* con
   for (int start = 0; start < n_jobs; start += VISO_MAX_BATCH) {
     const int nb = n_jobs - start < VISO_MAX_BATCH ? n_jobs - start : VISO_MAX_BATCH;
     std::vector<RansacJob> hj(nb);
-    std::vector<size_t> o_uv(nb), o_smp(nb), o_F(nb), o_cnt(nb), o_mask(nb), o_inl(nb), o_A(nb), o_out(nb), o_n(nb);
-    size_t off = align_up(sizeof(RansacJob) * nb, 256), pin_need = off;
+    // Device scratch mirrors the pinned staging area for everything that goes up (job descriptors, match coordinates,
+    // sample tables: ONE upload) and keeps everything that comes back in two contiguous blocks (one 128-byte result
+    // slot and one mask row per job: TWO read-backs) - API calls, not bytes, are what this call costs.
+    std::vector<size_t> o_uv(nb), o_smp(nb), o_F(nb), o_inl(nb), o_A(nb);
+    size_t off = align_up(sizeof(RansacJob) * nb, 256);
     int maxN = 0;
     for (int j = 0; j < nb; j++) {
       const int n = N[start + j];
@@ -385,42 +388,38 @@ extern "C" int visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* con
       for (int k = 0; k < iters * 8; k++)
         if (samples[start + j][k] < 0 || samples[start + j][k] >= n) return visocu_set_error(ctx, VISOCU_EINVAL, "ransac job %d: sample index out of range", start + j);
       if (n > maxN) maxN = n;
-      const int lda = (n + 3) & ~3;
+      hj[j].N = n; hj[j].lda = (n + 3) & ~3;
       o_uv[j] = off; off += align_up((size_t)n * 16, 256);
       o_smp[j] = off; off += align_up((size_t)iters * 32, 256);
-      o_F[j] = off; off += align_up((size_t)iters * 72, 256);
-      o_cnt[j] = off; off += align_up((size_t)iters * 4, 256);
-      o_mask[j] = off; off += align_up((size_t)n, 256);
-      o_inl[j] = off; off += align_up((size_t)n * 4, 256);
-      o_A[j] = off; off += align_up((size_t)lda * 72, 256);
-      o_out[j] = off; off += 256;
-      o_n[j] = off; off += 256;
-      pin_need += align_up((size_t)n * 16, 256) + align_up((size_t)iters * 32, 256) + 512;
-      hj[j].N = n; hj[j].lda = lda;
     }
-    pin_need += align_up((size_t)nb * 72, 256) + (size_t)nb * 8 + 256;
+    const size_t up_bytes = off;                                        // uploaded in one copy
+    const size_t cstride = align_up((size_t)iters * 4, 256), mstride = align_up((size_t)maxN, 256);
+    const size_t o_cnt = off; off += cstride * nb;
+    const size_t o_slot = off; off += (size_t)128 * nb;                 // F9 (72 B) + n_inl, best (8 B) per job
+    const size_t o_mask = off; off += mstride * nb;
+    for (int j = 0; j < nb; j++) {
+      o_F[j] = off; off += align_up((size_t)iters * 72, 256);
+      o_inl[j] = off; off += align_up((size_t)hj[j].N * 4, 256);
+      o_A[j] = off; off += align_up((size_t)hj[j].lda * 72, 256);
+    }
     int rc = visocu_ensure_scratch(ctx, off);
     if (rc) return rc;
-    if ((rc = visocu_ensure_pinned(ctx, pin_need))) return rc;
+    const size_t p_slot = align_up(up_bytes, 256), p_mask = p_slot + align_up((size_t)128 * nb, 256);
+    if ((rc = visocu_ensure_pinned(ctx, p_mask + mstride * nb))) return rc;
     uint8_t* sb = (uint8_t*)ctx->scratch;
     uint8_t* pin = (uint8_t*)ctx->pinned;
-    size_t po = align_up(sizeof(RansacJob) * nb, 256);
     for (int j = 0; j < nb; j++) {
       const int n = hj[j].N;
       hj[j].uv = (const float4*)(sb + o_uv[j]); hj[j].samples = (const int32_t*)(sb + o_smp[j]);
-      hj[j].F_all = (double*)(sb + o_F[j]); hj[j].counts = (int32_t*)(sb + o_cnt[j]);
-      hj[j].mask = sb + o_mask[j]; hj[j].inl = (int32_t*)(sb + o_inl[j]); hj[j].A = (double*)(sb + o_A[j]);
-      hj[j].F9 = (double*)(sb + o_out[j]); hj[j].n_inl = (int32_t*)(sb + o_n[j]);
-      memcpy(pin + po, uv[start + j], (size_t)n * 16);
-      CU_COPY(ctx, sb + o_uv[j], pin + po, (size_t)n * 16, cudaMemcpyHostToDevice);
-      po += align_up((size_t)n * 16, 256);
-      memcpy(pin + po, samples[start + j], (size_t)iters * 32);
-      CU_COPY(ctx, sb + o_smp[j], pin + po, (size_t)iters * 32, cudaMemcpyHostToDevice);
-      po += align_up((size_t)iters * 32, 256);
-      CU_TRY(ctx, cudaMemsetAsync(sb + o_cnt[j], 0, (size_t)iters * 4, ctx->stream));
+      hj[j].F_all = (double*)(sb + o_F[j]); hj[j].counts = (int32_t*)(sb + o_cnt + cstride * j);
+      hj[j].mask = sb + o_mask + mstride * j; hj[j].inl = (int32_t*)(sb + o_inl[j]); hj[j].A = (double*)(sb + o_A[j]);
+      hj[j].F9 = (double*)(sb + o_slot + 128 * j); hj[j].n_inl = (int32_t*)(sb + o_slot + 128 * j + 72);
+      memcpy(pin + o_uv[j], uv[start + j], (size_t)n * 16);
+      memcpy(pin + o_smp[j], samples[start + j], (size_t)iters * 32);
     }
     memcpy(pin, hj.data(), sizeof(RansacJob) * nb);
-    CU_COPY(ctx, sb, pin, sizeof(RansacJob) * nb, cudaMemcpyHostToDevice);
+    CU_COPY(ctx, sb, pin, up_bytes, cudaMemcpyHostToDevice);
+    CU_TRY(ctx, cudaMemsetAsync(sb + o_cnt, 0, cstride * nb, ctx->stream));
     const RansacJob* dj = (const RansacJob*)sb;
     k_hypotheses<<<dim3((iters + 11) / 12, nb), 128, 0, ctx->stream>>>(dj, iters);
     CU_LAUNCH_CHECK(ctx);
@@ -429,14 +428,9 @@ extern "C" int visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* con
     CU_LAUNCH_CHECK(ctx);
     k_finish<<<nb, FINISH_THREADS, 0, ctx->stream>>>(dj, iters, thresh);
     CU_LAUNCH_CHECK(ctx);
-    // results: F9 + (n_inl, best) per job through pinned memory, masks / optional tables straight to the caller
-    double* pinF = (double*)(pin + po);
-    int32_t* pinN = (int32_t*)(pin + po + align_up((size_t)nb * 72, 256));
-    for (int j = 0; j < nb; j++) {
-      CU_COPY(ctx, pinF + 9 * j, hj[j].F9, 72, cudaMemcpyDeviceToHost);
-      CU_COPY(ctx, pinN + 2 * j, hj[j].n_inl, 8, cudaMemcpyDeviceToHost);
-      if (inlier_mask && inlier_mask[start + j])
-        CU_COPY(ctx, inlier_mask[start + j], hj[j].mask, (size_t)hj[j].N, cudaMemcpyDeviceToHost);
+    CU_COPY(ctx, pin + p_slot, sb + o_slot, (size_t)128 * nb, cudaMemcpyDeviceToHost);
+    if (inlier_mask) CU_COPY(ctx, pin + p_mask, sb + o_mask, mstride * nb, cudaMemcpyDeviceToHost);
+    for (int j = 0; j < nb; j++) {                  // optional per-hypothesis tables (tests): straight to the caller
       if (counts && counts[start + j])
         CU_COPY(ctx, counts[start + j], hj[j].counts, (size_t)iters * 4, cudaMemcpyDeviceToHost);
       if (F_all && F_all[start + j])
@@ -444,9 +438,11 @@ extern "C" int visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* con
     }
     CU_TRY(ctx, visocu_stream_wait(ctx));
     for (int j = 0; j < nb; j++) {
-      memcpy(F9 + 9 * (size_t)(start + j), pinF + 9 * j, 72);
-      n_inliers[start + j] = pinN[2 * j];
-      if (best_iter) best_iter[start + j] = pinN[2 * j + 1];
+      memcpy(F9 + 9 * (size_t)(start + j), pin + p_slot + 128 * j, 72);
+      const int32_t* nn = (const int32_t*)(pin + p_slot + 128 * j + 72);
+      n_inliers[start + j] = nn[0];
+      if (best_iter) best_iter[start + j] = nn[1];
+      if (inlier_mask && inlier_mask[start + j]) memcpy(inlier_mask[start + j], pin + p_mask + mstride * j, (size_t)hj[j].N);
     }
   }
   return VISOCU_OK;

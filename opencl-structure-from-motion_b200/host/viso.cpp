@@ -41,12 +41,32 @@ Matrix VisualOdometry::transformationVectorToMatrix(std::vector<double> tr) {
 }
 
 std::vector<int> VisualOdometry::getRandomSample(unsigned N, unsigned num) {
-  std::vector<int> pool(N);
-  std::iota(pool.begin(), pool.end(), 0);
-  for (unsigned i = 0; i < num; i++) {
-    std::uniform_int_distribution<unsigned> pick(i, N - 1);
-    std::swap(pool.at(i), pool.at(pick(sample_generator)));
+  // Partial Fisher-Yates over 0..N-1 with a fresh uniform_int_distribution(i, N-1) per draw, exactly the calls of
+  // viso.cpp:86-102.  The reference builds the N-element index set anew for every sample (2000 times per frame); here
+  // the identity permutation is kept and the few swaps of a sample are undone afterwards: same numbers, no allocation.
+  if (sample_pool.size() != N) {
+    sample_pool.resize(N);
+    std::iota(sample_pool.begin(), sample_pool.end(), 0);
   }
-  pool.resize(num);
-  return pool;
+  unsigned picked[16];
+  std::vector<int> out(num);
+  const unsigned cnt = num < 16 ? num : 16;
+  if (num > 16) {                       // not used by the library (8-point and 3-point samples); keep the plain form
+    std::vector<int> pool(N);
+    std::iota(pool.begin(), pool.end(), 0);
+    for (unsigned i = 0; i < num; i++) {
+      std::uniform_int_distribution<unsigned> pick(i, N - 1);
+      std::swap(pool.at(i), pool.at(pick(sample_generator)));
+    }
+    pool.resize(num);
+    return pool;
+  }
+  for (unsigned i = 0; i < cnt; i++) {
+    std::uniform_int_distribution<unsigned> pick(i, N - 1);
+    picked[i] = pick(sample_generator);
+    std::swap(sample_pool.at(i), sample_pool.at(picked[i]));
+  }
+  for (unsigned i = 0; i < cnt; i++) out[i] = sample_pool[i];
+  for (unsigned i = cnt; i-- > 0;) std::swap(sample_pool[i], sample_pool[picked[i]]);
+  return out;
 }

@@ -70,6 +70,7 @@ protected:
   double* p_predict;
   std::vector<Matcher::p_match> p_matched;
   std::default_random_engine sample_generator;
+  std::vector<int> sample_pool;                     // identity permutation reused by getRandomSample
 
 private:
   parameters param;
