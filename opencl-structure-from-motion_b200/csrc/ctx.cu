@@ -162,11 +162,6 @@ extern "C" int visocu_device_info(const visocu_ctx* ctx, int32_t* sm_count, int3
   return VISOCU_OK;
 }
 
-bool visocu_uniform_carveout() {
-  static const bool on = [] { const char* e = getenv("VISOCU_CARVEOUT"); return !(e && e[0] == '0'); }();
-  return on;
-}
-
 int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->scratch_bytes) return VISOCU_OK;
   CU_TRY(ctx, visocu_stream_wait(ctx));

@@ -619,15 +619,6 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
       std::lock_guard<std::mutex> lock(mtx);
       if (!done[ctx->device & 63]) {
         CU_TRY(ctx, cudaFuncSetAttribute(k_filter_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        if (visocu_uniform_carveout()) {
-          // one shared-memory / L1 split for every kernel of the pipeline: an SM never has to drain to switch
-          CU_TRY(ctx, cudaFuncSetAttribute(k_half_image, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-          CU_TRY(ctx, cudaFuncSetAttribute(k_sobel_full, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-          CU_TRY(ctx, cudaFuncSetAttribute(k_filter_nms, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-          CU_TRY(ctx, cudaFuncSetAttribute(k_cell_count, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-          CU_TRY(ctx, cudaFuncSetAttribute(k_emit_records, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-          CU_TRY(ctx, cudaFuncSetAttribute(k_build_bins, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        }
         done[ctx->device & 63] = true;
       }
     }

@@ -521,18 +521,6 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
   if (pass < ctx->g.first_pass || pass > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "pass %d not available", pass);
   if (use_prior && !ranges) return visocu_set_error(ctx, VISOCU_EINVAL, "use_prior needs ranges");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  if (visocu_uniform_carveout()) {
-    static std::mutex mtx;
-    static bool done[64] = {false};
-    std::lock_guard<std::mutex> lock(mtx);
-    if (!done[ctx->device & 63]) {
-      CU_TRY(ctx, cudaFuncSetAttribute(k_match, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      CU_TRY(ctx, cudaFuncSetAttribute(k_match_count, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      CU_TRY(ctx, cudaFuncSetAttribute(k_match_emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      CU_TRY(ctx, cudaFuncSetAttribute(k_refine, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      done[ctx->device & 63] = true;
-    }
-  }
   const Geometry& g = ctx->g;
   const int nstat = g.ub * g.vb;
   for (int start = 0; start < n_jobs; start += VISO_MAX_BATCH) {

@@ -36,8 +36,10 @@ __host__ __device__ inline size_t ro_smem_bytes(int n) {
 }
 
 struct Mesh {
-  uint16_t *nx, *pv, *og;      // per half-edge: next / previous around the origin (counter-clockwise), origin vertex
-  const uint32_t* pt;          // x | y << 16 per vertex
+  // per half-edge: next / previous around the origin (counter-clockwise), origin vertex.  Three separate arrays that never
+  // alias: with __restrict__ the compiler may hoist the loads of one above the stores to another
+  uint16_t* __restrict__ nx; uint16_t* __restrict__ pv; uint16_t* __restrict__ og;
+  const uint32_t* __restrict__ pt;   // x | y << 16 per vertex
   int* bump; int ecap; volatile int* fail;
   int guard;                   // remaining loop iterations of this thread before it gives up
 
@@ -292,15 +294,19 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   uint8_t* side = (uint8_t*)(pre + n + 1);
   // (8 npad + 19 n + 2 <= 12 ecap because npad < 2 n)
 
-  auto bitonic = [&]() {
+  // Bitonic merge sort of keys[0, m), ascending.  Every compare-exchange puts the smaller key at the lower index (the
+  // first step of each merge pairs i with its mirror image in the block), so the elements beyond m can stay virtual
+  // "+infinity" padding: pairs that reach past m are skipped, and the work follows m, not the next power of two.
+  auto bitonic = [&](int m) {
     for (int k = 2; k <= npad; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int t = tid; t < (npad >> 1); t += RO_THREADS) {
           const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));              // element with bit j clear
-          const int p = i | j;
-          const bool up = (i & k) == 0;
-          const unsigned long long a = keys[i], b = keys[p];
-          if ((a > b) == up) { keys[i] = b; keys[p] = a; }
+          const int p = (j == (k >> 1)) ? (i ^ (k - 1)) : (i | j);
+          if (p < m) {
+            const unsigned long long a = keys[i], b = keys[p];
+            if (a > b) { keys[i] = b; keys[p] = a; }
+          }
         }
         __syncthreads();
       }
@@ -320,7 +326,7 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
     keys[i] = key;
   }
   __syncthreads();
-  bitonic();
+  bitonic(nl);
   for (int i = tid; i < npad; i += RO_THREADS)
     if (keys[i] != ~0ull && (i + 1 == npad || keys[i + 1] == ~0ull)) s_more = i + 1;     // number of vertices
   __syncthreads();
@@ -352,7 +358,7 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   for (int i = tid; i < npad; i += RO_THREADS)
     keys[i] = i < n ? ((unsigned long long)ay[i] << 40) | ((unsigned long long)ax[i] << 16) | (unsigned)i : ~0ull;
   __syncthreads();
-  bitonic();
+  bitonic(n);
   const unsigned long long t_sorted = now();
   uint16_t* xl = la; uint16_t* yl = lb; uint16_t* spare = lc;
   for (int i = tid; i < n; i += RO_THREADS) { xl[i] = (uint16_t)i; yl[i] = (uint16_t)keys[i]; nlo[i] = 0; nsz[i] = (uint16_t)n; }
@@ -484,9 +490,25 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
     if (tid == 0) { J.result[0] = nl; J.result[1] = 3; J.result[2] = s_bump; J.result[3] = nl; }
     return;
   }
-  // one vote counter per list position; the ring pointers of the mesh are no longer needed, the counters take their place
-  unsigned int* support = (unsigned int*)he_nx;
-  for (int i = tid; i < nl; i += RO_THREADS) support[i] = 0;
+  // The ring pointers of the mesh are no longer needed.  Their arrays now hold, per list position, the vote counter and
+  // the quantities the vote compares (flow / disparity of the match, computed once with the reference's float
+  // operations, matcher.cpp:1267-1349), and per vertex its list position: the vote itself touches shared memory only.
+  unsigned int* support = (unsigned int*)he_nx;                       // nl words
+  float* q_d = (float*)he_nx + nl;                                    // disparity (methods 1 and 2), nl words <= rest of he_nx
+  float* q_u = (float*)he_pv;                                         // flow u, flow v (methods 0 and 2)
+  float* q_v = q_u + nl;
+  uint16_t* vpos = (uint16_t*)(q_v + nl);                             // 8 nl + 2 n bytes <= 12 ecap / ... of he_pv
+  const bool vote_in_smem = (size_t)8 * nl <= (size_t)4 * ecap && (size_t)8 * nl + (size_t)2 * n <= (size_t)4 * ecap;
+  for (int i = tid; i < nl; i += RO_THREADS) {
+    support[i] = 0;
+    if (vote_in_smem) {
+      const visocu_pmatch& r = J.in[src[i]];
+      q_u[i] = __fsub_rn(r.u1c, r.u1p); q_v[i] = __fsub_rn(r.v1c, r.v1p);
+      q_d[i] = method == 1 ? __fsub_rn(r.u1c, r.u2c) : __fsub_rn(r.u1p, r.u2p);
+    }
+  }
+  if (vote_in_smem)
+    for (int i = tid; i < n; i += RO_THREADS) vpos[i] = (uint16_t)J.vert[i];
   __syncthreads();
   const int nedge = min(s_bump, ecap);
   for (int k = tid; k < nedge; k += RO_THREADS) {
@@ -495,8 +517,18 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
     // an edge with a triangle on both sides votes twice (the reference votes per triangle, matcher.cpp:1259-1362)
     const int t = ((o0 & 0x8000) ? 0 : 1) + ((o1 & 0x8000) ? 0 : 1);
     if (t == 0) continue;
-    const int pa = J.vert[o0 & 0x7FFF], pb = J.vert[o1 & 0x7FFF];
-    if (edge_agrees(J.in[src[pa]], J.in[src[pb]], method, flow_tol, disp_tol)) {
+    int pa, pb;
+    bool agree;
+    if (vote_in_smem) {
+      pa = vpos[o0 & 0x7FFF]; pb = vpos[o1 & 0x7FFF];
+      const bool flow_ok = __fadd_rn(fabsf(__fsub_rn(q_u[pa], q_u[pb])), fabsf(__fsub_rn(q_v[pa], q_v[pb]))) < flow_tol;
+      const bool disp_ok = fabsf(__fsub_rn(q_d[pa], q_d[pb])) < disp_tol;
+      agree = method == 0 ? flow_ok : (method == 1 ? disp_ok : (disp_ok && flow_ok));
+    } else {
+      pa = J.vert[o0 & 0x7FFF]; pb = J.vert[o1 & 0x7FFF];
+      agree = edge_agrees(J.in[src[pa]], J.in[src[pb]], method, flow_tol, disp_tol);
+    }
+    if (agree) {
       atomicAdd(&support[pa], (unsigned)t);
       atomicAdd(&support[pb], (unsigned)t);
     }
@@ -554,8 +586,6 @@ int visocu_launch_remove_outliers(visocu_ctx* ctx, const RoJob* jobs_dev, int n_
     std::lock_guard<std::mutex> lock(mtx);
     if (!done[ctx->device & 63]) {
       CU_TRY(ctx, cudaFuncSetAttribute(k_remove_outliers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-      if (visocu_uniform_carveout())
-        CU_TRY(ctx, cudaFuncSetAttribute(k_remove_outliers, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       done[ctx->device & 63] = true;
     }
   }

@@ -77,7 +77,6 @@ struct visocu_ctx {
 int visocu_set_error(visocu_ctx* ctx, int code, const char* fmt, ...);
 cudaError_t visocu_stream_wait(visocu_ctx* ctx);     // waits for the context's stream (yielding the CPU if ev_sync exists)
 int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes);
-bool visocu_uniform_carveout();                      // VISOCU_CARVEOUT=0 leaves the per-kernel default split
 int visocu_ensure_pinned(visocu_ctx* ctx, size_t bytes);
 
 #define CU_TRY(ctx, expr)                                                                        \
