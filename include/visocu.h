@@ -115,6 +115,13 @@ int  visocu_nms(visocu_ctx* ctx, const int16_t* f1, const int16_t* f2, int32_t w
 int  visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
                   int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
                   visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers);
+/* The same call split in two for pipelined callers (flow matching with device outlier removal, pixel refinement or none,
+ * at most 128 jobs): _deferred enqueues everything and returns; the outlier removal runs on a second stream with its own
+ * scratch memory, so the context can take the next frames (visocu_push_frames) and other matching calls meanwhile.
+ * _collect waits for it and delivers what visocu_match would have delivered.  One deferred call per context at a time. */
+int  visocu_match_deferred(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
+                           int32_t use_prior, const visocu_range* const* ranges, int32_t refine);
+int  visocu_match_collect(visocu_ctx* ctx, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers);
 /* Matcher::removeOutliers alone on caller-supplied match lists (host memory, compacted in place).  status[j] = 0: done,
  * 1: list unchanged, not handled by the device path (see visocu_match). */
 int  visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t method, visocu_pmatch* const* inout, const int32_t* n,

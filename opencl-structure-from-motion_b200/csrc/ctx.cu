@@ -42,20 +42,22 @@ WriteValueFn write_value_fn() {
 }
 }  // namespace
 
-cudaError_t visocu_stream_wait(visocu_ctx* ctx) {
+cudaError_t visocu_stream_wait_on(visocu_ctx* ctx, int which) {
+  cudaStream_t st = which ? ctx->stream2 : ctx->stream;
   if (ctx->ev_sync) {
-    cudaError_t e = cudaEventRecord(ctx->ev_sync, ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->ev_sync, st);
     return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_sync);
   }
   WriteValueFn wv = write_value_fn();
   if (wv && ctx->wait_flag) {
-    const uint32_t seq = ++ctx->wait_seq;
-    if (wv((CUstream)ctx->stream, (CUdeviceptr)(uintptr_t)ctx->wait_flag_dev, seq, 0) == CUDA_SUCCESS) {
-      volatile uint32_t* flag = ctx->wait_flag;
+    uint32_t& counter = which ? ctx->wait_seq2 : ctx->wait_seq;
+    const uint32_t seq = ++counter;
+    volatile uint32_t* flag = ctx->wait_flag + (which ? 8 : 0);          // two words of the 64-byte block
+    if (wv((CUstream)st, (CUdeviceptr)((uintptr_t)ctx->wait_flag_dev + (which ? 32 : 0)), seq, 0) == CUDA_SUCCESS) {
       unsigned spins = 0;
       while (*flag != seq) {
         if ((++spins & 0x3FFF) == 0) {                 // now and then: did the stream die?
-          cudaError_t e = cudaStreamQuery(ctx->stream);
+          cudaError_t e = cudaStreamQuery(st);
           if (e != cudaSuccess && e != cudaErrorNotReady) return e;
         }
         sched_yield();
@@ -63,8 +65,10 @@ cudaError_t visocu_stream_wait(visocu_ctx* ctx) {
       return cudaSuccess;
     }
   }
-  return cudaStreamSynchronize(ctx->stream);
+  return cudaStreamSynchronize(st);
 }
+
+cudaError_t visocu_stream_wait(visocu_ctx* ctx) { return visocu_stream_wait_on(ctx, 0); }
 
 extern "C" const char* visocu_last_error(const visocu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -92,6 +96,8 @@ extern "C" int visocu_create(int device, visocu_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount; ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
   snprintf(ctx->name, sizeof ctx->name, "%s", prop.name);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaMalloc(&ctx->d_stats, 2 * sizeof(uint64_t))) != cudaSuccess) {
     visocu_set_error(nullptr, VISOCU_ECUDA, "context setup: %s", cudaGetErrorString(e));
@@ -128,6 +134,7 @@ extern "C" void visocu_destroy(visocu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   if (getenv("VISOCU_RO_STATS") && (ctx->ro_jobs || ctx->ro_declined)) {
     const double nj = ctx->ro_jobs ? (double)ctx->ro_jobs : 1.0;
     fprintf(stderr, "[outliers] %llu lists on the device, mean us: sort %.1f partition %.1f build %.1f vote %.1f; declined %llu "
@@ -139,6 +146,9 @@ extern "C" void visocu_destroy(visocu_ctx* ctx) {
   }
   free_pool(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->scratch2) cudaFree(ctx->scratch2);
+  if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->img_stage) cudaFree(ctx->img_stage);
   if (ctx->counts_stage) cudaFree(ctx->counts_stage);
   if (ctx->wait_flag) cudaFreeHost((void*)ctx->wait_flag);

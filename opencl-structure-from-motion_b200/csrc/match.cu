@@ -17,6 +17,7 @@
 #include "visocu_internal.cuh"
 #include "outliers.cuh"
 #include <mutex>
+#include <utility>
 #include <cmath>
 #include <cstring>
 
@@ -509,12 +510,55 @@ int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJ
 
 }  // namespace
 
-extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
-                            int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
-                            visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers) {
+// The tail of a matching call: result words are in pinned memory; fetch the lists and hand everything to the caller.
+static int match_tail(visocu_ctx* ctx, const visocu_deferred& st, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out,
+                      int32_t* outliers) {
+  const int nb = st.nb;
+  const int32_t* pw = (const int32_t*)st.pin_words;
+  int maxn = 0;
+  for (int j = 0; j < nb; j++) {
+    const int n = pw[16 * j];
+    n_out[j] = n;
+    if (n > maxn) maxn = n;
+    if (n > cap[j]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "job %d produced %d matches, room for %d", j, n, cap[j]);
+    const int status = pw[16 * j + 1];
+    outliers[j] = status == 0 ? 1 : 0;
+    if (status == 0 && n > 3) { for (int k = 0; k < 4; k++) ctx->ro_ns[k] += (uint64_t)pw[16 * j + 4 + k]; ctx->ro_jobs++; }
+    else if (status != 0) { ctx->ro_declined++; ctx->ro_reason[status & 3]++; ctx->ro_declined_n += (uint64_t)pw[16 * j + 3]; }
+  }
+  if (maxn > 0) {
+    const size_t wbytes = (size_t)maxn * 48;
+    ctx->d2h_bytes += (uint64_t)wbytes * nb;
+    CU_TRY(ctx, cudaMemcpy2DAsync(st.pin_lists, wbytes, st.dev_lists, st.ostride, wbytes, nb, cudaMemcpyDeviceToHost, ctx->stream2));
+    CU_TRY(ctx, visocu_stream_wait_on(ctx, 1));
+    for (int j = 0; j < nb; j++)
+      if (n_out[j] > 0) memcpy(out[j], st.pin_lists + wbytes * j, (size_t)n_out[j] * 48);
+  }
+  return VISOCU_OK;
+}
+
+// scratch and pinned staging of the deferred call are a second set: the first one is reused by the calls in between
+struct ScratchSwap {
+  visocu_ctx* ctx; bool on;
+  ScratchSwap(visocu_ctx* c, bool enable) : ctx(c), on(enable) { swap(); }
+  ~ScratchSwap() { swap(); }
+  void swap() {
+    if (!on) return;
+    std::swap(ctx->scratch, ctx->scratch2); std::swap(ctx->scratch_bytes, ctx->scratch2_bytes);
+    std::swap(ctx->pinned, ctx->pinned2); std::swap(ctx->pinned_bytes, ctx->pinned2_bytes);
+  }
+};
+
+static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
+                      int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
+                      visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers, bool deferred) {
   if (!ctx) return VISOCU_EINVAL;
   if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
-  if (n_jobs <= 0 || !jobs || !out || !cap || !n_out) return visocu_set_error(ctx, VISOCU_EINVAL, "bad match arguments");
+  if (n_jobs <= 0 || !jobs || (!deferred && (!out || !cap || !n_out))) return visocu_set_error(ctx, VISOCU_EINVAL, "bad match arguments");
+  if (deferred && ctx->deferred.pending) return visocu_set_error(ctx, VISOCU_ESTATE, "a deferred matching call has not been collected");
+  if (deferred && (method != 0 || n_jobs > VISO_MAX_BATCH || refine == 2))
+    return visocu_set_error(ctx, VISOCU_EINVAL, "deferred matching: flow method, pixel refinement, at most %d jobs", VISO_MAX_BATCH);
+  ScratchSwap swap_guard(ctx, deferred);
   if (method < 0 || method > 2) return visocu_set_error(ctx, VISOCU_EINVAL, "method %d not supported (0 = flow, 1 = stereo, 2 = quad)", method);
   if (refine < 0 || refine > 2) return visocu_set_error(ctx, VISOCU_EINVAL, "refine must be 0, 1 or 2");
   if (refine == 2) { int rc0 = upload_pinv(ctx); if (rc0) return rc0; }
@@ -526,7 +570,8 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
   for (int start = 0; start < n_jobs; start += VISO_MAX_BATCH) {
     const int nb = n_jobs - start < VISO_MAX_BATCH ? n_jobs - start : VISO_MAX_BATCH;
     std::vector<MatchJob> hj(nb);
-    std::vector<RoJob> rj(outliers ? nb : 0);
+    const bool ro = outliers != nullptr || deferred;    // outlier removal on the device
+    std::vector<RoJob> rj(ro ? nb : 0);
     int maxq = 0;
     for (int j = 0; j < nb; j++) {
       int rc = fill_job(ctx, jobs[start + j], method, pass, hj[j]);
@@ -545,15 +590,15 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
     // worker threads sharing a GPU that lock is what bounds the throughput.)
     const size_t rb = use_prior ? align_up((size_t)nstat * sizeof(visocu_range), 256) : 0;
     const size_t h_mj = 0, h_rj = align_up(sizeof(MatchJob) * nb, 256);
-    const size_t h_rng = h_rj + (outliers ? align_up(sizeof(RoJob) * nb, 256) : 0);
+    const size_t h_rng = h_rj + (ro ? align_up(sizeof(RoJob) * nb, 256) : 0);
     const size_t hdr_bytes = h_rng + rb * nb;
     const size_t o_words = hdr_bytes, words_bytes = (size_t)nb * 64;                  // 16 int32 per job
     const size_t ostride = align_up((size_t)(maxq + 1) * 48, 256);
     const size_t o_list = align_up(o_words + words_bytes, 256);                      // lists of the matching kernels
     const size_t o_list2 = o_list + ostride * nb;                                    // survivors of the outlier removal
-    size_t off = o_list2 + (outliers ? ostride * nb : 0);
+    size_t off = o_list2 + (ro ? ostride * nb : 0);
     std::vector<size_t> o_res(nb), o_blk(nb), o_keep(nb), o_idx(nb), o_vert(nb), o_hnd(nb), o_rep(nb);
-    const bool dedupe = outliers && method != 0;       // flow matching keeps one match per pixel (matcher.cpp:1036-1039)
+    const bool dedupe = ro && method != 0;       // flow matching keeps one match per pixel (matcher.cpp:1036-1039)
     const size_t kstride = (size_t)maxq + 1;             // words per job in the position buffer
     size_t o_keys = 0;
     for (int j = 0; j < nb; j++) {
@@ -561,7 +606,7 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
       o_res[j] = off; off += align_up((size_t)(nq + 1) * 16, 256);
       o_blk[j] = off; off += align_up((size_t)(nq / CHUNK + 2) * 4, 256);
       o_keep[j] = off; off += align_up((size_t)nq + 1, 256);
-      if (outliers) {
+      if (ro) {
         o_idx[j] = off; off += align_up((size_t)(nq + 1) * 4, 256);
         o_vert[j] = off; off += align_up((size_t)(nq + 1) * 4, 256);
         o_hnd[j] = off; off += align_up((size_t)(nq / 2 + 2) * 8, 256);
@@ -589,7 +634,7 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
         memcpy(pin + h_rng + rb * j, ranges[start + j], (size_t)nstat * sizeof(visocu_range));
         hj[j].ranges = (const visocu_range*)(sb + h_rng + rb * j);
       }
-      if (outliers) {
+      if (ro) {
         rj[j].in = hj[j].out; rj[j].keep_in = (refine == 2 && maxq > 0) ? hj[j].keep : nullptr; rj[j].n_in = hj[j].n_out;
         rj[j].out = (visocu_pmatch*)(sb + o_list2 + ostride * j);
         rj[j].result = words; rj[j].idx = (int32_t*)(sb + o_idx[j]); rj[j].vert = (int32_t*)(sb + o_vert[j]);
@@ -597,7 +642,7 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
       }
     }
     memcpy(pin + h_mj, hj.data(), sizeof(MatchJob) * nb);
-    if (outliers) memcpy(pin + h_rj, rj.data(), sizeof(RoJob) * nb);
+    if (ro) memcpy(pin + h_rj, rj.data(), sizeof(RoJob) * nb);
     CU_COPY(ctx, sb, pin, hdr_bytes, cudaMemcpyHostToDevice);
     const MatchJob* dj = (const MatchJob*)(sb + h_mj);
     if (maxq > 0) {
@@ -640,7 +685,21 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
         CU_COPY(ctx, sb + h_rj, pin + h_rj, sizeof(RoJob) * nb, cudaMemcpyHostToDevice);
       }
     }
-    if (outliers && (rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, maxq))) return rc;
+    if (deferred) {
+      // The outlier removal and the read-back of its result words go to the second stream, behind the kernels above;
+      // the caller's next feature and pass-1 launches on the first stream do not wait for them.
+      if (!stage_lists) return visocu_set_error(ctx, VISOCU_EINVAL, "deferred matching: lists too large for the staging area");
+      CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+      CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+      if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, maxq, ctx->stream2))) return rc;
+      ctx->d2h_bytes += words_bytes;
+      CU_TRY(ctx, cudaMemcpyAsync(pin + p_words, sb + o_words, words_bytes, cudaMemcpyDeviceToHost, ctx->stream2));
+      visocu_deferred& st = ctx->deferred;
+      st.pending = true; st.nb = nb; st.pin_words = pin + p_words; st.pin_lists = pin + p_lists;
+      st.dev_lists = sb + o_list2; st.ostride = ostride;
+      return VISOCU_OK;
+    }
+    if (ro && (rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, maxq, ctx->stream))) return rc;
     int32_t* pw = (int32_t*)(pin + p_words);
     CU_COPY(ctx, pw, sb + o_words, words_bytes, cudaMemcpyDeviceToHost);
     CU_TRY(ctx, visocu_stream_wait(ctx));
@@ -657,7 +716,7 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
         else if (status != 0) { ctx->ro_declined++; ctx->ro_reason[status & 3]++; ctx->ro_declined_n += (uint64_t)pw[16 * j + 3]; }
       }
     }
-    const uint8_t* lists = sb + (outliers ? o_list2 : o_list);
+    const uint8_t* lists = sb + (ro ? o_list2 : o_list);
     if (maxn > 0 && stage_lists) {
       const size_t wbytes = (size_t)maxn * 48;
       ctx->d2h_bytes += (uint64_t)wbytes * nb;
@@ -686,6 +745,26 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
     }
   }
   return VISOCU_OK;
+}
+
+extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
+                            int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
+                            visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers) {
+  return match_impl(ctx, n_jobs, jobs, method, pass, use_prior, ranges, tr_delta, refine, out, cap, n_out, outliers, false);
+}
+
+extern "C" int visocu_match_deferred(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
+                                     int32_t use_prior, const visocu_range* const* ranges, int32_t refine) {
+  return match_impl(ctx, n_jobs, jobs, method, pass, use_prior, ranges, nullptr, refine, nullptr, nullptr, nullptr, nullptr, true);
+}
+
+extern "C" int visocu_match_collect(visocu_ctx* ctx, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers) {
+  if (!ctx || !out || !cap || !n_out || !outliers) return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad collect arguments") : VISOCU_EINVAL;
+  if (!ctx->deferred.pending) return visocu_set_error(ctx, VISOCU_ESTATE, "no deferred matching call to collect");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->deferred.pending = false;
+  CU_TRY(ctx, visocu_stream_wait_on(ctx, 1));
+  return match_tail(ctx, ctx->deferred, out, cap, n_out, outliers);
 }
 
 extern "C" int visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, int32_t mode, visocu_pmatch* inout, int32_t n,

@@ -574,7 +574,7 @@ __global__ void k_outlier_keys(const RoJob* __restrict__ jobs, uint32_t* keys, i
 
 }  // namespace
 
-int visocu_launch_remove_outliers(visocu_ctx* ctx, const RoJob* jobs_dev, int n_jobs, int method, int max_records) {
+int visocu_launch_remove_outliers(visocu_ctx* ctx, const RoJob* jobs_dev, int n_jobs, int method, int max_records, cudaStream_t stream) {
   // shared memory for the largest list of the launch, at most the 227 KB a CTA can have
   size_t smem = ro_smem_bytes(max_records);
   const size_t smem_max = 227 * 1024 - 256;          // the kernel also has a few static shared variables
@@ -589,7 +589,7 @@ int visocu_launch_remove_outliers(visocu_ctx* ctx, const RoJob* jobs_dev, int n_
       done[ctx->device & 63] = true;
     }
   }
-  k_remove_outliers<<<n_jobs, RO_THREADS, smem, ctx->stream>>>(jobs_dev, method, (float)ctx->param.outlier_flow_tolerance,
+  k_remove_outliers<<<n_jobs, RO_THREADS, smem, stream>>>(jobs_dev, method, (float)ctx->param.outlier_flow_tolerance,
                                                               (float)ctx->param.outlier_disp_tolerance, (int)smem);
   CU_LAUNCH_CHECK(ctx);
   return VISOCU_OK;
@@ -647,7 +647,7 @@ extern "C" int visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t m
   }
   memcpy(pin, hj.data(), sizeof(RoJob) * n_jobs);
   CU_COPY(ctx, sb, pin, sizeof(RoJob) * n_jobs, cudaMemcpyHostToDevice);
-  if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)sb, n_jobs, method, maxn))) return rc;
+  if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)sb, n_jobs, method, maxn, ctx->stream))) return rc;
   int32_t* pin_res = (int32_t*)(pin + align_up(sizeof(RoJob) * n_jobs, 256));
   for (int j = 0; j < n_jobs; j++) CU_COPY(ctx, pin_res + 16 * j, hj[j].result, 64, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, visocu_stream_wait(ctx));

@@ -24,4 +24,4 @@ int visocu_launch_outlier_keys(visocu_ctx* ctx, const RoJob* jobs_dev, int n_job
 // records that take part: rep[i] = 1.  Returns false, leaving rep untouched, if all positions are distinct.
 bool ro_resolve_duplicates(const uint32_t* keys, int n_records, uint8_t* rep);
 // launches one CTA per job on the context's stream; jobs is a device array
-int visocu_launch_remove_outliers(visocu_ctx* ctx, const RoJob* jobs_dev, int n_jobs, int method, int max_records);
+int visocu_launch_remove_outliers(visocu_ctx* ctx, const RoJob* jobs_dev, int n_jobs, int method, int max_records, cudaStream_t stream);

@@ -35,11 +35,25 @@ struct Geometry {
 
 struct SlotList { int n; int s[VISO_MAX_BATCH]; };
 
+// state of a matching call whose outlier removal runs on the second stream (visocu_match_deferred / _collect)
+struct visocu_deferred {
+  bool pending = false;
+  int nb = 0;
+  uint8_t* pin_words = nullptr; uint8_t* pin_lists = nullptr;   // pinned: 16 result words per job, staged lists
+  const uint8_t* dev_lists = nullptr; size_t ostride = 0;       // device: survivor lists, uniform stride
+};
+
 struct visocu_ctx {
   int device = 0;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
   char name[64] = {0};
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;    // deferred outlier removal (overlaps the next frame's feature and pass-1 kernels)
+  cudaEvent_t ev_fork = nullptr;
+  visocu_deferred deferred;
+  void* scratch2 = nullptr; size_t scratch2_bytes = 0;
+  void* pinned2 = nullptr;  size_t pinned2_bytes = 0;
+  uint32_t wait_seq2 = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   volatile uint32_t* wait_flag = nullptr; void* wait_flag_dev = nullptr; uint32_t wait_seq = 0;   // see visocu_stream_wait
   cudaEvent_t ev_sync = nullptr;     // blocking-sync event: host threads sleep instead of spinning while the GPU works
@@ -75,7 +89,8 @@ struct visocu_ctx {
 };
 
 int visocu_set_error(visocu_ctx* ctx, int code, const char* fmt, ...);
-cudaError_t visocu_stream_wait(visocu_ctx* ctx);     // waits for the context's stream (yielding the CPU if ev_sync exists)
+cudaError_t visocu_stream_wait(visocu_ctx* ctx);
+cudaError_t visocu_stream_wait_on(visocu_ctx* ctx, int which);   // 0 = main stream, 1 = second stream     // waits for the context's stream (yielding the CPU if ev_sync exists)
 int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes);
 int visocu_ensure_pinned(visocu_ctx* ctx, size_t bytes);
 

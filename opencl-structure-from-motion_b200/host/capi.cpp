@@ -47,6 +47,7 @@ struct MonoAccess : public VisualOdometryMono {
 }  // namespace
 
 VISOB_API void visob_set_device(int device) { visob::set_device(device); }
+VISOB_API void visob_set_pipeline(int on) { visob::set_pipeline(on != 0); }
 
 namespace visob { extern std::atomic<long long> g_stage_ns[8]; extern std::atomic<long long> g_stage_calls[8]; }
 // stage ids: 0 pushBack, 1 matching pass 1, 2 matching pass 2 (+refinement), 3 priors, 4 removeOutliers (< 2000 matches), 5 removeOutliers (larger), 6 ransacEstimateF, 7 estimateMotion (total, includes 6)
@@ -241,17 +242,11 @@ struct Runner {
   Matcher& matcher_of(int seq) { return batches[seq % threads]->sequence(seq / threads); }
 };
 
-// one frame for every sequence of worker `tid`
-void runner_advance(Runner* r, int tid, const uint8_t* const* imgs, const uint8_t* const* imgs2, const int32_t* dims, int on_device,
-                    int bucket, int32_t* n_matches_out, int32_t* ok_out) {
-  uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+// host stages that follow the matching of one frame for every sequence of worker `tid`: bucketing, and for the odometry
+// mode normalisation, sample tables, ONE batched RANSAC call for all of the worker's sequences, pose
+void runner_post(Runner* r, int tid, int bucket, int32_t* n_matches_out, int32_t* ok_out) {
   MatcherBatch* b = r->batches[tid];
-  std::vector<const uint8_t*> i1, i2;
-  for (int s = tid; s < r->S; s += r->threads) { i1.push_back(imgs[s]); if (imgs2) i2.push_back(imgs2[s]); }
-  b->pushBack(i1.data(), imgs2 ? i2.data() : 0, d, false, on_device != 0);
-  b->matchFeatures(r->method);
   if (r->mode == 1) {
-    // bucketing + normalisation + sample tables per sequence, then ONE RANSAC call for all of this worker's sequences
     std::vector<int> ids;
     std::vector<const float*> uv;
     std::vector<int32_t> N;
@@ -288,6 +283,21 @@ void runner_advance(Runner* r, int tid, const uint8_t* const* imgs, const uint8_
     if (n_matches_out) n_matches_out[s] = r->last_matches[s];
     if (ok_out) ok_out[s] = r->last_ok[s];
   }
+}
+
+void runner_push(Runner* r, int tid, const uint8_t* const* imgs, const uint8_t* const* imgs2, const int32_t* dims, int on_device) {
+  uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+  std::vector<const uint8_t*> i1, i2;
+  for (int s = tid; s < r->S; s += r->threads) { i1.push_back(imgs[s]); if (imgs2) i2.push_back(imgs2[s]); }
+  r->batches[tid]->pushBack(i1.data(), imgs2 ? i2.data() : 0, d, false, on_device != 0);
+}
+
+// one frame for every sequence of worker `tid`
+void runner_advance(Runner* r, int tid, const uint8_t* const* imgs, const uint8_t* const* imgs2, const int32_t* dims, int on_device,
+                    int bucket, int32_t* n_matches_out, int32_t* ok_out) {
+  runner_push(r, tid, imgs, imgs2, dims, on_device);
+  r->batches[tid]->matchFeatures(r->method);
+  runner_post(r, tid, bucket, n_matches_out, ok_out);
 }
 
 template <class F> void run_workers(int threads, F work) {
@@ -347,9 +357,28 @@ VISOB_API double visob_runner_run(void* h, int n_steps, const uint8_t* const* im
   auto t0 = std::chrono::steady_clock::now();
   run_workers(r->threads, [&](int tid) {
     visob::set_device(r->device);
-    for (int k = 0; k < n_steps; k++)
-      runner_advance(r, tid, imgs + (size_t)k * r->S, imgs2 ? imgs2 + (size_t)k * r->S : 0, dims, on_device, bucket,
-                     n_matches_out ? n_matches_out + (size_t)k * r->S : 0, ok_out ? ok_out + (size_t)k * r->S : 0);
+    MatcherBatch* b = r->batches[tid];
+    if (!b->pipelineAvailable(r->method)) {
+      for (int k = 0; k < n_steps; k++)
+        runner_advance(r, tid, imgs + (size_t)k * r->S, imgs2 ? imgs2 + (size_t)k * r->S : 0, dims, on_device, bucket,
+                       n_matches_out ? n_matches_out + (size_t)k * r->S : 0, ok_out ? ok_out + (size_t)k * r->S : 0);
+      return;
+    }
+    // Pipelined: the second pass of step k is only enqueued (its outlier removal runs on the second stream) and is
+    // collected during step k + 1, after that step's features and first pass; the host stages of step k follow then.
+    // Every step's results are complete when the call returns.
+    for (int k = 0; k <= n_steps; k++) {
+      bool have = false, current = false;
+      if (k < n_steps) {
+        runner_push(r, tid, imgs + (size_t)k * r->S, imgs2 ? imgs2 + (size_t)k * r->S : 0, dims, on_device);
+        have = b->matchFeaturesPipelined(r->method, &current);
+      } else {
+        have = b->finishPipelined();
+      }
+      const int done = current ? k : k - 1;            // the step whose matches the sequences hold now
+      if ((have || current) && done >= 0 && done < n_steps)
+        runner_post(r, tid, bucket, n_matches_out ? n_matches_out + (size_t)done * r->S : 0, ok_out ? ok_out + (size_t)done * r->S : 0);
+    }
   });
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }

@@ -5,5 +5,7 @@
 namespace visob {
 void set_device(int device);     // affects Matcher / filter:: objects created afterwards by this thread
 int current_device();
+void set_pipeline(bool on);       // MatcherBatch::matchFeaturesPipelined in the sequence runner (default off)
+bool pipeline_enabled();
 }
 #endif

@@ -38,6 +38,15 @@ bool device_outliers() {
   static const bool on = [] { const char* e = getenv("VISOB_HOST_OUTLIERS"); return !(e && e[0] == '1'); }();
   return on;
 }
+// The pipelined runner (MatcherBatch::matchFeaturesPipelined) is off unless asked for: measured on B200 it does not pay,
+// see DESIGN.md section 6.  visob_set_pipeline(1) / VISOB_PIPELINE=1 switch it on.
+static std::atomic<int> g_pipeline(-1);
+void set_pipeline(bool on) { g_pipeline = on ? 1 : 0; }
+bool pipeline_enabled() {
+  int v = g_pipeline.load();
+  if (v < 0) { const char* e = getenv("VISOB_PIPELINE"); v = (e && e[0] == '1') ? 1 : 0; g_pipeline = v; }
+  return v == 1;
+}
 static thread_local int t_device = 0;
 void set_device(int device) { t_device = device; }
 int current_device() { return t_device; }
@@ -403,7 +412,7 @@ void Matcher::removeOutliers(vector<p_match>& p_matched, int32_t method) {
 // MatcherBatch: S independent sequences on ONE context.  Every GPU stage is issued once for all sequences (the C-ABI is
 // batched: one launch per kernel covers all S frames / pairs), the host stages run per sequence in between.  The result
 // of every sequence is identical to what a stand-alone Matcher produces.
-MatcherBatch::MatcherBatch(Matcher::parameters param, int32_t n_sequences) : ctx(0), width(0), height(0) {
+MatcherBatch::MatcherBatch(Matcher::parameters param, int32_t n_sequences) : pending_method(0), pending(false), ctx(0), width(0), height(0) {
   for (int32_t s = 0; s < n_sequences; s++) seq.push_back(new Matcher(param));
   device = visob::current_device();
 }
@@ -506,3 +515,78 @@ void MatcherBatch::matchFeatures(int32_t method) {
   }
   for (int32_t s : active) seq[s]->matchAfterPass2(method);
 }
+
+// ---- pipelined matching (see matcher.h)
+bool MatcherBatch::pipelineAvailable(int32_t method) const {
+  return visob::pipeline_enabled() && method == 0 && !seq.empty() && seq[0]->refineMode() != 2 && visob::device_outliers() &&
+         (int32_t)seq.size() <= 128;
+}
+
+bool MatcherBatch::issuePass2(const vector<int32_t>& active, int32_t method, bool use_prior, int refine) {
+  visob::StageTimer timer(2);
+  const size_t n = active.size();
+  vector<visocu_quad> quads(n);
+  vector<const visocu_range*> rptr(n);
+  pending_cap.assign(n, 0);
+  for (size_t k = 0; k < n; k++) {
+    Matcher* m = seq[active[k]];
+    quads[k] = visocu_quad{m->slot[0], m->slot[1], m->slot[2], m->slot[3]};
+    rptr[k] = reinterpret_cast<const visocu_range*>(m->ranges.data());
+    pending_cap[k] = m->queryCount(1, method) + 1;
+  }
+  const int rc = visocu_match_deferred(ctx, (int32_t)n, quads.data(), method, 1, use_prior ? 1 : 0, use_prior ? rptr.data() : 0, refine);
+  if (rc != VISOCU_OK) { std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl; return false; }
+  pending_active = active; pending_method = method; pending = true;
+  return true;
+}
+
+bool MatcherBatch::collectPending() {
+  if (!pending) return false;
+  visob::StageTimer timer(2);
+  pending = false;
+  const size_t n = pending_active.size();
+  vector<visocu_pmatch*> outs(n);
+  vector<int32_t> cnt(n, 0), done(n, 0);
+  for (size_t k = 0; k < n; k++) {
+    Matcher* m = seq[pending_active[k]];
+    m->p_matched_2.resize((size_t)pending_cap[k]);
+    outs[k] = reinterpret_cast<visocu_pmatch*>(m->p_matched_2.data());
+  }
+  const int rc = visocu_match_collect(ctx, outs.data(), pending_cap.data(), cnt.data(), done.data());
+  if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+  for (size_t k = 0; k < n; k++) {
+    Matcher* m = seq[pending_active[k]];
+    m->p_matched_2.resize(rc == VISOCU_OK ? cnt[k] : 0);
+    m->ro_done[1] = rc == VISOCU_OK && done[k] != 0;
+    m->matchAfterPass2(pending_method);
+  }
+  return rc == VISOCU_OK;
+}
+
+bool MatcherBatch::matchFeaturesPipelined(int32_t method, bool* current) {
+  *current = false;
+  if (!ctx) return false;
+  if (!pipelineAvailable(method)) {
+    const bool had = collectPending();     // cannot happen in a homogeneous run; keeps the state machine sound
+    (void)had;
+    matchFeatures(method);
+    *current = true;
+    return true;
+  }
+  vector<int32_t> active;
+  // matchBegin clears the match lists of the sequences: the previous call's lists are collected into them further down
+  for (size_t s = 0; s < seq.size(); s++)
+    if (seq[s]->matchBegin(method)) active.push_back((int32_t)s);
+  const Matcher::parameters& p = seq[0]->param;
+  const int refine = seq[0]->refineMode();
+  bool pass1_ok = !active.empty();
+  if (pass1_ok && p.multi_stage) {
+    pass1_ok = matchPass(active, 0, method, false, 0);
+    if (pass1_ok) for (int32_t s : active) seq[s]->matchAfterPass1(method);
+  }
+  const bool had_previous = collectPending();
+  if (pass1_ok) issuePass2(active, method, p.multi_stage != 0, refine);
+  return had_previous;
+}
+
+bool MatcherBatch::finishPipelined() { return collectPending(); }

@@ -132,6 +132,14 @@ public:
   // one image (and optionally one right image) per sequence; dims as for Matcher::pushBack
   void pushBack(const uint8_t* const* I1, const uint8_t* const* I2, uint32_t* dims, bool replace, bool on_device = false);
   void matchFeatures(int32_t method);
+  // Pipelined variant for callers that walk many frames (the sequence runner): the second matching pass of this call is
+  // only enqueued - its outlier removal runs on the context's second stream while the caller pushes the next frames - and
+  // the lists of the PREVIOUS call are collected instead.  Returns true if the sequences now hold the previous call's
+  // matches (getMatches etc. refer to those).  finishPipelined() collects the last call.  Falls back to the synchronous
+  // matchFeatures (returning true with the current matches) where deferral is not available: see pipelineAvailable().
+  bool matchFeaturesPipelined(int32_t method, bool* current);
+  bool finishPipelined();
+  bool pipelineAvailable(int32_t method) const;
   int32_t size() const { return (int32_t)seq.size(); }
   Matcher& sequence(int32_t i) { return *seq[i]; }
   visocu_ctx* context() { return ctx; }
@@ -139,6 +147,11 @@ public:
 private:
   bool ensure(int32_t w, int32_t h);
   bool matchPass(const std::vector<int32_t>& active, int pass, int32_t method, bool use_prior, int refine);
+  bool issuePass2(const std::vector<int32_t>& active, int32_t method, bool use_prior, int refine);
+  bool collectPending();
+  std::vector<int32_t> pending_active, pending_cap;     // sequences and list capacities of the enqueued pass
+  int32_t pending_method;
+  bool pending;
   std::vector<Matcher*> seq;
   visocu_ctx* ctx;
   int device;

@@ -268,6 +268,11 @@ class Sfm:
         return out
 
 
+def set_pipeline(on):
+    """Deferred second matching pass in Runner.run (off by default)."""
+    lib().visob_set_pipeline(int(bool(on)))
+
+
 def delaunay(x, y):
     x = np.ascontiguousarray(x, np.int32); y = np.ascontiguousarray(y, np.int32)
     cap = 2 * len(x) + 8

@@ -311,3 +311,48 @@ def test_structure_from_motion_facade():
     assert len(got_pts) == len(want_pts)
     assert np.abs(got_pts - want_pts).max() <= 1e-3 * max(1.0, np.abs(want_pts).max())
     assert np.abs(sfm.pose() - pose).max() < 1e-5
+
+
+def test_pipelined_runner_equals_stepwise():
+    """runner.run walks K frames with the second matching pass of every step deferred (its outlier removal overlaps the
+    next step's feature and pass-1 kernels, MatcherBatch::matchFeaturesPipelined): per step and sequence the same match
+    counts as the stepwise runner, the same final lists, and for the odometry mode the same poses."""
+    S, T = 5, 5
+    dims = np.array([500, 260, 500], np.int32)
+    seqs = [synth.blob_sequence(T, 500, 260, seed=80 + s) for s in range(S)]
+    imgs = [[np.ascontiguousarray(seqs[s][k]) for s in range(S)] for k in range(T)]
+    ptrs = [[i.ctypes.data for i in row] for row in imgs]
+    mp = H.MonoParams(match=V.Params())
+    a = H.Runner(0, S, 2, 0, 0, mp)
+    counts_step = np.array([a.step(ptrs[k], dims)[1] for k in range(T)])
+    want = [a.matches(s) for s in range(S)]
+    a.close()
+    H.set_pipeline(True)
+    b = H.Runner(0, S, 2, 0, 0, mp)
+    secs, nm, ok = b.run(ptrs, dims)
+    got = [b.matches(s) for s in range(S)]
+    b.close()
+    H.set_pipeline(False)
+    assert np.array_equal(nm, counts_step) and nm[1:].min() > 300
+    for s in range(S):
+        assert got[s].tobytes() == want[s].tobytes()
+    # odometry mode
+    S, T = 3, 4
+    seqs = [synth.corridor_sequence(T, seed=1234 + s) for s in range(S)]
+    imgs = [[np.ascontiguousarray(seqs[s][k]) for s in range(S)] for k in range(T)]
+    ptrs = [[i.ctypes.data for i in row] for row in imgs]
+    dims = np.array([1241, 376, 1241], np.int32)
+    _, hp = _mono_params(None, 2)
+    a = H.Runner(0, S, 2, 1, 0, hp)
+    oks = np.array([a.step(ptrs[k], dims)[2] for k in range(T)])
+    want_T = [a.motion(s) for s in range(S)]; want_m = [a.matches(s) for s in range(S)]
+    a.close()
+    H.set_pipeline(True)
+    b = H.Runner(0, S, 2, 1, 0, hp)
+    secs, nm, ok = b.run(ptrs, dims)
+    H.set_pipeline(False)
+    assert np.array_equal(ok, oks) and ok[1:].min() == 1
+    for s in range(S):
+        assert b.matches(s).tobytes() == want_m[s].tobytes()
+        assert np.abs(b.motion(s) - want_T[s]).max() < 1e-9
+    b.close()
