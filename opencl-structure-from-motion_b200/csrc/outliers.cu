@@ -675,7 +675,7 @@ int visocu_launch_outlier_keys(visocu_ctx* ctx, const RoJob* jobs_dev, int n_job
 // positions is the point Triangle triangulates, the others it ignores (they collect no votes and are removed).
 bool ro_resolve_duplicates(const uint32_t* keys, int n_records, uint8_t* rep) {
   static thread_local std::vector<uint32_t> kk, seen_words;
-  static thread_local std::vector<int32_t> a, rec;
+  static thread_local std::vector<int32_t> rec;
   kk.clear(); rec.clear();
   for (int i = 0; i < n_records; i++)
     if (keys[i] != 0xFFFFFFFFu) { kk.push_back(keys[i]); rec.push_back(i); }
@@ -695,26 +695,30 @@ bool ro_resolve_duplicates(const uint32_t* keys, int n_records, uint8_t* rep) {
     seen_words[h] = k;
   }
   if (!dup) return false;
-  a.resize(n);
-  for (int i = 0; i < n; i++) a[i] = i;
+  // elements: position in the high word (what the sort compares), index into rec[] in the low word
+  static thread_local std::vector<unsigned long long> el;
+  el.resize((size_t)n + 1);
+  for (int i = 0; i < n; i++) el[i] = ((unsigned long long)kk[i] << 32) | (unsigned)i;
+  el[n] = ~0ull;
   unsigned seed = 1;
-  std::vector<std::pair<int, int> > stack;
+  static thread_local std::vector<std::pair<int, int> > stack;
+  stack.clear();
   stack.push_back(std::make_pair(0, n));
   while (!stack.empty()) {
     const int lo = stack.back().first, len = stack.back().second;
     stack.pop_back();
     if (len < 2) continue;
-    int32_t* v = a.data() + lo;
+    unsigned long long* v = el.data() + lo;
     if (len == 2) {
-      if (kk[v[0]] > kk[v[1]]) std::swap(v[0], v[1]);
+      if ((v[0] >> 32) > (v[1] >> 32)) std::swap(v[0], v[1]);
       continue;
     }
     seed = (seed * 1366u + 150889u) % 714025u;
-    const uint32_t pkey = kk[v[seed / (714025u / (unsigned)len + 1u)]];
+    const unsigned long long pkey = v[seed / (714025u / (unsigned)len + 1u)] >> 32;
     int left = -1, right = len;
     while (left < right) {
-      do { left++; } while (left <= right && kk[v[left]] < pkey);
-      do { right--; } while (left <= right && kk[v[right]] > pkey);
+      do { left++; } while (left <= right && (v[left] >> 32) < pkey);
+      do { right--; } while (left <= right && (v[right] >> 32) > pkey);
       if (left < right) std::swap(v[left], v[right]);
     }
     if (right < len - 2) stack.push_back(std::make_pair(lo + right + 1, len - right - 1));    // taken second
@@ -722,6 +726,6 @@ bool ro_resolve_duplicates(const uint32_t* keys, int n_records, uint8_t* rep) {
   }
   for (int i = 0; i < n_records; i++) rep[i] = 0;
   for (int i = 0; i < n; i++)
-    if (i == 0 || kk[a[i]] != kk[a[i - 1]]) rep[rec[a[i]]] = 1;
+    if (i == 0 || (el[i] >> 32) != (el[i - 1] >> 32)) rep[rec[(size_t)(el[i] & 0xFFFFFFFFu)]] = 1;
   return true;
 }

@@ -82,3 +82,17 @@ def test_sad_extremes(ctx):
     assert len(m) > 0.9 * n and np.all(m['i1p'] == m['i1c'])
     cand, scanned = ctx.match_stats()
     assert cand >= 2 * n
+
+
+def test_deferred_matching_state_errors(ctx):
+    """visocu_match_deferred / visocu_match_collect: misuse is reported with a status, never a crash."""
+    import ctypes as C
+    lib = V.lib()
+    ctx.configure(V.Params(), 320, 200, 4)
+    n = np.zeros(1, np.int32); cap = np.array([16], np.int32); done = np.zeros(1, np.int32)
+    buf = np.zeros(16, V.P_MATCH); optr = (C.c_void_p * 1)(buf.ctypes.data)
+    rc = lib.visocu_match_collect(ctx.h, optr, cap.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p), done.ctypes.data_as(C.c_void_p))
+    assert rc != 0 and b'no deferred' in lib.visocu_last_error(ctx.h)
+    q = np.zeros(1, V.QUAD); q[0] = (0, 1, 2, 3)
+    rc = lib.visocu_match_deferred(ctx.h, 1, q.ctypes.data_as(C.c_void_p), 2, 1, 0, None, 0)      # quad: not deferrable
+    assert rc != 0 and b'deferred matching' in lib.visocu_last_error(ctx.h)
