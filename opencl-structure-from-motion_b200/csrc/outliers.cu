@@ -138,10 +138,22 @@ __device__ Handles merge(Mesh& m, FreeList& fl, Handles L, Handles R, int axis) 
     const int lowerright = m.org(basel), lowerleft = m.dest(basel);
     int lcand = m.onext(basel ^ 1), rcand = m.oprev(basel);
     int upperleft = m.dest(lcand), upperright = m.dest(rcand);
+    // The first test of the left and of the right candidate loop read disjoint parts of the mesh (the left loop only
+    // touches edges of the left triangulation and the ring of lowerleft, the right loop the mirror image), and most
+    // steps delete nothing.  Both first tests are therefore evaluated up front, before any store, so that their load
+    // chains overlap; the loops below continue from the second candidate on.
+    const int lnx0 = m.onext(lcand), rnx0 = m.oprev(rcand);
+    const int lapex0 = m.dest(lnx0), rapex0 = m.dest(rnx0);
     const bool leftfinished = m.ccw(upperleft, lowerleft, lowerright) <= 0;
     const bool rightfinished = m.ccw(upperright, lowerleft, lowerright) <= 0;
     if (leftfinished && rightfinished) break;
-    if (!leftfinished) {
+    const bool ldel0 = !leftfinished && lnx0 != (basel ^ 1) && m.ccw(lowerleft, upperleft, lapex0) > 0 &&
+                       m.incircle(lowerleft, lowerright, upperleft, lapex0) > 0;
+    const bool rdel0 = !rightfinished && rnx0 != basel && m.ccw(lowerright, rapex0, upperright) > 0 &&
+                       m.incircle(lowerleft, lowerright, upperright, rapex0) > 0;
+    if (ldel0) {
+      remove_edge(m, fl, lcand);
+      lcand = lnx0; upperleft = lapex0;
       while (m.tick()) {
         const int nx = m.onext(lcand);
         if (nx == (basel ^ 1)) break;
@@ -152,7 +164,9 @@ __device__ Handles merge(Mesh& m, FreeList& fl, Handles L, Handles R, int axis) 
         lcand = nx; upperleft = apex;
       }
     }
-    if (!rightfinished) {
+    if (rdel0) {
+      remove_edge(m, fl, rcand);
+      rcand = rnx0; upperright = rapex0;
       while (m.tick()) {
         const int nx = m.oprev(rcand);
         if (nx == basel) break;
