@@ -122,6 +122,16 @@ int  visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int3
 int  visocu_match_deferred(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
                            int32_t use_prior, const visocu_range* const* ranges, int32_t refine);
 int  visocu_match_collect(visocu_ctx* ctx, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers);
+/* Both passes of multi-stage FLOW matching in one submission (matcher.cpp:219-233 without a host round trip): first pass on
+ * the sparse features, its outlier removal, Matcher::computePriorStatistics (matcher.cpp:734-868) on the survivors - on the
+ * device -, second pass on the dense features with those ranges, refinement (0 or 1), outlier removal.  out1 / out2 receive
+ * the two lists, done1 / done2 say whether the outlier removal of the list ran on the device (if done1[j] is 0 the second
+ * list of job j is meaningless: the caller votes on list 1 itself and repeats the second pass with visocu_match);
+ * ranges_out[j] (optional, u_bins * v_bins entries) receives the prior ranges.  At most 128 jobs. */
+int  visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine,
+                        visocu_pmatch* const* out1, const int32_t* cap1, int32_t* n1, int32_t* done1,
+                        visocu_pmatch* const* out2, const int32_t* cap2, int32_t* n2, int32_t* done2,
+                        visocu_range* const* ranges_out);
 /* Matcher::removeOutliers alone on caller-supplied match lists (host memory, compacted in place).  status[j] = 0: done,
  * 1: list unchanged, not handled by the device path (see visocu_match). */
 int  visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t method, visocu_pmatch* const* inout, const int32_t* n,

@@ -147,6 +147,8 @@ extern "C" void visocu_destroy(visocu_ctx* ctx) {
   free_pool(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->scratch2) cudaFree(ctx->scratch2);
+  if (ctx->d_ranges) cudaFree(ctx->d_ranges);
+  if (ctx->pin_ranges) cudaFreeHost(ctx->pin_ranges);
   if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->img_stage) cudaFree(ctx->img_stage);

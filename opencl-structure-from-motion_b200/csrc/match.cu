@@ -512,7 +512,8 @@ int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJ
 
 // The tail of a matching call: result words are in pinned memory; fetch the lists and hand everything to the caller.
 static int match_tail(visocu_ctx* ctx, const visocu_deferred& st, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out,
-                      int32_t* outliers) {
+                      int32_t* outliers, int which_stream) {
+  cudaStream_t stream = which_stream ? ctx->stream2 : ctx->stream;
   const int nb = st.nb;
   const int32_t* pw = (const int32_t*)st.pin_words;
   int maxn = 0;
@@ -529,8 +530,8 @@ static int match_tail(visocu_ctx* ctx, const visocu_deferred& st, visocu_pmatch*
   if (maxn > 0) {
     const size_t wbytes = (size_t)maxn * 48;
     ctx->d2h_bytes += (uint64_t)wbytes * nb;
-    CU_TRY(ctx, cudaMemcpy2DAsync(st.pin_lists, wbytes, st.dev_lists, st.ostride, wbytes, nb, cudaMemcpyDeviceToHost, ctx->stream2));
-    CU_TRY(ctx, visocu_stream_wait_on(ctx, 1));
+    CU_TRY(ctx, cudaMemcpy2DAsync(st.pin_lists, wbytes, st.dev_lists, st.ostride, wbytes, nb, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(ctx, visocu_stream_wait_on(ctx, which_stream));
     for (int j = 0; j < nb; j++)
       if (n_out[j] > 0) memcpy(out[j], st.pin_lists + wbytes * j, (size_t)n_out[j] * 48);
   }
@@ -549,21 +550,28 @@ struct ScratchSwap {
   }
 };
 
+// mode 0: complete call.  1: deferred (outlier removal on the second stream, second scratch set, visocu_match_collect).
+// 2 / 3: first / second pass of a fused call (visocu_match_fused): everything enqueued on the main stream, nothing
+// waited for, state in ctx->part[]; the second pass works in the second scratch set and takes its prior ranges from
+// device memory (dev_ranges, one block of dev_ranges_stride bytes per job).
 static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
                       int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
-                      visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers, bool deferred) {
+                      visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers, int mode,
+                      const uint8_t* dev_ranges = nullptr, size_t dev_ranges_stride = 0) {
+  const bool deferred = mode != 0;                   // no result is delivered by this call
+  const bool second_set = mode == 1 || mode == 3;
   if (!ctx) return VISOCU_EINVAL;
   if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
   if (n_jobs <= 0 || !jobs || (!deferred && (!out || !cap || !n_out))) return visocu_set_error(ctx, VISOCU_EINVAL, "bad match arguments");
-  if (deferred && ctx->deferred.pending) return visocu_set_error(ctx, VISOCU_ESTATE, "a deferred matching call has not been collected");
+  if (mode != 0 && ctx->deferred.pending) return visocu_set_error(ctx, VISOCU_ESTATE, "a deferred matching call has not been collected");
   if (deferred && (method != 0 || n_jobs > VISO_MAX_BATCH || refine == 2))
     return visocu_set_error(ctx, VISOCU_EINVAL, "deferred matching: flow method, pixel refinement, at most %d jobs", VISO_MAX_BATCH);
-  ScratchSwap swap_guard(ctx, deferred);
+  ScratchSwap swap_guard(ctx, second_set);
   if (method < 0 || method > 2) return visocu_set_error(ctx, VISOCU_EINVAL, "method %d not supported (0 = flow, 1 = stereo, 2 = quad)", method);
   if (refine < 0 || refine > 2) return visocu_set_error(ctx, VISOCU_EINVAL, "refine must be 0, 1 or 2");
   if (refine == 2) { int rc0 = upload_pinv(ctx); if (rc0) return rc0; }
   if (pass < ctx->g.first_pass || pass > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "pass %d not available", pass);
-  if (use_prior && !ranges) return visocu_set_error(ctx, VISOCU_EINVAL, "use_prior needs ranges");
+  if (use_prior && !ranges && !dev_ranges) return visocu_set_error(ctx, VISOCU_EINVAL, "use_prior needs ranges");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const Geometry& g = ctx->g;
   const int nstat = g.ub * g.vb;
@@ -582,13 +590,13 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
       const int nq = empty ? 0 : (method == 2 ? hj[j].s[0].n : hj[j].s[2].n);
       hj[j].nq = nq;
       if (nq > maxq) maxq = nq;
-      if (use_prior && !ranges[start + j]) return visocu_set_error(ctx, VISOCU_EINVAL, "job %d has no ranges", start + j);
+      if (use_prior && !dev_ranges && !ranges[start + j]) return visocu_set_error(ctx, VISOCU_EINVAL, "job %d has no ranges", start + j);
     }
     // Device scratch.  A header block (job descriptors of both kernels and the prior ranges of every job) goes up in ONE
     // copy; the per-job result words come back in ONE copy; the match lists have a uniform stride so that ONE 2-D copy
     // into pinned memory fetches them all.  (Every API call costs microseconds under the driver's lock, and with many
     // worker threads sharing a GPU that lock is what bounds the throughput.)
-    const size_t rb = use_prior ? align_up((size_t)nstat * sizeof(visocu_range), 256) : 0;
+    const size_t rb = (use_prior && !dev_ranges) ? align_up((size_t)nstat * sizeof(visocu_range), 256) : 0;
     const size_t h_mj = 0, h_rj = align_up(sizeof(MatchJob) * nb, 256);
     const size_t h_rng = h_rj + (ro ? align_up(sizeof(RoJob) * nb, 256) : 0);
     const size_t hdr_bytes = h_rng + rb * nb;
@@ -630,7 +638,9 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
       hj[j].f = ctx->param.f; hj[j].cu = ctx->param.cu; hj[j].cv = ctx->param.cv; hj[j].base = ctx->param.base;
       hj[j].has_tr = (method == 2 && tr_delta && tr_delta[start + j]) ? 1 : 0;
       if (hj[j].has_tr) memcpy(hj[j].tr, tr_delta[start + j], sizeof hj[j].tr);
-      if (use_prior) {
+      if (use_prior && dev_ranges) {
+        hj[j].ranges = (const visocu_range*)(dev_ranges + dev_ranges_stride * j);
+      } else if (use_prior) {
         memcpy(pin + h_rng + rb * j, ranges[start + j], (size_t)nstat * sizeof(visocu_range));
         hj[j].ranges = (const visocu_range*)(sb + h_rng + rb * j);
       }
@@ -685,7 +695,18 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
         CU_COPY(ctx, sb + h_rj, pin + h_rj, sizeof(RoJob) * nb, cudaMemcpyHostToDevice);
       }
     }
-    if (deferred) {
+    if (mode >= 2) {
+      // one pass of a fused call: outlier removal and the read-back of the result words queued on the main stream
+      if (!stage_lists) return visocu_set_error(ctx, VISOCU_EINVAL, "fused matching: lists too large for the staging area");
+      if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, maxq, ctx->stream))) return rc;
+      ctx->d2h_bytes += words_bytes;
+      CU_TRY(ctx, cudaMemcpyAsync(pin + p_words, sb + o_words, words_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      visocu_deferred& st = ctx->part[mode - 2];
+      st.pending = true; st.nb = nb; st.pin_words = pin + p_words; st.pin_lists = pin + p_lists;
+      st.dev_lists = sb + o_list2; st.ostride = ostride; st.dev_words = (const int32_t*)(sb + o_words);
+      return VISOCU_OK;
+    }
+    if (mode == 1) {
       // The outlier removal and the read-back of its result words go to the second stream, behind the kernels above;
       // the caller's next feature and pass-1 launches on the first stream do not wait for them.
       if (!stage_lists) return visocu_set_error(ctx, VISOCU_EINVAL, "deferred matching: lists too large for the staging area");
@@ -747,15 +768,81 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
   return VISOCU_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Matcher::computePriorStatistics (matcher.cpp:734-868) for the flow method, on the survivors of the first pass where
+// the outlier kernel left them: per bin, minimum and maximum of the displacements of all matches in the 3x3 bin
+// neighbourhood, widened to at least 20 pixels, or +-match_radius for bins nobody touched.  One CTA per job.  Minima
+// and maxima of a set do not depend on the order, so float atomics (as ordered integers) reproduce the host loop exactly.
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (v >= 0.f) atomicMin((int*)addr, __float_as_int(v)); else atomicMax((unsigned int*)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax((int*)addr, __float_as_int(v)); else atomicMin((unsigned int*)addr, __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(256) k_prior_ranges(Geometry g, const uint8_t* lists, size_t ostride, const int32_t* words,
+                                                      uint8_t* ranges, size_t rstride, float* tmp_global, int use_smem) {
+  extern __shared__ float s_tmp[];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  const int nbin = g.ub * g.vb;
+  float* lo = use_smem ? s_tmp : tmp_global + (size_t)j * 9 * nbin;         // 4 values per bin each, then the seen flags
+  float* hi = lo + 4 * nbin;
+  float* seen = hi + 4 * nbin;
+  for (int i = tid; i < 4 * nbin; i += 256) { lo[i] = 1000000.f; hi[i] = -1000000.f; }
+  for (int i = tid; i < nbin; i += 256) seen[i] = 0.f;
+  __syncthreads();
+  const int n = words[16 * j + 1] == 0 ? words[16 * j] : 0;                 // a declined list is redone by the caller
+  const visocu_pmatch* list = (const visocu_pmatch*)(lists + ostride * j);
+  const float bs = (float)g.binsize;
+  for (int i = tid; i < n; i += 256) {
+    const visocu_pmatch m = list[i];
+    const float d[4] = {__fsub_rn(m.u1p, m.u1c), __fsub_rn(m.v1p, m.v1c), __fsub_rn(m.u1c, m.u1p), __fsub_rn(m.v1c, m.v1p)};
+    const int cu = (int)floorf(__fdiv_rn(m.u1c, bs)), cv = (int)floorf(__fdiv_rn(m.v1c, bs));
+    const int u0 = min(max(cu - 1, 0), g.ub - 1), u1 = min(max(cu + 1, 0), g.ub - 1);
+    const int v0 = min(max(cv - 1, 0), g.vb - 1), v1 = min(max(cv + 1, 0), g.vb - 1);
+    for (int v = v0; v <= v1; v++)
+      for (int u = u0; u <= u1; u++) {
+        const int b = v * g.ub + u;
+        seen[b] = 1.f;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { atomic_min_float(&lo[4 * b + k], d[k]); atomic_max_float(&hi[4 * b + k], d[k]); }
+      }
+  }
+  __syncthreads();
+  visocu_range* out = (visocu_range*)(ranges + rstride * j);
+  const float radius = (float)g.radius;
+  for (int b = tid; b < nbin; b += 256) {
+    visocu_range r;
+    memset(&r, 0, sizeof r);
+    const bool s = seen[b] != 0.f;
+#pragma unroll
+    for (int st = 0; st < 2; st++) {
+      float dmin[2], dmax[2];
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+        dmin[a] = s ? lo[4 * b + 2 * st + a] : -radius;
+        dmax[a] = s ? hi[4 * b + 2 * st + a] : radius;
+        const float span = __fsub_rn(dmax[a], dmin[a]);
+        if (span < 20.f) {                                                   // matcher.cpp:845-854
+          const float grow = ceilf(__fdiv_rn(__fsub_rn(20.f, span), 2.f));
+          dmin[a] = __fsub_rn(dmin[a], grow); dmax[a] = __fadd_rn(dmax[a], grow);
+        }
+      }
+      r.u_min[st] = dmin[0]; r.u_max[st] = dmax[0]; r.v_min[st] = dmin[1]; r.v_max[st] = dmax[1];
+    }
+    out[b] = r;
+  }
+}
+
 extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
                             int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
                             visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers) {
-  return match_impl(ctx, n_jobs, jobs, method, pass, use_prior, ranges, tr_delta, refine, out, cap, n_out, outliers, false);
+  return match_impl(ctx, n_jobs, jobs, method, pass, use_prior, ranges, tr_delta, refine, out, cap, n_out, outliers, 0);
 }
 
 extern "C" int visocu_match_deferred(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
                                      int32_t use_prior, const visocu_range* const* ranges, int32_t refine) {
-  return match_impl(ctx, n_jobs, jobs, method, pass, use_prior, ranges, nullptr, refine, nullptr, nullptr, nullptr, nullptr, true);
+  return match_impl(ctx, n_jobs, jobs, method, pass, use_prior, ranges, nullptr, refine, nullptr, nullptr, nullptr, nullptr, 1);
 }
 
 extern "C" int visocu_match_collect(visocu_ctx* ctx, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers) {
@@ -764,7 +851,61 @@ extern "C" int visocu_match_collect(visocu_ctx* ctx, visocu_pmatch* const* out, 
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   ctx->deferred.pending = false;
   CU_TRY(ctx, visocu_stream_wait_on(ctx, 1));
-  return match_tail(ctx, ctx->deferred, out, cap, n_out, outliers);
+  return match_tail(ctx, ctx->deferred, out, cap, n_out, outliers, 1);
+}
+
+extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine,
+                                  visocu_pmatch* const* out1, const int32_t* cap1, int32_t* n1, int32_t* done1,
+                                  visocu_pmatch* const* out2, const int32_t* cap2, int32_t* n2, int32_t* done2,
+                                  visocu_range* const* ranges_out) {
+  if (!ctx) return VISOCU_EINVAL;
+  if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
+  if (n_jobs <= 0 || n_jobs > VISO_MAX_BATCH || !jobs || !out1 || !cap1 || !n1 || !done1 || !out2 || !cap2 || !n2 || !done2)
+    return visocu_set_error(ctx, VISOCU_EINVAL, "bad fused match arguments (at most %d jobs)", VISO_MAX_BATCH);
+  if (ctx->g.first_pass != 0) return visocu_set_error(ctx, VISOCU_EINVAL, "fused matching needs multi_stage");
+  if (refine < 0 || refine > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "fused matching: refine must be 0 or 1");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const Geometry& g = ctx->g;
+  const int nbin = g.ub * g.vb;
+  const size_t rstride = align_up((size_t)nbin * sizeof(visocu_range), 256);
+  const size_t tmp_bytes = (size_t)n_jobs * 9 * nbin * sizeof(float);
+  const size_t need = rstride * n_jobs + tmp_bytes;
+  if (need > ctx->d_ranges_bytes) {
+    CU_TRY(ctx, visocu_stream_wait(ctx));
+    if (ctx->d_ranges) cudaFree(ctx->d_ranges);
+    ctx->d_ranges = nullptr; ctx->d_ranges_bytes = 0;
+    CU_TRY(ctx, cudaMalloc(&ctx->d_ranges, need));
+    ctx->d_ranges_bytes = need;
+    if (ctx->pin_ranges) cudaFreeHost(ctx->pin_ranges);
+    ctx->pin_ranges = nullptr;
+    CU_TRY(ctx, cudaMallocHost(&ctx->pin_ranges, rstride * VISO_MAX_BATCH));
+  }
+  uint8_t* d_rng = (uint8_t*)ctx->d_ranges;
+  // first pass (sparse features, no prior) and its outlier removal
+  int rc = match_impl(ctx, n_jobs, jobs, 0, 0, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 2);
+  if (rc) return rc;
+  // prior ranges from its survivors, on the device
+  const visocu_deferred& A = ctx->part[0];
+  const size_t smem = (size_t)9 * nbin * sizeof(float);
+  const int use_smem = smem <= 40 * 1024 ? 1 : 0;
+  k_prior_ranges<<<n_jobs, 256, use_smem ? smem : 0, ctx->stream>>>(g, A.dev_lists, A.ostride, A.dev_words, d_rng, rstride,
+                                                                   (float*)(d_rng + rstride * n_jobs), use_smem);
+  CU_LAUNCH_CHECK(ctx);
+  // second pass (dense features, the ranges as prior), refinement, outlier removal
+  rc = match_impl(ctx, n_jobs, jobs, 0, 1, 1, nullptr, nullptr, refine, nullptr, nullptr, nullptr, nullptr, 3, d_rng, rstride);
+  if (rc) return rc;
+  if (ranges_out) {
+    ctx->d2h_bytes += rstride * n_jobs;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->pin_ranges, d_rng, rstride * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU_TRY(ctx, visocu_stream_wait(ctx));
+  ctx->part[0].pending = ctx->part[1].pending = false;
+  if ((rc = match_tail(ctx, ctx->part[0], out1, cap1, n1, done1, 0))) return rc;
+  if ((rc = match_tail(ctx, ctx->part[1], out2, cap2, n2, done2, 0))) return rc;
+  if (ranges_out)
+    for (int j = 0; j < n_jobs; j++)
+      if (ranges_out[j]) memcpy(ranges_out[j], (const uint8_t*)ctx->pin_ranges + rstride * j, (size_t)nbin * sizeof(visocu_range));
+  return VISOCU_OK;
 }
 
 extern "C" int visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, int32_t mode, visocu_pmatch* inout, int32_t n,

@@ -41,6 +41,7 @@ struct visocu_deferred {
   int nb = 0;
   uint8_t* pin_words = nullptr; uint8_t* pin_lists = nullptr;   // pinned: 16 result words per job, staged lists
   const uint8_t* dev_lists = nullptr; size_t ostride = 0;       // device: survivor lists, uniform stride
+  const int32_t* dev_words = nullptr;                           // device: the 16 result words per job
 };
 
 struct visocu_ctx {
@@ -51,6 +52,8 @@ struct visocu_ctx {
   cudaStream_t stream2 = nullptr;    // deferred outlier removal (overlaps the next frame's feature and pass-1 kernels)
   cudaEvent_t ev_fork = nullptr;
   visocu_deferred deferred;
+  visocu_deferred part[2];           // the two passes of a fused call (visocu_match_fused)
+  void* d_ranges = nullptr; size_t d_ranges_bytes = 0; void* pin_ranges = nullptr;   // prior ranges computed on the device between the passes
   void* scratch2 = nullptr; size_t scratch2_bytes = 0;
   void* pinned2 = nullptr;  size_t pinned2_bytes = 0;
   uint32_t wait_seq2 = 0;

@@ -88,6 +88,12 @@ VISOB_API int visob_matcher_prior(void* m, const void* matches, int n, int metho
   return (int)r.size();
 }
 
+VISOB_API int visob_matcher_ranges(void* m, float* ranges_out, int cap_bins) {     // the ranges the last matchFeatures used
+  const std::vector<Matcher::range>& r = ((Matcher*)m)->priorRanges();
+  if (ranges_out) memcpy(ranges_out, r.data(), sizeof(Matcher::range) * (size_t)std::min((int)r.size(), cap_bins));
+  return (int)r.size();
+}
+
 // ---- filter::
 VISOB_API int visob_filter(int which, const uint8_t* in, uint8_t* out_a, uint8_t* out_b, int16_t* out16, int w, int h) {
   try {

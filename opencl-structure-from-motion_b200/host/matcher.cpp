@@ -212,6 +212,10 @@ void Matcher::matchFeatures(int32_t method, Matrix* Tr_delta) {
     visocu_set_intrinsics(ctx, vp.f, vp.cu, vp.cv, vp.base);      // setIntrinsics may have been called after the first push
   }
   const int refine = refineMode();
+  if (fusedAvailable(*this, method)) {
+    fusedMatch(ctx, vector<Matcher*>(1, this), method);
+    return;
+  }
   if (param.multi_stage) {
     if (!matching(0, p_matched_1, method, false, 0)) return;
     matchAfterPass1(method);
@@ -220,6 +224,52 @@ void Matcher::matchFeatures(int32_t method, Matrix* Tr_delta) {
     if (!matching(1, p_matched_2, method, false, refine)) return;
   }
   matchAfterPass2(method);
+}
+
+// Flow matching with both passes, the outlier removal of both and the prior statistics in between on the device, one
+// submission and one wait per call.  VISOB_FUSED=0 keeps the pass-by-pass path (host prior statistics).
+bool Matcher::fusedAvailable(const Matcher& m, int32_t method) {
+  static const bool on = [] { const char* e = getenv("VISOB_FUSED"); return !(e && e[0] == '0'); }();
+  return on && method == 0 && m.param.multi_stage && m.refineMode() != 2 && visob::device_outliers() && !m.has_tr;
+}
+
+void Matcher::fusedMatch(visocu_ctx* ctx, const vector<Matcher*>& group, int32_t method) {
+  visob::StageTimer timer(2);
+  const size_t n = group.size();
+  vector<visocu_quad> quads(n);
+  vector<visocu_pmatch*> o1(n), o2(n);
+  vector<visocu_range*> rp(n);
+  vector<int32_t> c1(n), c2(n), n1(n, 0), n2(n, 0), d1(n, 0), d2(n, 0);
+  for (size_t k = 0; k < n; k++) {
+    Matcher* m = group[k];
+    quads[k] = visocu_quad{m->slot[0], m->slot[1], m->slot[2], m->slot[3]};
+    c1[k] = m->queryCount(0, method) + 1; c2[k] = m->queryCount(1, method) + 1;
+    m->p_matched_1.resize((size_t)c1[k]); m->p_matched_2.resize((size_t)c2[k]);
+    o1[k] = reinterpret_cast<visocu_pmatch*>(m->p_matched_1.data());
+    o2[k] = reinterpret_cast<visocu_pmatch*>(m->p_matched_2.data());
+    const float bs = (float)m->param.match_binsize;
+    const size_t nbin = (size_t)ceil((float)m->dims_c[0] / bs) * (size_t)ceil((float)m->dims_c[1] / bs);
+    m->ranges.resize(nbin);
+    rp[k] = reinterpret_cast<visocu_range*>(m->ranges.data());
+  }
+  const int rc = visocu_match_fused(ctx, (int32_t)n, quads.data(), group[0]->refineMode(), o1.data(), c1.data(), n1.data(), d1.data(),
+                                    o2.data(), c2.data(), n2.data(), d2.data(), rp.data());
+  if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+  for (size_t k = 0; k < n; k++) {
+    Matcher* m = group[k];
+    m->p_matched_1.resize(rc == VISOCU_OK ? n1[k] : 0);
+    m->p_matched_2.resize(rc == VISOCU_OK ? n2[k] : 0);
+    m->ro_done[0] = rc == VISOCU_OK && d1[k] != 0;
+    m->ro_done[1] = rc == VISOCU_OK && d2[k] != 0;
+    if (rc != VISOCU_OK) continue;
+    if (!m->ro_done[0]) {
+      // the device declined the first list (too long, degenerate): the second pass ran on ranges of nothing - redo it
+      // pass by pass for this matcher
+      m->matchAfterPass1(method);
+      if (!m->matching(1, m->p_matched_2, method, true, m->refineMode())) continue;
+    }
+    m->matchAfterPass2(method);
+  }
 }
 
 // sanity checks of matcher.cpp:190-212: silently keep the old matches if a needed set is empty
@@ -506,6 +556,12 @@ void MatcherBatch::matchFeatures(int32_t method) {
   if (active.empty()) return;
   const Matcher::parameters& p = seq[0]->param;
   const int refine = seq[0]->refineMode();
+  if (Matcher::fusedAvailable(*seq[0], method) && active.size() <= 128) {
+    vector<Matcher*> group;
+    for (int32_t s : active) group.push_back(seq[s]);
+    Matcher::fusedMatch(ctx, group, method);
+    return;
+  }
   if (p.multi_stage) {
     if (!matchPass(active, 0, method, false, 0)) return;
     for (int32_t s : active) seq[s]->matchAfterPass1(method);

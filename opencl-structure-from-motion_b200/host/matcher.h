@@ -98,6 +98,9 @@ private:
   bool ensureContext(int32_t w, int32_t h);
   bool fetchImage(int which, std::vector<uint8_t>& out);
   bool matching(int pass, std::vector<p_match>& out, int32_t method, bool use_prior, int refine);
+  // both passes of multi-stage flow matching as one submission (visocu_match_fused) for a group of matchers on one context
+  static bool fusedAvailable(const Matcher& m, int32_t method);
+  static void fusedMatch(visocu_ctx* ctx, const std::vector<Matcher*>& group, int32_t method);
 
   parameters param;
   int32_t margin;

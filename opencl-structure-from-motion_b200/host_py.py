@@ -137,6 +137,14 @@ class Matcher:
         n = lib().visob_matcher_remove_outliers(self.h, _p(m), len(m), method)
         return m[:n].copy()
 
+    def ranges(self):
+        """Prior ranges of the last matchFeatures (computed on the device for multi-stage flow matching)."""
+        nb = lib().visob_matcher_ranges(self.h, None, 0)
+        out = np.zeros((nb, 16), np.float32)
+        if nb:
+            lib().visob_matcher_ranges(self.h, _p(out), nb)
+        return out
+
     def prior(self, matches, method):
         m = np.ascontiguousarray(matches, dtype=P_MATCH)
         nb = lib().visob_matcher_prior(self.h, _p(m), len(m), method, None, 0)

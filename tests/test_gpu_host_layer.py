@@ -356,3 +356,21 @@ def test_pipelined_runner_equals_stepwise():
         assert b.matches(s).tobytes() == want_m[s].tobytes()
         assert np.abs(b.motion(s) - want_T[s]).max() < 1e-9
     b.close()
+
+
+def test_device_prior_ranges_equal_reference(ref):
+    """Multi-stage flow matching computes Matcher::computePriorStatistics (matcher.cpp:734-868) on the device between the
+    two passes (k_prior_ranges): the ranges must be bit-identical to the reference's statistics of the same first-pass
+    list, in half- and full-resolution mode."""
+    a, b = synth.blob_pair(1244, 376, seed=91, shift=(4, -2))
+    for kw in (dict(), dict(half_resolution=0)):
+        assert pad_safe_width(1244, 3, kw.get('half_resolution', 1))
+        rm = ref.matcher(pyref.MatcherParams(**kw)); hm = H.Matcher(V.Params(**kw))
+        for m in (rm, hm):
+            m.push(a); m.push(b); m.match_features(0)
+        first = hm.matches(1)
+        assert len(first) > 200 and first.tobytes() == rm.matches(1).tobytes()
+        # flow matching uses stages 0 and 1 of the four a range holds (matcher.cpp:1020-1026); the others are never read
+        want = rm.prior(first, 0).reshape(-1, 4, 4)[:, :, :2]
+        got = hm.ranges().reshape(-1, 4, 4)[:, :, :2]
+        assert got.shape == want.shape and got.tobytes() == want.tobytes()
