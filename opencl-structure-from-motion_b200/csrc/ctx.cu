@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <sched.h>
+#include <time.h>
 #include <cstring>
 #include <cmath>
 #include <cstdlib>
@@ -54,13 +55,22 @@ cudaError_t visocu_stream_wait_on(visocu_ctx* ctx, int which) {
     const uint32_t seq = ++counter;
     volatile uint32_t* flag = ctx->wait_flag + (which ? 8 : 0);          // two words of the 64-byte block
     if (wv((CUstream)st, (CUdeviceptr)((uintptr_t)ctx->wait_flag_dev + (which ? 32 : 0)), seq, 0) == CUDA_SUCCESS) {
+      // VISOCU_WAIT_SLEEP_US=n (set by callers that run more worker threads than they have cores): after a short
+      // spin the thread sleeps n microseconds between polls, so that it does not take half of a shared core away from
+      // a worker that has host work to do
+      static const int sleep_us = [] { const char* e = getenv("VISOCU_WAIT_SLEEP_US"); return e ? atoi(e) : 0; }();
       unsigned spins = 0;
       while (*flag != seq) {
         if ((++spins & 0x3FFF) == 0) {                 // now and then: did the stream die?
           cudaError_t e = cudaStreamQuery(st);
           if (e != cudaSuccess && e != cudaErrorNotReady) return e;
         }
-        sched_yield();
+        if (sleep_us > 0 && spins > 64) {
+          struct timespec ts = {0, (long)sleep_us * 1000L};
+          nanosleep(&ts, nullptr);
+        } else {
+          sched_yield();
+        }
       }
       return cudaSuccess;
     }
