@@ -166,6 +166,11 @@ int  visocu_ransac_F(visocu_ctx* ctx, int32_t n_jobs, const float* const* uv, co
 int  visocu_triangulate(visocu_ctx* ctx, const float* uv, int32_t N, const double* P1, const double* P2, int32_t n_sol,
                         double* X, int32_t* n_front);
 int  visocu_best_plane(visocu_ctx* ctx, const double* d, int32_t n, double threshold, double weight, int32_t* best_idx);
+/* batched forms: one upload, one launch, one read-back for n_jobs problems (at most 128) */
+int  visocu_triangulate_batch(visocu_ctx* ctx, int32_t n_jobs, const float* const* uv, const int32_t* N, const double* const* P1,
+                              const double* const* P2, const int32_t* n_sol, double* const* X, int32_t* const* n_front);
+int  visocu_best_plane_batch(visocu_ctx* ctx, int32_t n_jobs, const double* const* d, const int32_t* n, const double* threshold,
+                             const double* weight, int32_t* best_idx);
 
 /* host<->device bytes copied by this context since creation (bench.py's h2d / d2h bytes per step) */
 int  visocu_transfer_bytes(const visocu_ctx* ctx, uint64_t* h2d, uint64_t* d2h);

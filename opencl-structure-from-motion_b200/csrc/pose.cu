@@ -20,8 +20,10 @@ struct TriJob {
   double P2[4][12];
 };
 
-__global__ void __launch_bounds__(128) k_triangulate(TriJob job) {
+__global__ void __launch_bounds__(128) k_triangulate(const TriJob* __restrict__ jobs) {
+  const TriJob& job = jobs[blockIdx.z];
   const int i = blockIdx.x * 128 + threadIdx.x, sol = blockIdx.y;
+  if (sol >= job.n_sol) return;
   int front = 0;
   if (i < job.N) {
     const float4 m = job.uv[i];
@@ -92,7 +94,12 @@ __global__ void __launch_bounds__(128) k_triangulate(TriJob job) {
 
 // one warp per candidate i: sum_j exp(-(d_j - d_i)^2 w) with a fixed lane-strided + butterfly summation order
 // (deterministic; differs from the reference's sequential order only in rounding).  Candidates need d_i > threshold.
-__global__ void __launch_bounds__(256) k_plane_sums(const double* d, int n, double threshold, double weight, double* sums) {
+struct PlaneJob { const double* d; double* sums; double threshold, weight; int n, pad; };
+
+__global__ void __launch_bounds__(256) k_plane_sums(const PlaneJob* __restrict__ jobs) {
+  const PlaneJob J = jobs[blockIdx.y];
+  const double* d = J.d; double* sums = J.sums;
+  const int n = J.n; const double threshold = J.threshold, weight = J.weight;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= n) return;
   const double di = d[i];
@@ -112,55 +119,106 @@ __global__ void __launch_bounds__(256) k_plane_sums(const double* d, int n, doub
 
 }  // namespace
 
+extern "C" int visocu_triangulate_batch(visocu_ctx* ctx, int32_t n_jobs, const float* const* uv, const int32_t* N, const double* const* P1,
+                                        const double* const* P2, const int32_t* n_sol, double* const* X, int32_t* const* n_front) {
+  if (!ctx || n_jobs <= 0 || n_jobs > VISO_MAX_BATCH || !uv || !N || !P1 || !P2 || !n_sol || !X || !n_front)
+    return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad triangulate arguments") : VISOCU_EINVAL;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  // one upload (job descriptors + coordinates), one launch, one read-back (points + counters), pinned staging
+  std::vector<TriJob> hj(n_jobs);
+  std::vector<size_t> o_uv(n_jobs), o_X(n_jobs), o_cnt(n_jobs);
+  size_t off = align_up(sizeof(TriJob) * n_jobs, 256);
+  int maxN = 0, maxsol = 0;
+  for (int j = 0; j < n_jobs; j++) {
+    if (!uv[j] || !P1[j] || !P2[j] || !X[j] || !n_front[j] || N[j] <= 0 || n_sol[j] < 1 || n_sol[j] > 4)
+      return visocu_set_error(ctx, VISOCU_EINVAL, "bad triangulate job %d", j);
+    o_uv[j] = off; off += align_up((size_t)N[j] * 16, 256);
+    if (N[j] > maxN) maxN = N[j];
+    if (n_sol[j] > maxsol) maxsol = n_sol[j];
+  }
+  const size_t up_bytes = off;
+  for (int j = 0; j < n_jobs; j++) {
+    o_X[j] = off; off += align_up((size_t)n_sol[j] * 4 * N[j] * 8, 256);
+    o_cnt[j] = off; off += 256;
+  }
+  int rc = visocu_ensure_scratch(ctx, off);
+  if (rc) return rc;
+  if ((rc = visocu_ensure_pinned(ctx, off))) return rc;
+  uint8_t* sb = (uint8_t*)ctx->scratch;
+  uint8_t* pin = (uint8_t*)ctx->pinned;
+  for (int j = 0; j < n_jobs; j++) {
+    TriJob& job = hj[j];
+    job.uv = (const float4*)(sb + o_uv[j]); job.X = (double*)(sb + o_X[j]); job.n_front = (int32_t*)(sb + o_cnt[j]);
+    job.N = N[j]; job.n_sol = n_sol[j];
+    memcpy(job.P1, P1[j], sizeof job.P1);
+    memcpy(job.P2, P2[j], sizeof(double) * 12 * n_sol[j]);
+    memcpy(pin + o_uv[j], uv[j], (size_t)N[j] * 16);
+  }
+  memcpy(pin, hj.data(), sizeof(TriJob) * n_jobs);
+  CU_COPY(ctx, sb, pin, up_bytes, cudaMemcpyHostToDevice);
+  CU_TRY(ctx, cudaMemsetAsync(sb + up_bytes, 0, off - up_bytes, ctx->stream));
+  k_triangulate<<<dim3((maxN + 127) / 128, maxsol, n_jobs), 128, 0, ctx->stream>>>((const TriJob*)sb);
+  CU_LAUNCH_CHECK(ctx);
+  CU_COPY(ctx, pin + up_bytes, sb + up_bytes, off - up_bytes, cudaMemcpyDeviceToHost);
+  CU_TRY(ctx, visocu_stream_wait(ctx));
+  for (int j = 0; j < n_jobs; j++) {
+    memcpy(X[j], pin + o_X[j], (size_t)n_sol[j] * 4 * N[j] * 8);
+    memcpy(n_front[j], pin + o_cnt[j], (size_t)n_sol[j] * 4);
+  }
+  return VISOCU_OK;
+}
+
 extern "C" int visocu_triangulate(visocu_ctx* ctx, const float* uv, int32_t N, const double* P1, const double* P2, int32_t n_sol,
                                   double* X, int32_t* n_front) {
   if (!ctx || !uv || !P1 || !P2 || !X || !n_front || N <= 0 || n_sol < 1 || n_sol > 4) return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad triangulate arguments") : VISOCU_EINVAL;
+  return visocu_triangulate_batch(ctx, 1, &uv, &N, &P1, &P2, &n_sol, &X, &n_front);
+}
+
+extern "C" int visocu_best_plane_batch(visocu_ctx* ctx, int32_t n_jobs, const double* const* d, const int32_t* n, const double* threshold,
+                                       const double* weight, int32_t* best_idx) {
+  if (!ctx || n_jobs <= 0 || n_jobs > VISO_MAX_BATCH || !d || !n || !threshold || !weight || !best_idx)
+    return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad best_plane arguments") : VISOCU_EINVAL;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  const size_t o_uv = 0, o_X = align_up((size_t)N * 16, 256), o_cnt = o_X + align_up((size_t)n_sol * 4 * N * 8, 256);
-  int rc = visocu_ensure_scratch(ctx, o_cnt + 256);
+  std::vector<PlaneJob> hj(n_jobs);
+  std::vector<size_t> o_d(n_jobs), o_s(n_jobs);
+  size_t off = align_up(sizeof(PlaneJob) * n_jobs, 256);
+  int maxn = 0;
+  for (int j = 0; j < n_jobs; j++) {
+    if (!d[j] || n[j] <= 0) return visocu_set_error(ctx, VISOCU_EINVAL, "bad best_plane job %d", j);
+    o_d[j] = off; off += align_up((size_t)n[j] * 8, 256);
+    if (n[j] > maxn) maxn = n[j];
+  }
+  const size_t up_bytes = off;
+  for (int j = 0; j < n_jobs; j++) { o_s[j] = off; off += align_up((size_t)n[j] * 8, 256); }
+  int rc = visocu_ensure_scratch(ctx, off);
   if (rc) return rc;
-  if ((rc = visocu_ensure_pinned(ctx, o_cnt + 256))) return rc;       // same layout in pinned memory: no pageable copies
+  if ((rc = visocu_ensure_pinned(ctx, off))) return rc;
   uint8_t* sb = (uint8_t*)ctx->scratch;
   uint8_t* pin = (uint8_t*)ctx->pinned;
-  TriJob job;
-  job.uv = (const float4*)(sb + o_uv); job.X = (double*)(sb + o_X); job.n_front = (int32_t*)(sb + o_cnt);
-  job.N = N; job.n_sol = n_sol;
-  memcpy(job.P1, P1, sizeof job.P1);
-  memcpy(job.P2, P2, sizeof(double) * 12 * n_sol);
-  memcpy(pin + o_uv, uv, (size_t)N * 16);
-  CU_COPY(ctx, sb + o_uv, pin + o_uv, (size_t)N * 16, cudaMemcpyHostToDevice);
-  CU_TRY(ctx, cudaMemsetAsync(sb + o_cnt, 0, 16, ctx->stream));
-  k_triangulate<<<dim3((N + 127) / 128, n_sol), 128, 0, ctx->stream>>>(job);
+  for (int j = 0; j < n_jobs; j++) {
+    hj[j].d = (const double*)(sb + o_d[j]); hj[j].sums = (double*)(sb + o_s[j]);
+    hj[j].threshold = threshold[j]; hj[j].weight = weight[j]; hj[j].n = n[j]; hj[j].pad = 0;
+    memcpy(pin + o_d[j], d[j], (size_t)n[j] * 8);
+  }
+  memcpy(pin, hj.data(), sizeof(PlaneJob) * n_jobs);
+  CU_COPY(ctx, sb, pin, up_bytes, cudaMemcpyHostToDevice);
+  k_plane_sums<<<dim3((maxn + 7) / 8, n_jobs), 256, 0, ctx->stream>>>((const PlaneJob*)sb);
   CU_LAUNCH_CHECK(ctx);
-  // X and the counters are adjacent in both layouts: one read-back
-  CU_COPY(ctx, pin + o_X, sb + o_X, o_cnt - o_X + 16, cudaMemcpyDeviceToHost);
+  CU_COPY(ctx, pin + up_bytes, sb + up_bytes, off - up_bytes, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, visocu_stream_wait(ctx));
-  memcpy(X, pin + o_X, (size_t)n_sol * 4 * N * 8);
-  memcpy(n_front, pin + o_cnt, (size_t)n_sol * 4);
+  for (int j = 0; j < n_jobs; j++) {
+    // arg-max with the reference's rule: strictly larger wins, so the first maximum is kept; index 0 if no candidate
+    const double* sums = (const double*)(pin + o_s[j]);
+    double best_sum = 0;
+    int32_t best = 0;
+    for (int32_t i = 0; i < n[j]; i++)
+      if (sums[i] > best_sum) { best_sum = sums[i]; best = i; }
+    best_idx[j] = best;
+  }
   return VISOCU_OK;
 }
 
 extern "C" int visocu_best_plane(visocu_ctx* ctx, const double* d, int32_t n, double threshold, double weight, int32_t* best_idx) {
   if (!ctx || !d || !best_idx || n <= 0) return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad best_plane arguments") : VISOCU_EINVAL;
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  const size_t o_s = align_up((size_t)n * 8, 256);
-  int rc = visocu_ensure_scratch(ctx, 2 * o_s);
-  if (rc) return rc;
-  if ((rc = visocu_ensure_pinned(ctx, 2 * o_s))) return rc;
-  uint8_t* sb = (uint8_t*)ctx->scratch;
-  uint8_t* pin = (uint8_t*)ctx->pinned;
-  memcpy(pin, d, (size_t)n * 8);
-  CU_COPY(ctx, sb, pin, (size_t)n * 8, cudaMemcpyHostToDevice);
-  k_plane_sums<<<(n + 7) / 8, 256, 0, ctx->stream>>>((const double*)sb, n, threshold, weight, (double*)(sb + o_s));
-  CU_LAUNCH_CHECK(ctx);
-  const double* sums = (const double*)(pin + o_s);
-  CU_COPY(ctx, pin + o_s, sb + o_s, (size_t)n * 8, cudaMemcpyDeviceToHost);
-  CU_TRY(ctx, visocu_stream_wait(ctx));
-  // arg-max with the reference's rule: strictly larger wins, so the first maximum is kept; index 0 if no candidate
-  double best_sum = 0;
-  int32_t best = 0;
-  for (int32_t i = 0; i < n; i++)
-    if (sums[i] > best_sum) { best_sum = sums[i]; best = i; }
-  *best_idx = best;
-  return VISOCU_OK;
+  return visocu_best_plane_batch(ctx, 1, &d, &n, &threshold, &weight, best_idx);
 }

@@ -273,8 +273,36 @@ void runner_post(Runner* r, int tid, int bucket, int32_t* n_matches_out, int32_t
       visocu_ctx* ctx = b->context();
       const VisualOdometryMono::parameters mp = to_cpp(&r->params);
       if (visocu_ransac_F(ctx, nj, uv.data(), N.data(), smp.data(), mp.ransac_iters, mp.inlier_threshold, F.data(), mptr.data(),
-                          ninl.data(), best.data(), 0, 0) == VISOCU_OK)
-        for (int j = 0; j < nj; j++) r->last_ok[ids[j]] = r->monos[ids[j]]->batchFinish(&F[9 * (size_t)j], mptr[j]) ? 1 : 0;
+                          ninl.data(), best.data(), 0, 0) == VISOCU_OK) {
+        // pose recovery: the two GPU stages (four triangulations per sequence, ground-plane vote) as one batched call
+        // each for all of the worker's sequences
+        std::vector<int> alive;
+        for (int j = 0; j < nj; j++)
+          if (r->monos[ids[j]]->poseStageA(&F[9 * (size_t)j], mptr[j])) alive.push_back(ids[j]);
+        if (!alive.empty()) {
+          const int na = (int)alive.size();
+          std::vector<const float*> tuv(na); std::vector<int32_t> tN(na), tsol(na, 4);
+          std::vector<const double*> tP1(na), tP2(na); std::vector<double*> tX(na); std::vector<int32_t*> tfront(na);
+          for (int a = 0; a < na; a++) {
+            VisualOdometryMono::PoseRequest& q = r->monos[alive[a]]->poseRequest();
+            tuv[a] = q.uv.data(); tN[a] = q.N; tP1[a] = q.P1; tP2[a] = q.P2; tX[a] = q.X.data(); tfront[a] = q.n_front;
+          }
+          std::vector<int> alive2;
+          if (visocu_triangulate_batch(ctx, na, tuv.data(), tN.data(), tP1.data(), tP2.data(), tsol.data(), tX.data(), tfront.data()) == VISOCU_OK)
+            for (int a = 0; a < na; a++)
+              if (r->monos[alive[a]]->poseStageB()) alive2.push_back(alive[a]);
+          if (!alive2.empty()) {
+            const int nb = (int)alive2.size();
+            std::vector<const double*> pd(nb); std::vector<int32_t> pn(nb), pbest(nb, 0); std::vector<double> pth(nb), pw(nb);
+            for (int a = 0; a < nb; a++) {
+              VisualOdometryMono::PoseRequest& q = r->monos[alive2[a]]->poseRequest();
+              pd[a] = q.d.data(); pn[a] = (int32_t)q.d.size(); pth[a] = q.threshold; pw[a] = q.weight;
+            }
+            if (visocu_best_plane_batch(ctx, nb, pd.data(), pn.data(), pth.data(), pw.data(), pbest.data()) == VISOCU_OK)
+              for (int a = 0; a < nb; a++) r->last_ok[alive2[a]] = r->monos[alive2[a]]->poseStageC(pbest[a]) ? 1 : 0;
+          }
+        }
+      }
     }
   } else {
     int k = 0;

@@ -161,11 +161,12 @@ vector<double> VisualOdometryMono::estimateMotion(vector<Matcher::p_match> p_mat
 }
 
 // everything of estimateMotion after the RANSAC step (viso_mono.cpp:125-189)
-vector<double> VisualOdometryMono::poseFromF(Matrix F, vector<Matcher::p_match>& p_matched, Matrix& Tp, Matrix& Tc) {
+// Pose from F (viso_mono.cpp:100-190 after the RANSAC) in three host phases around the two GPU stages.
+// Phase 1: denormalise, essential matrix, the four (R, t) candidates of EtoRt (viso_mono.cpp:347-392).
+bool VisualOdometryMono::poseBegin(Matrix F, vector<Matcher::p_match>& p_matched, Matrix& Tp, Matrix& Tc) {
   double K_data[9] = {param.calib.f, 0, param.calib.cu, 0, param.calib.f, param.calib.cv, 0, 0, 1};
-  Matrix K(3, 3, K_data);
-
-  // denormalise, essential matrix, rank 2 again
+  pose_K = Matrix(3, 3, K_data);
+  Matrix& K = pose_K;
   F = ~Tc * F * Tp;
   Matrix E = ~K * F * K;
   Matrix U, W, V;
@@ -173,29 +174,82 @@ vector<double> VisualOdometryMono::poseFromF(Matrix F, vector<Matcher::p_match>&
   W.val[2][0] = 0;
   E = U * Matrix::diag(W) * ~V;
 
-  Matrix X, R, t;
-  EtoRt(E, K, p_matched, X, R, t);
-  if (X.val == 0) return vector<double>();
+  double W_data[9] = {0, -1, 0, +1, 0, 0, 0, 0, 1};
+  double Z_data[9] = {0, +1, 0, -1, 0, 0, 0, 0, 0};
+  Matrix Wm(3, 3, W_data), Z(3, 3, Z_data);
+  Matrix S;
+  E.svd(U, S, V);
+  Matrix T = U * Z * ~U;
+  Matrix Ra = U * Wm * (~V);
+  Matrix Rb = U * (~Wm) * (~V);
+  Matrix t(3, 1);
+  t.val[0][0] = T.val[2][1]; t.val[1][0] = T.val[0][2]; t.val[2][0] = T.val[1][0];
+  if (Ra.det() < 0) Ra = -Ra;
+  if (Rb.det() < 0) Rb = -Rb;
+  // four (R, t) candidates; all four triangulations (4 N independent 4x4 null-vector problems) run in one GPU launch
+  pose_Rs[0] = Ra; pose_Rs[1] = Ra; pose_Rs[2] = Rb; pose_Rs[3] = Rb;
+  pose_ts[0] = t; pose_ts[1] = -t; pose_ts[2] = t; pose_ts[3] = -t;
+  const int32_t N = (int32_t)p_matched.size();
+  Matrix P1(3, 4);
+  P1.setMat(K, 0, 0);
+  P1.getData(pose.P1);
+  for (int32_t i = 0; i < 4; i++) {
+    Matrix P2(3, 4);
+    P2.setMat(pose_Rs[i], 0, 0);
+    P2.setMat(pose_ts[i], 0, 3);
+    P2 = K * P2;
+    P2.getData(pose.P2 + 12 * i);
+  }
+  pose.N = N;
+  pose.uv.resize((size_t)N * 4);
+  for (int32_t i = 0; i < N; i++) {
+    pose.uv[4 * i + 0] = p_matched[i].u1p; pose.uv[4 * i + 1] = p_matched[i].v1p;
+    pose.uv[4 * i + 2] = p_matched[i].u1c; pose.uv[4 * i + 3] = p_matched[i].v1c;
+  }
+  pose.X.resize((size_t)16 * N);
+  for (int i = 0; i < 4; i++) pose.n_front[i] = 0;
+  return N > 0;
+}
 
+// Phase 2: keep the candidate with most points in front of both cameras (first wins on ties), normalise, median test,
+// distances along the road normal for the plane vote (viso_mono.cpp:134-160, 74-98).
+bool VisualOdometryMono::poseMiddle() {
+  const int32_t N = pose.N;
+  Matrix X;
+  int32_t max_inliers = 0;
+  for (int32_t i = 0; i < 4; i++) {
+    if (pose.n_front[i] > max_inliers) {
+      max_inliers = pose.n_front[i];
+      X = Matrix(4, N, pose.X.data() + (size_t)4 * N * i);
+      pose_R = pose_Rs[i];
+      pose_t = pose_ts[i];
+    }
+  }
+  if (X.val == 0) return false;
   X = X / X.getMat(3, 0, 3, -1);
   vector<int32_t> pos_idx;
   for (int32_t i = 0; i < X.n; i++)
     if (X.val[2][i] > 0) pos_idx.push_back(i);
   Matrix X_plane = X.extractCols(pos_idx);
-  if (X_plane.n < 10) return vector<double>();
-
+  if (X_plane.n < 10) return false;
   double median;
   smallerThanMedian(X_plane, median);
-  if (median > param.motion_threshold) return vector<double>();
-
-  Matrix x_plane(2, X_plane.n);
-  x_plane.setMat(X_plane.getMat(1, 0, 2, -1), 0, 0);
+  if (median > param.motion_threshold) return false;
   const double sigma = median / 50.0;
-  const double weight = 1.0 / (2.0 * sigma * sigma);
-  const double threshold = median / param.motion_threshold;
-  const double best_d = findBestPlane(x_plane, threshold, weight);
-  t = t * param.height / best_d;
+  pose.weight = 1.0 / (2.0 * sigma * sigma);
+  pose.threshold = median / param.motion_threshold;
+  // signed distance of every point along the plane normal; the vote finds the mode of a Gaussian kernel density
+  const double ny = cos(-param.pitch), nz = sin(-param.pitch);
+  pose.d.resize(X_plane.n);
+  for (int32_t i = 0; i < X_plane.n; i++) pose.d[i] = ny * X_plane.val[1][i] + nz * X_plane.val[2][i];
+  return true;
+}
 
+// Phase 3: scale the translation with the camera height over the plane distance, Euler angles.
+vector<double> VisualOdometryMono::poseEnd(int32_t best_idx) {
+  const double best_d = pose.d[best_idx];
+  Matrix t = pose_t * param.height / best_d;
+  const Matrix& R = pose_R;
   const double ry = asin(R.val[0][2]);
   const double rx = asin(-R.val[1][2] / cos(ry));
   const double rz = asin(-R.val[0][1] / cos(ry));
@@ -203,6 +257,48 @@ vector<double> VisualOdometryMono::poseFromF(Matrix F, vector<Matcher::p_match>&
   tr[0] = rx; tr[1] = ry; tr[2] = rz;
   tr[3] = t.val[0][0]; tr[4] = t.val[1][0]; tr[5] = t.val[2][0];
   return tr;
+}
+
+vector<double> VisualOdometryMono::poseFromF(Matrix F, vector<Matcher::p_match>& p_matched, Matrix& Tp, Matrix& Tc) {
+  if (!poseBegin(F, p_matched, Tp, Tc)) return vector<double>();
+  visocu_ctx* ctx = matcher->context();
+  if (!ctx || visocu_triangulate(ctx, pose.uv.data(), pose.N, pose.P1, pose.P2, 4, pose.X.data(), pose.n_front) != VISOCU_OK) {
+    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+    return vector<double>();
+  }
+  if (!poseMiddle()) return vector<double>();
+  int32_t best_idx = 0;
+  if (visocu_best_plane(ctx, pose.d.data(), (int32_t)pose.d.size(), pose.threshold, pose.weight, &best_idx) != VISOCU_OK) {
+    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+    best_idx = 0;
+  }
+  return poseEnd(best_idx);
+}
+
+bool VisualOdometryMono::poseStageA(const double* F9, const uint8_t* mask) {
+  MonoTimer timer(7);
+  if (!batch_ready) return false;
+  inliers.clear();
+  for (size_t i = 0; i < normalized_last.size(); i++)
+    if (mask[i]) inliers.push_back((int32_t)i);
+  if (inliers.size() < 10) return false;
+  Matrix F(3, 3, F9);
+  F_last = F;
+  return poseBegin(F, p_matched, Tp_last, Tc_last);
+}
+
+bool VisualOdometryMono::poseStageB() {
+  MonoTimer timer(7);
+  return poseMiddle();
+}
+
+bool VisualOdometryMono::poseStageC(int32_t best_idx) {
+  MonoTimer timer(7);
+  vector<double> tr = poseEnd(best_idx);
+  if (tr.size() != 6) return false;
+  Tr_delta = transformationVectorToMatrix(tr);
+  Tr_valid = true;
+  return true;
 }
 
 Matrix VisualOdometryMono::smallerThanMedian(Matrix& X, double& median) {
@@ -242,58 +338,6 @@ bool VisualOdometryMono::normalizeFeaturePoints(vector<Matcher::p_match>& p_matc
   Tp = Matrix(3, 3, Tp_data);
   Tc = Matrix(3, 3, Tc_data);
   return true;
-}
-
-void VisualOdometryMono::EtoRt(Matrix& E, Matrix& K, vector<Matcher::p_match>& p_matched, Matrix& X, Matrix& R, Matrix& t) {
-  double W_data[9] = {0, -1, 0, +1, 0, 0, 0, 0, 1};
-  double Z_data[9] = {0, +1, 0, -1, 0, 0, 0, 0, 0};
-  Matrix W(3, 3, W_data), Z(3, 3, Z_data);
-  Matrix U, S, V;
-  E.svd(U, S, V);
-  Matrix T = U * Z * ~U;
-  Matrix Ra = U * W * (~V);
-  Matrix Rb = U * (~W) * (~V);
-  t = Matrix(3, 1);
-  t.val[0][0] = T.val[2][1]; t.val[1][0] = T.val[0][2]; t.val[2][0] = T.val[1][0];
-  if (Ra.det() < 0) Ra = -Ra;
-  if (Rb.det() < 0) Rb = -Rb;
-  // four (R, t) candidates, keep the one with most points in front of both cameras (first wins on ties).  All four
-  // triangulations (4 N independent 4x4 null-vector problems) run in one GPU launch.
-  Matrix Rs[4] = {Ra, Ra, Rb, Rb};
-  Matrix ts[4] = {t, -t, t, -t};
-  const int32_t N = (int32_t)p_matched.size();
-  Matrix P1(3, 4);
-  P1.setMat(K, 0, 0);
-  double P1d[12], P2d[48];
-  P1.getData(P1d);
-  for (int32_t i = 0; i < 4; i++) {
-    Matrix P2(3, 4);
-    P2.setMat(Rs[i], 0, 0);
-    P2.setMat(ts[i], 0, 3);
-    P2 = K * P2;
-    P2.getData(P2d + 12 * i);
-  }
-  vector<float> uv((size_t)N * 4);
-  for (int32_t i = 0; i < N; i++) {
-    uv[4 * i + 0] = p_matched[i].u1p; uv[4 * i + 1] = p_matched[i].v1p;
-    uv[4 * i + 2] = p_matched[i].u1c; uv[4 * i + 3] = p_matched[i].v1c;
-  }
-  vector<double> Xall((size_t)16 * N);
-  int32_t n_front[4] = {0, 0, 0, 0};
-  visocu_ctx* ctx = matcher->context();
-  if (!ctx || visocu_triangulate(ctx, uv.data(), N, P1d, P2d, 4, Xall.data(), n_front) != VISOCU_OK) {
-    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
-    return;
-  }
-  int32_t max_inliers = 0;
-  for (int32_t i = 0; i < 4; i++) {
-    if (n_front[i] > max_inliers) {
-      max_inliers = n_front[i];
-      X = Matrix(4, N, Xall.data() + (size_t)4 * N * i);
-      R = Rs[i];
-      t = ts[i];
-    }
-  }
 }
 
 int32_t VisualOdometryMono::triangulateChieral(vector<Matcher::p_match>& p_matched, Matrix& K, Matrix& R, Matrix& t, Matrix& X) {

@@ -32,6 +32,19 @@ public:
   // the caller runs visocu_ransac_F for several sequences at once and hands F and the inlier mask to batchFinish
   bool batchPrepare(const float** uv, int32_t* N, const int32_t** samples);
   bool batchFinish(const double* F9, const uint8_t* mask);
+  // The same finish in three steps, so that a caller with several sequences can run the two GPU stages of the pose
+  // recovery (four triangulations, ground-plane vote) as ONE batched call each: poseStageA (after RANSAC) fills the
+  // triangulation request, poseStageB (after visocu_triangulate_batch) the plane-vote request, poseStageC (after
+  // visocu_best_plane_batch) sets the motion.  A stage that returns false ends the frame (process() == false).
+  struct PoseRequest {
+    std::vector<float> uv; int32_t N; double P1[12], P2[48];          // triangulation: matches in pixels, 4 candidate cameras
+    std::vector<double> X; int32_t n_front[4];                       // its results: 4 x (4 x N) points, points in front
+    std::vector<double> d; double threshold, weight;                 // plane vote: distances along the road normal
+  };
+  bool poseStageA(const double* F9, const uint8_t* mask);
+  bool poseStageB();
+  bool poseStageC(int32_t best_idx);
+  PoseRequest& poseRequest() { return pose; }
   const Matrix& lastF() const { return F_last; }
   const std::vector<int>& lastSamples() const { return samples_last; }
 
@@ -44,7 +57,6 @@ private:
   void packNormalized(const std::vector<Matcher::p_match>& pm);
   Matrix smallerThanMedian(Matrix& X, double& median);
   bool normalizeFeaturePoints(std::vector<Matcher::p_match>& p_matched, Matrix& Tp, Matrix& Tc);
-  void EtoRt(Matrix& E, Matrix& K, std::vector<Matcher::p_match>& p_matched, Matrix& X, Matrix& R, Matrix& t);
   int32_t triangulateChieral(std::vector<Matcher::p_match>& p_matched, Matrix& K, Matrix& R, Matrix& t, Matrix& X);
 
 protected:
@@ -55,5 +67,10 @@ protected:
   std::vector<Matcher::p_match> normalized_last;
   Matrix Tp_last, Tc_last;
   bool batch_ready = false;
+  PoseRequest pose;
+  Matrix pose_K, pose_Rs[4], pose_ts[4], pose_R, pose_t;
+  bool poseBegin(Matrix F, std::vector<Matcher::p_match>& p_matched, Matrix& Tp, Matrix& Tc);
+  bool poseMiddle();
+  std::vector<double> poseEnd(int32_t best_idx);
 };
 #endif
