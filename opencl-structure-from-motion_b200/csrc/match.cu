@@ -511,8 +511,10 @@ int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJ
 }  // namespace
 
 // The tail of a matching call: result words are in pinned memory; fetch the lists and hand everything to the caller.
-static int match_tail(visocu_ctx* ctx, const visocu_deferred& st, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out,
-                      int32_t* outliers, int which_stream) {
+// The tail of a matching call: result words are in pinned memory; fetch the lists and hand everything to the caller.
+// In two steps so that several tails (the two passes of a fused call) share one wait.
+static int match_tail_issue(visocu_ctx* ctx, const visocu_deferred& st, const int32_t* cap, int32_t* n_out, int32_t* outliers,
+                            int which_stream, int* maxn_out) {
   cudaStream_t stream = which_stream ? ctx->stream2 : ctx->stream;
   const int nb = st.nb;
   const int32_t* pw = (const int32_t*)st.pin_words;
@@ -527,13 +529,29 @@ static int match_tail(visocu_ctx* ctx, const visocu_deferred& st, visocu_pmatch*
     if (status == 0 && n > 3) { for (int k = 0; k < 4; k++) ctx->ro_ns[k] += (uint64_t)pw[16 * j + 4 + k]; ctx->ro_jobs++; }
     else if (status != 0) { ctx->ro_declined++; ctx->ro_reason[status & 3]++; ctx->ro_declined_n += (uint64_t)pw[16 * j + 3]; }
   }
+  *maxn_out = maxn;
   if (maxn > 0) {
     const size_t wbytes = (size_t)maxn * 48;
     ctx->d2h_bytes += (uint64_t)wbytes * nb;
     CU_TRY(ctx, cudaMemcpy2DAsync(st.pin_lists, wbytes, st.dev_lists, st.ostride, wbytes, nb, cudaMemcpyDeviceToHost, stream));
+  }
+  return VISOCU_OK;
+}
+
+static void match_tail_deliver(const visocu_deferred& st, visocu_pmatch* const* out, const int32_t* n_out, int maxn) {
+  const size_t wbytes = (size_t)maxn * 48;
+  for (int j = 0; j < st.nb; j++)
+    if (n_out[j] > 0) memcpy(out[j], st.pin_lists + wbytes * j, (size_t)n_out[j] * 48);
+}
+
+static int match_tail(visocu_ctx* ctx, const visocu_deferred& st, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out,
+                      int32_t* outliers, int which_stream) {
+  int maxn = 0;
+  int rc = match_tail_issue(ctx, st, cap, n_out, outliers, which_stream, &maxn);
+  if (rc) return rc;
+  if (maxn > 0) {
     CU_TRY(ctx, visocu_stream_wait_on(ctx, which_stream));
-    for (int j = 0; j < nb; j++)
-      if (n_out[j] > 0) memcpy(out[j], st.pin_lists + wbytes * j, (size_t)n_out[j] * 48);
+    match_tail_deliver(st, out, n_out, maxn);
   }
   return VISOCU_OK;
 }
@@ -780,7 +798,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f) atomicMax((int*)addr, __float_as_int(v)); else atomicMin((unsigned int*)addr, __float_as_uint(v));
 }
 
-__global__ void __launch_bounds__(256) k_prior_ranges(Geometry g, const uint8_t* lists, size_t ostride, const int32_t* words,
+__global__ void __launch_bounds__(1024) k_prior_ranges(Geometry g, const uint8_t* lists, size_t ostride, const int32_t* words,
                                                       uint8_t* ranges, size_t rstride, float* tmp_global, int use_smem) {
   extern __shared__ float s_tmp[];
   const int j = blockIdx.x, tid = threadIdx.x;
@@ -788,13 +806,13 @@ __global__ void __launch_bounds__(256) k_prior_ranges(Geometry g, const uint8_t*
   float* lo = use_smem ? s_tmp : tmp_global + (size_t)j * 9 * nbin;         // 4 values per bin each, then the seen flags
   float* hi = lo + 4 * nbin;
   float* seen = hi + 4 * nbin;
-  for (int i = tid; i < 4 * nbin; i += 256) { lo[i] = 1000000.f; hi[i] = -1000000.f; }
-  for (int i = tid; i < nbin; i += 256) seen[i] = 0.f;
+  for (int i = tid; i < 4 * nbin; i += 1024) { lo[i] = 1000000.f; hi[i] = -1000000.f; }
+  for (int i = tid; i < nbin; i += 1024) seen[i] = 0.f;
   __syncthreads();
   const int n = words[16 * j + 1] == 0 ? words[16 * j] : 0;                 // a declined list is redone by the caller
   const visocu_pmatch* list = (const visocu_pmatch*)(lists + ostride * j);
   const float bs = (float)g.binsize;
-  for (int i = tid; i < n; i += 256) {
+  for (int i = tid; i < n; i += 1024) {
     const visocu_pmatch m = list[i];
     const float d[4] = {__fsub_rn(m.u1p, m.u1c), __fsub_rn(m.v1p, m.v1c), __fsub_rn(m.u1c, m.u1p), __fsub_rn(m.v1c, m.v1p)};
     const int cu = (int)floorf(__fdiv_rn(m.u1c, bs)), cv = (int)floorf(__fdiv_rn(m.v1c, bs));
@@ -811,7 +829,7 @@ __global__ void __launch_bounds__(256) k_prior_ranges(Geometry g, const uint8_t*
   __syncthreads();
   visocu_range* out = (visocu_range*)(ranges + rstride * j);
   const float radius = (float)g.radius;
-  for (int b = tid; b < nbin; b += 256) {
+  for (int b = tid; b < nbin; b += 1024) {
     visocu_range r;
     memset(&r, 0, sizeof r);
     const bool s = seen[b] != 0.f;
@@ -888,7 +906,7 @@ extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_
   const visocu_deferred& A = ctx->part[0];
   const size_t smem = (size_t)9 * nbin * sizeof(float);
   const int use_smem = smem <= 40 * 1024 ? 1 : 0;
-  k_prior_ranges<<<n_jobs, 256, use_smem ? smem : 0, ctx->stream>>>(g, A.dev_lists, A.ostride, A.dev_words, d_rng, rstride,
+  k_prior_ranges<<<n_jobs, 1024, use_smem ? smem : 0, ctx->stream>>>(g, A.dev_lists, A.ostride, A.dev_words, d_rng, rstride,
                                                                    (float*)(d_rng + rstride * n_jobs), use_smem);
   CU_LAUNCH_CHECK(ctx);
   // second pass (dense features, the ranges as prior), refinement, outlier removal
@@ -900,8 +918,12 @@ extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_
   }
   CU_TRY(ctx, visocu_stream_wait(ctx));
   ctx->part[0].pending = ctx->part[1].pending = false;
-  if ((rc = match_tail(ctx, ctx->part[0], out1, cap1, n1, done1, 0))) return rc;
-  if ((rc = match_tail(ctx, ctx->part[1], out2, cap2, n2, done2, 0))) return rc;
+  int maxn1 = 0, maxn2 = 0;
+  if ((rc = match_tail_issue(ctx, ctx->part[0], cap1, n1, done1, 0, &maxn1))) return rc;
+  if ((rc = match_tail_issue(ctx, ctx->part[1], cap2, n2, done2, 0, &maxn2))) return rc;
+  if (maxn1 > 0 || maxn2 > 0) CU_TRY(ctx, visocu_stream_wait(ctx));
+  if (maxn1 > 0) match_tail_deliver(ctx->part[0], out1, n1, maxn1);
+  if (maxn2 > 0) match_tail_deliver(ctx->part[1], out2, n2, maxn2);
   if (ranges_out)
     for (int j = 0; j < n_jobs; j++)
       if (ranges_out[j]) memcpy(ranges_out[j], (const uint8_t*)ctx->pin_ranges + rstride * j, (size_t)nbin * sizeof(visocu_range));
