@@ -22,7 +22,9 @@
 namespace visob {
 namespace {
 
-struct HalfEdge { int32_t onext, oprev, org, dead; };
+// xy: coordinates of the origin (x | y << 16, relative to the bounding box), so that the predicates need no second,
+// dependent load through the vertex number
+struct HalfEdge { int32_t onext, oprev, org; uint32_t xy; };
 
 struct Pt { int32_t x, y; };
 
@@ -31,23 +33,42 @@ struct Mesh {
   HalfEdge* he;                             // per directed edge; sym(e) = e ^ 1 (storage owned by the caller)
   int nhe, cap;
   std::vector<HalfEdge> store;
+  std::vector<uint8_t> flag;                // per half-edge: 1 = removed, 2 = left face is the unbounded face
   void set_points(const Pt* p) { pt = p; }
   void reset(size_t want) {
     if (store.size() < want) store.resize(want);
     he = store.data(); cap = (int)store.size(); nhe = 0;
+    flag.assign(store.size(), 0);
   }
+  uint32_t packed(int v) const { return (uint32_t)pt[v].x | ((uint32_t)pt[v].y << 16); }
 
   int make_edge(int a, int b) {
     if (nhe + 2 > cap) {                    // cannot happen with the 12 n reservation (3 n live + deleted edges); grow anyway
       store.resize(store.size() * 2 + 64);
       he = store.data(); cap = (int)store.size();
+      flag.resize(store.size(), 0);
     }
     const int e = nhe;
-    he[e] = HalfEdge{e, e, a, 0};
-    he[e + 1] = HalfEdge{e + 1, e + 1, b, 0};
+    he[e] = HalfEdge{e, e, a, packed(a)};
+    he[e + 1] = HalfEdge{e + 1, e + 1, b, packed(b)};
     nhe += 2;
     return e;
   }
+  // edge between the origins of half-edges ea and eb (numbers and coordinates copied from them)
+  int make_edge_like(int ea, int eb) {
+    if (nhe + 2 > cap) {
+      store.resize(store.size() * 2 + 64);
+      he = store.data(); cap = (int)store.size();
+      flag.resize(store.size(), 0);
+    }
+    const int e = nhe;
+    he[e] = HalfEdge{e, e, he[ea].org, he[ea].xy};
+    he[e + 1] = HalfEdge{e + 1, e + 1, he[eb].org, he[eb].xy};
+    nhe += 2;
+    return e;
+  }
+  uint32_t xy(int e) const { return he[e].xy; }          // coordinates of the origin of e
+  uint32_t dxy(int e) const { return he[e ^ 1].xy; }     // ... of its destination
   static int sym(int e) { return e ^ 1; }
   int org(int e) const { return he[e].org; }
   int dest(int e) const { return he[e ^ 1].org; }
@@ -68,20 +89,37 @@ struct Mesh {
   }
   // new edge from dest(a) to org(b) so that a, the new edge and b share their left face
   int connect(int a, int b) {
-    int e = make_edge(dest(a), org(b));
+    int e = make_edge_like(a ^ 1, b);
     insert_after(lnext(a), e);
     insert_after(b, sym(e));
     return e;
   }
   void remove(int e) {
     unlink(e); unlink(sym(e));
-    he[e].dead = he[e ^ 1].dead = 1;
+    flag[e] = flag[e ^ 1] = 1;
   }
-  // > 0 iff a, b, c make a left turn
+  // > 0 iff a, b, c make a left turn (vertex numbers)
   int64_t ccw(int a, int b, int c) const {
     const Pt A = pt[a], B = pt[b], C = pt[c];
     return (int64_t)(A.x - C.x) * (B.y - C.y) - (int64_t)(A.y - C.y) * (B.x - C.x);
   }
+  // the same on packed coordinates
+  static int64_t ccw_xy(uint32_t A, uint32_t B, uint32_t C) {
+    const int cx = (int)(C & 0xFFFF), cy = (int)(C >> 16);
+    const int64_t ax = (int)(A & 0xFFFF) - cx, ay = (int)(A >> 16) - cy;
+    const int64_t bx = (int)(B & 0xFFFF) - cx, by = (int)(B >> 16) - cy;
+    return ax * by - ay * bx;
+  }
+  static int64_t incircle_xy(uint32_t A, uint32_t B, uint32_t C, uint32_t D) {
+    const int dx = (int)(D & 0xFFFF), dy = (int)(D >> 16);
+    const int64_t adx = (int)(A & 0xFFFF) - dx, ady = (int)(A >> 16) - dy;
+    const int64_t bdx = (int)(B & 0xFFFF) - dx, bdy = (int)(B >> 16) - dy;
+    const int64_t cdx = (int)(C & 0xFFFF) - dx, cdy = (int)(C >> 16) - dy;
+    const int64_t al = adx * adx + ady * ady, bl = bdx * bdx + bdy * bdy, cl = cdx * cdx + cdy * cdy;
+    return al * (bdx * cdy - cdx * bdy) + bl * (cdx * ady - adx * cdy) + cl * (adx * bdy - bdx * ady);
+  }
+  static int px(uint32_t v) { return (int)(v & 0xFFFF); }
+  static int py(uint32_t v) { return (int)(v >> 16); }
   // > 0 iff d lies strictly inside the circle through a, b, c (a, b, c counter-clockwise)
   int64_t incircle(int a, int b, int c, int d) const {
     const Pt A = pt[a], B = pt[b], C = pt[c], D = pt[d];
@@ -152,36 +190,36 @@ Handles merge(Mesh& m, Handles L, Handles R, int axis) {
   int ldo = L.ldo, ldi = L.rdo, rdi = R.ldo, rdo = R.rdo;
   if (axis == 1) {
     // the two sets are separated by a horizontal line: seat the handles on the y-extremes
-    while (m.pt[m.dest(ldo)].y < m.pt[m.org(ldo)].y) ldo = m.rprev(ldo);
-    while (m.pt[m.dest(m.onext(ldi))].y > m.pt[m.org(ldi)].y) ldi = Mesh::sym(m.onext(ldi));
-    while (m.pt[m.dest(rdi)].y < m.pt[m.org(rdi)].y) rdi = m.rprev(rdi);
-    while (m.pt[m.dest(m.onext(rdo))].y > m.pt[m.org(rdo)].y) rdo = Mesh::sym(m.onext(rdo));
+    while (Mesh::py(m.dxy(ldo)) < Mesh::py(m.xy(ldo))) ldo = m.rprev(ldo);
+    while (Mesh::py(m.dxy(m.onext(ldi))) > Mesh::py(m.xy(ldi))) ldi = Mesh::sym(m.onext(ldi));
+    while (Mesh::py(m.dxy(rdi)) < Mesh::py(m.xy(rdi))) rdi = m.rprev(rdi);
+    while (Mesh::py(m.dxy(m.onext(rdo))) > Mesh::py(m.xy(rdo))) rdo = Mesh::sym(m.onext(rdo));
   }
   // lower common tangent
   bool changed;
   do {
     changed = false;
-    if (m.ccw(m.org(ldi), m.dest(ldi), m.org(rdi)) > 0) { ldi = m.lnext(ldi); changed = true; }
-    if (m.ccw(m.dest(rdi), m.org(rdi), m.org(ldi)) > 0) { rdi = m.rprev(rdi); changed = true; }
+    if (Mesh::ccw_xy(m.xy(ldi), m.dxy(ldi), m.xy(rdi)) > 0) { ldi = m.lnext(ldi); changed = true; }
+    if (Mesh::ccw_xy(m.dxy(rdi), m.xy(rdi), m.xy(ldi)) > 0) { rdi = m.rprev(rdi); changed = true; }
   } while (changed);
   int basel = m.connect(Mesh::sym(rdi), ldi);       // from org(rdi) = lower right to org(ldi) = lower left
   if (m.org(ldi) == m.org(ldo)) ldo = Mesh::sym(basel);
   if (m.org(rdi) == m.org(rdo)) rdo = basel;
   // knit the seam upwards
   for (;;) {
-    const int lowerright = m.org(basel), lowerleft = m.dest(basel);
+    const uint32_t lowerright = m.xy(basel), lowerleft = m.dxy(basel);
     int lcand = m.onext(Mesh::sym(basel)), rcand = m.oprev(basel);
-    int upperleft = m.dest(lcand), upperright = m.dest(rcand);
-    const bool leftfinished = m.ccw(upperleft, lowerleft, lowerright) <= 0;
-    const bool rightfinished = m.ccw(upperright, lowerleft, lowerright) <= 0;
+    uint32_t upperleft = m.dxy(lcand), upperright = m.dxy(rcand);
+    const bool leftfinished = Mesh::ccw_xy(upperleft, lowerleft, lowerright) <= 0;
+    const bool rightfinished = Mesh::ccw_xy(upperright, lowerleft, lowerright) <= 0;
     if (leftfinished && rightfinished) break;
     if (!leftfinished) {
       for (;;) {
         const int nx = m.onext(lcand);
         if (nx == Mesh::sym(basel)) break;
-        const int apex = m.dest(nx);
-        if (m.ccw(lowerleft, upperleft, apex) <= 0) break;                 // no real triangle beyond lcand
-        if (m.incircle(lowerleft, lowerright, upperleft, apex) <= 0) break;
+        const uint32_t apex = m.dxy(nx);
+        if (Mesh::ccw_xy(lowerleft, upperleft, apex) <= 0) break;                 // no real triangle beyond lcand
+        if (Mesh::incircle_xy(lowerleft, lowerright, upperleft, apex) <= 0) break;
         m.remove(lcand);
         lcand = nx; upperleft = apex;
       }
@@ -190,22 +228,22 @@ Handles merge(Mesh& m, Handles L, Handles R, int axis) {
       for (;;) {
         const int nx = m.oprev(rcand);
         if (nx == basel) break;
-        const int apex = m.dest(nx);
-        if (m.ccw(lowerright, apex, upperright) <= 0) break;
-        if (m.incircle(lowerleft, lowerright, upperright, apex) <= 0) break;
+        const uint32_t apex = m.dxy(nx);
+        if (Mesh::ccw_xy(lowerright, apex, upperright) <= 0) break;
+        if (Mesh::incircle_xy(lowerleft, lowerright, upperright, apex) <= 0) break;
         m.remove(rcand);
         rcand = nx; upperright = apex;
       }
     }
-    if (leftfinished || (!rightfinished && m.incircle(upperleft, lowerleft, lowerright, upperright) > 0))
+    if (leftfinished || (!rightfinished && Mesh::incircle_xy(upperleft, lowerleft, lowerright, upperright) > 0))
       basel = m.connect(rcand, Mesh::sym(basel));      // new base: upper right -> lower left
     else
       basel = m.connect(Mesh::sym(basel), Mesh::sym(lcand));   // new base: lower right -> upper left
   }
   if (axis == 1) {
     // back to the x-extremes expected by the parent (vertical cut) and by the leaves
-    while (m.pt[m.dest(m.oprev(ldo))].x < m.pt[m.org(ldo)].x) ldo = Mesh::sym(m.oprev(ldo));
-    while (m.pt[m.dest(rdo)].x > m.pt[m.org(rdo)].x) rdo = m.lnext(rdo);
+    while (Mesh::px(m.dxy(m.oprev(ldo))) < Mesh::px(m.xy(ldo))) ldo = Mesh::sym(m.oprev(ldo));
+    while (Mesh::px(m.dxy(rdo)) > Mesh::px(m.xy(rdo))) rdo = m.lnext(rdo);
   }
   return Handles{ldo, rdo};
 }
@@ -262,6 +300,10 @@ Handles triangulate(Scratch& S, const int32_t* x, const int32_t* y, int n) {
     xlo = std::min(xlo, x[i]); xhi = std::max(xhi, x[i]);
     ylo = std::min(ylo, y[i]); yhi = std::max(yhi, y[i]);
   }
+  if (xhi - xlo > 0xFFFF || yhi - ylo > 0xFFFF) {
+    fprintf(stderr, "ERROR: delaunay: coordinate range %d x %d exceeds 65535\n", xhi - xlo, yhi - ylo);
+    return none;
+  }
   // sort by (x, y, input index): two stable counting passes (pixel coordinates span a few thousand values)
   S.a.resize(n);
   for (int i = 0; i < n; i++) S.a[i] = i;
@@ -304,7 +346,8 @@ Handles triangulate(Scratch& S, const int32_t* x, const int32_t* y, int n) {
   // renumber once more, in partition order: every subtree of the divide-and-conquer then works on a contiguous range
   // of vertices (and of the edges it creates), which keeps the merge loops in cache
   S.pts.resize(nu);
-  for (int i = 0; i < nu; i++) { S.pts[i] = Pt{S.sx[S.v[i]], S.sy[S.v[i]]}; S.tmp[i] = S.orig[S.v[i]]; }
+  // coordinates relative to the bounding box: they are packed into 16 + 16 bits inside the half-edge records
+  for (int i = 0; i < nu; i++) { S.pts[i] = Pt{S.sx[S.v[i]] - xlo, S.sy[S.v[i]] - ylo}; S.tmp[i] = S.orig[S.v[i]]; }
   for (int i = 0; i < nu; i++) { S.orig[i] = S.tmp[i]; S.v[i] = i; }
   S.m.set_points(S.pts.data());
   return build(S.m, S.v.data(), nu, 0);
@@ -327,7 +370,7 @@ void delaunay_triangles(const int32_t* x, const int32_t* y, int n, std::vector<i
   const int ne = m.nhe;
   tri.reserve(6 * S.orig.size());
   for (int e = 0; e < ne; e++) {
-    if (m.he[e].dead) continue;
+    if (m.flag[e]) continue;
     const int e2 = m.lnext(e);
     if (e2 < e) continue;
     const int e3 = m.lnext(e2);
@@ -347,11 +390,11 @@ void delaunay_edges(const int32_t* x, const int32_t* y, int n, std::vector<int32
   // mark the half-edges whose left face is the unbounded face: one walk around it, starting at the clockwise
   // hull edge out of the rightmost vertex.  Every other face of a Delaunay triangulation is a triangle.
   int e = h.rdo;
-  do { m.he[e].dead |= 2; e = m.lnext(e); } while (e != h.rdo);
+  do { m.flag[e] |= 2; e = m.lnext(e); } while (e != h.rdo);
   const int ne = m.nhe;
   edges.reserve(9 * S.orig.size());
   for (int k = 0; k < ne; k += 2) {
-    const int d0 = m.he[k].dead, d1 = m.he[k + 1].dead;
+    const int d0 = m.flag[k], d1 = m.flag[k + 1];
     if ((d0 | d1) & 1) continue;
     const int t = (d0 & 2 ? 0 : 1) + (d1 & 2 ? 0 : 1);
     if (t == 0) continue;
