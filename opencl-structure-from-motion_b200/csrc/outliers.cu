@@ -11,9 +11,11 @@
 //      merge, on a 16-bit quad-edge structure with per-subtree free lists; the top levels are single threads walking
 //      the seam at shared-memory latency while the other CTAs of the batch keep the SMs busy;
 //   4. support vote per triangle edge with shared-memory atomics, order-preserving compaction of the survivors.
-// A list that does not fit (more than about 4800 points in 227 KB), contains duplicate positions (Triangle's answer
-// then depends on its randomised quicksort) or trips an internal guard is handed back unchanged with status 1, and
-// the host runs the identical algorithm (host/delaunay.cpp) on it.
+// Duplicate positions (Triangle triangulates one point per position, the one its randomised quicksort leaves first) are
+// resolved before the kernel runs by replaying that sort on the host (ro_resolve_duplicates below); the kernel gets one
+// flag per match.  A list that does not fit (more than about 5700 points in 227 KB), has coordinates above 8191 (the
+// 32-bit predicates), fewer than four distinct positions, or trips an internal guard is handed back unchanged with a
+// non-zero status, and the host runs the identical algorithm (host/delaunay.cpp) on it.
 #include "visocu_internal.cuh"
 #include "outliers.cuh"
 #include <cstdio>
