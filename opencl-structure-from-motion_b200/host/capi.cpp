@@ -168,6 +168,10 @@ VISOB_API int visob_stereo_process(void* v, uint8_t* I1, uint8_t* I2, const int3
   uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
   return ((StereoAccess*)v)->process(I1, I2, d, replace != 0) ? 1 : 0;
 }
+VISOB_API int visob_stereo_process_matches(void* v, const void* matches, int n) {     // host only: no image, no GPU
+  std::vector<Matcher::p_match> pm((const Matcher::p_match*)matches, (const Matcher::p_match*)matches + n);
+  return ((VisualOdometry*)(StereoAccess*)v)->process(pm) ? 1 : 0;
+}
 VISOB_API void visob_stereo_get_motion(void* v, double* out16) {
   Matrix T = ((StereoAccess*)v)->getMotion();
   for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out16[4 * i + j] = T.val[i][j];

@@ -227,6 +227,10 @@ class Stereo:
         I1 = np.ascontiguousarray(I1, np.uint8); I2 = np.ascontiguousarray(I2, np.uint8)
         return bool(lib().visob_stereo_process(self.h, _p(I1), _p(I2), _p(_dims(I1)), int(replace)))
 
+    def process_matches(self, matches):
+        m = np.ascontiguousarray(matches, dtype=P_MATCH)
+        return bool(lib().visob_stereo_process_matches(self.h, _p(m), len(m)))
+
     def motion(self):
         out = np.zeros((4, 4))
         lib().visob_stereo_get_motion(self.h, _p(out))

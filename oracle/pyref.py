@@ -338,6 +338,10 @@ class RefStereo:
         dims = np.array([w, h, w], np.int32)
         return bool(self.lib.ref_stereo_process(self.h, _p(I1), _p(I2), _p(dims), int(replace)))
 
+    def process_matches(self, matches):
+        m = np.ascontiguousarray(matches, dtype=P_MATCH)
+        return bool(self.lib.ref_stereo_process_matches(self.h, _p(m), len(m)))
+
     def motion(self):
         out = np.zeros((4, 4))
         self.lib.ref_stereo_get_motion(self.h, _p(out))

@@ -138,3 +138,42 @@ def test_reconstruction_matches_reference(ref, point_type, min_len, min_angle):
             assert np.abs(a - b).max() <= 1e-5 * max(1.0, np.abs(a).max())
         total = len(a)
     assert total > 50
+
+
+def test_stereo_odometry_from_matches():
+    """VisualOdometryStereo::estimateMotion (viso_stereo.cpp:42-145) is host code: fed with the same quad matches, the
+    3-point RANSAC over Gauss-Newton fits and the final refinement must pick the same inliers and the same motion as
+    the reference.  Synthetic rig: f = 645.2, base 0.54 m, 0.8 m forward with a slight yaw, 0.3 px noise, 15 % outliers."""
+    ref = pyref.RefLib(fresh=True)        # the sample generator of the reference is process-wide state (viso.cpp:88)
+    rng = np.random.RandomState(5)
+    f, cu, cv, base = 645.2, 635.9, 194.1, 0.54
+    kw = dict(f=f, cu=cu, cv=cv, base=base)
+    rv = ref.stereo(pyref.StereoParams(match=pyref.MatcherParams(), **kw))
+    hv = H.Stereo(H.StereoParams(match=V.Params(), **kw))
+    for step in range(3):
+        n = 400
+        P = np.stack([rng.uniform(-10, 10, n), rng.uniform(-3, 1.6, n), rng.uniform(5, 50, n)], 1)
+        yaw = 0.01 * (step + 1)
+        R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+        t = np.array([0.02, -0.01, -0.8])
+        Q = P @ R.T + t                                        # the same points in the current left camera frame
+
+        def project(X, shift):
+            return f * (X[:, 0] - shift) / X[:, 2] + cu, f * X[:, 1] / X[:, 2] + cv
+
+        m = np.zeros(n, pyref.P_MATCH)
+        for name in ('i1p', 'i2p', 'i1c', 'i2c'):
+            m[name] = np.arange(n)
+        m['u1p'], m['v1p'] = project(P, 0.0); m['u2p'], m['v2p'] = project(P, base)
+        m['u1c'], m['v1c'] = project(Q, 0.0); m['u2c'], m['v2c'] = project(Q, base)
+        for name in ('u1p', 'v1p', 'u2p', 'u1c', 'v1c', 'u2c'):
+            m[name] += rng.normal(0, 0.3, n).astype(np.float32)
+        m['v2p'] = m['v1p']; m['v2c'] = m['v1c']
+        bad = rng.rand(n) < 0.15
+        m['u1c'][bad] += rng.uniform(-40, 40, bad.sum()).astype(np.float32)
+        ok_r, ok_h = rv.process_matches(m), hv.process_matches(m)
+        assert ok_r and ok_h
+        assert np.array_equal(rv.inliers(), hv.inliers()) and len(hv.inliers()) > 250
+        Tr, Th = rv.motion(), hv.motion()
+        assert np.abs(Tr - Th).max() < 1e-9
+        assert abs(Th[2, 3] + 0.8) < 0.05
