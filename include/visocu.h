@@ -54,7 +54,9 @@ typedef struct { float u_min[4], u_max[4], v_min[4], v_max[4]; } visocu_range;
 /* One matching job = the four ring-buffer entries of Matcher::matching (matcher.cpp:965); -1 = unused. */
 typedef struct { int32_t f1p, f2p, f1c, f2c; } visocu_quad;
 
-/* ---- runtime (replaces OpenCL::Container::init / getDevice, opencl_wrapper.cpp:66-128) ---- */
+/* ---- runtime (replaces OpenCL::Container::init / getDevice, opencl_wrapper.cpp:66-128) ----
+ * A process that drives several contexts from several threads should export CUDA_DEVICE_MAX_CONNECTIONS=32 before its
+ * first CUDA call (one hardware queue per stream); the library never changes its host's environment. */
 int  visocu_create(int device, visocu_ctx** out);
 void visocu_destroy(visocu_ctx* ctx);
 const char* visocu_last_error(const visocu_ctx* ctx);          /* ctx may be NULL: last create() error */

@@ -85,11 +85,11 @@ extern "C" const char* visocu_last_error(const visocu_ctx* ctx) { return ctx ? c
 extern "C" int visocu_create(int device, visocu_ctx** out) {
   if (!out) return VISOCU_EINVAL;
   *out = nullptr;
-  // One context = one stream, and a process drives many of them (one per host worker).  With the default of 8 hardware
-  // work queues, streams share queues and a 1 ms outlier-removal kernel at the head of one stream stalls the kernels of
-  // its queue neighbours; 32 queues removed that (flow bench: 13.9 k -> 23.2 k pairs/s).  Only effective if set before
-  // the process initialises CUDA, hence also at the top of bench.py; an explicit user setting wins.
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+  // One context = one stream, and a process may drive many of them (one per host worker).  With the default of 8 hardware
+  // work queues, streams share queues and a long kernel at the head of one stream stalls the kernels of its queue
+  // neighbours; CUDA_DEVICE_MAX_CONNECTIONS=32 removes that (flow bench: 13.9 k -> 23.2 k pairs/s).  That variable is
+  // process-wide and only read when CUDA initialises, so it is the APPLICATION's to set (bench.py does, before anything
+  // touches CUDA; include/visocu.h says so); the library does not modify its host's environment.
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev <= 0)
@@ -111,7 +111,7 @@ extern "C" int visocu_create(int device, visocu_ctx** out) {
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaMalloc(&ctx->d_stats, 2 * sizeof(uint64_t))) != cudaSuccess) {
     visocu_set_error(nullptr, VISOCU_ECUDA, "context setup: %s", cudaGetErrorString(e));
-    delete ctx;
+    visocu_destroy(ctx);             // releases whatever was created before the failure
     return VISOCU_ECUDA;
   }
   cudaMemset(ctx->d_stats, 0, 2 * sizeof(uint64_t));
@@ -126,7 +126,6 @@ extern "C" int visocu_create(int device, visocu_ctx** out) {
     }
     cudaGetLastError();
   }
-  if (const char* e = getenv("VISOCU_DBG")) ctx->dbg_flags = atoi(e);
   // VISOCU_BLOCKING_SYNC=1: waiting host threads sleep (for runs with more worker threads than cores)
   if (const char* e = getenv("VISOCU_BLOCKING_SYNC"))
     if (e[0] == '1') cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming);
@@ -172,6 +171,7 @@ extern "C" void visocu_destroy(visocu_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   delete ctx;
 }
 
@@ -240,8 +240,8 @@ extern "C" int visocu_configure(visocu_ctx* ctx, const visocu_params* p, int32_t
   g.vb = (int)ceilf((float)height / (float)p->match_binsize);
   g.nbins = 4 * g.ub * g.vb;
   g.radius = p->match_radius; g.disp_tol = p->match_disp_tolerance;
-  if (g.ub > 4095 || g.vb > 4095 || width > 8191 * g.scale || height > 8191 * g.scale)
-    return visocu_set_error(ctx, VISOCU_EINVAL, "image or bin grid too large for the packed match keys");
+  if (g.ub > 4095 || g.vb > 4095 || width > 8191 * g.scale || height > 8191 * g.scale || g.cap[0] > (1 << 24) || g.cap[1] > (1 << 24))
+    return visocu_set_error(ctx, VISOCU_EINVAL, "image, bin grid or feature capacity too large for the packed match keys (24-bit feature index)");
 
   // carve one pool
   size_t plane_f = align_up((size_t)g.bpl * g.h + 64, 256), plane_m = align_up((size_t)g.bplm * g.hm + 64, 256);

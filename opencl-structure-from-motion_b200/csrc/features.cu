@@ -189,7 +189,7 @@ __device__ __forceinline__ bool mbar_wait_or_trap(uint32_t bar, uint32_t phase) 
 }
 
 __global__ void __launch_bounds__(FILTER_THREADS, 2)
-k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __grid_constant__ CUtensorMap tmap, int use_tma, int max_cells, int dbg) {
+k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __grid_constant__ CUtensorMap tmap, int use_tma, int max_cells) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int slot = sl.s[blockIdx.z];
   const FrameDev F = frames[slot];
@@ -309,7 +309,6 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
     }
     if (tid == 0) *s_qn = 0;
     __syncthreads();
-    if (dbg & 2) return;
 
     // 3a: cell extrema.  Dense cells: one thread per cell; sparse cells: four lanes per cell, each scanning every
     // fourth column, combined with warp shuffles.  Candidates that pass the tau test are queued.
@@ -367,7 +366,7 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
     // positions inside the cell can never be strictly better than the cell extremum, so the reference's cell
     // exclusion is implied.  Row-wise packed scan: two responses per 32-bit word, VIMNMX.U16x2 reduction, one exit
     // test per row; maxima are handled as minima of the complemented values; lanes outside the window read as 0xFFFF.
-    const int nq = (dbg & 1) ? 0 : *s_qn;     // dbg: timing experiments only (profiles/), results are wrong when set
+    const int nq = *s_qn;
     for (int q = tid; q < nq; q += FILTER_THREADS) {
       const uint32_t ent = s_queue[q];
       const int p = ent >> 26, c = (ent >> 16) & 3, pos = (ent >> 18) & 255, gcell = ent & 0xFFFF;
@@ -625,7 +624,7 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
     if (smem_bytes > 227 * 1024) return visocu_set_error(ctx, VISOCU_EINVAL, "tile needs %zu bytes of shared memory", smem_bytes);
     dim3 grid((g.bplm + TW - 1) / TW, (g.hm + TH - 1) / TH, sl.n);
     if (ctx->profile) CU_TRY(ctx, cudaEventRecord(ctx->pev0, st));
-    k_filter_nms<<<grid, FILTER_THREADS, smem_bytes, st>>>(g, ctx->frames_d, sl, nmax, ctx->tmap_img, ctx->use_tma, max_cells, ctx->dbg_flags);
+    k_filter_nms<<<grid, FILTER_THREADS, smem_bytes, st>>>(g, ctx->frames_d, sl, nmax, ctx->tmap_img, ctx->use_tma, max_cells);
     CU_LAUNCH_CHECK(ctx);
     if (ctx->profile) {
       // profiling mode only: this synchronises the stream after every fused launch

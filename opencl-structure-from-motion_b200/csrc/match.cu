@@ -148,11 +148,14 @@ __device__ __forceinline__ int find_match_predicted(const Geometry& g, const Set
             const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv)));
             cost = __dadd_rn(cost, __dmul_rn(4.0, dist));
           }
+          n_cand++;
+          // the reference starts from min_cost = 1e7 and keeps a candidate only if cost < min_cost (matcher.cpp:899,955):
+          // NaN, +inf and costs >= 1e7 (a degenerate projection: z2c near 0) never win and min_ind stays 0
+          if (!(cost < 10000000.0)) continue;
           const int ub2 = min((int)floorf((float)u2 / bs), g.ub - 1);
           const unsigned long long cb = (unsigned long long)__double_as_longlong(cost);      // cost >= 0: bit order = value order
           const unsigned long long ord = ((unsigned long long)ub2 << 36) | ((unsigned long long)vbin << 24) | (unsigned long long)ent.y;
           if (cb < best_cost || (cb == best_cost && ord < best_ord)) { best_cost = cb; best_ord = ord; }
-          n_cand++;
         }
       }
     }

@@ -80,7 +80,6 @@ struct visocu_ctx {
   CUtensorMap tmap_img;              // TMA descriptor of the matching-resolution image planes of the pool
   int use_tma = 0;
   int pinv_ready = 0;                // paraboloid pseudo-inverse uploaded to constant memory (sub-pixel refinement)
-  int dbg_flags = 0;                 // VISOCU_DBG: skips kernel phases for timing experiments (never set in tests/bench)
   size_t filter_smem_attr = 0;       // dynamic shared memory opted in for the fused kernel on this device
   uint64_t h2d_bytes = 0, d2h_bytes = 0;   // host<->device traffic issued by this context
   int profile = 0;                   // time the fused filter+NMS launches with events (visocu_profile)

@@ -10,8 +10,8 @@
 // sizes (n/2 by alternating axis, leaves of 2-3 vertices sorted by x), both tangent tests per iteration of the
 // lower-tangent search, strict `> 0` in-circle tests, candidate validity evaluated before the candidate-removal
 // loops, and the same walks that re-seat the hull handles on the y-extremes before, and on the x-extremes after, a
-// merge across a horizontal cut.  tests/test_host_delaunay.py checks the resulting outlier decisions against the
-// reference on grid-heavy random inputs.
+// merge across a horizontal cut.  tests/test_host_cpu.py::test_remove_outliers_matches_reference checks the resulting
+// outlier decisions against the reference on grid-heavy random inputs (duplicates and lists beyond the device limit included).
 #include "delaunay.h"
 
 #include <algorithm>

@@ -107,6 +107,7 @@ class RefLib:
         L.ref_matcher_gain.restype = C.c_float
         L.ref_time_matcher_sequence.restype = C.c_double
         L.ref_time_mono_sequence.restype = C.c_double
+        L.ref_find_best_plane.restype = C.c_double
         self.info = L.ref_build_info().decode()
 
     # ---- filters (w must be a multiple of 16; returns planes of the same shape)
@@ -435,6 +436,19 @@ class RefMono:
         n = self.lib.ref_ransac_with_samples(self.h, _p(m), len(m), _p(s), iters, _p(F), _p(inl),
                                              _p(counts) if want_all else None, _p(Fall) if want_all else None, C.byref(best))
         return dict(n_inliers=n, F=F, inliers=inl[:max(n, 0)].copy(), counts=counts, F_all=Fall, best_iter=best.value)
+
+    def triangulate_chieral(self, matches, K, R, t):
+        """VisualOdometryMono::triangulateChieral (viso_mono.cpp:394-431): (X 4 x n, points in front of both cameras)."""
+        m = np.ascontiguousarray(matches, dtype=P_MATCH)
+        X = np.zeros((4, len(m)))
+        num = self.lib.ref_triangulate_chieral(self.h, _p(m), len(m), _p(np.ascontiguousarray(K, np.float64)),
+                                               _p(np.ascontiguousarray(R, np.float64)), _p(np.ascontiguousarray(t, np.float64).ravel()), _p(X))
+        return X, num
+
+    def find_best_plane(self, x_plane, threshold, weight):
+        """VisualOdometryMono::findBestPlane (viso_mono.cpp:74-98); x_plane 2 x n.  Returns the winning distance."""
+        xp = np.ascontiguousarray(x_plane, np.float64)
+        return float(self.lib.ref_find_best_plane(self.h, _p(xp), xp.shape[1], C.c_double(threshold), C.c_double(weight)))
 
     def estimate_motion(self, matches):
         m = np.ascontiguousarray(matches, dtype=P_MATCH)

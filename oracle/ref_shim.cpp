@@ -352,6 +352,20 @@ REF_API int ref_estimate_motion(void* v, const void* matches, int n, double* tr6
   for (int i = 0; i < 6; i++) tr6[i] = tr[i];
   return 1;
 }
+// VisualOdometryMono::triangulateChieral (viso_mono.cpp:394-431) for one (R|t) candidate: K, R 3x3 row-major, t 3;
+// X4n receives the 4 x n homogeneous points (row-major), the return value is the number of points in front of both cameras
+REF_API int ref_triangulate_chieral(void* v, const void* matches, int n, const double* K9, const double* R9, const double* t3, double* X4n) {
+  std::vector<Matcher::p_match> pm((const Matcher::p_match*)matches, (const Matcher::p_match*)matches + n);
+  Matrix K(3, 3, K9), R(3, 3, R9), t(3, 1, t3), X;
+  const int num = ((MonoProbe*)v)->triangulateChieral(pm, K, R, t, X);
+  if (X4n) for (int i = 0; i < 4; i++) for (int j = 0; j < n; j++) X4n[(size_t)i * n + j] = X.val[i][j];
+  return num;
+}
+// VisualOdometryMono::findBestPlane (viso_mono.cpp:74-98): x_plane is 2 x n row-major; returns the winning plane distance
+REF_API double ref_find_best_plane(void* v, const double* x_plane2n, int n, double threshold, double weight) {
+  Matrix xp(2, n, x_plane2n);
+  return ((MonoProbe*)v)->findBestPlane(xp, threshold, weight);
+}
 // Matrix::svd (matrix.cpp:586-814): A is m x n row-major; U m x m, W min(m,n), V n x n
 REF_API void ref_svd(const double* A, int m, int n, double* U, double* W, double* V) {
   Matrix M(m, n, A), Um, Wm, Vm;

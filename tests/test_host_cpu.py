@@ -61,6 +61,10 @@ def test_remove_outliers_matches_reference(ref):
         w = int(rng.integers(40, 1300)); h = int(rng.integers(40, 400)); method = int(rng.choice([0, 2]))
         m = _random_matches(rng, n, w, h, grid, dup=trial % 2 == 0)
         assert hm.remove_outliers(m, method).tobytes() == rm.remove_outliers(m, method).tobytes(), (trial, n, grid, method)
+    for n, grid, dup in ((7000, 1, False), (9000, 2, True)):      # beyond the ~5700 points the device kernel takes: the host path
+        m = _random_matches(rng, n, 1300, 400, grid, dup)
+        assert len(m) > 5700
+        assert hm.remove_outliers(m, 0).tobytes() == rm.remove_outliers(m, 0).tobytes(), (n, grid, dup)
     for n in (0, 1, 3, 4):          # tiny inputs: <= 3 matches are returned untouched (matcher.cpp:1210)
         m = _random_matches(rng, 50, 100, 100, 1, False)[:n]
         assert hm.remove_outliers(m, 0).tobytes() == rm.remove_outliers(m, 0).tobytes()
