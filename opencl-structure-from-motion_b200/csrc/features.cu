@@ -9,19 +9,19 @@
 //   Matcher::createIndexVector ............................. matcher.cpp:870-890
 // None of it is a translation of the reference's SSE row/column passes or its integral image: the blob and
 // checkerboard responses never leave the SM (they live in shared memory only), the NMS neighbourhood test is
-// reduced to "window minimum == cell minimum", and the output order (cell-column-major, then class) is
+// reduced to "window extreme == cell extreme", and the output order (cell-column-major, then class) is
 // rebuilt with a deterministic scan instead of push_back.
 #include "visocu_internal.cuh"
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 namespace {
 
-constexpr int TW = 128;          // tile core width  (pixels whose du/dv this CTA writes, whose NMS cells it owns)
-constexpr int TH = 64;           // tile core height
-constexpr int SEG = 16;          // rows per column walker
-constexpr int FILTER_THREADS = 256;
 constexpr int CELLS_PER_BLOCK = 512;
+constexpr int MAX_FILTER_THREADS = 512;
 
 // ----------------------------------------------------------------------------------------------------------
 // half-resolution image: 2x2 box mean, truncating (matcher.cpp:636-647).  One thread = 4 output pixels.
@@ -56,125 +56,182 @@ __global__ void k_half_image(Geometry g, const FrameDev* frames, SlotList sl) {
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// horizontal 5-tap sums of one image row at columns x-2..x+2 (p[0..4])
-struct HRow { int hd, ha, h1, h3, hc, pc; };
-__device__ __forceinline__ HRow hrow(const uint8_t* p) {
-  int p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3], p4 = p[4];
-  HRow r;
-  r.hd = (p0 - p4) + 2 * (p1 - p3);          // (1,2,0,-2,-1) left -> right
-  r.ha = (p0 + p4) + 4 * (p1 + p3) + 6 * p2; // (1,4,6,4,1)
-  r.h1 = p0 + p1 + p2 + p3 + p4;
-  r.h3 = p1 + p2 + p3;
-  r.hc = (p0 + p1) - (p3 + p4);              // (1,1,0,-1,-1)
-  r.pc = p2;
-  return r;
-}
-
-// full-resolution Sobel planes only (the *_full planes of matcher.cpp:676 used by the refinement).
-// One thread walks SEG rows of one column with a 5-row register window.
-__global__ void __launch_bounds__(256) k_sobel_full(Geometry g, const FrameDev* frames, SlotList sl) {
-  const FrameDev F = frames[sl.s[blockIdx.z]];
-  int x = blockIdx.x * 256 + threadIdx.x;
-  int y0 = blockIdx.y * 32;
-  if (x >= g.bpl) return;
-  int hd[5], ha[5];
-  auto load = [&](int y, int slot) {
-    int a = 0, d = 0;
-    if (y >= 0 && y < g.h && x >= 2 && x <= g.w - 3) {
-      HRow r = hrow(F.img + (size_t)y * g.bpl + x - 2);
-      a = r.ha; d = r.hd;
-    }
-    hd[slot] = d; ha[slot] = a;
-  };
-#pragma unroll
-  for (int k = 0; k < 4; k++) load(y0 - 2 + k, k);
-  for (int r = 0; r < 32; r += 5) {
-#pragma unroll
-    for (int ph = 0; ph < 5; ph++) {
-      int y = y0 + r + ph;
-      if (r + ph < 32 && y < g.h) {
-        load(y + 2, (ph + 4) % 5);
-        int du = 128, dv = 128;
-        if (x >= 2 && x <= g.w - 3 && y >= 2 && y <= g.h - 3) {
-          int s0 = ph % 5, s1 = (ph + 1) % 5, s2 = (ph + 2) % 5, s3 = (ph + 3) % 5, s4 = (ph + 4) % 5;
-          du = (((hd[s0] + hd[s4]) + 4 * (hd[s1] + hd[s3]) + 6 * hd[s2]) >> 7) + 128;
-          dv = (((ha[s0] - ha[s4]) + 2 * (ha[s1] - ha[s3])) >> 7) + 128;
-          du = min(max(du, 0), 255); dv = min(max(dv, 0), 255);
-        }
-        F.du_full[(size_t)y * g.bpl + x] = (uint8_t)du;
-        F.dv_full[(size_t)y * g.bpl + x] = (uint8_t)dv;
-      }
-    }
-  }
-}
-
-// ----------------------------------------------------------------------------------------------------------
-// Fused kernel.  One CTA = one TW x TH tile of one image.
-//   phase 1  one elected thread issues a TMA tile load (cp.async.bulk.tensor.3d, zero fill outside the image) of the
-//            image tile plus halo into shared memory; everybody waits on the mbarrier.
-//   phase 2  register-window filters.  A thread owns one 32-bit word (4 pixels) of a row segment and walks down the
-//            rows.  All arithmetic is done on two 16-bit lanes per register ((b0,b2) and (b1,b3) of the word): every
-//            intermediate is kept non-negative by a bias (765 on the horizontal (1,2,0,-2,-1) sum, 510 on the
-//            (1,1,0,-1,-1) sum, ...), so plain 32-bit integer adds and subtracts never carry between the lanes.
-//            du and dv leave as one coalesced 32-bit store per word and row; the blob response f1 (+6375) and the
-//            checkerboard response f2 (+2040) go to shared memory only.
-//   phase 3  NMS on the biased responses.  Dense cells: one thread per cell; sparse cells: four lanes per cell, each
-//            scanning every fourth column, combined with warp shuffles.  Extrema are reduced as keys
-//            (value << 8 | position) so that "first in column-major order" falls out of a min / max.  The four
-//            candidates of a cell that pass the tau test get a window scan for a strictly better value.
-// A cell is owned by the tile that contains its origin; the halo is nmax to the left/top and 2*nmax to the
-// right/bottom because a cell spans [i,i+n] and its extremum's neighbourhood [i-n,i+2n] (matcher.cpp:356,383).
+// Packed filter arithmetic.  A thread owns one 32-bit word (4 pixels b0..b3) of an image row and walks down the rows
+// with a 5-row register window.  Everything is computed on two 16-bit lanes per register, (b0,b2) and (b1,b3) of the
+// word; every intermediate is kept non-negative by a bias, so plain 32-bit adds, subtracts and multiplies by small
+// constants never carry between the lanes (ptxas spreads them over the FMA pipe as IMAD and the ALU pipe as IADD3).
 constexpr int BIAS_F1 = 6375;    // 25 * 255: f1 + BIAS_F1 >= 0
 constexpr int BIAS_F2 = 2040;    //  8 * 255
 #define K2(v) ((uint32_t)(v) | ((uint32_t)(v) << 16))   /* the same constant in both 16-bit lanes */
 
-struct TileShape { int nmax, FW, FH, NWo, NW, IS, IH, FS, iw0; size_t img_bytes, smem; };
-__host__ __device__ inline TileShape tile_shape(int nmax) {
-  TileShape t;
-  t.nmax = nmax;
-  t.FW = TW + 3 * nmax; t.FH = TH + 3 * nmax;
-  // response columns start at fxs = fx0 rounded down to a multiple of 4 (fx0 = x0 - nmax, x0 multiple of TW)
-  const int lead = ((-nmax) % 4 + 4) % 4;                 // fx0 - fxs
-  t.NWo = (lead + t.FW + 3) / 4;                           // response words per row
-  // the image tile starts one word left of the response columns, moved further left to a 16-byte boundary because
-  // the TMA needs a 16-byte aligned global address for the first element of the box
-  t.iw0 = ((((-(nmax + lead + 4)) % 16) + 16) % 16) / 4;   // words between the tile origin and response word -1
-  t.NW = (t.iw0 + t.NWo + 2 + 3) & ~3;                     // image words per row, 16 B multiple
-  t.IS = t.NW * 4; t.IH = t.FH + 4;
-  t.FS = t.NWo * 4;
-  t.img_bytes = ((size_t)t.IH * t.IS + 127) & ~(size_t)127;
-  t.smem = t.img_bytes + 2 * (size_t)t.FH * t.FS * sizeof(int16_t) + 16;   // + the mbarrier
-  return t;
-}
-
-struct Win {   // 5-row windows of the horizontal sums of one word: [row slot][lane pair A=(b0,b2), B=(b1,b3)]
-  uint32_t hd[5][2], ha[5][2], h1[5][2], h3[5][2], hc[5][2], pc[5][2];
-};
-
-// horizontal sums of the 4 pixels of word C (neighbours L, R) into window slot S
-template <int S>
-__device__ __forceinline__ void hrow4(Win& w, uint32_t L, uint32_t C, uint32_t R, bool core) {
+// the six tap vectors of word C with neighbours L and R: t[k] = pixels (x-2+k, x+k) for x = b0, i.e.
+// (l2,b0) (l3,b1) (b0,b2) (b1,b3) (b2,r0) (b3,r1); lane pair A = pixels (b0,b2) uses t[0..4], B = (b1,b3) uses t[1..5]
+__device__ __forceinline__ void taps6(uint32_t L, uint32_t C, uint32_t R, uint32_t t[6]) {
   const uint32_t s2a = __funnelshift_r(L, C, 16);          // bytes l2 l3 b0 b1
   const uint32_t s2b = __funnelshift_r(C, R, 16);          // bytes b2 b3 r0 r1
-  uint32_t t[6];
-  t[0] = s2a & 0x00FF00FFu;                                // (l2, b0)
-  t[1] = __byte_perm(s2a, 0, 0x4341);                      // (l3, b1)
-  t[2] = C & 0x00FF00FFu;                                  // (b0, b2)
-  t[3] = __byte_perm(C, 0, 0x4341);                        // (b1, b3)
-  t[4] = s2b & 0x00FF00FFu;                                // (b2, r0)
-  t[5] = __byte_perm(s2b, 0, 0x4341);                      // (b3, r1)
-#pragma unroll
-  for (int k = 0; k < 2; k++) {                            // k = 0: pixels (b0,b2), k = 1: pixels (b1,b3)
-    const uint32_t t0 = t[k], t1 = t[k + 1], t2 = t[k + 2], t3 = t[k + 3], t4 = t[k + 4];
-    if (core) {
-      w.hd[S][k] = (t0 + 2 * t1 + K2(765)) - (t4 + 2 * t3);          // (1,2,0,-2,-1) + 765
-      w.ha[S][k] = (t0 + t4) + 4 * (t1 + t3) + 6 * t2;               // (1,4,6,4,1)
+  t[0] = s2a & 0x00FF00FFu;
+  t[1] = __byte_perm(s2a, 0, 0x4341);
+  t[2] = C & 0x00FF00FFu;
+  t[3] = __byte_perm(C, 0, 0x4341);
+  t[4] = s2b & 0x00FF00FFu;
+  t[5] = __byte_perm(s2b, 0, 0x4341);
+}
+
+// Sobel walker: du = ((1,4,6,4,1)^T x (1,2,0,-2,-1)) >> 7 + 128, dv = ((1,2,0,-2,-1)^T x (1,4,6,4,1)) >> 7 + 128
+// (filter.cpp:316-324).  The sums are formed at twice their scale with a bias of 32768, so the result byte is simply the
+// high byte of each 16-bit lane and one PRMT assembles the four pixels of the output word.
+// col: word L of the first row needed (two rows above the first output row); IW: words per row of the image tile.
+// Writes rows [gy0, gy0 + nrow) of word column gx to the planes du / dv (stride bpl).
+__device__ __forceinline__ void walk_sobel(const uint32_t* col, int IW, int nrow, int gy0, int gx, int bpl, int himg,
+                                           uint8_t* __restrict__ du, uint8_t* __restrict__ dv) {
+  uint32_t hd[5][2], ha[5][2];
+#define SOB_HROW(S, r) {                                                                        \
+    const uint32_t* q = col + (r) * IW; uint32_t t[6]; taps6(q[0], q[1], q[2], t);                \
+    _Pragma("unroll") for (int k = 0; k < 2; k++) {                                               \
+      hd[S][k] = (t[k] + 2 * t[k + 1] + K2(765)) - (t[k + 4] + 2 * t[k + 3]);      /* (1,2,0,-2,-1) + 765 */ \
+      ha[S][k] = (t[k] + t[k + 4]) + 4 * (t[k + 1] + t[k + 3]) + 6 * t[k + 2];     /* (1,4,6,4,1) */          \
+    } }
+  SOB_HROW(0, 0) SOB_HROW(1, 1) SOB_HROW(2, 2) SOB_HROW(3, 3)
+  const bool first_word = gx == 0, last_word = gx == bpl - 4;
+  for (int r5 = 0; r5 < nrow; r5 += 5) {
+#define SOB_STEP(PH)                                                                                              \
+    if (r5 + PH < nrow) {                                                                                         \
+      constexpr int s0 = PH % 5, s1 = (PH + 1) % 5, s2 = (PH + 2) % 5, s3 = (PH + 3) % 5, s4 = (PH + 4) % 5;      \
+      const int gy = gy0 + r5 + PH;                                                                               \
+      SOB_HROW(s4, r5 + PH + 4)                                                                                   \
+      uint32_t u2[2], v2[2];                                                                                      \
+      _Pragma("unroll") for (int k = 0; k < 2; k++) {                                                             \
+        u2[k] = 2 * (hd[s0][k] + hd[s4][k]) + 8 * (hd[s1][k] + hd[s3][k]) + 12 * hd[s2][k] + K2(8288);            \
+        v2[k] = 2 * ((ha[s0][k] + K2(4080)) - ha[s4][k]) + 4 * ((ha[s1][k] + K2(4080)) - ha[s3][k]) + K2(8288);   \
+      }                                                                                                           \
+      uint32_t wu = __byte_perm(u2[0], u2[1], 0x7351), wv = __byte_perm(v2[0], v2[1], 0x7351);                    \
+      if (gy < 2 || gy > himg - 3) { wu = 0x80808080u; wv = 0x80808080u; }                                        \
+      if (first_word) { wu = (wu & 0xFFFF0000u) | 0x8080u; wv = (wv & 0xFFFF0000u) | 0x8080u; }                   \
+      if (last_word) { wu = (wu & 0x0000FFFFu) | 0x80800000u; wv = (wv & 0x0000FFFFu) | 0x80800000u; }            \
+      *(uint32_t*)(du + (size_t)gy * bpl + gx) = wu;                                                              \
+      *(uint32_t*)(dv + (size_t)gy * bpl + gx) = wv;                                                              \
     }
-    w.h1[S][k] = t0 + t1 + t2 + t3 + t4;
-    w.h3[S][k] = t1 + t2 + t3;
-    w.hc[S][k] = (t0 + t1 + K2(510)) - (t3 + t4);                    // (1,1,0,-1,-1) + 510
-    w.pc[S][k] = t2;
+    SOB_STEP(0) SOB_STEP(1) SOB_STEP(2) SOB_STEP(3) SOB_STEP(4)
+#undef SOB_STEP
   }
+#undef SOB_HROW
+}
+
+// Blob / checkerboard walker: f1 = -box5 + 2 box3 + 7 centre (filter.cpp:343-365), f2 = (1,1,0,-1,-1)^T x (1,1,0,-1,-1)
+// (filter.cpp:331-336), stored biased (BIAS_F1 / BIAS_F2) as int16 rows of FS samples in shared memory.
+// col as above; out1 / out2 point at the first output row of this word (4 samples = 8 bytes, 8-byte aligned).
+__device__ __forceinline__ void walk_blob_checker(const uint32_t* col, int IW, int nrow, int16_t* out1, int16_t* out2, int FS) {
+  uint32_t h1[5][2], h3[5][2], hc[5][2], pc[5][2];
+#define BC_HROW(S, r) {                                                                         \
+    const uint32_t* q = col + (r) * IW; uint32_t t[6]; taps6(q[0], q[1], q[2], t);                \
+    _Pragma("unroll") for (int k = 0; k < 2; k++) {                                               \
+      h3[S][k] = t[k + 1] + t[k + 2] + t[k + 3];                                                  \
+      h1[S][k] = h3[S][k] + t[k] + t[k + 4];                                                      \
+      hc[S][k] = (t[k] + t[k + 1] + K2(510)) - (t[k + 3] + t[k + 4]);             /* (1,1,0,-1,-1) + 510 */   \
+      pc[S][k] = t[k + 2];                                                                        \
+    } }
+  BC_HROW(0, 0) BC_HROW(1, 1) BC_HROW(2, 2) BC_HROW(3, 3)
+  for (int r5 = 0; r5 < nrow; r5 += 5) {
+#define BC_STEP(PH)                                                                                               \
+    if (r5 + PH < nrow) {                                                                                         \
+      constexpr int s0 = PH % 5, s1 = (PH + 1) % 5, s2 = (PH + 2) % 5, s3 = (PH + 3) % 5, s4 = (PH + 4) % 5;      \
+      BC_HROW(s4, r5 + PH + 4)                                                                                    \
+      uint32_t f1[2], f2[2];                                                                                      \
+      _Pragma("unroll") for (int k = 0; k < 2; k++) {                                                             \
+        const uint32_t b3 = h3[s1][k] + h3[s2][k] + h3[s3][k];                                                    \
+        const uint32_t b5 = h1[s0][k] + h1[s1][k] + h1[s2][k] + h1[s3][k] + h1[s4][k];                            \
+        f1[k] = (7 * pc[s2][k] + 2 * b3 + K2(BIAS_F1)) - b5;                                                      \
+        f2[k] = (hc[s0][k] + hc[s1][k] + K2(BIAS_F2)) - (hc[s3][k] + hc[s4][k]);                                  \
+      }                                                                                                           \
+      *(uint2*)(out1 + (r5 + PH) * FS) = make_uint2(__byte_perm(f1[0], f1[1], 0x5410), __byte_perm(f1[0], f1[1], 0x7632)); \
+      *(uint2*)(out2 + (r5 + PH) * FS) = make_uint2(__byte_perm(f2[0], f2[1], 0x5410), __byte_perm(f2[0], f2[1], 0x7632)); \
+    }
+    BC_STEP(0) BC_STEP(1) BC_STEP(2) BC_STEP(3) BC_STEP(4)
+#undef BC_STEP
+  }
+#undef BC_HROW
+}
+
+// full-resolution Sobel planes only (the *_full planes of matcher.cpp:676 used by the refinement), half-resolution mode:
+// the same walker on words loaded from global memory through a small shared-memory tile.
+constexpr int SF_TW = 256, SF_TH = 32;                      // core pixels of one CTA
+__global__ void __launch_bounds__(256) k_sobel_full(Geometry g, const FrameDev* frames, SlotList sl) {
+  __shared__ uint32_t simg[(SF_TH + 4) * (SF_TW / 4 + 2)];
+  const FrameDev F = frames[sl.s[blockIdx.z]];
+  const int x0 = blockIdx.x * SF_TW, y0 = blockIdx.y * SF_TH;
+  constexpr int IW = SF_TW / 4 + 2;
+  for (int idx = threadIdx.x; idx < (SF_TH + 4) * IW; idx += 256) {
+    const int ly = idx / IW, lw = idx - ly * IW;
+    const int gx = x0 - 4 + 4 * lw, gy = y0 - 2 + ly;
+    uint32_t v = 0;
+    if (gy >= 0 && gy < g.h && gx >= 0 && gx < g.bpl) v = __ldg((const uint32_t*)(F.img + (size_t)gy * g.bpl + gx));
+    simg[idx] = v;
+  }
+  __syncthreads();
+  // 64 word columns x 4 row segments of 8 rows
+  const int wcol = threadIdx.x & 63, seg = threadIdx.x >> 6;
+  const int gx = x0 + 4 * wcol, gy0 = y0 + 8 * seg;
+  if (gx >= g.bpl || gy0 >= g.h) return;
+  walk_sobel(simg + (8 * seg) * IW + wcol, IW, min(8, g.h - gy0), gy0, gx, g.bpl, g.h, F.du_full, F.dv_full);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Tiling of the fused kernel.  Tiles are aligned to the cell grid of the NMS pass with the larger neighbourhood (the
+// sparse pass when multi_stage): a tile owns kx x ky of its cells, which lie completely inside the tile, so the response
+// planes need a halo of only n samples to the left / top and max(n, 2 n_other) to the right / bottom.  Cells of the
+// other pass belong to the tile that contains their origin.  du / dv are written for the 4-aligned pixel range of the
+// tile; first and last tiles extend to the image borders.
+struct TileCfg {
+  int nA, stepA, orgA;     // the aligning pass: n, n + 1, n + margin
+  int extR;                // response halo to the right / bottom of the tile's cell range
+  int kx, ky, ntx, nty, TWn, THn;
+  int NWf, FS, FH;         // response planes in shared memory: words (4 samples) per row, samples per row, rows
+  int IS, IH;              // image tile: bytes per row (multiple of 16), rows
+  int seg;                 // rows per filter walker
+  int max_cells;           // owned cells of one tile, both passes
+  int threads;
+  unsigned img_bytes, f_bytes, smem;
+};
+
+struct TileRange {         // one axis of one tile
+  int own_lo, own_hi;      // cells with origin in [own_lo, own_hi) belong to the tile
+  int f_lo, f_hi;          // response samples held in shared memory: [f_lo, f_hi), f_lo 4-aligned along x
+  int d_lo, d_hi;          // du / dv samples written
+  int i_lo, i_hi;          // image samples needed (along x: i_lo 16-byte aligned)
+};
+
+__host__ __device__ inline TileRange tile_range(const TileCfg& t, int idx, int ntiles, int len, int len_pad, bool xaxis) {
+  TileRange r;
+  const int TN = xaxis ? t.TWn : t.THn;
+  const int n0 = t.orgA + TN * idx;
+  const bool first = idx == 0, last = idx == ntiles - 1;
+  r.own_lo = first ? 0 : n0;
+  r.own_hi = last ? 0x3FFFFFFF : n0 + TN;
+  int f_lo = first ? VISO_MARGIN : n0 - t.nA;
+  int f_hi = len - VISO_MARGIN;
+  if (!last && n0 + TN + t.extR < f_hi) f_hi = n0 + TN + t.extR;
+  int d_lo = first ? 0 : n0, d_hi = last ? len_pad : n0 + TN;
+  if (xaxis) { f_lo &= ~3; d_lo &= ~3; if (!last) d_hi &= ~3; }
+  if (d_lo > len_pad) d_lo = len_pad;
+  if (d_hi > len_pad) d_hi = len_pad;
+  if (f_hi < f_lo) f_hi = f_lo;
+  if (xaxis) f_hi = f_lo + ((f_hi - f_lo + 3) & ~3);
+  r.f_lo = f_lo; r.f_hi = f_hi; r.d_lo = d_lo; r.d_hi = d_hi;
+  int lo = d_lo < f_lo ? d_lo : f_lo, hi = d_hi > f_hi ? d_hi : f_hi;
+  if (d_hi <= d_lo) { lo = f_lo; hi = f_hi; }
+  if (f_hi <= f_lo) { lo = d_lo; hi = d_hi; }
+  if (xaxis) { r.i_lo = (lo - 4) & ~15; r.i_hi = hi + 4; }
+  else { r.i_lo = lo - 2; r.i_hi = hi + 2; }
+  return r;
+}
+
+// owned cell range of pass p along one axis: cells k with origin org + k * step in [own_lo, own_hi), k < ncells
+__host__ __device__ inline void owned_cells(const TileRange& r, int n, int ncells, int& klo, int& nk) {
+  const int step = n + 1, org = n + VISO_MARGIN;
+  int a = r.own_lo - org; klo = a > 0 ? (a + step - 1) / step : 0;
+  int khi = ncells;
+  if (r.own_hi < 0x3FFFFFFF) { int b = r.own_hi - org; khi = b > 0 ? (b + step - 1) / step : 0; if (khi > ncells) khi = ncells; }
+  nk = khi > klo ? khi - klo : 0;
 }
 
 __device__ __forceinline__ bool mbar_wait_or_trap(uint32_t bar, uint32_t phase) {
@@ -188,22 +245,201 @@ __device__ __forceinline__ bool mbar_wait_or_trap(uint32_t bar, uint32_t phase) 
   }
 }
 
-__global__ void __launch_bounds__(FILTER_THREADS, 2)
-k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __grid_constant__ CUtensorMap tmap, int use_tma, int max_cells) {
+// ---- phase 3a: cell extremes as keys (value << 16 | position), position = (dx << 4 | dy) for the minimum and its
+// complement for the maximum, so that "first extreme in column-major order" (matcher.cpp:356-379) falls out of min / max.
+// A row of the cell is read as 32-bit words (two samples each); the key of the low sample is w * 65536 + pos (an IMAD on
+// the FMA pipe), the key of the high sample (w & 0xFFFF0000) | pos (a LOP3 on the ALU pipe).
+struct Keys4 { uint32_t mn1, mx1, mn2, mx2; };
+
+template <int N1, bool ODD>
+__device__ __forceinline__ void cell_keys_rows(const uint32_t* r1, const uint32_t* r2, int FSW, int nrows, Keys4& K) {
+  // r1 / r2: word holding sample i0 (ODD: in its high half) of the first row, planes f1 / f2; positions are relative
+  // to this row (dy = 0 .. nrows - 1)
+  constexpr int NW = (N1 + (ODD ? 1 : 0) + 1) / 2;
+#pragma unroll
+  for (int rr = 0; rr < (N1 + 1) / 2 + (N1 > 5 ? 0 : N1 / 2); rr++) {      // at most N1 rows (dense) or ceil(N1 / 2) (sparse halves)
+    if (rr < nrows) {
+      uint32_t a[NW], b[NW];
+#pragma unroll
+      for (int j = 0; j < NW; j++) { a[j] = r1[rr * FSW + j]; b[j] = r2[rr * FSW + j]; }
+#pragma unroll
+      for (int j = 0; j < NW; j++) {
+        const int dx_lo = 2 * j - (ODD ? 1 : 0), dx_hi = dx_lo + 1;
+        if (dx_lo >= 0 && dx_lo < N1) {
+          const uint32_t p = (uint32_t)((dx_lo << 4) | rr);
+          K.mn1 = min(K.mn1, a[j] * 65536u + p); K.mx1 = max(K.mx1, a[j] * 65536u + (p ^ 0xFFu));
+          K.mn2 = min(K.mn2, b[j] * 65536u + p); K.mx2 = max(K.mx2, b[j] * 65536u + (p ^ 0xFFu));
+        }
+        if (dx_hi >= 0 && dx_hi < N1) {
+          const uint32_t p = (uint32_t)((dx_hi << 4) | rr);
+          K.mn1 = min(K.mn1, (a[j] & 0xFFFF0000u) | p); K.mx1 = max(K.mx1, (a[j] & 0xFFFF0000u) | (p ^ 0xFFu));
+          K.mn2 = min(K.mn2, (b[j] & 0xFFFF0000u) | p); K.mx2 = max(K.mx2, (b[j] & 0xFFFF0000u) | (p ^ 0xFFu));
+        }
+      }
+    }
+  }
+}
+
+// any cell size: one 16-bit load per sample
+__device__ __forceinline__ void cell_keys_generic(const int16_t* q1, const int16_t* q2, int FS, int n1, int row_lo, int row_hi, Keys4& K) {
+  for (int dj = row_lo; dj < row_hi; dj++)
+    for (int di = 0; di < n1; di++) {
+      const uint32_t p = (uint32_t)((di << 4) | (dj - row_lo));
+      const uint32_t v1 = (uint32_t)(uint16_t)q1[dj * FS + di] << 16, v2 = (uint32_t)(uint16_t)q2[dj * FS + di] << 16;
+      K.mn1 = min(K.mn1, v1 | p); K.mx1 = max(K.mx1, v1 | (p ^ 0xFFu));
+      K.mn2 = min(K.mn2, v2 | p); K.mx2 = max(K.mx2, v2 | (p ^ 0xFFu));
+    }
+}
+
+// keys of rows [row_lo, row_hi) of the cell whose first sample is (i0, j0) in the response planes; positions come back
+// relative to row_lo and are shifted to the cell by the caller
+__device__ __forceinline__ void cell_keys(const int16_t* sf1, const int16_t* sf2, int FS, int n1, int i0, int j0, int row_lo, int row_hi, Keys4& K) {
+  const int FSW = FS >> 1;
+  const uint32_t* r1 = (const uint32_t*)(sf1 + (j0 + row_lo) * FS) + (i0 >> 1);
+  const uint32_t* r2 = (const uint32_t*)(sf2 + (j0 + row_lo) * FS) + (i0 >> 1);
+  const int nrows = row_hi - row_lo;
+  const bool odd = i0 & 1;
+  switch (n1) {
+    case 3: if (odd) cell_keys_rows<3, true>(r1, r2, FSW, nrows, K); else cell_keys_rows<3, false>(r1, r2, FSW, nrows, K); break;
+    case 4: if (odd) cell_keys_rows<4, true>(r1, r2, FSW, nrows, K); else cell_keys_rows<4, false>(r1, r2, FSW, nrows, K); break;
+    case 7: if (odd) cell_keys_rows<7, true>(r1, r2, FSW, nrows, K); else cell_keys_rows<7, false>(r1, r2, FSW, nrows, K); break;
+    case 10: if (odd) cell_keys_rows<10, true>(r1, r2, FSW, nrows, K); else cell_keys_rows<10, false>(r1, r2, FSW, nrows, K); break;
+    default: cell_keys_generic(sf1 + j0 * FS + i0, sf2 + j0 * FS + i0, FS, n1, row_lo, row_hi, K); break;
+  }
+}
+
+// ---- phase 3b: window test of the candidates of one pass and one kind (minima or maxima).
+// A candidate survives iff nothing in its clamped (2n+1)^2 window is strictly better (matcher.cpp:383-427); positions
+// inside the cell can never be strictly better than the cell extreme, so the reference's cell exclusion is implied.
+// Every lane walks through its own candidates (slots tid, tid + T, ...); one loop iteration scans the two rows at
+// distance r above and below the extreme, r = 0 .. n (most rejections happen next to the extreme), and a lane that is
+// done with a candidate fetches its next one while its neighbours keep scanning: no lane waits for another's window.
+// Rows are read as n+1 32-bit words (two samples each); of the 2n+2 samples exactly one lies outside the window (the
+// low half of the first word or the high half of the last) and is neutralised by a mask.
+template <int N1, bool IS_MIN>
+__device__ __forceinline__ void scan_candidates(const int16_t* sf1, const int16_t* sf2, int FS, uint8_t* codes, int ncell, int nk,
+                                                int n, int cx0, int cy0, int xhi, int yhi, int tid, int T) {
+  // cx0 / cy0: response-plane coordinates of the first owned cell's origin; slot = 2 * cell + plane
+  const int FSW = FS >> 1;
+  const int nslots = 2 * ncell;
+  const int step = n + 1;
+  int s = tid;
+  bool active = false;
+  const uint32_t* rowc = nullptr;    // word of the first window column in the extreme's row
+  uint32_t target2 = 0, m_first = 0, m_last = 0;
+  int r = 0, rdn = 0;
+  uint8_t* code = nullptr;
+  const int nw_rt = N1 > 0 ? N1 : n + 1;
+  for (;;) {
+    if (!active) {
+      int pos = 0xFF, cell = 0, plane = 0;
+      for (; s < nslots; s += T) {
+        cell = s >> 1; plane = s & 1;
+        pos = codes[4 * cell + 2 * plane + (IS_MIN ? 0 : 1)];
+        if (pos != 0xFF) break;
+      }
+      if (s >= nslots) break;
+      s += T;
+      const int kk = cell % nk, ll = cell / nk;
+      const int ex = cx0 + kk * step + (pos >> 4), ey = cy0 + ll * step + (pos & 15);
+      const int16_t* sf = plane ? sf2 : sf1;
+      code = codes + 4 * cell + 2 * plane + (IS_MIN ? 0 : 1);
+      const uint32_t val = (uint16_t)sf[ey * FS + ex];
+      const int xs = ex - n;
+      if (ex + n > xhi) {
+        // window clamped at the right image border (last cell columns only): plain scan
+        const int xe = xhi, ye = min(ey + n, yhi);
+        bool keep = true;
+        for (int j2 = ey - n; j2 <= ye && keep; j2++)
+          for (int i2 = xs; i2 <= xe; i2++) {
+            const uint32_t v = (uint16_t)sf[j2 * FS + i2];
+            if (IS_MIN ? v < val : v > val) { keep = false; break; }
+          }
+        if (!keep) *code = 0xFF;
+        continue;
+      }
+      target2 = val | (val << 16);
+      rowc = (const uint32_t*)(sf + ey * FS) + (xs >> 1);
+      // neutral element of the reduction: 0xFFFF for minima (OR mask), 0 for maxima (AND mask)
+      m_first = (xs & 1) ? 0x0000FFFFu : 0u;
+      m_last = (xs & 1) ? 0u : 0xFFFF0000u;
+      rdn = min(n, yhi - ey);
+      r = 0;
+      active = true;
+    }
+    // rows ey - r (always inside the valid region) and ey + r (if not clamped away)
+    uint32_t acc;
+    {
+      const uint32_t* up = rowc - r * FSW;
+      const uint32_t* dn = rowc + (r <= rdn ? r : -r) * FSW;       // clamped away: read the upper row twice
+      if (N1 > 0) {
+        uint32_t a[N1 > 0 ? N1 : 1], b[N1 > 0 ? N1 : 1];
+#pragma unroll
+        for (int j = 0; j < N1; j++) { a[j] = up[j]; b[j] = dn[j]; }
+        if (IS_MIN) {
+          a[0] |= m_first; b[0] |= m_first; a[N1 - 1] |= m_last; b[N1 - 1] |= m_last;
+          acc = __vminu2(a[0], b[0]);
+#pragma unroll
+          for (int j = 1; j < N1; j++) acc = __vimin3_u16x2(acc, a[j], b[j]);
+        } else {
+          a[0] &= ~m_first; b[0] &= ~m_first; a[N1 - 1] &= ~m_last; b[N1 - 1] &= ~m_last;
+          acc = __vmaxu2(a[0], b[0]);
+#pragma unroll
+          for (int j = 1; j < N1; j++) acc = __vimax3_u16x2(acc, a[j], b[j]);
+        }
+      } else {
+        if (IS_MIN) {
+          acc = __vminu2(up[0] | m_first, dn[0] | m_first);
+          for (int j = 1; j < nw_rt - 1; j++) acc = __vimin3_u16x2(acc, up[j], dn[j]);
+          acc = __vimin3_u16x2(acc, up[nw_rt - 1] | m_last | (nw_rt == 1 ? m_first : 0u), dn[nw_rt - 1] | m_last | (nw_rt == 1 ? m_first : 0u));
+        } else {
+          acc = __vmaxu2(up[0] & ~m_first, dn[0] & ~m_first);
+          for (int j = 1; j < nw_rt - 1; j++) acc = __vimax3_u16x2(acc, up[j], dn[j]);
+          acc = __vimax3_u16x2(acc, up[nw_rt - 1] & ~m_last & (nw_rt == 1 ? ~m_first : ~0u), dn[nw_rt - 1] & ~m_last & (nw_rt == 1 ? ~m_first : ~0u));
+        }
+      }
+    }
+    const bool better = (IS_MIN ? __vminu2(acc, target2) : __vmaxu2(acc, target2)) != target2;
+    if (better) { *code = 0xFF; active = false; }
+    else if (++r > n) active = false;
+  }
+}
+
+template <bool IS_MIN>
+__device__ __forceinline__ void scan_dispatch(const int16_t* sf1, const int16_t* sf2, int FS, uint8_t* codes, int ncell, int nk, int n,
+                                              int cx0, int cy0, int xhi, int yhi, int tid, int T) {
+  switch (n + 1) {
+    case 3: scan_candidates<3, IS_MIN>(sf1, sf2, FS, codes, ncell, nk, n, cx0, cy0, xhi, yhi, tid, T); break;
+    case 4: scan_candidates<4, IS_MIN>(sf1, sf2, FS, codes, ncell, nk, n, cx0, cy0, xhi, yhi, tid, T); break;
+    case 7: scan_candidates<7, IS_MIN>(sf1, sf2, FS, codes, ncell, nk, n, cx0, cy0, xhi, yhi, tid, T); break;
+    case 10: scan_candidates<10, IS_MIN>(sf1, sf2, FS, codes, ncell, nk, n, cx0, cy0, xhi, yhi, tid, T); break;
+    default: scan_candidates<0, IS_MIN>(sf1, sf2, FS, codes, ncell, nk, n, cx0, cy0, xhi, yhi, tid, T); break;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Fused kernel.  One CTA = one tile of one image (TileCfg above).
+//   phase 1  one elected thread issues a TMA tile load (cp.async.bulk.tensor.3d, zero fill outside the image) of the
+//            image tile into shared memory; everybody waits on the mbarrier.
+//   phase 2  register-window filters: Sobel walkers write du / dv (one coalesced 32-bit store per word and row),
+//            blob / checkerboard walkers write the biased responses f1 / f2 to shared memory only.
+//   phase 3  NMS of both passes on the responses: cell extremes as keys, tau test, window test, then one code word per
+//            owned cell (4 bytes = position of the kept extreme of each class or 0xFF) to global memory.
+__global__ void __launch_bounds__(MAX_FILTER_THREADS, 2)
+k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const __grid_constant__ SlotList sl, const __grid_constant__ TileCfg t,
+             const __grid_constant__ CUtensorMap tmap, int use_tma) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int slot = sl.s[blockIdx.z];
   const FrameDev F = frames[slot];
-  const int tid = threadIdx.x;
-  const TileShape ts = tile_shape(nmax);
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const int fx0 = x0 - nmax, fy0 = y0 - nmax;              // origin of the response region that NMS reads
-  const int fxs = fx0 & ~3;                                // response columns in shared memory start here
-  const int rx0 = fxs - 4 - 4 * ts.iw0, iy0 = fy0 - 2;      // image tile origin (16-byte aligned in x)
-  const int FH = ts.FH, FS = ts.FS, IS = ts.IS, IH = ts.IH, NWo = ts.NWo;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const TileRange X = tile_range(t, blockIdx.x, t.ntx, g.wm, g.bplm, true);
+  const TileRange Y = tile_range(t, blockIdx.y, t.nty, g.hm, g.hm, false);
+  const int FS = t.FS, IS = t.IS, IH = t.IH, IW = IS >> 2;
   uint8_t* simg = smem;
-  int16_t* sf1 = (int16_t*)(smem + ts.img_bytes);
-  int16_t* sf2 = sf1 + (size_t)FH * FS;
-  uint64_t* s_bar = (uint64_t*)(sf2 + (size_t)FH * FS);
+  int16_t* sf1 = (int16_t*)(smem + t.img_bytes);
+  int16_t* sf2 = sf1 + (size_t)t.FH * FS;
+  uint64_t* s_bar = (uint64_t*)(smem + t.img_bytes + t.f_bytes);
+  uint32_t* s_code = (uint32_t*)(s_bar + 2);
 
   // ---- phase 1
   if (use_tma) {
@@ -219,15 +455,14 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          :: "r"(dst), "l"(&tmap), "r"(rx0), "r"(iy0), "r"(slot), "r"(bar) : "memory");
+          :: "r"(dst), "l"(&tmap), "r"(X.i_lo), "r"(Y.i_lo), "r"(slot), "r"(bar) : "memory");
     }
     mbar_wait_or_trap(bar, 0);
   } else {
     const uint8_t* __restrict__ I = g.half ? F.half : F.img;
-    const int words = IS >> 2;
-    for (int idx = tid; idx < IH * words; idx += FILTER_THREADS) {
-      const int ly = idx / words, lw = idx - ly * words;
-      const int gx = rx0 + 4 * lw, gy = iy0 + ly;
+    for (int idx = tid; idx < IH * IW; idx += T) {
+      const int ly = idx / IW, lw = idx - ly * IW;
+      const int gx = X.i_lo + 4 * lw, gy = Y.i_lo + ly;
       uint32_t v = 0;
       if (gy >= 0 && gy < g.hm && gx >= 0 && gx < g.bplm) v = __ldg((const uint32_t*)(I + (size_t)gy * g.bplm + gx));
       *(uint32_t*)(simg + ly * IS + 4 * lw) = v;
@@ -235,177 +470,104 @@ k_filter_nms(Geometry g, const FrameDev* frames, SlotList sl, int nmax, const __
     __syncthreads();
   }
 
-  // ---- phase 2
+  // ---- phase 2: work items = (word column, row segment) of the Sobel range, then of the response range
   {
-    const int nseg = (FH + SEG - 1) / SEG;
-    for (int item = tid; item < NWo * nseg; item += FILTER_THREADS) {
-      const int seg = item / NWo, j = item - seg * NWo;
-      const int ly0 = seg * SEG;
-      const int nrow = min(SEG, FH - ly0);
-      const int gx = fxs + 4 * j;                                          // first pixel of this word
-      const uint32_t* col = (const uint32_t*)simg + ts.iw0 + j;            // words L, C, R of an image-tile row
-      const int IW = IS >> 2;
-      const bool core = gx >= x0 && gx < x0 + TW && gx < g.bplm;           // du/dv are written for core words only
-      Win w;
-#define VISO_HROW(S, r) { const uint32_t* q = col + (r) * IW; hrow4<S>(w, q[0], q[1], q[2], core); }
-      VISO_HROW(0, ly0) VISO_HROW(1, ly0 + 1) VISO_HROW(2, ly0 + 2) VISO_HROW(3, ly0 + 3)
-      for (int r5 = 0; r5 < nrow; r5 += 5) {
-#define VISO_STEP(PH)                                                                                                  \
-        if (r5 + PH < nrow) {                                                                                          \
-          constexpr int s0 = PH % 5, s1 = (PH + 1) % 5, s2 = (PH + 2) % 5, s3 = (PH + 3) % 5, s4 = (PH + 4) % 5;       \
-          const int ly = ly0 + r5 + PH, gy = fy0 + ly;                                                                 \
-          VISO_HROW(s4, ly + 4)                                                                                        \
-          uint32_t f1[2], f2[2], du[2], dv[2];                                                                         \
-          _Pragma("unroll") for (int k = 0; k < 2; k++) {                                                              \
-            const uint32_t b3 = w.h3[s1][k] + w.h3[s2][k] + w.h3[s3][k];                                               \
-            const uint32_t b5 = w.h1[s0][k] + w.h1[s1][k] + w.h1[s2][k] + w.h1[s3][k] + w.h1[s4][k];                   \
-            f1[k] = (7 * w.pc[s2][k] + 2 * b3 + K2(BIAS_F1)) - b5;                                                     \
-            f2[k] = (w.hc[s0][k] + w.hc[s1][k] + K2(BIAS_F2)) - (w.hc[s3][k] + w.hc[s4][k]);                           \
-            if (core) {                                                                                                \
-              const uint32_t a = (w.hd[s0][k] + w.hd[s4][k]) + 4 * (w.hd[s1][k] + w.hd[s3][k]) + 6 * w.hd[s2][k] + K2(4144); \
-              du[k] = (a >> 7) & 0x01FF01FFu;                                                                          \
-              const uint32_t b = (w.ha[s0][k] + 2 * w.ha[s1][k] + K2(12240 + 4144)) - (w.ha[s4][k] + 2 * w.ha[s3][k]); \
-              dv[k] = (b >> 7) & 0x01FF01FFu;                                                                          \
-            }                                                                                                          \
-          }                                                                                                            \
-          *(uint2*)(sf1 + ly * FS + 4 * j) = make_uint2(__byte_perm(f1[0], f1[1], 0x5410), __byte_perm(f1[0], f1[1], 0x7632)); \
-          *(uint2*)(sf2 + ly * FS + 4 * j) = make_uint2(__byte_perm(f2[0], f2[1], 0x5410), __byte_perm(f2[0], f2[1], 0x7632)); \
-          if (core && gy >= y0 && gy < y0 + TH && gy < g.hm) {                                                         \
-            uint32_t wu = du[0] | (du[1] << 8), wv = dv[0] | (dv[1] << 8);                                             \
-            if (gy < 2 || gy > g.hm - 3) { wu = 0x80808080u; wv = 0x80808080u; }                                       \
-            if (gx == 0) { wu = (wu & 0xFFFF0000u) | 0x8080u; wv = (wv & 0xFFFF0000u) | 0x8080u; }                     \
-            if (gx == g.bplm - 4) { wu = (wu & 0x0000FFFFu) | 0x80800000u; wv = (wv & 0x0000FFFFu) | 0x80800000u; }    \
-            *(uint32_t*)(F.du + (size_t)gy * g.bplm + gx) = wu;                                                        \
-            *(uint32_t*)(F.dv + (size_t)gy * g.bplm + gx) = wv;                                                        \
-          }                                                                                                            \
-        }
-        VISO_STEP(0) VISO_STEP(1) VISO_STEP(2) VISO_STEP(3) VISO_STEP(4)
-#undef VISO_STEP
+    const int seg = t.seg;
+    const int nwa = (X.d_hi - X.d_lo) >> 2, nra = Y.d_hi - Y.d_lo, nsa = nra > 0 ? (nra + seg - 1) / seg : 0;
+    const int nwb = (X.f_hi - X.f_lo) >> 2, nrb = Y.f_hi - Y.f_lo, nsb = nrb > 0 ? (nrb + seg - 1) / seg : 0;
+    const int na = nwa * nsa, nb = nwb * nsb;
+    const uint32_t* img32 = (const uint32_t*)simg;
+    for (int item = tid; item < na + nb; item += T) {
+      if (item < na) {
+        const int sg = item / nwa, j = item - sg * nwa;
+        const int gx = X.d_lo + 4 * j, gy0 = Y.d_lo + sg * seg;
+        const uint32_t* col = img32 + (gy0 - 2 - Y.i_lo) * IW + ((gx - X.i_lo) >> 2) - 1;
+        walk_sobel(col, IW, min(seg, Y.d_hi - gy0), gy0, gx, g.bplm, g.hm, F.du, F.dv);
+      } else {
+        const int it = item - na;
+        const int sg = it / nwb, j = it - sg * nwb;
+        const int gx = X.f_lo + 4 * j, ly0 = sg * seg, gy0 = Y.f_lo + ly0;
+        const uint32_t* col = img32 + (gy0 - 2 - Y.i_lo) * IW + ((gx - X.i_lo) >> 2) - 1;
+        walk_blob_checker(col, IW, min(seg, nrb - ly0), sf1 + ly0 * FS + 4 * j, sf2 + ly0 * FS + 4 * j, FS);
       }
-#undef VISO_HROW
     }
   }
   __syncthreads();
 
   // ---- phase 3
   {
-    uint32_t* s_code = (uint32_t*)(s_bar + 2);                             // one code word per owned cell (both passes)
-    uint32_t* s_queue = s_code + max_cells;                                // candidates that passed the tau test
-    int* s_qn = (int*)(s_bar + 1);
-    const int xhi = g.wm - 1 - VISO_MARGIN - fxs, yhi = g.hm - 1 - VISO_MARGIN - fy0;   // window clamps, smem coordinates
+    const int xhi = g.wm - 1 - VISO_MARGIN - X.f_lo, yhi = g.hm - 1 - VISO_MARGIN - Y.f_lo;   // window clamps, plane coordinates
     int klo[2], nk[2], llo[2], nl[2], cbase[2];
     int ncell_total = 0;
 #pragma unroll
     for (int p = 0; p < 2; p++) {
       klo[p] = llo[p] = nk[p] = nl[p] = 0; cbase[p] = ncell_total;
       if (p < g.first_pass) continue;
-      const int step = g.n[p] + 1, org = g.n[p] + VISO_MARGIN;
-      int a = x0 - org; klo[p] = a > 0 ? (a + step - 1) / step : 0;
-      int b = x0 + TW - org; const int khi = b > 0 ? min((b + step - 1) / step, g.ncx[p]) : 0;
-      a = y0 - org; llo[p] = a > 0 ? (a + step - 1) / step : 0;
-      b = y0 + TH - org; const int lhi = b > 0 ? min((b + step - 1) / step, g.ncy[p]) : 0;
-      nk[p] = max(khi - klo[p], 0); nl[p] = max(lhi - llo[p], 0);
+      owned_cells(X, g.n[p], g.ncx[p], klo[p], nk[p]);
+      owned_cells(Y, g.n[p], g.ncy[p], llo[p], nl[p]);
       ncell_total += nk[p] * nl[p];
     }
-    if (tid == 0) *s_qn = 0;
-    __syncthreads();
 
-    // 3a: cell extrema.  Dense cells: one thread per cell; sparse cells: four lanes per cell, each scanning every
-    // fourth column, combined with warp shuffles.  Candidates that pass the tau test are queued.
+    // 3a: cell extremes and tau test.  Sparse-pass cells are split between two lanes (upper / lower rows).
 #pragma unroll
     for (int p = 0; p < 2; p++) {
       if (p < g.first_pass) continue;
-      const int n = g.n[p], step = n + 1, org = n + VISO_MARGIN;
+      const int n = g.n[p], n1 = n + 1, org = n + VISO_MARGIN;
       const int ncell = nk[p] * nl[p];
-      const int G = p == 0 ? 4 : 1;                                        // lanes per cell
-      const int nitem = ((ncell * G + 31) & ~31);                          // whole warps take part in the shuffles
-      for (int item = tid; item < nitem; item += FILTER_THREADS) {
-        const int cell = item / G, t = item - cell * G;
+      const int G = n1 >= 6 ? 2 : 1;                                        // lanes per cell
+      const int half_rows = (n1 + 1) >> 1;
+      const int nitem = (ncell * G + 31) & ~31;                            // whole warps take part in the shuffle
+      for (int item = tid; item < nitem; item += T) {
+        const int cell = item / G, tt = item - cell * G;
         const bool live = cell < ncell;
         const int kk = live ? cell % nk[p] : 0, ll = live ? cell / nk[p] : 0;
-        const int lx = org + (klo[p] + kk) * step - fxs, ly = org + (llo[p] + ll) * step - fy0;
-        int k1min = 0x7FFFFFFF, k1max = -1, k2min = 0x7FFFFFFF, k2max = -1;
+        const int i0 = org + (klo[p] + kk) * n1 - X.f_lo, j0 = org + (llo[p] + ll) * n1 - Y.f_lo;
+        Keys4 K = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u};
+        const int row_lo = G == 2 ? tt * half_rows : 0, row_hi = G == 2 ? (tt ? n1 : half_rows) : n1;
         if (live) {
-          for (int di = t; di <= n; di += G) {
-            const int16_t* q1 = sf1 + ly * FS + lx + di;
-            const int16_t* q2 = sf2 + ly * FS + lx + di;
-            for (int dj = 0; dj <= n; dj++) {
-              const int pos = (di << 4) | dj;
-              const int a1 = q1[dj * FS] * 256 + pos, a2 = q2[dj * FS] * 256 + pos;      // (value << 8) | position
-              k1min = min(k1min, a1); k1max = max(k1max, a1 ^ 255);                    // ^255: position -> 255 - position
-              k2min = min(k2min, a2); k2max = max(k2max, a2 ^ 255);
-            }
-          }
+          cell_keys(sf1, sf2, FS, n1, i0, j0, row_lo, row_hi, K);
+          // positions are relative to row_lo: shift them to the cell (dy is the low nibble; complemented for maxima)
+          K.mn1 += row_lo; K.mn2 += row_lo; K.mx1 -= row_lo; K.mx2 -= row_lo;
         }
-        if (G == 4) {
-#pragma unroll
-          for (int o = 1; o < 4; o <<= 1) {
-            k1min = min(k1min, __shfl_xor_sync(0xFFFFFFFFu, k1min, o)); k1max = max(k1max, __shfl_xor_sync(0xFFFFFFFFu, k1max, o));
-            k2min = min(k2min, __shfl_xor_sync(0xFFFFFFFFu, k2min, o)); k2max = max(k2max, __shfl_xor_sync(0xFFFFFFFFu, k2max, o));
-          }
+        if (G == 2) {
+          K.mn1 = min(K.mn1, __shfl_xor_sync(0xFFFFFFFFu, K.mn1, 1)); K.mx1 = max(K.mx1, __shfl_xor_sync(0xFFFFFFFFu, K.mx1, 1));
+          K.mn2 = min(K.mn2, __shfl_xor_sync(0xFFFFFFFFu, K.mn2, 1)); K.mx2 = max(K.mx2, __shfl_xor_sync(0xFFFFFFFFu, K.mx2, 1));
         }
-        if (live) {
-          if (t == 0) s_code[cbase[p] + cell] = 0xFFFFFFFFu;
-          // class c: 0 = f1 min, 1 = f1 max, 2 = f2 min, 3 = f2 max
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            if (G == 4 && c != t) continue;
-            const int key = c == 0 ? k1min : (c == 1 ? k1max : (c == 2 ? k2min : k2max));
-            const bool is_min = (c & 1) == 0;
-            const int val = key >> 8, pos = is_min ? (key & 255) : 255 - (key & 255);
-            const int bias = c < 2 ? BIAS_F1 : BIAS_F2;
-            if (is_min ? (val <= bias - g.tau) : (val >= bias + g.tau))
-              s_queue[atomicAdd(s_qn, 1)] = (uint32_t)(cbase[p] + cell) | ((uint32_t)c << 16) | ((uint32_t)pos << 18) | ((uint32_t)p << 26);
-          }
+        if (live && tt == 0) {
+          // class c: 0 = f1 min, 1 = f1 max, 2 = f2 min, 3 = f2 max; code byte = position or 0xFF
+          uint32_t code = 0;
+          code |= ((int)(K.mn1 >> 16) <= BIAS_F1 - g.tau) ? (K.mn1 & 0xFFu) : 0xFFu;
+          code |= (((int)(K.mx1 >> 16) >= BIAS_F1 + g.tau) ? ((K.mx1 & 0xFFu) ^ 0xFFu) : 0xFFu) << 8;
+          code |= (((int)(K.mn2 >> 16) <= BIAS_F2 - g.tau) ? (K.mn2 & 0xFFu) : 0xFFu) << 16;
+          code |= (((int)(K.mx2 >> 16) >= BIAS_F2 + g.tau) ? ((K.mx2 & 0xFFu) ^ 0xFFu) : 0xFFu) << 24;
+          s_code[cbase[p] + cell] = code;
         }
       }
     }
     __syncthreads();
 
-    // 3b: one thread per queued candidate.  Keep it iff nothing in its clamped (2n+1)^2 window is strictly better;
-    // positions inside the cell can never be strictly better than the cell extremum, so the reference's cell
-    // exclusion is implied.  Row-wise packed scan: two responses per 32-bit word, VIMNMX.U16x2 reduction, one exit
-    // test per row; maxima are handled as minima of the complemented values; lanes outside the window read as 0xFFFF.
-    const int nq = *s_qn;
-    for (int q = tid; q < nq; q += FILTER_THREADS) {
-      const uint32_t ent = s_queue[q];
-      const int p = ent >> 26, c = (ent >> 16) & 3, pos = (ent >> 18) & 255, gcell = ent & 0xFFFF;
-      const int cell = gcell - cbase[p];
-      const int n = g.n[p], step = n + 1, org = n + VISO_MARGIN;
-      const int kk = cell % nk[p], ll = cell / nk[p];
-      const int lx = org + (klo[p] + kk) * step - fxs, ly = org + (llo[p] + ll) * step - fy0;
-      const int16_t* sf = c < 2 ? sf1 : sf2;
-      const bool is_min = (c & 1) == 0;
-      const int ex = lx + (pos >> 4), ey = ly + (pos & 15);
-      const int val = sf[ey * FS + ex];
-      const int xs = ex - n, xe = min(ex + n, xhi), ye = min(ey + n, yhi);
-      const uint32_t flip = is_min ? 0u : 0xFFFFFFFFu;
-      const uint32_t target = is_min ? (uint32_t)val : (uint32_t)(0xFFFF - val);
-      const int w0 = xs >> 1, w1 = xe >> 1;
-      const uint32_t m0 = (xs & 1) ? 0x0000FFFFu : 0u, m1 = (xe & 1) ? 0u : 0xFFFF0000u;
-      bool keep = true;
-      for (int j2 = ey - n; j2 <= ye && keep; j2++) {
-        const uint32_t* row = (const uint32_t*)(sf + j2 * FS);
-        uint32_t acc = (row[w0] ^ flip) | m0;
-        if (w1 > w0) {
-#pragma unroll 4
-          for (int wq = w0 + 1; wq < w1; wq++) acc = __vminu2(acc, row[wq] ^ flip);
-          acc = __vminu2(acc, (row[w1] ^ flip) | m1);
-        } else {
-          acc |= m1;
-        }
-        if (min(acc & 0xFFFFu, acc >> 16) < target) keep = false;
-      }
-      if (keep) ((uint8_t*)s_code)[4 * gcell + c] = (uint8_t)pos;
+    // 3b: window tests, one loop per pass and kind
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      if (p < g.first_pass) continue;
+      const int n = g.n[p], n1 = n + 1, org = n + VISO_MARGIN;
+      const int ncell = nk[p] * nl[p];
+      if (ncell == 0) continue;
+      const int cx0 = org + klo[p] * n1 - X.f_lo, cy0 = org + llo[p] * n1 - Y.f_lo;
+      uint8_t* codes = (uint8_t*)(s_code + cbase[p]);
+      scan_dispatch<true>(sf1, sf2, FS, codes, ncell, nk[p], n, cx0, cy0, xhi, yhi, tid, T);
+      scan_dispatch<false>(sf1, sf2, FS, codes, ncell, nk[p], n, cx0, cy0, xhi, yhi, tid, T);
     }
     __syncthreads();
 
     // 3c: code words to global memory, cell-column-major
-    for (int idx = tid; idx < ncell_total; idx += FILTER_THREADS) {
-      const int p = (idx >= cbase[1] && nk[1] * nl[1] > 0) ? 1 : 0;
-      const int cell = idx - cbase[p];
-      const int kk = cell % nk[p], ll = cell / nk[p];
-      F.codes[p][(size_t)(klo[p] + kk) * g.ncy[p] + (llo[p] + ll)] = s_code[idx];
+    for (int idx = tid; idx < ncell_total; idx += T) {
+      const bool second = idx >= cbase[1] && nk[1] * nl[1] > 0;
+      const int cell = idx - (second ? cbase[1] : cbase[0]);
+      const int nkp = second ? nk[1] : nk[0];
+      const int kk = cell % nkp, ll = cell / nkp;
+      uint32_t* dst = second ? F.codes[1] : F.codes[0];
+      dst[(size_t)((second ? klo[1] : klo[0]) + kk) * (second ? g.ncy[1] : g.ncy[0]) + ((second ? llo[1] : llo[0]) + ll)] = s_code[idx];
     }
   }
 }
@@ -592,6 +754,116 @@ __global__ void k_gather_counts(const FrameDev* frames, SlotList sl, int32_t* ou
 
 }  // namespace
 
+// ----------------------------------------------------------------------------------------------------------
+// host side: tile configurations, tensor maps, launch
+namespace {
+
+// kx x ky aligning-pass cells per tile; returns false if the configuration does not fit (TMA box, shared memory)
+bool make_tile_cfg(const Geometry& g, int kx, int ky, int threads, TileCfg& t) {
+  memset(&t, 0, sizeof t);
+  const int pa = g.first_pass;                              // the aligning pass: sparse when multi_stage (n[0] >= n[1])
+  t.nA = g.n[pa]; t.stepA = t.nA + 1; t.orgA = t.nA + VISO_MARGIN;
+  t.extR = t.nA;
+  if (pa == 0 && 2 * g.n[1] > t.extR) t.extR = 2 * g.n[1];
+  t.kx = kx; t.ky = ky; t.TWn = kx * t.stepA; t.THn = ky * t.stepA;
+  t.ntx = g.ncx[pa] > 0 ? (g.ncx[pa] + kx - 1) / kx : (g.bplm - t.orgA + t.TWn - 1) / t.TWn;
+  t.nty = g.ncy[pa] > 0 ? (g.ncy[pa] + ky - 1) / ky : (g.hm - t.orgA + t.THn - 1) / t.THn;
+  if (t.ntx < 1) t.ntx = 1;
+  if (t.nty < 1) t.nty = 1;
+  int nwf = 1, is = 16, fh = 1, ih = 1, nwa_max = 1, nra_max = 1;
+  int cells_x[2] = {0, 0}, cells_y[2] = {0, 0};
+  for (int a = 0; a < t.ntx; a++) {
+    const TileRange X = tile_range(t, a, t.ntx, g.wm, g.bplm, true);
+    nwf = std::max(nwf, (X.f_hi - X.f_lo) / 4);
+    is = std::max(is, (int)align_up((size_t)(X.i_hi - X.i_lo), 16));
+    nwa_max = std::max(nwa_max, (X.d_hi - X.d_lo) / 4);
+    for (int p = g.first_pass; p < 2; p++) { int klo, nk; owned_cells(X, g.n[p], g.ncx[p], klo, nk); cells_x[p] = std::max(cells_x[p], nk); }
+  }
+  for (int b = 0; b < t.nty; b++) {
+    const TileRange Y = tile_range(t, b, t.nty, g.hm, g.hm, false);
+    fh = std::max(fh, Y.f_hi - Y.f_lo);
+    ih = std::max(ih, Y.i_hi - Y.i_lo);
+    nra_max = std::max(nra_max, Y.d_hi - Y.d_lo);
+    for (int p = g.first_pass; p < 2; p++) { int llo, nl; owned_cells(Y, g.n[p], g.ncy[p], llo, nl); cells_y[p] = std::max(cells_y[p], nl); }
+  }
+  t.NWf = nwf; t.FS = 4 * nwf; t.FH = fh; t.IS = is; t.IH = ih;
+  t.max_cells = cells_x[0] * cells_y[0] + cells_x[1] * cells_y[1];
+  t.threads = threads;
+  // rows per walker: as short as possible (more walkers) while one round of the threads covers a whole tile
+  t.seg = std::max(fh, nra_max);
+  for (int s = 8; s < std::max(fh, nra_max); s++)
+    if (nwa_max * ((nra_max + s - 1) / s) + nwf * ((fh + s - 1) / s) <= threads) { t.seg = s; break; }
+  t.img_bytes = (unsigned)align_up((size_t)t.IS * t.IH, 128);
+  t.f_bytes = (unsigned)align_up((size_t)2 * t.FH * t.FS * sizeof(int16_t) + 16, 16);
+  t.smem = t.img_bytes + t.f_bytes + 16 + (unsigned)t.max_cells * 4 + 16;
+  return t.IS <= 256 && t.IH <= 256 && t.smem <= 227 * 1024;
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// TMA descriptor of the matching-resolution image plane of every frame slot: a 3-D tensor (bytes per line, rows,
+// frame slots) with the tile's box; out-of-bounds elements are filled with zeros, which is what the filters expect
+// outside the image.
+int encode_tile_map(visocu_ctx* ctx, const TileCfg& t, CUtensorMap* out) {
+  const Geometry& g = ctx->g;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CU_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return visocu_set_error(ctx, VISOCU_ECUDA, "cuTensorMapEncodeTiled is not available");
+  const FrameDev& F0 = ctx->frames_h[0];
+  void* base = g.half ? (void*)F0.half : (void*)F0.img;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.bplm, (cuuint64_t)g.hm, (cuuint64_t)ctx->n_frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.bplm, (cuuint64_t)ctx->frame_stride};
+  const cuuint32_t box[3] = {(cuuint32_t)t.IS, (cuuint32_t)t.IH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ((EncodeFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return visocu_set_error(ctx, VISOCU_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return VISOCU_OK;
+}
+
+}  // namespace
+
+// Tile configurations of a context: up to VISO_TILE_LEVELS sizes, largest first.  Large tiles have the smallest halo
+// (best throughput when a launch has many frames), small tiles give a launch of a few frames enough CTAs to spread
+// over the GPU.  VISOCU_TILE="kx,ky,threads" pins one configuration (experiments).
+int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes) {
+  const Geometry& g = ctx->g;
+  ctx->frame_stride = frame_stride_bytes;
+  ctx->use_tma = 1;
+  if (const char* env = getenv("VISOCU_TMA")) if (env[0] == '0') ctx->use_tma = 0;    // debugging switch: stage the tile with plain loads
+  const int stepA = g.n[g.first_pass] + 1;
+  int cand[VISO_TILE_LEVELS][3] = {{210 / stepA, 60 / stepA, 512}, {100 / stepA, 60 / stepA, 512}, {100 / stepA, 30 / stepA, 256}};
+  int ncand = VISO_TILE_LEVELS;
+  if (const char* env = getenv("VISOCU_TILE")) {
+    int kx = 0, ky = 0, th = 0;
+    if (sscanf(env, "%d,%d,%d", &kx, &ky, &th) == 3 && kx > 0 && ky > 0 && th >= 32 && th <= MAX_FILTER_THREADS && th % 32 == 0) {
+      cand[0][0] = kx; cand[0][1] = ky; cand[0][2] = th; ncand = 1;
+    }
+  }
+  ctx->n_tiles = 0;
+  for (int c = 0; c < ncand; c++) {
+    int kx = std::max(cand[c][0], 1), ky = std::max(cand[c][1], 1);
+    TileCfg t;
+    bool ok = make_tile_cfg(g, kx, ky, cand[c][2], t);
+    while (!ok && (kx > 1 || ky > 1)) {                     // shrink until the box and the shared memory fit
+      if (kx >= ky && kx > 1) kx = (kx + 1) / 2; else ky = (ky + 1) / 2;
+      ok = make_tile_cfg(g, kx, ky, cand[c][2], t);
+    }
+    if (!ok) continue;
+    visocu_tile& slot = ctx->tiles[ctx->n_tiles];
+    static_assert(sizeof(TileCfg) <= sizeof(slot.cfg), "TileCfg storage");
+    memcpy(slot.cfg, &t, sizeof t);
+    if (ctx->use_tma) { int rc = encode_tile_map(ctx, t, &slot.tmap); if (rc) return rc; }
+    ctx->n_tiles++;
+  }
+  if (ctx->n_tiles == 0) return visocu_set_error(ctx, VISOCU_EINVAL, "no tile configuration fits %dx%d with nms_n = %d", g.wm, g.hm, g.n[1]);
+  return VISOCU_OK;
+}
+
 int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
   const Geometry& g = ctx->g;
   cudaStream_t st = ctx->stream;
@@ -599,17 +871,18 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
     dim3 bh(32, 8), gh((g.bplm / 4 + 31) / 32, (g.hm + 7) / 8, sl.n);
     k_half_image<<<gh, bh, 0, st>>>(g, ctx->frames_d, sl);
     CU_LAUNCH_CHECK(ctx);
-    dim3 gs((g.bpl + 255) / 256, (g.h + 31) / 32, sl.n);
+    dim3 gs((g.bpl + SF_TW - 1) / SF_TW, (g.h + SF_TH - 1) / SF_TH, sl.n);
     k_sobel_full<<<gs, 256, 0, st>>>(g, ctx->frames_d, sl);
     CU_LAUNCH_CHECK(ctx);
   }
-  const int nmax = g.first_pass == 0 ? (g.n[0] > g.n[1] ? g.n[0] : g.n[1]) : g.n[1];
   {
-    const TileShape ts = tile_shape(nmax);
-    // owned NMS cells of one tile (both passes): code words + a queue of up to four candidates per cell
-    int max_cells = 0;
-    for (int p = g.first_pass; p < 2; p++) max_cells += ((TW + g.n[p]) / (g.n[p] + 1) + 1) * ((TH + g.n[p]) / (g.n[p] + 1) + 1);
-    const size_t smem_bytes = ts.smem + (size_t)max_cells * 20;
+    // the largest tiles that still give the launch about one CTA per SM; else the smallest
+    int pick = ctx->n_tiles - 1;
+    for (int c = 0; c < ctx->n_tiles; c++) {
+      TileCfg t; memcpy(&t, ctx->tiles[c].cfg, sizeof t);
+      if ((long long)t.ntx * t.nty * sl.n >= ctx->sm_count) { pick = c; break; }
+    }
+    TileCfg t; memcpy(&t, ctx->tiles[pick].cfg, sizeof t);
     // opt in to large dynamic shared memory once per device (the attribute belongs to the function on a device, not
     // to a context: several contexts with different tile shapes share it)
     {
@@ -621,10 +894,9 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
         done[ctx->device & 63] = true;
       }
     }
-    if (smem_bytes > 227 * 1024) return visocu_set_error(ctx, VISOCU_EINVAL, "tile needs %zu bytes of shared memory", smem_bytes);
-    dim3 grid((g.bplm + TW - 1) / TW, (g.hm + TH - 1) / TH, sl.n);
+    dim3 grid(t.ntx, t.nty, sl.n);
     if (ctx->profile) CU_TRY(ctx, cudaEventRecord(ctx->pev0, st));
-    k_filter_nms<<<grid, FILTER_THREADS, smem_bytes, st>>>(g, ctx->frames_d, sl, nmax, ctx->tmap_img, ctx->use_tma, max_cells);
+    k_filter_nms<<<grid, t.threads, t.smem, st>>>(g, ctx->frames_d, sl, t, ctx->tiles[pick].tmap, ctx->use_tma);
     CU_LAUNCH_CHECK(ctx);
     if (ctx->profile) {
       // profiling mode only: this synchronises the stream after every fused launch
@@ -652,37 +924,5 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
     k_gather_counts<<<1, VISO_MAX_BATCH, 0, st>>>(ctx->frames_d, sl, ctx->counts_stage);
     CU_LAUNCH_CHECK(ctx);
   }
-  return VISOCU_OK;
-}
-
-// TMA descriptor of the matching-resolution image plane of every frame slot: a 3-D tensor (bytes per line, rows,
-// frame slots) with the tile box of tile_shape(nmax); out-of-bounds elements are filled with zeros, which is what
-// the filters expect outside the image.
-int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes) {
-  const Geometry& g = ctx->g;
-  const int nmax = g.first_pass == 0 ? (g.n[0] > g.n[1] ? g.n[0] : g.n[1]) : g.n[1];
-  const TileShape ts = tile_shape(nmax);
-  ctx->use_tma = 0;
-  const char* env = getenv("VISOCU_TMA");
-  if (env && env[0] == '0') return VISOCU_OK;             // debugging switch: stage the tile with plain loads
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  CU_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  if (!fn || qres != cudaDriverEntryPointSuccess) return visocu_set_error(ctx, VISOCU_ECUDA, "cuTensorMapEncodeTiled is not available");
-  const FrameDev& F0 = ctx->frames_h[0];
-  void* base = g.half ? (void*)F0.half : (void*)F0.img;
-  const cuuint64_t dims[3] = {(cuuint64_t)g.bplm, (cuuint64_t)g.hm, (cuuint64_t)ctx->n_frames};
-  const cuuint64_t strides[2] = {(cuuint64_t)g.bplm, (cuuint64_t)frame_stride_bytes};
-  const cuuint32_t box[3] = {(cuuint32_t)ts.IS, (cuuint32_t)ts.IH, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  if (ts.IS > 256 || ts.IH > 256) return visocu_set_error(ctx, VISOCU_EINVAL, "tile box %dx%d exceeds the TMA limit", ts.IS, ts.IH);
-  CUresult r = ((EncodeFn)fn)(&ctx->tmap_img, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return visocu_set_error(ctx, VISOCU_ECUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  ctx->use_tma = 1;
   return VISOCU_OK;
 }

@@ -35,6 +35,10 @@ struct Geometry {
 
 struct SlotList { int n; int s[VISO_MAX_BATCH]; };
 
+#define VISO_TILE_LEVELS 3
+// one tile configuration of the fused filter+NMS kernel (csrc/features.cu: TileCfg) and its TMA descriptor
+struct visocu_tile { alignas(64) CUtensorMap tmap; alignas(8) unsigned char cfg[128]; };
+
 // state of a matching call whose outlier removal runs on the second stream (visocu_match_deferred / _collect)
 struct visocu_deferred {
   bool pending = false;
@@ -77,10 +81,11 @@ struct visocu_ctx {
   int32_t* counts_stage = nullptr;   // device: 4 int32 per frame of the last feature launch (one read-back per push)
   uint8_t* img_stage = nullptr; size_t img_stage_bytes = 0;   // contiguous landing area for host images
   uint64_t launches = 0;
-  CUtensorMap tmap_img;              // TMA descriptor of the matching-resolution image planes of the pool
+  visocu_tile tiles[VISO_TILE_LEVELS];   // tile configurations, largest first (visocu_make_tensor_map)
+  int n_tiles = 0;
+  size_t frame_stride = 0;           // bytes between the pool blocks of consecutive frame slots
   int use_tma = 0;
   int pinv_ready = 0;                // paraboloid pseudo-inverse uploaded to constant memory (sub-pixel refinement)
-  size_t filter_smem_attr = 0;       // dynamic shared memory opted in for the fused kernel on this device
   uint64_t h2d_bytes = 0, d2h_bytes = 0;   // host<->device traffic issued by this context
   int profile = 0;                   // time the fused filter+NMS launches with events (visocu_profile)
   cudaEvent_t pev0 = nullptr, pev1 = nullptr;
