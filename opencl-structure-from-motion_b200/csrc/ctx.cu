@@ -137,6 +137,7 @@ static void free_pool(visocu_ctx* ctx) {
   if (ctx->pool) cudaFree(ctx->pool);
   if (ctx->frames_d) cudaFree(ctx->frames_d);
   ctx->pool = nullptr; ctx->frames_d = nullptr; ctx->configured = false;
+  visocu_free_tiles(ctx);
 }
 
 extern "C" void visocu_destroy(visocu_ctx* ctx) {

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace {
 
@@ -180,28 +181,35 @@ __global__ void __launch_bounds__(256) k_sobel_full(Geometry g, const FrameDev* 
 // sparse pass when multi_stage): a tile owns kx x ky of its cells, which lie completely inside the tile, so the response
 // planes need a halo of only n samples to the left / top and max(n, 2 n_other) to the right / bottom.  Cells of the
 // other pass belong to the tile that contains their origin.  du / dv are written for the 4-aligned pixel range of the
-// tile; first and last tiles extend to the image borders.
+// tile; first and last tiles extend to the image borders.  Everything that depends on the tile index along one axis is
+// computed once on the host (AxisTile tables in device memory): the kernel does no division to find its ranges.
 struct TileCfg {
   int nA, stepA, orgA;     // the aligning pass: n, n + 1, n + margin
   int extR;                // response halo to the right / bottom of the tile's cell range
   int kx, ky, ntx, nty, TWn, THn;
   int NWf, FS, FH;         // response planes in shared memory: words (4 samples) per row, samples per row, rows
   int IS, IH;              // image tile: bytes per row (multiple of 16), rows
-  int seg;                 // rows per filter walker
   int max_cells;           // owned cells of one tile, both passes
   int threads;
   unsigned img_bytes, f_bytes, smem;
+  const struct AxisTile* xt;   // ntx entries
+  const struct AxisTile* yt;   // nty entries
 };
 
-struct TileRange {         // one axis of one tile
+struct AxisTile {          // one axis of one tile
   int own_lo, own_hi;      // cells with origin in [own_lo, own_hi) belong to the tile
-  int f_lo, f_hi;          // response samples held in shared memory: [f_lo, f_hi), f_lo 4-aligned along x
+  int f_lo, f_hi;          // response samples computed into shared memory: [f_lo, f_hi), f_lo 4-aligned along x
+  int v_hi, fill_hi;       // samples in [v_hi, fill_hi) lie beyond the last valid one (len - margin - 1): set to the neutral value
   int d_lo, d_hi;          // du / dv samples written
   int i_lo, i_hi;          // image samples needed (along x: i_lo 16-byte aligned)
+  int klo[2], nk[2];       // owned cells of the two passes along this axis
+  float inv_nk[2];         // 1 / nk (x axis: cell index -> column, row)
+  int nwa, nwb;            // x axis: word columns of the Sobel / response range
+  float inv_nwa, inv_nwb;
+  int segA, segB, nsA, nsB;   // y axis: rows per Sobel / response walker and number of row segments
 };
 
-__host__ __device__ inline TileRange tile_range(const TileCfg& t, int idx, int ntiles, int len, int len_pad, bool xaxis) {
-  TileRange r;
+__host__ __device__ inline void tile_range(const TileCfg& t, int idx, int ntiles, int len, int len_pad, bool xaxis, AxisTile& r) {
   const int TN = xaxis ? t.TWn : t.THn;
   const int n0 = t.orgA + TN * idx;
   const bool first = idx == 0, last = idx == ntiles - 1;
@@ -217,22 +225,31 @@ __host__ __device__ inline TileRange tile_range(const TileCfg& t, int idx, int n
   if (f_hi < f_lo) f_hi = f_lo;
   if (xaxis) f_hi = f_lo + ((f_hi - f_lo + 3) & ~3);
   r.f_lo = f_lo; r.f_hi = f_hi; r.d_lo = d_lo; r.d_hi = d_hi;
+  // Windows are clamped at len - 1 - margin (matcher.cpp:383-384).  Instead of clamping, the samples behind that line are
+  // given the response 0, which is never strictly better than a candidate (|candidate| >= tau >= 1): the scans need no
+  // border case.  They read up to n + 1 samples past the last valid one.
+  r.v_hi = f_hi; r.fill_hi = f_hi;
+  if (f_hi >= len - VISO_MARGIN && f_hi > f_lo) { r.v_hi = len - VISO_MARGIN; r.fill_hi = len - VISO_MARGIN + t.nA + 1; if (r.fill_hi < f_hi) r.fill_hi = f_hi; }
+  if (xaxis) r.fill_hi = f_lo + ((r.fill_hi - f_lo + 3) & ~3);
   int lo = d_lo < f_lo ? d_lo : f_lo, hi = d_hi > f_hi ? d_hi : f_hi;
   if (d_hi <= d_lo) { lo = f_lo; hi = f_hi; }
   if (f_hi <= f_lo) { lo = d_lo; hi = d_hi; }
   if (xaxis) { r.i_lo = (lo - 4) & ~15; r.i_hi = hi + 4; }
   else { r.i_lo = lo - 2; r.i_hi = hi + 2; }
-  return r;
 }
 
 // owned cell range of pass p along one axis: cells k with origin org + k * step in [own_lo, own_hi), k < ncells
-__host__ __device__ inline void owned_cells(const TileRange& r, int n, int ncells, int& klo, int& nk) {
+inline void owned_cells(const AxisTile& r, int n, int ncells, int& klo, int& nk) {
   const int step = n + 1, org = n + VISO_MARGIN;
   int a = r.own_lo - org; klo = a > 0 ? (a + step - 1) / step : 0;
   int khi = ncells;
   if (r.own_hi < 0x3FFFFFFF) { int b = r.own_hi - org; khi = b > 0 ? (b + step - 1) / step : 0; if (khi > ncells) khi = ncells; }
   nk = khi > klo ? khi - klo : 0;
 }
+
+// q = a / d for 0 <= a < 2^20 with inv = 1.0f / d: (a + 0.5) / d is at least 0.5 / d away from an integer, far more than
+// the rounding error of the float product
+__device__ __forceinline__ int fast_div(int a, float inv) { return __float2int_rz(((float)a + 0.5f) * inv); }
 
 __device__ __forceinline__ bool mbar_wait_or_trap(uint32_t bar, uint32_t phase) {
   const long long t0 = clock64();
@@ -249,31 +266,41 @@ __device__ __forceinline__ bool mbar_wait_or_trap(uint32_t bar, uint32_t phase) 
 // complement for the maximum, so that "first extreme in column-major order" (matcher.cpp:356-379) falls out of min / max.
 // A row of the cell is read as 32-bit words (two samples each); the key of the low sample is w * 65536 + pos (an IMAD on
 // the FMA pipe), the key of the high sample (w & 0xFFFF0000) | pos (a LOP3 on the ALU pipe).
-struct Keys4 { uint32_t mn1, mx1, mn2, mx2; };
+struct Keys4 { uint32_t k[4]; };      // 0 = f1 min, 1 = f1 max, 2 = f2 min, 3 = f2 max
 
-template <int N1, bool ODD>
+template <int N1, bool ODD, int ROWS>
 __device__ __forceinline__ void cell_keys_rows(const uint32_t* r1, const uint32_t* r2, int FSW, int nrows, Keys4& K) {
   // r1 / r2: word holding sample i0 (ODD: in its high half) of the first row, planes f1 / f2; positions are relative
-  // to this row (dy = 0 .. nrows - 1)
+  // to this row (dy = 0 .. nrows - 1).  Words are fetched in pairs (64-bit loads) when the first word is 8-byte aligned.
   constexpr int NW = (N1 + (ODD ? 1 : 0) + 1) / 2;
+  constexpr int NWP = (NW + 1) & ~1;
+  const bool aligned = (((uintptr_t)r1) & 7) == 0;
 #pragma unroll
-  for (int rr = 0; rr < (N1 + 1) / 2 + (N1 > 5 ? 0 : N1 / 2); rr++) {      // at most N1 rows (dense) or ceil(N1 / 2) (sparse halves)
+  for (int rr = 0; rr < ROWS; rr++) {
     if (rr < nrows) {
-      uint32_t a[NW], b[NW];
+      uint32_t a[NWP], b[NWP];
+      if (aligned) {
 #pragma unroll
-      for (int j = 0; j < NW; j++) { a[j] = r1[rr * FSW + j]; b[j] = r2[rr * FSW + j]; }
+        for (int j = 0; j < NWP; j += 2) {
+          const uint2 va = *(const uint2*)(r1 + rr * FSW + j), vb = *(const uint2*)(r2 + rr * FSW + j);
+          a[j] = va.x; a[j + 1] = va.y; b[j] = vb.x; b[j + 1] = vb.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NW; j++) { a[j] = r1[rr * FSW + j]; b[j] = r2[rr * FSW + j]; }
+      }
 #pragma unroll
       for (int j = 0; j < NW; j++) {
         const int dx_lo = 2 * j - (ODD ? 1 : 0), dx_hi = dx_lo + 1;
         if (dx_lo >= 0 && dx_lo < N1) {
           const uint32_t p = (uint32_t)((dx_lo << 4) | rr);
-          K.mn1 = min(K.mn1, a[j] * 65536u + p); K.mx1 = max(K.mx1, a[j] * 65536u + (p ^ 0xFFu));
-          K.mn2 = min(K.mn2, b[j] * 65536u + p); K.mx2 = max(K.mx2, b[j] * 65536u + (p ^ 0xFFu));
+          K.k[0] = min(K.k[0], a[j] * 65536u + p); K.k[1] = max(K.k[1], a[j] * 65536u + (p ^ 0xFFu));
+          K.k[2] = min(K.k[2], b[j] * 65536u + p); K.k[3] = max(K.k[3], b[j] * 65536u + (p ^ 0xFFu));
         }
         if (dx_hi >= 0 && dx_hi < N1) {
           const uint32_t p = (uint32_t)((dx_hi << 4) | rr);
-          K.mn1 = min(K.mn1, (a[j] & 0xFFFF0000u) | p); K.mx1 = max(K.mx1, (a[j] & 0xFFFF0000u) | (p ^ 0xFFu));
-          K.mn2 = min(K.mn2, (b[j] & 0xFFFF0000u) | p); K.mx2 = max(K.mx2, (b[j] & 0xFFFF0000u) | (p ^ 0xFFu));
+          K.k[0] = min(K.k[0], (a[j] & 0xFFFF0000u) | p); K.k[1] = max(K.k[1], (a[j] & 0xFFFF0000u) | (p ^ 0xFFu));
+          K.k[2] = min(K.k[2], (b[j] & 0xFFFF0000u) | p); K.k[3] = max(K.k[3], (b[j] & 0xFFFF0000u) | (p ^ 0xFFu));
         }
       }
     }
@@ -281,139 +308,193 @@ __device__ __forceinline__ void cell_keys_rows(const uint32_t* r1, const uint32_
 }
 
 // any cell size: one 16-bit load per sample
-__device__ __forceinline__ void cell_keys_generic(const int16_t* q1, const int16_t* q2, int FS, int n1, int row_lo, int row_hi, Keys4& K) {
-  for (int dj = row_lo; dj < row_hi; dj++)
+__device__ __forceinline__ void cell_keys_generic(const int16_t* q1, const int16_t* q2, int FS, int n1, int nrows, Keys4& K) {
+  for (int dj = 0; dj < nrows; dj++)
     for (int di = 0; di < n1; di++) {
-      const uint32_t p = (uint32_t)((di << 4) | (dj - row_lo));
+      const uint32_t p = (uint32_t)((di << 4) | dj);
       const uint32_t v1 = (uint32_t)(uint16_t)q1[dj * FS + di] << 16, v2 = (uint32_t)(uint16_t)q2[dj * FS + di] << 16;
-      K.mn1 = min(K.mn1, v1 | p); K.mx1 = max(K.mx1, v1 | (p ^ 0xFFu));
-      K.mn2 = min(K.mn2, v2 | p); K.mx2 = max(K.mx2, v2 | (p ^ 0xFFu));
+      K.k[0] = min(K.k[0], v1 | p); K.k[1] = max(K.k[1], v1 | (p ^ 0xFFu));
+      K.k[2] = min(K.k[2], v2 | p); K.k[3] = max(K.k[3], v2 | (p ^ 0xFFu));
     }
 }
 
-// keys of rows [row_lo, row_hi) of the cell whose first sample is (i0, j0) in the response planes; positions come back
-// relative to row_lo and are shifted to the cell by the caller
-__device__ __forceinline__ void cell_keys(const int16_t* sf1, const int16_t* sf2, int FS, int n1, int i0, int j0, int row_lo, int row_hi, Keys4& K) {
-  const int FSW = FS >> 1;
-  const uint32_t* r1 = (const uint32_t*)(sf1 + (j0 + row_lo) * FS) + (i0 >> 1);
-  const uint32_t* r2 = (const uint32_t*)(sf2 + (j0 + row_lo) * FS) + (i0 >> 1);
-  const int nrows = row_hi - row_lo;
-  const bool odd = i0 & 1;
-  switch (n1) {
-    case 3: if (odd) cell_keys_rows<3, true>(r1, r2, FSW, nrows, K); else cell_keys_rows<3, false>(r1, r2, FSW, nrows, K); break;
-    case 4: if (odd) cell_keys_rows<4, true>(r1, r2, FSW, nrows, K); else cell_keys_rows<4, false>(r1, r2, FSW, nrows, K); break;
-    case 7: if (odd) cell_keys_rows<7, true>(r1, r2, FSW, nrows, K); else cell_keys_rows<7, false>(r1, r2, FSW, nrows, K); break;
-    case 10: if (odd) cell_keys_rows<10, true>(r1, r2, FSW, nrows, K); else cell_keys_rows<10, false>(r1, r2, FSW, nrows, K); break;
-    default: cell_keys_generic(sf1 + j0 * FS + i0, sf2 + j0 * FS + i0, FS, n1, row_lo, row_hi, K); break;
-  }
-}
-
-// ---- phase 3b: window test of the candidates of one pass and one kind (minima or maxima).
-// A candidate survives iff nothing in its clamped (2n+1)^2 window is strictly better (matcher.cpp:383-427); positions
-// inside the cell can never be strictly better than the cell extreme, so the reference's cell exclusion is implied.
-// Every lane walks through its own candidates (slots tid, tid + T, ...); one loop iteration scans the two rows at
-// distance r above and below the extreme, r = 0 .. n (most rejections happen next to the extreme), and a lane that is
-// done with a candidate fetches its next one while its neighbours keep scanning: no lane waits for another's window.
-// Rows are read as n+1 32-bit words (two samples each); of the 2n+2 samples exactly one lies outside the window (the
-// low half of the first word or the high half of the last) and is neutralised by a mask.
+// ---- window test (matcher.cpp:383-427): a candidate survives iff nothing in its clamped (2n+1)^2 window is strictly
+// better; positions inside the cell can never be strictly better than the cell extreme, so the reference's cell
+// exclusion is implied.  A window row is read as n+1 32-bit words (two samples each); of the 2n+2 samples exactly one
+// lies outside the window (the low half of the first word or the high half of the last) and is neutralised by a mask.
+// Rows are combined with packed 16-bit min3 / max3 (VIMNMX3.U16x2) before the masks are applied.
 template <int N1, bool IS_MIN>
-__device__ __forceinline__ void scan_candidates(const int16_t* sf1, const int16_t* sf2, int FS, uint8_t* codes, int ncell, int nk,
-                                                int n, int cx0, int cy0, int xhi, int yhi, int tid, int T) {
-  // cx0 / cy0: response-plane coordinates of the first owned cell's origin; slot = 2 * cell + plane
-  const int FSW = FS >> 1;
-  const int nslots = 2 * ncell;
-  const int step = n + 1;
-  int s = tid;
-  bool active = false;
-  const uint32_t* rowc = nullptr;    // word of the first window column in the extreme's row
-  uint32_t target2 = 0, m_first = 0, m_last = 0;
-  int r = 0, rdn = 0;
-  uint8_t* code = nullptr;
-  const int nw_rt = N1 > 0 ? N1 : n + 1;
-  for (;;) {
-    if (!active) {
-      int pos = 0xFF, cell = 0, plane = 0;
-      for (; s < nslots; s += T) {
-        cell = s >> 1; plane = s & 1;
-        pos = codes[4 * cell + 2 * plane + (IS_MIN ? 0 : 1)];
-        if (pos != 0xFF) break;
-      }
-      if (s >= nslots) break;
-      s += T;
-      const int kk = cell % nk, ll = cell / nk;
-      const int ex = cx0 + kk * step + (pos >> 4), ey = cy0 + ll * step + (pos & 15);
-      const int16_t* sf = plane ? sf2 : sf1;
-      code = codes + 4 * cell + 2 * plane + (IS_MIN ? 0 : 1);
-      const uint32_t val = (uint16_t)sf[ey * FS + ex];
-      const int xs = ex - n;
-      if (ex + n > xhi) {
-        // window clamped at the right image border (last cell columns only): plain scan
-        const int xe = xhi, ye = min(ey + n, yhi);
-        bool keep = true;
-        for (int j2 = ey - n; j2 <= ye && keep; j2++)
-          for (int i2 = xs; i2 <= xe; i2++) {
-            const uint32_t v = (uint16_t)sf[j2 * FS + i2];
-            if (IS_MIN ? v < val : v > val) { keep = false; break; }
-          }
-        if (!keep) *code = 0xFF;
-        continue;
-      }
-      target2 = val | (val << 16);
-      rowc = (const uint32_t*)(sf + ey * FS) + (xs >> 1);
-      // neutral element of the reduction: 0xFFFF for minima (OR mask), 0 for maxima (AND mask)
-      m_first = (xs & 1) ? 0x0000FFFFu : 0u;
-      m_last = (xs & 1) ? 0u : 0xFFFF0000u;
-      rdn = min(n, yhi - ey);
-      r = 0;
-      active = true;
+__device__ __forceinline__ bool rows_better(const uint32_t* r0, const uint32_t* r1, const uint32_t* r2, int nw, uint32_t m_first, uint32_t m_last, uint32_t target2) {
+  uint32_t acc;
+  if (N1 > 0) {
+    uint32_t x[N1 > 0 ? N1 : 1];
+#pragma unroll
+    for (int j = 0; j < N1; j++) x[j] = IS_MIN ? __vimin3_u16x2(r0[j], r1[j], r2[j]) : __vimax3_u16x2(r0[j], r1[j], r2[j]);
+    if (IS_MIN) { x[0] |= m_first; x[N1 - 1] |= m_last; } else { x[0] &= ~m_first; x[N1 - 1] &= ~m_last; }
+    acc = x[0];
+#pragma unroll
+    for (int j = 1; j + 1 < N1; j += 2) acc = IS_MIN ? __vimin3_u16x2(acc, x[j], x[j + 1]) : __vimax3_u16x2(acc, x[j], x[j + 1]);
+    if ((N1 & 1) == 0) acc = IS_MIN ? __vminu2(acc, x[N1 - 1]) : __vmaxu2(acc, x[N1 - 1]);
+  } else {
+    acc = IS_MIN ? 0xFFFFFFFFu : 0u;
+    for (int j = 0; j < nw; j++) {
+      uint32_t x = IS_MIN ? __vimin3_u16x2(r0[j], r1[j], r2[j]) : __vimax3_u16x2(r0[j], r1[j], r2[j]);
+      if (j == 0) x = IS_MIN ? (x | m_first) : (x & ~m_first);
+      if (j == nw - 1) x = IS_MIN ? (x | m_last) : (x & ~m_last);
+      acc = IS_MIN ? __vminu2(acc, x) : __vmaxu2(acc, x);
     }
-    // rows ey - r (always inside the valid region) and ey + r (if not clamped away)
-    uint32_t acc;
-    {
-      const uint32_t* up = rowc - r * FSW;
-      const uint32_t* dn = rowc + (r <= rdn ? r : -r) * FSW;       // clamped away: read the upper row twice
+  }
+  return (IS_MIN ? __vminu2(acc, target2) : __vmaxu2(acc, target2)) != target2;
+}
+
+// windows clamped at the right or bottom image border (last cell columns / rows only): plain scan
+__device__ __noinline__ bool slow_keep(const int16_t* sf, int FS, int ex, int ey, int n, int xhi, int yhi, uint32_t val, bool is_min) {
+  const int xe = min(ex + n, xhi), ye = min(ey + n, yhi);
+  for (int j2 = ey - n; j2 <= ye; j2++)
+    for (int i2 = ex - n; i2 <= xe; i2++) {
+      const uint32_t v = (uint16_t)sf[j2 * FS + i2];
+      if (is_min ? v < val : v > val) return false;
+    }
+  return true;
+}
+
+struct NmsArgs {
+  const int16_t* sf1; const int16_t* sf2;   // response planes (sf2 = sf1 + FH * FS)
+  int FS;
+  uint32_t* codes;         // one word per owned cell of this pass
+  uint32_t* queue[2];      // candidates that passed the quick test: [0] minima, [1] maxima
+  int* qn;                 // their counters (two ints)
+  int n, ncell, nk; float inv_nk;
+  int cx0, cy0;            // plane coordinates of the first owned cell's origin
+  int xhi, yhi, tau;
+};
+
+// Cell extremes, tau test and quick window test (the three rows around the extreme, where most candidates die) of all
+// owned cells of one pass.  G lanes per cell: one for small cells; two for cells of six or more rows, the upper rows on
+// the even lane and the lower rows on the odd one, f1 classes tested by the even lane and f2 classes by the odd one.
+// Survivors of the quick test are queued (warp-aggregated) for phase 3b.
+template <int N1>
+__device__ __forceinline__ void nms_cells(const NmsArgs& A, int tid, int T) {
+  const int n = A.n, n1 = n + 1, FS = A.FS, FSW = FS >> 1;
+  const bool two = n1 >= 6;
+  const int G = two ? 2 : 1;
+  const int half_rows = (n1 + 1) >> 1;
+  constexpr int ROWS = N1 >= 6 ? (N1 + 1) / 2 : N1;
+  const int nitem = (A.ncell * G + 31) & ~31;                      // whole warps take part in the shuffles and ballots
+  const unsigned lane = tid & 31, lt = (1u << lane) - 1u;
+  const uint32_t* sfw = (const uint32_t*)A.sf1;
+  for (int item = tid; item < nitem; item += T) {
+    const int cell = two ? item >> 1 : item, tt = two ? item & 1 : 0;
+    const bool live = cell < A.ncell;
+    const int ll = live ? fast_div(cell, A.inv_nk) : 0, kk = live ? cell - ll * A.nk : 0;
+    const int i0 = A.cx0 + kk * n1, j0 = A.cy0 + ll * n1;
+    Keys4 K = {{0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u}};
+    const int row_lo = two ? tt * half_rows : 0, nrows = two ? (tt ? n1 - half_rows : half_rows) : n1;
+    if (live) {
+      const uint32_t* r1 = (const uint32_t*)(A.sf1 + (j0 + row_lo) * FS) + (i0 >> 1);
+      const uint32_t* r2 = (const uint32_t*)(A.sf2 + (j0 + row_lo) * FS) + (i0 >> 1);
       if (N1 > 0) {
-        uint32_t a[N1 > 0 ? N1 : 1], b[N1 > 0 ? N1 : 1];
-#pragma unroll
-        for (int j = 0; j < N1; j++) { a[j] = up[j]; b[j] = dn[j]; }
-        if (IS_MIN) {
-          a[0] |= m_first; b[0] |= m_first; a[N1 - 1] |= m_last; b[N1 - 1] |= m_last;
-          acc = __vminu2(a[0], b[0]);
-#pragma unroll
-          for (int j = 1; j < N1; j++) acc = __vimin3_u16x2(acc, a[j], b[j]);
-        } else {
-          a[0] &= ~m_first; b[0] &= ~m_first; a[N1 - 1] &= ~m_last; b[N1 - 1] &= ~m_last;
-          acc = __vmaxu2(a[0], b[0]);
-#pragma unroll
-          for (int j = 1; j < N1; j++) acc = __vimax3_u16x2(acc, a[j], b[j]);
-        }
+        constexpr int NC = N1 > 0 ? N1 : 1;
+        if (i0 & 1) cell_keys_rows<NC, true, ROWS>(r1, r2, FSW, nrows, K);
+        else cell_keys_rows<NC, false, ROWS>(r1, r2, FSW, nrows, K);
       } else {
-        if (IS_MIN) {
-          acc = __vminu2(up[0] | m_first, dn[0] | m_first);
-          for (int j = 1; j < nw_rt - 1; j++) acc = __vimin3_u16x2(acc, up[j], dn[j]);
-          acc = __vimin3_u16x2(acc, up[nw_rt - 1] | m_last | (nw_rt == 1 ? m_first : 0u), dn[nw_rt - 1] | m_last | (nw_rt == 1 ? m_first : 0u));
-        } else {
-          acc = __vmaxu2(up[0] & ~m_first, dn[0] & ~m_first);
-          for (int j = 1; j < nw_rt - 1; j++) acc = __vimax3_u16x2(acc, up[j], dn[j]);
-          acc = __vimax3_u16x2(acc, up[nw_rt - 1] & ~m_last & (nw_rt == 1 ? ~m_first : ~0u), dn[nw_rt - 1] & ~m_last & (nw_rt == 1 ? ~m_first : ~0u));
-        }
+        cell_keys_generic(A.sf1 + (j0 + row_lo) * FS + i0, A.sf2 + (j0 + row_lo) * FS + i0, FS, n1, nrows, K);
       }
+      // positions are relative to row_lo: shift them to the cell (dy is the low nibble; complemented for maxima)
+      K.k[0] += row_lo; K.k[2] += row_lo; K.k[1] -= row_lo; K.k[3] -= row_lo;
     }
-    const bool better = (IS_MIN ? __vminu2(acc, target2) : __vmaxu2(acc, target2)) != target2;
-    if (better) { *code = 0xFF; active = false; }
-    else if (++r > n) active = false;
+    if (two) {
+      K.k[0] = min(K.k[0], __shfl_xor_sync(0xFFFFFFFFu, K.k[0], 1)); K.k[1] = max(K.k[1], __shfl_xor_sync(0xFFFFFFFFu, K.k[1], 1));
+      K.k[2] = min(K.k[2], __shfl_xor_sync(0xFFFFFFFFu, K.k[2], 1)); K.k[3] = max(K.k[3], __shfl_xor_sync(0xFFFFFFFFu, K.k[3], 1));
+    }
+    // a single lane tests the four classes one after the other; a lane pair tests two classes each (the even lane
+    // those of f1, the odd lane those of f2), minima in the first round and maxima in the second
+    uint32_t code = 0xFFFFFFFFu;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (!(two && u >= 2)) {
+        const bool is_min = (u & 1) == 0;
+        const int plane = two ? tt : u >> 1;
+        const int c = two ? 2 * tt + u : u;
+        const uint32_t key = two ? (tt ? K.k[2 + (u & 1)] : K.k[u & 1]) : K.k[u];
+        const uint32_t val = key >> 16, pos = is_min ? (key & 0xFFu) : ((key & 0xFFu) ^ 0xFFu);
+        const int bias = plane ? BIAS_F2 : BIAS_F1;
+        bool cand = live && (is_min ? (int)val <= bias - A.tau : (int)val >= bias + A.tau);
+        bool push = false;
+        uint32_t ent = 0;
+        if (cand) {
+          const int ex = i0 + (int)(pos >> 4), ey = j0 + (int)(pos & 15), xs = ex - n;
+          const int16_t* sf = plane ? A.sf2 : A.sf1;
+          if (A.tau < 1 && (ex + n > A.xhi || ey + n > A.yhi)) {
+            cand = slow_keep(sf, FS, ex, ey, n, A.xhi, A.yhi, val, is_min);    // the neutral border needs tau >= 1
+          } else {
+            const uint32_t* mid = (const uint32_t*)(sf + ey * FS) + (xs >> 1);
+            const uint32_t m_first = (xs & 1) ? 0x0000FFFFu : 0u, m_last = (xs & 1) ? 0u : 0xFFFF0000u;
+            const uint32_t target2 = val | (val << 16);
+            const bool better = is_min ? rows_better<N1, true>(mid - FSW, mid, mid + FSW, n1, m_first, m_last, target2)
+                                       : rows_better<N1, false>(mid - FSW, mid, mid + FSW, n1, m_first, m_last, target2);
+            if (better) cand = false;
+            else if (n > 1) { push = true; ent = (uint32_t)(mid - sfw) | ((uint32_t)(xs & 1) << 16) | ((uint32_t)(4 * cell + c) << 17); }
+          }
+        }
+        if (cand) code = (code & ~(0xFFu << (8 * c))) | (pos << (8 * c));
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, push);
+        if (m) {
+          int base = 0;
+          const int leader = __ffs(m) - 1;
+          if ((int)lane == leader) base = atomicAdd(A.qn + (u & 1), __popc(m));
+          base = __shfl_sync(0xFFFFFFFFu, base, leader);
+          if (push) A.queue[u & 1][base + __popc(m & lt)] = ent;
+        }
+          }
+    }
+    if (live) {
+      if (!two) A.codes[cell] = code;
+      else ((uint16_t*)(A.codes + cell))[tt] = (uint16_t)(tt ? code >> 16 : code);
+    }
   }
 }
 
-template <bool IS_MIN>
-__device__ __forceinline__ void scan_dispatch(const int16_t* sf1, const int16_t* sf2, int FS, uint8_t* codes, int ncell, int nk, int n,
-                                              int cx0, int cy0, int xhi, int yhi, int tid, int T) {
-  switch (n + 1) {
-    case 3: scan_candidates<3, IS_MIN>(sf1, sf2, FS, codes, ncell, nk, n, cx0, cy0, xhi, yhi, tid, T); break;
-    case 4: scan_candidates<4, IS_MIN>(sf1, sf2, FS, codes, ncell, nk, n, cx0, cy0, xhi, yhi, tid, T); break;
-    case 7: scan_candidates<7, IS_MIN>(sf1, sf2, FS, codes, ncell, nk, n, cx0, cy0, xhi, yhi, tid, T); break;
-    case 10: scan_candidates<10, IS_MIN>(sf1, sf2, FS, codes, ncell, nk, n, cx0, cy0, xhi, yhi, tid, T); break;
-    default: scan_candidates<0, IS_MIN>(sf1, sf2, FS, codes, ncell, nk, n, cx0, cy0, xhi, yhi, tid, T); break;
+// ---- phase 3b: the remaining rows (distance 2 .. n above and below the extreme) of the queued candidates
+template <int N1, bool IS_MIN>
+__device__ __forceinline__ void finish_scans(const NmsArgs& A, const uint32_t* queue, int nq, int tid, int T) {
+  const int n = A.n, FSW = A.FS >> 1;
+  const uint32_t* sfw = (const uint32_t*)A.sf1;
+  uint8_t* codeb = (uint8_t*)A.codes;
+  for (int q = tid; q < nq; q += T) {
+    const uint32_t ent = queue[q];
+    const uint32_t* rowc = sfw + (ent & 0xFFFFu);
+    const uint32_t parity = (ent >> 16) & 1u;
+    const uint32_t m_first = parity ? 0x0000FFFFu : 0u, m_last = parity ? 0u : 0xFFFF0000u;
+    const uint32_t val = ((const uint16_t*)rowc)[parity + n];
+    const uint32_t target2 = val | (val << 16);
+    bool better = false;
+    for (int r = 2; r <= n && !better; r++) {
+      const uint32_t* up = rowc - r * FSW;
+      const uint32_t* dn = rowc + r * FSW;
+      better = rows_better<N1, IS_MIN>(up, dn, dn, n + 1, m_first, m_last, target2);
+    }
+    if (better) codeb[ent >> 17] = 0xFF;
+  }
+}
+
+__device__ __forceinline__ void nms_pass(const NmsArgs& A, int tid, int T) {
+  switch (A.n + 1) {
+    case 3: nms_cells<3>(A, tid, T); break;
+    case 4: nms_cells<4>(A, tid, T); break;
+    case 7: nms_cells<7>(A, tid, T); break;
+    case 10: nms_cells<10>(A, tid, T); break;
+    default: nms_cells<0>(A, tid, T); break;
+  }
+}
+__device__ __forceinline__ void finish_pass(const NmsArgs& A, int tid, int T) {
+  const int q0 = A.qn[0], q1 = A.qn[1];
+  switch (A.n + 1) {
+    case 3: finish_scans<3, true>(A, A.queue[0], q0, tid, T); finish_scans<3, false>(A, A.queue[1], q1, tid, T); break;
+    case 4: finish_scans<4, true>(A, A.queue[0], q0, tid, T); finish_scans<4, false>(A, A.queue[1], q1, tid, T); break;
+    case 7: finish_scans<7, true>(A, A.queue[0], q0, tid, T); finish_scans<7, false>(A, A.queue[1], q1, tid, T); break;
+    case 10: finish_scans<10, true>(A, A.queue[0], q0, tid, T); finish_scans<10, false>(A, A.queue[1], q1, tid, T); break;
+    default: finish_scans<0, true>(A, A.queue[0], q0, tid, T); finish_scans<0, false>(A, A.queue[1], q1, tid, T); break;
   }
 }
 
@@ -423,8 +504,9 @@ __device__ __forceinline__ void scan_dispatch(const int16_t* sf1, const int16_t*
 //            image tile into shared memory; everybody waits on the mbarrier.
 //   phase 2  register-window filters: Sobel walkers write du / dv (one coalesced 32-bit store per word and row),
 //            blob / checkerboard walkers write the biased responses f1 / f2 to shared memory only.
-//   phase 3  NMS of both passes on the responses: cell extremes as keys, tau test, window test, then one code word per
-//            owned cell (4 bytes = position of the kept extreme of each class or 0xFF) to global memory.
+//   phase 3  NMS of both passes on the responses: cell extremes as keys, tau test, quick window test (3a), the rest of
+//            the windows of the survivors (3b), then one code word per owned cell (4 bytes = position of the kept
+//            extreme of each class or 0xFF) to global memory (3c).  The candidate queues reuse the image tile.
 __global__ void __launch_bounds__(MAX_FILTER_THREADS, 2)
 k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const __grid_constant__ SlotList sl, const __grid_constant__ TileCfg t,
              const __grid_constant__ CUtensorMap tmap, int use_tma) {
@@ -432,16 +514,19 @@ k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const _
   const int slot = sl.s[blockIdx.z];
   const FrameDev F = frames[slot];
   const int tid = threadIdx.x, T = blockDim.x;
-  const TileRange X = tile_range(t, blockIdx.x, t.ntx, g.wm, g.bplm, true);
-  const TileRange Y = tile_range(t, blockIdx.y, t.nty, g.hm, g.hm, false);
+  const AxisTile& X = t.xt[blockIdx.x];
+  const AxisTile& Y = t.yt[blockIdx.y];
   const int FS = t.FS, IS = t.IS, IH = t.IH, IW = IS >> 2;
   uint8_t* simg = smem;
   int16_t* sf1 = (int16_t*)(smem + t.img_bytes);
   int16_t* sf2 = sf1 + (size_t)t.FH * FS;
   uint64_t* s_bar = (uint64_t*)(smem + t.img_bytes + t.f_bytes);
-  uint32_t* s_code = (uint32_t*)(s_bar + 2);
+  int* s_qn = (int*)(s_bar + 2);                          // four candidate counters
+  uint32_t* s_code = (uint32_t*)(s_qn + 4);
+  const int x_ilo = X.i_lo, y_ilo = Y.i_lo;
 
   // ---- phase 1
+  if (tid < 4) s_qn[tid] = 0;
   if (use_tma) {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(simg);
@@ -455,14 +540,14 @@ k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const _
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          :: "r"(dst), "l"(&tmap), "r"(X.i_lo), "r"(Y.i_lo), "r"(slot), "r"(bar) : "memory");
+          :: "r"(dst), "l"(&tmap), "r"(x_ilo), "r"(y_ilo), "r"(slot), "r"(bar) : "memory");
     }
     mbar_wait_or_trap(bar, 0);
   } else {
     const uint8_t* __restrict__ I = g.half ? F.half : F.img;
     for (int idx = tid; idx < IH * IW; idx += T) {
       const int ly = idx / IW, lw = idx - ly * IW;
-      const int gx = X.i_lo + 4 * lw, gy = Y.i_lo + ly;
+      const int gx = x_ilo + 4 * lw, gy = y_ilo + ly;
       uint32_t v = 0;
       if (gy >= 0 && gy < g.hm && gx >= 0 && gx < g.bplm) v = __ldg((const uint32_t*)(I + (size_t)gy * g.bplm + gx));
       *(uint32_t*)(simg + ly * IS + 4 * lw) = v;
@@ -472,102 +557,74 @@ k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const _
 
   // ---- phase 2: work items = (word column, row segment) of the Sobel range, then of the response range
   {
-    const int seg = t.seg;
-    const int nwa = (X.d_hi - X.d_lo) >> 2, nra = Y.d_hi - Y.d_lo, nsa = nra > 0 ? (nra + seg - 1) / seg : 0;
-    const int nwb = (X.f_hi - X.f_lo) >> 2, nrb = Y.f_hi - Y.f_lo, nsb = nrb > 0 ? (nrb + seg - 1) / seg : 0;
-    const int na = nwa * nsa, nb = nwb * nsb;
+    const int nwa = X.nwa, nwb = X.nwb, nrb = Y.f_hi - Y.f_lo;
+    const int na = nwa * Y.nsA, nb = nwb * Y.nsB;
     const uint32_t* img32 = (const uint32_t*)simg;
     for (int item = tid; item < na + nb; item += T) {
       if (item < na) {
-        const int sg = item / nwa, j = item - sg * nwa;
-        const int gx = X.d_lo + 4 * j, gy0 = Y.d_lo + sg * seg;
-        const uint32_t* col = img32 + (gy0 - 2 - Y.i_lo) * IW + ((gx - X.i_lo) >> 2) - 1;
-        walk_sobel(col, IW, min(seg, Y.d_hi - gy0), gy0, gx, g.bplm, g.hm, F.du, F.dv);
+        const int sg = fast_div(item, X.inv_nwa), j = item - sg * nwa;
+        const int gx = X.d_lo + 4 * j, gy0 = Y.d_lo + sg * Y.segA;
+        const uint32_t* col = img32 + (gy0 - 2 - y_ilo) * IW + ((gx - x_ilo) >> 2) - 1;
+        walk_sobel(col, IW, min(Y.segA, Y.d_hi - gy0), gy0, gx, g.bplm, g.hm, F.du, F.dv);
       } else {
         const int it = item - na;
-        const int sg = it / nwb, j = it - sg * nwb;
-        const int gx = X.f_lo + 4 * j, ly0 = sg * seg, gy0 = Y.f_lo + ly0;
-        const uint32_t* col = img32 + (gy0 - 2 - Y.i_lo) * IW + ((gx - X.i_lo) >> 2) - 1;
-        walk_blob_checker(col, IW, min(seg, nrb - ly0), sf1 + ly0 * FS + 4 * j, sf2 + ly0 * FS + 4 * j, FS);
+        const int sg = fast_div(it, X.inv_nwb), j = it - sg * nwb;
+        const int gx = X.f_lo + 4 * j, ly0 = sg * Y.segB, gy0 = Y.f_lo + ly0;
+        const uint32_t* col = img32 + (gy0 - 2 - y_ilo) * IW + ((gx - x_ilo) >> 2) - 1;
+        walk_blob_checker(col, IW, min(Y.segB, nrb - ly0), sf1 + ly0 * FS + 4 * j, sf2 + ly0 * FS + 4 * j, FS);
       }
     }
   }
   __syncthreads();
+  if (X.fill_hi > X.v_hi || Y.fill_hi > Y.v_hi) {           // tiles at the right / bottom image border only
+    const int vw = X.v_hi - X.f_lo, fw = X.fill_hi - X.f_lo, vr = Y.v_hi - Y.f_lo, fr = Y.fill_hi - Y.f_lo;
+    const int ncol = fw - vw;
+    for (int idx = tid; idx < fr * ncol; idx += T) {        // columns behind the last valid one, all rows
+      const int row = idx / ncol, c = vw + idx - row * ncol;
+      sf1[row * FS + c] = BIAS_F1; sf2[row * FS + c] = BIAS_F2;
+    }
+    for (int idx = tid; idx < (fr - vr) * vw; idx += T) {   // rows below the last valid one
+      const int row = vr + idx / vw, c = idx % vw;
+      sf1[row * FS + c] = BIAS_F1; sf2[row * FS + c] = BIAS_F2;
+    }
+    __syncthreads();
+  }
 
   // ---- phase 3
   {
-    const int xhi = g.wm - 1 - VISO_MARGIN - X.f_lo, yhi = g.hm - 1 - VISO_MARGIN - Y.f_lo;   // window clamps, plane coordinates
-    int klo[2], nk[2], llo[2], nl[2], cbase[2];
+    NmsArgs A[2];
     int ncell_total = 0;
+    uint32_t* qbase = (uint32_t*)simg;                    // the image tile is dead: its memory holds the candidate queues
 #pragma unroll
     for (int p = 0; p < 2; p++) {
-      klo[p] = llo[p] = nk[p] = nl[p] = 0; cbase[p] = ncell_total;
-      if (p < g.first_pass) continue;
-      owned_cells(X, g.n[p], g.ncx[p], klo[p], nk[p]);
-      owned_cells(Y, g.n[p], g.ncy[p], llo[p], nl[p]);
-      ncell_total += nk[p] * nl[p];
+      NmsArgs& a = A[p];
+      const int n = g.n[p], org = n + VISO_MARGIN;
+      a.sf1 = sf1; a.sf2 = sf2; a.FS = FS;
+      a.n = n; a.nk = X.nk[p]; a.inv_nk = X.inv_nk[p];
+      a.ncell = p < g.first_pass ? 0 : X.nk[p] * Y.nk[p];
+      a.codes = s_code + ncell_total;
+      a.queue[0] = qbase; a.queue[1] = qbase + 2 * a.ncell; qbase += 4 * a.ncell;
+      a.qn = s_qn + 2 * p;
+      a.cx0 = org + X.klo[p] * (n + 1) - X.f_lo; a.cy0 = org + Y.klo[p] * (n + 1) - Y.f_lo;
+      a.xhi = g.wm - 1 - VISO_MARGIN - X.f_lo; a.yhi = g.hm - 1 - VISO_MARGIN - Y.f_lo;    // window clamps, plane coordinates
+      a.tau = g.tau;
+      ncell_total += a.ncell;
     }
-
-    // 3a: cell extremes and tau test.  Sparse-pass cells are split between two lanes (upper / lower rows).
-#pragma unroll
-    for (int p = 0; p < 2; p++) {
-      if (p < g.first_pass) continue;
-      const int n = g.n[p], n1 = n + 1, org = n + VISO_MARGIN;
-      const int ncell = nk[p] * nl[p];
-      const int G = n1 >= 6 ? 2 : 1;                                        // lanes per cell
-      const int half_rows = (n1 + 1) >> 1;
-      const int nitem = (ncell * G + 31) & ~31;                            // whole warps take part in the shuffle
-      for (int item = tid; item < nitem; item += T) {
-        const int cell = item / G, tt = item - cell * G;
-        const bool live = cell < ncell;
-        const int kk = live ? cell % nk[p] : 0, ll = live ? cell / nk[p] : 0;
-        const int i0 = org + (klo[p] + kk) * n1 - X.f_lo, j0 = org + (llo[p] + ll) * n1 - Y.f_lo;
-        Keys4 K = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u};
-        const int row_lo = G == 2 ? tt * half_rows : 0, row_hi = G == 2 ? (tt ? n1 : half_rows) : n1;
-        if (live) {
-          cell_keys(sf1, sf2, FS, n1, i0, j0, row_lo, row_hi, K);
-          // positions are relative to row_lo: shift them to the cell (dy is the low nibble; complemented for maxima)
-          K.mn1 += row_lo; K.mn2 += row_lo; K.mx1 -= row_lo; K.mx2 -= row_lo;
-        }
-        if (G == 2) {
-          K.mn1 = min(K.mn1, __shfl_xor_sync(0xFFFFFFFFu, K.mn1, 1)); K.mx1 = max(K.mx1, __shfl_xor_sync(0xFFFFFFFFu, K.mx1, 1));
-          K.mn2 = min(K.mn2, __shfl_xor_sync(0xFFFFFFFFu, K.mn2, 1)); K.mx2 = max(K.mx2, __shfl_xor_sync(0xFFFFFFFFu, K.mx2, 1));
-        }
-        if (live && tt == 0) {
-          // class c: 0 = f1 min, 1 = f1 max, 2 = f2 min, 3 = f2 max; code byte = position or 0xFF
-          uint32_t code = 0;
-          code |= ((int)(K.mn1 >> 16) <= BIAS_F1 - g.tau) ? (K.mn1 & 0xFFu) : 0xFFu;
-          code |= (((int)(K.mx1 >> 16) >= BIAS_F1 + g.tau) ? ((K.mx1 & 0xFFu) ^ 0xFFu) : 0xFFu) << 8;
-          code |= (((int)(K.mn2 >> 16) <= BIAS_F2 - g.tau) ? (K.mn2 & 0xFFu) : 0xFFu) << 16;
-          code |= (((int)(K.mx2 >> 16) >= BIAS_F2 + g.tau) ? ((K.mx2 & 0xFFu) ^ 0xFFu) : 0xFFu) << 24;
-          s_code[cbase[p] + cell] = code;
-        }
-      }
-    }
+    if (A[0].ncell > 0) nms_pass(A[0], tid, T);
+    if (A[1].ncell > 0) nms_pass(A[1], tid, T);
     __syncthreads();
-
-    // 3b: window tests, one loop per pass and kind
-#pragma unroll
-    for (int p = 0; p < 2; p++) {
-      if (p < g.first_pass) continue;
-      const int n = g.n[p], n1 = n + 1, org = n + VISO_MARGIN;
-      const int ncell = nk[p] * nl[p];
-      if (ncell == 0) continue;
-      const int cx0 = org + klo[p] * n1 - X.f_lo, cy0 = org + llo[p] * n1 - Y.f_lo;
-      uint8_t* codes = (uint8_t*)(s_code + cbase[p]);
-      scan_dispatch<true>(sf1, sf2, FS, codes, ncell, nk[p], n, cx0, cy0, xhi, yhi, tid, T);
-      scan_dispatch<false>(sf1, sf2, FS, codes, ncell, nk[p], n, cx0, cy0, xhi, yhi, tid, T);
-    }
+    if (A[0].ncell > 0) finish_pass(A[0], tid, T);
+    if (A[1].ncell > 0) finish_pass(A[1], tid, T);
     __syncthreads();
 
     // 3c: code words to global memory, cell-column-major
     for (int idx = tid; idx < ncell_total; idx += T) {
-      const bool second = idx >= cbase[1] && nk[1] * nl[1] > 0;
-      const int cell = idx - (second ? cbase[1] : cbase[0]);
-      const int nkp = second ? nk[1] : nk[0];
-      const int kk = cell % nkp, ll = cell / nkp;
+      const bool second = idx >= A[0].ncell;
+      const int cell = second ? idx - A[0].ncell : idx;
+      const int nkp = second ? A[1].nk : A[0].nk;
+      const int ll = fast_div(cell, second ? A[1].inv_nk : A[0].inv_nk), kk = cell - ll * nkp;
       uint32_t* dst = second ? F.codes[1] : F.codes[0];
-      dst[(size_t)((second ? klo[1] : klo[0]) + kk) * (second ? g.ncy[1] : g.ncy[0]) + ((second ? llo[1] : llo[0]) + ll)] = s_code[idx];
+      dst[(size_t)((second ? X.klo[1] : X.klo[0]) + kk) * (second ? g.ncy[1] : g.ncy[0]) + ((second ? Y.klo[1] : Y.klo[0]) + ll)] = s_code[idx];
     }
   }
 }
@@ -758,8 +815,9 @@ __global__ void k_gather_counts(const FrameDev* frames, SlotList sl, int32_t* ou
 // host side: tile configurations, tensor maps, launch
 namespace {
 
-// kx x ky aligning-pass cells per tile; returns false if the configuration does not fit (TMA box, shared memory)
-bool make_tile_cfg(const Geometry& g, int kx, int ky, int threads, TileCfg& t) {
+// kx x ky aligning-pass cells per tile; fills the configuration and the two per-axis tables (host copies); returns false
+// if the configuration does not fit (TMA box, shared memory, packed queue entries)
+bool make_tile_cfg(const Geometry& g, int kx, int ky, int threads, TileCfg& t, std::vector<AxisTile>& xt, std::vector<AxisTile>& yt) {
   memset(&t, 0, sizeof t);
   const int pa = g.first_pass;                              // the aligning pass: sparse when multi_stage (n[0] >= n[1])
   t.nA = g.n[pa]; t.stepA = t.nA + 1; t.orgA = t.nA + VISO_MARGIN;
@@ -770,33 +828,57 @@ bool make_tile_cfg(const Geometry& g, int kx, int ky, int threads, TileCfg& t) {
   t.nty = g.ncy[pa] > 0 ? (g.ncy[pa] + ky - 1) / ky : (g.hm - t.orgA + t.THn - 1) / t.THn;
   if (t.ntx < 1) t.ntx = 1;
   if (t.nty < 1) t.nty = 1;
-  int nwf = 1, is = 16, fh = 1, ih = 1, nwa_max = 1, nra_max = 1;
+  xt.assign(t.ntx, AxisTile()); yt.assign(t.nty, AxisTile());
+  int nwf = 1, is = 16, fh = 1, ih = 1, nwa_max = 1, nwf_alloc = 1;
   int cells_x[2] = {0, 0}, cells_y[2] = {0, 0};
   for (int a = 0; a < t.ntx; a++) {
-    const TileRange X = tile_range(t, a, t.ntx, g.wm, g.bplm, true);
-    nwf = std::max(nwf, (X.f_hi - X.f_lo) / 4);
+    AxisTile& X = xt[a];
+    memset(&X, 0, sizeof X);
+    tile_range(t, a, t.ntx, g.wm, g.bplm, true, X);
+    X.nwa = (X.d_hi - X.d_lo) / 4; X.nwb = (X.f_hi - X.f_lo) / 4;
+    nwf_alloc = std::max(nwf_alloc, (X.fill_hi - X.f_lo) / 4);
+    X.inv_nwa = 1.0f / (float)std::max(X.nwa, 1); X.inv_nwb = 1.0f / (float)std::max(X.nwb, 1);
+    nwf = std::max(nwf, X.nwb);
     is = std::max(is, (int)align_up((size_t)(X.i_hi - X.i_lo), 16));
-    nwa_max = std::max(nwa_max, (X.d_hi - X.d_lo) / 4);
-    for (int p = g.first_pass; p < 2; p++) { int klo, nk; owned_cells(X, g.n[p], g.ncx[p], klo, nk); cells_x[p] = std::max(cells_x[p], nk); }
+    nwa_max = std::max(nwa_max, X.nwa);
+    for (int p = 0; p < 2; p++) {
+      if (p >= g.first_pass) owned_cells(X, g.n[p], g.ncx[p], X.klo[p], X.nk[p]);
+      X.inv_nk[p] = 1.0f / (float)std::max(X.nk[p], 1);
+      cells_x[p] = std::max(cells_x[p], X.nk[p]);
+    }
   }
   for (int b = 0; b < t.nty; b++) {
-    const TileRange Y = tile_range(t, b, t.nty, g.hm, g.hm, false);
-    fh = std::max(fh, Y.f_hi - Y.f_lo);
+    AxisTile& Y = yt[b];
+    memset(&Y, 0, sizeof Y);
+    tile_range(t, b, t.nty, g.hm, g.hm, false, Y);
+    fh = std::max(fh, Y.fill_hi - Y.f_lo);
     ih = std::max(ih, Y.i_hi - Y.i_lo);
-    nra_max = std::max(nra_max, Y.d_hi - Y.d_lo);
-    for (int p = g.first_pass; p < 2; p++) { int llo, nl; owned_cells(Y, g.n[p], g.ncy[p], llo, nl); cells_y[p] = std::max(cells_y[p], nl); }
+    for (int p = 0; p < 2; p++) {
+      if (p >= g.first_pass) owned_cells(Y, g.n[p], g.ncy[p], Y.klo[p], Y.nk[p]);
+      Y.inv_nk[p] = 1.0f / (float)std::max(Y.nk[p], 1);
+      cells_y[p] = std::max(cells_y[p], Y.nk[p]);
+    }
   }
-  t.NWf = nwf; t.FS = 4 * nwf; t.FH = fh; t.IS = is; t.IH = ih;
+  // rows per walker: as short as possible (more walkers) while one round of the threads covers the whole tile
+  for (int b = 0; b < t.nty; b++) {
+    AxisTile& Y = yt[b];
+    const int nra = std::max(Y.d_hi - Y.d_lo, 0), nrb = std::max(Y.f_hi - Y.f_lo, 0);
+    Y.nsA = nra > 0 ? 1 : 0; Y.nsB = nrb > 0 ? 1 : 0;
+    for (int s = 8; s <= std::max(nra, nrb); s++) {
+      const int na = (nra + s - 1) / s, nb = (nrb + s - 1) / s;
+      if (nwa_max * na + nwf * nb <= threads) { Y.nsA = na; Y.nsB = nb; break; }
+    }
+    Y.segA = Y.nsA ? (nra + Y.nsA - 1) / Y.nsA : 1;
+    Y.segB = Y.nsB ? (nrb + Y.nsB - 1) / Y.nsB : 1;
+  }
+  t.NWf = nwf_alloc; t.FS = 4 * nwf_alloc; t.FH = fh; t.IS = is; t.IH = ih;
   t.max_cells = cells_x[0] * cells_y[0] + cells_x[1] * cells_y[1];
   t.threads = threads;
-  // rows per walker: as short as possible (more walkers) while one round of the threads covers a whole tile
-  t.seg = std::max(fh, nra_max);
-  for (int s = 8; s < std::max(fh, nra_max); s++)
-    if (nwa_max * ((nra_max + s - 1) / s) + nwf * ((fh + s - 1) / s) <= threads) { t.seg = s; break; }
-  t.img_bytes = (unsigned)align_up((size_t)t.IS * t.IH, 128);
+  // the image tile doubles as the candidate queues of phase 3 (four entries of 4 bytes per cell at most)
+  t.img_bytes = (unsigned)align_up(std::max((size_t)t.IS * t.IH, (size_t)16 * t.max_cells), 128);
   t.f_bytes = (unsigned)align_up((size_t)2 * t.FH * t.FS * sizeof(int16_t) + 16, 16);
-  t.smem = t.img_bytes + t.f_bytes + 16 + (unsigned)t.max_cells * 4 + 16;
-  return t.IS <= 256 && t.IH <= 256 && t.smem <= 227 * 1024;
+  t.smem = t.img_bytes + t.f_bytes + 16 + 16 + (unsigned)t.max_cells * 4 + 16;
+  return t.IS <= 256 && t.IH <= 256 && t.smem <= 227 * 1024 && (size_t)t.FH * t.FS <= 65535 && t.max_cells <= 8191;
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -830,6 +912,14 @@ int encode_tile_map(visocu_ctx* ctx, const TileCfg& t, CUtensorMap* out) {
 // Tile configurations of a context: up to VISO_TILE_LEVELS sizes, largest first.  Large tiles have the smallest halo
 // (best throughput when a launch has many frames), small tiles give a launch of a few frames enough CTAs to spread
 // over the GPU.  VISOCU_TILE="kx,ky,threads" pins one configuration (experiments).
+void visocu_free_tiles(visocu_ctx* ctx) {
+  for (int c = 0; c < VISO_TILE_LEVELS; c++) {
+    if (ctx->tiles[c].tables) cudaFree(ctx->tiles[c].tables);
+    ctx->tiles[c].tables = nullptr;
+  }
+  ctx->n_tiles = 0;
+}
+
 int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes) {
   const Geometry& g = ctx->g;
   ctx->frame_stride = frame_stride_bytes;
@@ -844,21 +934,29 @@ int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes) {
       cand[0][0] = kx; cand[0][1] = ky; cand[0][2] = th; ncand = 1;
     }
   }
-  ctx->n_tiles = 0;
+  visocu_free_tiles(ctx);
   for (int c = 0; c < ncand; c++) {
     int kx = std::max(cand[c][0], 1), ky = std::max(cand[c][1], 1);
     TileCfg t;
-    bool ok = make_tile_cfg(g, kx, ky, cand[c][2], t);
+    std::vector<AxisTile> xt, yt;
+    bool ok = make_tile_cfg(g, kx, ky, cand[c][2], t, xt, yt);
     while (!ok && (kx > 1 || ky > 1)) {                     // shrink until the box and the shared memory fit
       if (kx >= ky && kx > 1) kx = (kx + 1) / 2; else ky = (ky + 1) / 2;
-      ok = make_tile_cfg(g, kx, ky, cand[c][2], t);
+      ok = make_tile_cfg(g, kx, ky, cand[c][2], t, xt, yt);
     }
     if (!ok) continue;
     visocu_tile& slot = ctx->tiles[ctx->n_tiles];
     static_assert(sizeof(TileCfg) <= sizeof(slot.cfg), "TileCfg storage");
+    // per-axis tables: x entries then y entries in one device block
+    const size_t nb = sizeof(AxisTile) * (xt.size() + yt.size());
+    CU_TRY(ctx, cudaMalloc(&slot.tables, nb));
+    std::vector<AxisTile> both(xt);
+    both.insert(both.end(), yt.begin(), yt.end());
+    CU_TRY(ctx, cudaMemcpy(slot.tables, both.data(), nb, cudaMemcpyHostToDevice));
+    t.xt = (const AxisTile*)slot.tables; t.yt = t.xt + xt.size();
     memcpy(slot.cfg, &t, sizeof t);
-    if (ctx->use_tma) { int rc = encode_tile_map(ctx, t, &slot.tmap); if (rc) return rc; }
     ctx->n_tiles++;
+    if (ctx->use_tma) { int rc = encode_tile_map(ctx, t, &slot.tmap); if (rc) return rc; }
   }
   if (ctx->n_tiles == 0) return visocu_set_error(ctx, VISOCU_EINVAL, "no tile configuration fits %dx%d with nms_n = %d", g.wm, g.hm, g.n[1]);
   return VISOCU_OK;

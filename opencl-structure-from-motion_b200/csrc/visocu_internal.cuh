@@ -37,7 +37,7 @@ struct SlotList { int n; int s[VISO_MAX_BATCH]; };
 
 #define VISO_TILE_LEVELS 3
 // one tile configuration of the fused filter+NMS kernel (csrc/features.cu: TileCfg) and its TMA descriptor
-struct visocu_tile { alignas(64) CUtensorMap tmap; alignas(8) unsigned char cfg[128]; };
+struct visocu_tile { alignas(64) CUtensorMap tmap; alignas(8) unsigned char cfg[128]; void* tables = nullptr; };
 
 // state of a matching call whose outlier removal runs on the second stream (visocu_match_deferred / _collect)
 struct visocu_deferred {
@@ -134,3 +134,4 @@ __host__ __device__ static inline int viso_cell_count(int len, int n) {
 // launchers implemented in the kernel translation units
 int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl);
 int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes);
+void visocu_free_tiles(visocu_ctx* ctx);
