@@ -500,7 +500,7 @@ extern "C" int visocu_get_plane(visocu_ctx* ctx, int32_t frame, int32_t which, u
     case 2: src = F.du_full; w = g.w; h = g.h; bpl = g.bpl; break;
     case 3: src = F.dv_full; w = g.w; h = g.h; bpl = g.bpl; break;
     case 4: src = F.img; w = g.w; h = g.h; bpl = g.bpl; break;
-    case 5: src = F.half; break;
+    case 5: src = F.half; if (src && ctx->fused_half) { int rc2 = visocu_make_half_image(ctx, frame); if (rc2) return rc2; } break;
     default: return visocu_set_error(ctx, VISOCU_EINVAL, "unknown plane %d", which);
   }
   if (!src) return visocu_set_error(ctx, VISOCU_ESTATE, "plane %d does not exist in this configuration", which);

@@ -78,65 +78,78 @@ __device__ __forceinline__ void taps6(uint32_t L, uint32_t C, uint32_t R, uint32
   t[5] = __byte_perm(s2b, 0, 0x4341);
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(x) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(x), "r"(y) : "memory"); }
+
 // Sobel walker: du = ((1,4,6,4,1)^T x (1,2,0,-2,-1)) >> 7 + 128, dv = ((1,2,0,-2,-1)^T x (1,4,6,4,1)) >> 7 + 128
 // (filter.cpp:316-324).  The sums are formed at twice their scale with a bias of 32768, so the result byte is simply the
 // high byte of each 16-bit lane and one PRMT assembles the four pixels of the output word.
-// col: word L of the first row needed (two rows above the first output row); IW: words per row of the image tile.
-// Writes rows [gy0, gy0 + nrow) of word column gx to the planes du / dv (stride bpl).
-__device__ __forceinline__ void walk_sobel(const uint32_t* col, int IW, int nrow, int gy0, int gx, int bpl, int himg,
+// col: shared-memory address of word L of the first row needed (two rows above the first output row); IWB: bytes per
+// row of the image tile.  Writes rows [gy0, gy0 + nrow) of word column gx to the planes du / dv (stride bpl).
+__device__ __forceinline__ void walk_sobel(uint32_t col, int IWB, int nrow, int gy0, int gx, int bpl, int himg,
                                            uint8_t* __restrict__ du, uint8_t* __restrict__ dv) {
   uint32_t hd[5][2], ha[5][2];
-#define SOB_HROW(S, r) {                                                                        \
-    const uint32_t* q = col + (r) * IW; uint32_t t[6]; taps6(q[0], q[1], q[2], t);                \
+#define SOB_HROW(S) {                                                                           \
+    uint32_t t[6]; taps6(lds32(col), lds32(col + 4), lds32(col + 8), t); col += IWB;              \
     _Pragma("unroll") for (int k = 0; k < 2; k++) {                                               \
       hd[S][k] = (t[k] + 2 * t[k + 1] + K2(765)) - (t[k + 4] + 2 * t[k + 3]);      /* (1,2,0,-2,-1) + 765 */ \
       ha[S][k] = (t[k] + t[k + 4]) + 4 * (t[k + 1] + t[k + 3]) + 6 * t[k + 2];     /* (1,4,6,4,1) */          \
     } }
-  SOB_HROW(0, 0) SOB_HROW(1, 1) SOB_HROW(2, 2) SOB_HROW(3, 3)
-  const bool first_word = gx == 0, last_word = gx == bpl - 4;
+  SOB_HROW(0) SOB_HROW(1) SOB_HROW(2) SOB_HROW(3)
+  uint8_t* pu = du + (size_t)gy0 * bpl + gx;
+  uint8_t* pv = dv + (size_t)gy0 * bpl + gx;
+  uint8_t* const pu0 = pu; uint8_t* const pv0 = pv;
   for (int r5 = 0; r5 < nrow; r5 += 5) {
 #define SOB_STEP(PH)                                                                                              \
     if (r5 + PH < nrow) {                                                                                         \
       constexpr int s0 = PH % 5, s1 = (PH + 1) % 5, s2 = (PH + 2) % 5, s3 = (PH + 3) % 5, s4 = (PH + 4) % 5;      \
-      const int gy = gy0 + r5 + PH;                                                                               \
-      SOB_HROW(s4, r5 + PH + 4)                                                                                   \
+      SOB_HROW(s4)                                                                                                \
       uint32_t u2[2], v2[2];                                                                                      \
       _Pragma("unroll") for (int k = 0; k < 2; k++) {                                                             \
         u2[k] = 2 * (hd[s0][k] + hd[s4][k]) + 8 * (hd[s1][k] + hd[s3][k]) + 12 * hd[s2][k] + K2(8288);            \
         v2[k] = 2 * ((ha[s0][k] + K2(4080)) - ha[s4][k]) + 4 * ((ha[s1][k] + K2(4080)) - ha[s3][k]) + K2(8288);   \
       }                                                                                                           \
-      uint32_t wu = __byte_perm(u2[0], u2[1], 0x7351), wv = __byte_perm(v2[0], v2[1], 0x7351);                    \
-      if (gy < 2 || gy > himg - 3) { wu = 0x80808080u; wv = 0x80808080u; }                                        \
-      if (first_word) { wu = (wu & 0xFFFF0000u) | 0x8080u; wv = (wv & 0xFFFF0000u) | 0x8080u; }                   \
-      if (last_word) { wu = (wu & 0x0000FFFFu) | 0x80800000u; wv = (wv & 0x0000FFFFu) | 0x80800000u; }            \
-      *(uint32_t*)(du + (size_t)gy * bpl + gx) = wu;                                                              \
-      *(uint32_t*)(dv + (size_t)gy * bpl + gx) = wv;                                                              \
+      *(uint32_t*)pu = __byte_perm(u2[0], u2[1], 0x7351); pu += bpl;                                              \
+      *(uint32_t*)pv = __byte_perm(v2[0], v2[1], 0x7351); pv += bpl;                                              \
     }
     SOB_STEP(0) SOB_STEP(1) SOB_STEP(2) SOB_STEP(3) SOB_STEP(4)
 #undef SOB_STEP
   }
 #undef SOB_HROW
+  // image border (filter.cpp:185-186 and the pad columns): the two outermost rows and columns read 128.  The same
+  // thread stored the words above, so these stores land after them.
+  if (gy0 < 2 || gy0 + nrow > himg - 2 || gx == 0 || gx == bpl - 4) {
+    for (int r = 0; r < nrow; r++) {
+      const int gy = gy0 + r;
+      if (gy < 2 || gy > himg - 3) { *(uint32_t*)(pu0 + r * bpl) = 0x80808080u; *(uint32_t*)(pv0 + r * bpl) = 0x80808080u; }
+      else if (gx == 0) { *(uint16_t*)(pu0 + r * bpl) = 0x8080; *(uint16_t*)(pv0 + r * bpl) = 0x8080; }
+      if (gx == bpl - 4 && gy >= 2 && gy <= himg - 3) { *(uint16_t*)(pu0 + r * bpl + 2) = 0x8080; *(uint16_t*)(pv0 + r * bpl + 2) = 0x8080; }
+    }
+  }
 }
 
 // Blob / checkerboard walker: f1 = -box5 + 2 box3 + 7 centre (filter.cpp:343-365), f2 = (1,1,0,-1,-1)^T x (1,1,0,-1,-1)
 // (filter.cpp:331-336), stored biased (BIAS_F1 / BIAS_F2) as int16 rows of FS samples in shared memory.
-// col as above; out1 / out2 point at the first output row of this word (4 samples = 8 bytes, 8-byte aligned).
-__device__ __forceinline__ void walk_blob_checker(const uint32_t* col, int IW, int nrow, int16_t* out1, int16_t* out2, int FS) {
+// col as above; out1 / out2: shared-memory addresses of the first output row of this word (4 samples = 8 bytes, 8-byte
+// aligned); FSB: bytes per row of the response planes.
+__device__ __forceinline__ void walk_blob_checker(uint32_t col, int IWB, int nrow, uint32_t out1, uint32_t out2, int FSB) {
   uint32_t h1[5][2], h3[5][2], hc[5][2], pc[5][2];
-#define BC_HROW(S, r) {                                                                         \
-    const uint32_t* q = col + (r) * IW; uint32_t t[6]; taps6(q[0], q[1], q[2], t);                \
+#define BC_HROW(S) {                                                                            \
+    uint32_t t[6]; taps6(lds32(col), lds32(col + 4), lds32(col + 8), t); col += IWB;              \
     _Pragma("unroll") for (int k = 0; k < 2; k++) {                                               \
       h3[S][k] = t[k + 1] + t[k + 2] + t[k + 3];                                                  \
       h1[S][k] = h3[S][k] + t[k] + t[k + 4];                                                      \
       hc[S][k] = (t[k] + t[k + 1] + K2(510)) - (t[k + 3] + t[k + 4]);             /* (1,1,0,-1,-1) + 510 */   \
       pc[S][k] = t[k + 2];                                                                        \
     } }
-  BC_HROW(0, 0) BC_HROW(1, 1) BC_HROW(2, 2) BC_HROW(3, 3)
+  BC_HROW(0) BC_HROW(1) BC_HROW(2) BC_HROW(3)
   for (int r5 = 0; r5 < nrow; r5 += 5) {
 #define BC_STEP(PH)                                                                                               \
     if (r5 + PH < nrow) {                                                                                         \
       constexpr int s0 = PH % 5, s1 = (PH + 1) % 5, s2 = (PH + 2) % 5, s3 = (PH + 3) % 5, s4 = (PH + 4) % 5;      \
-      BC_HROW(s4, r5 + PH + 4)                                                                                    \
+      BC_HROW(s4)                                                                                                 \
       uint32_t f1[2], f2[2];                                                                                      \
       _Pragma("unroll") for (int k = 0; k < 2; k++) {                                                             \
         const uint32_t b3 = h3[s1][k] + h3[s2][k] + h3[s3][k];                                                    \
@@ -144,8 +157,8 @@ __device__ __forceinline__ void walk_blob_checker(const uint32_t* col, int IW, i
         f1[k] = (7 * pc[s2][k] + 2 * b3 + K2(BIAS_F1)) - b5;                                                      \
         f2[k] = (hc[s0][k] + hc[s1][k] + K2(BIAS_F2)) - (hc[s3][k] + hc[s4][k]);                                  \
       }                                                                                                           \
-      *(uint2*)(out1 + (r5 + PH) * FS) = make_uint2(__byte_perm(f1[0], f1[1], 0x5410), __byte_perm(f1[0], f1[1], 0x7632)); \
-      *(uint2*)(out2 + (r5 + PH) * FS) = make_uint2(__byte_perm(f2[0], f2[1], 0x5410), __byte_perm(f2[0], f2[1], 0x7632)); \
+      sts64(out1, __byte_perm(f1[0], f1[1], 0x5410), __byte_perm(f1[0], f1[1], 0x7632)); out1 += FSB;             \
+      sts64(out2, __byte_perm(f2[0], f2[1], 0x5410), __byte_perm(f2[0], f2[1], 0x7632)); out2 += FSB;             \
     }
     BC_STEP(0) BC_STEP(1) BC_STEP(2) BC_STEP(3) BC_STEP(4)
 #undef BC_STEP
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(256) k_sobel_full(Geometry g, const FrameDev* 
   const int wcol = threadIdx.x & 63, seg = threadIdx.x >> 6;
   const int gx = x0 + 4 * wcol, gy0 = y0 + 8 * seg;
   if (gx >= g.bpl || gy0 >= g.h) return;
-  walk_sobel(simg + (8 * seg) * IW + wcol, IW, min(8, g.h - gy0), gy0, gx, g.bpl, g.h, F.du_full, F.dv_full);
+  walk_sobel((uint32_t)__cvta_generic_to_shared(simg + (8 * seg) * IW + wcol), 4 * IW, min(8, g.h - gy0), gy0, gx, g.bpl, g.h, F.du_full, F.dv_full);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -191,6 +204,9 @@ struct TileCfg {
   int IS, IH;              // image tile: bytes per row (multiple of 16), rows
   int max_cells;           // owned cells of one tile, both passes
   int threads;
+  // fused half-resolution mode: the full-resolution tile is staged in P parts of HP half-resolution rows (SR = 2 HP + 4
+  // full-resolution rows) by nbox TMA boxes of BW bytes per row (two boxes overlap so that no word column straddles them)
+  int fused, HP, P, SR, nbox, BW, segF;
   unsigned img_bytes, f_bytes, smem;
   const struct AxisTile* xt;   // ntx entries
   const struct AxisTile* yt;   // nty entries
@@ -206,6 +222,8 @@ struct AxisTile {          // one axis of one tile
   float inv_nk[2];         // 1 / nk (x axis: cell index -> column, row)
   int nwa, nwb;            // x axis: word columns of the Sobel / response range
   float inv_nwa, inv_nwb;
+  int df_lo, df_hi;        // fused half-resolution mode: full-resolution du / dv samples written along this axis
+  int nwF; float inv_nwF;  // x axis: their word columns
   int segA, segB, nsA, nsB;   // y axis: rows per Sobel / response walker and number of row segments
 };
 
@@ -245,6 +263,15 @@ inline void owned_cells(const AxisTile& r, int n, int ncells, int& klo, int& nk)
   int khi = ncells;
   if (r.own_hi < 0x3FFFFFFF) { int b = r.own_hi - org; khi = b > 0 ? (b + step - 1) / step : 0; if (khi > ncells) khi = ncells; }
   nk = khi > klo ? khi - klo : 0;
+}
+
+// atomicAdd on a shared-memory word (the generic form costs a dozen instructions when the compiler cannot see the
+// address space)
+__device__ __forceinline__ int atom_add_shared(int* p, int v) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
 }
 
 // q = a / d for 0 <= a < 2^20 with inv = 1.0f / d: (a + 0.5) / d is at least 0.5 / d away from an integer, far more than
@@ -374,16 +401,14 @@ struct NmsArgs {
 // the even lane and the lower rows on the odd one, f1 classes tested by the even lane and f2 classes by the odd one.
 // Survivors of the quick test are queued (warp-aggregated) for phase 3b.
 template <int N1>
-__device__ __forceinline__ void nms_cells(const NmsArgs& A, int tid, int T) {
+__device__ __forceinline__ void nms_cells(const NmsArgs& A, int item, unsigned lane) {
   const int n = A.n, n1 = n + 1, FS = A.FS, FSW = FS >> 1;
   const bool two = n1 >= 6;
-  const int G = two ? 2 : 1;
   const int half_rows = (n1 + 1) >> 1;
   constexpr int ROWS = N1 >= 6 ? (N1 + 1) / 2 : N1;
-  const int nitem = (A.ncell * G + 31) & ~31;                      // whole warps take part in the shuffles and ballots
-  const unsigned lane = tid & 31, lt = (1u << lane) - 1u;
+  const unsigned lt = (1u << lane) - 1u;                             // whole warps take part in the shuffles and ballots
   const uint32_t* sfw = (const uint32_t*)A.sf1;
-  for (int item = tid; item < nitem; item += T) {
+  {
     const int cell = two ? item >> 1 : item, tt = two ? item & 1 : 0;
     const bool live = cell < A.ncell;
     const int ll = live ? fast_div(cell, A.inv_nk) : 0, kk = live ? cell - ll * A.nk : 0;
@@ -442,7 +467,7 @@ __device__ __forceinline__ void nms_cells(const NmsArgs& A, int tid, int T) {
         if (m) {
           int base = 0;
           const int leader = __ffs(m) - 1;
-          if ((int)lane == leader) base = atomicAdd(A.qn + (u & 1), __popc(m));
+          if ((int)lane == leader) base = atom_add_shared(A.qn + (u & 1), __popc(m));
           base = __shfl_sync(0xFFFFFFFFu, base, leader);
           if (push) A.queue[u & 1][base + __popc(m & lt)] = ent;
         }
@@ -457,11 +482,11 @@ __device__ __forceinline__ void nms_cells(const NmsArgs& A, int tid, int T) {
 
 // ---- phase 3b: the remaining rows (distance 2 .. n above and below the extreme) of the queued candidates
 template <int N1, bool IS_MIN>
-__device__ __forceinline__ void finish_scans(const NmsArgs& A, const uint32_t* queue, int nq, int tid, int T) {
+__device__ __forceinline__ void finish_scans(const NmsArgs& A, const uint32_t* queue, int nq, int q) {
   const int n = A.n, FSW = A.FS >> 1;
   const uint32_t* sfw = (const uint32_t*)A.sf1;
   uint8_t* codeb = (uint8_t*)A.codes;
-  for (int q = tid; q < nq; q += T) {
+  if (q < nq) {
     const uint32_t ent = queue[q];
     const uint32_t* rowc = sfw + (ent & 0xFFFFu);
     const uint32_t parity = (ent >> 16) & 1u;
@@ -478,24 +503,33 @@ __device__ __forceinline__ void finish_scans(const NmsArgs& A, const uint32_t* q
   }
 }
 
-__device__ __forceinline__ void nms_pass(const NmsArgs& A, int tid, int T) {
+__device__ __forceinline__ void nms_pass(const NmsArgs& A, int item, unsigned lane) {
   switch (A.n + 1) {
-    case 3: nms_cells<3>(A, tid, T); break;
-    case 4: nms_cells<4>(A, tid, T); break;
-    case 7: nms_cells<7>(A, tid, T); break;
-    case 10: nms_cells<10>(A, tid, T); break;
-    default: nms_cells<0>(A, tid, T); break;
+    case 3: nms_cells<3>(A, item, lane); break;
+    case 4: nms_cells<4>(A, item, lane); break;
+    case 7: nms_cells<7>(A, item, lane); break;
+    case 10: nms_cells<10>(A, item, lane); break;
+    default: nms_cells<0>(A, item, lane); break;
   }
 }
-__device__ __forceinline__ void finish_pass(const NmsArgs& A, int tid, int T) {
-  const int q0 = A.qn[0], q1 = A.qn[1];
+// kind 0: minima, 1: maxima
+__device__ __forceinline__ void finish_pass(const NmsArgs& A, int kind, int nq, int q) {
+  const uint32_t* queue = A.queue[kind];
   switch (A.n + 1) {
-    case 3: finish_scans<3, true>(A, A.queue[0], q0, tid, T); finish_scans<3, false>(A, A.queue[1], q1, tid, T); break;
-    case 4: finish_scans<4, true>(A, A.queue[0], q0, tid, T); finish_scans<4, false>(A, A.queue[1], q1, tid, T); break;
-    case 7: finish_scans<7, true>(A, A.queue[0], q0, tid, T); finish_scans<7, false>(A, A.queue[1], q1, tid, T); break;
-    case 10: finish_scans<10, true>(A, A.queue[0], q0, tid, T); finish_scans<10, false>(A, A.queue[1], q1, tid, T); break;
-    default: finish_scans<0, true>(A, A.queue[0], q0, tid, T); finish_scans<0, false>(A, A.queue[1], q1, tid, T); break;
+    case 3: if (kind) finish_scans<3, false>(A, queue, nq, q); else finish_scans<3, true>(A, queue, nq, q); break;
+    case 4: if (kind) finish_scans<4, false>(A, queue, nq, q); else finish_scans<4, true>(A, queue, nq, q); break;
+    case 7: if (kind) finish_scans<7, false>(A, queue, nq, q); else finish_scans<7, true>(A, queue, nq, q); break;
+    case 10: if (kind) finish_scans<10, false>(A, queue, nq, q); else finish_scans<10, true>(A, queue, nq, q); break;
+    default: if (kind) finish_scans<0, false>(A, queue, nq, q); else finish_scans<0, true>(A, queue, nq, q); break;
   }
+}
+
+// Warp-granular dynamic scheduling: the warps of a CTA take chunks of 32 work items from a shared counter, expensive
+// chunks first, so that no warp waits long at the barrier that ends a phase.
+__device__ __forceinline__ int next_chunk(int* counter, unsigned lane) {
+  int c = 0;
+  if (lane == 0) c = atom_add_shared(counter, 1);
+  return __shfl_sync(0xFFFFFFFFu, c, 0);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -509,7 +543,7 @@ __device__ __forceinline__ void finish_pass(const NmsArgs& A, int tid, int T) {
 //            extreme of each class or 0xFF) to global memory (3c).  The candidate queues reuse the image tile.
 __global__ void __launch_bounds__(MAX_FILTER_THREADS, 2)
 k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const __grid_constant__ SlotList sl, const __grid_constant__ TileCfg t,
-             const __grid_constant__ CUtensorMap tmap, int use_tma) {
+             const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_full, int use_tma) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int slot = sl.s[blockIdx.z];
   const FrameDev F = frames[slot];
@@ -521,13 +555,86 @@ k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const _
   int16_t* sf1 = (int16_t*)(smem + t.img_bytes);
   int16_t* sf2 = sf1 + (size_t)t.FH * FS;
   uint64_t* s_bar = (uint64_t*)(smem + t.img_bytes + t.f_bytes);
-  int* s_qn = (int*)(s_bar + 2);                          // four candidate counters
-  uint32_t* s_code = (uint32_t*)(s_qn + 4);
+  int* s_qn = (int*)(s_bar + 2);                          // four candidate counters, two chunk counters
+  uint32_t* s_code = (uint32_t*)(s_qn + 8);
   const int x_ilo = X.i_lo, y_ilo = Y.i_lo;
 
   // ---- phase 1
-  if (tid < 4) s_qn[tid] = 0;
-  if (use_tma) {
+  if (tid < 8) s_qn[tid] = 0;
+  if (t.fused) {
+    // Half-resolution mode, fused: the FULL-resolution tile comes in by TMA, part by part, into the (still unused) response
+    // plane area.  Sobel walkers write du_full / dv_full from it (matcher.cpp:676), and the 2x2 box mean of
+    // createHalfResolutionImage (matcher.cpp:636-647) goes straight into the image tile that the phases below work on:
+    // the half-resolution image never exists in global memory.
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
+    const uint32_t stage = (uint32_t)__cvta_generic_to_shared(sf1);
+    const uint32_t simg_sa = (uint32_t)__cvta_generic_to_shared(simg);
+    const unsigned lane = tid & 31;
+    const int SR = t.SR, BW = t.BW;
+    const int fx0 = 2 * x_ilo;                              // full-resolution column of staging byte 0
+    const int xr = t.nbox == 2 ? 2 * IS - BW : 0;           // first column of the right box, relative to fx0
+    const uint32_t right = stage + (uint32_t)(BW * SR) - (uint32_t)xr;
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    for (int p = 0; p < t.P; p++) {
+      const int hr0 = p * t.HP, hr1 = min(hr0 + t.HP, IH);  // half-resolution rows of the image tile formed by this part
+      const int fy0 = 2 * (y_ilo + hr0) - 2;                // first staged full-resolution row
+      if (tid == 0) {
+        s_qn[6] = 0;
+        const uint32_t bytes = (uint32_t)(t.nbox * BW * SR);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            :: "r"(stage), "l"(&tmap_full), "r"(fx0), "r"(fy0), "r"(slot), "r"(bar) : "memory");
+        if (t.nbox == 2)
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+              :: "r"(stage + (uint32_t)(BW * SR)), "l"(&tmap_full), "r"(fx0 + xr), "r"(fy0), "r"(slot), "r"(bar) : "memory");
+      }
+      mbar_wait_or_trap(bar, (uint32_t)(p & 1));
+      // full-resolution Sobel rows of this part
+      const int ry0 = max(Y.df_lo, 2 * (y_ilo + hr0)), ry1 = min(Y.df_hi, 2 * (y_ilo + hr1));
+      const int nrF = max(ry1 - ry0, 0), nsF = (nrF + t.segF - 1) / t.segF;
+      const int nitem = X.nwF * nsF, ncW = (nitem + 31) >> 5;
+      const int nmean = (hr1 - hr0) * IW, ncB = (nmean + 127) >> 7;
+      for (int c = next_chunk(s_qn + 6, lane); c < ncW + ncB; c = next_chunk(s_qn + 6, lane)) {
+        if (c < ncW) {
+          const int item = 32 * c + (int)lane;
+          if (item < nitem) {
+            const int sg = fast_div(item, X.inv_nwF), j = item - sg * X.nwF;
+            const int gx = X.df_lo + 4 * j, gy0 = ry0 + sg * t.segF;
+            const int b = gx - fx0;                          // byte column in the staged rows
+            const uint32_t base = (t.nbox == 2 && b + 8 > BW) ? right : stage;
+            walk_sobel(base + (uint32_t)((gy0 - 2 - fy0) * BW + b - 4), BW, min(t.segF, ry1 - gy0), gy0, gx, g.bpl, g.h, F.du_full, F.dv_full);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int idx = 128 * (c - ncW) + 32 * k + (int)lane;
+            if (idx < nmean) {
+              const int hr = fast_div(idx, 1.0f / (float)IW), w = idx - hr * IW;
+              const int b8 = 8 * w;
+              const uint32_t base = (t.nbox == 2 && b8 + 8 > BW) ? right : stage;
+              const uint32_t a = base + (uint32_t)((2 * hr + 2) * BW + b8);
+              const uint2 r0 = lds64(a), r1 = lds64(a + (uint32_t)BW);
+              // pairs of horizontal neighbours as 16-bit lanes, rows added, truncating division by four
+              const uint32_t s0 = (r0.x & 0x00FF00FFu) + ((r0.x >> 8) & 0x00FF00FFu) + (r1.x & 0x00FF00FFu) + ((r1.x >> 8) & 0x00FF00FFu);
+              const uint32_t s1 = (r0.y & 0x00FF00FFu) + ((r0.y >> 8) & 0x00FF00FFu) + (r1.y & 0x00FF00FFu) + ((r1.y >> 8) & 0x00FF00FFu);
+              uint32_t out = __byte_perm((s0 >> 2) & 0x00FF00FFu, (s1 >> 2) & 0x00FF00FFu, 0x6420);
+              const int gxh = x_ilo + 4 * w, gyh = y_ilo + hr0 + hr;
+              if (gyh >= g.hm) out = 0;
+              else if (gxh + 3 >= g.wm) out = gxh >= g.wm ? 0u : out & (0xFFFFFFFFu >> (8 * (gxh + 4 - g.wm)));   // pad columns stay zero
+              sts32(simg_sa + (uint32_t)((hr0 + hr) * IS + 4 * w), out);
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  } else if (use_tma) {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(simg);
     if (tid == 0) {
@@ -559,19 +666,23 @@ k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const _
   {
     const int nwa = X.nwa, nwb = X.nwb, nrb = Y.f_hi - Y.f_lo;
     const int na = nwa * Y.nsA, nb = nwb * Y.nsB;
-    const uint32_t* img32 = (const uint32_t*)simg;
-    for (int item = tid; item < na + nb; item += T) {
-      if (item < na) {
+    const int na32 = (na + 31) & ~31;                       // response walkers start on a warp boundary: no warp runs both kinds
+    const uint32_t img_sa = (uint32_t)__cvta_generic_to_shared(simg), f1_sa = (uint32_t)__cvta_generic_to_shared(sf1);
+    const uint32_t f2_sa = f1_sa + (uint32_t)(t.FH * FS * 2);
+    for (int item = tid; item < na32 + nb; item += T) {
+      if (item < na32) {
+        if (item >= na) continue;
         const int sg = fast_div(item, X.inv_nwa), j = item - sg * nwa;
         const int gx = X.d_lo + 4 * j, gy0 = Y.d_lo + sg * Y.segA;
-        const uint32_t* col = img32 + (gy0 - 2 - y_ilo) * IW + ((gx - x_ilo) >> 2) - 1;
-        walk_sobel(col, IW, min(Y.segA, Y.d_hi - gy0), gy0, gx, g.bplm, g.hm, F.du, F.dv);
+        const uint32_t col = img_sa + (uint32_t)((gy0 - 2 - y_ilo) * IS + (gx - x_ilo) - 4);
+        walk_sobel(col, IS, min(Y.segA, Y.d_hi - gy0), gy0, gx, g.bplm, g.hm, F.du, F.dv);
       } else {
-        const int it = item - na;
+        const int it = item - na32;
         const int sg = fast_div(it, X.inv_nwb), j = it - sg * nwb;
         const int gx = X.f_lo + 4 * j, ly0 = sg * Y.segB, gy0 = Y.f_lo + ly0;
-        const uint32_t* col = img32 + (gy0 - 2 - y_ilo) * IW + ((gx - x_ilo) >> 2) - 1;
-        walk_blob_checker(col, IW, min(Y.segB, nrb - ly0), sf1 + ly0 * FS + 4 * j, sf2 + ly0 * FS + 4 * j, FS);
+        const uint32_t col = img_sa + (uint32_t)((gy0 - 2 - y_ilo) * IS + (gx - x_ilo) - 4);
+        const uint32_t o = (uint32_t)((ly0 * FS + 4 * j) * 2);
+        walk_blob_checker(col, IS, min(Y.segB, nrb - ly0), f1_sa + o, f2_sa + o, 2 * FS);
       }
     }
   }
@@ -610,11 +721,28 @@ k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const _
       a.tau = g.tau;
       ncell_total += a.ncell;
     }
-    if (A[0].ncell > 0) nms_pass(A[0], tid, T);
-    if (A[1].ncell > 0) nms_pass(A[1], tid, T);
+    const unsigned lane = tid & 31;
+    {
+      // 3a: chunks of the sparse pass (two lanes per cell if its cells have six or more rows) first, then the dense pass
+      const int g0 = g.n[0] + 1 >= 6 ? 2 : 1, g1 = g.n[1] + 1 >= 6 ? 2 : 1;
+      const int nc0 = (A[0].ncell * g0 + 31) >> 5, nc1 = (A[1].ncell * g1 + 31) >> 5;
+      for (int c = next_chunk(s_qn + 4, lane); c < nc0 + nc1; c = next_chunk(s_qn + 4, lane)) {
+        if (c < nc0) nms_pass(A[0], 32 * c + lane, lane);
+        else nms_pass(A[1], 32 * (c - nc0) + lane, lane);
+      }
+    }
     __syncthreads();
-    if (A[0].ncell > 0) finish_pass(A[0], tid, T);
-    if (A[1].ncell > 0) finish_pass(A[1], tid, T);
+    {
+      // 3b: chunks of the four candidate queues
+      const int q0 = s_qn[0], q1 = s_qn[1], q2 = s_qn[2], q3 = s_qn[3];
+      const int e0 = (q0 + 31) >> 5, e1 = e0 + ((q1 + 31) >> 5), e2 = e1 + ((q2 + 31) >> 5), e3 = e2 + ((q3 + 31) >> 5);
+      for (int c = next_chunk(s_qn + 5, lane); c < e3; c = next_chunk(s_qn + 5, lane)) {
+        if (c < e0) finish_pass(A[0], 0, q0, 32 * c + lane);
+        else if (c < e1) finish_pass(A[0], 1, q1, 32 * (c - e0) + lane);
+        else if (c < e2) finish_pass(A[1], 0, q2, 32 * (c - e1) + lane);
+        else finish_pass(A[1], 1, q3, 32 * (c - e2) + lane);
+      }
+    }
     __syncthreads();
 
     // 3c: code words to global memory, cell-column-major
@@ -817,7 +945,7 @@ namespace {
 
 // kx x ky aligning-pass cells per tile; fills the configuration and the two per-axis tables (host copies); returns false
 // if the configuration does not fit (TMA box, shared memory, packed queue entries)
-bool make_tile_cfg(const Geometry& g, int kx, int ky, int threads, TileCfg& t, std::vector<AxisTile>& xt, std::vector<AxisTile>& yt) {
+bool make_tile_cfg(const Geometry& g, int kx, int ky, int threads, bool fused, TileCfg& t, std::vector<AxisTile>& xt, std::vector<AxisTile>& yt) {
   memset(&t, 0, sizeof t);
   const int pa = g.first_pass;                              // the aligning pass: sparse when multi_stage (n[0] >= n[1])
   t.nA = g.n[pa]; t.stepA = t.nA + 1; t.orgA = t.nA + VISO_MARGIN;
@@ -835,6 +963,8 @@ bool make_tile_cfg(const Geometry& g, int kx, int ky, int threads, TileCfg& t, s
     AxisTile& X = xt[a];
     memset(&X, 0, sizeof X);
     tile_range(t, a, t.ntx, g.wm, g.bplm, true, X);
+    // fused half-resolution mode: the last tile also writes the full-resolution pad columns up to bpl (> 2 bplm if w is odd)
+    if (fused && a == t.ntx - 1 && X.i_hi < (g.bpl + 1) / 2 + 4) X.i_hi = (g.bpl + 1) / 2 + 4;
     X.nwa = (X.d_hi - X.d_lo) / 4; X.nwb = (X.f_hi - X.f_lo) / 4;
     nwf_alloc = std::max(nwf_alloc, (X.fill_hi - X.f_lo) / 4);
     X.inv_nwa = 1.0f / (float)std::max(X.nwa, 1); X.inv_nwb = 1.0f / (float)std::max(X.nwb, 1);
@@ -866,7 +996,7 @@ bool make_tile_cfg(const Geometry& g, int kx, int ky, int threads, TileCfg& t, s
     Y.nsA = nra > 0 ? 1 : 0; Y.nsB = nrb > 0 ? 1 : 0;
     for (int s = 8; s <= std::max(nra, nrb); s++) {
       const int na = (nra + s - 1) / s, nb = (nrb + s - 1) / s;
-      if (nwa_max * na + nwf * nb <= threads) { Y.nsA = na; Y.nsB = nb; break; }
+      if (((nwa_max * na + 31) & ~31) + nwf * nb <= threads) { Y.nsA = na; Y.nsB = nb; break; }
     }
     Y.segA = Y.nsA ? (nra + Y.nsA - 1) / Y.nsA : 1;
     Y.segB = Y.nsB ? (nrb + Y.nsB - 1) / Y.nsB : 1;
@@ -877,7 +1007,32 @@ bool make_tile_cfg(const Geometry& g, int kx, int ky, int threads, TileCfg& t, s
   // the image tile doubles as the candidate queues of phase 3 (four entries of 4 bytes per cell at most)
   t.img_bytes = (unsigned)align_up(std::max((size_t)t.IS * t.IH, (size_t)16 * t.max_cells), 128);
   t.f_bytes = (unsigned)align_up((size_t)2 * t.FH * t.FS * sizeof(int16_t) + 16, 16);
-  t.smem = t.img_bytes + t.f_bytes + 16 + 16 + (unsigned)t.max_cells * 4 + 16;
+  t.smem = t.img_bytes + t.f_bytes + 16 + 32 + (unsigned)t.max_cells * 4 + 16;
+  if (fused) {
+    // full-resolution staging inside the response plane area: two overlapping boxes of 256 bytes per row cover 2 IS <= 480
+    if (2 * t.IS > 480) return false;
+    t.fused = 1;
+    t.nbox = 2 * t.IS > 256 ? 2 : 1;
+    t.BW = t.nbox == 2 ? 256 : 2 * t.IS;
+    const int rows_fit = (int)(t.f_bytes / (unsigned)(t.nbox * t.BW));
+    int hp = std::min((rows_fit - 4) / 2, 126);
+    if (hp < 4) return false;
+    t.P = (t.IH + hp - 1) / hp;
+    t.HP = (t.IH + t.P - 1) / t.P;
+    t.SR = 2 * t.HP + 4;
+    int nwF_max = 1;
+    for (int a = 0; a < t.ntx; a++) {
+      AxisTile& X = xt[a];
+      X.df_lo = 2 * X.d_lo; X.df_hi = a == t.ntx - 1 ? g.bpl : 2 * X.d_hi;
+      X.nwF = std::max(X.df_hi - X.df_lo, 0) / 4; X.inv_nwF = 1.0f / (float)std::max(X.nwF, 1);
+      nwF_max = std::max(nwF_max, X.nwF);
+    }
+    for (int b = 0; b < t.nty; b++) { AxisTile& Y = yt[b]; Y.df_lo = 2 * Y.d_lo; Y.df_hi = b == t.nty - 1 ? g.h : 2 * Y.d_hi; }
+    // rows per full-resolution Sobel walker: one round of the threads covers a part
+    t.segF = 2 * t.HP;
+    for (int sg = 8; sg < 2 * t.HP; sg++)
+      if (nwF_max * ((2 * t.HP + sg - 1) / sg) <= threads) { t.segF = sg; break; }
+  }
   return t.IS <= 256 && t.IH <= 256 && t.smem <= 227 * 1024 && (size_t)t.FH * t.FS <= 65535 && t.max_cells <= 8191;
 }
 
@@ -888,17 +1043,18 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
 // TMA descriptor of the matching-resolution image plane of every frame slot: a 3-D tensor (bytes per line, rows,
 // frame slots) with the tile's box; out-of-bounds elements are filled with zeros, which is what the filters expect
 // outside the image.
-int encode_tile_map(visocu_ctx* ctx, const TileCfg& t, CUtensorMap* out) {
+int encode_tile_map(visocu_ctx* ctx, const TileCfg& t, CUtensorMap* out, bool full) {
   const Geometry& g = ctx->g;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   CU_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) return visocu_set_error(ctx, VISOCU_ECUDA, "cuTensorMapEncodeTiled is not available");
   const FrameDev& F0 = ctx->frames_h[0];
-  void* base = g.half ? (void*)F0.half : (void*)F0.img;
-  const cuuint64_t dims[3] = {(cuuint64_t)g.bplm, (cuuint64_t)g.hm, (cuuint64_t)ctx->n_frames};
-  const cuuint64_t strides[2] = {(cuuint64_t)g.bplm, (cuuint64_t)ctx->frame_stride};
-  const cuuint32_t box[3] = {(cuuint32_t)t.IS, (cuuint32_t)t.IH, 1};
+  // full: the full-resolution image planes with the staging box of the fused half-resolution mode
+  void* base = (g.half && !full) ? (void*)F0.half : (void*)F0.img;
+  const cuuint64_t dims[3] = {(cuuint64_t)(full ? g.bpl : g.bplm), (cuuint64_t)(full ? g.h : g.hm), (cuuint64_t)ctx->n_frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)(full ? g.bpl : g.bplm), (cuuint64_t)ctx->frame_stride};
+  const cuuint32_t box[3] = {(cuuint32_t)(full ? t.BW : t.IS), (cuuint32_t)(full ? t.SR : t.IH), 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = ((EncodeFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -926,7 +1082,11 @@ int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes) {
   ctx->use_tma = 1;
   if (const char* env = getenv("VISOCU_TMA")) if (env[0] == '0') ctx->use_tma = 0;    // debugging switch: stage the tile with plain loads
   const int stepA = g.n[g.first_pass] + 1;
-  int cand[VISO_TILE_LEVELS][3] = {{210 / stepA, 60 / stepA, 512}, {100 / stepA, 60 / stepA, 512}, {100 / stepA, 30 / stepA, 256}};
+  // VISOCU_FUSED_HALF=0: half-resolution mode with separate kernels for the half image and the full-resolution Sobel planes
+  bool fused = g.half && ctx->use_tma;
+  if (const char* env = getenv("VISOCU_FUSED_HALF")) if (env[0] == '0') fused = false;
+  ctx->fused_half = fused ? 1 : 0;
+  int cand[VISO_TILE_LEVELS][3] = {{(fused ? 190 : 210) / stepA, 60 / stepA, fused ? 384 : 512}, {100 / stepA, 60 / stepA, fused ? 384 : 512}, {100 / stepA, 30 / stepA, 256}};
   int ncand = VISO_TILE_LEVELS;
   if (const char* env = getenv("VISOCU_TILE")) {
     int kx = 0, ky = 0, th = 0;
@@ -939,10 +1099,10 @@ int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes) {
     int kx = std::max(cand[c][0], 1), ky = std::max(cand[c][1], 1);
     TileCfg t;
     std::vector<AxisTile> xt, yt;
-    bool ok = make_tile_cfg(g, kx, ky, cand[c][2], t, xt, yt);
+    bool ok = make_tile_cfg(g, kx, ky, cand[c][2], fused, t, xt, yt);
     while (!ok && (kx > 1 || ky > 1)) {                     // shrink until the box and the shared memory fit
       if (kx >= ky && kx > 1) kx = (kx + 1) / 2; else ky = (ky + 1) / 2;
-      ok = make_tile_cfg(g, kx, ky, cand[c][2], t, xt, yt);
+      ok = make_tile_cfg(g, kx, ky, cand[c][2], fused, t, xt, yt);
     }
     if (!ok) continue;
     visocu_tile& slot = ctx->tiles[ctx->n_tiles];
@@ -956,16 +1116,28 @@ int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes) {
     t.xt = (const AxisTile*)slot.tables; t.yt = t.xt + xt.size();
     memcpy(slot.cfg, &t, sizeof t);
     ctx->n_tiles++;
-    if (ctx->use_tma) { int rc = encode_tile_map(ctx, t, &slot.tmap); if (rc) return rc; }
+    if (ctx->use_tma) { int rc = encode_tile_map(ctx, t, &slot.tmap, false); if (rc) return rc; }
+    if (t.fused) { int rc = encode_tile_map(ctx, t, &slot.tmap_full, true); if (rc) return rc; }
   }
   if (ctx->n_tiles == 0) return visocu_set_error(ctx, VISOCU_EINVAL, "no tile configuration fits %dx%d with nms_n = %d", g.wm, g.hm, g.n[1]);
+  return VISOCU_OK;
+}
+
+// the half-resolution image of one frame, for visocu_get_plane (the fused path never writes it)
+int visocu_make_half_image(visocu_ctx* ctx, int frame) {
+  const Geometry& g = ctx->g;
+  if (!g.half) return VISOCU_OK;
+  SlotList sl; sl.n = 1; sl.s[0] = frame;
+  dim3 bh(32, 8), gh((g.bplm / 4 + 31) / 32, (g.hm + 7) / 8, 1);
+  k_half_image<<<gh, bh, 0, ctx->stream>>>(g, ctx->frames_d, sl);
+  CU_LAUNCH_CHECK(ctx);
   return VISOCU_OK;
 }
 
 int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
   const Geometry& g = ctx->g;
   cudaStream_t st = ctx->stream;
-  if (g.half) {
+  if (g.half && !ctx->fused_half) {
     dim3 bh(32, 8), gh((g.bplm / 4 + 31) / 32, (g.hm + 7) / 8, sl.n);
     k_half_image<<<gh, bh, 0, st>>>(g, ctx->frames_d, sl);
     CU_LAUNCH_CHECK(ctx);
@@ -994,7 +1166,7 @@ int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl) {
     }
     dim3 grid(t.ntx, t.nty, sl.n);
     if (ctx->profile) CU_TRY(ctx, cudaEventRecord(ctx->pev0, st));
-    k_filter_nms<<<grid, t.threads, t.smem, st>>>(g, ctx->frames_d, sl, t, ctx->tiles[pick].tmap, ctx->use_tma);
+    k_filter_nms<<<grid, t.threads, t.smem, st>>>(g, ctx->frames_d, sl, t, ctx->tiles[pick].tmap, ctx->tiles[pick].tmap_full, ctx->use_tma);
     CU_LAUNCH_CHECK(ctx);
     if (ctx->profile) {
       // profiling mode only: this synchronises the stream after every fused launch

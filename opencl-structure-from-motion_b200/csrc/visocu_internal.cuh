@@ -37,7 +37,7 @@ struct SlotList { int n; int s[VISO_MAX_BATCH]; };
 
 #define VISO_TILE_LEVELS 3
 // one tile configuration of the fused filter+NMS kernel (csrc/features.cu: TileCfg) and its TMA descriptor
-struct visocu_tile { alignas(64) CUtensorMap tmap; alignas(8) unsigned char cfg[128]; void* tables = nullptr; };
+struct visocu_tile { alignas(64) CUtensorMap tmap; alignas(64) CUtensorMap tmap_full; alignas(8) unsigned char cfg[160]; void* tables = nullptr; };
 
 // state of a matching call whose outlier removal runs on the second stream (visocu_match_deferred / _collect)
 struct visocu_deferred {
@@ -85,6 +85,7 @@ struct visocu_ctx {
   int n_tiles = 0;
   size_t frame_stride = 0;           // bytes between the pool blocks of consecutive frame slots
   int use_tma = 0;
+  int fused_half = 0;                // half-resolution mode runs as one fused kernel (full-resolution tile staged by TMA)
   int pinv_ready = 0;                // paraboloid pseudo-inverse uploaded to constant memory (sub-pixel refinement)
   uint64_t h2d_bytes = 0, d2h_bytes = 0;   // host<->device traffic issued by this context
   int profile = 0;                   // time the fused filter+NMS launches with events (visocu_profile)
@@ -135,3 +136,4 @@ __host__ __device__ static inline int viso_cell_count(int len, int n) {
 int visocu_launch_features(visocu_ctx* ctx, const SlotList& sl);
 int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes);
 void visocu_free_tiles(visocu_ctx* ctx);
+int visocu_make_half_image(visocu_ctx* ctx, int frame);

@@ -30,6 +30,9 @@ for _ in range(reps):
     ns, nd = ctx.push_frames(frames, ptrs=ptrs, bpl_in=W, on_device=True)
 ms, nl, nf = ctx.profile_read()
 bpl = W + 15 - (W - 1) % 16
-alg = 3.0 * (bpl * H if not half else ((W // 2) + 15 - ((W // 2) - 1) % 16) * (H // 2))
+# algorithmic bytes per frame: 3 B per pixel of the padded image in full-resolution mode; in half-resolution
+# mode 1 B read + 2 B (du_full, dv_full) + 0.5 B (half-resolution du, dv) = 3.5 B per full-resolution pixel (the half image
+# is never written by the fused kernel; with VISOCU_FUSED_HALF=0 three kernels run and only the last one is timed here)
+alg = (3.5 if half else 3.0) * bpl * H
 print('frames/launch %d  launch %.4f ms  %.2f us/frame  algorithmic %.1f GB/s  (features per frame: %d sparse, %d dense)' % (
     nb, ms / nl, 1e3 * ms / nf, alg * nf / (ms * 1e-3) / 1e9, ns[0], nd[0]))
