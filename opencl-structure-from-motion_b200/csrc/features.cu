@@ -567,40 +567,45 @@ k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const _
     // createHalfResolutionImage (matcher.cpp:636-647) goes straight into the image tile that the phases below work on:
     // the half-resolution image never exists in global memory.
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
-    const uint32_t stage = (uint32_t)__cvta_generic_to_shared(sf1);
+    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(sf1);
     const uint32_t simg_sa = (uint32_t)__cvta_generic_to_shared(simg);
     const unsigned lane = tid & 31;
     const int SR = t.SR, BW = t.BW;
     const int fx0 = 2 * x_ilo;                              // full-resolution column of staging byte 0
     const int xr = t.nbox == 2 ? 2 * IS - BW : 0;           // first column of the right box, relative to fx0
-    const uint32_t right = stage + (uint32_t)(BW * SR) - (uint32_t)xr;
+    const uint32_t part_bytes = (uint32_t)(t.nbox * BW * SR);   // one staging buffer; two of them alternate
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // part p goes to buffer p & 1 and signals mbarrier p & 1; the load of part p + 1 is in flight while part p is worked on
+    auto load_part = [&](int p) {
+      const uint32_t dst = stage0 + (uint32_t)(p & 1) * part_bytes, b = bar + 8u * (uint32_t)(p & 1);
+      const int fy = 2 * (y_ilo + p * t.HP) - 2;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(part_bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          :: "r"(dst), "l"(&tmap_full), "r"(fx0), "r"(fy), "r"(slot), "r"(b) : "memory");
+      if (t.nbox == 2)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            :: "r"(dst + (uint32_t)(BW * SR)), "l"(&tmap_full), "r"(fx0 + xr), "r"(fy), "r"(slot), "r"(b) : "memory");
+    };
+    if (tid == 0) { load_part(0); if (t.P > 1) load_part(1); }
     for (int p = 0; p < t.P; p++) {
       const int hr0 = p * t.HP, hr1 = min(hr0 + t.HP, IH);  // half-resolution rows of the image tile formed by this part
       const int fy0 = 2 * (y_ilo + hr0) - 2;                // first staged full-resolution row
-      if (tid == 0) {
-        s_qn[6] = 0;
-        const uint32_t bytes = (uint32_t)(t.nbox * BW * SR);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            :: "r"(stage), "l"(&tmap_full), "r"(fx0), "r"(fy0), "r"(slot), "r"(bar) : "memory");
-        if (t.nbox == 2)
-          asm volatile(
-              "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-              :: "r"(stage + (uint32_t)(BW * SR)), "l"(&tmap_full), "r"(fx0 + xr), "r"(fy0), "r"(slot), "r"(bar) : "memory");
-      }
-      mbar_wait_or_trap(bar, (uint32_t)(p & 1));
+      const uint32_t stage = stage0 + (uint32_t)(p & 1) * part_bytes;
+      const uint32_t right = stage + (uint32_t)(BW * SR) - (uint32_t)xr;
+      mbar_wait_or_trap(bar + 8u * (uint32_t)(p & 1), (uint32_t)((p >> 1) & 1));
       // full-resolution Sobel rows of this part
       const int ry0 = max(Y.df_lo, 2 * (y_ilo + hr0)), ry1 = min(Y.df_hi, 2 * (y_ilo + hr1));
       const int nrF = max(ry1 - ry0, 0), nsF = (nrF + t.segF - 1) / t.segF;
       const int nitem = X.nwF * nsF, ncW = (nitem + 31) >> 5;
       const int nmean = (hr1 - hr0) * IW, ncB = (nmean + 127) >> 7;
-      for (int c = next_chunk(s_qn + 6, lane); c < ncW + ncB; c = next_chunk(s_qn + 6, lane)) {
+      for (int c = next_chunk(s_qn + 6 + (p & 1), lane); c < ncW + ncB; c = next_chunk(s_qn + 6 + (p & 1), lane)) {
         if (c < ncW) {
           const int item = 32 * c + (int)lane;
           if (item < nitem) {
@@ -632,7 +637,9 @@ k_filter_nms(const __grid_constant__ Geometry g, const FrameDev* frames, const _
           }
         }
       }
+      if (tid == 0) s_qn[6 + ((p + 1) & 1)] = 0;            // chunk counter of the next part (idle since the part before this one)
       __syncthreads();
+      if (tid == 0 && p + 2 < t.P) load_part(p + 2);        // this buffer is free again
     }
   } else if (use_tma) {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_bar);
@@ -1014,7 +1021,7 @@ bool make_tile_cfg(const Geometry& g, int kx, int ky, int threads, bool fused, T
     t.fused = 1;
     t.nbox = 2 * t.IS > 256 ? 2 : 1;
     t.BW = t.nbox == 2 ? 256 : 2 * t.IS;
-    const int rows_fit = (int)(t.f_bytes / (unsigned)(t.nbox * t.BW));
+    const int rows_fit = (int)(t.f_bytes / (unsigned)(2 * t.nbox * t.BW));     // two staging buffers
     int hp = std::min((rows_fit - 4) / 2, 126);
     if (hp < 4) return false;
     t.P = (t.IH + hp - 1) / hp;
@@ -1086,7 +1093,13 @@ int visocu_make_tensor_map(visocu_ctx* ctx, size_t frame_stride_bytes) {
   bool fused = g.half && ctx->use_tma;
   if (const char* env = getenv("VISOCU_FUSED_HALF")) if (env[0] == '0') fused = false;
   ctx->fused_half = fused ? 1 : 0;
-  int cand[VISO_TILE_LEVELS][3] = {{(fused ? 190 : 210) / stepA, 60 / stepA, fused ? 384 : 512}, {100 / stepA, 60 / stepA, fused ? 384 : 512}, {100 / stepA, 30 / stepA, 256}};
+  // upper limits of the tile size per level (aligning-pass cells); the cells of the image are then spread evenly over the
+  // tiles so that no tile row or column is nearly empty.  Fused half-resolution mode: 2 IS <= 480 limits the width.
+  const int pa = g.first_pass;
+  auto balanced = [](int ncells, int kmax) { kmax = std::max(kmax, 1); if (ncells <= 0) return kmax; const int nt = (ncells + kmax - 1) / kmax; return (ncells + nt - 1) / nt; };
+  int cand[VISO_TILE_LEVELS][3] = {{balanced(g.ncx[pa], (fused ? 190 : 210) / stepA), balanced(g.ncy[pa], (fused ? 80 : 60) / stepA), 512},
+                                   {balanced(g.ncx[pa], 100 / stepA), balanced(g.ncy[pa], 60 / stepA), fused ? 384 : 512},
+                                   {balanced(g.ncx[pa], 100 / stepA), balanced(g.ncy[pa], 30 / stepA), 256}};
   int ncand = VISO_TILE_LEVELS;
   if (const char* env = getenv("VISOCU_TILE")) {
     int kx = 0, ky = 0, th = 0;
