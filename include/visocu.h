@@ -83,7 +83,8 @@ int  visocu_memcpy_h2d(visocu_ctx* ctx, void* dst, const void* src, size_t bytes
  * (matcher.cpp:158-175), [half image (630-647)], fused sobel5x5 / blob5x5 / checkerboard5x5 + both
  * nonMaximumSuppression passes (filter.cpp:316-365, matcher.cpp:330-431, 684-694), computeDescriptors
  * (433-477) and the bin index of createIndexVector (870-890).  n_sparse / n_dense (may be NULL) receive the
- * record counts n?1 / n?2; the call synchronises only if they are requested. */
+ * record counts n?1 / n?2; the call reads them back and waits only if they are requested (otherwise it returns as soon as
+ * the work is enqueued, and visocu_frame_counts or the next matching call learns the counts). */
 int  visocu_push_frames(visocu_ctx* ctx, int32_t n, const int32_t* frames, const uint8_t* const* imgs,
                         int32_t bpl_in, int32_t on_device, int32_t* n_sparse, int32_t* n_dense);
 int  visocu_frame_counts(visocu_ctx* ctx, int32_t n, const int32_t* frames, int32_t* n_sparse, int32_t* n_dense);
@@ -126,14 +127,19 @@ int  visocu_match_deferred(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* j
 int  visocu_match_collect(visocu_ctx* ctx, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers);
 /* Both passes of multi-stage FLOW matching in one submission (matcher.cpp:219-233 without a host round trip): first pass on
  * the sparse features, its outlier removal, Matcher::computePriorStatistics (matcher.cpp:734-868) on the survivors - on the
- * device -, second pass on the dense features with those ranges, refinement (0 or 1), outlier removal.  out1 / out2 receive
- * the two lists, done1 / done2 say whether the outlier removal of the list ran on the device (if done1[j] is 0 the second
- * list of job j is meaningless: the caller votes on list 1 itself and repeats the second pass with visocu_match);
- * ranges_out[j] (optional, u_bins * v_bins entries) receives the prior ranges.  At most 128 jobs. */
+ * device -, second pass on the dense features with those ranges, refinement (0 or 1), outlier removal.  The kernels take
+ * the record counts of the frames from device memory and everything is sized by the capacity of the record lists, so the
+ * frames may have been pushed without reading their counts back (visocu_push_frames with null count pointers): pushing
+ * and matching a frame is then ONE submission, and the wait at the end of this call the only one.  The results are
+ * written by the last kernel into pinned memory owned by the context: list1[j] / list2[j] point into it and stay valid
+ * until the next matching call on this context.  done1 / done2 say whether the outlier removal of the list ran on the
+ * device (if done1[j] is 0 the second list of job j is meaningless: the caller votes on list 1 itself and repeats the second
+ * pass with visocu_match); ranges_out[j] (optional, u_bins * v_bins entries) receives the prior ranges; counts (optional,
+ * 4 per job) the sparse and dense record counts of f1p and of f1c.  At most 128 jobs. */
 int  visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine,
-                        visocu_pmatch* const* out1, const int32_t* cap1, int32_t* n1, int32_t* done1,
-                        visocu_pmatch* const* out2, const int32_t* cap2, int32_t* n2, int32_t* done2,
-                        visocu_range* const* ranges_out);
+                        const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
+                        const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
+                        visocu_range* const* ranges_out, int32_t* counts);
 /* Matcher::removeOutliers alone on caller-supplied match lists (host memory, compacted in place).  status[j] = 0: done,
  * 1: list unchanged, not handled by the device path (see visocu_match). */
 int  visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t method, visocu_pmatch* const* inout, const int32_t* n,

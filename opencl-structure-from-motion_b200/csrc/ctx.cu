@@ -159,6 +159,8 @@ extern "C" void visocu_destroy(visocu_ctx* ctx) {
   if (ctx->scratch2) cudaFree(ctx->scratch2);
   if (ctx->d_ranges) cudaFree(ctx->d_ranges);
   if (ctx->pin_ranges) cudaFreeHost(ctx->pin_ranges);
+  if (ctx->deliver) cudaFreeHost(ctx->deliver);
+  if (ctx->deliver2) cudaFreeHost(ctx->deliver2);
   if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->img_stage) cudaFree(ctx->img_stage);
@@ -382,6 +384,24 @@ extern "C" int visocu_launch_count(const visocu_ctx* ctx, uint64_t* n) {
   return VISOCU_OK;
 }
 
+// Row-wise copy of a batch of images into the 16-byte-stride frame planes (matcher.cpp:163-175); pad columns stay zero.
+// One launch for all frames of a push: a source row starts at any byte, a destination word is assembled from four bytes.
+struct RepitchArgs { const uint8_t* src[VISO_MAX_BATCH]; };
+__global__ void __launch_bounds__(256) k_repitch(Geometry g, const FrameDev* frames, SlotList sl, RepitchArgs a, int bpl_in) {
+  const uint8_t* __restrict__ src = a.src[blockIdx.y];
+  uint8_t* dst = frames[sl.s[blockIdx.y]].img;
+  const int wpr = g.bpl >> 2;
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < wpr * g.h; idx += gridDim.x * 256) {
+    const int y = idx / wpr, x = 4 * (idx - y * wpr);
+    const uint8_t* r = src + (size_t)y * bpl_in + x;
+    uint32_t v = 0;
+    if (x + 3 < g.w) v = (uint32_t)r[0] | ((uint32_t)r[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)r[3] << 24);
+    else
+      for (int k = 0; k < 4; k++) if (x + k < g.w) v |= (uint32_t)r[k] << (8 * k);
+    *(uint32_t*)(dst + (size_t)y * g.bpl + x) = v;
+  }
+}
+
 static int check_frames(visocu_ctx* ctx, int32_t n, const int32_t* frames) {
   if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
   if (n <= 0 || !frames) return visocu_set_error(ctx, VISOCU_EINVAL, "empty frame list");
@@ -433,6 +453,8 @@ extern "C" int visocu_push_frames(visocu_ctx* ctx, int32_t n, const int32_t* fra
         ctx->img_stage_bytes = want;
       }
     }
+    RepitchArgs ra;
+    bool repitch = false;
     for (int i = 0; i < sl.n; i++) {
       int f = frames[start + i];
       if (!imgs[start + i]) return visocu_set_error(ctx, VISOCU_EINVAL, "null image %d", start + i);
@@ -441,19 +463,30 @@ extern "C" int visocu_push_frames(visocu_ctx* ctx, int32_t n, const int32_t* fra
       // PCIe as ONE contiguous transfer into a staging area and is re-pitched on the device: a pitched host-to-device
       // copy of 376 unaligned 1241-byte rows is several times slower than the 0.47 MB it moves.
       if (on_device) {
-        CU_TRY(ctx, cudaMemcpy2DAsync(ctx->frames_h[f].img, g.bpl, imgs[start + i], bpl_in, g.w, g.h, cudaMemcpyDeviceToDevice, ctx->stream));
+        ra.src[i] = imgs[start + i]; repitch = true;
       } else if (bpl_in == g.bpl) {
         CU_COPY(ctx, ctx->frames_h[f].img, imgs[start + i], (size_t)bpl_in * g.h, cudaMemcpyHostToDevice);
       } else {
         uint8_t* stage = ctx->img_stage + (size_t)i * stage_stride;
         CU_COPY(ctx, stage, imgs[start + i], (size_t)bpl_in * (g.h - 1) + g.w, cudaMemcpyHostToDevice);
-        CU_TRY(ctx, cudaMemcpy2DAsync(ctx->frames_h[f].img, g.bpl, stage, bpl_in, g.w, g.h, cudaMemcpyDeviceToDevice, ctx->stream));
+        ra.src[i] = stage; repitch = true;
       }
       ctx->frame_valid[f] = 1;
     }
+    if (repitch) {
+      int gx = (g.bpl / 4 * g.h + 255) / 256; if (gx > 64) gx = 64;
+      k_repitch<<<dim3(gx, sl.n), 256, 0, ctx->stream>>>(g, ctx->frames_d, sl, ra, bpl_in);
+      CU_LAUNCH_CHECK(ctx);
+    }
     if (!ctx->counts_stage) CU_TRY(ctx, cudaMalloc(&ctx->counts_stage, VISO_MAX_BATCH * 16));
     if ((rc = visocu_launch_features(ctx, sl))) return rc;
-    // the host needs the record counts to size the matching launches: one small read-back per launch
+    if (!n_sparse && !n_dense) {
+      // Lazy mode: nobody asked for the record counts, so nothing is read back and nothing is waited for.  The matching
+      // call that follows takes the counts from device memory (visocu_match_fused) or fetches them (visocu_frame_counts).
+      for (int i = 0; i < sl.n; i++) { ctx->h_counts[2 * (size_t)sl.s[i]] = -1; ctx->h_counts[2 * (size_t)sl.s[i] + 1] = -1; }
+      continue;
+    }
+    // the caller wants the record counts: one small read-back per launch
     if ((rc = visocu_ensure_pinned(ctx, (size_t)sl.n * 16))) return rc;
     int32_t* stage = (int32_t*)ctx->pinned;
     CU_COPY(ctx, stage, ctx->counts_stage, (size_t)sl.n * 16, cudaMemcpyDeviceToHost);
@@ -476,6 +509,7 @@ extern "C" int visocu_get_features(visocu_ctx* ctx, int32_t frame, int32_t pass,
   if (rc) return rc;
   if (pass < 0 || pass > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "pass must be 0 or 1");
   if (!ctx->frame_valid[frame]) return visocu_set_error(ctx, VISOCU_ESTATE, "frame %d holds no features", frame);
+  if (ctx->h_counts[2 * (size_t)frame] < 0) { if ((rc = visocu_frame_counts(ctx, 1, &frame, nullptr, nullptr))) return rc; }
   int32_t n = ctx->h_counts[2 * (size_t)frame + pass];
   if (n_out) *n_out = n;
   if (!out12) return VISOCU_OK;

@@ -41,7 +41,8 @@ struct MatchJob {
   int has_tr, pad2;
   const uint8_t* du[4];              // planes used by the refinement (full resolution)
   const uint8_t* dv[4];
-  int nq, pad;
+  int nq, dyn;                       // dyn: nq is only the capacity, the real count comes from cnt[] (device memory)
+  const int32_t* cnt[4];             // record counters of the four sets for this pass (null = set not used)
 };
 
 __device__ __forceinline__ int bin_index(const Geometry& g, int u, int v) {
@@ -49,6 +50,15 @@ __device__ __forceinline__ int bin_index(const Geometry& g, int u, int v) {
   int ub = min((int)floorf((float)u / bs), g.ub - 1);
   int vb = min((int)floorf((float)v / bs), g.vb - 1);
   return vb * g.ub + ub;
+}
+
+// number of queries of a job.  Lazy mode (the host has not read the record counts back): taken from the frames' counters,
+// with the reference's rule that nothing is matched if a needed set is empty (matcher.cpp:190-212).
+__device__ __forceinline__ int job_nq(const MatchJob& J, int method) {
+  if (!J.dyn) return J.nq;
+  const int a = J.cnt[0] ? *J.cnt[0] : 1, b = J.cnt[1] ? *J.cnt[1] : 1, c = J.cnt[2] ? *J.cnt[2] : 1, d = J.cnt[3] ? *J.cnt[3] : 1;
+  if (a == 0 || b == 0 || c == 0 || d == 0) return 0;
+  return min(method == 2 ? a : c, J.nq);
 }
 
 // one hop: best candidate in set B for feature i1 of set A (all G lanes of the group call this together)
@@ -172,9 +182,12 @@ __device__ __forceinline__ int find_match_predicted(const Geometry& g, const Set
 __global__ void __launch_bounds__(MATCH_THREADS) k_match(Geometry g, const MatchJob* jobs, int method, int use_prior, uint64_t* stats) {
   const MatchJob& J = jobs[blockIdx.y];
   const int sub = threadIdx.x % G;
-  const int i = blockIdx.x * (MATCH_THREADS / G) + threadIdx.x / G;
-  const bool active = i < J.nq;
+  const int nq = job_nq(J, method);
   unsigned n_cand = 0, n_scan = 0;
+  // a block takes 32 queries at a time; the grid covers all of them unless it was sized by the capacity (lazy mode)
+  for (int base = blockIdx.x * (MATCH_THREADS / G); base < nq; base += gridDim.x * (MATCH_THREADS / G)) {
+  const int i = base + threadIdx.x / G;
+  const bool active = i < nq;
   int4 res = make_int4(0, 0, 0, 0);
   if (method == 0) {
     int stat_bin = 0;
@@ -232,6 +245,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(Geometry g, const Match
     res = make_int4(i2p, i2c, i1c, ok);
   }
   if (active && sub == 0) J.res[i] = res;
+  }
   // work counters: one atomic per warp
   for (int o = 16; o; o >>= 1) { n_cand += __shfl_xor_sync(0xFFFFFFFFu, n_cand, o); n_scan += __shfl_xor_sync(0xFFFFFFFFu, n_scan, o); }
   if ((threadIdx.x & 31) == 0 && (n_cand | n_scan)) {
@@ -241,8 +255,8 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match(Geometry g, const Match
 }
 
 // accepted-and-kept flag of query i (identical in the count and the emit kernel)
-__device__ __forceinline__ int keep_flag(const MatchJob& J, int method, int i) {
-  if (i >= J.nq) return 0;
+__device__ __forceinline__ int keep_flag(const MatchJob& J, int method, int i, int nq) {
+  if (i >= nq) return 0;
   if (!J.res[i].w) return 0;
   if (method == 2) return 1;                       // flow and stereo keep one match per current-left pixel
   const int2 uv = *(const int2*)(J.s[2].rec + (size_t)i * 12);
@@ -256,8 +270,9 @@ __device__ __forceinline__ int keep_flag(const MatchJob& J, int method, int i) {
 
 __global__ void __launch_bounds__(CHUNK) k_match_count(const MatchJob* jobs, int method) {
   const MatchJob& J = jobs[blockIdx.y];
-  if ((int)blockIdx.x * CHUNK >= J.nq && blockIdx.x > 0) return;
-  int f = keep_flag(J, method, blockIdx.x * CHUNK + threadIdx.x);
+  const int nq = job_nq(J, method);
+  if ((int)blockIdx.x * CHUNK >= nq && blockIdx.x > 0) return;
+  int f = keep_flag(J, method, blockIdx.x * CHUNK + threadIdx.x, nq);
   __shared__ int wsum[32];
   for (int o = 16; o; o >>= 1) f += __shfl_xor_sync(0xFFFFFFFFu, f, o);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = f;
@@ -271,7 +286,8 @@ __global__ void __launch_bounds__(CHUNK) k_match_count(const MatchJob* jobs, int
 
 __global__ void __launch_bounds__(CHUNK) k_match_emit(const MatchJob* jobs, int method) {
   const MatchJob& J = jobs[blockIdx.y];
-  const int nchunk = (J.nq + CHUNK - 1) / CHUNK;
+  const int nq = job_nq(J, method);
+  const int nchunk = (nq + CHUNK - 1) / CHUNK;
   if ((int)blockIdx.x >= nchunk) {
     if (nchunk == 0 && blockIdx.x == 0 && threadIdx.x == 0) *J.n_out = 0;
     return;
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(CHUNK) k_match_emit(const MatchJob* jobs, int 
   const int base = s_base;
   __syncthreads();
   const int i = blockIdx.x * CHUNK + tid;
-  const int f = keep_flag(J, method, i);
+  const int f = keep_flag(J, method, i, nq);
   int incl = f;
   for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
   if (lane == 31) wsum[wid] = incl;
@@ -493,7 +509,7 @@ int upload_pinv(visocu_ctx* ctx) {
   return VISOCU_OK;
 }
 
-int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJob& J) {
+int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJob& J, bool dyn = false) {
   const int ids[4] = {q.f1p, q.f2p, q.f1c, q.f2c};
   const bool need[4] = {method != 1, method == 2, true, method != 0};
   memset(&J, 0, sizeof J);
@@ -504,7 +520,8 @@ int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJ
     if (!ctx->frame_valid[f]) return visocu_set_error(ctx, VISOCU_ESTATE, "frame %d holds no features", f);
     const FrameDev& F = ctx->frames_h[f];
     J.s[k].rec = F.rec[pass]; J.s[k].bin_start = F.bin_start[pass]; J.s[k].bin_ent = F.bin_ent[pass];
-    J.s[k].n = ctx->h_counts[2 * (size_t)f + pass];
+    J.s[k].n = dyn ? ctx->g.cap[pass] : ctx->h_counts[2 * (size_t)f + pass];
+    if (dyn) J.cnt[k] = F.counts + pass;
     J.du[k] = ctx->g.half ? F.du_full : F.du;
     J.dv[k] = ctx->g.half ? F.dv_full : F.dv;
   }
@@ -578,7 +595,7 @@ struct ScratchSwap {
 static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
                       int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
                       visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers, int mode,
-                      const uint8_t* dev_ranges = nullptr, size_t dev_ranges_stride = 0) {
+                      const uint8_t* dev_ranges = nullptr, size_t dev_ranges_stride = 0, bool dyn = false) {
   const bool deferred = mode != 0;                   // no result is delivered by this call
   const bool second_set = mode == 1 || mode == 3;
   if (!ctx) return VISOCU_EINVAL;
@@ -596,6 +613,16 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const Geometry& g = ctx->g;
   const int nstat = g.ub * g.vb;
+  if (!dyn) {
+    // record counts the host has not read back yet (frames pushed without count pointers): fetch them now
+    std::vector<int32_t> unknown;
+    for (int j = 0; j < n_jobs; j++) {
+      const int ids[4] = {jobs[j].f1p, jobs[j].f2p, jobs[j].f1c, jobs[j].f2c};
+      for (int k = 0; k < 4; k++)
+        if (ids[k] >= 0 && ids[k] < ctx->n_frames && ctx->h_counts[2 * (size_t)ids[k]] < 0) unknown.push_back(ids[k]);
+    }
+    if (!unknown.empty()) { int rc0 = visocu_frame_counts(ctx, (int32_t)unknown.size(), unknown.data(), nullptr, nullptr); if (rc0) return rc0; }
+  }
   for (int start = 0; start < n_jobs; start += VISO_MAX_BATCH) {
     const int nb = n_jobs - start < VISO_MAX_BATCH ? n_jobs - start : VISO_MAX_BATCH;
     std::vector<MatchJob> hj(nb);
@@ -603,13 +630,13 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
     std::vector<RoJob> rj(ro ? nb : 0);
     int maxq = 0;
     for (int j = 0; j < nb; j++) {
-      int rc = fill_job(ctx, jobs[start + j], method, pass, hj[j]);
+      int rc = fill_job(ctx, jobs[start + j], method, pass, hj[j], dyn);
       if (rc) return rc;
       bool empty = false;
       const bool need[4] = {method != 1, method == 2, true, method != 0};
       for (int k = 0; k < 4; k++) if (need[k] && hj[j].s[k].n == 0) empty = true;
       const int nq = empty ? 0 : (method == 2 ? hj[j].s[0].n : hj[j].s[2].n);
-      hj[j].nq = nq;
+      hj[j].nq = nq; hj[j].dyn = dyn ? 1 : 0;
       if (nq > maxq) maxq = nq;
       if (use_prior && !dev_ranges && !ranges[start + j]) return visocu_set_error(ctx, VISOCU_EINVAL, "job %d has no ranges", start + j);
     }
@@ -645,7 +672,7 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
     if (dedupe) { o_keys = off; off += align_up(kstride * 4 * nb, 256); }
     int rc = visocu_ensure_scratch(ctx, off);
     if (rc) return rc;
-    const bool stage_lists = ostride * nb <= ((size_t)64 << 20);                     // else copy list by list to the caller
+    const bool stage_lists = !dyn && ostride * nb <= ((size_t)64 << 20);             // else copy list by list to the caller (lazy mode: the deliver kernel)
     const size_t p_words = align_up(hdr_bytes, 256), p_lists = p_words + align_up(words_bytes, 256);
     const size_t p_keys = p_lists + (stage_lists ? ostride * nb : 0);
     if ((rc = visocu_ensure_pinned(ctx, p_keys + (dedupe ? kstride * 5 * nb : 0)))) return rc;
@@ -677,7 +704,9 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
     CU_COPY(ctx, sb, pin, hdr_bytes, cudaMemcpyHostToDevice);
     const MatchJob* dj = (const MatchJob*)(sb + h_mj);
     if (maxq > 0) {
-      dim3 gm((maxq + MATCH_THREADS / G - 1) / (MATCH_THREADS / G), nb);
+      int gmx = (maxq + MATCH_THREADS / G - 1) / (MATCH_THREADS / G);
+      if (dyn && gmx > 160) gmx = 160;                    // sized by the capacity: the blocks stride over the real queries
+      dim3 gm(gmx, nb);
       k_match<<<gm, MATCH_THREADS, 0, ctx->stream>>>(g, dj, method, use_prior, ctx->d_stats);
       CU_LAUNCH_CHECK(ctx);
     }
@@ -688,6 +717,7 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
     CU_LAUNCH_CHECK(ctx);
     if (refine && maxq > 0) {
       int gx = (maxq + 7) / 8; if (gx > 4096) gx = 4096;
+      if (dyn && gx > 592) gx = 592;                      // sized by the capacity: the warps stride over the real list
       dim3 gr(gx, nb);
       k_refine<<<gr, 256, 0, ctx->stream>>>(g, dj, method, refine, nullptr, 0, nullptr);
       CU_LAUNCH_CHECK(ctx);
@@ -718,13 +748,23 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
     }
     if (mode >= 2) {
       // one pass of a fused call: outlier removal and the read-back of the result words queued on the main stream
-      if (!stage_lists) return visocu_set_error(ctx, VISOCU_EINVAL, "fused matching: lists too large for the staging area");
-      if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, maxq, ctx->stream))) return rc;
+      // Shared memory of the outlier kernel follows the longest list.  Lazy mode: flow matches are one-to-one, so a list is
+      // no longer than the feature list of the previous frame, whose count arrived with the previous step's results.
+      int max_list = maxq;
+      if (dyn) {
+        int bound = 0;
+        for (int j = 0; j < nb && bound >= 0; j++) {
+          const int c = ctx->h_counts[2 * (size_t)jobs[start + j].f1p + pass];
+          bound = c < 0 ? -1 : (c > bound ? c : bound);
+        }
+        if (bound >= 0 && bound < max_list) max_list = bound;
+      }
+      if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, max_list, ctx->stream))) return rc;
       ctx->d2h_bytes += words_bytes;
       CU_TRY(ctx, cudaMemcpyAsync(pin + p_words, sb + o_words, words_bytes, cudaMemcpyDeviceToHost, ctx->stream));
       visocu_deferred& st = ctx->part[mode - 2];
       st.pending = true; st.nb = nb; st.pin_words = pin + p_words; st.pin_lists = pin + p_lists;
-      st.dev_lists = sb + o_list2; st.ostride = ostride; st.dev_words = (const int32_t*)(sb + o_words);
+      st.dev_lists = sb + o_list2; st.ostride = ostride; st.dev_words = (const int32_t*)(sb + o_words); st.dev_jobs = dj;
       return VISOCU_OK;
     }
     if (mode == 1) {
@@ -875,13 +915,42 @@ extern "C" int visocu_match_collect(visocu_ctx* ctx, visocu_pmatch* const* out, 
   return match_tail(ctx, ctx->deferred, out, cap, n_out, outliers, 1);
 }
 
+// Results of a fused call, written by the GPU itself into mapped pinned host memory: per job a header (the 16 result words
+// of each pass and the record counts of the two frames) and the two survivor lists.  One kernel, one CTA per job; the
+// host needs no second round trip to learn how many records to copy.
+struct DeliverArgs {
+  const MatchJob* jobs2;                      // second-pass jobs: cnt[0] / cnt[2] point at the dense counters of f1p / f1c
+  const int32_t* words1; const int32_t* words2;
+  const uint8_t* lists1; const uint8_t* lists2;
+  size_t ostride1, ostride2;
+  uint8_t* dst; size_t dstride, off1, off2;
+  int with_lists;
+};
+__global__ void __launch_bounds__(256) k_deliver(DeliverArgs a) {
+  const int j = blockIdx.x, tid = threadIdx.x;
+  uint8_t* out = a.dst + a.dstride * j;
+  int32_t* hdr = (int32_t*)out;
+  if (tid < 16) { hdr[tid] = a.words1[16 * j + tid]; hdr[16 + tid] = a.words2[16 * j + tid]; }
+  if (tid >= 32 && tid < 38) {
+    // sparse, dense, overflow flag of the previous and of the current frame (FrameDev::counts)
+    const int32_t* c = (tid < 35 ? a.jobs2[j].cnt[0] : a.jobs2[j].cnt[2]) - 1;
+    hdr[tid] = c[(tid - 32) % 3];
+  }
+  if (!a.with_lists) return;
+  const int n1 = a.words1[16 * j], n2 = a.words2[16 * j];
+  const uint4* s1 = (const uint4*)(a.lists1 + a.ostride1 * j); uint4* d1 = (uint4*)(out + a.off1);
+  for (int i = tid; i < 3 * n1; i += 256) d1[i] = s1[i];
+  const uint4* s2 = (const uint4*)(a.lists2 + a.ostride2 * j); uint4* d2 = (uint4*)(out + a.off2);
+  for (int i = tid; i < 3 * n2; i += 256) d2[i] = s2[i];
+}
+
 extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine,
-                                  visocu_pmatch* const* out1, const int32_t* cap1, int32_t* n1, int32_t* done1,
-                                  visocu_pmatch* const* out2, const int32_t* cap2, int32_t* n2, int32_t* done2,
-                                  visocu_range* const* ranges_out) {
+                                  const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
+                                  const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
+                                  visocu_range* const* ranges_out, int32_t* counts) {
   if (!ctx) return VISOCU_EINVAL;
   if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
-  if (n_jobs <= 0 || n_jobs > VISO_MAX_BATCH || !jobs || !out1 || !cap1 || !n1 || !done1 || !out2 || !cap2 || !n2 || !done2)
+  if (n_jobs <= 0 || n_jobs > VISO_MAX_BATCH || !jobs || !list1 || !n1 || !done1 || !list2 || !n2 || !done2)
     return visocu_set_error(ctx, VISOCU_EINVAL, "bad fused match arguments (at most %d jobs)", VISO_MAX_BATCH);
   if (ctx->g.first_pass != 0) return visocu_set_error(ctx, VISOCU_EINVAL, "fused matching needs multi_stage");
   if (refine < 0 || refine > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "fused matching: refine must be 0 or 1");
@@ -901,9 +970,23 @@ extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_
     ctx->pin_ranges = nullptr;
     CU_TRY(ctx, cudaMallocHost(&ctx->pin_ranges, rstride * VISO_MAX_BATCH));
   }
+  // delivery area: header + both lists at their capacity, per job
+  const size_t off1 = 256, off2 = off1 + align_up((size_t)(g.cap[0] + 1) * 48, 256);
+  // Small geometries: the lists travel with the header (zero-copy writes of the last kernel, one wait).  Large ones (4K:
+  // over a hundred megabytes of capacity per job): only the header does, and the lists are copied once their lengths are known.
+  const bool zero_copy = off2 + align_up((size_t)(g.cap[1] + 1) * 48, 256) <= ((size_t)8 << 20);
+  const size_t dstride = zero_copy ? off2 + align_up((size_t)(g.cap[1] + 1) * 48, 256) : 256;
+  if (dstride * n_jobs > ctx->deliver_bytes) {
+    CU_TRY(ctx, visocu_stream_wait(ctx));
+    if (ctx->deliver) cudaFreeHost(ctx->deliver);
+    ctx->deliver = nullptr; ctx->deliver_bytes = 0;
+    CU_TRY(ctx, cudaHostAlloc(&ctx->deliver, dstride * n_jobs, cudaHostAllocMapped));
+    CU_TRY(ctx, cudaHostGetDevicePointer(&ctx->deliver_dev, ctx->deliver, 0));
+    ctx->deliver_bytes = dstride * n_jobs;
+  }
   uint8_t* d_rng = (uint8_t*)ctx->d_ranges;
-  // first pass (sparse features, no prior) and its outlier removal
-  int rc = match_impl(ctx, n_jobs, jobs, 0, 0, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 2);
+  // first pass (sparse features, no prior) and its outlier removal; the record counts are taken from device memory
+  int rc = match_impl(ctx, n_jobs, jobs, 0, 0, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 2, nullptr, 0, true);
   if (rc) return rc;
   // prior ranges from its survivors, on the device
   const visocu_deferred& A = ctx->part[0];
@@ -913,20 +996,63 @@ extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_
                                                                    (float*)(d_rng + rstride * n_jobs), use_smem);
   CU_LAUNCH_CHECK(ctx);
   // second pass (dense features, the ranges as prior), refinement, outlier removal
-  rc = match_impl(ctx, n_jobs, jobs, 0, 1, 1, nullptr, nullptr, refine, nullptr, nullptr, nullptr, nullptr, 3, d_rng, rstride);
+  rc = match_impl(ctx, n_jobs, jobs, 0, 1, 1, nullptr, nullptr, refine, nullptr, nullptr, nullptr, nullptr, 3, d_rng, rstride, true);
   if (rc) return rc;
+  const visocu_deferred& B = ctx->part[1];
+  DeliverArgs da;
+  da.jobs2 = (const MatchJob*)B.dev_jobs; da.words1 = A.dev_words; da.words2 = B.dev_words;
+  da.lists1 = A.dev_lists; da.lists2 = B.dev_lists; da.ostride1 = A.ostride; da.ostride2 = B.ostride;
+  da.dst = (uint8_t*)ctx->deliver_dev; da.dstride = dstride; da.off1 = off1; da.off2 = off2; da.with_lists = zero_copy ? 1 : 0;
+  k_deliver<<<n_jobs, 256, 0, ctx->stream>>>(da);
+  CU_LAUNCH_CHECK(ctx);
   if (ranges_out) {
     ctx->d2h_bytes += rstride * n_jobs;
     CU_TRY(ctx, cudaMemcpyAsync(ctx->pin_ranges, d_rng, rstride * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  CU_TRY(ctx, visocu_stream_wait(ctx));
+  CU_TRY(ctx, visocu_stream_wait(ctx));                 // the only wait of a push + match step
   ctx->part[0].pending = ctx->part[1].pending = false;
-  int maxn1 = 0, maxn2 = 0;
-  if ((rc = match_tail_issue(ctx, ctx->part[0], cap1, n1, done1, 0, &maxn1))) return rc;
-  if ((rc = match_tail_issue(ctx, ctx->part[1], cap2, n2, done2, 0, &maxn2))) return rc;
-  if (maxn1 > 0 || maxn2 > 0) CU_TRY(ctx, visocu_stream_wait(ctx));
-  if (maxn1 > 0) match_tail_deliver(ctx->part[0], out1, n1, maxn1);
-  if (maxn2 > 0) match_tail_deliver(ctx->part[1], out2, n2, maxn2);
+  int overflow = -1;
+  for (int j = 0; j < n_jobs; j++) {
+    const uint8_t* base = (const uint8_t*)ctx->deliver + dstride * j;
+    const int32_t* hdr = (const int32_t*)base;
+    for (int p = 0; p < 2; p++) {
+      const int32_t* w = hdr + 16 * p;
+      const int n = w[0], status = w[1];
+      (p ? n2 : n1)[j] = n; (p ? done2 : done1)[j] = status == 0 ? 1 : 0;
+      if (status == 0 && n > 3) { for (int k = 0; k < 4; k++) ctx->ro_ns[k] += (uint64_t)w[4 + k]; ctx->ro_jobs++; }
+      else if (status != 0) { ctx->ro_declined++; ctx->ro_reason[status & 3]++; ctx->ro_declined_n += (uint64_t)w[3]; }
+      ctx->d2h_bytes += 64 + (uint64_t)n * 48;
+    }
+    if (zero_copy) { list1[j] = (const visocu_pmatch*)(base + off1); list2[j] = (const visocu_pmatch*)(base + off2); }
+    const int fr[2] = {jobs[j].f1p, jobs[j].f1c};
+    for (int k = 0; k < 2; k++) {
+      ctx->h_counts[2 * (size_t)fr[k] + 0] = hdr[32 + 3 * k]; ctx->h_counts[2 * (size_t)fr[k] + 1] = hdr[33 + 3 * k];
+      if (hdr[34 + 3 * k]) overflow = fr[k];
+      if (counts) { counts[4 * j + 2 * k] = hdr[32 + 3 * k]; counts[4 * j + 2 * k + 1] = hdr[33 + 3 * k]; }
+    }
+    ctx->d2h_bytes += 24;
+  }
+  if (overflow >= 0) return visocu_set_error(ctx, VISOCU_ECAPACITY, "feature list of frame %d overflowed", overflow);
+  if (!zero_copy) {
+    size_t total = 0;
+    for (int j = 0; j < n_jobs; j++) total += align_up((size_t)n1[j] * 48 + 48, 256) + align_up((size_t)n2[j] * 48 + 48, 256);
+    if (total > ctx->deliver2_bytes) {
+      if (ctx->deliver2) cudaFreeHost(ctx->deliver2);
+      ctx->deliver2 = nullptr; ctx->deliver2_bytes = 0;
+      CU_TRY(ctx, cudaMallocHost(&ctx->deliver2, total + total / 4));
+      ctx->deliver2_bytes = total + total / 4;
+    }
+    uint8_t* dst = (uint8_t*)ctx->deliver2;
+    for (int j = 0; j < n_jobs; j++) {
+      list1[j] = (const visocu_pmatch*)dst;
+      if (n1[j] > 0) CU_TRY(ctx, cudaMemcpyAsync(dst, A.dev_lists + A.ostride * j, (size_t)n1[j] * 48, cudaMemcpyDeviceToHost, ctx->stream));
+      dst += align_up((size_t)n1[j] * 48 + 48, 256);
+      list2[j] = (const visocu_pmatch*)dst;
+      if (n2[j] > 0) CU_TRY(ctx, cudaMemcpyAsync(dst, B.dev_lists + B.ostride * j, (size_t)n2[j] * 48, cudaMemcpyDeviceToHost, ctx->stream));
+      dst += align_up((size_t)n2[j] * 48 + 48, 256);
+    }
+    CU_TRY(ctx, visocu_stream_wait(ctx));
+  }
   if (ranges_out)
     for (int j = 0; j < n_jobs; j++)
       if (ranges_out[j]) memcpy(ranges_out[j], (const uint8_t*)ctx->pin_ranges + rstride * j, (size_t)nbin * sizeof(visocu_range));

@@ -46,6 +46,7 @@ struct visocu_deferred {
   uint8_t* pin_words = nullptr; uint8_t* pin_lists = nullptr;   // pinned: 16 result words per job, staged lists
   const uint8_t* dev_lists = nullptr; size_t ostride = 0;       // device: survivor lists, uniform stride
   const int32_t* dev_words = nullptr;                           // device: the 16 result words per job
+  const void* dev_jobs = nullptr;                               // device: the MatchJob array of the pass
 };
 
 struct visocu_ctx {
@@ -57,6 +58,8 @@ struct visocu_ctx {
   cudaEvent_t ev_fork = nullptr;
   visocu_deferred deferred;
   visocu_deferred part[2];           // the two passes of a fused call (visocu_match_fused)
+  void* deliver2 = nullptr; size_t deliver2_bytes = 0;        // pinned landing area of the lists when they are too large for that
+  void* deliver = nullptr; void* deliver_dev = nullptr; size_t deliver_bytes = 0;     // mapped pinned memory the last kernel of a fused call writes the results to
   void* d_ranges = nullptr; size_t d_ranges_bytes = 0; void* pin_ranges = nullptr;   // prior ranges computed on the device between the passes
   void* scratch2 = nullptr; size_t scratch2_bytes = 0;
   void* pinned2 = nullptr;  size_t pinned2_bytes = 0;

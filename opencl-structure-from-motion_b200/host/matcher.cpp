@@ -71,6 +71,26 @@ Matcher::Matcher(parameters param) : param(param), ctx(0), owns_ctx(true), slot_
 
 void Matcher::seedShuffle(unsigned seed) { srandom_r(seed, &rnd_data); }
 
+bool Matcher::lazyCounts() const {
+  static const bool on = [] { const char* e = getenv("VISOB_LAZY"); return !(e && e[0] == '0'); }();
+  static const bool fused = [] { const char* e = getenv("VISOB_FUSED"); return !(e && e[0] == '0'); }();
+  return on && fused && param.multi_stage && refineMode() != 2 && visob::device_outliers();
+}
+
+// record counts that were not read back at push time (-1): fetch them from the device
+void Matcher::syncCounts() {
+  int32_t frames[4], which[4], n = 0;
+  for (int k = 0; k < 4; k++)
+    if (slot[k] >= 0 && (n_feat[k] < 0 || n_feat[4 + k] < 0)) { frames[n] = slot[k]; which[n] = k; n++; }
+  if (n == 0 || !ctx) return;
+  int32_t ns[4], nd[4];
+  if (visocu_frame_counts(ctx, n, frames, ns, nd) != VISOCU_OK) {
+    std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+    for (int i = 0; i < n; i++) { ns[i] = 0; nd[i] = 0; }
+  }
+  for (int i = 0; i < n; i++) { n_feat[which[i]] = ns[i]; n_feat[4 + which[i]] = nd[i]; }
+}
+
 Matcher::~Matcher() {
   if (ctx && owns_ctx) visocu_destroy(ctx);
 }
@@ -118,9 +138,12 @@ void Matcher::push(const uint8_t* I1, const uint8_t* I2, uint32_t* dims, bool re
   int32_t frames[2];
   if (!pushPrepare(I1, I2, dims, replace, frames)) return;
   const uint8_t* imgs[2] = {I1, I2};
-  int32_t ns[2] = {0, 0}, nd[2] = {0, 0};
+  int32_t ns[2] = {-1, -1}, nd[2] = {-1, -1};
   const int nimg = I2 ? 2 : 1;
-  const bool ok = visocu_push_frames(ctx, nimg, frames, imgs, (int32_t)dims[2], on_device ? 1 : 0, ns, nd) == VISOCU_OK;
+  // flow matching of a monocular sequence goes through the fused call, which needs no record counts on the host: the
+  // push then returns without waiting for the GPU (the counts are fetched lazily if somebody asks, syncCounts)
+  const bool lazy = lazyCounts() && !I2;
+  const bool ok = visocu_push_frames(ctx, nimg, frames, imgs, (int32_t)dims[2], on_device ? 1 : 0, lazy ? 0 : ns, lazy ? 0 : nd) == VISOCU_OK;
   if (!ok) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
   pushFinish(ok, I2 != 0, ns, nd);
 }
@@ -200,9 +223,10 @@ bool Matcher::matching(int pass, vector<p_match>& out, int32_t method, bool use_
 }
 
 void Matcher::matchFeatures(int32_t method, Matrix* Tr_delta) {
+  has_tr = false;
+  if (!fusedAvailable(*this, method)) syncCounts();
   if (!matchBegin(method)) return;
   // motion-predicted search (quad matching only, matcher.cpp:1112-1138): rows 0..2 of Tr_delta go to the kernel
-  has_tr = false;
   if (Tr_delta && method == 2 && Tr_delta->m >= 3 && Tr_delta->n >= 4) {
     has_tr = true;
     for (int r = 0; r < 3; r++)
@@ -216,6 +240,8 @@ void Matcher::matchFeatures(int32_t method, Matrix* Tr_delta) {
     fusedMatch(ctx, vector<Matcher*>(1, this), method);
     return;
   }
+  p_matched_1.clear();
+  p_matched_2.clear();
   if (param.multi_stage) {
     if (!matching(0, p_matched_1, method, false, 0)) return;
     matchAfterPass1(method);
@@ -237,31 +263,35 @@ void Matcher::fusedMatch(visocu_ctx* ctx, const vector<Matcher*>& group, int32_t
   visob::StageTimer timer(2);
   const size_t n = group.size();
   vector<visocu_quad> quads(n);
-  vector<visocu_pmatch*> o1(n), o2(n);
+  vector<const visocu_pmatch*> l1(n), l2(n);
   vector<visocu_range*> rp(n);
-  vector<int32_t> c1(n), c2(n), n1(n, 0), n2(n, 0), d1(n, 0), d2(n, 0);
+  vector<int32_t> n1(n, 0), n2(n, 0), d1(n, 0), d2(n, 0), counts(4 * n, 0);
   for (size_t k = 0; k < n; k++) {
     Matcher* m = group[k];
     quads[k] = visocu_quad{m->slot[0], m->slot[1], m->slot[2], m->slot[3]};
-    c1[k] = m->queryCount(0, method) + 1; c2[k] = m->queryCount(1, method) + 1;
-    m->p_matched_1.resize((size_t)c1[k]); m->p_matched_2.resize((size_t)c2[k]);
-    o1[k] = reinterpret_cast<visocu_pmatch*>(m->p_matched_1.data());
-    o2[k] = reinterpret_cast<visocu_pmatch*>(m->p_matched_2.data());
     const float bs = (float)m->param.match_binsize;
     const size_t nbin = (size_t)ceil((float)m->dims_c[0] / bs) * (size_t)ceil((float)m->dims_c[1] / bs);
     m->ranges.resize(nbin);
     rp[k] = reinterpret_cast<visocu_range*>(m->ranges.data());
   }
-  const int rc = visocu_match_fused(ctx, (int32_t)n, quads.data(), group[0]->refineMode(), o1.data(), c1.data(), n1.data(), d1.data(),
-                                    o2.data(), c2.data(), n2.data(), d2.data(), rp.data());
+  const int rc = visocu_match_fused(ctx, (int32_t)n, quads.data(), group[0]->refineMode(), l1.data(), n1.data(), d1.data(),
+                                    l2.data(), n2.data(), d2.data(), rp.data(), counts.data());
   if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
   for (size_t k = 0; k < n; k++) {
     Matcher* m = group[k];
-    m->p_matched_1.resize(rc == VISOCU_OK ? n1[k] : 0);
-    m->p_matched_2.resize(rc == VISOCU_OK ? n2[k] : 0);
-    m->ro_done[0] = rc == VISOCU_OK && d1[k] != 0;
-    m->ro_done[1] = rc == VISOCU_OK && d2[k] != 0;
-    if (rc != VISOCU_OK) continue;
+    if (rc != VISOCU_OK) { m->p_matched_1.clear(); m->p_matched_2.clear(); m->ro_done[0] = m->ro_done[1] = false; continue; }
+    // the record counts arrive with the results (the frames were pushed without reading them back)
+    m->n_feat[0] = counts[4 * k + 0]; m->n_feat[4] = counts[4 * k + 1];
+    m->n_feat[2] = counts[4 * k + 2]; m->n_feat[6] = counts[4 * k + 3];
+    // the reference returns from matchFeatures without touching its match lists if a needed feature set is empty
+    // (matcher.cpp:190-212); the kernels matched nothing in that case
+    if (m->n_feat[0] == 0 || m->n_feat[2] == 0 || m->n_feat[4] == 0 || m->n_feat[6] == 0) continue;
+    const p_match* a1 = reinterpret_cast<const p_match*>(l1[k]);
+    const p_match* a2 = reinterpret_cast<const p_match*>(l2[k]);
+    m->p_matched_1.assign(a1, a1 + n1[k]);
+    m->p_matched_2.assign(a2, a2 + n2[k]);
+    m->ro_done[0] = d1[k] != 0;
+    m->ro_done[1] = d2[k] != 0;
     if (!m->ro_done[0]) {
       // the device declined the first list (too long, degenerate): the second pass ran on ranges of nothing - redo it
       // pass by pass for this matcher
@@ -286,8 +316,6 @@ bool Matcher::matchBegin(int32_t method) {
     if (n2[0] == 0 || n2[1] == 0 || n2[2] == 0 || n2[3] == 0) return false;
     if (param.multi_stage && (n1[0] == 0 || n1[1] == 0 || n1[2] == 0 || n1[3] == 0)) return false;
   }
-  p_matched_1.clear();
-  p_matched_2.clear();
   return true;
 }
 
@@ -508,9 +536,10 @@ void MatcherBatch::pushBack(const uint8_t* const* I1, const uint8_t* const* I2, 
     if (i2) { frames.push_back(f[1]); imgs.push_back(i2); owner.push_back((int32_t)s); }
   }
   if (frames.empty()) return;
-  vector<int32_t> ns(frames.size()), nd(frames.size());
+  vector<int32_t> ns(frames.size(), -1), nd(frames.size(), -1);
+  const bool lazy = seq[0]->lazyCounts() && !I2;           // see Matcher::push
   const bool ok = visocu_push_frames(ctx, (int32_t)frames.size(), frames.data(), imgs.data(), (int32_t)dims[2], on_device ? 1 : 0,
-                                     ns.data(), nd.data()) == VISOCU_OK;
+                                     lazy ? 0 : ns.data(), lazy ? 0 : nd.data()) == VISOCU_OK;
   if (!ok) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
   for (size_t k = 0; k < frames.size();) {
     const int32_t s = owner[k];
@@ -551,17 +580,21 @@ bool MatcherBatch::matchPass(const vector<int32_t>& active, int pass, int32_t me
 void MatcherBatch::matchFeatures(int32_t method) {
   if (!ctx) return;
   vector<int32_t> active;
-  for (size_t s = 0; s < seq.size(); s++)
+  const bool fused = Matcher::fusedAvailable(*seq[0], method) && seq.size() <= 128;
+  for (size_t s = 0; s < seq.size(); s++) {
+    if (!fused) seq[s]->syncCounts();
     if (seq[s]->matchBegin(method)) active.push_back((int32_t)s);
+  }
   if (active.empty()) return;
   const Matcher::parameters& p = seq[0]->param;
   const int refine = seq[0]->refineMode();
-  if (Matcher::fusedAvailable(*seq[0], method) && active.size() <= 128) {
+  if (fused) {
     vector<Matcher*> group;
     for (int32_t s : active) group.push_back(seq[s]);
     Matcher::fusedMatch(ctx, group, method);
     return;
   }
+  for (int32_t s : active) { seq[s]->p_matched_1.clear(); seq[s]->p_matched_2.clear(); }
   if (p.multi_stage) {
     if (!matchPass(active, 0, method, false, 0)) return;
     for (int32_t s : active) seq[s]->matchAfterPass1(method);
@@ -631,8 +664,10 @@ bool MatcherBatch::matchFeaturesPipelined(int32_t method, bool* current) {
   }
   vector<int32_t> active;
   // matchBegin clears the match lists of the sequences: the previous call's lists are collected into them further down
-  for (size_t s = 0; s < seq.size(); s++)
-    if (seq[s]->matchBegin(method)) active.push_back((int32_t)s);
+  for (size_t s = 0; s < seq.size(); s++) {
+    seq[s]->syncCounts();
+    if (seq[s]->matchBegin(method)) { active.push_back((int32_t)s); seq[s]->p_matched_1.clear(); seq[s]->p_matched_2.clear(); }
+  }
   const Matcher::parameters& p = seq[0]->param;
   const int refine = seq[0]->refineMode();
   bool pass1_ok = !active.empty();

@@ -76,7 +76,7 @@ public:
   void seedShuffle(unsigned seed);
   // stage access for parity tests: 1 = pass-1 list after removeOutliers, 2 = getMatches()
   const std::vector<p_match>& matches(int stage) const { return stage == 1 ? p_matched_1 : p_matched_2; }
-  int32_t featureCount(int which) const { return which >= 0 && which < 8 ? n_feat[which] : 0; }   // 1p1 2p1 1c1 2c1 1p2 2p2 1c2 2c2
+  int32_t featureCount(int which) { syncCounts(); return which >= 0 && which < 8 ? n_feat[which] : 0; }   // 1p1 2p1 1c1 2c1 1p2 2p2 1c2 2c2
   // host stages, usable on their own (used by the batch runner and the tests)
   struct range { float u_min[4], u_max[4], v_min[4], v_max[4]; };
   void computePriorStatistics(std::vector<p_match>& p_matched, int32_t method);
@@ -94,6 +94,8 @@ private:
   void matchAfterPass1(int32_t method);
   void matchAfterPass2(int32_t method);
   int refineMode() const;
+  bool lazyCounts() const;               // push without reading the record counts back (n_feat = -1 until somebody needs them)
+  void syncCounts();
   int32_t queryCount(int pass, int32_t method) const;
   bool ensureContext(int32_t w, int32_t h);
   bool fetchImage(int which, std::vector<uint8_t>& out);
