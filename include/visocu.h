@@ -118,13 +118,6 @@ int  visocu_nms(visocu_ctx* ctx, const int16_t* f1, const int16_t* f2, int32_t w
 int  visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
                   int32_t use_prior, const visocu_range* const* ranges, const double* const* tr_delta, int32_t refine,
                   visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers);
-/* The same call split in two for pipelined callers (flow matching with device outlier removal, pixel refinement or none,
- * at most 128 jobs): _deferred enqueues everything and returns; the outlier removal runs on a second stream with its own
- * scratch memory, so the context can take the next frames (visocu_push_frames) and other matching calls meanwhile.
- * _collect waits for it and delivers what visocu_match would have delivered.  One deferred call per context at a time. */
-int  visocu_match_deferred(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
-                           int32_t use_prior, const visocu_range* const* ranges, int32_t refine);
-int  visocu_match_collect(visocu_ctx* ctx, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers);
 /* Both passes of multi-stage FLOW matching in one submission (matcher.cpp:219-233 without a host round trip): first pass on
  * the sparse features, its outlier removal, Matcher::computePriorStatistics (matcher.cpp:734-868) on the survivors - on the
  * device -, second pass on the dense features with those ranges, refinement (0 or 1), outlier removal.  The kernels take
@@ -140,6 +133,19 @@ int  visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs
                         const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
                         const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
                         visocu_range* const* ranges_out, int32_t* counts);
+/* The same call in two halves, for callers that keep several steps in flight: _submit enqueues everything on the current
+ * lane and returns, _collect waits for that lane and delivers what visocu_match_fused delivers.  after_lane (or -1): the
+ * lane on which the previous frames of the jobs were pushed, if it is not the current one - the matching then starts
+ * behind that lane's feature kernels.  A step that repeats with the same frames, jobs and sizes (a runner walking
+ * sequences through the lanes in turn) is captured as a CUDA graph and replayed: one graph launch per half step.
+ * Lanes: a context holds several complete sets of per-step resources (stream, scratch and staging memory, result area);
+ * visocu_set_lane(ctx, k), 0 <= k < 6, makes set k the one every following call works with.  Lane 0 is the default. */
+int  visocu_set_lane(visocu_ctx* ctx, int32_t lane);
+int  visocu_match_fused_submit(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine, int32_t want_ranges,
+                               int32_t after_lane);
+int  visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
+                                const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
+                                visocu_range* const* ranges_out, int32_t* counts);
 /* Matcher::removeOutliers alone on caller-supplied match lists (host memory, compacted in place).  status[j] = 0: done,
  * 1: list unchanged, not handled by the device path (see visocu_match). */
 int  visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t method, visocu_pmatch* const* inout, const int32_t* n,

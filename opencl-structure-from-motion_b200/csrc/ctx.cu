@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cmath>
 #include <cstdlib>
+#include <functional>
 
 static thread_local std::string g_create_error;
 
@@ -43,42 +44,126 @@ WriteValueFn write_value_fn() {
 }
 }  // namespace
 
-cudaError_t visocu_stream_wait_on(visocu_ctx* ctx, int which) {
-  cudaStream_t st = which ? ctx->stream2 : ctx->stream;
+// the host-visible completion word of the current lane's stream: enqueue only
+cudaError_t visocu_stream_signal(visocu_ctx* ctx, uint32_t* seq_out) {
+  WriteValueFn wv = write_value_fn();
+  if (!wv || !ctx->wait_flag || ctx->ev_sync) { *seq_out = 0; return cudaSuccess; }
+  const uint32_t seq = ++ctx->wait_seq;
+  if (wv((CUstream)ctx->stream, (CUdeviceptr)(uintptr_t)ctx->wait_flag_dev, seq, 0) != CUDA_SUCCESS) { *seq_out = 0; return cudaSuccess; }
+  *seq_out = seq;
+  return cudaSuccess;
+}
+
+// wait until the completion word shows seq (0: fall back to a synchronising call)
+cudaError_t visocu_stream_wait_seq(visocu_ctx* ctx, uint32_t seq) {
+  cudaStream_t st = ctx->stream;
   if (ctx->ev_sync) {
     cudaError_t e = cudaEventRecord(ctx->ev_sync, st);
     return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_sync);
   }
-  WriteValueFn wv = write_value_fn();
-  if (wv && ctx->wait_flag) {
-    uint32_t& counter = which ? ctx->wait_seq2 : ctx->wait_seq;
-    const uint32_t seq = ++counter;
-    volatile uint32_t* flag = ctx->wait_flag + (which ? 8 : 0);          // two words of the 64-byte block
-    if (wv((CUstream)st, (CUdeviceptr)((uintptr_t)ctx->wait_flag_dev + (which ? 32 : 0)), seq, 0) == CUDA_SUCCESS) {
-      // VISOCU_WAIT_SLEEP_US=n (set by callers that run more worker threads than they have cores): after a short
-      // spin the thread sleeps n microseconds between polls, so that it does not take half of a shared core away from
-      // a worker that has host work to do
-      static const int sleep_us = [] { const char* e = getenv("VISOCU_WAIT_SLEEP_US"); return e ? atoi(e) : 0; }();
-      unsigned spins = 0;
-      while (*flag != seq) {
-        if ((++spins & 0x3FFF) == 0) {                 // now and then: did the stream die?
-          cudaError_t e = cudaStreamQuery(st);
-          if (e != cudaSuccess && e != cudaErrorNotReady) return e;
-        }
-        if (sleep_us > 0 && spins > 64) {
-          struct timespec ts = {0, (long)sleep_us * 1000L};
-          nanosleep(&ts, nullptr);
-        } else {
-          sched_yield();
-        }
-      }
-      return cudaSuccess;
+  if (seq == 0 || !ctx->wait_flag) return cudaStreamSynchronize(st);
+  // VISOCU_WAIT_SLEEP_US=n (set by callers that run more worker threads than they have cores): after a short
+  // spin the thread sleeps n microseconds between polls, so that it does not take half of a shared core away from
+  // a worker that has host work to do
+  static const int sleep_us = [] { const char* e = getenv("VISOCU_WAIT_SLEEP_US"); return e ? atoi(e) : 0; }();
+  volatile uint32_t* flag = ctx->wait_flag;
+  unsigned spins = 0;
+  while ((int32_t)(*flag - seq) < 0) {
+    if ((++spins & 0x3FFF) == 0) {                 // now and then: did the stream die?
+      cudaError_t e = cudaStreamQuery(st);
+      if (e != cudaSuccess && e != cudaErrorNotReady) return e;
+    }
+    if (sleep_us > 0 && spins > 64) {
+      struct timespec ts = {0, (long)sleep_us * 1000L};
+      nanosleep(&ts, nullptr);
+    } else {
+      sched_yield();
     }
   }
-  return cudaStreamSynchronize(st);
+  return cudaSuccess;
 }
 
-cudaError_t visocu_stream_wait(visocu_ctx* ctx) { return visocu_stream_wait_on(ctx, 0); }
+cudaError_t visocu_stream_wait(visocu_ctx* ctx) {
+  uint32_t seq = 0;
+  visocu_stream_signal(ctx, &seq);
+  return visocu_stream_wait_seq(ctx, seq);
+}
+
+// ---- lanes
+static cudaError_t make_wait_flag(volatile uint32_t** flag, void** dev) {
+  void* f = nullptr;
+  *flag = nullptr; *dev = nullptr;
+  if (cudaHostAlloc(&f, 64, cudaHostAllocMapped) == cudaSuccess) {
+    memset(f, 0, 64);
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, f, 0) == cudaSuccess) { *flag = (volatile uint32_t*)f; *dev = d; }
+    else cudaFreeHost(f);
+  }
+  cudaGetLastError();
+  return cudaSuccess;
+}
+
+#define VISO_LANE_FIELDS(X) X(stream) X(scratch) X(scratch_bytes) X(scratch2) X(scratch2_bytes) X(pinned) X(pinned_bytes) X(pinned2) \
+  X(pinned2_bytes) X(d_ranges) X(d_ranges_bytes) X(pin_ranges) X(deliver) X(deliver_dev) X(deliver_bytes) X(deliver2) X(deliver2_bytes) \
+  X(wait_flag) X(wait_flag_dev) X(wait_seq) X(counts_stage) X(img_stage) X(img_stage_bytes) X(src_table) X(src_table_pin) X(ev_push) \
+  X(g_push) X(g_match) X(fused_pending) X(fused_n) X(fused_ranges) X(fused_seq) X(fused_jobs)
+
+int visocu_use_lane(visocu_ctx* ctx, int lane) {
+  if (lane < 0 || lane >= VISO_LANES) return visocu_set_error(ctx, VISOCU_EINVAL, "lane %d out of range", lane);
+  if (lane == ctx->lane) return VISOCU_OK;
+  visocu_lane& out = ctx->lanes[ctx->lane];
+  visocu_lane& in = ctx->lanes[lane];
+#define X(f) out.f = ctx->f;
+  VISO_LANE_FIELDS(X)
+#undef X
+  out.part[0] = ctx->part[0]; out.part[1] = ctx->part[1];
+  out.created = true;
+  if (!in.created) {
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamCreateWithFlags(&in.stream, cudaStreamNonBlocking));
+    make_wait_flag(&in.wait_flag, &in.wait_flag_dev);
+    in.created = true;
+  }
+#define X(f) ctx->f = in.f;
+  VISO_LANE_FIELDS(X)
+#undef X
+  ctx->part[0] = in.part[0]; ctx->part[1] = in.part[1];
+  ctx->lane = lane;
+  return VISOCU_OK;
+}
+extern "C" int visocu_set_lane(visocu_ctx* ctx, int32_t lane) { return ctx ? visocu_use_lane(ctx, lane) : VISOCU_EINVAL; }
+
+static void destroy_graph(visocu_graph& g) { if (g.exec) cudaGraphExecDestroy(g.exec); g = visocu_graph(); }
+static void free_lane_resources(visocu_ctx* ctx) {     // of the lane in the working fields
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  destroy_graph(ctx->g_push); destroy_graph(ctx->g_match);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->scratch2) cudaFree(ctx->scratch2);
+  if (ctx->d_ranges) cudaFree(ctx->d_ranges);
+  if (ctx->pin_ranges) cudaFreeHost(ctx->pin_ranges);
+  if (ctx->deliver) cudaFreeHost(ctx->deliver);
+  if (ctx->deliver2) cudaFreeHost(ctx->deliver2);
+  if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
+  if (ctx->img_stage) cudaFree(ctx->img_stage);
+  if (ctx->counts_stage) cudaFree(ctx->counts_stage);
+  if (ctx->src_table) cudaFree((void*)ctx->src_table);
+  if (ctx->src_table_pin) cudaFreeHost((void*)ctx->src_table_pin);
+  if (ctx->wait_flag) cudaFreeHost((void*)ctx->wait_flag);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->ev_push) cudaEventDestroy(ctx->ev_push);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = nullptr; ctx->scratch = ctx->scratch2 = ctx->d_ranges = ctx->pin_ranges = ctx->deliver = ctx->deliver2 = nullptr;
+  ctx->pinned = ctx->pinned2 = nullptr; ctx->img_stage = nullptr; ctx->counts_stage = nullptr; ctx->wait_flag = nullptr;
+  ctx->src_table = ctx->src_table_pin = nullptr; ctx->ev_push = nullptr;
+  ctx->scratch_bytes = ctx->scratch2_bytes = ctx->pinned_bytes = ctx->pinned2_bytes = ctx->d_ranges_bytes = ctx->deliver_bytes = 0;
+  ctx->deliver2_bytes = ctx->img_stage_bytes = 0;
+}
+void visocu_drop_lane_graphs(visocu_ctx* ctx) { destroy_graph(ctx->g_push); destroy_graph(ctx->g_match); }
+// graphs bake frame pointers and sizes: a re-configuration drops them on every lane
+void visocu_drop_graphs(visocu_ctx* ctx) {
+  destroy_graph(ctx->g_push); destroy_graph(ctx->g_match);
+  for (int l = 0; l < VISO_LANES; l++) { destroy_graph(ctx->lanes[l].g_push); destroy_graph(ctx->lanes[l].g_match); }
+}
 
 extern "C" const char* visocu_last_error(const visocu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -106,8 +191,6 @@ extern "C" int visocu_create(int device, visocu_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount; ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
   snprintf(ctx->name, sizeof ctx->name, "%s", prop.name);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaMalloc(&ctx->d_stats, 2 * sizeof(uint64_t))) != cudaSuccess) {
     visocu_set_error(nullptr, VISOCU_ECUDA, "context setup: %s", cudaGetErrorString(e));
@@ -115,17 +198,9 @@ extern "C" int visocu_create(int device, visocu_ctx** out) {
     return VISOCU_ECUDA;
   }
   cudaMemset(ctx->d_stats, 0, 2 * sizeof(uint64_t));
-  {
-    // completion word of visocu_stream_wait: pinned, mapped, written by the stream itself
-    void* flag = nullptr;
-    if (cudaHostAlloc(&flag, 64, cudaHostAllocMapped) == cudaSuccess) {
-      memset(flag, 0, 64);
-      void* dev = nullptr;
-      if (cudaHostGetDevicePointer(&dev, flag, 0) == cudaSuccess) { ctx->wait_flag = (volatile uint32_t*)flag; ctx->wait_flag_dev = dev; }
-      else cudaFreeHost(flag);
-    }
-    cudaGetLastError();
-  }
+  make_wait_flag(&ctx->wait_flag, &ctx->wait_flag_dev);      // completion word of visocu_stream_wait: pinned, mapped, written by the stream itself
+  ctx->lanes[0].created = true;
+  if (const char* e = getenv("VISOCU_GRAPHS")) ctx->use_graphs = e[0] != '0';
   // VISOCU_BLOCKING_SYNC=1: waiting host threads sleep (for runs with more worker threads than cores)
   if (const char* e = getenv("VISOCU_BLOCKING_SYNC"))
     if (e[0] == '1') cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming);
@@ -138,13 +213,14 @@ static void free_pool(visocu_ctx* ctx) {
   if (ctx->frames_d) cudaFree(ctx->frames_d);
   ctx->pool = nullptr; ctx->frames_d = nullptr; ctx->configured = false;
   visocu_free_tiles(ctx);
+  visocu_drop_graphs(ctx);
 }
 
 extern "C" void visocu_destroy(visocu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+  for (int l = 0; l < VISO_LANES; l++)
+    if (l == ctx->lane || ctx->lanes[l].created) { if (visocu_use_lane(ctx, l) == VISOCU_OK && ctx->stream) cudaStreamSynchronize(ctx->stream); }
   if (getenv("VISOCU_RO_STATS") && (ctx->ro_jobs || ctx->ro_declined)) {
     const double nj = ctx->ro_jobs ? (double)ctx->ro_jobs : 1.0;
     fprintf(stderr, "[outliers] %llu lists on the device, mean us: sort %.1f partition %.1f build %.1f vote %.1f; declined %llu "
@@ -154,27 +230,15 @@ extern "C" void visocu_destroy(visocu_ctx* ctx) {
             (unsigned long long)ctx->ro_reason[2], (unsigned long long)ctx->ro_reason[3],
             ctx->ro_declined ? (double)ctx->ro_declined_n / (double)ctx->ro_declined : 0.0);
   }
+  for (int l = 0; l < VISO_LANES; l++)
+    if (l == ctx->lane || ctx->lanes[l].created) { if (visocu_use_lane(ctx, l) == VISOCU_OK) free_lane_resources(ctx); }
   free_pool(ctx);
-  if (ctx->scratch) cudaFree(ctx->scratch);
-  if (ctx->scratch2) cudaFree(ctx->scratch2);
-  if (ctx->d_ranges) cudaFree(ctx->d_ranges);
-  if (ctx->pin_ranges) cudaFreeHost(ctx->pin_ranges);
-  if (ctx->deliver) cudaFreeHost(ctx->deliver);
-  if (ctx->deliver2) cudaFreeHost(ctx->deliver2);
-  if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  if (ctx->img_stage) cudaFree(ctx->img_stage);
-  if (ctx->counts_stage) cudaFree(ctx->counts_stage);
-  if (ctx->wait_flag) cudaFreeHost((void*)ctx->wait_flag);
-  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->pev0) cudaEventDestroy(ctx->pev0);
   if (ctx->pev1) cudaEventDestroy(ctx->pev1);
   if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
-  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   delete ctx;
 }
 
@@ -188,6 +252,7 @@ extern "C" int visocu_device_info(const visocu_ctx* ctx, int32_t* sm_count, int3
 }
 
 int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes) {
+  if (!ctx->in_step && (ctx->g_push.exec || ctx->g_match.exec)) visocu_drop_lane_graphs(ctx);   // the graphs replay copies out of these buffers
   if (bytes <= ctx->scratch_bytes) return VISOCU_OK;
   CU_TRY(ctx, visocu_stream_wait(ctx));
   if (ctx->scratch) cudaFree(ctx->scratch);
@@ -199,6 +264,7 @@ int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes) {
 }
 
 int visocu_ensure_pinned(visocu_ctx* ctx, size_t bytes) {
+  if (!ctx->in_step && (ctx->g_push.exec || ctx->g_match.exec)) visocu_drop_lane_graphs(ctx);
   if (bytes <= ctx->pinned_bytes) return VISOCU_OK;
   CU_TRY(ctx, visocu_stream_wait(ctx));
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -218,9 +284,11 @@ extern "C" int visocu_configure(visocu_ctx* ctx, const visocu_params* p, int32_t
   if (p->nms_n < 1 || p->nms_n > 14) return visocu_set_error(ctx, VISOCU_EINVAL, "nms_n=%d outside the supported range 1..14", p->nms_n);
   if (p->match_binsize < 1) return visocu_set_error(ctx, VISOCU_EINVAL, "match_binsize must be positive");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int l = 0; l < VISO_LANES; l++) if (ctx->lanes[l].created && l != ctx->lane && ctx->lanes[l].stream) cudaStreamSynchronize(ctx->lanes[l].stream);
   CU_TRY(ctx, visocu_stream_wait(ctx));
   free_pool(ctx);
   ctx->param = *p;
+  ctx->ro_bound[0] = ctx->ro_bound[1] = -1;
   Geometry& g = ctx->g;
   g.w = width; g.h = height; g.bpl = viso_bpl(width);
   g.half = p->half_resolution ? 1 : 0;
@@ -386,9 +454,8 @@ extern "C" int visocu_launch_count(const visocu_ctx* ctx, uint64_t* n) {
 
 // Row-wise copy of a batch of images into the 16-byte-stride frame planes (matcher.cpp:163-175); pad columns stay zero.
 // One launch for all frames of a push: a source row starts at any byte, a destination word is assembled from four bytes.
-struct RepitchArgs { const uint8_t* src[VISO_MAX_BATCH]; };
-__global__ void __launch_bounds__(256) k_repitch(Geometry g, const FrameDev* frames, SlotList sl, RepitchArgs a, int bpl_in) {
-  const uint8_t* __restrict__ src = a.src[blockIdx.y];
+__global__ void __launch_bounds__(256) k_repitch(Geometry g, const FrameDev* frames, SlotList sl, const uint8_t* const* table, int bpl_in) {
+  const uint8_t* __restrict__ src = table[blockIdx.y];
   uint8_t* dst = frames[sl.s[blockIdx.y]].img;
   const int wpr = g.bpl >> 2;
   for (int idx = blockIdx.x * 256 + threadIdx.x; idx < wpr * g.h; idx += gridDim.x * 256) {
@@ -430,6 +497,122 @@ extern "C" int visocu_frame_counts(visocu_ctx* ctx, int32_t n, const int32_t* fr
   return VISOCU_OK;
 }
 
+// Run `enqueue` on the lane's stream, or replay it as a CUDA graph once the same call (same key) has been seen twice: the
+// first time buffers get their final size, the second time the stream is captured, from then on one graph launch replaces
+// the individual launches and copies.  Everything `enqueue` does must depend on the key only.
+static int run_or_replay_impl(visocu_ctx* ctx, visocu_graph& g, uint64_t key, const std::function<int()>& enqueue, const char** what);
+int visocu_run_or_replay(visocu_ctx* ctx, visocu_graph& g, uint64_t key, const std::function<int()>& enqueue) {
+  static const bool dbg = getenv("VISOCU_GRAPH_DEBUG") != nullptr;
+  if (!dbg) { const char* w; return run_or_replay_impl(ctx, g, key, enqueue, &w); }
+  struct timespec a, b; clock_gettime(CLOCK_MONOTONIC, &a);
+  const char* what = "?";
+  const int rc = run_or_replay_impl(ctx, g, key, enqueue, &what);
+  clock_gettime(CLOCK_MONOTONIC, &b);
+  fprintf(stderr, "[graph] lane %d %s %s key %016llx %.1f us\n", ctx->lane, &g == &ctx->g_push ? "push " : "match", what, (unsigned long long)key,
+          (b.tv_sec - a.tv_sec) * 1e6 + (b.tv_nsec - a.tv_nsec) * 1e-3);
+  return rc;
+}
+static int run_or_replay_impl(visocu_ctx* ctx, visocu_graph& g, uint64_t key, const std::function<int()>& enqueue, const char** what) {
+  *what = "plain";
+  if (!ctx->use_graphs || ctx->profile) return enqueue();
+  if (g.key != key) { destroy_graph(g); g.key = key; }
+  if (g.exec) {
+    *what = "replay";
+    CU_TRY(ctx, cudaGraphLaunch(g.exec, ctx->stream));
+    ctx->launches += (uint64_t)g.seen;                   // kernels inside the graph
+    return VISOCU_OK;
+  }
+  if (g.seen == 0) { g.seen = 1; return enqueue(); }
+  if (g.seen < 0) return enqueue();                      // capture failed before: stay with plain launches
+  const uint64_t l0 = ctx->launches;
+  *what = "capture";
+  CU_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  if (rc != VISOCU_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    g.seen = -1;
+    ctx->launches = l0;
+    *what = "capture-failed";
+    return rc != VISOCU_OK ? rc : enqueue();
+  }
+  const int kernels = (int)(ctx->launches - l0);
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e2 != cudaSuccess) { cudaGetLastError(); g.seen = -1; ctx->launches = l0; return enqueue(); }
+  g.exec = exec; g.seen = kernels;
+  CU_TRY(ctx, cudaGraphLaunch(g.exec, ctx->stream));
+  return VISOCU_OK;
+}
+
+static uint64_t hash_words(uint64_t h, const void* data, size_t bytes) {
+  const uint8_t* p = (const uint8_t*)data;
+  for (size_t i = 0; i < bytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+// One batch (at most VISO_MAX_BATCH frames) of a push: host images cross PCIe as ONE contiguous transfer each into a staging
+// area (a pitched host-to-device copy of 376 unaligned 1241-byte rows is several times slower than the 0.47 MB it moves);
+// then, graph-able: the table of source pointers, the re-pitch kernel and the feature kernels.
+static int push_batch(visocu_ctx* ctx, const SlotList& sl, const uint8_t* const* imgs, int32_t bpl_in, int32_t on_device) {
+  const Geometry& g = ctx->g;
+  int rc;
+  const size_t stage_stride = align_up((size_t)bpl_in * g.h, 256);
+  const bool direct = !on_device && bpl_in == g.bpl;      // already in the frame layout: straight into the frame planes
+  if (!on_device && !direct) {
+    const size_t want = stage_stride * (size_t)sl.n;
+    if (want > ctx->img_stage_bytes) {
+      CU_TRY(ctx, visocu_stream_wait(ctx));
+      visocu_drop_lane_graphs(ctx);
+      if (ctx->img_stage) cudaFree(ctx->img_stage);
+      ctx->img_stage = nullptr; ctx->img_stage_bytes = 0;
+      CU_TRY(ctx, cudaMalloc(&ctx->img_stage, want));
+      ctx->img_stage_bytes = want;
+    }
+  }
+  if (!ctx->src_table) {
+    CU_TRY(ctx, cudaMalloc((void**)&ctx->src_table, sizeof(void*) * VISO_MAX_BATCH));
+    CU_TRY(ctx, cudaMallocHost((void**)&ctx->src_table_pin, sizeof(void*) * VISO_MAX_BATCH));
+  }
+  if (!ctx->counts_stage) CU_TRY(ctx, cudaMalloc(&ctx->counts_stage, VISO_MAX_BATCH * 16));
+  if (!ctx->ev_push) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_push, cudaEventDisableTiming));
+  for (int i = 0; i < sl.n; i++) {
+    if (!imgs[i]) return visocu_set_error(ctx, VISOCU_EINVAL, "null image %d", i);
+    const int f = sl.s[i];
+    if (on_device) {
+      ctx->src_table_pin[i] = imgs[i];
+    } else if (direct) {
+      CU_COPY(ctx, ctx->frames_h[f].img, imgs[i], (size_t)bpl_in * g.h, cudaMemcpyHostToDevice);
+    } else {
+      uint8_t* stage = ctx->img_stage + (size_t)i * stage_stride;
+      CU_COPY(ctx, stage, imgs[i], (size_t)bpl_in * (g.h - 1) + g.w, cudaMemcpyHostToDevice);
+      ctx->src_table_pin[i] = stage;
+    }
+    ctx->frame_valid[f] = 1;
+  }
+  uint64_t key = hash_words(1469598103934665603ull, &sl.n, sizeof(int));
+  key = hash_words(key, sl.s, sizeof(int) * (size_t)sl.n);
+  key = hash_words(key, &bpl_in, sizeof bpl_in);
+  key = hash_words(key, &direct, sizeof direct);
+  ctx->in_step++;
+  rc = visocu_run_or_replay(ctx, ctx->g_push, key, [&]() -> int {
+    if (!direct) {
+      CU_TRY(ctx, cudaMemcpyAsync((void*)ctx->src_table, (const void*)ctx->src_table_pin, sizeof(void*) * (size_t)sl.n, cudaMemcpyHostToDevice, ctx->stream));
+      int gx = (g.bpl / 4 * g.h + 255) / 256; if (gx > 64) gx = 64;
+      k_repitch<<<dim3(gx, sl.n), 256, 0, ctx->stream>>>(g, ctx->frames_d, sl, ctx->src_table, bpl_in);
+      CU_LAUNCH_CHECK(ctx);
+    }
+    return visocu_launch_features(ctx, sl);
+  });
+  ctx->in_step--;
+  if (rc) return rc;
+  CU_TRY(ctx, cudaEventRecord(ctx->ev_push, ctx->stream));
+  return VISOCU_OK;
+}
+
 extern "C" int visocu_push_frames(visocu_ctx* ctx, int32_t n, const int32_t* frames, const uint8_t* const* imgs,
                                   int32_t bpl_in, int32_t on_device, int32_t* n_sparse, int32_t* n_dense) {
   if (!ctx) return VISOCU_EINVAL;
@@ -442,44 +625,8 @@ extern "C" int visocu_push_frames(visocu_ctx* ctx, int32_t n, const int32_t* fra
   for (int start = 0; start < n; start += VISO_MAX_BATCH) {
     SlotList sl;
     sl.n = n - start < VISO_MAX_BATCH ? n - start : VISO_MAX_BATCH;
-    const size_t stage_stride = align_up((size_t)bpl_in * g.h, 256);
-    if (!on_device && bpl_in != g.bpl) {
-      const size_t want = stage_stride * (size_t)sl.n;
-      if (want > ctx->img_stage_bytes) {
-        CU_TRY(ctx, visocu_stream_wait(ctx));
-        if (ctx->img_stage) cudaFree(ctx->img_stage);
-        ctx->img_stage = nullptr; ctx->img_stage_bytes = 0;
-        CU_TRY(ctx, cudaMalloc(&ctx->img_stage, want));
-        ctx->img_stage_bytes = want;
-      }
-    }
-    RepitchArgs ra;
-    bool repitch = false;
-    for (int i = 0; i < sl.n; i++) {
-      int f = frames[start + i];
-      if (!imgs[start + i]) return visocu_set_error(ctx, VISOCU_EINVAL, "null image %d", start + i);
-      sl.s[i] = f;
-      // row-wise copy into the 16-byte stride (matcher.cpp:163-175); pad columns stay zero.  A host image crosses
-      // PCIe as ONE contiguous transfer into a staging area and is re-pitched on the device: a pitched host-to-device
-      // copy of 376 unaligned 1241-byte rows is several times slower than the 0.47 MB it moves.
-      if (on_device) {
-        ra.src[i] = imgs[start + i]; repitch = true;
-      } else if (bpl_in == g.bpl) {
-        CU_COPY(ctx, ctx->frames_h[f].img, imgs[start + i], (size_t)bpl_in * g.h, cudaMemcpyHostToDevice);
-      } else {
-        uint8_t* stage = ctx->img_stage + (size_t)i * stage_stride;
-        CU_COPY(ctx, stage, imgs[start + i], (size_t)bpl_in * (g.h - 1) + g.w, cudaMemcpyHostToDevice);
-        ra.src[i] = stage; repitch = true;
-      }
-      ctx->frame_valid[f] = 1;
-    }
-    if (repitch) {
-      int gx = (g.bpl / 4 * g.h + 255) / 256; if (gx > 64) gx = 64;
-      k_repitch<<<dim3(gx, sl.n), 256, 0, ctx->stream>>>(g, ctx->frames_d, sl, ra, bpl_in);
-      CU_LAUNCH_CHECK(ctx);
-    }
-    if (!ctx->counts_stage) CU_TRY(ctx, cudaMalloc(&ctx->counts_stage, VISO_MAX_BATCH * 16));
-    if ((rc = visocu_launch_features(ctx, sl))) return rc;
+    for (int i = 0; i < sl.n; i++) sl.s[i] = frames[start + i];
+    if ((rc = push_batch(ctx, sl, imgs + start, bpl_in, on_device))) return rc;
     if (!n_sparse && !n_dense) {
       // Lazy mode: nobody asked for the record counts, so nothing is read back and nothing is waited for.  The matching
       // call that follows takes the counts from device memory (visocu_match_fused) or fetches them (visocu_frame_counts).

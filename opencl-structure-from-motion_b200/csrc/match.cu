@@ -530,53 +530,8 @@ int fill_job(visocu_ctx* ctx, const visocu_quad& q, int method, int pass, MatchJ
 
 }  // namespace
 
-// The tail of a matching call: result words are in pinned memory; fetch the lists and hand everything to the caller.
-// The tail of a matching call: result words are in pinned memory; fetch the lists and hand everything to the caller.
-// In two steps so that several tails (the two passes of a fused call) share one wait.
-static int match_tail_issue(visocu_ctx* ctx, const visocu_deferred& st, const int32_t* cap, int32_t* n_out, int32_t* outliers,
-                            int which_stream, int* maxn_out) {
-  cudaStream_t stream = which_stream ? ctx->stream2 : ctx->stream;
-  const int nb = st.nb;
-  const int32_t* pw = (const int32_t*)st.pin_words;
-  int maxn = 0;
-  for (int j = 0; j < nb; j++) {
-    const int n = pw[16 * j];
-    n_out[j] = n;
-    if (n > maxn) maxn = n;
-    if (n > cap[j]) return visocu_set_error(ctx, VISOCU_ECAPACITY, "job %d produced %d matches, room for %d", j, n, cap[j]);
-    const int status = pw[16 * j + 1];
-    outliers[j] = status == 0 ? 1 : 0;
-    if (status == 0 && n > 3) { for (int k = 0; k < 4; k++) ctx->ro_ns[k] += (uint64_t)pw[16 * j + 4 + k]; ctx->ro_jobs++; }
-    else if (status != 0) { ctx->ro_declined++; ctx->ro_reason[status & 3]++; ctx->ro_declined_n += (uint64_t)pw[16 * j + 3]; }
-  }
-  *maxn_out = maxn;
-  if (maxn > 0) {
-    const size_t wbytes = (size_t)maxn * 48;
-    ctx->d2h_bytes += (uint64_t)wbytes * nb;
-    CU_TRY(ctx, cudaMemcpy2DAsync(st.pin_lists, wbytes, st.dev_lists, st.ostride, wbytes, nb, cudaMemcpyDeviceToHost, stream));
-  }
-  return VISOCU_OK;
-}
-
-static void match_tail_deliver(const visocu_deferred& st, visocu_pmatch* const* out, const int32_t* n_out, int maxn) {
-  const size_t wbytes = (size_t)maxn * 48;
-  for (int j = 0; j < st.nb; j++)
-    if (n_out[j] > 0) memcpy(out[j], st.pin_lists + wbytes * j, (size_t)n_out[j] * 48);
-}
-
-static int match_tail(visocu_ctx* ctx, const visocu_deferred& st, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out,
-                      int32_t* outliers, int which_stream) {
-  int maxn = 0;
-  int rc = match_tail_issue(ctx, st, cap, n_out, outliers, which_stream, &maxn);
-  if (rc) return rc;
-  if (maxn > 0) {
-    CU_TRY(ctx, visocu_stream_wait_on(ctx, which_stream));
-    match_tail_deliver(st, out, n_out, maxn);
-  }
-  return VISOCU_OK;
-}
-
-// scratch and pinned staging of the deferred call are a second set: the first one is reused by the calls in between
+// the second pass of a fused call works in a second set of scratch and pinned staging memory: the first set still holds
+// the first pass's lists and job descriptors
 struct ScratchSwap {
   visocu_ctx* ctx; bool on;
   ScratchSwap(visocu_ctx* c, bool enable) : ctx(c), on(enable) { swap(); }
@@ -588,8 +543,7 @@ struct ScratchSwap {
   }
 };
 
-// mode 0: complete call.  1: deferred (outlier removal on the second stream, second scratch set, visocu_match_collect).
-// 2 / 3: first / second pass of a fused call (visocu_match_fused): everything enqueued on the main stream, nothing
+// mode 0: complete call.  2 / 3: first / second pass of a fused call (visocu_match_fused): everything enqueued on the main stream, nothing
 // waited for, state in ctx->part[]; the second pass works in the second scratch set and takes its prior ranges from
 // device memory (dev_ranges, one block of dev_ranges_stride bytes per job).
 static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
@@ -597,11 +551,10 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
                       visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers, int mode,
                       const uint8_t* dev_ranges = nullptr, size_t dev_ranges_stride = 0, bool dyn = false) {
   const bool deferred = mode != 0;                   // no result is delivered by this call
-  const bool second_set = mode == 1 || mode == 3;
+  const bool second_set = mode == 3;
   if (!ctx) return VISOCU_EINVAL;
   if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
   if (n_jobs <= 0 || !jobs || (!deferred && (!out || !cap || !n_out))) return visocu_set_error(ctx, VISOCU_EINVAL, "bad match arguments");
-  if (mode != 0 && ctx->deferred.pending) return visocu_set_error(ctx, VISOCU_ESTATE, "a deferred matching call has not been collected");
   if (deferred && (method != 0 || n_jobs > VISO_MAX_BATCH || refine == 2))
     return visocu_set_error(ctx, VISOCU_EINVAL, "deferred matching: flow method, pixel refinement, at most %d jobs", VISO_MAX_BATCH);
   ScratchSwap swap_guard(ctx, second_set);
@@ -749,36 +702,14 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
     if (mode >= 2) {
       // one pass of a fused call: outlier removal and the read-back of the result words queued on the main stream
       // Shared memory of the outlier kernel follows the longest list.  Lazy mode: flow matches are one-to-one, so a list is
-      // no longer than the feature list of the previous frame, whose count arrived with the previous step's results.
+      // no longer than a frame's feature list; the context keeps the longest one seen so far plus a margin (ro_bound).  A
+      // longer list than that is declined by the kernel and voted on by the host, and the bound grows.
       int max_list = maxq;
-      if (dyn) {
-        int bound = 0;
-        for (int j = 0; j < nb && bound >= 0; j++) {
-          const int c = ctx->h_counts[2 * (size_t)jobs[start + j].f1p + pass];
-          bound = c < 0 ? -1 : (c > bound ? c : bound);
-        }
-        if (bound >= 0 && bound < max_list) max_list = bound;
-      }
+      if (dyn && ctx->ro_bound[pass] >= 0 && ctx->ro_bound[pass] < max_list) max_list = ctx->ro_bound[pass];
       if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, max_list, ctx->stream))) return rc;
-      ctx->d2h_bytes += words_bytes;
-      CU_TRY(ctx, cudaMemcpyAsync(pin + p_words, sb + o_words, words_bytes, cudaMemcpyDeviceToHost, ctx->stream));
       visocu_deferred& st = ctx->part[mode - 2];
       st.pending = true; st.nb = nb; st.pin_words = pin + p_words; st.pin_lists = pin + p_lists;
       st.dev_lists = sb + o_list2; st.ostride = ostride; st.dev_words = (const int32_t*)(sb + o_words); st.dev_jobs = dj;
-      return VISOCU_OK;
-    }
-    if (mode == 1) {
-      // The outlier removal and the read-back of its result words go to the second stream, behind the kernels above;
-      // the caller's next feature and pass-1 launches on the first stream do not wait for them.
-      if (!stage_lists) return visocu_set_error(ctx, VISOCU_EINVAL, "deferred matching: lists too large for the staging area");
-      CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-      CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-      if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, maxq, ctx->stream2))) return rc;
-      ctx->d2h_bytes += words_bytes;
-      CU_TRY(ctx, cudaMemcpyAsync(pin + p_words, sb + o_words, words_bytes, cudaMemcpyDeviceToHost, ctx->stream2));
-      visocu_deferred& st = ctx->deferred;
-      st.pending = true; st.nb = nb; st.pin_words = pin + p_words; st.pin_lists = pin + p_lists;
-      st.dev_lists = sb + o_list2; st.ostride = ostride;
       return VISOCU_OK;
     }
     if (ro && (rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, maxq, ctx->stream))) return rc;
@@ -901,20 +832,6 @@ extern "C" int visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* 
   return match_impl(ctx, n_jobs, jobs, method, pass, use_prior, ranges, tr_delta, refine, out, cap, n_out, outliers, 0);
 }
 
-extern "C" int visocu_match_deferred(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t method, int32_t pass,
-                                     int32_t use_prior, const visocu_range* const* ranges, int32_t refine) {
-  return match_impl(ctx, n_jobs, jobs, method, pass, use_prior, ranges, nullptr, refine, nullptr, nullptr, nullptr, nullptr, 1);
-}
-
-extern "C" int visocu_match_collect(visocu_ctx* ctx, visocu_pmatch* const* out, const int32_t* cap, int32_t* n_out, int32_t* outliers) {
-  if (!ctx || !out || !cap || !n_out || !outliers) return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad collect arguments") : VISOCU_EINVAL;
-  if (!ctx->deferred.pending) return visocu_set_error(ctx, VISOCU_ESTATE, "no deferred matching call to collect");
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  ctx->deferred.pending = false;
-  CU_TRY(ctx, visocu_stream_wait_on(ctx, 1));
-  return match_tail(ctx, ctx->deferred, out, cap, n_out, outliers, 1);
-}
-
 // Results of a fused call, written by the GPU itself into mapped pinned host memory: per job a header (the 16 result words
 // of each pass and the record counts of the two frames) and the two survivor lists.  One kernel, one CTA per job; the
 // host needs no second round trip to learn how many records to copy.
@@ -944,46 +861,28 @@ __global__ void __launch_bounds__(256) k_deliver(DeliverArgs a) {
   for (int i = tid; i < 3 * n2; i += 256) d2[i] = s2[i];
 }
 
-extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine,
-                                  const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
-                                  const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
-                                  visocu_range* const* ranges_out, int32_t* counts) {
-  if (!ctx) return VISOCU_EINVAL;
-  if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
-  if (n_jobs <= 0 || n_jobs > VISO_MAX_BATCH || !jobs || !list1 || !n1 || !done1 || !list2 || !n2 || !done2)
-    return visocu_set_error(ctx, VISOCU_EINVAL, "bad fused match arguments (at most %d jobs)", VISO_MAX_BATCH);
-  if (ctx->g.first_pass != 0) return visocu_set_error(ctx, VISOCU_EINVAL, "fused matching needs multi_stage");
-  if (refine < 0 || refine > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "fused matching: refine must be 0 or 1");
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
+namespace {
+struct FusedLayout { size_t rstride, off1, off2, dstride; bool zero_copy; };
+FusedLayout fused_layout(const Geometry& g) {
+  FusedLayout L;
+  L.rstride = align_up((size_t)g.ub * g.vb * sizeof(visocu_range), 256);
+  // delivery area: header + both lists at their capacity, per job.  Small geometries: the lists travel with the header
+  // (zero-copy writes of the last kernel, one wait).  Large ones (4K: over a hundred megabytes of capacity per job): only
+  // the header does, and the lists are copied once their lengths are known.
+  L.off1 = 256; L.off2 = L.off1 + align_up((size_t)(g.cap[0] + 1) * 48, 256);
+  const size_t full = L.off2 + align_up((size_t)(g.cap[1] + 1) * 48, 256);
+  L.zero_copy = full <= ((size_t)8 << 20);
+  L.dstride = L.zero_copy ? full : 256;
+  return L;
+}
+}  // namespace
+
+// everything of a fused call that is enqueued on the lane's stream (replayable as a graph: depends on the job list, the
+// refinement mode, the ranges flag and the outlier bound only)
+static int fused_enqueue(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine, bool want_ranges) {
   const Geometry& g = ctx->g;
   const int nbin = g.ub * g.vb;
-  const size_t rstride = align_up((size_t)nbin * sizeof(visocu_range), 256);
-  const size_t tmp_bytes = (size_t)n_jobs * 9 * nbin * sizeof(float);
-  const size_t need = rstride * n_jobs + tmp_bytes;
-  if (need > ctx->d_ranges_bytes) {
-    CU_TRY(ctx, visocu_stream_wait(ctx));
-    if (ctx->d_ranges) cudaFree(ctx->d_ranges);
-    ctx->d_ranges = nullptr; ctx->d_ranges_bytes = 0;
-    CU_TRY(ctx, cudaMalloc(&ctx->d_ranges, need));
-    ctx->d_ranges_bytes = need;
-    if (ctx->pin_ranges) cudaFreeHost(ctx->pin_ranges);
-    ctx->pin_ranges = nullptr;
-    CU_TRY(ctx, cudaMallocHost(&ctx->pin_ranges, rstride * VISO_MAX_BATCH));
-  }
-  // delivery area: header + both lists at their capacity, per job
-  const size_t off1 = 256, off2 = off1 + align_up((size_t)(g.cap[0] + 1) * 48, 256);
-  // Small geometries: the lists travel with the header (zero-copy writes of the last kernel, one wait).  Large ones (4K:
-  // over a hundred megabytes of capacity per job): only the header does, and the lists are copied once their lengths are known.
-  const bool zero_copy = off2 + align_up((size_t)(g.cap[1] + 1) * 48, 256) <= ((size_t)8 << 20);
-  const size_t dstride = zero_copy ? off2 + align_up((size_t)(g.cap[1] + 1) * 48, 256) : 256;
-  if (dstride * n_jobs > ctx->deliver_bytes) {
-    CU_TRY(ctx, visocu_stream_wait(ctx));
-    if (ctx->deliver) cudaFreeHost(ctx->deliver);
-    ctx->deliver = nullptr; ctx->deliver_bytes = 0;
-    CU_TRY(ctx, cudaHostAlloc(&ctx->deliver, dstride * n_jobs, cudaHostAllocMapped));
-    CU_TRY(ctx, cudaHostGetDevicePointer(&ctx->deliver_dev, ctx->deliver, 0));
-    ctx->deliver_bytes = dstride * n_jobs;
-  }
+  const FusedLayout L = fused_layout(g);
   uint8_t* d_rng = (uint8_t*)ctx->d_ranges;
   // first pass (sparse features, no prior) and its outlier removal; the record counts are taken from device memory
   int rc = match_impl(ctx, n_jobs, jobs, 0, 0, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 2, nullptr, 0, true);
@@ -992,28 +891,96 @@ extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_
   const visocu_deferred& A = ctx->part[0];
   const size_t smem = (size_t)9 * nbin * sizeof(float);
   const int use_smem = smem <= 40 * 1024 ? 1 : 0;
-  k_prior_ranges<<<n_jobs, 1024, use_smem ? smem : 0, ctx->stream>>>(g, A.dev_lists, A.ostride, A.dev_words, d_rng, rstride,
-                                                                   (float*)(d_rng + rstride * n_jobs), use_smem);
+  k_prior_ranges<<<n_jobs, 1024, use_smem ? smem : 0, ctx->stream>>>(g, A.dev_lists, A.ostride, A.dev_words, d_rng, L.rstride,
+                                                                   (float*)(d_rng + L.rstride * n_jobs), use_smem);
   CU_LAUNCH_CHECK(ctx);
   // second pass (dense features, the ranges as prior), refinement, outlier removal
-  rc = match_impl(ctx, n_jobs, jobs, 0, 1, 1, nullptr, nullptr, refine, nullptr, nullptr, nullptr, nullptr, 3, d_rng, rstride, true);
+  rc = match_impl(ctx, n_jobs, jobs, 0, 1, 1, nullptr, nullptr, refine, nullptr, nullptr, nullptr, nullptr, 3, d_rng, L.rstride, true);
   if (rc) return rc;
   const visocu_deferred& B = ctx->part[1];
   DeliverArgs da;
   da.jobs2 = (const MatchJob*)B.dev_jobs; da.words1 = A.dev_words; da.words2 = B.dev_words;
   da.lists1 = A.dev_lists; da.lists2 = B.dev_lists; da.ostride1 = A.ostride; da.ostride2 = B.ostride;
-  da.dst = (uint8_t*)ctx->deliver_dev; da.dstride = dstride; da.off1 = off1; da.off2 = off2; da.with_lists = zero_copy ? 1 : 0;
+  da.dst = (uint8_t*)ctx->deliver_dev; da.dstride = L.dstride; da.off1 = L.off1; da.off2 = L.off2; da.with_lists = L.zero_copy ? 1 : 0;
   k_deliver<<<n_jobs, 256, 0, ctx->stream>>>(da);
   CU_LAUNCH_CHECK(ctx);
-  if (ranges_out) {
-    ctx->d2h_bytes += rstride * n_jobs;
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->pin_ranges, d_rng, rstride * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+  if (want_ranges) CU_TRY(ctx, cudaMemcpyAsync(ctx->pin_ranges, d_rng, L.rstride * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+  return VISOCU_OK;
+}
+
+extern "C" int visocu_match_fused_submit(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine, int32_t want_ranges,
+                                         int32_t after_lane) {
+  if (!ctx) return VISOCU_EINVAL;
+  if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
+  if (n_jobs <= 0 || n_jobs > VISO_MAX_BATCH || !jobs) return visocu_set_error(ctx, VISOCU_EINVAL, "bad fused match arguments (at most %d jobs)", VISO_MAX_BATCH);
+  if (ctx->g.first_pass != 0) return visocu_set_error(ctx, VISOCU_EINVAL, "fused matching needs multi_stage");
+  if (refine < 0 || refine > 1) return visocu_set_error(ctx, VISOCU_EINVAL, "fused matching: refine must be 0 or 1");
+  if (ctx->fused_pending) return visocu_set_error(ctx, VISOCU_ESTATE, "the lane's previous fused call has not been collected");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const Geometry& g = ctx->g;
+  const int nbin = g.ub * g.vb;
+  const FusedLayout L = fused_layout(g);
+  const size_t need = L.rstride * n_jobs + (size_t)n_jobs * 9 * nbin * sizeof(float);
+  if (need > ctx->d_ranges_bytes) {
+    CU_TRY(ctx, visocu_stream_wait(ctx));
+    visocu_drop_lane_graphs(ctx);
+    if (ctx->d_ranges) cudaFree(ctx->d_ranges);
+    ctx->d_ranges = nullptr; ctx->d_ranges_bytes = 0;
+    CU_TRY(ctx, cudaMalloc(&ctx->d_ranges, need));
+    ctx->d_ranges_bytes = need;
+    if (ctx->pin_ranges) cudaFreeHost(ctx->pin_ranges);
+    ctx->pin_ranges = nullptr;
+    CU_TRY(ctx, cudaMallocHost(&ctx->pin_ranges, L.rstride * VISO_MAX_BATCH));
   }
-  CU_TRY(ctx, visocu_stream_wait(ctx));                 // the only wait of a push + match step
+  if (L.dstride * n_jobs > ctx->deliver_bytes) {
+    CU_TRY(ctx, visocu_stream_wait(ctx));
+    visocu_drop_lane_graphs(ctx);
+    if (ctx->deliver) cudaFreeHost(ctx->deliver);
+    ctx->deliver = nullptr; ctx->deliver_bytes = 0;
+    CU_TRY(ctx, cudaHostAlloc(&ctx->deliver, L.dstride * n_jobs, cudaHostAllocMapped));
+    CU_TRY(ctx, cudaHostGetDevicePointer(&ctx->deliver_dev, ctx->deliver, 0));
+    ctx->deliver_bytes = L.dstride * n_jobs;
+  }
+  for (int j = 0; j < n_jobs; j++) {
+    const int f[2] = {jobs[j].f1p, jobs[j].f1c};
+    for (int k = 0; k < 2; k++)
+      if (f[k] < 0 || f[k] >= ctx->n_frames || !ctx->frame_valid[f[k]]) return visocu_set_error(ctx, VISOCU_ESTATE, "frame %d holds no features", f[k]);
+  }
+  // the previous frames may have been pushed on another lane: its feature kernels must be done before ours read them
+  if (after_lane >= 0 && after_lane < VISO_LANES && after_lane != ctx->lane && ctx->lanes[after_lane].ev_push)
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lanes[after_lane].ev_push, 0));
+  uint64_t key = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; for (size_t i = 0; i < n; i++) { key ^= b[i]; key *= 1099511628211ull; } };
+  mix(&n_jobs, sizeof n_jobs); mix(jobs, sizeof(visocu_quad) * (size_t)n_jobs); mix(&refine, sizeof refine); mix(&want_ranges, sizeof want_ranges);
+  mix(ctx->ro_bound, sizeof ctx->ro_bound);
+  ctx->in_step++;
+  const int rc = visocu_run_or_replay(ctx, ctx->g_match, key, [&]() -> int { return fused_enqueue(ctx, n_jobs, jobs, refine, want_ranges != 0); });
+  ctx->in_step--;
+  if (rc) return rc;
+  CU_TRY(ctx, visocu_stream_signal(ctx, &ctx->fused_seq));
+  ctx->fused_pending = true; ctx->fused_n = n_jobs; ctx->fused_ranges = want_ranges != 0;
+  ctx->fused_jobs.assign(jobs, jobs + n_jobs);
+  return VISOCU_OK;
+}
+
+extern "C" int visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
+                                          const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
+                                          visocu_range* const* ranges_out, int32_t* counts) {
+  if (!ctx || !list1 || !n1 || !done1 || !list2 || !n2 || !done2) return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad collect arguments") : VISOCU_EINVAL;
+  if (!ctx->fused_pending) return visocu_set_error(ctx, VISOCU_ESTATE, "no fused matching call to collect on this lane");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->fused_pending = false;
+  CU_TRY(ctx, visocu_stream_wait_seq(ctx, ctx->fused_seq));          // the only wait of a push + match step
   ctx->part[0].pending = ctx->part[1].pending = false;
+  const Geometry& g = ctx->g;
+  const int nbin = g.ub * g.vb, n_jobs = ctx->fused_n;
+  const FusedLayout L = fused_layout(g);
+  const visocu_quad* jobs = ctx->fused_jobs.data();
+  const visocu_deferred& A = ctx->part[0];
+  const visocu_deferred& B = ctx->part[1];
   int overflow = -1;
   for (int j = 0; j < n_jobs; j++) {
-    const uint8_t* base = (const uint8_t*)ctx->deliver + dstride * j;
+    const uint8_t* base = (const uint8_t*)ctx->deliver + L.dstride * j;
     const int32_t* hdr = (const int32_t*)base;
     for (int p = 0; p < 2; p++) {
       const int32_t* w = hdr + 16 * p;
@@ -1023,17 +990,22 @@ extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_
       else if (status != 0) { ctx->ro_declined++; ctx->ro_reason[status & 3]++; ctx->ro_declined_n += (uint64_t)w[3]; }
       ctx->d2h_bytes += 64 + (uint64_t)n * 48;
     }
-    if (zero_copy) { list1[j] = (const visocu_pmatch*)(base + off1); list2[j] = (const visocu_pmatch*)(base + off2); }
+    if (L.zero_copy) { list1[j] = (const visocu_pmatch*)(base + L.off1); list2[j] = (const visocu_pmatch*)(base + L.off2); }
     const int fr[2] = {jobs[j].f1p, jobs[j].f1c};
     for (int k = 0; k < 2; k++) {
       ctx->h_counts[2 * (size_t)fr[k] + 0] = hdr[32 + 3 * k]; ctx->h_counts[2 * (size_t)fr[k] + 1] = hdr[33 + 3 * k];
       if (hdr[34 + 3 * k]) overflow = fr[k];
       if (counts) { counts[4 * j + 2 * k] = hdr[32 + 3 * k]; counts[4 * j + 2 * k + 1] = hdr[33 + 3 * k]; }
+      // shared memory of the next outlier launches: the longest feature list seen, with a margin
+      for (int p = 0; p < 2; p++) {
+        const int c = hdr[32 + 3 * k + p], want = (c + c / 4 + 256 + 511) & ~511;      // in steps of 512: the bound is part of the graph key
+        if (c > ctx->ro_bound_seen[p]) { ctx->ro_bound_seen[p] = c; if (ctx->ro_bound[p] < want) ctx->ro_bound[p] = want < g.cap[p] ? want : g.cap[p]; }
+      }
     }
     ctx->d2h_bytes += 24;
   }
   if (overflow >= 0) return visocu_set_error(ctx, VISOCU_ECAPACITY, "feature list of frame %d overflowed", overflow);
-  if (!zero_copy) {
+  if (!L.zero_copy) {
     size_t total = 0;
     for (int j = 0; j < n_jobs; j++) total += align_up((size_t)n1[j] * 48 + 48, 256) + align_up((size_t)n2[j] * 48 + 48, 256);
     if (total > ctx->deliver2_bytes) {
@@ -1053,10 +1025,20 @@ extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_
     }
     CU_TRY(ctx, visocu_stream_wait(ctx));
   }
-  if (ranges_out)
+  if (ctx->fused_ranges) ctx->d2h_bytes += L.rstride * n_jobs;
+  if (ranges_out && ctx->fused_ranges)
     for (int j = 0; j < n_jobs; j++)
-      if (ranges_out[j]) memcpy(ranges_out[j], (const uint8_t*)ctx->pin_ranges + rstride * j, (size_t)nbin * sizeof(visocu_range));
+      if (ranges_out[j]) memcpy(ranges_out[j], (const uint8_t*)ctx->pin_ranges + L.rstride * j, (size_t)nbin * sizeof(visocu_range));
   return VISOCU_OK;
+}
+
+extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine,
+                                  const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
+                                  const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
+                                  visocu_range* const* ranges_out, int32_t* counts) {
+  const int rc = visocu_match_fused_submit(ctx, n_jobs, jobs, refine, ranges_out ? 1 : 0, -1);
+  if (rc) return rc;
+  return visocu_match_fused_collect(ctx, list1, n1, done1, list2, n2, done2, ranges_out, counts);
 }
 
 extern "C" int visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, int32_t mode, visocu_pmatch* inout, int32_t n,

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <functional>
 #include <string>
 #include <vector>
 #include "visocu.h"
@@ -49,21 +50,54 @@ struct visocu_deferred {
   const void* dev_jobs = nullptr;                               // device: the MatchJob array of the pass
 };
 
+// Everything a step in flight needs for itself: a context has VISO_LANES of these, so that several push + match steps
+// (of the same sequences, on consecutive frames) can be in flight at once without sharing a stream, scratch memory or
+// a result area.  visocu_set_lane swaps one of them into the context's working fields of the same names.
+#define VISO_LANES 6            // 0: default; 0..3: pipelined steps (lane = step & 3); 4: synchronous fall-backs and odometry calls
+struct visocu_graph { cudaGraphExec_t exec = nullptr; uint64_t key = 0; int seen = 0; };
+struct visocu_lane {
+  cudaStream_t stream = nullptr;
+  void* scratch = nullptr; size_t scratch_bytes = 0;
+  void* scratch2 = nullptr; size_t scratch2_bytes = 0;
+  void* pinned = nullptr; size_t pinned_bytes = 0;
+  void* pinned2 = nullptr; size_t pinned2_bytes = 0;
+  visocu_deferred part[2];
+  void* d_ranges = nullptr; size_t d_ranges_bytes = 0; void* pin_ranges = nullptr;
+  void* deliver = nullptr; void* deliver_dev = nullptr; size_t deliver_bytes = 0;
+  void* deliver2 = nullptr; size_t deliver2_bytes = 0;
+  volatile uint32_t* wait_flag = nullptr; void* wait_flag_dev = nullptr; uint32_t wait_seq = 0;
+  int32_t* counts_stage = nullptr;
+  uint8_t* img_stage = nullptr; size_t img_stage_bytes = 0;
+  const uint8_t** src_table = nullptr; const uint8_t** src_table_pin = nullptr;   // image pointers of a push (device / pinned copy)
+  cudaEvent_t ev_push = nullptr;       // recorded behind the feature kernels of the lane's last push
+  visocu_graph g_push, g_match;        // the two halves of a step, captured once their shape repeats
+  bool fused_pending = false; int fused_n = 0; bool fused_ranges = false; uint32_t fused_seq = 0;
+  std::vector<visocu_quad> fused_jobs;  // the submitted, not yet collected fused call of the lane
+  bool created = false;
+};
+
 struct visocu_ctx {
   int device = 0;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
   char name[64] = {0};
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;    // deferred outlier removal (overlaps the next frame's feature and pass-1 kernels)
-  cudaEvent_t ev_fork = nullptr;
-  visocu_deferred deferred;
+  int lane = 0;                      // the lane whose resources are in the working fields below
+  visocu_lane lanes[VISO_LANES];     // parked lanes (the entry of the current lane is stale)
+  int use_graphs = 1;                // VISOCU_GRAPHS=0: always enqueue kernel by kernel
+  int in_step = 0;                   // > 0 while a (replayable) step is being enqueued: buffer growth does not drop the graphs
+  bool fused_pending = false; int fused_n = 0; bool fused_ranges = false; uint32_t fused_seq = 0;   // per lane, see VISO_LANE_FIELDS
+  std::vector<visocu_quad> fused_jobs;
+  int ro_bound_seen[2] = {0, 0};
+  int ro_bound[2] = {-1, -1};        // longest match list seen per pass (shared-memory size of the outlier kernel in lazy mode)
+  const uint8_t** src_table = nullptr; const uint8_t** src_table_pin = nullptr;
+  cudaEvent_t ev_push = nullptr;
+  visocu_graph g_push, g_match;
   visocu_deferred part[2];           // the two passes of a fused call (visocu_match_fused)
   void* deliver2 = nullptr; size_t deliver2_bytes = 0;        // pinned landing area of the lists when they are too large for that
   void* deliver = nullptr; void* deliver_dev = nullptr; size_t deliver_bytes = 0;     // mapped pinned memory the last kernel of a fused call writes the results to
   void* d_ranges = nullptr; size_t d_ranges_bytes = 0; void* pin_ranges = nullptr;   // prior ranges computed on the device between the passes
   void* scratch2 = nullptr; size_t scratch2_bytes = 0;
   void* pinned2 = nullptr;  size_t pinned2_bytes = 0;
-  uint32_t wait_seq2 = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   volatile uint32_t* wait_flag = nullptr; void* wait_flag_dev = nullptr; uint32_t wait_seq = 0;   // see visocu_stream_wait
   cudaEvent_t ev_sync = nullptr;     // blocking-sync event: host threads sleep instead of spinning while the GPU works
@@ -100,10 +134,15 @@ struct visocu_ctx {
 };
 
 int visocu_set_error(visocu_ctx* ctx, int code, const char* fmt, ...);
-cudaError_t visocu_stream_wait(visocu_ctx* ctx);
-cudaError_t visocu_stream_wait_on(visocu_ctx* ctx, int which);   // 0 = main stream, 1 = second stream     // waits for the context's stream (yielding the CPU if ev_sync exists)
+cudaError_t visocu_stream_wait(visocu_ctx* ctx);                 // enqueue a completion word on the lane's stream and wait for it
+cudaError_t visocu_stream_signal(visocu_ctx* ctx, uint32_t* seq_out);
+cudaError_t visocu_stream_wait_seq(visocu_ctx* ctx, uint32_t seq);
+void visocu_drop_graphs(visocu_ctx* ctx);
+void visocu_drop_lane_graphs(visocu_ctx* ctx);               // of the current lane
+int visocu_use_lane(visocu_ctx* ctx, int lane);                  // swap the lane's resources into the working fields
 int visocu_ensure_scratch(visocu_ctx* ctx, size_t bytes);
 int visocu_ensure_pinned(visocu_ctx* ctx, size_t bytes);
+int visocu_run_or_replay(visocu_ctx* ctx, visocu_graph& g, uint64_t key, const std::function<int()>& enqueue);
 
 #define CU_TRY(ctx, expr)                                                                        \
   do {                                                                                           \

@@ -47,7 +47,7 @@ struct MonoAccess : public VisualOdometryMono {
 }  // namespace
 
 VISOB_API void visob_set_device(int device) { visob::set_device(device); }
-VISOB_API void visob_set_pipeline(int on) { visob::set_pipeline(on != 0); }
+VISOB_API void visob_set_pipeline_depth(int depth) { visob::set_pipeline_depth(depth); }
 
 namespace visob { extern std::atomic<long long> g_stage_ns[8]; extern std::atomic<long long> g_stage_calls[8]; }
 // stage ids: 0 pushBack, 1 matching pass 1, 2 matching pass 2 (+refinement), 3 priors, 4 removeOutliers (< 2000 matches), 5 removeOutliers (larger), 6 ransacEstimateF, 7 estimateMotion (total, includes 6)
@@ -330,11 +330,20 @@ void runner_push(Runner* r, int tid, const uint8_t* const* imgs, const uint8_t* 
   r->batches[tid]->pushBack(i1.data(), imgs2 ? i2.data() : 0, d, false, on_device != 0);
 }
 
-// one frame for every sequence of worker `tid`
+// one frame for every sequence of worker `tid`, synchronously
 void runner_advance(Runner* r, int tid, const uint8_t* const* imgs, const uint8_t* const* imgs2, const int32_t* dims, int on_device,
                     int bucket, int32_t* n_matches_out, int32_t* ok_out) {
-  runner_push(r, tid, imgs, imgs2, dims, on_device);
-  r->batches[tid]->matchFeatures(r->method);
+  MatcherBatch* b = r->batches[tid];
+  if (!imgs2 && b->stepAvailable(r->method)) {
+    uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+    std::vector<const uint8_t*> i1;
+    for (int s = tid; s < r->S; s += r->threads) i1.push_back(imgs[s]);
+    while (b->stepsInFlight() > 0) b->stepCollect();
+    if (b->stepSubmit(i1.data(), d, on_device != 0)) b->stepCollect();
+  } else {
+    runner_push(r, tid, imgs, imgs2, dims, on_device);
+    b->matchFeatures(r->method);
+  }
   runner_post(r, tid, bucket, n_matches_out, ok_out);
 }
 
@@ -396,27 +405,33 @@ VISOB_API double visob_runner_run(void* h, int n_steps, const uint8_t* const* im
   run_workers(r->threads, [&](int tid) {
     visob::set_device(r->device);
     MatcherBatch* b = r->batches[tid];
-    if (!b->pipelineAvailable(r->method)) {
+    if (imgs2 || !b->stepAvailable(r->method)) {
       for (int k = 0; k < n_steps; k++)
         runner_advance(r, tid, imgs + (size_t)k * r->S, imgs2 ? imgs2 + (size_t)k * r->S : 0, dims, on_device, bucket,
                        n_matches_out ? n_matches_out + (size_t)k * r->S : 0, ok_out ? ok_out + (size_t)k * r->S : 0);
       return;
     }
-    // Pipelined: the second pass of step k is only enqueued (its outlier removal runs on the second stream) and is
-    // collected during step k + 1, after that step's features and first pass; the host stages of step k follow then.
-    // Every step's results are complete when the call returns.
-    for (int k = 0; k <= n_steps; k++) {
-      bool have = false, current = false;
-      if (k < n_steps) {
-        runner_push(r, tid, imgs + (size_t)k * r->S, imgs2 ? imgs2 + (size_t)k * r->S : 0, dims, on_device);
-        have = b->matchFeaturesPipelined(r->method, &current);
-      } else {
-        have = b->finishPipelined();
-      }
-      const int done = current ? k : k - 1;            // the step whose matches the sequences hold now
-      if ((have || current) && done >= 0 && done < n_steps)
-        runner_post(r, tid, bucket, n_matches_out ? n_matches_out + (size_t)done * r->S : 0, ok_out ? ok_out + (size_t)done * r->S : 0);
+    // Pipelined: up to `depth` steps of the worker's sequences are in flight.  Step k is submitted (push of frame k and
+    // its matching against frame k - 1: one submission, replayed as a graph); then the oldest step is collected if the
+    // window is full, and its host stages (bucketing, odometry) run while the GPU works on the younger steps.  Every
+    // step's results are complete when the call returns.
+    const int depth = visob::pipeline_depth();
+    uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+    std::vector<const uint8_t*> i1;
+    while (b->stepsInFlight() > 0) b->stepCollect();
+    int collected = 0;
+    auto collect_one = [&]() {
+      b->stepCollect();
+      runner_post(r, tid, bucket, n_matches_out ? n_matches_out + (size_t)collected * r->S : 0, ok_out ? ok_out + (size_t)collected * r->S : 0);
+      collected++;
+    };
+    for (int k = 0; k < n_steps; k++) {
+      i1.clear();
+      for (int s = tid; s < r->S; s += r->threads) i1.push_back(imgs[(size_t)k * r->S + s]);
+      if (!b->stepSubmit(i1.data(), d, on_device != 0)) break;
+      if (b->stepsInFlight() >= depth) collect_one();
     }
+    while (b->stepsInFlight() > 0) collect_one();
   });
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }

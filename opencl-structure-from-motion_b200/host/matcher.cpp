@@ -38,14 +38,12 @@ bool device_outliers() {
   static const bool on = [] { const char* e = getenv("VISOB_HOST_OUTLIERS"); return !(e && e[0] == '1'); }();
   return on;
 }
-// The pipelined runner (MatcherBatch::matchFeaturesPipelined) is off unless asked for: measured on B200 it does not pay,
-// see DESIGN.md section 6.  visob_set_pipeline(1) / VISOB_PIPELINE=1 switch it on.
-static std::atomic<int> g_pipeline(-1);
-void set_pipeline(bool on) { g_pipeline = on ? 1 : 0; }
-bool pipeline_enabled() {
-  int v = g_pipeline.load();
-  if (v < 0) { const char* e = getenv("VISOB_PIPELINE"); v = (e && e[0] == '1') ? 1 : 0; g_pipeline = v; }
-  return v == 1;
+static std::atomic<int> g_depth(-1);
+void set_pipeline_depth(int depth) { g_depth = depth < 1 ? 1 : (depth > 3 ? 3 : depth); }
+int pipeline_depth() {
+  int v = g_depth.load();
+  if (v < 0) { const char* e = getenv("VISOB_DEPTH"); v = e ? atoi(e) : 2; v = v < 1 ? 1 : (v > 3 ? 3 : v); g_depth = v; }
+  return v;
 }
 static thread_local int t_device = 0;
 void set_device(int device) { t_device = device; }
@@ -277,29 +275,32 @@ void Matcher::fusedMatch(visocu_ctx* ctx, const vector<Matcher*>& group, int32_t
   const int rc = visocu_match_fused(ctx, (int32_t)n, quads.data(), group[0]->refineMode(), l1.data(), n1.data(), d1.data(),
                                     l2.data(), n2.data(), d2.data(), rp.data(), counts.data());
   if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
-  for (size_t k = 0; k < n; k++) {
-    Matcher* m = group[k];
-    if (rc != VISOCU_OK) { m->p_matched_1.clear(); m->p_matched_2.clear(); m->ro_done[0] = m->ro_done[1] = false; continue; }
-    // the record counts arrive with the results (the frames were pushed without reading them back)
-    m->n_feat[0] = counts[4 * k + 0]; m->n_feat[4] = counts[4 * k + 1];
-    m->n_feat[2] = counts[4 * k + 2]; m->n_feat[6] = counts[4 * k + 3];
-    // the reference returns from matchFeatures without touching its match lists if a needed feature set is empty
-    // (matcher.cpp:190-212); the kernels matched nothing in that case
-    if (m->n_feat[0] == 0 || m->n_feat[2] == 0 || m->n_feat[4] == 0 || m->n_feat[6] == 0) continue;
-    const p_match* a1 = reinterpret_cast<const p_match*>(l1[k]);
-    const p_match* a2 = reinterpret_cast<const p_match*>(l2[k]);
-    m->p_matched_1.assign(a1, a1 + n1[k]);
-    m->p_matched_2.assign(a2, a2 + n2[k]);
-    m->ro_done[0] = d1[k] != 0;
-    m->ro_done[1] = d2[k] != 0;
-    if (!m->ro_done[0]) {
-      // the device declined the first list (too long, degenerate): the second pass ran on ranges of nothing - redo it
-      // pass by pass for this matcher
-      m->matchAfterPass1(method);
-      if (!m->matching(1, m->p_matched_2, method, true, m->refineMode())) continue;
-    }
-    m->matchAfterPass2(method);
+  for (size_t k = 0; k < n; k++) takeFused(group[k], rc == VISOCU_OK, &counts[4 * k], l1[k], n1[k], d1[k], l2[k], n2[k], d2[k], method);
+}
+
+// results of a fused call for one matcher
+void Matcher::takeFused(Matcher* m, bool ok, const int32_t* counts, const visocu_pmatch* l1, int32_t n1, int32_t d1,
+                        const visocu_pmatch* l2, int32_t n2, int32_t d2, int32_t method) {
+  if (!ok) { m->p_matched_1.clear(); m->p_matched_2.clear(); m->ro_done[0] = m->ro_done[1] = false; return; }
+  // the record counts arrive with the results (the frames were pushed without reading them back)
+  m->n_feat[0] = counts[0]; m->n_feat[4] = counts[1];
+  m->n_feat[2] = counts[2]; m->n_feat[6] = counts[3];
+  // the reference returns from matchFeatures without touching its match lists if a needed feature set is empty
+  // (matcher.cpp:190-212); the kernels matched nothing in that case
+  if (m->n_feat[0] == 0 || m->n_feat[2] == 0 || m->n_feat[4] == 0 || m->n_feat[6] == 0) return;
+  const p_match* a1 = reinterpret_cast<const p_match*>(l1);
+  const p_match* a2 = reinterpret_cast<const p_match*>(l2);
+  m->p_matched_1.assign(a1, a1 + n1);
+  m->p_matched_2.assign(a2, a2 + n2);
+  m->ro_done[0] = d1 != 0;
+  m->ro_done[1] = d2 != 0;
+  if (!m->ro_done[0]) {
+    // the device declined the first list (too long, degenerate): the second pass ran on ranges of nothing - redo it
+    // pass by pass for this matcher
+    m->matchAfterPass1(method);
+    if (!m->matching(1, m->p_matched_2, method, true, m->refineMode())) return;
   }
+  m->matchAfterPass2(method);
 }
 
 // sanity checks of matcher.cpp:190-212: silently keep the old matches if a needed set is empty
@@ -490,7 +491,7 @@ void Matcher::removeOutliers(vector<p_match>& p_matched, int32_t method) {
 // MatcherBatch: S independent sequences on ONE context.  Every GPU stage is issued once for all sequences (the C-ABI is
 // batched: one launch per kernel covers all S frames / pairs), the host stages run per sequence in between.  The result
 // of every sequence is identical to what a stand-alone Matcher produces.
-MatcherBatch::MatcherBatch(Matcher::parameters param, int32_t n_sequences) : pending_method(0), pending(false), ctx(0), width(0), height(0) {
+MatcherBatch::MatcherBatch(Matcher::parameters param, int32_t n_sequences) : k_submit(0), k_collect(0), ctx(0), width(0), height(0) {
   for (int32_t s = 0; s < n_sequences; s++) seq.push_back(new Matcher(param));
   device = visob::current_device();
 }
@@ -605,79 +606,69 @@ void MatcherBatch::matchFeatures(int32_t method) {
   for (int32_t s : active) seq[s]->matchAfterPass2(method);
 }
 
-// ---- pipelined matching (see matcher.h)
-bool MatcherBatch::pipelineAvailable(int32_t method) const {
-  return visob::pipeline_enabled() && method == 0 && !seq.empty() && seq[0]->refineMode() != 2 && visob::device_outliers() &&
-         (int32_t)seq.size() <= 128;
+// ---- pipelined stepping (see matcher.h)
+bool MatcherBatch::stepAvailable(int32_t method) const {
+  return method == 0 && !seq.empty() && seq[0]->lazyCounts() && (int32_t)seq.size() <= 128;
 }
 
-bool MatcherBatch::issuePass2(const vector<int32_t>& active, int32_t method, bool use_prior, int refine) {
-  visob::StageTimer timer(2);
-  const size_t n = active.size();
-  vector<visocu_quad> quads(n);
-  vector<const visocu_range*> rptr(n);
-  pending_cap.assign(n, 0);
-  for (size_t k = 0; k < n; k++) {
-    Matcher* m = seq[active[k]];
-    quads[k] = visocu_quad{m->slot[0], m->slot[1], m->slot[2], m->slot[3]};
-    rptr[k] = reinterpret_cast<const visocu_range*>(m->ranges.data());
-    pending_cap[k] = m->queryCount(1, method) + 1;
+bool MatcherBatch::stepSubmit(const uint8_t* const* I1, uint32_t* dims, bool on_device) {
+  visob::StageTimer timer(0);
+  if ((int32_t)dims[0] <= 0 || (int32_t)dims[1] <= 0 || dims[2] < dims[0]) {
+    std::cerr << "ERROR: Image dimension mismatch!" << std::endl;
+    return false;
   }
-  const int rc = visocu_match_deferred(ctx, (int32_t)n, quads.data(), method, 1, use_prior ? 1 : 0, use_prior ? rptr.data() : 0, refine);
-  if (rc != VISOCU_OK) { std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl; return false; }
-  pending_active = active; pending_method = method; pending = true;
+  if (!ensure((int32_t)dims[0], (int32_t)dims[1])) return false;
+  if (k_submit - k_collect >= 3) return false;                       // the fourth frame of the ring is still being read
+  const size_t S = seq.size();
+  const int64_t k = k_submit;
+  const int lane = (int)(k & 3);
+  if (visocu_set_lane(ctx, lane) != VISOCU_OK) { std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl; return false; }
+  // frame k of sequence s lives in slot 4 s + (k & 3): four consecutive frames stay alive
+  vector<int32_t> frames(S);
+  vector<visocu_quad> quads(S);
+  for (size_t s = 0; s < S; s++) {
+    frames[s] = 4 * (int32_t)s + lane;
+    quads[s] = visocu_quad{4 * (int32_t)s + (int)((k + 3) & 3), -1, frames[s], -1};
+    if (!I1[s]) { std::cerr << "ERROR: Image dimension mismatch!" << std::endl; return false; }
+  }
+  bool ok = visocu_push_frames(ctx, (int32_t)S, frames.data(), I1, (int32_t)dims[2], on_device ? 1 : 0, 0, 0) == VISOCU_OK;
+  if (ok && k > 0)
+    ok = visocu_match_fused_submit(ctx, (int32_t)S, quads.data(), seq[0]->refineMode(), 0, (int)((k + 3) & 3)) == VISOCU_OK;
+  if (!ok) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+  visocu_set_lane(ctx, 4);
+  if (!ok) return false;
+  for (int c = 0; c < 3; c++) step_dims[c] = (int32_t)dims[c];
+  k_submit++;
   return true;
 }
 
-bool MatcherBatch::collectPending() {
-  if (!pending) return false;
+bool MatcherBatch::stepCollect() {
+  if (k_collect >= k_submit) return false;
   visob::StageTimer timer(2);
-  pending = false;
-  const size_t n = pending_active.size();
-  vector<visocu_pmatch*> outs(n);
-  vector<int32_t> cnt(n, 0), done(n, 0);
-  for (size_t k = 0; k < n; k++) {
-    Matcher* m = seq[pending_active[k]];
-    m->p_matched_2.resize((size_t)pending_cap[k]);
-    outs[k] = reinterpret_cast<visocu_pmatch*>(m->p_matched_2.data());
+  const size_t S = seq.size();
+  const int64_t k = k_collect++;
+  const int lane = (int)(k & 3), prev = (int)((k + 3) & 3);
+  for (size_t s = 0; s < S; s++) {
+    Matcher* m = seq[s];
+    // the sequence now refers to the pair (frame k - 1, frame k)
+    m->slot[0] = k > 0 ? 4 * (int32_t)s + prev : -1; m->slot[1] = -1;
+    m->slot[2] = 4 * (int32_t)s + lane; m->slot[3] = -1;
+    for (int c = 0; c < 3; c++) { m->dims_p[c] = k > 0 ? step_dims[c] : 0; m->dims_c[c] = step_dims[c]; }
+    m->dims_c[2] = step_dims[0] + 15 - (step_dims[0] - 1) % 16;
+    if (k > 0) m->dims_p[2] = m->dims_c[2];
+    m->have_I1p = m->have_I1c = false;
+    m->n_feat[1] = m->n_feat[3] = m->n_feat[5] = m->n_feat[7] = 0;
   }
-  const int rc = visocu_match_collect(ctx, outs.data(), pending_cap.data(), cnt.data(), done.data());
-  if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
-  for (size_t k = 0; k < n; k++) {
-    Matcher* m = seq[pending_active[k]];
-    m->p_matched_2.resize(rc == VISOCU_OK ? cnt[k] : 0);
-    m->ro_done[1] = rc == VISOCU_OK && done[k] != 0;
-    m->matchAfterPass2(pending_method);
-  }
-  return rc == VISOCU_OK;
-}
-
-bool MatcherBatch::matchFeaturesPipelined(int32_t method, bool* current) {
-  *current = false;
-  if (!ctx) return false;
-  if (!pipelineAvailable(method)) {
-    const bool had = collectPending();     // cannot happen in a homogeneous run; keeps the state machine sound
-    (void)had;
-    matchFeatures(method);
-    *current = true;
+  if (k == 0) {                                                       // only a push: nothing to collect but its counts
+    for (size_t s = 0; s < S; s++) { Matcher* m = seq[s]; m->n_feat[0] = m->n_feat[4] = 0; m->n_feat[2] = m->n_feat[6] = -1; }
     return true;
   }
-  vector<int32_t> active;
-  // matchBegin clears the match lists of the sequences: the previous call's lists are collected into them further down
-  for (size_t s = 0; s < seq.size(); s++) {
-    seq[s]->syncCounts();
-    if (seq[s]->matchBegin(method)) { active.push_back((int32_t)s); seq[s]->p_matched_1.clear(); seq[s]->p_matched_2.clear(); }
-  }
-  const Matcher::parameters& p = seq[0]->param;
-  const int refine = seq[0]->refineMode();
-  bool pass1_ok = !active.empty();
-  if (pass1_ok && p.multi_stage) {
-    pass1_ok = matchPass(active, 0, method, false, 0);
-    if (pass1_ok) for (int32_t s : active) seq[s]->matchAfterPass1(method);
-  }
-  const bool had_previous = collectPending();
-  if (pass1_ok) issuePass2(active, method, p.multi_stage != 0, refine);
-  return had_previous;
+  if (visocu_set_lane(ctx, lane) != VISOCU_OK) return false;
+  vector<const visocu_pmatch*> l1(S), l2(S);
+  vector<int32_t> n1(S, 0), n2(S, 0), d1(S, 0), d2(S, 0), counts(4 * S, 0);
+  const int rc = visocu_match_fused_collect(ctx, l1.data(), n1.data(), d1.data(), l2.data(), n2.data(), d2.data(), 0, counts.data());
+  if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
+  visocu_set_lane(ctx, 4);                                            // fall-backs and odometry calls run on their own lane
+  for (size_t s = 0; s < S; s++) Matcher::takeFused(seq[s], rc == VISOCU_OK, &counts[4 * s], l1[s], n1[s], d1[s], l2[s], n2[s], d2[s], 0);
+  return rc == VISOCU_OK;
 }
-
-bool MatcherBatch::finishPipelined() { return collectPending(); }

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "matrix.h"
+#include "visocu.h"
 
 struct visocu_ctx;
 
@@ -103,6 +104,8 @@ private:
   // both passes of multi-stage flow matching as one submission (visocu_match_fused) for a group of matchers on one context
   static bool fusedAvailable(const Matcher& m, int32_t method);
   static void fusedMatch(visocu_ctx* ctx, const std::vector<Matcher*>& group, int32_t method);
+  static void takeFused(Matcher* m, bool ok, const int32_t* counts, const visocu_pmatch* l1, int32_t n1, int32_t d1,
+                        const visocu_pmatch* l2, int32_t n2, int32_t d2, int32_t method);
 
   parameters param;
   int32_t margin;
@@ -137,14 +140,15 @@ public:
   // one image (and optionally one right image) per sequence; dims as for Matcher::pushBack
   void pushBack(const uint8_t* const* I1, const uint8_t* const* I2, uint32_t* dims, bool replace, bool on_device = false);
   void matchFeatures(int32_t method);
-  // Pipelined variant for callers that walk many frames (the sequence runner): the second matching pass of this call is
-  // only enqueued - its outlier removal runs on the context's second stream while the caller pushes the next frames - and
-  // the lists of the PREVIOUS call are collected instead.  Returns true if the sequences now hold the previous call's
-  // matches (getMatches etc. refer to those).  finishPipelined() collects the last call.  Falls back to the synchronous
-  // matchFeatures (returning true with the current matches) where deferral is not available: see pipelineAvailable().
-  bool matchFeaturesPipelined(int32_t method, bool* current);
-  bool finishPipelined();
-  bool pipelineAvailable(int32_t method) const;
+  // Pipelined stepping for callers that walk many frames (the sequence runner): stepSubmit pushes one new frame per sequence
+  // and enqueues its flow matching against the previous frame - one submission, nothing is waited for -, stepCollect waits
+  // for the OLDEST submitted step and puts its matches into the sequences (getMatches, bucketFeatures ... then refer to that
+  // step).  Up to three steps may be in flight: consecutive steps use different lanes of the context and a ring of four
+  // frames per sequence, and a step that repeats is replayed as a CUDA graph.  Do not mix with pushBack / matchFeatures.
+  bool stepAvailable(int32_t method) const;
+  bool stepSubmit(const uint8_t* const* I1, uint32_t* dims, bool on_device);
+  bool stepCollect();
+  int32_t stepsInFlight() const { return (int32_t)(k_submit - k_collect); }
   int32_t size() const { return (int32_t)seq.size(); }
   Matcher& sequence(int32_t i) { return *seq[i]; }
   visocu_ctx* context() { return ctx; }
@@ -152,11 +156,8 @@ public:
 private:
   bool ensure(int32_t w, int32_t h);
   bool matchPass(const std::vector<int32_t>& active, int pass, int32_t method, bool use_prior, int refine);
-  bool issuePass2(const std::vector<int32_t>& active, int32_t method, bool use_prior, int refine);
-  bool collectPending();
-  std::vector<int32_t> pending_active, pending_cap;     // sequences and list capacities of the enqueued pass
-  int32_t pending_method;
-  bool pending;
+  int32_t step_dims[3];
+  int64_t k_submit, k_collect;                          // steps submitted / collected so far (stepSubmit / stepCollect)
   std::vector<Matcher*> seq;
   visocu_ctx* ctx;
   int device;

@@ -280,9 +280,9 @@ class Sfm:
         return out
 
 
-def set_pipeline(on):
-    """Deferred second matching pass in Runner.run (off by default)."""
-    lib().visob_set_pipeline(int(bool(on)))
+def set_pipeline_depth(depth):
+    """Steps that Runner.run keeps in flight per sequence (1 = synchronous, default 2, at most 3)."""
+    lib().visob_set_pipeline_depth(int(depth))
 
 
 def delaunay(x, y):

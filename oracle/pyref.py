@@ -108,6 +108,7 @@ class RefLib:
         L.ref_time_matcher_sequence.restype = C.c_double
         L.ref_time_mono_sequence.restype = C.c_double
         L.ref_find_best_plane.restype = C.c_double
+        L.ref_time_parallel.restype = C.c_double
         self.info = L.ref_build_info().decode()
 
     # ---- filters (w must be a multiple of 16; returns planes of the same shape)
@@ -478,3 +479,18 @@ def time_mono_sequence(ref, params, imgs):
     per = np.zeros(n - 1); ok = np.zeros(n - 1, np.int32); mot = np.zeros((n - 1, 4, 4))
     tot = ref.lib.ref_time_mono_sequence(C.byref(params), _p(imgs), C.c_size_t(h * w), _p(dims), n, _p(per), _p(ok), _p(mot))
     return tot, per, ok, mot
+
+
+def time_parallel(ref, mono_params, workload, imgs, imgs2, nthreads, warm_pairs, timed_pairs, bucket=None):
+    """The reference on nthreads persistent host threads (one sequence each); returns (wall seconds of the timed pairs,
+    pairs per thread).  workload: 0 flow, 1 stereo quad, 2 mono odometry."""
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    n, h, w = imgs.shape
+    dims = np.array([w, h, w], np.int32)
+    if imgs2 is not None:
+        imgs2 = np.ascontiguousarray(imgs2, np.uint8)
+    bm, bw, bh = bucket if bucket else (0, 50.0, 50.0)
+    done = np.zeros(nthreads, np.int32)
+    wall = ref.lib.ref_time_parallel(C.byref(mono_params), int(workload), _p(imgs), _p(imgs2), C.c_size_t(h * w), n, _p(dims), int(nthreads),
+                                     int(warm_pairs), int(timed_pairs), int(bm), C.c_float(bw), C.c_float(bh), _p(done))
+    return wall, done

@@ -27,6 +27,8 @@
 #include <limits>
 #include <chrono>
 #include <mutex>
+#include <thread>
+#include <atomic>
 #include <streambuf>
 #include <mm_malloc.h>
 
@@ -480,4 +482,57 @@ REF_API double ref_time_mono_sequence(const RefMonoParams* p, uint8_t* imgs, siz
     if (motions16) { Matrix T = vo.getMotion(); for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) motions16[16 * (k - 1) + 4 * i + j] = T.val[i][j]; }
   }
   return total;
+}
+
+// The reference on all host cores, for bench.py's reference arm and cpu_baseline: nthreads persistent threads, one
+// independent sequence each (the reference is single-threaded per sequence).  Every thread builds its own object, pushes
+// its first frame, runs warm_pairs frame pairs, meets the others at a barrier and then runs timed_pairs pairs; only those
+// are timed (thread creation, construction and the first frame are not).  workload 0: Matcher flow (pushBack +
+// matchFeatures(0) + getMatches), 1: stereo quad (+ bucketFeatures), 2: VisualOdometryMono::process.  Frames come from a
+// pool of nframes consecutive frames (imgs + k * stride; right images imgs2), walked back and forth so that consecutive
+// frames are always neighbours; thread t starts at frame 3 t.  Returns the wall-clock seconds from the barrier to the
+// last thread's finish; pairs_done (optional) receives the timed pairs of every thread.
+REF_API double ref_time_parallel(const RefMonoParams* mp, int workload, uint8_t* imgs, uint8_t* imgs2, size_t stride, int nframes,
+                                 const int32_t* dims, int nthreads, int warm_pairs, int timed_pairs, int bucket_max, float bw, float bh,
+                                 int32_t* pairs_done) {
+  std::atomic<int> ready(0), go(0);
+  std::vector<double> finish(nthreads, 0.0);
+  std::chrono::steady_clock::time_point t0;
+  auto frame_of = [&](int t, int k) { const int period = 2 * (nframes - 1); int i = (3 * t + k) % period; return i < nframes ? i : period - i; };
+  auto work = [&](int t) {
+    uint32_t d[3] = {(uint32_t)dims[0], (uint32_t)dims[1], (uint32_t)dims[2]};
+    CoutSilencer* quiet = nullptr; (void)quiet;
+    Matcher* m = nullptr; MonoProbe* vo = nullptr;
+    if (workload == 2) vo = new MonoProbe(to_ref(mp)); else m = new Matcher(to_ref(&mp->match));
+    int done = 0;
+    auto step = [&](int k) {
+      const int f = frame_of(t, k);
+      uint8_t* I1 = imgs + (size_t)f * stride;
+      uint8_t* I2 = (workload == 1 && imgs2) ? imgs2 + (size_t)f * stride : 0;
+      if (vo) { vo->process(I1, d, false); return; }
+      m->pushBack(I1, I2, d, false);
+      if (k == 0) return;
+      m->matchFeatures(workload == 1 ? 2 : 0, 0);
+      if (bucket_max > 0) m->bucketFeatures(bucket_max, bw, bh);
+      std::vector<Matcher::p_match> r = m->getMatches();
+      (void)r;
+    };
+    for (int k = 0; k <= warm_pairs; k++) step(k);
+    ready.fetch_add(1);
+    while (go.load() == 0) std::this_thread::yield();
+    for (int k = warm_pairs + 1; k <= warm_pairs + timed_pairs; k++) { step(k); done++; }
+    finish[t] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (pairs_done) pairs_done[t] = done;
+    delete m; delete vo;
+  };
+  CoutSilencer quiet;                                    // "Estimate F time" etc. of estimateMotion
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; t++) pool.emplace_back(work, t);
+  while (ready.load() < nthreads) std::this_thread::yield();
+  t0 = std::chrono::steady_clock::now();
+  go.store(1);
+  for (std::thread& th : pool) th.join();
+  double wall = 0;
+  for (double f : finish) wall = std::max(wall, f);
+  return wall;
 }

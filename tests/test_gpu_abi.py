@@ -84,15 +84,44 @@ def test_sad_extremes(ctx):
     assert cand >= 2 * n
 
 
-def test_deferred_matching_state_errors(ctx):
-    """visocu_match_deferred / visocu_match_collect: misuse is reported with a status, never a crash."""
+def test_fused_submit_collect_and_lanes(ctx, ref):
+    """visocu_match_fused_submit / _collect on two lanes of one context: misuse is reported with a status, never a crash,
+    and two steps in flight on different lanes deliver the lists of the reference."""
     import ctypes as C
+    import pyref
     lib = V.lib()
-    ctx.configure(V.Params(), 320, 200, 4)
-    n = np.zeros(1, np.int32); cap = np.array([16], np.int32); done = np.zeros(1, np.int32)
-    buf = np.zeros(16, V.P_MATCH); optr = (C.c_void_p * 1)(buf.ctypes.data)
-    rc = lib.visocu_match_collect(ctx.h, optr, cap.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p), done.ctypes.data_as(C.c_void_p))
-    assert rc != 0 and b'no deferred' in lib.visocu_last_error(ctx.h)
-    q = np.zeros(1, V.QUAD); q[0] = (0, 1, 2, 3)
-    rc = lib.visocu_match_deferred(ctx.h, 1, q.ctypes.data_as(C.c_void_p), 2, 1, 0, None, 0)      # quad: not deferrable
-    assert rc != 0 and b'deferred matching' in lib.visocu_last_error(ctx.h)
+    w, h = 500, 260
+    p = V.Params(); p.match_radius //= 2
+    ctx.configure(p, w, h, 4)
+    z = lambda n, t: np.zeros(n, t)
+    l1 = (C.c_void_p * 1)(); l2 = (C.c_void_p * 1)()
+    n1, n2, d1, d2, cnt = z(1, np.int32), z(1, np.int32), z(1, np.int32), z(1, np.int32), z(4, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.visocu_match_fused_collect(ctx.h, l1, vp(n1), vp(d1), l2, vp(n2), vp(d2), None, vp(cnt))
+    assert rc != 0 and b'no fused matching call' in lib.visocu_last_error(ctx.h)
+    assert lib.visocu_set_lane(ctx.h, 9) != 0 and b'out of range' in lib.visocu_last_error(ctx.h)
+    q = np.zeros(1, V.QUAD); q[0] = (0, -1, 1, -1)
+    rc = lib.visocu_match_fused_submit(ctx.h, 1, vp(q), 1, 0, -1)
+    assert rc != 0 and b'holds no features' in lib.visocu_last_error(ctx.h)
+    # three frames; frames 0, 1 pushed on lane 0, frame 2 on lane 1; pairs (0,1) and (1,2) in flight together
+    seq = synth.blob_sequence(3, w, h, seed=77)
+    assert lib.visocu_set_lane(ctx.h, 0) == 0
+    ctx.push_frames([0, 1], [seq[0], seq[1]], want_counts=False)
+    assert lib.visocu_match_fused_submit(ctx.h, 1, vp(q), 1, 0, -1) == 0
+    assert lib.visocu_match_fused_submit(ctx.h, 1, vp(q), 1, 0, -1) != 0 and b'not been collected' in lib.visocu_last_error(ctx.h)
+    assert lib.visocu_set_lane(ctx.h, 1) == 0
+    ctx.push_frames([2], [seq[2]], want_counts=False)
+    q2 = np.zeros(1, V.QUAD); q2[0] = (1, -1, 2, -1)
+    assert lib.visocu_match_fused_submit(ctx.h, 1, vp(q2), 1, 0, 0) == 0
+    got = []
+    for lane in (0, 1):
+        assert lib.visocu_set_lane(ctx.h, lane) == 0
+        assert lib.visocu_match_fused_collect(ctx.h, l1, vp(n1), vp(d1), l2, vp(n2), vp(d2), None, vp(cnt)) == 0
+        assert d1[0] == 1 and d2[0] == 1 and cnt.min() > 100
+        got.append(np.ctypeslib.as_array((C.c_uint8 * (48 * int(n2[0]))).from_address(l2[0])).view(V.P_MATCH).copy())
+    assert lib.visocu_set_lane(ctx.h, 0) == 0
+    rm = ref.matcher(pyref.MatcherParams())
+    rm.push(seq[0]); rm.push(seq[1]); rm.match_features(0)
+    assert len(got[0]) > 300 and got[0].tobytes() == rm.matches(2).tobytes()
+    rm.push(seq[2]); rm.match_features(0)
+    assert got[1].tobytes() == rm.matches(2).tobytes()

@@ -313,11 +313,12 @@ def test_structure_from_motion_facade():
     assert np.abs(sfm.pose() - pose).max() < 1e-5
 
 
-def test_pipelined_runner_equals_stepwise():
-    """runner.run walks K frames with the second matching pass of every step deferred (its outlier removal overlaps the
-    next step's feature and pass-1 kernels, MatcherBatch::matchFeaturesPipelined): per step and sequence the same match
-    counts as the stepwise runner, the same final lists, and for the odometry mode the same poses."""
-    S, T = 5, 5
+def test_pipelined_runner_equals_stepwise(ref):
+    """runner.run keeps several steps of every sequence in flight (MatcherBatch::stepSubmit / stepCollect: consecutive steps
+    on different lanes of the context, a ring of four frames per sequence, steps replayed as CUDA graphs once they repeat):
+    per step and sequence the same match counts as stepping synchronously, the same final lists as the reference, and for
+    the odometry mode the same poses.  Twelve steps, so that every lane runs plain, captured and replayed."""
+    S, T = 5, 12
     dims = np.array([500, 260, 500], np.int32)
     seqs = [synth.blob_sequence(T, 500, 260, seed=80 + s) for s in range(S)]
     imgs = [[np.ascontiguousarray(seqs[s][k]) for s in range(S)] for k in range(T)]
@@ -327,17 +328,22 @@ def test_pipelined_runner_equals_stepwise():
     counts_step = np.array([a.step(ptrs[k], dims)[1] for k in range(T)])
     want = [a.matches(s) for s in range(S)]
     a.close()
-    H.set_pipeline(True)
-    b = H.Runner(0, S, 2, 0, 0, mp)
-    secs, nm, ok = b.run(ptrs, dims)
-    got = [b.matches(s) for s in range(S)]
-    b.close()
-    H.set_pipeline(False)
-    assert np.array_equal(nm, counts_step) and nm[1:].min() > 300
     for s in range(S):
-        assert got[s].tobytes() == want[s].tobytes()
+        rm = ref.matcher(pyref.MatcherParams())
+        rm.push(seqs[s][T - 2]); rm.push(seqs[s][T - 1]); rm.match_features(0)
+        assert want[s].tobytes() == rm.matches(2).tobytes()
+    for depth in (1, 2, 3):
+        H.set_pipeline_depth(depth)
+        b = H.Runner(0, S, 2, 0, 0, mp)
+        secs, nm, ok = b.run(ptrs, dims)
+        got = [b.matches(s) for s in range(S)]
+        b.close()
+        assert np.array_equal(nm, counts_step) and nm[1:].min() > 300, depth
+        for s in range(S):
+            assert got[s].tobytes() == want[s].tobytes(), (depth, s)
+    H.set_pipeline_depth(2)
     # odometry mode
-    S, T = 3, 4
+    S, T = 3, 7
     seqs = [synth.corridor_sequence(T, seed=1234 + s) for s in range(S)]
     imgs = [[np.ascontiguousarray(seqs[s][k]) for s in range(S)] for k in range(T)]
     ptrs = [[i.ctypes.data for i in row] for row in imgs]
@@ -347,10 +353,8 @@ def test_pipelined_runner_equals_stepwise():
     oks = np.array([a.step(ptrs[k], dims)[2] for k in range(T)])
     want_T = [a.motion(s) for s in range(S)]; want_m = [a.matches(s) for s in range(S)]
     a.close()
-    H.set_pipeline(True)
     b = H.Runner(0, S, 2, 1, 0, hp)
     secs, nm, ok = b.run(ptrs, dims)
-    H.set_pipeline(False)
     assert np.array_equal(ok, oks) and ok[1:].min() == 1
     for s in range(S):
         assert b.matches(s).tobytes() == want_m[s].tobytes()
