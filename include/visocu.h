@@ -128,24 +128,27 @@ int  visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int3
  * until the next matching call on this context.  done1 / done2 say whether the outlier removal of the list ran on the
  * device (if done1[j] is 0 the second list of job j is meaningless: the caller votes on list 1 itself and repeats the second
  * pass with visocu_match); ranges_out[j] (optional, u_bins * v_bins entries) receives the prior ranges; counts (optional,
- * 4 per job) the sparse and dense record counts of f1p and of f1c.  At most 128 jobs. */
+ * 4 per job) the sparse and dense record counts of f1p and of f1c.  *list2_compact = 1: the records of list2 are the 24
+ * bytes of a flow match that say something - (u1p, v1p, i1p, u1c, v1c, i1c), six words per match; the other six fields of
+ * p_match are -1 (matcher.cpp:1037) and do not cross PCIe - else complete 48-byte records.  At most 128 jobs. */
 int  visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine,
                         const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
                         const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
-                        visocu_range* const* ranges_out, int32_t* counts);
+                        visocu_range* const* ranges_out, int32_t* counts, int32_t* list2_compact);
 /* The same call in two halves, for callers that keep several steps in flight: _submit enqueues everything on the current
  * lane and returns, _collect waits for that lane and delivers what visocu_match_fused delivers.  after_lane (or -1): the
  * lane on which the previous frames of the jobs were pushed, if it is not the current one - the matching then starts
- * behind that lane's feature kernels.  A step that repeats with the same frames, jobs and sizes (a runner walking
+ * behind that lane's feature kernels.  flags: 1 = deliver the prior ranges, 2 = deliver the first list as well (else
+ * list1[j] is null unless the device declined that list and the caller has to vote on it).  A step that repeats with the same frames, jobs and sizes (a runner walking
  * sequences through the lanes in turn) is captured as a CUDA graph and replayed: one graph launch per half step.
  * Lanes: a context holds several complete sets of per-step resources (stream, scratch and staging memory, result area);
  * visocu_set_lane(ctx, k), 0 <= k < 6, makes set k the one every following call works with.  Lane 0 is the default. */
 int  visocu_set_lane(visocu_ctx* ctx, int32_t lane);
-int  visocu_match_fused_submit(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine, int32_t want_ranges,
+int  visocu_match_fused_submit(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine, int32_t flags,
                                int32_t after_lane);
 int  visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
                                 const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
-                                visocu_range* const* ranges_out, int32_t* counts);
+                                visocu_range* const* ranges_out, int32_t* counts, int32_t* list2_compact);
 /* Matcher::removeOutliers alone on caller-supplied match lists (host memory, compacted in place).  status[j] = 0: done,
  * 1: list unchanged, not handled by the device path (see visocu_match). */
 int  visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t method, visocu_pmatch* const* inout, const int32_t* n,

@@ -106,7 +106,7 @@ static cudaError_t make_wait_flag(volatile uint32_t** flag, void** dev) {
 #define VISO_LANE_FIELDS(X) X(stream) X(scratch) X(scratch_bytes) X(scratch2) X(scratch2_bytes) X(pinned) X(pinned_bytes) X(pinned2) \
   X(pinned2_bytes) X(d_ranges) X(d_ranges_bytes) X(pin_ranges) X(deliver) X(deliver_dev) X(deliver_bytes) X(deliver2) X(deliver2_bytes) \
   X(wait_flag) X(wait_flag_dev) X(wait_seq) X(counts_stage) X(img_stage) X(img_stage_bytes) X(src_table) X(src_table_pin) X(ev_push) \
-  X(g_push) X(g_match) X(fused_pending) X(fused_n) X(fused_ranges) X(fused_seq) X(fused_jobs)
+  X(g_push) X(g_match) X(fused_pending) X(fused_n) X(fused_ranges) X(fused_list1) X(fused_seq) X(fused_jobs)
 
 int visocu_use_lane(visocu_ctx* ctx, int lane) {
   if (lane < 0 || lane >= VISO_LANES) return visocu_set_error(ctx, VISOCU_EINVAL, "lane %d out of range", lane);

@@ -855,10 +855,14 @@ __global__ void __launch_bounds__(256) k_deliver(DeliverArgs a) {
   }
   if (!a.with_lists) return;
   const int n1 = a.words1[16 * j], n2 = a.words2[16 * j];
-  const uint4* s1 = (const uint4*)(a.lists1 + a.ostride1 * j); uint4* d1 = (uint4*)(out + a.off1);
-  for (int i = tid; i < 3 * n1; i += 256) d1[i] = s1[i];
-  const uint4* s2 = (const uint4*)(a.lists2 + a.ostride2 * j); uint4* d2 = (uint4*)(out + a.off2);
-  for (int i = tid; i < 3 * n2; i += 256) d2[i] = s2[i];
+  if (a.with_lists & 2) {
+    const uint4* s1 = (const uint4*)(a.lists1 + a.ostride1 * j); uint4* d1 = (uint4*)(out + a.off1);
+    for (int i = tid; i < 3 * n1; i += 256) d1[i] = s1[i];
+  }
+  // Flow matches carry -1 in the six fields of the right images (matcher.cpp:1037): only the 24 bytes that say something
+  // cross PCIe - (u1p, v1p, i1p) and (u1c, v1c, i1c) as six words per record - and the host puts the constants back.
+  const uint32_t* s2 = (const uint32_t*)(a.lists2 + a.ostride2 * j); uint32_t* d2 = (uint32_t*)(out + a.off2);
+  for (int i = tid; i < 6 * n2; i += 256) { const int r = i / 6, w = i - 6 * r; d2[i] = s2[12 * r + (w < 3 ? w : w + 3)]; }
 }
 
 namespace {
@@ -871,7 +875,8 @@ FusedLayout fused_layout(const Geometry& g) {
   // the header does, and the lists are copied once their lengths are known.
   L.off1 = 256; L.off2 = L.off1 + align_up((size_t)(g.cap[0] + 1) * 48, 256);
   const size_t full = L.off2 + align_up((size_t)(g.cap[1] + 1) * 48, 256);
-  L.zero_copy = full <= ((size_t)8 << 20);
+  static const bool allow = [] { const char* e = getenv("VISOCU_ZEROCOPY"); return !(e && e[0] == '0'); }();   // 0: always copy the lists after the header
+  L.zero_copy = allow && full <= ((size_t)8 << 20);
   L.dstride = L.zero_copy ? full : 256;
   return L;
 }
@@ -879,7 +884,7 @@ FusedLayout fused_layout(const Geometry& g) {
 
 // everything of a fused call that is enqueued on the lane's stream (replayable as a graph: depends on the job list, the
 // refinement mode, the ranges flag and the outlier bound only)
-static int fused_enqueue(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine, bool want_ranges) {
+static int fused_enqueue(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine, bool want_ranges, bool want_list1) {
   const Geometry& g = ctx->g;
   const int nbin = g.ub * g.vb;
   const FusedLayout L = fused_layout(g);
@@ -901,15 +906,17 @@ static int fused_enqueue(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* job
   DeliverArgs da;
   da.jobs2 = (const MatchJob*)B.dev_jobs; da.words1 = A.dev_words; da.words2 = B.dev_words;
   da.lists1 = A.dev_lists; da.lists2 = B.dev_lists; da.ostride1 = A.ostride; da.ostride2 = B.ostride;
-  da.dst = (uint8_t*)ctx->deliver_dev; da.dstride = L.dstride; da.off1 = L.off1; da.off2 = L.off2; da.with_lists = L.zero_copy ? 1 : 0;
+  da.dst = (uint8_t*)ctx->deliver_dev; da.dstride = L.dstride; da.off1 = L.off1; da.off2 = L.off2;
+  da.with_lists = L.zero_copy ? (want_list1 ? 3 : 1) : 0;
   k_deliver<<<n_jobs, 256, 0, ctx->stream>>>(da);
   CU_LAUNCH_CHECK(ctx);
   if (want_ranges) CU_TRY(ctx, cudaMemcpyAsync(ctx->pin_ranges, d_rng, L.rstride * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
   return VISOCU_OK;
 }
 
-extern "C" int visocu_match_fused_submit(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine, int32_t want_ranges,
+extern "C" int visocu_match_fused_submit(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine, int32_t flags,
                                          int32_t after_lane) {
+  const int32_t want_ranges = flags;
   if (!ctx) return VISOCU_EINVAL;
   if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
   if (n_jobs <= 0 || n_jobs > VISO_MAX_BATCH || !jobs) return visocu_set_error(ctx, VISOCU_EINVAL, "bad fused match arguments (at most %d jobs)", VISO_MAX_BATCH);
@@ -954,19 +961,19 @@ extern "C" int visocu_match_fused_submit(visocu_ctx* ctx, int32_t n_jobs, const 
   mix(&n_jobs, sizeof n_jobs); mix(jobs, sizeof(visocu_quad) * (size_t)n_jobs); mix(&refine, sizeof refine); mix(&want_ranges, sizeof want_ranges);
   mix(ctx->ro_bound, sizeof ctx->ro_bound);
   ctx->in_step++;
-  const int rc = visocu_run_or_replay(ctx, ctx->g_match, key, [&]() -> int { return fused_enqueue(ctx, n_jobs, jobs, refine, want_ranges != 0); });
+  const int rc = visocu_run_or_replay(ctx, ctx->g_match, key, [&]() -> int { return fused_enqueue(ctx, n_jobs, jobs, refine, (want_ranges & 1) != 0, (want_ranges & 2) != 0); });
   ctx->in_step--;
   if (rc) return rc;
   CU_TRY(ctx, visocu_stream_signal(ctx, &ctx->fused_seq));
-  ctx->fused_pending = true; ctx->fused_n = n_jobs; ctx->fused_ranges = want_ranges != 0;
+  ctx->fused_pending = true; ctx->fused_n = n_jobs; ctx->fused_ranges = (want_ranges & 1) != 0; ctx->fused_list1 = (want_ranges & 2) != 0;
   ctx->fused_jobs.assign(jobs, jobs + n_jobs);
   return VISOCU_OK;
 }
 
 extern "C" int visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
                                           const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
-                                          visocu_range* const* ranges_out, int32_t* counts) {
-  if (!ctx || !list1 || !n1 || !done1 || !list2 || !n2 || !done2) return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad collect arguments") : VISOCU_EINVAL;
+                                          visocu_range* const* ranges_out, int32_t* counts, int32_t* list2_compact) {
+  if (!ctx || !list1 || !n1 || !done1 || !list2 || !n2 || !done2 || !list2_compact) return ctx ? visocu_set_error(ctx, VISOCU_EINVAL, "bad collect arguments") : VISOCU_EINVAL;
   if (!ctx->fused_pending) return visocu_set_error(ctx, VISOCU_ESTATE, "no fused matching call to collect on this lane");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   ctx->fused_pending = false;
@@ -975,6 +982,7 @@ extern "C" int visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch**
   const Geometry& g = ctx->g;
   const int nbin = g.ub * g.vb, n_jobs = ctx->fused_n;
   const FusedLayout L = fused_layout(g);
+  *list2_compact = L.zero_copy ? 1 : 0;
   const visocu_quad* jobs = ctx->fused_jobs.data();
   const visocu_deferred& A = ctx->part[0];
   const visocu_deferred& B = ctx->part[1];
@@ -988,9 +996,9 @@ extern "C" int visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch**
       (p ? n2 : n1)[j] = n; (p ? done2 : done1)[j] = status == 0 ? 1 : 0;
       if (status == 0 && n > 3) { for (int k = 0; k < 4; k++) ctx->ro_ns[k] += (uint64_t)w[4 + k]; ctx->ro_jobs++; }
       else if (status != 0) { ctx->ro_declined++; ctx->ro_reason[status & 3]++; ctx->ro_declined_n += (uint64_t)w[3]; }
-      ctx->d2h_bytes += 64 + (uint64_t)n * 48;
+      ctx->d2h_bytes += 64 + (L.zero_copy ? (p ? (uint64_t)n * 24 : (ctx->fused_list1 ? (uint64_t)n * 48 : 0)) : (uint64_t)n * 48);
     }
-    if (L.zero_copy) { list1[j] = (const visocu_pmatch*)(base + L.off1); list2[j] = (const visocu_pmatch*)(base + L.off2); }
+    if (L.zero_copy) { list1[j] = ctx->fused_list1 ? (const visocu_pmatch*)(base + L.off1) : nullptr; list2[j] = (const visocu_pmatch*)(base + L.off2); }
     const int fr[2] = {jobs[j].f1p, jobs[j].f1c};
     for (int k = 0; k < 2; k++) {
       ctx->h_counts[2 * (size_t)fr[k] + 0] = hdr[32 + 3 * k]; ctx->h_counts[2 * (size_t)fr[k] + 1] = hdr[33 + 3 * k];
@@ -1005,6 +1013,27 @@ extern "C" int visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch**
     ctx->d2h_bytes += 24;
   }
   if (overflow >= 0) return visocu_set_error(ctx, VISOCU_ECAPACITY, "feature list of frame %d overflowed", overflow);
+  if (L.zero_copy && !ctx->fused_list1) {
+    // the first list stayed on the device; a job whose first list the outlier kernel declined needs it on the host
+    size_t total = 0;
+    for (int j = 0; j < n_jobs; j++) if (!done1[j]) total += align_up((size_t)n1[j] * 48 + 48, 256);
+    if (total > 0) {
+      if (total > ctx->deliver2_bytes) {
+        if (ctx->deliver2) cudaFreeHost(ctx->deliver2);
+        ctx->deliver2 = nullptr; ctx->deliver2_bytes = 0;
+        CU_TRY(ctx, cudaMallocHost(&ctx->deliver2, total));
+        ctx->deliver2_bytes = total;
+      }
+      uint8_t* dst = (uint8_t*)ctx->deliver2;
+      for (int j = 0; j < n_jobs; j++) {
+        if (done1[j]) continue;
+        list1[j] = (const visocu_pmatch*)dst;
+        if (n1[j] > 0) CU_TRY(ctx, cudaMemcpyAsync(dst, A.dev_lists + A.ostride * j, (size_t)n1[j] * 48, cudaMemcpyDeviceToHost, ctx->stream));
+        dst += align_up((size_t)n1[j] * 48 + 48, 256);
+      }
+      CU_TRY(ctx, visocu_stream_wait(ctx));
+    }
+  }
   if (!L.zero_copy) {
     size_t total = 0;
     for (int j = 0; j < n_jobs; j++) total += align_up((size_t)n1[j] * 48 + 48, 256) + align_up((size_t)n2[j] * 48 + 48, 256);
@@ -1035,10 +1064,10 @@ extern "C" int visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch**
 extern "C" int visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine,
                                   const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
                                   const visocu_pmatch** list2, int32_t* n2, int32_t* done2,
-                                  visocu_range* const* ranges_out, int32_t* counts) {
-  const int rc = visocu_match_fused_submit(ctx, n_jobs, jobs, refine, ranges_out ? 1 : 0, -1);
+                                  visocu_range* const* ranges_out, int32_t* counts, int32_t* list2_compact) {
+  const int rc = visocu_match_fused_submit(ctx, n_jobs, jobs, refine, (ranges_out ? 1 : 0) | 2, -1);
   if (rc) return rc;
-  return visocu_match_fused_collect(ctx, list1, n1, done1, list2, n2, done2, ranges_out, counts);
+  return visocu_match_fused_collect(ctx, list1, n1, done1, list2, n2, done2, ranges_out, counts, list2_compact);
 }
 
 extern "C" int visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, int32_t mode, visocu_pmatch* inout, int32_t n,

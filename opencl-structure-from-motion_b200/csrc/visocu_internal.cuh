@@ -71,7 +71,7 @@ struct visocu_lane {
   const uint8_t** src_table = nullptr; const uint8_t** src_table_pin = nullptr;   // image pointers of a push (device / pinned copy)
   cudaEvent_t ev_push = nullptr;       // recorded behind the feature kernels of the lane's last push
   visocu_graph g_push, g_match;        // the two halves of a step, captured once their shape repeats
-  bool fused_pending = false; int fused_n = 0; bool fused_ranges = false; uint32_t fused_seq = 0;
+  bool fused_pending = false; int fused_n = 0; bool fused_ranges = false, fused_list1 = false; uint32_t fused_seq = 0;
   std::vector<visocu_quad> fused_jobs;  // the submitted, not yet collected fused call of the lane
   bool created = false;
 };
@@ -85,7 +85,7 @@ struct visocu_ctx {
   visocu_lane lanes[VISO_LANES];     // parked lanes (the entry of the current lane is stale)
   int use_graphs = 1;                // VISOCU_GRAPHS=0: always enqueue kernel by kernel
   int in_step = 0;                   // > 0 while a (replayable) step is being enqueued: buffer growth does not drop the graphs
-  bool fused_pending = false; int fused_n = 0; bool fused_ranges = false; uint32_t fused_seq = 0;   // per lane, see VISO_LANE_FIELDS
+  bool fused_pending = false; int fused_n = 0; bool fused_ranges = false, fused_list1 = false; uint32_t fused_seq = 0;   // per lane, see VISO_LANE_FIELDS
   std::vector<visocu_quad> fused_jobs;
   int ro_bound_seen[2] = {0, 0};
   int ro_bound[2] = {-1, -1};        // longest match list seen per pass (shared-memory size of the outlier kernel in lazy mode)

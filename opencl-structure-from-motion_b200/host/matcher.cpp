@@ -272,15 +272,16 @@ void Matcher::fusedMatch(visocu_ctx* ctx, const vector<Matcher*>& group, int32_t
     m->ranges.resize(nbin);
     rp[k] = reinterpret_cast<visocu_range*>(m->ranges.data());
   }
+  int32_t compact = 0;
   const int rc = visocu_match_fused(ctx, (int32_t)n, quads.data(), group[0]->refineMode(), l1.data(), n1.data(), d1.data(),
-                                    l2.data(), n2.data(), d2.data(), rp.data(), counts.data());
+                                    l2.data(), n2.data(), d2.data(), rp.data(), counts.data(), &compact);
   if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
-  for (size_t k = 0; k < n; k++) takeFused(group[k], rc == VISOCU_OK, &counts[4 * k], l1[k], n1[k], d1[k], l2[k], n2[k], d2[k], method);
+  for (size_t k = 0; k < n; k++) takeFused(group[k], rc == VISOCU_OK, &counts[4 * k], l1[k], n1[k], d1[k], l2[k], n2[k], d2[k], method, compact != 0);
 }
 
 // results of a fused call for one matcher
 void Matcher::takeFused(Matcher* m, bool ok, const int32_t* counts, const visocu_pmatch* l1, int32_t n1, int32_t d1,
-                        const visocu_pmatch* l2, int32_t n2, int32_t d2, int32_t method) {
+                        const visocu_pmatch* l2, int32_t n2, int32_t d2, int32_t method, bool compact) {
   if (!ok) { m->p_matched_1.clear(); m->p_matched_2.clear(); m->ro_done[0] = m->ro_done[1] = false; return; }
   // the record counts arrive with the results (the frames were pushed without reading them back)
   m->n_feat[0] = counts[0]; m->n_feat[4] = counts[1];
@@ -290,8 +291,22 @@ void Matcher::takeFused(Matcher* m, bool ok, const int32_t* counts, const visocu
   if (m->n_feat[0] == 0 || m->n_feat[2] == 0 || m->n_feat[4] == 0 || m->n_feat[6] == 0) return;
   const p_match* a1 = reinterpret_cast<const p_match*>(l1);
   const p_match* a2 = reinterpret_cast<const p_match*>(l2);
-  m->p_matched_1.assign(a1, a1 + n1);
-  m->p_matched_2.assign(a2, a2 + n2);
+  if (a1) m->p_matched_1.assign(a1, a1 + n1); else m->p_matched_1.clear();     // not delivered (sequence runner): nobody reads it
+  if (!compact) {
+    m->p_matched_2.assign(a2, a2 + n2);
+  } else {
+    // six words per flow match crossed PCIe: (u1p, v1p, i1p, u1c, v1c, i1c); the fields of the right images are -1
+    struct Half { float u, v; int32_t i; };
+    const Half* h = reinterpret_cast<const Half*>(l2);
+    m->p_matched_2.resize((size_t)n2);
+    for (int32_t i = 0; i < n2; i++) {
+      p_match& o = m->p_matched_2[i];
+      o.u1p = h[2 * i].u; o.v1p = h[2 * i].v; o.i1p = h[2 * i].i;
+      o.u2p = -1; o.v2p = -1; o.i2p = -1;
+      o.u1c = h[2 * i + 1].u; o.v1c = h[2 * i + 1].v; o.i1c = h[2 * i + 1].i;
+      o.u2c = -1; o.v2c = -1; o.i2c = -1;
+    }
+  }
   m->ro_done[0] = d1 != 0;
   m->ro_done[1] = d2 != 0;
   if (!m->ro_done[0]) {
@@ -666,9 +681,10 @@ bool MatcherBatch::stepCollect() {
   if (visocu_set_lane(ctx, lane) != VISOCU_OK) return false;
   vector<const visocu_pmatch*> l1(S), l2(S);
   vector<int32_t> n1(S, 0), n2(S, 0), d1(S, 0), d2(S, 0), counts(4 * S, 0);
-  const int rc = visocu_match_fused_collect(ctx, l1.data(), n1.data(), d1.data(), l2.data(), n2.data(), d2.data(), 0, counts.data());
+  int32_t compact = 0;
+  const int rc = visocu_match_fused_collect(ctx, l1.data(), n1.data(), d1.data(), l2.data(), n2.data(), d2.data(), 0, counts.data(), &compact);
   if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
   visocu_set_lane(ctx, 4);                                            // fall-backs and odometry calls run on their own lane
-  for (size_t s = 0; s < S; s++) Matcher::takeFused(seq[s], rc == VISOCU_OK, &counts[4 * s], l1[s], n1[s], d1[s], l2[s], n2[s], d2[s], 0);
+  for (size_t s = 0; s < S; s++) Matcher::takeFused(seq[s], rc == VISOCU_OK, &counts[4 * s], l1[s], n1[s], d1[s], l2[s], n2[s], d2[s], 0, compact != 0);
   return rc == VISOCU_OK;
 }

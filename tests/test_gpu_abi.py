@@ -97,7 +97,8 @@ def test_fused_submit_collect_and_lanes(ctx, ref):
     l1 = (C.c_void_p * 1)(); l2 = (C.c_void_p * 1)()
     n1, n2, d1, d2, cnt = z(1, np.int32), z(1, np.int32), z(1, np.int32), z(1, np.int32), z(4, np.int32)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.visocu_match_fused_collect(ctx.h, l1, vp(n1), vp(d1), l2, vp(n2), vp(d2), None, vp(cnt))
+    compact = C.c_int32()
+    rc = lib.visocu_match_fused_collect(ctx.h, l1, vp(n1), vp(d1), l2, vp(n2), vp(d2), None, vp(cnt), C.byref(compact))
     assert rc != 0 and b'no fused matching call' in lib.visocu_last_error(ctx.h)
     assert lib.visocu_set_lane(ctx.h, 9) != 0 and b'out of range' in lib.visocu_last_error(ctx.h)
     q = np.zeros(1, V.QUAD); q[0] = (0, -1, 1, -1)
@@ -116,9 +117,18 @@ def test_fused_submit_collect_and_lanes(ctx, ref):
     got = []
     for lane in (0, 1):
         assert lib.visocu_set_lane(ctx.h, lane) == 0
-        assert lib.visocu_match_fused_collect(ctx.h, l1, vp(n1), vp(d1), l2, vp(n2), vp(d2), None, vp(cnt)) == 0
+        assert lib.visocu_match_fused_collect(ctx.h, l1, vp(n1), vp(d1), l2, vp(n2), vp(d2), None, vp(cnt), C.byref(compact)) == 0
         assert d1[0] == 1 and d2[0] == 1 and cnt.min() > 100
-        got.append(np.ctypeslib.as_array((C.c_uint8 * (48 * int(n2[0]))).from_address(l2[0])).view(V.P_MATCH).copy())
+        assert compact.value == 1 and not l1[0]                       # flags 0: the first list stays on the device
+        # compact flow records: (u1p, v1p, i1p, u1c, v1c, i1c), the other fields of p_match are -1
+        half = np.dtype([('u', 'f4'), ('v', 'f4'), ('i', 'i4')])
+        raw = np.ctypeslib.as_array((C.c_uint8 * (24 * int(n2[0]))).from_address(l2[0])).view(half).reshape(-1, 2)
+        m = np.zeros(int(n2[0]), V.P_MATCH)
+        for f in ('u2p', 'v2p', 'i2p', 'u2c', 'v2c', 'i2c'):
+            m[f] = -1
+        m['u1p'], m['v1p'], m['i1p'] = raw[:, 0]['u'], raw[:, 0]['v'], raw[:, 0]['i']
+        m['u1c'], m['v1c'], m['i1c'] = raw[:, 1]['u'], raw[:, 1]['v'], raw[:, 1]['i']
+        got.append(m)
     assert lib.visocu_set_lane(ctx.h, 0) == 0
     rm = ref.matcher(pyref.MatcherParams())
     rm.push(seq[0]); rm.push(seq[1]); rm.match_features(0)
