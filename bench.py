@@ -325,7 +325,7 @@ def extra_workloads(args):
     todo = [('quad', ['--workload', 'quad']), ('mono', ['--workload', 'mono']), ('mono_bucket1000', ['--workload', 'mono', '--bucket', '1000']),
             ('flow_3840x2160', ['--workload', 'flow4k', '--sequences', '16', '--steps', '6'])]
     for name, extra in todo:
-        if name.split('_')[0] == args.workload and '--bucket' not in extra:
+        if extra[1] == args.workload and '--bucket' not in extra and int(args.bucket) == 2:
             continue
         cmd = [sys.executable, os.path.abspath(__file__), '--steps', '20', '--warmup', '3', '--no-extra', '--no-cpu-baseline', '--no-roofline'] + extra
         try:

@@ -857,22 +857,35 @@ __global__ void __launch_bounds__(CELLS_PER_BLOCK) k_emit_records(Geometry g, co
     if (all > g.cap[p]) { F.counts[2] = 1; all = g.cap[p]; }
     F.counts[p] = all;
   }
-  for (int e = wid; e < total; e += CELLS_PER_BLOCK / 32) {
-    if (base + e >= g.cap[p]) break;
-    const uint32_t ent = s_list[e];
-    const int u = ent & 0x1FFF, v = (ent >> 13) & 0x1FFF, cls = ent >> 26;
-    const int s = lane >> 1;
-    const uint8_t* plane = (lane & 1) ? F.dv : F.du;
-    uint32_t byte = plane[(size_t)(v + c_desc_oy[s]) * g.bplm + u + c_desc_ox[s]];
-    uint32_t w = byte << (8 * (lane & 3));
-    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
-    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
-    uint32_t dw = __shfl_sync(0xFFFFFFFFu, w, ((lane - 4) & 7) * 4);
-    if (lane < 12) {
-      int32_t out;
-      if (lane == 0) out = u * g.scale; else if (lane == 1) out = v * g.scale; else if (lane == 2) out = 0;
-      else if (lane == 3) out = cls; else out = (int32_t)dw;
-      F.rec[p][(size_t)(base + e) * 12 + lane] = out;
+  // four records per warp and round: the byte gathers of a round are independent loads in flight together
+  constexpr int NWARP = CELLS_PER_BLOCK / 32, UNR = 4;
+  const int s = lane >> 1;
+  const uint8_t* plane = (lane & 1) ? F.dv : F.du;
+  const int ox = c_desc_ox[s], oy = c_desc_oy[s];
+  const int limit = min(total, g.cap[p] - base);
+  for (int e0 = wid; e0 < limit; e0 += NWARP * UNR) {
+    uint32_t ent[UNR], byte[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      const int e = e0 + k * NWARP;
+      ent[k] = e < limit ? s_list[e] : s_list[e0];
+      const int u = ent[k] & 0x1FFF, v = (ent[k] >> 13) & 0x1FFF;
+      byte[k] = plane[(size_t)(v + oy) * g.bplm + u + ox];
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      const int e = e0 + k * NWARP;
+      const int u = ent[k] & 0x1FFF, v = (ent[k] >> 13) & 0x1FFF, cls = ent[k] >> 26;
+      uint32_t w = byte[k] << (8 * (lane & 3));
+      w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+      w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
+      const uint32_t dw = __shfl_sync(0xFFFFFFFFu, w, ((lane - 4) & 7) * 4);
+      if (lane < 12 && e < limit) {
+        int32_t out;
+        if (lane == 0) out = u * g.scale; else if (lane == 1) out = v * g.scale; else if (lane == 2) out = 0;
+        else if (lane == 3) out = cls; else out = (int32_t)dw;
+        F.rec[p][(size_t)(base + e) * 12 + lane] = out;
+      }
     }
   }
 }

@@ -358,6 +358,20 @@ __constant__ int8_t c_sd_plane[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 
 __constant__ int8_t c_sd_dx[16] = {0, -2, 0, 2, -1, 0, 0, 1, -2, 0, 2, 0, 0, -1, 1, 0};
 __constant__ int8_t c_sd_dy[16] = {-2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2, -1, 0, 0, 1};
 
+// SAD of the 16-byte descriptors at a (image 1) and b (image 2); the pointers address the centre pixel in the du and dv
+// planes.  The sample list is spelled out so that every load is [row pointer + immediate]: (plane, dx, dy) as in the
+// tables above.
+#define VISO_SD_LIST(X) X(0, 0, -2) X(0, -2, -1) X(0, 0, -1) X(0, 2, -1) X(0, -1, 0) X(0, 0, 0) X(0, 0, 0) X(0, 1, 0) \
+                        X(0, -2, 1) X(0, 0, 1) X(0, 2, 1) X(0, 0, 2) X(1, 0, -1) X(1, -1, 0) X(1, 1, 0) X(1, 0, 1)
+__device__ __forceinline__ int sd_cost(const uint8_t* __restrict__ au, const uint8_t* __restrict__ av, const uint8_t* __restrict__ bu,
+                                       const uint8_t* __restrict__ bv, int bpl) {
+  unsigned sad = 0;
+#define X(P, DX, DY) sad = __usad((unsigned)(P ? av : au)[(DY) * bpl + (DX)], (unsigned)(P ? bv : bu)[(DY) * bpl + (DX)], sad);
+  VISO_SD_LIST(X)
+#undef X
+  return (int)sad;
+}
+
 // one warp relocates (u2,v2) in image 2 to the best of the 5x5 positions around it; lane = candidate
 __device__ __forceinline__ void relocate(const uint8_t* du1, const uint8_t* dv1, const uint8_t* du2, const uint8_t* dv2,
                                          int bpl, int w, int h, float u1, float v1, float& u2, float& v2, int lane) {
@@ -366,16 +380,8 @@ __device__ __forceinline__ void relocate(const uint8_t* du1, const uint8_t* dv1,
   int key = 0x7FFFFFFF;
   if (lane < 25) {
     const int cu = (int)u2 + lane % 5 - 2, cv = (int)v2 + lane / 5 - 2;
-    int sad = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      const int dx = c_sd_dx[k], dy = c_sd_dy[k];
-      const uint8_t* p1 = c_sd_plane[k] ? dv1 : du1;
-      const uint8_t* p2 = c_sd_plane[k] ? dv2 : du2;
-      int a = p1[(size_t)(iv1 + dy) * bpl + iu1 + dx], b = p2[(size_t)(cv + dy) * bpl + cu + dx];
-      sad += abs(a - b);
-    }
-    key = sad * 32 + lane;
+    const size_t o1 = (size_t)iv1 * bpl + iu1, o2 = (size_t)cv * bpl + cu;
+    key = sd_cost(du1 + o1, dv1 + o1, du2 + o2, dv2 + o2, bpl) * 32 + lane;
   }
   key = __reduce_min_sync(0xFFFFFFFFu, key);
   const int best = key & 31;
@@ -400,14 +406,8 @@ __device__ __forceinline__ bool parabolic(const uint8_t* du1, const uint8_t* dv1
     int sad = 0x7FFFFF;
     if (idx < 49) {
       const int cu = iu2 + idx % 7 - 3, cv = iv2 + idx / 7 - 3;
-      sad = 0;
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const int dx = c_sd_dx[k], dy = c_sd_dy[k];
-        const uint8_t* p1 = c_sd_plane[k] ? dv1 : du1;
-        const uint8_t* p2 = c_sd_plane[k] ? dv2 : du2;
-        sad += abs((int)p1[(size_t)(iv1 + dy) * bpl + iu1 + dx] - (int)p2[(size_t)(cv + dy) * bpl + cu + dx]);
-      }
+      const size_t o1 = (size_t)iv1 * bpl + iu1, o2 = (size_t)cv * bpl + cu;
+      sad = sd_cost(du1 + o1, dv1 + o1, du2 + o2, dv2 + o2, bpl);
     }
     cost[r] = sad;
   }
