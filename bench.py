@@ -269,7 +269,9 @@ def run_ours(args, rank, world, local_rank):
     S = args.sequences if args.scaling == 'weak' else max(1, args.sequences // world)
     K, Wm = args.steps, max(args.warmup, GRAPH_WARMUP)
     # host workers per GPU: one per core of the rank's share, but at least 8 and at most one per 2 sequences
-    threads = args.threads or max(8, (os.cpu_count() or 1) // max(1, min(world, 8)))
+    # (at most 16: beyond that the batches of a worker get too small to fill the GPU - measured 41.6 k pairs/s with 32 workers
+    # x 2 sequences against 53 k with 16 x 4)
+    threads = args.threads or min(16, max(8, (os.cpu_count() or 1) // max(1, min(world, 8))))
     threads = max(1, min(threads, S))
     if threads * world > (os.cpu_count() or 1):
         # more workers than cores: waiting workers sleep between polls instead of yielding
@@ -294,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
         roof = roofline_leg(local_rank, st, mp, half, max(5, min(K, 20)))
         roof2 = roofline_leg(local_rank, st, mp, 1 - half, max(5, min(K, 20)))
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` captures
-        traffic = {(1241, 1): (162316544, 'profiles/r2_filter_nms_half_summary.md'), (1241, 0): (147268864, 'profiles/r2_filter_nms_full_summary.md')}
+        traffic = {(1241, 1): (159603200, 'profiles/r2_filter_nms_summary.md (r2_filter_nms_half_raw.csv)'), (1241, 0): (144969984, 'profiles/r2_filter_nms_summary.md (r2_filter_nms_full_raw.csv)')}
         for r in (roof, roof2):
             tr = traffic.get((st.W, int(r['bytes_per_pixel'] == 3.5)))
             r['traffic'] = tr[0] if tr else None
@@ -418,7 +420,7 @@ def main():
             'vs_baseline': None, 'dtype': 'u8', 'data': 'dry-run' if args.dry_run else 'synthetic',
             'config': {'workload': workload_name, 'sequences_per_gpu': S, 'frame_pairs_per_step': S * world,
                        'host_threads_per_gpu': threads, 'host_cores': cores,
-                       'steps_in_flight_per_sequence': int(os.environ.get('VISOB_DEPTH', '2')) if args.workload in ('flow', 'mono', 'flow4k') else 1,
+                       'steps_in_flight_per_sequence': int(os.environ.get('VISOB_DEPTH', '3')) if args.workload in ('flow', 'mono', 'flow4k') else 1,
                        'timing': 'wall clock of the K steps inside the host library between barriers, device idle on both sides (event_ms = CUDA '
                                  'events around the same region: %.3f)' % res_dev.get('event_ms', 0.0),
                        'inputs': 'frames resident in HBM (pushBackDevice); every step uses new frames, %d sequences x %.2f MB per step, L2 not flushed '

@@ -5,7 +5,7 @@
 namespace visob {
 void set_device(int device);     // affects Matcher / filter:: objects created afterwards by this thread
 int current_device();
-void set_pipeline_depth(int depth);   // steps the sequence runner keeps in flight per sequence (1 .. 3, default 2; VISOB_DEPTH)
+void set_pipeline_depth(int depth);   // steps the sequence runner keeps in flight per sequence (1 .. 3, default 3; VISOB_DEPTH)
 int pipeline_depth();
 }
 #endif

@@ -42,7 +42,7 @@ static std::atomic<int> g_depth(-1);
 void set_pipeline_depth(int depth) { g_depth = depth < 1 ? 1 : (depth > 3 ? 3 : depth); }
 int pipeline_depth() {
   int v = g_depth.load();
-  if (v < 0) { const char* e = getenv("VISOB_DEPTH"); v = e ? atoi(e) : 2; v = v < 1 ? 1 : (v > 3 ? 3 : v); g_depth = v; }
+  if (v < 0) { const char* e = getenv("VISOB_DEPTH"); v = e ? atoi(e) : 3; v = v < 1 ? 1 : (v > 3 ? 3 : v); g_depth = v; }
   return v;
 }
 static thread_local int t_device = 0;

@@ -281,7 +281,7 @@ class Sfm:
 
 
 def set_pipeline_depth(depth):
-    """Steps that Runner.run keeps in flight per sequence (1 = synchronous, default 2, at most 3)."""
+    """Steps that Runner.run keeps in flight per sequence (1 = synchronous, default and maximum 3)."""
     lib().visob_set_pipeline_depth(int(depth))
 
 

@@ -341,7 +341,7 @@ def test_pipelined_runner_equals_stepwise(ref):
         assert np.array_equal(nm, counts_step) and nm[1:].min() > 300, depth
         for s in range(S):
             assert got[s].tobytes() == want[s].tobytes(), (depth, s)
-    H.set_pipeline_depth(2)
+    H.set_pipeline_depth(3)
     # odometry mode
     S, T = 3, 7
     seqs = [synth.corridor_sequence(T, seed=1234 + s) for s in range(S)]

@@ -119,6 +119,12 @@ def test_bench_rank_aggregation_gloo():
     assert abs(r['ms_per_step'] - 20.0) < 1e-6
     assert abs(r['value'] - 2 * r['config']['sequences_per_gpu'] / 0.020) < 1e-3
     assert r['gpu_launches'] == 0 and r['data'] == 'dry-run'
+    # configs[4] as written: 64 sequences in total over the ranks (strong scaling)
+    out = subprocess.run(cmd[:-1] + ['--scaling', 'strong', '--sequences', '64', '--dry-run'], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][0])
+    assert r['scaling'] == 'strong' and r['config']['sequences_per_gpu'] == 32 and r['config']['frame_pairs_per_step'] == 64
+    assert abs(r['value'] - 64 / 0.020) < 1e-3
 
 
 @pytest.mark.parametrize('point_type,min_len,min_angle', [(0, 2, 3.0), (1, 2, 2.0), (2, 3, 1.0)])
