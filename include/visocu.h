@@ -153,6 +153,23 @@ int  visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch** list1, in
  * 1: list unchanged, not handled by the device path (see visocu_match). */
 int  visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t method, visocu_pmatch* const* inout, const int32_t* n,
                             int32_t* n_out, int32_t* status);
+/* Lists too long for the device path of removeOutliers (more than about 5 700 vertices: 3840x2160 frames): the
+ * triangulation is a divide-and-conquer tree (triangle.cpp divconqdelaunay with alternating cuts, matcher.cpp:1255), and
+ * its lower part - all the work but the seams of the top few merges - consists of independent nodes that fit the device
+ * kernel.  visocu_delaunay_subtrees triangulates such nodes: pts = the vertices of the whole problem (x | y << 16, both
+ * below 8192, all distinct), node j = pts[first[j] .. first[j] + count[j]) with 4 <= count[j] <= 5000, axis[j] = direction
+ * of the node's own cut (0 = vertical).  The result is ONE mesh in the numbering of the whole problem, ready to be merged
+ * further: *mesh = *n_halfedges records of four words (onext, oprev, origin vertex, x | y << 16 of the origin; sym(e) =
+ * e ^ 1; origin -1 = deleted or unused) followed by room for extra_halfedges more; node j owns the half-edges from
+ * mesh_first[j] (2 * visocu_delaunay_edge_capacity(count[j]) of them) and numbers its vertices first[j] + v, v in the order
+ * of its partition tree, (*vert)[first[j] + v] = index within the node of vertex v.  (*result)[16 j + 1] = status (0 =
+ * done), [16 j + 2] = edges allocated, [16 j + 4], [16 j + 5] = hull handles (counter-clockwise hull edge out of the
+ * leftmost vertex, clockwise hull edge out of the rightmost).  The memory belongs to the context and stays valid (and
+ * writable) until the next call on this lane.  The caller (host/delaunay.cpp) runs the merges above the nodes and votes. */
+int32_t visocu_delaunay_edge_capacity(int32_t n_vertices);
+int  visocu_delaunay_subtrees(visocu_ctx* ctx, const uint32_t* pts, int32_t n_pts, int32_t n_jobs, const int32_t* first,
+                              const int32_t* count, const int32_t* axis, int32_t extra_halfedges, int32_t** mesh,
+                              int32_t* mesh_first, int32_t* n_halfedges, const int32_t** vert, const int32_t** result);
 /* Matcher::refinement alone on caller-supplied matches: mode 1 = pixel, 2 = sub-pixel (n_out <= n survive) */
 int  visocu_refine(visocu_ctx* ctx, const visocu_quad* job, int32_t method, int32_t mode, visocu_pmatch* inout, int32_t n,
                    int32_t* n_out);

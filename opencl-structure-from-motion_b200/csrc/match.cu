@@ -701,9 +701,10 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
     }
     if (mode >= 2) {
       // one pass of a fused call: outlier removal and the read-back of the result words queued on the main stream
-      // Shared memory of the outlier kernel follows the longest list.  Lazy mode: flow matches are one-to-one, so a list is
-      // no longer than a frame's feature list; the context keeps the longest one seen so far plus a margin (ro_bound).  A
-      // longer list than that is declined by the kernel and voted on by the host, and the bound grows.
+      // Shared memory of the outlier kernel follows the longest list.  Lazy mode: the host does not know the lengths when it
+      // launches; the context keeps the longest list seen so far per pass plus a margin (ro_bound, -1 = nothing seen yet:
+      // room for a complete feature list).  A longer list is declined by the kernel and voted on by the host, and the
+      // bound grows.
       int max_list = maxq;
       if (dyn && ctx->ro_bound[pass] >= 0 && ctx->ro_bound[pass] < max_list) max_list = ctx->ro_bound[pass];
       if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + h_rj), nb, method, max_list, ctx->stream))) return rc;
@@ -1004,11 +1005,12 @@ extern "C" int visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch**
       ctx->h_counts[2 * (size_t)fr[k] + 0] = hdr[32 + 3 * k]; ctx->h_counts[2 * (size_t)fr[k] + 1] = hdr[33 + 3 * k];
       if (hdr[34 + 3 * k]) overflow = fr[k];
       if (counts) { counts[4 * j + 2 * k] = hdr[32 + 3 * k]; counts[4 * j + 2 * k + 1] = hdr[33 + 3 * k]; }
-      // shared memory of the next outlier launches: the longest feature list seen, with a margin
-      for (int p = 0; p < 2; p++) {
-        const int c = hdr[32 + 3 * k + p], want = (c + c / 4 + 256 + 511) & ~511;      // in steps of 512: the bound is part of the graph key
-        if (c > ctx->ro_bound_seen[p]) { ctx->ro_bound_seen[p] = c; if (ctx->ro_bound[p] < want) ctx->ro_bound[p] = want < g.cap[p] ? want : g.cap[p]; }
-      }
+    }
+    // shared memory of the next outlier launches: the longest match list seen per pass (declined ones included), with a
+    // margin.  Tight on purpose: what the outlier CTA does not take is what kernels of other streams can use on its SM
+    for (int p = 0; p < 2; p++) {
+      const int c = hdr[16 * p + 3], want = (c + c / 8 + 128 + 255) & ~255;          // in steps of 256: the bound is part of the graph key
+      if (c > ctx->ro_bound_seen[p]) { ctx->ro_bound_seen[p] = c; if (ctx->ro_bound[p] < want) ctx->ro_bound[p] = want < g.cap[p] ? want : g.cap[p]; }
     }
     ctx->d2h_bytes += 24;
   }

@@ -22,13 +22,16 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
 namespace {
 
-constexpr int RO_THREADS = 1024;        // with 64 registers each: the CTA owns every register of its SM, so no other kernel's
-                                        // warps compete with the single-threaded top merges for issue slots
+// Threads per CTA: a template parameter of the kernel.  1024 threads of 64 registers own every register of their SM: the
+// shortest chain for one list (sorts, partitions and the lower merge levels are block-wide), but no other kernel can use
+// the SM while one lane walks the seams of the top merges.  Batched launches therefore run with fewer threads per list
+// (visocu_launch_remove_outliers) and leave the rest of the SM to the kernels of the other streams.
 constexpr int NIL = 0xFFFF;
 constexpr uint16_t DEAD = 0xFFFF;
 
@@ -56,16 +59,16 @@ struct Mesh {
   __device__ __forceinline__ bool tick() { return --guard >= 0; }    // false once this thread's loop budget is used up
   // Predicates in 32-bit arithmetic with 64-bit products only where needed: exact for coordinates below 8192 (checked
   // when the keys are built; larger images go to the host).  > 0 iff a, b, c make a left turn
-  __device__ __forceinline__ int ccw(int a, int b, int c) const {
-    const uint32_t A = pt[a], B = pt[b], C = pt[c];
+  __device__ __forceinline__ int ccw(int a, int b, int c) const { return ccw_pts(pt[a], pt[b], pt[c]); }
+  // > 0 iff d lies strictly inside the circle through a, b, c (counter-clockwise)
+  __device__ __forceinline__ long long incircle(int a, int b, int c, int d) const { return incircle_pts(pt[a], pt[b], pt[c], pt[d]); }
+  static __device__ __forceinline__ int ccw_pts(uint32_t A, uint32_t B, uint32_t C) {
     const int cx = (int)(C & 0xFFFF), cy = (int)(C >> 16);
     const int ax = (int)(A & 0xFFFF) - cx, ay = (int)(A >> 16) - cy;
     const int bx = (int)(B & 0xFFFF) - cx, by = (int)(B >> 16) - cy;
     return ax * by - ay * bx;                                        // |.| < 2^27
   }
-  // > 0 iff d lies strictly inside the circle through a, b, c (counter-clockwise)
-  __device__ __forceinline__ long long incircle(int a, int b, int c, int d) const {
-    const uint32_t A = pt[a], B = pt[b], C = pt[c], D = pt[d];
+  static __device__ __forceinline__ long long incircle_pts(uint32_t A, uint32_t B, uint32_t C, uint32_t D) {
     const int dx = (int)(D & 0xFFFF), dy = (int)(D >> 16);
     const int adx = (int)(A & 0xFFFF) - dx, ady = (int)(A >> 16) - dy;
     const int bdx = (int)(B & 0xFFFF) - dx, bdy = (int)(B >> 16) - dy;
@@ -78,13 +81,19 @@ struct Mesh {
 // free edges of a subtree: singly linked through nx[] of the even half-edge
 struct FreeList { int head, tail; };
 
+// W (here and below): the whole warp runs the function on one subtree, every lane with the same arguments and the same
+// loads and stores (same addresses, same values), so that merge() can spread the geometric tests of a step over lanes.
+// Only the edge counter must be bumped once.
+template <bool W>
 __device__ __forceinline__ int make_edge(Mesh& m, FreeList& fl, int a, int b) {
   int e;
   if (fl.head != NIL) {
     e = fl.head;
     fl.head = (e == fl.tail) ? NIL : m.nx[e];
   } else {
-    const int k = atomicAdd(m.bump, 1);
+    int k = 0;
+    if (!W || (threadIdx.x & 31) == 0) k = atomicAdd(m.bump, 1);
+    if (W) k = __shfl_sync(0xFFFFFFFFu, k, 0);
     if (k >= m.ecap) { *m.fail = 1; e = 0; } else e = 2 * k;
   }
   m.nx[e] = (uint16_t)e; m.pv[e] = (uint16_t)e; m.og[e] = (uint16_t)a;
@@ -102,8 +111,9 @@ __device__ __forceinline__ void unlink(Mesh& m, int e) {
   m.nx[p] = (uint16_t)n; m.pv[n] = (uint16_t)p;
 }
 // new edge from dest(a) to org(b) so that a, the new edge and b share their left face
+template <bool W>
 __device__ __forceinline__ int connect(Mesh& m, FreeList& fl, int a, int b) {
-  const int e = make_edge(m, fl, m.dest(a), m.org(b));
+  const int e = make_edge<W>(m, fl, m.dest(a), m.org(b));
   insert_after(m, m.lnext(a), e);
   insert_after(m, b, e ^ 1);
   return e;
@@ -119,6 +129,13 @@ struct Handles { int ldo, rdo; };   // ccw hull edge out of the leftmost vertex,
 
 // Merge of two triangulations separated by a vertical (axis 0) or horizontal (axis 1) line; the same steps, tests and
 // tie-breaking as merge() in host/delaunay.cpp.
+//
+// A step of the seam walk is a chain of dependent shared-memory loads followed by up to four orientation and three
+// in-circle tests on six points, then the stores of the new edge: a few hundred dependent instructions of one thread.  At
+// the top levels of the tree, where there are no more subtrees than warps, the warp owns the merge (W): all lanes chase
+// the pointers together (broadcast loads), lanes 0-4 evaluate one test each on points handed out by shuffles, and ballots
+// bring the outcomes back.  The candidate loops that follow a deletion stay sequential (most steps delete nothing).
+template <bool W>
 __device__ Handles merge(Mesh& m, FreeList& fl, Handles L, Handles R, int axis) {
   int ldo = L.ldo, ldi = L.rdo, rdi = R.ldo, rdo = R.rdo;
   if (axis == 1) {
@@ -133,7 +150,7 @@ __device__ Handles merge(Mesh& m, FreeList& fl, Handles L, Handles R, int axis) 
     if (m.ccw(m.org(ldi), m.dest(ldi), m.org(rdi)) > 0) { ldi = m.lnext(ldi); changed = true; }
     if (m.ccw(m.dest(rdi), m.org(rdi), m.org(ldi)) > 0) { rdi = m.rprev(rdi); changed = true; }
   } while (changed && m.tick());
-  int basel = connect(m, fl, rdi ^ 1, ldi);
+  int basel = connect<W>(m, fl, rdi ^ 1, ldi);
   if (m.org(ldi) == m.org(ldo)) ldo = basel ^ 1;
   if (m.org(rdi) == m.org(rdo)) rdo = basel;
   while (m.tick()) {
@@ -146,13 +163,37 @@ __device__ Handles merge(Mesh& m, FreeList& fl, Handles L, Handles R, int axis) 
     // chains overlap; the loops below continue from the second candidate on.
     const int lnx0 = m.onext(lcand), rnx0 = m.oprev(rcand);
     const int lapex0 = m.dest(lnx0), rapex0 = m.dest(rnx0);
-    const bool leftfinished = m.ccw(upperleft, lowerleft, lowerright) <= 0;
-    const bool rightfinished = m.ccw(upperright, lowerleft, lowerright) <= 0;
+    bool leftfinished, rightfinished, ldel0, rdel0, right_first = false;
+    if (W) {
+      // points 0..5 = lowerleft, lowerright, upperleft, upperright, left apex, right apex, one per lane; the tables hold,
+      // per lane (4 bits each), which of them are the arguments of its tests:
+      //   lane 0: ccw(UL, LL, LR)   lane 1: ccw(UR, LL, LR)   lane 2: ccw(LL, UL, LA), incircle(LL, LR, UL, LA)
+      //   lane 3: ccw(LR, RA, UR), incircle(LL, LR, UR, RA)   lane 4: incircle(UL, LL, LR, UR)
+      const int lane = threadIdx.x & 31;
+      int myv = rapex0;
+      myv = lane == 4 ? lapex0 : myv; myv = lane == 3 ? upperright : myv; myv = lane == 2 ? upperleft : myv;
+      myv = lane == 1 ? lowerright : myv; myv = lane == 0 ? lowerleft : myv;
+      const uint32_t myp = m.pt[myv];
+      const int sh = 4 * min(lane, 7);
+#define RO_PICK(table) __shfl_sync(0xFFFFFFFFu, myp, (int)(((table) >> sh) & 7u))
+      const uint32_t P = RO_PICK(0x01032u), Q = RO_PICK(0x05200u), R = RO_PICK(0x03411u);
+      const uint32_t A = RO_PICK(0x20000u), B = RO_PICK(0x01100u), C = RO_PICK(0x13200u), D = RO_PICK(0x35400u);
+#undef RO_PICK
+      const unsigned cpos = __ballot_sync(0xFFFFFFFFu, Mesh::ccw_pts(P, Q, R) > 0);
+      const unsigned ipos = __ballot_sync(0xFFFFFFFFu, Mesh::incircle_pts(A, B, C, D) > 0);
+      leftfinished = !(cpos & 1u); rightfinished = !(cpos & 2u);
+      ldel0 = !leftfinished && lnx0 != (basel ^ 1) && (cpos & 4u) && (ipos & 4u);
+      rdel0 = !rightfinished && rnx0 != basel && (cpos & 8u) && (ipos & 8u);
+      right_first = (ipos & 16u) != 0;                 // valid while neither candidate changes
+    } else {
+      leftfinished = m.ccw(upperleft, lowerleft, lowerright) <= 0;
+      rightfinished = m.ccw(upperright, lowerleft, lowerright) <= 0;
+      ldel0 = !leftfinished && lnx0 != (basel ^ 1) && m.ccw(lowerleft, upperleft, lapex0) > 0 &&
+              m.incircle(lowerleft, lowerright, upperleft, lapex0) > 0;
+      rdel0 = !rightfinished && rnx0 != basel && m.ccw(lowerright, rapex0, upperright) > 0 &&
+              m.incircle(lowerleft, lowerright, upperright, rapex0) > 0;
+    }
     if (leftfinished && rightfinished) break;
-    const bool ldel0 = !leftfinished && lnx0 != (basel ^ 1) && m.ccw(lowerleft, upperleft, lapex0) > 0 &&
-                       m.incircle(lowerleft, lowerright, upperleft, lapex0) > 0;
-    const bool rdel0 = !rightfinished && rnx0 != basel && m.ccw(lowerright, rapex0, upperright) > 0 &&
-                       m.incircle(lowerleft, lowerright, upperright, rapex0) > 0;
     if (ldel0) {
       remove_edge(m, fl, lcand);
       lcand = lnx0; upperleft = lapex0;
@@ -179,10 +220,12 @@ __device__ Handles merge(Mesh& m, FreeList& fl, Handles L, Handles R, int axis) 
         rcand = nx; upperright = apex;
       }
     }
-    if (leftfinished || (!rightfinished && m.incircle(upperleft, lowerleft, lowerright, upperright) > 0))
-      basel = connect(m, fl, rcand, basel ^ 1);
-    else
-      basel = connect(m, fl, basel ^ 1, lcand ^ 1);
+    bool right = leftfinished;
+    if (!leftfinished && !rightfinished)
+      right = (W && !ldel0 && !rdel0) ? right_first : m.incircle(upperleft, lowerleft, lowerright, upperright) > 0;
+    if (right) basel = connect<W>(m, fl, rcand, basel ^ 1);
+    else basel = connect<W>(m, fl, basel ^ 1, lcand ^ 1);
+    if (W) __syncwarp();
   }
   if (axis == 1) {
     while (m.px(m.dest(m.oprev(ldo))) < m.px(m.org(ldo)) && m.tick()) ldo = m.oprev(ldo) ^ 1;
@@ -192,22 +235,24 @@ __device__ Handles merge(Mesh& m, FreeList& fl, Handles L, Handles R, int axis) 
 }
 
 // two or three vertices, consecutive numbers starting at v, sorted by x
+template <bool W>
 __device__ Handles leaf(Mesh& m, FreeList& fl, int v, int n) {
   if (n == 2) {
-    const int a = make_edge(m, fl, v, v + 1);
+    const int a = make_edge<W>(m, fl, v, v + 1);
     return Handles{a, a ^ 1};
   }
-  const int a = make_edge(m, fl, v, v + 1);
-  const int b = make_edge(m, fl, v + 1, v + 2);
+  const int a = make_edge<W>(m, fl, v, v + 1);
+  const int b = make_edge<W>(m, fl, v + 1, v + 2);
   insert_after(m, b, a ^ 1);
   const int area = m.ccw(v, v + 1, v + 2);
   if (area == 0) return Handles{a, b ^ 1};
-  const int c = connect(m, fl, b, a);
+  const int c = connect<W>(m, fl, b, a);
   if (area > 0) return Handles{a, b ^ 1};
   return Handles{c ^ 1, c};
 }
 
 // exclusive prefix sum over the block of one value per thread; total returned to every thread
+template <int RO_THREADS>
 __device__ __forceinline__ int block_scan(int v, int* s_warp, int& total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int incl = v;
@@ -235,6 +280,7 @@ __device__ __forceinline__ bool edge_agrees(const visocu_pmatch& a, const visocu
 }
 
 // copy 48-byte records src[list[i]] -> dst[i], 12 lanes per record
+template <int RO_THREADS>
 __device__ __forceinline__ void copy_records(visocu_pmatch* dst, const visocu_pmatch* src, const int32_t* list, int n) {
   const int32_t* s = (const int32_t*)src;
   int32_t* d = (int32_t*)dst;
@@ -244,8 +290,9 @@ __device__ __forceinline__ void copy_records(visocu_pmatch* dst, const visocu_pm
   }
 }
 
-__global__ void __launch_bounds__(RO_THREADS, 1)
-k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, float disp_tol, int smem_bytes) {
+template <int RO_THREADS>
+__global__ void __launch_bounds__(RO_THREADS, 1024 / RO_THREADS)
+k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, float disp_tol, int smem_bytes, int warp_merges) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int s_warp[RO_THREADS / 32];
   __shared__ int s_bump, s_fail, s_flag, s_more;
@@ -257,14 +304,18 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   int32_t* src = J.idx;                              // global scratch: list position -> record index (after the keep flags)
 
   // ---- 0. records that survived the sub-pixel refinement (order preserved)
+  const bool pts_mode = J.pts_in != nullptr;         // vertices given as points: every one takes part
+  const int axis0 = J.axis0;
   int n = 0;
-  {
+  if (pts_mode) {
+    n = n_in;
+  } else {
     const int per = (n_in + RO_THREADS - 1) / RO_THREADS;
     const int i0 = min(tid * per, n_in), i1 = min(i0 + per, n_in);
     int cnt = 0;
     for (int i = i0; i < i1; i++) cnt += (!J.keep_in || J.keep_in[i]) ? 1 : 0;
     int total;
-    int off = block_scan(cnt, s_warp, total);
+    int off = block_scan<RO_THREADS>(cnt, s_warp, total);
     n = total;
     for (int i = i0; i < i1; i++) if (!J.keep_in || J.keep_in[i]) src[off++] = i;
   }
@@ -279,8 +330,8 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   const int nl = n;                                  // list length; n becomes the number of mesh vertices (distinct positions)
   if (n <= 3 || n > 0x7FF0 || need > (size_t)smem_bytes) {
     // nothing to vote on (matcher.cpp:1210-1211), or too large for the device path: hand the list over unchanged
-    copy_records(J.out, J.in, src, n);
-    if (tid == 0) { J.result[0] = n; J.result[1] = n <= 3 ? 0 : 1; J.result[2] = 0; J.result[3] = n; }
+    if (!pts_mode) copy_records<RO_THREADS>(J.out, J.in, src, n);
+    if (tid == 0) { J.result[0] = n; J.result[1] = (n <= 3 && !pts_mode) ? 0 : 1; J.result[2] = 0; J.result[3] = n; }
     return;
   }
 
@@ -333,9 +384,10 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   if (tid == 0) s_more = 0;
   for (int i = tid; i < npad; i += RO_THREADS) {
     unsigned long long key = ~0ull;
-    if (i < nl && (!J.rep || J.rep[src[i]])) {
-      const visocu_pmatch& r = J.in[src[i]];
-      const int x = (int)r.u1c, y = (int)r.v1c;
+    if (i < nl && (pts_mode || !J.rep || J.rep[src[i]])) {
+      int x, y;
+      if (pts_mode) { const uint32_t p = J.pts_in[i]; x = (int)(p & 0xFFFFu); y = (int)(p >> 16); }
+      else { const visocu_pmatch& r = J.in[src[i]]; x = (int)r.u1c; y = (int)r.v1c; }
       if (x < 0 || y < 0 || x > 8191 || y > 8191) s_fail = 1;        // range of the 32-bit predicates
       key = ((unsigned long long)(unsigned)x << 40) | ((unsigned long long)(unsigned)y << 16) | (unsigned)i;
     }
@@ -354,20 +406,20 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   }
   __syncthreads();
   if (s_fail) {
-    copy_records(J.out, J.in, src, nl);
+    if (!pts_mode) copy_records<RO_THREADS>(J.out, J.in, src, nl);
     if (tid == 0) { J.result[0] = nl; J.result[1] = 1; J.result[2] = 0; J.result[3] = nl; }
     return;
   }
   if (s_flag) {
     // Two vertices on one pixel: the caller did not resolve the duplicates (ro_resolve_duplicates) - Triangle's choice
     // among them depends on its randomised quicksort, which is replayed on the host, not here.
-    copy_records(J.out, J.in, src, nl);
+    if (!pts_mode) copy_records<RO_THREADS>(J.out, J.in, src, nl);
     if (tid == 0) { J.result[0] = nl; J.result[1] = 2; J.result[2] = 0; J.result[3] = nl; }
     return;
   }
   n = s_more;                                        // number of vertices (records that take part)
   if (n <= 3) {
-    copy_records(J.out, J.in, src, nl);
+    if (!pts_mode) copy_records<RO_THREADS>(J.out, J.in, src, nl);
     if (tid == 0) { J.result[0] = nl; J.result[1] = 3; J.result[2] = 0; J.result[3] = nl; }
     return;
   }
@@ -386,7 +438,7 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
     const int per = (n + RO_THREADS - 1) / RO_THREADS;
     const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
     for (;; depth++) {
-      const int axis = depth & 1;
+      const int axis = (depth + axis0) & 1;
       uint16_t* from = axis == 0 ? xl : yl;
       uint16_t* other = axis == 0 ? yl : xl;
       if (tid == 0) s_more = 0;
@@ -398,7 +450,7 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
       int cnt = 0;
       for (int i = i0; i < i1; i++) cnt += (nsz[i] > 3) ? side[other[i]] : 0;
       int total;
-      int run = block_scan(cnt, s_warp, total);
+      int run = block_scan<RO_THREADS>(cnt, s_warp, total);
       for (int i = i0; i < i1; i++) { pre[i] = (uint16_t)run; run += (nsz[i] > 3) ? side[other[i]] : 0; }
       if (i1 == n && i0 < n) pre[n] = (uint16_t)run;
       __syncthreads();
@@ -450,36 +502,45 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   m.guard = 64 * ecap;
   unsigned long long t_level = now();
   for (int d = maxdepth; d >= 0; d--) {
-    {
-      // Threads of a warp that run different merges take turns (the merges diverge completely), so the subtrees of a
-      // level are dealt to the warps first: 32 or fewer subtrees run on 32 different warps, one lane each.
-      for (int j = (tid & 31) * (RO_THREADS / 32) + (tid >> 5); j < (1 << d); j += RO_THREADS) {
-        int lo = 0, sz = n;
-        bool exists = true;
-        for (int t = d - 1; t >= 0; t--) {
-          if (sz <= 3) { exists = false; break; }
-          const int div = sz >> 1;
-          if ((j >> t) & 1) { lo += div; sz -= div; } else { sz = div; }
+    // one subtree of the level: its vertex range from the index, leaf or merge, handles and free list stored
+    auto subtree = [&](int j, auto warp_wide) {
+      constexpr bool W = decltype(warp_wide)::value;
+      int lo = 0, sz = n;
+      for (int t = d - 1; t >= 0; t--) {
+        if (sz <= 3) return;                         // the node does not exist: an ancestor is a leaf
+        const int div = sz >> 1;
+        if ((j >> t) & 1) { lo += div; sz -= div; } else { sz = div; }
+      }
+      FreeList fl{NIL, NIL};
+      Handles h;
+      if (sz <= 3) {
+        h = leaf<W>(m, fl, lo, sz);
+      } else {
+        const int div = sz >> 1;
+        const int sl = lo >> 1, sr = (lo + div) >> 1;
+        fl.head = f_h[sl]; fl.tail = f_t[sl];
+        if (f_h[sr] != NIL) {
+          if (fl.head == NIL) { fl.head = f_h[sr]; fl.tail = f_t[sr]; }
+          else { m.nx[fl.tail] = f_h[sr]; fl.tail = f_t[sr]; }
         }
-        if (!exists) continue;
-        FreeList fl{NIL, NIL};
-        Handles h;
-        if (sz <= 3) {
-          h = leaf(m, fl, lo, sz);
-        } else {
-          const int div = sz >> 1;
-          const int sl = lo >> 1, sr = (lo + div) >> 1;
-          fl.head = f_h[sl]; fl.tail = f_t[sl];
-          if (f_h[sr] != NIL) {
-            if (fl.head == NIL) { fl.head = f_h[sr]; fl.tail = f_t[sr]; }
-            else { m.nx[fl.tail] = f_h[sr]; fl.tail = f_t[sr]; }
-          }
-          h = merge(m, fl, Handles{h_l[sl], h_r[sl]}, Handles{h_l[sr], h_r[sr]}, d & 1);
-        }
-        if (m.guard < 0) s_fail = 1;
+        h = merge<W>(m, fl, Handles{h_l[sl], h_r[sl]}, Handles{h_l[sr], h_r[sr]}, (d + axis0) & 1);
+      }
+      if (m.guard < 0) s_fail = 1;
+      if (!W || (tid & 31) == 0) {
         h_l[lo >> 1] = (uint16_t)h.ldo; h_r[lo >> 1] = (uint16_t)h.rdo;
         f_h[lo >> 1] = (uint16_t)fl.head; f_t[lo >> 1] = (uint16_t)fl.tail;
       }
+    };
+    if (warp_merges && (1 << d) <= RO_THREADS / 32) {
+      // no more subtrees than warps: a warp per merge, the tests of a seam step spread over its lanes (merge<true>)
+      if ((tid >> 5) < (1 << d)) {
+        m.guard = __reduce_min_sync(0xFFFFFFFFu, m.guard);            // one loop budget for the warp: uniform control flow
+        subtree(tid >> 5, std::true_type());
+      }
+    } else {
+      // Threads of a warp that run different merges take turns (the merges diverge completely), so the subtrees of a
+      // level are dealt to the warps first: 32 or fewer subtrees run on 32 different warps, one lane each.
+      for (int j = (tid & 31) * (RO_THREADS / 32) + (tid >> 5); j < (1 << d); j += RO_THREADS) subtree(j, std::false_type());
     }
     __syncthreads();
     if (tid == 0 && d < 7) { const unsigned long long t = now(); J.result[9 + d] = (int32_t)(t - t_level); t_level = t; }
@@ -487,8 +548,25 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
     if (s_fail) break;
   }
   if (s_fail) {
-    copy_records(J.out, J.in, src, nl);
+    if (!pts_mode) copy_records<RO_THREADS>(J.out, J.in, src, nl);
     if (tid == 0) { J.result[0] = nl; J.result[1] = 3; J.result[2] = s_bump; J.result[3] = nl; }
+    return;
+  }
+
+  if (J.mesh_out) {
+    // triangulation only: the mesh in the caller's numbering, deleted edges and the unused tail marked, the hull handles
+    const int nh = 2 * min(s_bump, ecap), hb = J.he_base, vb = J.v_base;
+    for (int e = tid; e < 2 * ecap; e += RO_THREADS) {
+      int4 rec = make_int4(hb + e, hb + e, -1, 0);
+      if (e < nh) {
+        const int o = he_og[e];
+        if (o != DEAD) rec = make_int4(hb + he_nx[e], hb + he_pv[e], vb + o, (int)pts[o]);
+      }
+      J.mesh_out[e] = rec;
+    }
+    if (tid == 0) {
+      J.result[0] = n; J.result[1] = 0; J.result[2] = s_bump; J.result[3] = nl; J.result[4] = hb + h_l[0]; J.result[5] = hb + h_r[0];
+    }
     return;
   }
 
@@ -502,7 +580,7 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
   }
   __syncthreads();
   if (s_fail) {
-    copy_records(J.out, J.in, src, nl);
+    if (!pts_mode) copy_records<RO_THREADS>(J.out, J.in, src, nl);
     if (tid == 0) { J.result[0] = nl; J.result[1] = 3; J.result[2] = s_bump; J.result[3] = nl; }
     return;
   }
@@ -556,13 +634,13 @@ k_remove_outliers(const RoJob* __restrict__ jobs, int method, float flow_tol, fl
     int cnt = 0;
     for (int i = i0; i < i1; i++) cnt += support[i] >= 4u ? 1 : 0;
     int total;
-    int off = block_scan(cnt, s_warp, total);
+    int off = block_scan<RO_THREADS>(cnt, s_warp, total);
     // compacted index list in place of src (entries only move towards the front, chunk by chunk behind a barrier)
     int32_t* kept = J.vert;                          // the vertex map is no longer needed
     __syncthreads();
     for (int i = i0; i < i1; i++) if (support[i] >= 4u) kept[off++] = src[i];
     __syncthreads();
-    copy_records(J.out, J.in, kept, total);
+    copy_records<RO_THREADS>(J.out, J.in, kept, total);
     if (tid == 0) {
       J.result[0] = total; J.result[1] = 0; J.result[2] = s_bump; J.result[3] = nl;
       // phase times in nanoseconds (sort, partition, build, vote + compaction): read by profiles/profile_outliers.py
@@ -601,12 +679,20 @@ int visocu_launch_remove_outliers(visocu_ctx* ctx, const RoJob* jobs_dev, int n_
     static bool done[64] = {false};
     std::lock_guard<std::mutex> lock(mtx);
     if (!done[ctx->device & 63]) {
-      CU_TRY(ctx, cudaFuncSetAttribute(k_remove_outliers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+      CU_TRY(ctx, cudaFuncSetAttribute(k_remove_outliers<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+      CU_TRY(ctx, cudaFuncSetAttribute(k_remove_outliers<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+      CU_TRY(ctx, cudaFuncSetAttribute(k_remove_outliers<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
       done[ctx->device & 63] = true;
     }
   }
-  k_remove_outliers<<<n_jobs, RO_THREADS, smem, stream>>>(jobs_dev, method, (float)ctx->param.outlier_flow_tolerance,
-                                                              (float)ctx->param.outlier_disp_tolerance, (int)smem);
+  // one or two lists (a stand-alone Matcher): the shortest chain; batches: the smaller footprint
+  static const int forced = [] { const char* e = getenv("VISOCU_RO_THREADS"); return e ? atoi(e) : 0; }();
+  const int threads = forced ? forced : (n_jobs <= 2 ? 1024 : 512);
+  static const int warp = [] { const char* e = getenv("VISOCU_RO_WARP"); return (e && e[0] == '0') ? 0 : 1; }();
+  const float ft = (float)ctx->param.outlier_flow_tolerance, dt = (float)ctx->param.outlier_disp_tolerance;
+  if (threads >= 1024) k_remove_outliers<1024><<<n_jobs, 1024, smem, stream>>>(jobs_dev, method, ft, dt, (int)smem, warp);
+  else if (threads >= 512) k_remove_outliers<512><<<n_jobs, 512, smem, stream>>>(jobs_dev, method, ft, dt, (int)smem, warp);
+  else k_remove_outliers<256><<<n_jobs, 256, smem, stream>>>(jobs_dev, method, ft, dt, (int)smem, warp);
   CU_LAUNCH_CHECK(ctx);
   return VISOCU_OK;
 }
@@ -676,6 +762,68 @@ extern "C" int visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t m
     if (status[j] == 0 && n_out[j] > 0) CU_COPY(ctx, inout[j], hj[j].out, (size_t)n_out[j] * 48, cudaMemcpyDeviceToHost);
   }
   CU_TRY(ctx, visocu_stream_wait(ctx));
+  return VISOCU_OK;
+}
+
+int ro_edge_capacity_host(int n) { return ro_edge_capacity(n); }
+
+extern "C" int32_t visocu_delaunay_edge_capacity(int32_t n_vertices) { return n_vertices > 0 ? ro_edge_capacity(n_vertices) : 0; }
+
+// Nodes of a larger divide-and-conquer Delaunay triangulation built on the device, one CTA each (see include/visocu.h)
+extern "C" int visocu_delaunay_subtrees(visocu_ctx* ctx, const uint32_t* pts, int32_t n_pts, int32_t n_jobs, const int32_t* first,
+                                        const int32_t* count, const int32_t* axis, int32_t extra_halfedges, int32_t** mesh,
+                                        int32_t* mesh_first, int32_t* n_halfedges, const int32_t** vert, const int32_t** result) {
+  if (!ctx) return VISOCU_EINVAL;
+  if (!ctx->configured) return visocu_set_error(ctx, VISOCU_ESTATE, "context not configured");
+  if (!pts || n_pts <= 0 || n_jobs <= 0 || !first || !count || !axis || extra_halfedges < 0 || !mesh || !mesh_first || !n_halfedges || !vert || !result)
+    return visocu_set_error(ctx, VISOCU_EINVAL, "bad subtree arguments");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  // device: jobs | points | vertex maps | result words | handles scratch | meshes      host (pinned): jobs | result words | vertex maps | meshes + room
+  size_t n_he = 0;
+  int maxn = 0;
+  for (int j = 0; j < n_jobs; j++) {
+    if (first[j] < 0 || count[j] < 4 || count[j] > 0x7FF0 || (int64_t)first[j] + count[j] > n_pts)
+      return visocu_set_error(ctx, VISOCU_EINVAL, "subtree %d: range [%d, +%d) not inside %d points or size out of range", j, first[j], count[j], n_pts);
+    mesh_first[j] = (int32_t)n_he;
+    n_he += 2 * (size_t)ro_edge_capacity(count[j]);
+    if (count[j] > maxn) maxn = count[j];
+  }
+  if (n_he + (size_t)extra_halfedges > 0x7FFFFFF0u) return visocu_set_error(ctx, VISOCU_EINVAL, "too many half-edges");
+  const size_t d_jobs = 0, d_pts = align_up(sizeof(RoJob) * n_jobs, 256), d_vert = d_pts + align_up((size_t)4 * n_pts, 256);
+  const size_t d_res = d_vert + align_up((size_t)4 * n_pts, 256), d_hnd = d_res + (size_t)64 * n_jobs;
+  const size_t d_mesh = d_hnd + align_up((size_t)8 * ((size_t)n_pts / 2 + 2 * (size_t)n_jobs), 256), d_end = d_mesh + 16 * n_he;
+  const size_t h_res = align_up(sizeof(RoJob) * n_jobs, 256), h_vert = h_res + (size_t)64 * n_jobs, h_mesh = h_vert + align_up((size_t)4 * n_pts, 256);
+  const size_t h_end = h_mesh + 16 * (n_he + (size_t)extra_halfedges);
+  int rc = visocu_ensure_scratch(ctx, d_end);
+  if (rc) return rc;
+  if ((rc = visocu_ensure_pinned(ctx, h_end))) return rc;
+  uint8_t* sb = (uint8_t*)ctx->scratch;
+  uint8_t* pin = (uint8_t*)ctx->pinned;
+  RoJob* hj = (RoJob*)pin;
+  int32_t* hres = (int32_t*)(pin + h_res);
+  size_t hnd_off = 0;
+  for (int j = 0; j < n_jobs; j++) {
+    RoJob J;
+    memset(&J, 0, sizeof J);
+    J.result = (int32_t*)(sb + d_res) + 16 * j; J.n_in = J.result + 8;
+    J.vert = (int32_t*)(sb + d_vert) + first[j];
+    J.hnd = (uint16_t*)(sb + d_hnd) + hnd_off; hnd_off += 4 * ((size_t)count[j] / 2 + 2);
+    J.pts_in = (const uint32_t*)(sb + d_pts) + first[j];
+    J.mesh_out = (int4*)(sb + d_mesh) + mesh_first[j];
+    J.axis0 = axis[j] & 1; J.he_base = mesh_first[j]; J.v_base = first[j];
+    hj[j] = J;
+    memset(hres + 16 * j, 0, 64);
+    hres[16 * j + 1] = -1; hres[16 * j + 8] = count[j];
+  }
+  CU_COPY(ctx, sb + d_jobs, pin, sizeof(RoJob) * n_jobs, cudaMemcpyHostToDevice);
+  CU_COPY(ctx, sb + d_res, hres, (size_t)64 * n_jobs, cudaMemcpyHostToDevice);
+  CU_COPY(ctx, sb + d_pts, pts, (size_t)4 * n_pts, cudaMemcpyHostToDevice);
+  if ((rc = visocu_launch_remove_outliers(ctx, (const RoJob*)(sb + d_jobs), n_jobs, 0, maxn, ctx->stream))) return rc;
+  CU_COPY(ctx, hres, sb + d_res, (size_t)64 * n_jobs, cudaMemcpyDeviceToHost);
+  CU_COPY(ctx, pin + h_vert, sb + d_vert, (size_t)4 * n_pts, cudaMemcpyDeviceToHost);
+  CU_COPY(ctx, pin + h_mesh, sb + d_mesh, 16 * n_he, cudaMemcpyDeviceToHost);
+  CU_TRY(ctx, visocu_stream_wait(ctx));
+  *mesh = (int32_t*)(pin + h_mesh); *n_halfedges = (int32_t)n_he; *vert = (const int32_t*)(pin + h_vert); *result = hres;
   return VISOCU_OK;
 }
 

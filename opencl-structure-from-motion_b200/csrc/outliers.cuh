@@ -14,7 +14,18 @@ struct RoJob {
   int32_t* vert;               // scratch, n_in entries: mesh vertex -> list position
   const uint8_t* rep;          // optional, per record: 0 = duplicate position that Triangle ignores (ro_resolve_duplicates)
   uint16_t* hnd;               // scratch, 4 * (n_in / 2 + 2) entries: hull handles and free lists of the subtrees
+  // Triangulation only (visocu_delaunay_subtrees): the vertices are given as points, x | y << 16, all distinct, instead of
+  // match records; the job is a node of a larger divide-and-conquer tree whose cut is along axis0 (0 = vertical), and the
+  // mesh is written out instead of being voted on, in the numbering of the whole problem: 2 * ro_edge_capacity(n_in)
+  // half-edge records (onext, oprev, origin, x | y << 16 of the origin) starting at half-edge he_base, vertices numbered
+  // from v_base in the order of the node's partition tree; deleted and unused entries have origin -1.  vert = mesh vertex
+  // (local) -> index into pts_in; result[0] vertices, [1] status, [2] edges allocated, [4] and [5] the hull handles (ldo, rdo)
+  const uint32_t* pts_in;
+  int4* mesh_out;
+  int32_t axis0, he_base, v_base;
 };
+// edges a triangulation of n vertices may allocate on the device (also the stride of the arrays behind RoJob::mesh_out)
+int ro_edge_capacity_host(int n);
 
 // Positions of all records of a list as x << 16 | y (0xFFFFFFFF for records dropped by the sub-pixel refinement), for the
 // host-side duplicate resolution below.  keys_dev: n_jobs rows of `stride` words.

@@ -227,6 +227,18 @@ VISOB_API int visob_delaunay(const int32_t* x, const int32_t* y, int n, int32_t*
   if (tri_out) memcpy(tri_out, tri.data(), sizeof(int32_t) * 3 * (size_t)std::min(nt, cap_tri));
   return nt;
 }
+// edge list (a, b, triangles) of the triangulation; ctx != null: large inputs build their lower tree levels on that context
+VISOB_API int visob_delaunay_edges(void* ctx, const int32_t* x, const int32_t* y, int n, int32_t* edges_out, int cap_edges, int64_t* device_nodes) {
+  std::vector<int32_t> e;
+  const long before = visob::delaunay_device_nodes();
+  visob::delaunay_use_device((visocu_ctx*)ctx);
+  visob::delaunay_edges(x, y, n, e);
+  visob::delaunay_use_device(nullptr);
+  if (device_nodes) *device_nodes = visob::delaunay_device_nodes() - before;
+  const int ne = (int)e.size() / 3;
+  if (edges_out) memcpy(edges_out, e.data(), sizeof(int32_t) * 3 * (size_t)std::min(ne, cap_edges));
+  return ne;
+}
 VISOB_API void visob_svd(const double* A, int m, int n, double* U, double* W, double* V) {
   Matrix M(m, n, A), Um, Wm, Vm;
   M.svd(Um, Wm, Vm);

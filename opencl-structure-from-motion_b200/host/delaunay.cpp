@@ -13,6 +13,7 @@
 // merge across a horizontal cut.  tests/test_host_cpu.py::test_remove_outliers_matches_reference checks the resulting
 // outlier decisions against the reference on grid-heavy random inputs (duplicates and lists beyond the device limit included).
 #include "delaunay.h"
+#include "visocu.h"
 
 #include <algorithm>
 #include <cstdint>
@@ -33,7 +34,8 @@ struct Mesh {
   HalfEdge* he;                             // per directed edge; sym(e) = e ^ 1 (storage owned by the caller)
   int nhe, cap;
   std::vector<HalfEdge> store;
-  std::vector<uint8_t> flag;                // per half-edge: 1 = removed, 2 = left face is the unbounded face
+  std::vector<uint8_t> flag;                // per half-edge: 1 = removed, 2 = left face is the unbounded face (records taken over
+                                            // from the device mark removed and unused entries with org = -1 instead)
   void set_points(const Pt* p) { pt = p; }
   void reset(size_t want) {
     if (store.size() < want) store.resize(want);
@@ -42,12 +44,20 @@ struct Mesh {
   }
   uint32_t packed(int v) const { return (uint32_t)pt[v].x | ((uint32_t)pt[v].y << 16); }
 
+  // records that live elsewhere (the mesh the device delivered): used of them are taken, up to capacity may be written
+  void adopt(HalfEdge* records, int used, int capacity) {
+    he = records; nhe = used; cap = capacity;
+    flag.assign((size_t)capacity, 0);
+  }
+  void grow() {                             // cannot happen with the 12 n reservation (3 n live + deleted edges); grow anyway
+    std::vector<HalfEdge> bigger((size_t)cap * 2 + 64);
+    std::copy(he, he + nhe, bigger.begin());
+    store.swap(bigger);
+    he = store.data(); cap = (int)store.size();
+    flag.resize(store.size(), 0);
+  }
   int make_edge(int a, int b) {
-    if (nhe + 2 > cap) {                    // cannot happen with the 12 n reservation (3 n live + deleted edges); grow anyway
-      store.resize(store.size() * 2 + 64);
-      he = store.data(); cap = (int)store.size();
-      flag.resize(store.size(), 0);
-    }
+    if (nhe + 2 > cap) grow();
     const int e = nhe;
     he[e] = HalfEdge{e, e, a, packed(a)};
     he[e + 1] = HalfEdge{e + 1, e + 1, b, packed(b)};
@@ -56,11 +66,7 @@ struct Mesh {
   }
   // edge between the origins of half-edges ea and eb (numbers and coordinates copied from them)
   int make_edge_like(int ea, int eb) {
-    if (nhe + 2 > cap) {
-      store.resize(store.size() * 2 + 64);
-      he = store.data(); cap = (int)store.size();
-      flag.resize(store.size(), 0);
-    }
+    if (nhe + 2 > cap) grow();
     const int e = nhe;
     he[e] = HalfEdge{e, e, he[ea].org, he[ea].xy};
     he[e + 1] = HalfEdge{e + 1, e + 1, he[eb].org, he[eb].xy};
@@ -167,8 +173,7 @@ struct Handles { int ldo, rdo; };   // ccw hull edge out of the leftmost vertex,
 // Vertices are numbered by their rank in (x, y) order.  Every node keeps its vertex set twice, once in x order (xl)
 // and once in (y, x) order (yl); a split takes the first half of the list of its axis and distributes the other list
 // stably with one linear pass, so no comparison sort is needed below the root.  On return xl holds the final order.
-void partition(int* xl, int* yl, int n, int axis, uint8_t* side, int* tmp) {
-  if (n <= 3) return;                       // xl is already the x-sorted leaf
+int split(int* xl, int* yl, int n, int axis, uint8_t* side, int* tmp) {
   const int divider = n >> 1;
   int* from = axis == 0 ? xl : yl;          // list that defines the halves
   int* other = axis == 0 ? yl : xl;
@@ -182,8 +187,24 @@ void partition(int* xl, int* yl, int n, int axis, uint8_t* side, int* tmp) {
     b += s; a += 1 - s;
   }
   for (int i = 0; i < b; i++) other[divider + i] = tmp[i];
+  return divider;
+}
+
+void partition(int* xl, int* yl, int n, int axis, uint8_t* side, int* tmp) {
+  if (n <= 3) return;                       // xl is already the x-sorted leaf
+  const int divider = split(xl, yl, n, axis, side, tmp);
   partition(xl, yl, divider, 1 - axis, side, tmp);
   partition(xl + divider, yl + divider, n - divider, 1 - axis, side, tmp);
+}
+
+// the upper part of the same tree only: nodes of at most `stop` vertices are left as they are (x order in xl, (y, x)
+// order in yl) and listed, in order of their first vertex
+struct Node { int lo, n, axis; };
+void partition_nodes(int* xl, int* yl, int lo, int n, int axis, uint8_t* side, int* tmp, int stop, std::vector<Node>& nodes) {
+  if (n <= stop) { nodes.push_back(Node{lo, n, axis}); return; }
+  const int divider = split(xl + lo, yl + lo, n, axis, side, tmp);
+  partition_nodes(xl, yl, lo, divider, 1 - axis, side, tmp, stop, nodes);
+  partition_nodes(xl, yl, lo + divider, n - divider, 1 - axis, side, tmp, stop, nodes);
 }
 
 Handles merge(Mesh& m, Handles L, Handles R, int axis) {
@@ -278,8 +299,20 @@ struct Scratch {
   std::vector<Pt> pts, pts_in;
   std::vector<int> v, yl, tmp, a, b;
   std::vector<uint8_t> side;
+  std::vector<uint64_t> ka, kb;
   Mesh m;
+  // device-built nodes
+  std::vector<Node> nodes;
+  std::vector<uint32_t> packed;
+  std::vector<int32_t> first, count, axis;
+  std::vector<int32_t> mesh_first;
+  std::vector<Handles> node_h;
 };
+
+thread_local visocu_ctx* g_device = nullptr;
+thread_local long g_device_nodes = 0;
+const int kDeviceMin = 6000;          // fewer distinct points: the list fits the device path of removeOutliers as a whole
+const int kDeviceNode = 4096;         // largest node handed to the device (shared memory of one CTA)
 
 // stable counting sort of ids by key[id] (keys in [lo, lo + range))
 void counting_pass(const std::vector<int>& in, std::vector<int>& out, const int32_t* key, int lo, int range, std::vector<int32_t>& cnt) {
@@ -288,6 +321,16 @@ void counting_pass(const std::vector<int>& in, std::vector<int>& out, const int3
   for (int k = 0; k < range; k++) cnt[k + 1] += cnt[k];
   out.resize(in.size());
   for (int id : in) out[cnt[key[id] - lo]++] = id;
+}
+
+int build_on_device(Scratch& S, int nu, int xlo, int ylo, Handles& out);
+
+// stable counting sort of records by the 16-bit digit at `shift` (values in [0, range))
+void radix_pass(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, int shift, int range, std::vector<int32_t>& cnt) {
+  cnt.assign((size_t)range + 1, 0);
+  for (uint64_t k : in) cnt[((k >> shift) & 0xFFFF) + 1]++;
+  for (int k = 0; k < range; k++) cnt[k + 1] += cnt[k];
+  for (uint64_t k : in) out[cnt[(k >> shift) & 0xFFFF]++] = k;
 }
 
 // Builds the triangulation in S.m; S.orig maps mesh vertex numbers to input indices.  Returns the final hull handles
@@ -304,13 +347,16 @@ Handles triangulate(Scratch& S, const int32_t* x, const int32_t* y, int n) {
     fprintf(stderr, "ERROR: delaunay: coordinate range %d x %d exceeds 65535\n", xhi - xlo, yhi - ylo);
     return none;
   }
-  // sort by (x, y, input index): two stable counting passes (pixel coordinates span a few thousand values)
+  // sort by (x, y, input index): two stable counting passes (pixel coordinates span a few thousand values) over records
+  // that carry their keys along, x | y | index, so that every pass reads and writes one array front to back
+  S.ka.resize(n); S.kb.resize(n);
+  for (int i = 0; i < n; i++) S.ka[i] = ((uint64_t)(uint32_t)(x[i] - xlo) << 48) | ((uint64_t)(uint32_t)(y[i] - ylo) << 32) | (uint32_t)i;
+  radix_pass(S.ka, S.kb, 32, yhi - ylo + 1, S.cnt);
+  radix_pass(S.kb, S.ka, 48, xhi - xlo + 1, S.cnt);
   S.a.resize(n);
-  for (int i = 0; i < n; i++) S.a[i] = i;
-  counting_pass(S.a, S.b, y, ylo, yhi - ylo + 1, S.cnt);
-  counting_pass(S.b, S.a, x, xlo, xhi - xlo + 1, S.cnt);
+  for (int i = 0; i < n; i++) S.a[i] = (int)(uint32_t)S.ka[i];
   bool duplicates = false;
-  for (int i = 1; i < n && !duplicates; i++) duplicates = x[S.a[i]] == x[S.a[i - 1]] && y[S.a[i]] == y[S.a[i - 1]];
+  for (int i = 1; i < n && !duplicates; i++) duplicates = (S.ka[i] >> 32) == (S.ka[i - 1] >> 32);
   S.orig.clear();
   if (!duplicates) {
     S.orig.assign(S.a.begin(), S.a.end());
@@ -335,14 +381,20 @@ Handles triangulate(Scratch& S, const int32_t* x, const int32_t* y, int n) {
   if (nu < 2) return none;
   // vertices renumbered by (x, y) rank, coordinates stored in that order
   S.sx.resize(nu); S.sy.resize(nu);
-  for (int i = 0; i < nu; i++) { S.sx[i] = x[S.orig[i]]; S.sy[i] = y[S.orig[i]]; }
+  if (!duplicates) for (int i = 0; i < nu; i++) { S.sx[i] = xlo + (int32_t)(S.ka[i] >> 48); S.sy[i] = ylo + (int32_t)((S.ka[i] >> 32) & 0xFFFF); }
+  else for (int i = 0; i < nu; i++) { S.sx[i] = x[S.orig[i]]; S.sy[i] = y[S.orig[i]]; }
   S.v.resize(nu);
   for (int i = 0; i < nu; i++) S.v[i] = i;
   counting_pass(S.v, S.yl, S.sy.data(), ylo, yhi - ylo + 1, S.cnt);     // ids in (y, x) order
   S.side.resize(nu); S.tmp.resize(nu);
+  if (g_device && nu > kDeviceMin && xhi - xlo <= 8191 && yhi - ylo <= 8191) {
+    Handles h;
+    if (build_on_device(S, nu, xlo, ylo, h)) return h;
+  } else {
+    // root: vertical cut of the x-sorted list, children by alternating axes
+    partition(S.v.data(), S.yl.data(), nu, 0, S.side.data(), S.tmp.data());
+  }
   S.m.reset(12 * (size_t)nu + 64);
-  // root: vertical cut of the x-sorted list, children by alternating axes
-  partition(S.v.data(), S.yl.data(), nu, 0, S.side.data(), S.tmp.data());
   // renumber once more, in partition order: every subtree of the divide-and-conquer then works on a contiguous range
   // of vertices (and of the edges it creates), which keeps the merge loops in cache
   S.pts.resize(nu);
@@ -353,12 +405,82 @@ Handles triangulate(Scratch& S, const int32_t* x, const int32_t* y, int n) {
   return build(S.m, S.v.data(), nu, 0);
 }
 
+// Large triangulations: the tree is cut where its nodes fit the device kernel (depth 5 for the 87 k matches of a
+// 3840x2160 frame pair: 32 nodes of 2.7 k vertices), the device triangulates the nodes (one CTA each, in parallel), and
+// the few merges above them - whose seams are all that is left of the sequential work - run here, in place on the records the device delivered.
+// Returns 1 = done (handles in out), 0 = the device did not deliver; S.v / S.yl are then partitioned completely, exactly
+// as partition() from the root would have left them, and the caller builds on the host.
+int build_on_device(Scratch& S, int nu, int xlo, int ylo, Handles& out) {
+  S.nodes.clear();
+  partition_nodes(S.v.data(), S.yl.data(), 0, nu, 0, S.side.data(), S.tmp.data(), kDeviceNode, S.nodes);
+  const int nj = (int)S.nodes.size();
+  auto finish_on_host = [&]() {
+    for (const Node& nd : S.nodes) partition(S.v.data() + nd.lo, S.yl.data() + nd.lo, nd.n, nd.axis, S.side.data(), S.tmp.data());
+    return 0;
+  };
+  S.packed.resize(nu); S.first.resize(nj); S.count.resize(nj); S.axis.resize(nj); S.mesh_first.resize(nj);
+  for (int i = 0; i < nu; i++) S.packed[i] = (uint32_t)(S.sx[S.v[i]] - xlo) | ((uint32_t)(S.sy[S.v[i]] - ylo) << 16);
+  for (int j = 0; j < nj; j++) { S.first[j] = S.nodes[j].lo; S.count[j] = S.nodes[j].n; S.axis[j] = S.nodes[j].axis; }
+  int32_t* mesh = nullptr; const int32_t* vert = nullptr; const int32_t* res = nullptr;
+  int32_t n_he = 0;
+  const int extra = 65536 + nu / 2;        // half-edges the merges above the nodes may add (a few per seam vertex)
+  if (visocu_delaunay_subtrees(g_device, S.packed.data(), nu, nj, S.first.data(), S.count.data(), S.axis.data(), extra, &mesh, S.mesh_first.data(),
+                               &n_he, &vert, &res) != VISOCU_OK) {
+    fprintf(stderr, "WARNING: delaunay: device nodes failed (%s), triangulating on the host\n", visocu_last_error(g_device));
+    return finish_on_host();
+  }
+  // status, sizes, handles and the vertex maps are checked before use (the records themselves are taken as they are,
+  // like every other list a kernel delivers)
+  static_assert(sizeof(HalfEdge) == 16, "the device writes half-edge records of four words");
+  HalfEdge* he = reinterpret_cast<HalfEdge*>(mesh);
+  S.node_h.resize(nj);
+  for (int j = 0; j < nj; j++) {
+    const int32_t* r = res + 16 * j;
+    const int lo = S.nodes[j].lo, n = S.nodes[j].n, E = r[2], C2 = 2 * visocu_delaunay_edge_capacity(n), b0 = S.mesh_first[j];
+    if (r[1] != 0 || r[0] != n || E <= 0 || 2 * E > C2 || b0 < 0 || b0 + C2 > n_he || r[4] < b0 || r[4] >= b0 + 2 * E || r[5] < b0 || r[5] >= b0 + 2 * E)
+      return finish_on_host();
+    if (he[r[4]].org < 0 || he[r[5]].org < 0) return finish_on_host();
+    std::fill(S.side.begin() + lo, S.side.begin() + lo + n, 0);
+    for (int i = 0; i < n; i++) {
+      const int32_t k = vert[lo + i];
+      if (k < 0 || k >= n || S.side[lo + k]) return finish_on_host();
+      S.side[lo + k] = 1;
+      S.tmp[lo + i] = S.v[lo + k];            // vertex order of the complete partition tree (what partition() computes on the host)
+    }
+    S.node_h[j] = Handles{r[4], r[5]};
+  }
+  std::copy(S.tmp.begin(), S.tmp.begin() + nu, S.v.begin());
+  S.pts.resize(nu);
+  for (int i = 0; i < nu; i++) { S.pts[i] = Pt{S.sx[S.v[i]] - xlo, S.sy[S.v[i]] - ylo}; S.tmp[i] = S.orig[S.v[i]]; }
+  for (int i = 0; i < nu; i++) { S.orig[i] = S.tmp[i]; S.v[i] = i; }
+  Mesh& m = S.m;
+  m.set_points(S.pts.data());
+  m.adopt(he, n_he, n_he + extra);           // the merges work on the delivered records in place
+  // the merges above the nodes, in the order of the recursion
+  struct Top {
+    Scratch& S; int next;
+    Handles run(int n, int axis) {
+      if (n <= kDeviceNode) return S.node_h[next++];
+      const int divider = n >> 1;
+      const Handles L = run(divider, 1 - axis);
+      const Handles R = run(n - divider, 1 - axis);
+      return merge(S.m, L, R, axis);
+    }
+  } top{S, 0};
+  out = top.run(nu, 0);
+  g_device_nodes += nj;
+  return 1;
+}
+
 Scratch& scratch() {
   static thread_local Scratch S;     // reused from call to call (one ~5 k point triangulation per frame pair and worker)
   return S;
 }
 
 }  // namespace
+
+void delaunay_use_device(visocu_ctx* ctx) { g_device = ctx; }
+long delaunay_device_nodes() { return g_device_nodes; }
 
 void delaunay_triangles(const int32_t* x, const int32_t* y, int n, std::vector<int32_t>& tri) {
   tri.clear();
@@ -370,7 +492,7 @@ void delaunay_triangles(const int32_t* x, const int32_t* y, int n, std::vector<i
   const int ne = m.nhe;
   tri.reserve(6 * S.orig.size());
   for (int e = 0; e < ne; e++) {
-    if (m.flag[e]) continue;
+    if (m.flag[e] || m.he[e].org < 0) continue;
     const int e2 = m.lnext(e);
     if (e2 < e) continue;
     const int e3 = m.lnext(e2);
@@ -392,14 +514,22 @@ void delaunay_edges(const int32_t* x, const int32_t* y, int n, std::vector<int32
   int e = h.rdo;
   do { m.flag[e] |= 2; e = m.lnext(e); } while (e != h.rdo);
   const int ne = m.nhe;
-  edges.reserve(9 * S.orig.size());
+  edges.resize(3 * ((size_t)ne / 2));
+  int32_t* out = edges.data();
+  const HalfEdge* he = m.he;
+  const uint8_t* flag = m.flag.data();
+  const int32_t* orig = S.orig.data();
   for (int k = 0; k < ne; k += 2) {
-    const int d0 = m.flag[k], d1 = m.flag[k + 1];
+    const int o0 = he[k].org, o1 = he[k + 1].org;
+    if (o0 < 0) continue;                    // deleted or unused record of a device node
+    const int d0 = flag[k], d1 = flag[k + 1];
     if ((d0 | d1) & 1) continue;
     const int t = (d0 & 2 ? 0 : 1) + (d1 & 2 ? 0 : 1);
     if (t == 0) continue;
-    edges.push_back(S.orig[m.he[k].org]); edges.push_back(S.orig[m.he[k + 1].org]); edges.push_back(t);
+    out[0] = orig[o0]; out[1] = orig[o1]; out[2] = t;
+    out += 3;
   }
+  edges.resize((size_t)(out - edges.data()));
 }
 
 }  // namespace visob

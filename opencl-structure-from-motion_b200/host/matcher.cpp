@@ -477,23 +477,33 @@ void Matcher::removeOutliers(vector<p_match>& p_matched, int32_t method) {
   static thread_local vector<int32_t> x, y, edges, support;
   x.resize(n); y.resize(n);
   for (int32_t i = 0; i < n; i++) { x[i] = (int32_t)p_matched[i].u1c; y[i] = (int32_t)p_matched[i].v1c; }
+  // lists beyond the device path as a whole (3840x2160 frames): the nodes of the triangulation's tree that fit the device
+  // kernel are built there, the merges above them and the vote here (delaunay.cpp build_on_device)
+  static const bool device_nodes = [] { const char* e = getenv("VISOB_DEVICE_NODES"); return !(e && e[0] == '0'); }();
+  visob::delaunay_use_device(visob::device_outliers() && device_nodes ? ctx : nullptr);
   visob::delaunay_edges(x.data(), y.data(), n, edges);
+  visob::delaunay_use_device(nullptr);
   support.assign(n, 0);
   const float flow_tol = (float)param.outlier_flow_tolerance, disp_tol = (float)param.outlier_disp_tolerance;
-  // float arithmetic throughout, as in the reference (matcher.cpp:1273-1349: float flows, fabs on floats)
-  auto edge_ok = [&](const p_match& a, const p_match& b) -> bool {
-    if (method == 0) {
-      return fabsf((a.u1c - a.u1p) - (b.u1c - b.u1p)) + fabsf((a.v1c - a.v1p) - (b.v1c - b.v1p)) < flow_tol;
-    } else if (method == 1) {
-      return fabsf((a.u1c - a.u2c) - (b.u1c - b.u2c)) < disp_tol;
-    }
-    return fabsf((a.u1p - a.u2p) - (b.u1p - b.u2p)) < disp_tol &&
-           fabsf((a.u1c - a.u1p) - (b.u1c - b.u1p)) + fabsf((a.v1c - a.v1p) - (b.v1c - b.v1p)) < flow_tol;
+  // float arithmetic throughout, as in the reference (matcher.cpp:1273-1349: float flows, fabs on floats).  What an edge
+  // compares is computed once per match (the same float subtractions), so that the vote walks three small arrays instead
+  // of the 48-byte records
+  static thread_local vector<float> fu, fv, fd;
+  fu.resize(n); fv.resize(n); fd.resize(n);
+  for (int32_t i = 0; i < n; i++) {
+    const p_match& a = p_matched[i];
+    fu[i] = a.u1c - a.u1p; fv[i] = a.v1c - a.v1p;
+    fd[i] = method == 1 ? a.u1c - a.u2c : a.u1p - a.u2p;
+  }
+  auto edge_ok = [&](int32_t a, int32_t b) -> bool {
+    if (method == 0) return fabsf(fu[a] - fu[b]) + fabsf(fv[a] - fv[b]) < flow_tol;
+    if (method == 1) return fabsf(fd[a] - fd[b]) < disp_tol;
+    return fabsf(fd[a] - fd[b]) < disp_tol && fabsf(fu[a] - fu[b]) + fabsf(fv[a] - fv[b]) < flow_tol;
   };
   // the reference votes per triangle edge (matcher.cpp:1259-1362): an edge shared by two triangles counts twice
   for (size_t e = 0; e + 2 < edges.size(); e += 3) {
     const int32_t a = edges[e], b = edges[e + 1], t = edges[e + 2];
-    if (edge_ok(p_matched[a], p_matched[b])) { support[a] += t; support[b] += t; }
+    if (edge_ok(a, b)) { support[a] += t; support[b] += t; }
   }
   int32_t k = 0;
   for (int32_t i = 0; i < n; i++)

@@ -293,6 +293,20 @@ def delaunay(x, y):
     return tri[:n].copy()
 
 
+def delaunay_edges(x, y, ctx=None):
+    """(a, b, t) per undirected edge of the triangulation, t = triangles it bounds.  ctx: a visocu_py.Context - inputs of more
+    than 6000 points then build the lower levels of their tree on the device.  Returns (edges, nodes built on the device)."""
+    import ctypes as C
+    x = np.ascontiguousarray(x, np.int32); y = np.ascontiguousarray(y, np.int32)
+    cap = 3 * len(x) + 8
+    e = np.zeros((cap, 3), np.int32)
+    nodes = C.c_int64(0)
+    L = lib()
+    L.visob_delaunay_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    n = L.visob_delaunay_edges(ctx.h if ctx is not None else None, _p(x), _p(y), len(x), _p(e), cap, C.byref(nodes))
+    return e[:n].copy(), int(nodes.value)
+
+
 def svd(A):
     A = np.ascontiguousarray(A, np.float64)
     m, n = A.shape

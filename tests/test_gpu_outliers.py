@@ -75,3 +75,31 @@ def test_device_outlier_removal_declines_what_it_cannot_do(ref, rctx):
     rm = ref.matcher(pyref.MatcherParams(half_resolution=0))
     if status[3] == 0:                                                   # all collinear: no triangle, nobody survives
         assert got[3].tobytes() == rm.remove_outliers(line, 0).tobytes()
+
+
+def test_device_nodes_of_large_triangulations(rctx):
+    """visocu_delaunay_subtrees through host/delaunay.cpp: a triangulation of more points than the device kernel holds is cut
+    into nodes that the device builds; the edge list (hence every vote of removeOutliers) equals the all-host one."""
+    import host_py as H
+    rng = np.random.default_rng(41)
+    for n, w, h, grid in ((6500, 1241, 376, 1), (20000, 3840, 2160, 2), (87000, 3840, 2160, 2), (60000, 3840, 2160, 1), (9000, 8000, 200, 1)):
+        cells = rng.choice((w // grid) * (h // grid), size=n, replace=False)
+        x = ((cells % (w // grid)) * grid + 2).astype(np.int32); y = ((cells // (w // grid)) * grid + 3).astype(np.int32)
+        e_host, nodes0 = H.delaunay_edges(x, y)
+        e_dev, nodes = H.delaunay_edges(x, y, rctx)
+        assert nodes0 == 0 and nodes >= 2, (n, nodes)
+        norm = lambda e: np.unique(np.concatenate([np.sort(e[:, :2], 1), e[:, 2:]], 1), axis=0)
+        assert len(e_dev) == len(e_host) and np.array_equal(norm(e_host), norm(e_dev)), (n, w, h, grid)
+
+
+def test_large_lists_vote_with_device_nodes(ref):
+    """Matcher::removeOutliers on lists of 3840x2160 size (the device declines them as a whole): survivors equal the reference's."""
+    import host_py as H
+    import pyref
+    rng = np.random.default_rng(43)
+    hm = H.Matcher(V.Params()); rm = ref.matcher(pyref.MatcherParams())
+    img = np.zeros((480, 640), np.uint8)
+    hm.push(img)                                            # gives the matcher its context
+    for n, grid in ((20000, 2), (87000, 2)):
+        m = _random_matches(rng, n, 3800, 2100, grid, False)
+        assert hm.remove_outliers(m, 0).tobytes() == rm.remove_outliers(m, 0).tobytes(), (n, grid)

@@ -72,6 +72,28 @@ def test_remove_outliers_matches_reference(ref):
     assert hm.remove_outliers(line, 0).tobytes() == rm.remove_outliers(line, 0).tobytes()       # all collinear
 
 
+def test_large_list_tree_with_device_nodes(tmp_path):
+    """Lists beyond the device kernel (3840x2160): host/delaunay.cpp cuts the divide-and-conquer tree into nodes, takes their
+    meshes from the device and merges above them.  Here the device entry point is a stand-in (tests/sim_device_nodes.cpp:
+    the host algorithm answering in the device's format), so the cutting, the vertex maps, the import and the top merges run
+    on the CPU: same edge list as the all-host triangulation, also when the device fails, declines a node or returns a corrupt mesh."""
+    import ctypes as C
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / 'libsim_nodes.so')
+    subprocess.check_call(['g++', '-O2', '-std=c++14', '-shared', '-fPIC', '-I' + os.path.join(root, 'include'),
+                           '-I' + os.path.join(root, 'opencl-structure-from-motion_b200', 'host'),
+                           os.path.join(root, 'tests', 'sim_device_nodes.cpp'), '-o', so])
+    L = C.CDLL(so)
+    calls = C.c_int(); ne = C.c_int()
+    cases = [(5000, 1241, 376, 2, 0, 0), (6001, 2000, 300, 1, 0, 1), (7000, 1241, 376, 2, 0, 1), (20000, 3840, 2160, 2, 0, 1),
+             (87000, 3840, 2160, 2, 0, 1), (30000, 3840, 2160, 4, 0, 1), (9000, 8000, 200, 1, 0, 1), (9000, 9000, 200, 1, 0, 0),
+             (20000, 3840, 2160, 2, 1, 1), (20000, 3840, 2160, 2, 2, 1), (20000, 3840, 2160, 2, 3, 1)]
+    for n, w, h, grid, fail, want_calls in cases:
+        assert L.sim_check(n, w, h, 11 + n, grid, fail, C.byref(calls), C.byref(ne)) == 0, (n, w, h, grid, fail)
+        assert calls.value == want_calls and ne.value > 2.9 * n - 400, (n, w, h, calls.value, ne.value)
+
+
 def test_delaunay_is_delaunay():
     rng = np.random.default_rng(2)
     key = rng.choice(300 * 200, 500, replace=False)
