@@ -325,7 +325,7 @@ def extra_workloads(args):
     """Short single-GPU runs of the other configurations of BASELINE.json, each in its own process (fresh CUDA state)."""
     out = {}
     todo = [('quad', ['--workload', 'quad']), ('mono', ['--workload', 'mono']), ('mono_bucket1000', ['--workload', 'mono', '--bucket', '1000']),
-            ('flow_3840x2160', ['--workload', 'flow4k', '--sequences', '16', '--steps', '6'])]
+            ('flow_3840x2160', ['--workload', 'flow4k', '--sequences', '24', '--threads', '24', '--steps', '16'])]
     for name, extra in todo:
         if extra[1] == args.workload and '--bucket' not in extra and int(args.bucket) == 2:
             continue

@@ -43,6 +43,8 @@ struct MatchJob {
   const uint8_t* dv[4];
   int nq, dyn;                       // dyn: nq is only the capacity, the real count comes from cnt[] (device memory)
   const int32_t* cnt[4];             // record counters of the four sets for this pass (null = set not used)
+  const int32_t* gate;               // second pass of a fused call: status word of the first pass's outlier removal.  Non-zero
+                                     // (list declined: the host votes, computes the ranges and repeats this pass) = no queries
 };
 
 __device__ __forceinline__ int bin_index(const Geometry& g, int u, int v) {
@@ -56,6 +58,7 @@ __device__ __forceinline__ int bin_index(const Geometry& g, int u, int v) {
 // with the reference's rule that nothing is matched if a needed set is empty (matcher.cpp:190-212).
 __device__ __forceinline__ int job_nq(const MatchJob& J, int method) {
   if (!J.dyn) return J.nq;
+  if (J.gate && *J.gate != 0) return 0;
   const int a = J.cnt[0] ? *J.cnt[0] : 1, b = J.cnt[1] ? *J.cnt[1] : 1, c = J.cnt[2] ? *J.cnt[2] : 1, d = J.cnt[3] ? *J.cnt[3] : 1;
   if (a == 0 || b == 0 || c == 0 || d == 0) return 0;
   return min(method == 2 ? a : c, J.nq);
@@ -590,6 +593,7 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
       for (int k = 0; k < 4; k++) if (need[k] && hj[j].s[k].n == 0) empty = true;
       const int nq = empty ? 0 : (method == 2 ? hj[j].s[0].n : hj[j].s[2].n);
       hj[j].nq = nq; hj[j].dyn = dyn ? 1 : 0;
+      if (mode == 3 && dyn && n_jobs <= VISO_MAX_BATCH && ctx->part[0].pending) hj[j].gate = ctx->part[0].dev_words + 16 * j + 1;
       if (nq > maxq) maxq = nq;
       if (use_prior && !dev_ranges && !ranges[start + j]) return visocu_set_error(ctx, VISOCU_EINVAL, "job %d has no ranges", start + j);
     }

@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+pick='import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d["value"], d["e2e"]["value"], d["ms_per_step"], d["config"].get("host_ms_per_call"))'
+for cfg in "16 16" "24 24"; do set -- $cfg
+  echo "== 4K sequences=$1 threads=$2"; timeout 400 python bench.py --workload flow4k --sequences $1 --threads $2 --steps 6 --warmup 3 --no-extra --no-roofline --no-cpu-baseline 2>/dev/null | python -c "$pick"
+done
+echo "== flow default"; timeout 300 python bench.py --no-extra --no-roofline --no-cpu-baseline 2>/dev/null | python -c "$pick"
