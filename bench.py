@@ -337,7 +337,8 @@ def extra_workloads(args):
             out[name] = {'value': d['value'], 'e2e': d['e2e']['value'], 'unit': UNIT, 'ms_per_step': d['ms_per_step'], 'steps': d['steps'],
                          'workload': d['config']['workload'], 'sequences': d['config']['sequences_per_gpu'],
                          'matches_per_pair': d['config']['matches_per_pair'], 'process_ok_fraction': d['config']['process_ok_fraction'],
-                         'outlier_lists_declined': d['config']['outlier_removal'].get('declined')}
+                         'outlier_lists_declined': d['config']['outlier_removal'].get('declined'),
+                         'declined_lists_built_in_device_nodes': d['config']['outlier_removal'].get('declined_lists_built_in_device_nodes')}
         except Exception as e:
             out[name] = {'error': str(e)[:200]}
     return out
@@ -428,7 +429,7 @@ def main():
                        'device': info['name'], 'matches_per_pair': round(res_dev['matches_per_pair'], 1),
                        'process_ok_fraction': res_dev['ok_frac'],
                        'host_ms_per_call': res_dev.get('stages'),
-                       'outlier_removal': dict(where='device (csrc/outliers.cu; lists it declines go to the host implementation)',
+                       'outlier_removal': dict(where='device (csrc/outliers.cu); a list too long for one CTA (3840x2160) is declined as a whole: its triangulation tree is cut into nodes the same kernel builds, the few merges above them and the vote run on the host',
                                                **res_dev.get('outliers', {}))},
             'clocks': res_dev['clocks'],
             'e2e': {'value': round(pairs / (ms_e2e * 1e-3), 2), 'unit': UNIT, 'h2d_bytes_per_step': int(res_e2e['h2d'] * world),

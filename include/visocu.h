@@ -218,6 +218,8 @@ int  visocu_launch_count(const visocu_ctx* ctx, uint64_t* n);
 /* device outlier removal so far: out8 = lists handled, lists declined (too long, duplicates, guard: [2..4]), and the
  * summed kernel time of the handled lists in nanoseconds ([5] sort + partition, [6] build, [7] vote + compaction) */
 int  visocu_outlier_stats(const visocu_ctx* ctx, uint64_t* out8);
+/* visocu_delaunay_subtrees: out2[0] = calls (lists too long for the device path as a whole), out2[1] = nodes built */
+int  visocu_node_stats(const visocu_ctx* ctx, uint64_t* out2);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

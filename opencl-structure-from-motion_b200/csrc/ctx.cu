@@ -446,6 +446,12 @@ extern "C" int visocu_outlier_stats(const visocu_ctx* ctx, uint64_t* out8) {
   return VISOCU_OK;
 }
 
+extern "C" int visocu_node_stats(const visocu_ctx* ctx, uint64_t* out2) {
+  if (!ctx || !out2) return VISOCU_EINVAL;
+  out2[0] = ctx->ro_node_calls; out2[1] = ctx->ro_nodes;
+  return VISOCU_OK;
+}
+
 extern "C" int visocu_launch_count(const visocu_ctx* ctx, uint64_t* n) {
   if (!ctx || !n) return VISOCU_EINVAL;
   *n = ctx->launches;

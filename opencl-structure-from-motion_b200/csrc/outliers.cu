@@ -823,6 +823,8 @@ extern "C" int visocu_delaunay_subtrees(visocu_ctx* ctx, const uint32_t* pts, in
   CU_COPY(ctx, pin + h_vert, sb + d_vert, (size_t)4 * n_pts, cudaMemcpyDeviceToHost);
   CU_COPY(ctx, pin + h_mesh, sb + d_mesh, 16 * n_he, cudaMemcpyDeviceToHost);
   CU_TRY(ctx, visocu_stream_wait(ctx));
+  ctx->ro_node_calls++;
+  for (int j = 0; j < n_jobs; j++) if (hres[16 * j + 1] == 0) ctx->ro_nodes++;
   *mesh = (int32_t*)(pin + h_mesh); *n_halfedges = (int32_t)n_he; *vert = (const int32_t*)(pin + h_vert); *result = hres;
   return VISOCU_OK;
 }

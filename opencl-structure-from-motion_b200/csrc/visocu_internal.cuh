@@ -130,6 +130,7 @@ struct visocu_ctx {
   double filter_ms = 0; uint64_t filter_launches = 0, filter_frames = 0;
   uint64_t* d_stats = nullptr;       // [0] SAD candidates, [1] entries scanned
   uint64_t h_stats[2] = {0, 0};
+  uint64_t ro_node_calls = 0, ro_nodes = 0;   // visocu_delaunay_subtrees: large lists, nodes built for them
   uint64_t ro_ns[4] = {0, 0, 0, 0}, ro_jobs = 0, ro_declined = 0, ro_reason[4] = {0, 0, 0, 0}, ro_declined_n = 0;   // device outlier removal: phase times (VISOCU_RO_STATS)
 };
 

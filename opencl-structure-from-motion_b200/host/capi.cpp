@@ -473,6 +473,13 @@ VISOB_API void visob_runner_outlier_stats(void* h, uint64_t* out8) {
     if (m->context() && visocu_outlier_stats(m->context(), one) == 0)
       for (int k = 0; k < 8; k++) out8[k] += one[k];
 }
+VISOB_API void visob_runner_node_stats(void* h, uint64_t* out2) {
+  Runner* r = (Runner*)h;
+  uint64_t one[2];
+  out2[0] = out2[1] = 0;
+  for (MatcherBatch* m : r->batches)
+    if (m->context() && visocu_node_stats(m->context(), one) == 0) { out2[0] += one[0]; out2[1] += one[1]; }
+}
 VISOB_API uint64_t visob_runner_launches(void* h) {
   Runner* r = (Runner*)h;
   uint64_t total = 0, n = 0;

@@ -369,7 +369,9 @@ class Runner:
         out = np.zeros(8, np.uint64)
         lib().visob_runner_outlier_stats(self.h, _p(out))
         n = max(int(out[0]), 1)
-        return dict(lists=int(out[0]), declined=int(out[1]), declined_too_long=int(out[2]), declined_duplicates=int(out[3]),
+        nodes = np.zeros(2, np.uint64)
+        lib().visob_runner_node_stats(self.h, _p(nodes))
+        return dict(lists=int(out[0]), declined=int(out[1]), declined_lists_built_in_device_nodes=int(nodes[0]), device_nodes=int(nodes[1]), declined_too_long=int(out[2]), declined_duplicates=int(out[3]),
                     declined_guard=int(out[4]), sort_partition_us=round(float(out[5]) / n / 1e3, 1),
                     build_us=round(float(out[6]) / n / 1e3, 1), vote_us=round(float(out[7]) / n / 1e3, 1))
 
