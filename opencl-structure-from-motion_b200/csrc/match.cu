@@ -90,20 +90,28 @@ __device__ __forceinline__ int find_match(const Geometry& g, const SetDev& A, in
     for (int vbin = vbmin; vbin <= vbmax; vbin++) {
       const int row = (c * g.vb + vbin) * g.ub;
       const int e0 = B.bin_start[row + ubmin], e1 = ubmax >= ubmin ? B.bin_start[row + ubmax + 1] : e0;
-      for (int e = e0 + sub; e < e1; e += G) {
-        const int2 ent = B.bin_ent[e];
-        const int u2 = ent.x & 0xFFFF, v2 = (int)((unsigned)ent.x >> 16);
-        n_scan++;
-        if ((float)u2 >= u_min && (float)u2 <= u_max && (float)v2 >= v_min && (float)v2 <= v_max) {
-          const int32_t* t = B.rec + (size_t)ent.y * 12;
-          const uint4 ta = *(const uint4*)(t + 4), tb = *(const uint4*)(t + 8);
-          unsigned sad = __vsadu4(qa.x, ta.x) + __vsadu4(qa.y, ta.y) + __vsadu4(qa.z, ta.z) + __vsadu4(qa.w, ta.w) +
-                         __vsadu4(qb.x, tb.x) + __vsadu4(qb.y, tb.y) + __vsadu4(qb.z, tb.z) + __vsadu4(qb.w, tb.w);
-          const int ub2 = min((int)floorf((float)u2 / bs), g.ub - 1);
-          unsigned long long key = ((unsigned long long)sad << 48) | ((unsigned long long)ub2 << 36) |
-                                   ((unsigned long long)vbin << 24) | (unsigned long long)ent.y;
-          best = key < best ? key : best;
-          n_cand++;
+      // Most scanned entries fail the window test, so the scan is a chain of entry loads: four entries per lane are in
+      // flight at a time (a position of 0xFFFF, 0xFFFF stands for "past the end": it fails every window)
+      for (int e = e0 + sub; e < e1; e += 4 * G) {
+        int2 ent4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) ent4[k] = e + k * G < e1 ? B.bin_ent[e + k * G] : make_int2(-1, 0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int2 ent = ent4[k];
+          const int u2 = ent.x & 0xFFFF, v2 = (int)((unsigned)ent.x >> 16);
+          n_scan += e + k * G < e1 ? 1 : 0;
+          if ((float)u2 >= u_min && (float)u2 <= u_max && (float)v2 >= v_min && (float)v2 <= v_max) {
+            const int32_t* t = B.rec + (size_t)ent.y * 12;
+            const uint4 ta = *(const uint4*)(t + 4), tb = *(const uint4*)(t + 8);
+            unsigned sad = __vsadu4(qa.x, ta.x) + __vsadu4(qa.y, ta.y) + __vsadu4(qa.z, ta.z) + __vsadu4(qa.w, ta.w) +
+                           __vsadu4(qb.x, tb.x) + __vsadu4(qb.y, tb.y) + __vsadu4(qb.z, tb.z) + __vsadu4(qb.w, tb.w);
+            const int ub2 = min((int)floorf((float)u2 / bs), g.ub - 1);
+            unsigned long long key = ((unsigned long long)sad << 48) | ((unsigned long long)ub2 << 36) |
+                                     ((unsigned long long)vbin << 24) | (unsigned long long)ent.y;
+            best = key < best ? key : best;
+            n_cand++;
+          }
         }
       }
     }
@@ -182,7 +190,10 @@ __device__ __forceinline__ int find_match_predicted(const Geometry& g, const Set
   return best_cost == ~0ull ? 0 : (int)(best_ord & 0xFFFFFFull);
 }
 
-__global__ void __launch_bounds__(MATCH_THREADS) k_match(Geometry g, const MatchJob* jobs, int method, int use_prior, uint64_t* stats) {
+// one instantiation per matching method: flow and stereo matching stay clear of the registers the double-precision
+// prediction of quad matching needs
+template <int method>
+__global__ void __launch_bounds__(MATCH_THREADS, method == 2 ? 3 : 4) k_match(Geometry g, const MatchJob* jobs, int use_prior, uint64_t* stats) {
   const MatchJob& J = jobs[blockIdx.y];
   const int sub = threadIdx.x % G;
   const int nq = job_nq(J, method);
@@ -664,7 +675,9 @@ static int match_impl(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, 
       int gmx = (maxq + MATCH_THREADS / G - 1) / (MATCH_THREADS / G);
       if (dyn && gmx > 160) gmx = 160;                    // sized by the capacity: the blocks stride over the real queries
       dim3 gm(gmx, nb);
-      k_match<<<gm, MATCH_THREADS, 0, ctx->stream>>>(g, dj, method, use_prior, ctx->d_stats);
+      if (method == 0) k_match<0><<<gm, MATCH_THREADS, 0, ctx->stream>>>(g, dj, use_prior, ctx->d_stats);
+      else if (method == 1) k_match<1><<<gm, MATCH_THREADS, 0, ctx->stream>>>(g, dj, use_prior, ctx->d_stats);
+      else k_match<2><<<gm, MATCH_THREADS, 0, ctx->stream>>>(g, dj, use_prior, ctx->d_stats);
       CU_LAUNCH_CHECK(ctx);
     }
     dim3 gc((maxq + CHUNK - 1) / CHUNK > 0 ? (maxq + CHUNK - 1) / CHUNK : 1, nb);
