@@ -268,10 +268,11 @@ def run_ours(args, rank, world, local_rank):
     workload = args.workload
     S = args.sequences if args.scaling == 'weak' else max(1, args.sequences // world)
     K, Wm = args.steps, max(args.warmup, GRAPH_WARMUP)
-    # host workers per GPU: one per core of the rank's share, but at least 8 and at most one per 2 sequences
-    # (at most 16: beyond that the batches of a worker get too small to fill the GPU - measured 41.6 k pairs/s with 32 workers
-    # x 2 sequences against 53 k with 16 x 4)
-    threads = args.threads or min(16, max(8, (os.cpu_count() or 1) // max(1, min(world, 8))))
+    # host workers per GPU: one per core of the rank's share, between 6 and 12.  Fewer workers = larger batches per launch
+    # and less contention in the driver (frames resident: 63 k pairs/s with 4 - 6 workers, 58 k with 16); the end-to-end leg
+    # issues one copy per image and likes more of them (44 k with 4 workers, 54 k with 12 - 16): profiles/r2_pipeline_summary.md
+    cores = os.cpu_count() or 1
+    threads = args.threads or min(12, max(6, cores // max(1, min(world, 8))))
     threads = max(1, min(threads, S))
     if threads * world > (os.cpu_count() or 1):
         # more workers than cores: waiting workers sleep between polls instead of yielding
@@ -354,7 +355,7 @@ def main():
     ap.add_argument('--bucket', type=int, default=2, help='bucket.max_features (mono / quad); the reference CLI uses 1000 (main.cpp:71)')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help='strong: --sequences is the total over all GPUs (configs[4])')
     ap.add_argument('--sequences', type=int, default=64, help='independent sequences per GPU (weak) or in total (strong)')
-    ap.add_argument('--threads', type=int, default=0, help='host worker threads per rank (default: cores / ranks, at least 8)')
+    ap.add_argument('--threads', type=int, default=0, help='host worker threads per rank (default: cores / ranks, between 6 and 12)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the single-Matcher / pageable / other-workload figures')
     ap.add_argument('--no-roofline', action='store_true')

@@ -78,8 +78,10 @@ int  visocu_device_free(visocu_ctx* ctx, void* p);
 int  visocu_memcpy_h2d(visocu_ctx* ctx, void* dst, const void* src, size_t bytes);
 
 /* ---- feature front end: Matcher::pushBack -> computeFeatures (matcher.cpp:95-181, 649-732) ----
- * imgs[k] is image k, `bpl_in` bytes per line, read only during the call.  If on_device != 0 the pointers are
- * device pointers (inputs already resident in HBM).  For every frame: copy into the 16-byte-stride layout
+ * imgs[k] is image k, `bpl_in` bytes per line.  on_device = 0: host memory, read only during the call (the reference's
+ * pushBack copies the image before it returns, matcher.cpp:158-175); 1: device pointers (inputs already resident in HBM);
+ * 2: host memory that stays valid and unchanged until the results of the step have been collected (copies from pinned
+ * memory then run asynchronously; with on_device = 0 the call waits for them).  For every frame: copy into the 16-byte-stride layout
  * (matcher.cpp:158-175), [half image (630-647)], fused sobel5x5 / blob5x5 / checkerboard5x5 + both
  * nonMaximumSuppression passes (filter.cpp:316-365, matcher.cpp:330-431, 684-694), computeDescriptors
  * (433-477) and the bin index of createIndexVector (870-890).  n_sparse / n_dense (may be NULL) receive the

@@ -461,17 +461,29 @@ extern "C" int visocu_launch_count(const visocu_ctx* ctx, uint64_t* n) {
 // Row-wise copy of a batch of images into the 16-byte-stride frame planes (matcher.cpp:163-175); pad columns stay zero.
 // One launch for all frames of a push: a source row starts at any byte, a destination word is assembled from four bytes.
 __global__ void __launch_bounds__(256) k_repitch(Geometry g, const FrameDev* frames, SlotList sl, const uint8_t* const* table, int bpl_in) {
+  // The source rows have any alignment (1241 bytes per line): every lane loads the aligned word that holds its first byte,
+  // the neighbour's word arrives by shuffle, and a funnel shift lines the four pixels up - one request per warp and 128 bytes
   const uint8_t* __restrict__ src = table[blockIdx.y];
   uint8_t* dst = frames[sl.s[blockIdx.y]].img;
-  const int wpr = g.bpl >> 2;
-  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < wpr * g.h; idx += gridDim.x * 256) {
-    const int y = idx / wpr, x = 4 * (idx - y * wpr);
-    const uint8_t* r = src + (size_t)y * bpl_in + x;
-    uint32_t v = 0;
-    if (x + 3 < g.w) v = (uint32_t)r[0] | ((uint32_t)r[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)r[3] << 24);
-    else
-      for (int k = 0; k < 4; k++) if (x + k < g.w) v |= (uint32_t)r[k] << (8 * k);
-    *(uint32_t*)(dst + (size_t)y * g.bpl + x) = v;
+  const int wpr = g.bpl >> 2, total = wpr * g.h, lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * 256 + (threadIdx.x & ~31); base < total; base += gridDim.x * 256) {
+    const int idx = base + lane;
+    const bool in = idx < total;
+    const int y = in ? idx / wpr : 0, x = in ? 4 * (idx - y * wpr) : 0;
+    const int nb = in ? min(4, g.w - x) : 0;                        // pixels of this word inside the image (<= 0: padding)
+    const uintptr_t p = (uintptr_t)(src + (size_t)y * bpl_in + x);
+    const uint32_t* wp = (const uint32_t*)(p & ~(uintptr_t)3);
+    const int a = (int)(p & 3);
+    const uint32_t w0 = nb > 0 ? wp[0] : 0u;
+    uint32_t w1 = __shfl_down_sync(0xFFFFFFFFu, w0, 1);
+    const uintptr_t next = __shfl_down_sync(0xFFFFFFFFu, (unsigned long long)(nb > 0 ? (uintptr_t)wp : 0), 1);      // 0: that lane loaded nothing
+    const bool need1 = nb > 0 && a + nb > 4;                        // some wanted byte lies in the following word
+    if (need1 && (lane == 31 || next != (uintptr_t)(wp + 1))) w1 = wp[1];     // row ends, padding neighbours, the warp's last lane
+    if (in) {
+      uint32_t v = a ? __funnelshift_r(w0, w1, 8 * a) : w0;
+      v = nb >= 4 ? v : (nb > 0 ? v & (0xFFFFFFFFu >> (8 * (4 - nb))) : 0u);
+      *(uint32_t*)(dst + (size_t)y * g.bpl + x) = v;
+    }
   }
 }
 
@@ -567,8 +579,9 @@ static int push_batch(visocu_ctx* ctx, const SlotList& sl, const uint8_t* const*
   const Geometry& g = ctx->g;
   int rc;
   const size_t stage_stride = align_up((size_t)bpl_in * g.h, 256);
-  const bool direct = !on_device && bpl_in == g.bpl;      // already in the frame layout: straight into the frame planes
-  if (!on_device && !direct) {
+  const bool direct = on_device != 1 && bpl_in == g.bpl;  // already in the frame layout: straight into the frame planes
+  bool async_pinned = false;                              // on_device = 0: the caller may reuse its buffers when the call returns
+  if (on_device != 1 && !direct) {
     const size_t want = stage_stride * (size_t)sl.n;
     if (want > ctx->img_stage_bytes) {
       CU_TRY(ctx, visocu_stream_wait(ctx));
@@ -588,14 +601,26 @@ static int push_batch(visocu_ctx* ctx, const SlotList& sl, const uint8_t* const*
   for (int i = 0; i < sl.n; i++) {
     if (!imgs[i]) return visocu_set_error(ctx, VISOCU_EINVAL, "null image %d", i);
     const int f = sl.s[i];
-    if (on_device) {
+    if (on_device == 1) {
       ctx->src_table_pin[i] = imgs[i];
-    } else if (direct) {
-      CU_COPY(ctx, ctx->frames_h[f].img, imgs[i], (size_t)bpl_in * g.h, cudaMemcpyHostToDevice);
     } else {
-      uint8_t* stage = ctx->img_stage + (size_t)i * stage_stride;
-      CU_COPY(ctx, stage, imgs[i], (size_t)bpl_in * (g.h - 1) + g.w, cudaMemcpyHostToDevice);
-      ctx->src_table_pin[i] = stage;
+      // pinned host memory is copied asynchronously (pageable memory is staged by the driver before the copy call returns)
+      // (on_device = 2: the caller keeps the images valid until the step is collected, nothing to wait for.  Letting the
+      // layout kernel read pinned images in place over PCIe instead of copying them was tried: e2e 54 k -> 38 k pairs/s)
+      bool pinned = false;
+      if (on_device == 0) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, imgs[i]) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+      }
+      if (direct) {
+        CU_COPY(ctx, ctx->frames_h[f].img, imgs[i], (size_t)bpl_in * g.h, cudaMemcpyHostToDevice);
+      } else {
+        uint8_t* stage = ctx->img_stage + (size_t)i * stage_stride;
+        CU_COPY(ctx, stage, imgs[i], (size_t)bpl_in * (g.h - 1) + g.w, cudaMemcpyHostToDevice);
+        ctx->src_table_pin[i] = stage;
+      }
+      if (pinned) async_pinned = true;
     }
     ctx->frame_valid[f] = 1;
   }
@@ -616,6 +641,7 @@ static int push_batch(visocu_ctx* ctx, const SlotList& sl, const uint8_t* const*
   ctx->in_step--;
   if (rc) return rc;
   CU_TRY(ctx, cudaEventRecord(ctx->ev_push, ctx->stream));
+  if (async_pinned) CU_TRY(ctx, visocu_stream_wait(ctx));            // "read only during the call" also for pinned sources
   return VISOCU_OK;
 }
 

@@ -637,6 +637,7 @@ bool MatcherBatch::stepAvailable(int32_t method) const {
 }
 
 bool MatcherBatch::stepSubmit(const uint8_t* const* I1, uint32_t* dims, bool on_device) {
+  // host images of a step stay valid until the step is collected (the runner's contract): mode 2 of visocu_push_frames
   visob::StageTimer timer(0);
   if ((int32_t)dims[0] <= 0 || (int32_t)dims[1] <= 0 || dims[2] < dims[0]) {
     std::cerr << "ERROR: Image dimension mismatch!" << std::endl;
@@ -656,7 +657,7 @@ bool MatcherBatch::stepSubmit(const uint8_t* const* I1, uint32_t* dims, bool on_
     quads[s] = visocu_quad{4 * (int32_t)s + (int)((k + 3) & 3), -1, frames[s], -1};
     if (!I1[s]) { std::cerr << "ERROR: Image dimension mismatch!" << std::endl; return false; }
   }
-  bool ok = visocu_push_frames(ctx, (int32_t)S, frames.data(), I1, (int32_t)dims[2], on_device ? 1 : 0, 0, 0) == VISOCU_OK;
+  bool ok = visocu_push_frames(ctx, (int32_t)S, frames.data(), I1, (int32_t)dims[2], on_device ? 1 : 2, 0, 0) == VISOCU_OK;
   if (ok && k > 0)
     ok = visocu_match_fused_submit(ctx, (int32_t)S, quads.data(), seq[0]->refineMode(), 0, (int)((k + 3) & 3)) == VISOCU_OK;
   if (!ok) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;

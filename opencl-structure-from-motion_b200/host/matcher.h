@@ -144,7 +144,9 @@ public:
   // and enqueues its flow matching against the previous frame - one submission, nothing is waited for -, stepCollect waits
   // for the OLDEST submitted step and puts its matches into the sequences (getMatches, bucketFeatures ... then refer to that
   // step).  Up to three steps may be in flight: consecutive steps use different lanes of the context and a ring of four
-  // frames per sequence, and a step that repeats is replayed as a CUDA graph.  Do not mix with pushBack / matchFeatures.
+  // frames per sequence, and a step that repeats is replayed as a CUDA graph.  Host images of a step must stay valid and
+  // unchanged until that step has been collected (pinned ones are copied asynchronously).  Do not mix with pushBack /
+  // matchFeatures.
   bool stepAvailable(int32_t method) const;
   bool stepSubmit(const uint8_t* const* I1, uint32_t* dims, bool on_device);
   bool stepCollect();

@@ -342,6 +342,27 @@ def test_pipelined_runner_equals_stepwise(ref):
         for s in range(S):
             assert got[s].tobytes() == want[s].tobytes(), (depth, s)
     H.set_pipeline_depth(3)
+    # the same frames in pinned host memory: the runner copies them asynchronously (visocu_push_frames, on_device = 2)
+    import torch
+    pinned = torch.empty((T, S, 260, 500), dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = np.stack([np.stack(row) for row in imgs])
+    pptrs = [[pinned[k, s].data_ptr() for s in range(S)] for k in range(T)]
+    b = H.Runner(0, S, 2, 0, 0, mp)
+    secs, nm, ok = b.run(pptrs, dims)
+    got = [b.matches(s) for s in range(S)]
+    b.close()
+    assert np.array_equal(nm, counts_step)
+    for s in range(S):
+        assert got[s].tobytes() == want[s].tobytes(), ('pinned', s)
+    # the drop-in pushBack consumes a pinned image before it returns: the caller may overwrite its buffer at once
+    hm = H.Matcher(V.Params())
+    buf = torch.empty((260, 500), dtype=torch.uint8).pin_memory()
+    for k in (T - 2, T - 1):
+        buf.numpy()[:] = seqs[0][k]
+        hm.push(buf.numpy())                                 # a view of the pinned buffer: same address
+        buf.numpy()[:] = 0
+    hm.match_features(0)
+    assert hm.matches(2).tobytes() == want[0].tobytes()
     # odometry mode
     S, T = 3, 7
     seqs = [synth.corridor_sequence(T, seed=1234 + s) for s in range(S)]
