@@ -130,9 +130,11 @@ int  visocu_match(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int3
  * until the next matching call on this context.  done1 / done2 say whether the outlier removal of the list ran on the
  * device (if done1[j] is 0 the second list of job j is meaningless: the caller votes on list 1 itself and repeats the second
  * pass with visocu_match); ranges_out[j] (optional, u_bins * v_bins entries) receives the prior ranges; counts (optional,
- * 4 per job) the sparse and dense record counts of f1p and of f1c.  *list2_compact = 1: the records of list2 are the 24
- * bytes of a flow match that say something - (u1p, v1p, i1p, u1c, v1c, i1c), six words per match; the other six fields of
- * p_match are -1 (matcher.cpp:1037) and do not cross PCIe - else complete 48-byte records.  At most 128 jobs. */
+ * 4 per job) the sparse and dense record counts of f1p and of f1c.  *list2_compact says how the records of list2 crossed
+ * PCIe: 0 = complete 48-byte records; 1 = the 24 bytes of a flow match that say something, (u1p, v1p, i1p, u1c, v1c, i1c),
+ * six words per match - the other six fields of p_match are -1 (matcher.cpp:1037); 2 = the same in 12 bytes, three words
+ * (u1p | v1p << 16), (u1c | v1c << 16), (i1p | i1c << 16): without sub-pixel refinement (refine != 2) the coordinates are
+ * whole pixels, and they and the indices fit 16 bits (the kernel checks every value).  At most 128 jobs. */
 int  visocu_match_fused(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* jobs, int32_t refine,
                         const visocu_pmatch** list1, int32_t* n1, int32_t* done1,
                         const visocu_pmatch** list2, int32_t* n2, int32_t* done2,

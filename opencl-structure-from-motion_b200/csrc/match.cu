@@ -860,6 +860,7 @@ struct DeliverArgs {
   size_t ostride1, ostride2;
   uint8_t* dst; size_t dstride, off1, off2;
   int with_lists;
+  int packed16;                               // second list as 12 bytes per match (see below)
 };
 __global__ void __launch_bounds__(256) k_deliver(DeliverArgs a) {
   const int j = blockIdx.x, tid = threadIdx.x;
@@ -880,7 +881,32 @@ __global__ void __launch_bounds__(256) k_deliver(DeliverArgs a) {
   // Flow matches carry -1 in the six fields of the right images (matcher.cpp:1037): only the 24 bytes that say something
   // cross PCIe - (u1p, v1p, i1p) and (u1c, v1c, i1c) as six words per record - and the host puts the constants back.
   const uint32_t* s2 = (const uint32_t*)(a.lists2 + a.ostride2 * j); uint32_t* d2 = (uint32_t*)(out + a.off2);
-  for (int i = tid; i < 6 * n2; i += 256) { const int r = i / 6, w = i - 6 * r; d2[i] = s2[12 * r + (w < 3 ? w : w + 3)]; }
+  if (!a.packed16) {
+    if (tid == 38) hdr[38] = 1;                 // format of list 2: 1 = six words per match
+    for (int i = tid; i < 6 * n2; i += 256) { const int r = i / 6, w = i - 6 * r; d2[i] = s2[12 * r + (w < 3 ? w : w + 3)]; }
+    return;
+  }
+  // Without sub-pixel refinement the coordinates of a match are whole pixels (matcher.cpp:1013-1036 copies the integer
+  // feature positions, relocateMinimum moves them by whole pixels), and they and the feature indices fit 16 bits: three
+  // words per match, (u1p | v1p << 16), (u1c | v1c << 16), (i1p | i1c << 16).  A value that would not survive is reported
+  // (format 0x102: the host refuses the list instead of delivering something else than the reference).
+  int bad = 0;
+  for (int i = tid; i < 3 * n2; i += 256) {
+    const int r = i / 3, w = i - 3 * r;
+    uint32_t lo, hi;
+    if (w < 2) {
+      const float fu = __uint_as_float(s2[12 * r + 6 * w]), fv = __uint_as_float(s2[12 * r + 6 * w + 1]);
+      const int u = (int)fu, v = (int)fv;
+      if ((float)u != fu || (float)v != fv || (unsigned)u > 0xFFFFu || (unsigned)v > 0xFFFFu) bad = 1;
+      lo = (uint32_t)u; hi = (uint32_t)v;
+    } else {
+      lo = s2[12 * r + 2]; hi = s2[12 * r + 8];
+      if (lo > 0xFFFFu || hi > 0xFFFFu) bad = 1;
+    }
+    d2[i] = (lo & 0xFFFFu) | (hi << 16);
+  }
+  bad = __syncthreads_or(bad);
+  if (tid == 38) hdr[38] = bad ? 0x102 : 2;     // format of list 2: 2 = three words per match
 }
 
 namespace {
@@ -926,6 +952,7 @@ static int fused_enqueue(visocu_ctx* ctx, int32_t n_jobs, const visocu_quad* job
   da.lists1 = A.dev_lists; da.lists2 = B.dev_lists; da.ostride1 = A.ostride; da.ostride2 = B.ostride;
   da.dst = (uint8_t*)ctx->deliver_dev; da.dstride = L.dstride; da.off1 = L.off1; da.off2 = L.off2;
   da.with_lists = L.zero_copy ? (want_list1 ? 3 : 1) : 0;
+  da.packed16 = (refine != 2 && g.cap[0] <= 0xFFFF && g.cap[1] <= 0xFFFF) ? 1 : 0;
   k_deliver<<<n_jobs, 256, 0, ctx->stream>>>(da);
   CU_LAUNCH_CHECK(ctx);
   if (want_ranges) CU_TRY(ctx, cudaMemcpyAsync(ctx->pin_ranges, d_rng, L.rstride * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1000,7 +1027,7 @@ extern "C" int visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch**
   const Geometry& g = ctx->g;
   const int nbin = g.ub * g.vb, n_jobs = ctx->fused_n;
   const FusedLayout L = fused_layout(g);
-  *list2_compact = L.zero_copy ? 1 : 0;
+  *list2_compact = L.zero_copy ? ((const int32_t*)ctx->deliver)[38] : 0;        // written by k_deliver: 1 = 24, 2 = 12 bytes per match
   const visocu_quad* jobs = ctx->fused_jobs.data();
   const visocu_deferred& A = ctx->part[0];
   const visocu_deferred& B = ctx->part[1];
@@ -1008,13 +1035,15 @@ extern "C" int visocu_match_fused_collect(visocu_ctx* ctx, const visocu_pmatch**
   for (int j = 0; j < n_jobs; j++) {
     const uint8_t* base = (const uint8_t*)ctx->deliver + L.dstride * j;
     const int32_t* hdr = (const int32_t*)base;
+    if (L.zero_copy && hdr[38] != *list2_compact)
+      return visocu_set_error(ctx, VISOCU_ECAPACITY, "job %d: a match does not fit the packed delivery format", j);
     for (int p = 0; p < 2; p++) {
       const int32_t* w = hdr + 16 * p;
       const int n = w[0], status = w[1];
       (p ? n2 : n1)[j] = n; (p ? done2 : done1)[j] = status == 0 ? 1 : 0;
       if (status == 0 && n > 3) { for (int k = 0; k < 4; k++) ctx->ro_ns[k] += (uint64_t)w[4 + k]; ctx->ro_jobs++; }
       else if (status != 0) { ctx->ro_declined++; ctx->ro_reason[status & 3]++; ctx->ro_declined_n += (uint64_t)w[3]; }
-      ctx->d2h_bytes += 64 + (L.zero_copy ? (p ? (uint64_t)n * 24 : (ctx->fused_list1 ? (uint64_t)n * 48 : 0)) : (uint64_t)n * 48);
+      ctx->d2h_bytes += 64 + (L.zero_copy ? (p ? (uint64_t)n * (*list2_compact == 2 ? 12 : 24) : (ctx->fused_list1 ? (uint64_t)n * 48 : 0)) : (uint64_t)n * 48);
     }
     if (L.zero_copy) { list1[j] = ctx->fused_list1 ? (const visocu_pmatch*)(base + L.off1) : nullptr; list2[j] = (const visocu_pmatch*)(base + L.off2); }
     const int fr[2] = {jobs[j].f1p, jobs[j].f1c};

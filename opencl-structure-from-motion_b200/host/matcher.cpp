@@ -276,12 +276,12 @@ void Matcher::fusedMatch(visocu_ctx* ctx, const vector<Matcher*>& group, int32_t
   const int rc = visocu_match_fused(ctx, (int32_t)n, quads.data(), group[0]->refineMode(), l1.data(), n1.data(), d1.data(),
                                     l2.data(), n2.data(), d2.data(), rp.data(), counts.data(), &compact);
   if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
-  for (size_t k = 0; k < n; k++) takeFused(group[k], rc == VISOCU_OK, &counts[4 * k], l1[k], n1[k], d1[k], l2[k], n2[k], d2[k], method, compact != 0);
+  for (size_t k = 0; k < n; k++) takeFused(group[k], rc == VISOCU_OK, &counts[4 * k], l1[k], n1[k], d1[k], l2[k], n2[k], d2[k], method, compact);
 }
 
 // results of a fused call for one matcher
 void Matcher::takeFused(Matcher* m, bool ok, const int32_t* counts, const visocu_pmatch* l1, int32_t n1, int32_t d1,
-                        const visocu_pmatch* l2, int32_t n2, int32_t d2, int32_t method, bool compact) {
+                        const visocu_pmatch* l2, int32_t n2, int32_t d2, int32_t method, int compact) {
   if (!ok) { m->p_matched_1.clear(); m->p_matched_2.clear(); m->ro_done[0] = m->ro_done[1] = false; return; }
   // the record counts arrive with the results (the frames were pushed without reading them back)
   m->n_feat[0] = counts[0]; m->n_feat[4] = counts[1];
@@ -292,8 +292,20 @@ void Matcher::takeFused(Matcher* m, bool ok, const int32_t* counts, const visocu
   const p_match* a1 = reinterpret_cast<const p_match*>(l1);
   const p_match* a2 = reinterpret_cast<const p_match*>(l2);
   if (a1) m->p_matched_1.assign(a1, a1 + n1); else m->p_matched_1.clear();     // not delivered (sequence runner): nobody reads it
-  if (!compact) {
+  if (compact == 0) {
     m->p_matched_2.assign(a2, a2 + n2);
+  } else if (compact == 2) {
+    // three words per match: whole-pixel coordinates and feature indices in 16 bits each
+    const uint32_t* h = reinterpret_cast<const uint32_t*>(l2);
+    m->p_matched_2.resize((size_t)n2);
+    for (int32_t i = 0; i < n2; i++) {
+      p_match& o = m->p_matched_2[i];
+      const uint32_t a = h[3 * i], b = h[3 * i + 1], c = h[3 * i + 2];
+      o.u1p = (float)(a & 0xFFFFu); o.v1p = (float)(a >> 16); o.i1p = (int32_t)(c & 0xFFFFu);
+      o.u2p = -1; o.v2p = -1; o.i2p = -1;
+      o.u1c = (float)(b & 0xFFFFu); o.v1c = (float)(b >> 16); o.i1c = (int32_t)(c >> 16);
+      o.u2c = -1; o.v2c = -1; o.i2c = -1;
+    }
   } else {
     // six words per flow match crossed PCIe: (u1p, v1p, i1p, u1c, v1c, i1c); the fields of the right images are -1
     struct Half { float u, v; int32_t i; };
@@ -696,6 +708,6 @@ bool MatcherBatch::stepCollect() {
   const int rc = visocu_match_fused_collect(ctx, l1.data(), n1.data(), d1.data(), l2.data(), n2.data(), d2.data(), 0, counts.data(), &compact);
   if (rc != VISOCU_OK) std::cerr << "ERROR: " << visocu_last_error(ctx) << std::endl;
   visocu_set_lane(ctx, 4);                                            // fall-backs and odometry calls run on their own lane
-  for (size_t s = 0; s < S; s++) Matcher::takeFused(seq[s], rc == VISOCU_OK, &counts[4 * s], l1[s], n1[s], d1[s], l2[s], n2[s], d2[s], 0, compact != 0);
+  for (size_t s = 0; s < S; s++) Matcher::takeFused(seq[s], rc == VISOCU_OK, &counts[4 * s], l1[s], n1[s], d1[s], l2[s], n2[s], d2[s], 0, compact);
   return rc == VISOCU_OK;
 }

@@ -105,7 +105,7 @@ private:
   static bool fusedAvailable(const Matcher& m, int32_t method);
   static void fusedMatch(visocu_ctx* ctx, const std::vector<Matcher*>& group, int32_t method);
   static void takeFused(Matcher* m, bool ok, const int32_t* counts, const visocu_pmatch* l1, int32_t n1, int32_t d1,
-                        const visocu_pmatch* l2, int32_t n2, int32_t d2, int32_t method, bool compact);
+                        const visocu_pmatch* l2, int32_t n2, int32_t d2, int32_t method, int compact);
 
   parameters param;
   int32_t margin;

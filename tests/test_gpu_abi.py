@@ -114,24 +114,48 @@ def test_fused_submit_collect_and_lanes(ctx, ref):
     ctx.push_frames([2], [seq[2]], want_counts=False)
     q2 = np.zeros(1, V.QUAD); q2[0] = (1, -1, 2, -1)
     assert lib.visocu_match_fused_submit(ctx.h, 1, vp(q2), 1, 0, 0) == 0
+    def unpack(fmt, addr, n):
+        """list 2 of a fused call as p_match records: 1 = six words per match, 2 = three words (16-bit fields)"""
+        m = np.zeros(n, V.P_MATCH)
+        for f in ('u2p', 'v2p', 'i2p', 'u2c', 'v2c', 'i2c'):
+            m[f] = -1
+        if fmt == 1:
+            half = np.dtype([('u', 'f4'), ('v', 'f4'), ('i', 'i4')])
+            raw = np.ctypeslib.as_array((C.c_uint8 * (24 * n)).from_address(addr)).view(half).reshape(-1, 2)
+            m['u1p'], m['v1p'], m['i1p'] = raw[:, 0]['u'], raw[:, 0]['v'], raw[:, 0]['i']
+            m['u1c'], m['v1c'], m['i1c'] = raw[:, 1]['u'], raw[:, 1]['v'], raw[:, 1]['i']
+        else:
+            raw = np.ctypeslib.as_array((C.c_uint32 * (3 * n)).from_address(addr)).reshape(-1, 3)
+            m['u1p'], m['v1p'] = raw[:, 0] & 0xFFFF, raw[:, 0] >> 16
+            m['u1c'], m['v1c'] = raw[:, 1] & 0xFFFF, raw[:, 1] >> 16
+            m['i1p'], m['i1c'] = raw[:, 2] & 0xFFFF, raw[:, 2] >> 16
+        return m
+
     got = []
     for lane in (0, 1):
         assert lib.visocu_set_lane(ctx.h, lane) == 0
         assert lib.visocu_match_fused_collect(ctx.h, l1, vp(n1), vp(d1), l2, vp(n2), vp(d2), None, vp(cnt), C.byref(compact)) == 0
         assert d1[0] == 1 and d2[0] == 1 and cnt.min() > 100
-        assert compact.value == 1 and not l1[0]                       # flags 0: the first list stays on the device
-        # compact flow records: (u1p, v1p, i1p, u1c, v1c, i1c), the other fields of p_match are -1
-        half = np.dtype([('u', 'f4'), ('v', 'f4'), ('i', 'i4')])
-        raw = np.ctypeslib.as_array((C.c_uint8 * (24 * int(n2[0]))).from_address(l2[0])).view(half).reshape(-1, 2)
-        m = np.zeros(int(n2[0]), V.P_MATCH)
-        for f in ('u2p', 'v2p', 'i2p', 'u2c', 'v2c', 'i2c'):
-            m[f] = -1
-        m['u1p'], m['v1p'], m['i1p'] = raw[:, 0]['u'], raw[:, 0]['v'], raw[:, 0]['i']
-        m['u1c'], m['v1c'], m['i1c'] = raw[:, 1]['u'], raw[:, 1]['v'], raw[:, 1]['i']
-        got.append(m)
+        assert compact.value == 2 and not l1[0]                       # pixel refinement: 12 bytes per match; flags 0: list 1 stays on the device
+        got.append(unpack(2, l2[0], int(n2[0])))
     assert lib.visocu_set_lane(ctx.h, 0) == 0
     rm = ref.matcher(pyref.MatcherParams())
     rm.push(seq[0]); rm.push(seq[1]); rm.match_features(0)
     assert len(got[0]) > 300 and got[0].tobytes() == rm.matches(2).tobytes()
     rm.push(seq[2]); rm.match_features(0)
     assert got[1].tobytes() == rm.matches(2).tobytes()
+    # sub-pixel refinement is not part of the fused call
+    assert lib.visocu_match_fused_submit(ctx.h, 1, vp(q2), 2, 0, -1) != 0 and b'refine must be' in lib.visocu_last_error(ctx.h)
+    # more than 65535 records per list: indices no longer fit 16 bits, six words per match
+    w2, h2 = 1000, 600
+    p2 = V.Params(nms_n=4, half_resolution=0)
+    ctx.configure(p2, w2, h2, 2)
+    a2, b2 = synth.blob_pair(w2, h2, n_blobs=2500, seed=78)           # few blobs: the lists stay within the outlier kernel
+    ctx.push_frames([0, 1], [a2, b2], want_counts=False)
+    assert lib.visocu_match_fused_submit(ctx.h, 1, vp(q), 1, 0, -1) == 0
+    assert lib.visocu_match_fused_collect(ctx.h, l1, vp(n1), vp(d1), l2, vp(n2), vp(d2), None, vp(cnt), C.byref(compact)) == 0
+    assert compact.value == 1 and d2[0] == 1
+    wide = unpack(1, l2[0], int(n2[0]))
+    rm2 = ref.matcher(pyref.MatcherParams(nms_n=4, half_resolution=0))
+    rm2.push(a2); rm2.push(b2); rm2.match_features(0)
+    assert len(wide) > 300 and wide.tobytes() == rm2.matches(2).tobytes()
