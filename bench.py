@@ -272,7 +272,11 @@ def run_ours(args, rank, world, local_rank):
     # and less contention in the driver (frames resident: 63 k pairs/s with 4 - 6 workers, 58 k with 16); the end-to-end leg
     # issues one copy per image and likes more of them (44 k with 4 workers, 54 k with 12 - 16): profiles/r2_pipeline_summary.md
     cores = os.cpu_count() or 1
-    threads = args.threads or min(12, max(6, cores // max(1, min(world, 8))))
+    if workload == 'flow':
+        threads = args.threads or min(12, max(6, cores // max(1, min(world, 8))))
+    else:
+        # quad, odometry, 4K: the host stages (bucketing, estimateMotion, large-list votes) want every core
+        threads = args.threads or min(16, max(8, cores // max(1, min(world, 8))))
     threads = max(1, min(threads, S))
     if threads * world > (os.cpu_count() or 1):
         # more workers than cores: waiting workers sleep between polls instead of yielding
