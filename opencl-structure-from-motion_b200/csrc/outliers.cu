@@ -765,8 +765,6 @@ extern "C" int visocu_remove_outliers(visocu_ctx* ctx, int32_t n_jobs, int32_t m
   return VISOCU_OK;
 }
 
-int ro_edge_capacity_host(int n) { return ro_edge_capacity(n); }
-
 extern "C" int32_t visocu_delaunay_edge_capacity(int32_t n_vertices) { return n_vertices > 0 ? ro_edge_capacity(n_vertices) : 0; }
 
 // Nodes of a larger divide-and-conquer Delaunay triangulation built on the device, one CTA each (see include/visocu.h)

@@ -24,8 +24,7 @@ struct RoJob {
   int4* mesh_out;
   int32_t axis0, he_base, v_base;
 };
-// edges a triangulation of n vertices may allocate on the device (also the stride of the arrays behind RoJob::mesh_out)
-int ro_edge_capacity_host(int n);
+
 
 // Positions of all records of a list as x << 16 | y (0xFFFFFFFF for records dropped by the sub-pixel refinement), for the
 // host-side duplicate resolution below.  keys_dev: n_jobs rows of `stride` words.
