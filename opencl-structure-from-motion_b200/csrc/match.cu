@@ -87,6 +87,13 @@ __device__ __forceinline__ int find_match(const Geometry& g, const SetDev& A, in
     const float bs = (float)g.binsize;
     const int ubmin = min(max((int)floorf(u_min / bs), 0), g.ub - 1), ubmax = min(max((int)floorf(u_max / bs), 0), g.ub - 1);
     const int vbmin = min(max((int)floorf(v_min / bs), 0), g.vb - 1), vbmax = min(max((int)floorf(v_max / bs), 0), g.vb - 1);
+    // The window test of matcher.cpp:943 compares integer positions with float bounds: for an integer p, (float)p >= b is
+    // p >= ceil(b) and (float)p <= b is p <= floor(b), so the bounds are converted once instead of every scanned position
+    // (positions lie in [0, 16382], visocu_configure: bounds outside [-1, 65534] change nothing, and the 0xFFFF of a padding
+    // entry never passes; a NaN bound admits nothing, as it does there)
+    int iu_min = (int)fmaxf(ceilf(u_min), -1.f), iu_max = (int)fminf(floorf(u_max), 65534.f);
+    int iv_min = (int)fmaxf(ceilf(v_min), -1.f), iv_max = (int)fminf(floorf(v_max), 65534.f);
+    if (u_min != u_min || u_max != u_max || v_min != v_min || v_max != v_max) { iu_min = 1; iu_max = 0; }
     for (int vbin = vbmin; vbin <= vbmax; vbin++) {
       const int row = (c * g.vb + vbin) * g.ub;
       const int e0 = B.bin_start[row + ubmin], e1 = ubmax >= ubmin ? B.bin_start[row + ubmax + 1] : e0;
@@ -101,7 +108,7 @@ __device__ __forceinline__ int find_match(const Geometry& g, const SetDev& A, in
           const int2 ent = ent4[k];
           const int u2 = ent.x & 0xFFFF, v2 = (int)((unsigned)ent.x >> 16);
           n_scan += e + k * G < e1 ? 1 : 0;
-          if ((float)u2 >= u_min && (float)u2 <= u_max && (float)v2 >= v_min && (float)v2 <= v_max) {
+          if (u2 >= iu_min && u2 <= iu_max && v2 >= iv_min && v2 <= iv_max) {
             const int32_t* t = B.rec + (size_t)ent.y * 12;
             const uint4 ta = *(const uint4*)(t + 4), tb = *(const uint4*)(t + 8);
             unsigned sad = __vsadu4(qa.x, ta.x) + __vsadu4(qa.y, ta.y) + __vsadu4(qa.z, ta.z) + __vsadu4(qa.w, ta.w) +
